@@ -1,0 +1,98 @@
+/* basd_b200.h — C ABI of the B200-native BASD distillation-loss hot path.
+ *
+ * The reference (indrajeetadityaroy9/vit-bias-aware-structural-distillation) has no FFI: its boundary is the Python
+ * call BASDLoss.forward (src/losses/combined.py:48-85) plus the free function marchenko_pastur_rank
+ * (src/losses/layer_selector.py:8-20, second consumer src/models/teacher.py:177).  This header is what a binding for
+ * that path binds to; the drop-in Python module (vit_bias_aware_structural_distillation_b200/loss.py) is such a binding
+ * (ctypes).  INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is DEVICE memory owned by the caller (the library never allocates or frees);
+ *   - every call is asynchronous on `stream` and never synchronises with the host;
+ *   - return value 0 = success, non-zero = error; basd_last_error() gives a thread-local message;
+ *   - one workspace (basd_workspace_bytes) carries all intermediates from the forward phases to the backward
+ *     phases of the same step; it must stay untouched in between;
+ *   - the four phases are separate entry points so the host language can place the two collectives
+ *     (sum all-reduce of basd_view "stats" after phase 1, of "gw" after phase 3) with its own NCCL binding.
+ */
+#ifndef BASD_B200_H
+#define BASD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BASD_DTYPE_F32 0
+#define BASD_DTYPE_BF16 1
+#define BASD_MAX_POINTS 8
+#define BASD_MAX_LAYERS 64
+
+typedef struct basd_shape {
+    int B;          /* local (per-rank) batch                                         */
+    int Ns, Nt;     /* student / teacher tokens without CLS   (trainer.py:29, teacher.py:156-157) */
+    int Ds, Dt;     /* student / teacher width                                        */
+    int Lt;         /* teacher layers handed over (sorted keys, layer_selector.py:123) */
+    int P;          /* student extraction points (combined.py:34-40)                  */
+    int H;          /* attention heads (1 for CNN teachers, teacher.py:188-191)       */
+    int has_cls;    /* teacher_has_cls_token (combined.py:27)                         */
+    int act_dtype;  /* BASD_DTYPE_* of student and teacher tokens                     */
+    int attn_dtype; /* BASD_DTYPE_* of attention maps                                 */
+    int world_size; /* ranks whose pooled statistics are summed (equal local batches) */
+} basd_shape;
+
+typedef struct basd_inputs {
+    const void* student[BASD_MAX_POINTS];   /* P  tensors [B,Ns,Ds]; element strides below            */
+    const void* teacher[BASD_MAX_LAYERS];   /* Lt tensors [B,Nt,Dt]                                   */
+    const void* attn[BASD_MAX_LAYERS];      /* Lt tensors [B,H,Nt+1,Nt+1] (has_cls) or [B,H,Nt,Nt]    */
+    int64_t student_strides[3];             /* (batch, token, feature) in elements, same for all P    */
+    int64_t teacher_strides[3];
+    int64_t attn_strides[4];                /* (batch, head, query, key)                              */
+    const float* proj_s;                    /* [Ds,Ds] row-major  (layer_selector.py:51,55)           */
+    const float* proj_t;                    /* [Ds,Dt] row-major  (layer_selector.py:52,56)           */
+    const float* log_temperatures;          /* [P]                (layer_selector.py:58-63)           */
+} basd_inputs;
+
+/* Bytes of workspace needed for one forward+backward step of `shape`. */
+int basd_workspace_bytes(const basd_shape* shape, size_t* bytes);
+
+/* Phase 1 (replaces layer_selector.py:69-74,86-91,131-136 and relational.py:22-27 up to the pooled statistics):
+ * attention importance rows, teacher projection (tcgen05), per-layer token Gram + column sums (tcgen05). */
+int basd_forward_stats(const basd_shape* shape, const basd_inputs* in, void* workspace, void* stream);
+
+/* Phase 2 (layer_selector.py:16-19,36-37,92-112; combined.py:63-76; relational.py:29-50): MP ranks, eigenbases,
+ * principal angles, mixing weights, mixed teacher, per-sample Procrustes.  geo_loss: device float (mean over the local batch). */
+int basd_forward_solve(const basd_shape* shape, const basd_inputs* in, void* workspace, float* geo_loss, void* stream);
+
+/* Phase 3 (closed-form backward): d loss / d mixing weights, unscaled, into view "gw". */
+int basd_backward_dots(const basd_shape* shape, const basd_inputs* in, void* workspace, void* stream);
+
+/* Phase 4: gradients w.r.t. the P student tensors (dense [B,Ns,Ds], dtype grad_dtype) and
+ * log_temperatures [P] (fp32).  grad_geo: device float, upstream d(total)/d(geo_loss). */
+int basd_backward_finish(const basd_shape* shape, const basd_inputs* in, void* workspace, const float* grad_geo,
+                         void* const* grad_student, int grad_dtype, float* grad_log_temperatures, void* stream);
+
+/* Named views into the workspace (for the collectives and for tests).  Names: "stats" [(Lt+P)*(Ds*Ds+Ds)] f32,
+ * "gw" [P*Lt] f32, "ranks" [Lt] i32, "w" [P*Lt], "d2" [P*Lt], "geo_i" [P], "loss_b" [P*B], "rows" [Lt*B*Nt],
+ * "a" [P*B*Ns], "evals" [(Lt+P)*Ds], "cos" [P*Lt*Ds], "dbg" [P*B*5] (nuc, tr_s, tr_t, sweeps, chol flag), "gdir", "ktt". */
+int basd_view(const basd_shape* shape, void* workspace, const char* name, void** ptr, size_t* count);
+
+/* marchenko_pastur_rank(features[M,D]) (layer_selector.py:8-20), rank written to device int; D <= 224, M >= D.
+ * workspace: at least basd_mp_rank_workspace_bytes(M, D). */
+int basd_mp_rank_workspace_bytes(int64_t M, int D, size_t* bytes);
+int basd_mp_rank(const void* features, int64_t M, int D, int dtype, int64_t row_stride, int* rank_out, void* workspace,
+                 void* stream);
+
+/* Test hooks (used by tests/ only). */
+int basd_selftest_gemm(int variant, const void* A, const void* B, float* C, int M, int N, int K, void* stream);
+int basd_selftest_eig(const float* G, int n, float* evals, float* evecs, int* sweeps, void* workspace, void* stream);
+
+const char* basd_last_error(void);
+const char* basd_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BASD_B200_H */

@@ -1,0 +1,73 @@
+"""Generates tests/golden/*.pt by executing the UNMODIFIED reference (/root/reference/src/losses) on the synthetic
+inputs of oracle/synth.py.  Run in the build container only (the GPU box has no /root/reference):
+
+    python -m oracle.make_golden [tiny cfg1 cfg2]
+
+Each fixture stores the workload, seeds and the reference's outputs: loss, MP ranks, log_temperature gradients, and —
+because full student gradients of the big configs are too large to commit — their norms, a strided subsample and
+inner products with seeded random probes.  The tiny fixtures store full gradients.
+"""
+from __future__ import annotations
+
+import dataclasses
+import os
+import sys
+import time
+
+import torch
+import torch.nn as nn
+
+sys.path.insert(0, "/root/reference")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from oracle import synth  # noqa: E402
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+TINY = {
+    "tiny_cls": synth.Workload("tiny_cls", 4, 64, 64, 48, 96, 3, 2, True),
+    "tiny_interp": synth.Workload("tiny_interp", 4, 64, 36, 48, 96, 3, 2, True),
+    "tiny_cnn": synth.Workload("tiny_cnn", 6, 64, 16, 48, 128, 1, 1, False),
+}
+
+
+def probes(shape, n=4, seed=99):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.randn(shape, generator=g) for _ in range(n)]
+
+
+def run(name: str, w: synth.Workload, label_smoothing=0.001, full=False):
+    from src.losses.combined import BASDLoss      # the reference itself
+    inp = synth.make_inputs(w)
+    torch.manual_seed(0)
+    m = BASDLoss(nn.CrossEntropyLoss(label_smoothing=label_smoothing), w.Ds, w.Dt, w.student_depth, w.Ns,
+                 config=synth.module_config(w), teacher_has_cls_token=w.has_cls)
+    S = {l: v.float().clone().requires_grad_() for l, v in inp["student"].items()}
+    T = {j: v.float() for j, v in inp["teacher"].items()}
+    logits = inp["logits"].clone().requires_grad_()
+    t0 = time.time()
+    loss = m(logits, inp["targets"], S, T, inp["attn"])
+    loss.backward()
+    dt = time.time() - t0
+    out = dict(workload=dataclasses.asdict(w), seed=1234, module_seed=0, label_smoothing=label_smoothing,
+               loss=loss.detach(), ranks=dict(m.layer_selector.subspace_ranks),
+               grad_log_temperatures=m.layer_selector.log_temperatures.grad.clone(), token_layers=list(m.token_layers),
+               ref_seconds=dt, torch_version=torch.__version__)
+    out["grad_student_norm"] = {l: S[l].grad.norm() for l in S}
+    out["grad_student_probe"] = {l: torch.stack([(S[l].grad * p).sum() for p in probes(S[l].shape)]) for l in S}
+    out["grad_student_sub"] = {l: S[l].grad.flatten()[::997].clone() for l in S}
+    if full:
+        out["grad_student"] = {l: S[l].grad.clone() for l in S}
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    torch.save(out, os.path.join(GOLDEN_DIR, f"{name}.pt"))
+    print(f"{name}: loss {loss.item():.6f} ranks {out['ranks']} tgrad {out['grad_log_temperatures'].tolist()} ({dt:.1f}s)", flush=True)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["tiny", "cfg1"]
+    for k in which:
+        if k == "tiny":
+            for n, w in TINY.items():
+                run(n, w, full=True)
+        else:
+            run(k, synth.CONFIGS[k])

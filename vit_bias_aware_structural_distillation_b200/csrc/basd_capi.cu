@@ -1,0 +1,359 @@
+// C-ABI entry points (include/basd_b200.h): workspace layout and kernel orchestration of the four phases.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/basd_b200.h"
+#include "spectral.h"
+
+using namespace basd;
+
+static thread_local char g_err[512] = "";
+static int fail(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return 1;
+}
+#define CK(expr)                                                                                             \
+    do {                                                                                                     \
+        cudaError_t _e = (expr);                                                                             \
+        if (_e != cudaSuccess)                                                                               \
+            return fail("%s:%d %s -> %s; %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e), gemm_last_error()); \
+    } while (0)
+
+extern "C" const char* basd_last_error(void) { return g_err; }
+extern "C" const char* basd_version(void) { return "basd_b200 0.1 (sm_100a)"; }
+
+namespace {
+
+constexpr int kProcCtasMax = 160;
+
+struct Layout {
+    size_t rows, pt_hi, pt_lo, tpk, spk, z, stats, ranks, sweeps, evals, evecs_km, evecs_cm, d2, w, cosv, gamma, ang_scr, a, ssum,
+        tbar_hi, tbar_lo, ktt, proc_scr, gdir, theta, gwt, loss_b, dbg, geo_i, gw, gam_hi, gam_lo, corr, total;
+    int NsPad;
+};
+
+size_t align_up(size_t x) { return (x + 1023) & ~static_cast<size_t>(1023); }
+
+Layout make_layout(const basd_shape& s) {
+    Layout L;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
+    const size_t B = s.B, Ns = s.Ns, Nt = s.Nt, Ds = s.Ds, Dt = s.Dt, Lt = s.Lt, P = s.P;
+    L.NsPad = static_cast<int>((Ns + 7) / 8 * 8);
+    L.rows = take(4 * Lt * B * Nt);
+    L.pt_hi = take(2 * Ds * Dt);
+    L.pt_lo = take(2 * Ds * Dt);
+    const bool pack = s.act_dtype == BASD_DTYPE_F32;
+    L.tpk = take(pack ? 2 * Lt * B * Nt * Dt : 0);
+    L.spk = take(pack ? 2 * P * B * Ns * Ds : 0);
+    L.z = take(2 * Lt * B * Nt * Ds);
+    L.stats = take(4 * (Lt + P) * (Ds * Ds + Ds));
+    L.ranks = take(4 * Lt);
+    L.sweeps = take(4 * (2 * Lt + P));
+    L.evals = take(4 * (Lt + P) * Ds);
+    L.evecs_km = take(4 * (Lt + P) * Ds * Ds);
+    L.evecs_cm = take(4 * (Lt + P) * Ds * Ds);
+    L.d2 = take(4 * P * Lt);
+    L.w = take(4 * P * Lt);
+    L.cosv = take(4 * P * Lt * Ds);
+    L.gamma = take(4 * P * Lt * Ds * Ds);
+    L.ang_scr = take(4 * P * Lt * 8 * Ds * Ds);
+    L.a = take(4 * P * B * Ns);
+    L.ssum = take(4 * P * B);
+    L.tbar_hi = take(2 * P * B * Ns * Dt);
+    L.tbar_lo = take(2 * P * B * Ns * Dt);
+    L.ktt = take(4 * P * B * Ns * Ns);
+    L.proc_scr = take(4 * kProcCtasMax * procrustes_scratch_floats(s.Ns, s.Ds));
+    L.gdir = take(4 * P * B * Ns * Ds);
+    L.theta = take(2 * P * B * Ns * L.NsPad);
+    L.gwt = take(4 * P * B * Ns);
+    L.loss_b = take(4 * P * B);
+    L.dbg = take(4 * P * B * 5);
+    L.geo_i = take(4 * (P + 1));
+    L.gw = take(4 * P * Lt);
+    L.gam_hi = take(2 * P * Ds * Ds);
+    L.gam_lo = take(2 * P * Ds * Ds);
+    L.corr = take(4 * P * Ds);
+    L.total = off;
+    return L;
+}
+
+int check_shape(const basd_shape& s) {
+    if (s.B < 1 || s.Ns < 2 || s.Nt < 1 || s.Lt < 1 || s.P < 1) return fail("invalid shape");
+    if (s.P > BASD_MAX_POINTS || s.Lt > BASD_MAX_LAYERS) return fail("P <= %d and Lt <= %d required", BASD_MAX_POINTS, BASD_MAX_LAYERS);
+    if (s.Ds % 8 || s.Dt % 8) return fail("Ds and Dt must be multiples of 8 (16-byte rows), got %d, %d", s.Ds, s.Dt);
+    if (s.Ds > 224) return fail("Ds=%d > 224: pooled eigenproblems larger than one SM's shared memory are not built yet", s.Ds);
+    if (s.Ns > 224) return fail("Ns=%d > 224: per-sample problems larger than one SM's shared memory are not built yet", s.Ns);
+    if (s.Ds > s.Ns) return fail("Ds=%d > Ns=%d: the student-side factorisation of the Procrustes core is not built yet", s.Ds, s.Ns);
+    if (static_cast<long long>(s.B) * s.Nt * s.world_size < s.Ds)
+        return fail("pooled rows M < Ds (layer_selector.py:14-15 branch) is not supported");
+    if (s.world_size < 1) return fail("world_size must be >= 1");
+    return 0;
+}
+
+bool dense3(const int64_t* st, int N, int D) { return st[2] == 1 && st[1] == D && st[0] == static_cast<int64_t>(N) * D; }
+
+struct Resolved {
+    const __nv_bfloat16* teacher[BASD_MAX_LAYERS];
+    const __nv_bfloat16* student[BASD_MAX_POINTS];
+};
+
+// After phase 1 the bf16, dense versions of the tokens are either the inputs themselves or the packed copies.
+int resolve(const basd_shape& s, const basd_inputs& in, uint8_t* ws, const Layout& L, Resolved* r) {
+    const bool pack = s.act_dtype == BASD_DTYPE_F32;
+    if (!pack) {
+        if (!dense3(in.teacher_strides, s.Nt, s.Dt) || !dense3(in.student_strides, s.Ns, s.Ds))
+            return fail("bf16 token tensors must be dense [B,N,D] (make them contiguous in the binding)");
+    }
+    for (int j = 0; j < s.Lt; ++j) {
+        if (!in.teacher[j] || !in.attn[j]) return fail("null teacher/attention pointer at layer %d", j);
+        r->teacher[j] = pack ? reinterpret_cast<const __nv_bfloat16*>(ws + L.tpk) + static_cast<size_t>(j) * s.B * s.Nt * s.Dt
+                             : reinterpret_cast<const __nv_bfloat16*>(in.teacher[j]);
+        if (reinterpret_cast<uintptr_t>(r->teacher[j]) & 15) return fail("teacher tensor %d not 16-byte aligned", j);
+    }
+    for (int i = 0; i < s.P; ++i) {
+        if (!in.student[i]) return fail("null student pointer at point %d", i);
+        r->student[i] = pack ? reinterpret_cast<const __nv_bfloat16*>(ws + L.spk) + static_cast<size_t>(i) * s.B * s.Ns * s.Ds
+                             : reinterpret_cast<const __nv_bfloat16*>(in.student[i]);
+        if (reinterpret_cast<uintptr_t>(r->student[i]) & 15) return fail("student tensor %d not 16-byte aligned", i);
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int basd_workspace_bytes(const basd_shape* shape, size_t* bytes) {
+    if (!shape || !bytes) return fail("null argument");
+    if (check_shape(*shape)) return 1;
+    *bytes = make_layout(*shape).total;
+    return 0;
+}
+
+extern "C" int basd_view(const basd_shape* shape, void* workspace, const char* name, void** ptr, size_t* count) {
+    if (!shape || !workspace || !name || !ptr || !count) return fail("null argument");
+    const basd_shape& s = *shape;
+    const Layout L = make_layout(s);
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    const size_t B = s.B, Ns = s.Ns, Nt = s.Nt, Ds = s.Ds, Lt = s.Lt, P = s.P;
+    struct E { const char* n; size_t off; size_t cnt; } table[] = {
+        {"stats", L.stats, (Lt + P) * (Ds * Ds + Ds)}, {"gw", L.gw, P * Lt}, {"ranks", L.ranks, Lt}, {"w", L.w, P * Lt},
+        {"d2", L.d2, P * Lt}, {"geo_i", L.geo_i, P + 1}, {"loss_b", L.loss_b, P * B}, {"rows", L.rows, Lt * B * Nt},
+        {"a", L.a, P * B * Ns}, {"evals", L.evals, (Lt + P) * Ds}, {"cos", L.cosv, P * Lt * Ds}, {"dbg", L.dbg, P * B * 5},
+        {"gdir", L.gdir, P * B * Ns * Ds}, {"ktt", L.ktt, P * B * Ns * Ns}, {"sweeps", L.sweeps, 2 * Lt + P},
+        {"gamma", L.gamma, P * Lt * Ds * Ds}, {"gwt", L.gwt, P * B * Ns}, {"evecs", L.evecs_km, (Lt + P) * Ds * Ds},
+        {"corr", L.corr, P * Ds}, {"ssum", L.ssum, P * B},
+    };
+    for (const E& e : table)
+        if (!strcmp(e.n, name)) { *ptr = ws + e.off; *count = e.cnt; return 0; }
+    return fail("unknown view '%s'", name);
+}
+
+extern "C" int basd_forward_stats(const basd_shape* shape, const basd_inputs* in_, void* workspace, void* stream) {
+    if (!shape || !in_ || !workspace) return fail("null argument");
+    const basd_shape& s = *shape;
+    const basd_inputs& in = *in_;
+    if (check_shape(s)) return 1;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    const Layout L = make_layout(s);
+    const size_t Mt = static_cast<size_t>(s.B) * s.Nt, Ms = static_cast<size_t>(s.B) * s.Ns;
+    const size_t stat_stride = static_cast<size_t>(s.Ds) * s.Ds + s.Ds;
+    float* stats = reinterpret_cast<float*>(ws + L.stats);
+
+    CK(cudaMemsetAsync(stats, 0, sizeof(float) * (s.Lt + s.P) * stat_stride, st));
+    PtrTable attn;
+    memset(&attn, 0, sizeof attn);
+    for (int j = 0; j < s.Lt; ++j) attn.p[j] = in.attn[j];
+    long long as[4] = {in.attn_strides[0], in.attn_strides[1], in.attn_strides[2], in.attn_strides[3]};
+    CK(launch_importance_rows(attn, s.attn_dtype == BASD_DTYPE_BF16, s.Lt, s.B, s.H, s.Nt, s.has_cls, as,
+                              reinterpret_cast<float*>(ws + L.rows), st));
+    __nv_bfloat16* pt_hi = reinterpret_cast<__nv_bfloat16*>(ws + L.pt_hi);
+    __nv_bfloat16* pt_lo = reinterpret_cast<__nv_bfloat16*>(ws + L.pt_lo);
+    CK(launch_split_bf16(in.proj_t, pt_hi, pt_lo, static_cast<size_t>(s.Ds) * s.Dt, st));
+    if (s.act_dtype == BASD_DTYPE_F32) {
+        for (int j = 0; j < s.Lt; ++j)
+            CK(launch_pack_bf16(in.teacher[j], 0, in.teacher_strides[0], in.teacher_strides[1], in.teacher_strides[2], s.B, s.Nt, s.Dt,
+                                reinterpret_cast<__nv_bfloat16*>(ws + L.tpk) + static_cast<size_t>(j) * Mt * s.Dt, st));
+        for (int i = 0; i < s.P; ++i)
+            CK(launch_pack_bf16(in.student[i], 0, in.student_strides[0], in.student_strides[1], in.student_strides[2], s.B, s.Ns, s.Ds,
+                                reinterpret_cast<__nv_bfloat16*>(ws + L.spk) + static_cast<size_t>(i) * Ms * s.Ds, st));
+    }
+    Resolved r;
+    if (resolve(s, in, ws, L, &r)) return 1;
+    __nv_bfloat16* z = reinterpret_cast<__nv_bfloat16*>(ws + L.z);
+    for (int j = 0; j < s.Lt; ++j) CK(gemm_project(r.teacher[j], Mt, s.Dt, pt_hi, pt_lo, s.Ds, z + static_cast<size_t>(j) * Mt * s.Ds, st));
+    CK(gemm_gram_batched(z, Mt, s.Ds, s.Lt, stats, static_cast<long long>(stat_stride), st));
+    for (int j = 0; j < s.Lt; ++j)
+        CK(launch_colsum(z + static_cast<size_t>(j) * Mt * s.Ds, Mt, s.Ds, stats + j * stat_stride + static_cast<size_t>(s.Ds) * s.Ds, st));
+    for (int i = 0; i < s.P; ++i) {
+        float* g = stats + (s.Lt + i) * stat_stride;
+        CK(gemm_gram(r.student[i], Ms, s.Ds, g, st));
+        CK(launch_colsum(r.student[i], Ms, s.Ds, g + static_cast<size_t>(s.Ds) * s.Ds, st));
+    }
+    return 0;
+}
+
+extern "C" int basd_forward_solve(const basd_shape* shape, const basd_inputs* in_, void* workspace, float* geo_loss, void* stream) {
+    if (!shape || !in_ || !workspace || !geo_loss) return fail("null argument");
+    const basd_shape& s = *shape;
+    const basd_inputs& in = *in_;
+    if (check_shape(s)) return 1;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    const Layout L = make_layout(s);
+    Resolved r;
+    if (resolve(s, in, ws, L, &r)) return 1;
+    const float Mt = static_cast<float>(s.B) * s.Nt * s.world_size, Ms = static_cast<float>(s.B) * s.Ns * s.world_size;
+    float* stats = reinterpret_cast<float*>(ws + L.stats);
+    int* ranks = reinterpret_cast<int*>(ws + L.ranks);
+    float* evals = reinterpret_cast<float*>(ws + L.evals);
+    float* evk = reinterpret_cast<float*>(ws + L.evecs_km);
+    float* evc = reinterpret_cast<float*>(ws + L.evecs_cm);
+    float* d2 = reinterpret_cast<float*>(ws + L.d2);
+    float* w = reinterpret_cast<float*>(ws + L.w);
+
+    CK(launch_pooled_eig(stats, s.Ds, s.Lt, s.P, Mt, Ms, ranks, evals, evk, evc, reinterpret_cast<int*>(ws + L.sweeps), st));
+    CK(launch_angles(s.Ds, s.Lt, s.P, ranks, evals, evk, evc, in.proj_s, reinterpret_cast<float*>(ws + L.ang_scr), d2,
+                     reinterpret_cast<float*>(ws + L.gamma), reinterpret_cast<float*>(ws + L.cosv), in.log_temperatures, w, st));
+    float* a = reinterpret_cast<float*>(ws + L.a);
+    float* ssum = reinterpret_cast<float*>(ws + L.ssum);
+    CK(launch_importance_mix(reinterpret_cast<float*>(ws + L.rows), w, s.Lt, s.P, s.B, s.Nt, s.Ns, a, ssum, st));
+    PtrTable tt;
+    memset(&tt, 0, sizeof tt);
+    for (int j = 0; j < s.Lt; ++j) tt.p[j] = r.teacher[j];
+    __nv_bfloat16* thi = reinterpret_cast<__nv_bfloat16*>(ws + L.tbar_hi);
+    __nv_bfloat16* tlo = reinterpret_cast<__nv_bfloat16*>(ws + L.tbar_lo);
+    CK(launch_mix_teacher(tt, w, s.Lt, s.P, s.B, s.Nt, s.Ns, s.Dt, thi, tlo, st));
+    float* ktt = reinterpret_cast<float*>(ws + L.ktt);
+    CK(gemm_token_gram(thi, tlo, s.P * s.B, s.Ns, s.Dt, ktt, st));
+
+    ProcrustesArgs pa;
+    memset(&pa, 0, sizeof pa);
+    pa.Ns = s.Ns; pa.Ds = s.Ds; pa.B = s.B; pa.NsPad = L.NsPad; pa.n_problems = s.P * s.B;
+    pa.Ktt = ktt; pa.a = a; pa.ssum = ssum;
+    for (int i = 0; i < s.P; ++i) pa.student[i] = r.student[i];
+    pa.student_batch_stride = static_cast<long long>(s.Ns) * s.Ds;
+    pa.scratch = reinterpret_cast<float*>(ws + L.proc_scr);
+    pa.gdir = reinterpret_cast<float*>(ws + L.gdir);
+    pa.theta = reinterpret_cast<__nv_bfloat16*>(ws + L.theta);
+    pa.gwt = reinterpret_cast<float*>(ws + L.gwt);
+    pa.loss_b = reinterpret_cast<float*>(ws + L.loss_b);
+    pa.dbg = reinterpret_cast<float*>(ws + L.dbg);
+    int dev = 0, sms = 148;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int ctas = pa.n_problems < sms ? pa.n_problems : sms;
+    if (ctas > kProcCtasMax) ctas = kProcCtasMax;
+    CK(launch_procrustes(pa, ctas, st));
+    float* geo_i = reinterpret_cast<float*>(ws + L.geo_i);
+    CK(launch_loss_reduce(pa.loss_b, s.P, s.B, geo_i, geo_i + s.P, st));
+    CK(cudaMemcpyAsync(geo_loss, geo_i + s.P, sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+extern "C" int basd_backward_dots(const basd_shape* shape, const basd_inputs* in_, void* workspace, void* stream) {
+    if (!shape || !in_ || !workspace) return fail("null argument");
+    const basd_shape& s = *shape;
+    if (check_shape(s)) return 1;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    const Layout L = make_layout(s);
+    Resolved r;
+    if (resolve(s, *in_, ws, L, &r)) return 1;
+    PtrTable tt;
+    memset(&tt, 0, sizeof tt);
+    for (int j = 0; j < s.Lt; ++j) tt.p[j] = r.teacher[j];
+    __nv_bfloat16* thi = reinterpret_cast<__nv_bfloat16*>(ws + L.tbar_hi);
+    __nv_bfloat16* dtm = reinterpret_cast<__nv_bfloat16*>(ws + L.tbar_lo);     // lo half is dead after the token Gram
+    CK(gemm_theta_apply(reinterpret_cast<__nv_bfloat16*>(ws + L.theta), L.NsPad, thi, s.P * s.B, s.Ns, s.Dt, dtm, st));
+    float* gw = reinterpret_cast<float*>(ws + L.gw);
+    CK(cudaMemsetAsync(gw, 0, sizeof(float) * s.P * s.Lt, st));
+    CK(launch_wgrad_dots(tt, dtm, reinterpret_cast<float*>(ws + L.gwt), reinterpret_cast<float*>(ws + L.rows), s.Lt, s.P, s.B, s.Nt,
+                         s.Ns, s.Dt, gw, st));
+    return 0;
+}
+
+extern "C" int basd_backward_finish(const basd_shape* shape, const basd_inputs* in_, void* workspace, const float* grad_geo,
+                                    void* const* grad_student, int grad_dtype, float* grad_log_temperatures, void* stream) {
+    if (!shape || !in_ || !workspace || !grad_geo || !grad_student || !grad_log_temperatures) return fail("null argument");
+    const basd_shape& s = *shape;
+    const basd_inputs& in = *in_;
+    if (check_shape(s)) return 1;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    const Layout L = make_layout(s);
+    Resolved r;
+    if (resolve(s, in, ws, L, &r)) return 1;
+    const float Ms = static_cast<float>(s.B) * s.Ns * s.world_size;
+    const float scale = 1.f / (static_cast<float>(s.P) * s.B);
+    __nv_bfloat16* ghi = reinterpret_cast<__nv_bfloat16*>(ws + L.gam_hi);
+    __nv_bfloat16* glo = reinterpret_cast<__nv_bfloat16*>(ws + L.gam_lo);
+    float* corr = reinterpret_cast<float*>(ws + L.corr);
+    CK(launch_selector_bwd(s.Ds, s.Lt, s.P, reinterpret_cast<float*>(ws + L.gw), grad_geo, scale, reinterpret_cast<float*>(ws + L.w),
+                           reinterpret_cast<float*>(ws + L.d2), in.log_temperatures, reinterpret_cast<float*>(ws + L.gamma),
+                           reinterpret_cast<float*>(ws + L.stats), Ms, ghi, glo, corr, grad_log_temperatures, st));
+    const size_t MsL = static_cast<size_t>(s.B) * s.Ns;
+    for (int i = 0; i < s.P; ++i) {
+        if (!grad_student[i]) return fail("null grad_student[%d]", i);
+        CK(gemm_student_grad(r.student[i], MsL, s.Ds, ghi + static_cast<size_t>(i) * s.Ds * s.Ds, glo + static_cast<size_t>(i) * s.Ds * s.Ds,
+                             reinterpret_cast<float*>(ws + L.gdir) + static_cast<size_t>(i) * MsL * s.Ds, corr + static_cast<size_t>(i) * s.Ds,
+                             grad_geo, scale, grad_student[i], grad_dtype == BASD_DTYPE_BF16, st));
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------- marchenko_pastur_rank
+extern "C" int basd_mp_rank_workspace_bytes(int64_t M, int D, size_t* bytes) {
+    if (!bytes || M < 1 || D < 8) return fail("invalid argument");
+    *bytes = align_up(2 * static_cast<size_t>(M) * D) + align_up(4 * 2 * (static_cast<size_t>(D) * D + D)) + align_up(4 * 2 * D) +
+             2 * align_up(4 * 2 * static_cast<size_t>(D) * D) + 4096;
+    return 0;
+}
+
+extern "C" int basd_mp_rank(const void* features, int64_t M, int D, int dtype, int64_t row_stride, int* rank_out, void* workspace,
+                            void* stream) {
+    if (!features || !rank_out || !workspace) return fail("null argument");
+    if (D % 8 || D > 224) return fail("basd_mp_rank: D must be a multiple of 8 and <= 224 (got %d)", D);
+    if (M < D) return fail("basd_mp_rank: M < D branch (layer_selector.py:14-15) not supported");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    size_t off = 0;
+    __nv_bfloat16* zb = reinterpret_cast<__nv_bfloat16*>(ws + off); off += align_up(2 * static_cast<size_t>(M) * D);
+    float* stats = reinterpret_cast<float*>(ws + off); off += align_up(4 * 2 * (static_cast<size_t>(D) * D + D));
+    float* evals = reinterpret_cast<float*>(ws + off); off += align_up(4 * 2 * D);
+    float* evk = reinterpret_cast<float*>(ws + off); off += align_up(4 * 2 * static_cast<size_t>(D) * D);
+    float* evc = reinterpret_cast<float*>(ws + off); off += align_up(4 * 2 * static_cast<size_t>(D) * D);
+    int* ranks = reinterpret_cast<int*>(ws + off);
+    CK(launch_pack_bf16(features, dtype == BASD_DTYPE_BF16, 0, row_stride, 1, 1, static_cast<int>(M), D, zb, st));
+    CK(cudaMemsetAsync(stats, 0, 4 * 2 * (static_cast<size_t>(D) * D + D), st));
+    CK(gemm_gram(zb, static_cast<size_t>(M), D, stats, st));
+    CK(launch_pooled_eig(stats, D, 1, 0, static_cast<float>(M), 1.f, ranks, evals, evk, evc, nullptr, st));
+    CK(cudaMemcpyAsync(rank_out, ranks, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------- test hooks
+extern "C" int basd_selftest_gemm(int variant, const void* A, const void* B, float* C, int M, int N, int K, void* stream) {
+    CK(gemm_selftest(variant, reinterpret_cast<const __nv_bfloat16*>(A), reinterpret_cast<const __nv_bfloat16*>(B), C, M, N, K,
+                     reinterpret_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+// eigen-decomposition of a symmetric PSD matrix G [n][n]: evals [n] descending, evecs [n][n] (row e = e-th eigenvector).
+// workspace: 4 * (n*n + n) + 4 * n * n bytes (+ alignment slack 4096).
+extern "C" int basd_selftest_eig(const float* G, int n, float* evals, float* evecs, int* sweeps, void* workspace, void* stream) {
+    if (!G || !evals || !evecs || !workspace) return fail("null argument");
+    if (n > 224) return fail("n > 224");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    float* stats = reinterpret_cast<float*>(ws);
+    float* evc = reinterpret_cast<float*>(ws + align_up(4 * (static_cast<size_t>(n) * n + n)));
+    CK(cudaMemsetAsync(stats, 0, 4 * (static_cast<size_t>(n) * n + n), st));
+    CK(cudaMemcpyAsync(stats, G, 4 * static_cast<size_t>(n) * n, cudaMemcpyDeviceToDevice, st));
+    CK(launch_pooled_eig(stats, n, 0, 1, 1.f, 1.f, nullptr, evals, evecs, evc, sweeps, st));
+    return 0;
+}

@@ -1,0 +1,210 @@
+// Host launchers for the tcgen05 GEMM instances used by the BASD loss path (see umma_gemm.cuh).
+// Tensor maps are encoded on the host per call (cuTensorMapEncodeTiled, resolved at run time through
+// cudaGetDriverEntryPoint so the library links and loads on a machine without a driver).
+#include <cudaTypedefs.h>
+
+#include <cstdio>
+#include <cstring>
+
+#include "spectral.h"
+#include "umma_gemm.cuh"
+
+namespace basd {
+
+static thread_local char g_gemm_err[256] = "";
+const char* gemm_last_error() { return g_gemm_err; }
+
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeFn g_encode = nullptr;
+
+int gemm_init_driver_api() {
+    if (g_encode) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+        snprintf(g_gemm_err, sizeof g_gemm_err, "cuTensorMapEncodeTiled unavailable: %s", cudaGetErrorString(e));
+        return 1;
+    }
+    g_encode = reinterpret_cast<EncodeFn>(fn);
+    return 0;
+}
+
+// bf16 tensor viewed as [batch][rows][inner]; box = [1][box_rows][64]; SWIZZLE_128B; OOB -> zeros.
+static int make_map(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t rows, uint64_t batch, uint64_t row_pitch_elems,
+                    uint64_t batch_pitch_elems, uint32_t box_rows) {
+    if (gemm_init_driver_api()) return 1;
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (row_pitch_elems * 2) % 16 || (batch_pitch_elems * 2) % 16) {
+        snprintf(g_gemm_err, sizeof g_gemm_err, "TMA operand misaligned: ptr=%p row_pitch=%llu batch_pitch=%llu", ptr,
+                 (unsigned long long)row_pitch_elems, (unsigned long long)batch_pitch_elems);
+        return 1;
+    }
+    cuuint64_t dims[3] = {inner, rows, batch};
+    cuuint64_t strides[2] = {row_pitch_elems * 2, batch_pitch_elems * 2};
+    cuuint32_t box[3] = {64, box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        snprintf(g_gemm_err, sizeof g_gemm_err, "cuTensorMapEncodeTiled failed (%d) inner=%llu rows=%llu batch=%llu box_rows=%u", (int)r,
+                 (unsigned long long)inner, (unsigned long long)rows, (unsigned long long)batch, box_rows);
+        return 1;
+    }
+    return 0;
+}
+
+template <class Cfg, class Epi>
+static cudaError_t launch(const GemmMaps& maps, const GemmArgs& args, dim3 grid, cudaStream_t st) {
+    auto kern = umma_gemm_kernel<Cfg, Epi>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, st>>>(maps, args);
+    return cudaGetLastError();
+}
+
+static inline int cdiv(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
+
+//                      A_MN   B_MN   BN   MT NA NB T  alias  stages
+using CfgProject = GemmCfg<false, false, 192, 1, 1, 2, 2, false, 3>;
+using CfgGram    = GemmCfg<true,  true,  192, 2, 1, 1, 1, false, 3>;
+using CfgTheta   = GemmCfg<false, true,  128, 2, 1, 1, 1, false, 4>;
+template <int BN> using CfgTokenGram = GemmCfg<false, false, BN, 2, 2, 2, 3, true, 3>;
+using CfgTestTN  = GemmCfg<false, false, 192, 1, 1, 1, 1, false, 4>;
+
+cudaError_t gemm_project(const __nv_bfloat16* X, size_t M, int Dt, const __nv_bfloat16* Phi, const __nv_bfloat16* Plo, int Ds,
+                         __nv_bfloat16* Z, cudaStream_t st) {
+    GemmMaps maps;
+    memset(&maps, 0, sizeof maps);
+    if (make_map(&maps.a[0], X, Dt, M, 1, Dt, M * Dt, 128)) return cudaErrorInvalidValue;
+    if (make_map(&maps.b[0], Phi, Dt, Ds, 1, Dt, static_cast<uint64_t>(Ds) * Dt, CfgProject::kBN)) return cudaErrorInvalidValue;
+    if (make_map(&maps.b[1], Plo, Dt, Ds, 1, Dt, static_cast<uint64_t>(Ds) * Dt, CfgProject::kBN)) return cudaErrorInvalidValue;
+    GemmArgs a;
+    memset(&a, 0, sizeof a);
+    a.kb_total = cdiv(Dt, GEMM_BK);
+    a.out = Z; a.ld_out = Ds; a.rows_valid = static_cast<int>(M); a.cols_valid = Ds; a.alpha = 1.f;
+    return launch<CfgProject, EpiStoreBf16>(maps, a, dim3(cdiv(Ds, CfgProject::kBN), cdiv(M, 128), 1), st);
+}
+
+// G[batch] += Z[batch]^T Z[batch]; Z = [batches][M][Ds] contiguous; G batch stride given in floats.
+static cudaError_t gram_impl(const __nv_bfloat16* Z, size_t M, int Ds, int batches, float* G, long long g_stride, cudaStream_t st) {
+    GemmMaps maps;
+    memset(&maps, 0, sizeof maps);
+    if (make_map(&maps.a[0], Z, Ds, M, batches, Ds, M * Ds, 64)) return cudaErrorInvalidValue;
+    maps.b[0] = maps.a[0];
+    GemmArgs a;
+    memset(&a, 0, sizeof a);
+    a.kb_total = cdiv(M, GEMM_BK);
+    a.kb_per_split = 32;
+    a.n_splits = cdiv(a.kb_total, a.kb_per_split);
+    a.a_batched = 1; a.b_batched = 1;
+    a.out = G; a.out_batch_stride = g_stride; a.ld_out = Ds; a.rows_valid = Ds; a.cols_valid = Ds;
+    return launch<CfgGram, EpiAtomicAddF32>(maps, a, dim3(cdiv(Ds, CfgGram::kBN), cdiv(Ds, CfgGram::kMT * 128), batches * a.n_splits), st);
+}
+cudaError_t gemm_gram(const __nv_bfloat16* Z, size_t M, int Ds, float* G, cudaStream_t st) { return gram_impl(Z, M, Ds, 1, G, 0, st); }
+cudaError_t gemm_gram_batched(const __nv_bfloat16* Z, size_t M, int Ds, int batches, float* G, long long g_stride, cudaStream_t st) {
+    return gram_impl(Z, M, Ds, batches, G, g_stride, st);
+}
+
+template <int BN>
+static cudaError_t token_gram_impl(const __nv_bfloat16* Thi, const __nv_bfloat16* Tlo, int batches, int Ns, int Dt, float* Ktt,
+                                   cudaStream_t st) {
+    GemmMaps maps;
+    memset(&maps, 0, sizeof maps);
+    if (make_map(&maps.a[0], Thi, Dt, Ns, batches, Dt, static_cast<uint64_t>(Ns) * Dt, 128)) return cudaErrorInvalidValue;
+    if (make_map(&maps.a[1], Tlo, Dt, Ns, batches, Dt, static_cast<uint64_t>(Ns) * Dt, 128)) return cudaErrorInvalidValue;
+    GemmArgs a;
+    memset(&a, 0, sizeof a);
+    a.kb_total = cdiv(Dt, GEMM_BK);
+    a.a_batched = 1;
+    a.out = Ktt; a.out_batch_stride = static_cast<long long>(Ns) * Ns; a.ld_out = Ns; a.rows_valid = Ns; a.cols_valid = Ns; a.alpha = 1.f;
+    return launch<CfgTokenGram<BN>, EpiStoreF32>(maps, a, dim3(1, 1, batches), st);
+}
+cudaError_t gemm_token_gram(const __nv_bfloat16* Thi, const __nv_bfloat16* Tlo, int batches, int Ns, int Dt, float* Ktt, cudaStream_t st) {
+    if (Ns <= 64) return token_gram_impl<64>(Thi, Tlo, batches, Ns, Dt, Ktt, st);
+    if (Ns <= 128) return token_gram_impl<128>(Thi, Tlo, batches, Ns, Dt, Ktt, st);
+    if (Ns <= 208) return token_gram_impl<208>(Thi, Tlo, batches, Ns, Dt, Ktt, st);
+    if (Ns <= 256) return token_gram_impl<256>(Thi, Tlo, batches, Ns, Dt, Ktt, st);
+    snprintf(g_gemm_err, sizeof g_gemm_err, "token_gram: Ns=%d > 256 not supported yet", Ns);
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t gemm_theta_apply(const __nv_bfloat16* theta, int NsPad, const __nv_bfloat16* Thi, int batches, int Ns, int Dt,
+                             __nv_bfloat16* Dtm, cudaStream_t st) {
+    if (Ns > 256) {
+        snprintf(g_gemm_err, sizeof g_gemm_err, "theta_apply: Ns=%d > 256 not supported yet", Ns);
+        return cudaErrorInvalidValue;
+    }
+    GemmMaps maps;
+    memset(&maps, 0, sizeof maps);
+    if (make_map(&maps.a[0], theta, NsPad, Ns, batches, NsPad, static_cast<uint64_t>(Ns) * NsPad, 128)) return cudaErrorInvalidValue;
+    if (make_map(&maps.b[0], Thi, Dt, Ns, batches, Dt, static_cast<uint64_t>(Ns) * Dt, 64)) return cudaErrorInvalidValue;
+    GemmArgs a;
+    memset(&a, 0, sizeof a);
+    a.kb_total = cdiv(Ns, GEMM_BK);
+    a.a_batched = 1; a.b_batched = 1;
+    a.out = Dtm; a.out_batch_stride = static_cast<long long>(Ns) * Dt; a.ld_out = Dt; a.rows_valid = Ns; a.cols_valid = Dt; a.alpha = 1.f;
+    return launch<CfgTheta, EpiStoreBf16>(maps, a, dim3(cdiv(Dt, CfgTheta::kBN), 1, batches), st);
+}
+
+cudaError_t gemm_student_grad(const __nv_bfloat16* S, size_t M, int Ds, const __nv_bfloat16* Ghi, const __nv_bfloat16* Glo,
+                              const float* gdir, const float* corr, const float* scale_ptr, float scale_host, void* out,
+                              int out_is_bf16, cudaStream_t st) {
+    GemmMaps maps;
+    memset(&maps, 0, sizeof maps);
+    if (make_map(&maps.a[0], S, Ds, M, 1, Ds, M * Ds, 128)) return cudaErrorInvalidValue;
+    if (make_map(&maps.b[0], Ghi, Ds, Ds, 1, Ds, static_cast<uint64_t>(Ds) * Ds, CfgProject::kBN)) return cudaErrorInvalidValue;
+    if (make_map(&maps.b[1], Glo, Ds, Ds, 1, Ds, static_cast<uint64_t>(Ds) * Ds, CfgProject::kBN)) return cudaErrorInvalidValue;
+    GemmArgs a;
+    memset(&a, 0, sizeof a);
+    a.kb_total = cdiv(Ds, GEMM_BK);
+    a.out = out; a.ld_out = Ds; a.rows_valid = static_cast<int>(M); a.cols_valid = Ds;
+    a.aux0 = gdir; a.aux1 = corr; a.aux2 = scale_ptr; a.alpha = scale_host; a.beta = out_is_bf16 ? 1.f : 0.f;
+    return launch<CfgProject, EpiStudentGrad>(maps, a, dim3(cdiv(Ds, CfgProject::kBN), cdiv(M, 128), 1), st);
+}
+
+// variant 0: C[M][N] = A[M][K] B[N][K]^T          (both K-major)
+// variant 1: C[M][N] = A[K][M]^T B[K][N]          (both MN-major; split-K + atomics; C pre-zeroed)
+// variant 2: C[M][N] = A[M][K] B[K][N]            (A K-major, B MN-major)
+// variant 3: C[M][M] = A A^T + A B^T + B A^T      (token_gram path: A = hi [M][K], B = lo [M][K]; M <= 208)
+cudaError_t gemm_selftest(int variant, const __nv_bfloat16* A, const __nv_bfloat16* B, float* C, int M, int N, int K,
+                          cudaStream_t st) {
+    GemmMaps maps;
+    memset(&maps, 0, sizeof maps);
+    GemmArgs a;
+    memset(&a, 0, sizeof a);
+    a.out = C; a.ld_out = N; a.rows_valid = M; a.cols_valid = N; a.alpha = 1.f;
+    if (variant == 0) {
+        if (make_map(&maps.a[0], A, K, M, 1, K, static_cast<uint64_t>(M) * K, 128)) return cudaErrorInvalidValue;
+        if (make_map(&maps.b[0], B, K, N, 1, K, static_cast<uint64_t>(N) * K, CfgTestTN::kBN)) return cudaErrorInvalidValue;
+        a.kb_total = cdiv(K, GEMM_BK);
+        return launch<CfgTestTN, EpiStoreF32>(maps, a, dim3(cdiv(N, CfgTestTN::kBN), cdiv(M, 128), 1), st);
+    }
+    if (variant == 1) {
+        if (make_map(&maps.a[0], A, M, K, 1, M, static_cast<uint64_t>(M) * K, 64)) return cudaErrorInvalidValue;
+        if (make_map(&maps.b[0], B, N, K, 1, N, static_cast<uint64_t>(N) * K, 64)) return cudaErrorInvalidValue;
+        a.kb_total = cdiv(K, GEMM_BK);
+        a.kb_per_split = 4;
+        a.n_splits = cdiv(a.kb_total, a.kb_per_split);
+        a.a_batched = 1; a.b_batched = 1;
+        return launch<CfgGram, EpiAtomicAddF32>(maps, a, dim3(cdiv(N, CfgGram::kBN), cdiv(M, CfgGram::kMT * 128), a.n_splits), st);
+    }
+    if (variant == 2) {
+        if (make_map(&maps.a[0], A, K, M, 1, K, static_cast<uint64_t>(M) * K, 128)) return cudaErrorInvalidValue;
+        if (make_map(&maps.b[0], B, N, K, 1, N, static_cast<uint64_t>(N) * K, 64)) return cudaErrorInvalidValue;
+        a.kb_total = cdiv(K, GEMM_BK);
+        return launch<CfgTheta, EpiStoreF32>(maps, a, dim3(cdiv(N, CfgTheta::kBN), cdiv(M, CfgTheta::kMT * 128), 1), st);
+    }
+    if (variant == 3) {
+        return gemm_token_gram(A, B, 1, M, K, C, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace basd

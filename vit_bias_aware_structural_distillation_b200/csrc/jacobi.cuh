@@ -1,0 +1,134 @@
+// One-sided (Hestenes) Jacobi on a column-major fp32 matrix held in shared memory.
+//
+// Orthogonalises the n columns (length m, leading dimension ld) of A in place: A <- A V with V orthogonal,
+// until every pair of columns satisfies |a_p . a_q| <= tol * |a_p| |a_q|.  On exit the column norms are the
+// singular values of the input and the normalised columns its left singular vectors; for a symmetric PSD
+// input (A = G) the norms are the eigenvalues and the normalised columns the eigenvectors (G v = lambda v),
+// so no separate rotation accumulator is needed.  Replaces the LAPACK calls at
+// /root/reference/src/losses/layer_selector.py:16,36,92,99 and relational.py:48.
+//
+// Parallel ordering: round-robin tournament (n-1 steps per sweep, n/2 disjoint pairs per step).  A pair is
+// owned by a 16-lane group: each lane keeps its slice of both columns in registers (128-bit shared loads),
+// the three inner products are reduced with 4 xor-shuffles, the rotation is applied from registers.
+// ld must be a multiple of 4 with ld % 32 == 16 so the two groups of a warp hit disjoint banks.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace basd {
+
+constexpr int JAC_GROUP = 16;
+constexpr int JAC_MAX_CHUNKS = 4;      // 4 chunks x 64 rows -> m <= 256
+
+__host__ __device__ inline int jacobi_ld(int m) {     // smallest ld >= m with ld % 32 == 16
+    int ld = ((m + 31) / 32) * 32 + 16;
+    if (ld - 32 >= m) ld -= 32;
+    return ld;
+}
+
+// pair k (0 <= k < n/2) at step s (0 <= s < n-1); n even.
+__device__ __forceinline__ void jacobi_pair(int n, int s, int k, int& p, int& q) {
+    if (k == 0) { p = n - 1; q = s; return; }
+    const int m1 = n - 1;
+    p = s + k; if (p >= m1) p -= m1;
+    q = s - k; if (q < 0) q += m1;
+}
+
+// Returns the number of sweeps executed.  All threads of the CTA must call it (contains __syncthreads).
+// n_cols may be odd (the virtual last column is skipped).  Rows [m, ld) of every column must be zero.
+template <int CHUNKS>
+__device__ int jacobi_orthogonalize(float* __restrict__ A, int ld, int n_cols, float tol, int max_sweeps) {
+    const int n = (n_cols + 1) & ~1;
+    const int group = threadIdx.x / JAC_GROUP;
+    const int gl = threadIdx.x % JAC_GROUP;
+    const int n_groups = blockDim.x / JAC_GROUP;
+    const int half = n / 2;
+    const unsigned gmask = 0xFFFFu << (threadIdx.x & 16);   // the 16 lanes of this group (groups may diverge)
+    int sweep = 0;
+    if (n_cols < 2) return 0;
+    for (; sweep < max_sweeps; ++sweep) {
+        int rotated = 0;
+        for (int s = 0; s < n - 1; ++s) {
+            for (int k = group; k < half; k += n_groups) {
+                int p, q;
+                jacobi_pair(n, s, k, p, q);
+                if (p >= n_cols || q >= n_cols) continue;          // virtual padding column
+                float4 x[CHUNKS], y[CHUNKS];
+                float* cp = A + static_cast<size_t>(p) * ld;
+                float* cq = A + static_cast<size_t>(q) * ld;
+                float al = 0.f, be = 0.f, ga = 0.f;
+#pragma unroll
+                for (int c = 0; c < CHUNKS; ++c) {
+                    const int r = c * 64 + gl * 4;
+                    if (r < ld) {
+                        x[c] = *reinterpret_cast<const float4*>(cp + r);
+                        y[c] = *reinterpret_cast<const float4*>(cq + r);
+                    } else {
+                        x[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        y[c] = x[c];
+                    }
+                    al = fmaf(x[c].x, x[c].x, fmaf(x[c].y, x[c].y, fmaf(x[c].z, x[c].z, fmaf(x[c].w, x[c].w, al))));
+                    be = fmaf(y[c].x, y[c].x, fmaf(y[c].y, y[c].y, fmaf(y[c].z, y[c].z, fmaf(y[c].w, y[c].w, be))));
+                    ga = fmaf(x[c].x, y[c].x, fmaf(x[c].y, y[c].y, fmaf(x[c].z, y[c].z, fmaf(x[c].w, y[c].w, ga))));
+                }
+#pragma unroll
+                for (int o = JAC_GROUP / 2; o > 0; o >>= 1) {
+                    al += __shfl_xor_sync(gmask, al, o);
+                    be += __shfl_xor_sync(gmask, be, o);
+                    ga += __shfl_xor_sync(gmask, ga, o);
+                }
+                if (fabsf(ga) > tol * sqrtf(al * be)) {
+                    rotated = 1;
+                    const float zeta = (be - al) / (2.f * ga);
+                    const float t = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(fmaf(zeta, zeta, 1.f)));
+                    const float cs = rsqrtf(fmaf(t, t, 1.f));
+                    const float sn = cs * t;
+#pragma unroll
+                    for (int c = 0; c < CHUNKS; ++c) {
+                        const int r = c * 64 + gl * 4;
+                        if (r < ld) {
+                            float4 xn, yn;
+                            xn.x = cs * x[c].x - sn * y[c].x; yn.x = sn * x[c].x + cs * y[c].x;
+                            xn.y = cs * x[c].y - sn * y[c].y; yn.y = sn * x[c].y + cs * y[c].y;
+                            xn.z = cs * x[c].z - sn * y[c].z; yn.z = sn * x[c].z + cs * y[c].z;
+                            xn.w = cs * x[c].w - sn * y[c].w; yn.w = sn * x[c].w + cs * y[c].w;
+                            *reinterpret_cast<float4*>(cp + r) = xn;
+                            *reinterpret_cast<float4*>(cq + r) = yn;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (!__syncthreads_or(rotated)) { ++sweep; break; }
+    }
+    return sweep;
+}
+
+// Column norms (sqrt of sum of squares) of the first n_cols columns -> out[n_cols].  One warp per column.
+__device__ inline void column_norms(const float* __restrict__ A, int ld, int m, int n_cols, float* __restrict__ out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int c = warp; c < n_cols; c += nw) {
+        const float* col = A + static_cast<size_t>(c) * ld;
+        float s = 0.f;
+        for (int r = lane; r < m; r += 32) s = fmaf(col[r], col[r], s);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) out[c] = sqrtf(s);
+    }
+}
+
+// order[r] = index of the column with the r-th largest value (descending; ties by index).  n <= blockDim-strided.
+__device__ inline void rank_descending(const float* __restrict__ val, int n, int* __restrict__ order) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float v = val[i];
+        int r = 0;
+        for (int j = 0; j < n; ++j) {
+            const float u = val[j];
+            r += (u > v) || (u == v && j < i);
+        }
+        order[r] = i;
+    }
+}
+
+}  // namespace basd

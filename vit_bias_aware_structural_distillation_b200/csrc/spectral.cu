@@ -1,0 +1,553 @@
+// Spectral kernels of the BASD loss path (fp32, shared-memory one-sided Jacobi):
+//   pooled_eig_kernel   Marchenko-Pastur rank + centred-Gram eigenbases   (layer_selector.py:8-20, 23-37, 90-92)
+//   angles_kernel       principal angles, Grassmann distance and its pre-computed backward
+//                       (layer_selector.py:95-105)
+//   mix_weights_kernel  softmax mixing weights                              (layer_selector.py:107-108)
+//   procrustes_kernel   per-sample nuclear norm + closed-form gradients in token space
+//                       (relational.py:36-50)
+//   selector_bwd_kernel softmax/temperature backward + Gamma assembly       
+#include "spectral.h"
+
+#include <math_constants.h>
+
+#include "cta_linalg.cuh"
+#include "jacobi.cuh"
+
+namespace basd {
+
+constexpr float kJacobiTol = 3.0e-7f;
+constexpr int kJacobiMaxSweeps = 40;
+constexpr float kFp32Eps = 1.1920929e-7f;
+
+template <int CHUNKS>
+__device__ __forceinline__ int run_jacobi_chunks(float* A, int ld, int n) {
+    return jacobi_orthogonalize<CHUNKS>(A, ld, n, kJacobiTol, kJacobiMaxSweeps);
+}
+__device__ __forceinline__ int run_jacobi(float* A, int ld, int n) {
+    if (ld <= 64) return run_jacobi_chunks<1>(A, ld, n);
+    if (ld <= 128) return run_jacobi_chunks<2>(A, ld, n);
+    if (ld <= 192) return run_jacobi_chunks<3>(A, ld, n);
+    return run_jacobi_chunks<4>(A, ld, n);
+}
+
+// ------------------------------------------------------------------------------------------------
+// pooled_eig_kernel: one CTA per symmetric problem of size n = Ds.
+//   problem p in [0, Lt)        : MP rank of teacher layer p   (uncentred G / M)
+//   problem p in [Lt, 2Lt)      : centred eigen-decomposition of teacher layer p - Lt
+//   problem p in [2Lt, 2Lt + P) : centred eigen-decomposition of student extraction point p - 2Lt
+// stats layout: [(Lt + P)][n*n + n]  (Gram row-major, then column sums)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSpectralThreads, 1)
+pooled_eig_kernel(const float* __restrict__ stats, int n, int Lt, int P, float M_teacher, float M_student,
+                  int* __restrict__ ranks, float* __restrict__ evals, float* __restrict__ evecs_km,
+                  float* __restrict__ evecs_cm, int* __restrict__ sweeps_out) {
+    extern __shared__ float sm[];
+    const int ld = jacobi_ld(n);
+    float* A = sm;
+    float* vals = A + static_cast<size_t>(ld) * n;
+    float* csum = vals + n;
+    int* order = reinterpret_cast<int*>(csum + n);
+    __shared__ int s_count;
+
+    const int p = blockIdx.x;
+    const bool mp_mode = p < Lt;
+    const int gram_idx = mp_mode ? p : (p - Lt);                  // index into stats (teacher 0..Lt-1, student Lt..)
+    const float Mrows = gram_idx < Lt ? M_teacher : M_student;
+    const float* G = stats + static_cast<size_t>(gram_idx) * (n * n + n);
+    const float* cs = G + n * n;
+
+    for (int i = threadIdx.x; i < n; i += blockDim.x) csum[i] = cs[i];
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    const float invM = 1.f / Mrows;
+    for (int t = threadIdx.x; t < ld * n; t += blockDim.x) {
+        const int c = t / ld, r = t % ld;
+        float v = 0.f;
+        if (r < n) {
+            // symmetrise the split-K atomics result (bitwise symmetric input keeps Jacobi well behaved)
+            const float g = 0.5f * (G[r * n + c] + G[c * n + r]);
+            v = mp_mode ? g * invM : (g - csum[r] * csum[c] * invM);
+        }
+        A[c * ld + r] = v;
+    }
+    __syncthreads();
+    const int nsweeps = run_jacobi(A, ld, n);
+    column_norms(A, ld, n, n, vals);
+    __syncthreads();
+    rank_descending(vals, n, order);
+    __syncthreads();
+    if (threadIdx.x == 0 && sweeps_out) sweeps_out[p] = nsweeps;
+
+    if (mp_mode) {
+        // ascending index (n-1)/2 == descending index n-1-(n-1)/2  (torch.median = lower middle)
+        const float med = vals[order[n - 1 - (n - 1) / 2]];
+        const float sq = 1.f + sqrtf(static_cast<float>(n) * invM);
+        const float lam_plus = med * sq * sq;
+        int local = 0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) local += vals[i] > lam_plus;
+        atomicAdd(&s_count, local);
+        __syncthreads();
+        if (threadIdx.x == 0) ranks[p] = min(s_count, n - 1);
+        return;
+    }
+    const int q = p - Lt;                                         // output slot: teacher 0..Lt-1, student Lt..Lt+P-1
+    float* ev = evals + static_cast<size_t>(q) * n;
+    float* vk = evecs_km + static_cast<size_t>(q) * n * n;        // [eig][component]
+    float* vc = evecs_cm + static_cast<size_t>(q) * n * n;        // [component][eig]
+    for (int i = threadIdx.x; i < n; i += blockDim.x) ev[i] = vals[order[i]];
+    for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
+        const int e = t / n, c = t % n;
+        const int col = order[e];
+        const float nv = vals[col];
+        vk[e * n + c] = nv > 0.f ? A[col * ld + c] / nv : 0.f;
+    }
+    for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
+        const int c = t / n, e = t % n;
+        const int col = order[e];
+        const float nv = vals[col];
+        vc[c * n + e] = nv > 0.f ? A[col * ld + c] / nv : 0.f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// angles_kernel: grid (Lt, P).  Per (student point i, teacher layer j):
+//   A = V_s[:, :k]^T (P_s^T U_t)   (k x k);  cos = svdvals(A) via Jacobi on A^T A;
+//   d2 = sum sw theta^2 / sum sw;  Gamma_sym = d(d2)/dG_s + transpose   (n x n, saved for backward)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSpectralThreads, 1)
+angles_kernel(int n, int Lt, int P, const int* __restrict__ ranks, const float* __restrict__ evals,
+              const float* __restrict__ evecs_km, const float* __restrict__ evecs_cm, const float* __restrict__ proj_s,
+              float* __restrict__ scratch_all, float* __restrict__ d2_out, float* __restrict__ gamma_out,
+              float* __restrict__ cos_out) {
+    extern __shared__ float sm[];
+    const int j = blockIdx.x, i = blockIdx.y;
+    const int k = ranks[j];
+    const int ld = jacobi_ld(max(k, 1));
+    float* J = sm;                                               // k x k Jacobi matrix (ld x k)
+    float* vals = J + static_cast<size_t>(jacobi_ld(n - 1)) * (n - 1);
+    float* coef = vals + n;
+    float* red = coef + n;                                       // 33 floats
+    int* order = reinterpret_cast<int*>(red + 40);
+
+    const float* lam_t = evals + static_cast<size_t>(j) * n;
+    const float* Ut = evecs_km + static_cast<size_t>(j) * n * n;             // [eig][comp]
+    const float* lam_s = evals + static_cast<size_t>(Lt + i) * n;
+    const float* Vs_km = evecs_km + static_cast<size_t>(Lt + i) * n * n;     // [eig][comp]
+    const float* Vs_cm = evecs_cm + static_cast<size_t>(Lt + i) * n * n;     // [comp][eig]
+    float* gam = gamma_out + (static_cast<size_t>(i) * Lt + j) * n * n;
+    float* scratch = scratch_all + (static_cast<size_t>(i) * Lt + j) * (8 * static_cast<size_t>(n) * n);
+    float* Ur = scratch;                      // [b][c]   k x n
+    float* Wg = Ur + n * n;                   // [b][e]   column b contiguous in e
+    float* WgR = Wg + n * n;                  // [e][b]
+    float* Qg = WgR + n * n;                  // [b'][b]
+    float* WQg = Qg + n * n;                  // [b'][e]
+    float* Fg = WQg + n * n;                  // [a][e]
+    float* T1g = Fg + n * n;                  // [c'][e]
+    float* Gg = T1g + n * n;                  // [c'][c]
+
+    if (k == 0) {                              // reference: 0/0 -> NaN (layer_selector.py:105)
+        if (threadIdx.x == 0) d2_out[i * Lt + j] = CUDART_NAN_F;
+        for (int t = threadIdx.x; t < n * n; t += blockDim.x) gam[t] = 0.f;
+        return;
+    }
+    // (a) Ur[b][c] = sum_r Ut[b][r] P_s[r][c]
+    cta_gemm(n, k, n,
+             [&](int c, int r) { return proj_s[r * n + c]; },
+             [&](int r, int b) { return Ut[b * n + r]; },
+             [&](int c, int b, float v) { Ur[b * n + c] = v; });
+    __syncthreads();
+    // (b) W[e][b] = sum_c Vs[e][c] Ur[b][c]
+    cta_gemm(n, k, n,
+             [&](int e, int c) { return Vs_cm[c * n + e]; },
+             [&](int c, int b) { return Ur[b * n + c]; },
+             [&](int e, int b, float v) { Wg[b * n + e] = v; WgR[e * k + b] = v; });
+    __syncthreads();
+    // (c) J = A^T A,  A = W[:k,:k]
+    for (int t = threadIdx.x; t < ld * k; t += blockDim.x) J[t] = 0.f;
+    __syncthreads();
+    cta_gemm(k, k, k,
+             [&](int b, int a) { return WgR[a * k + b]; },
+             [&](int a, int b2) { return WgR[a * k + b2]; },
+             [&](int b, int b2, float v) { J[b2 * ld + b] = v; });
+    __syncthreads();
+    run_jacobi(J, ld, k);
+    column_norms(J, ld, k, k, vals);          // vals = sigma^2
+    __syncthreads();
+    rank_descending(vals, k, order);
+    __syncthreads();
+    // (d) distances and d(d2)/dsigma
+    float swsum = 0.f, acc = 0.f;
+    for (int r = threadIdx.x; r < k; r += blockDim.x) swsum += sqrtf(fmaxf(lam_t[r], 0.f));
+    swsum = cta_sum(swsum, red);
+    for (int r = threadIdx.x; r < k; r += blockDim.x) {
+        const int col = order[r];
+        const float sig = sqrtf(vals[col]);
+        const float sw = sqrtf(fmaxf(lam_t[r], 0.f));
+        const float clampv = 1.f - kFp32Eps;
+        const float sc = fminf(sig, clampv);
+        const float th = acosf(sc);
+        acc += sw * th * th;
+        float ds = 0.f;
+        if (sig <= clampv) ds = sw * 2.f * th * (-rsqrtf(fmaxf(1.f - sc * sc, 1e-30f))) / swsum;
+        // Q = Y diag(dsigma / sigma) Y^T with Y = normalised columns (column norm = sigma^2)
+        coef[col] = (sig > 1e-20f) ? ds / (sig * vals[col] * vals[col]) : 0.f;
+        if (cos_out) cos_out[(static_cast<size_t>(i) * Lt + j) * n + r] = sig;
+    }
+    acc = cta_sum(acc, red);
+    if (threadIdx.x == 0) d2_out[i * Lt + j] = acc / swsum;
+    __syncthreads();
+    // Q[b][b'] = sum_m J[b][m] coef_m J[b'][m]
+    cta_gemm(k, k, k,
+             [&](int b, int m) { return J[m * ld + b] * coef[m]; },
+             [&](int m, int b2) { return J[m * ld + b2]; },
+             [&](int b, int b2, float v) { Qg[b2 * k + b] = v; });
+    __syncthreads();
+    // (e) WQ[e][b'] = sum_b W[e][b] Q[b][b']
+    cta_gemm(n, k, k,
+             [&](int e, int b) { return Wg[b * n + e]; },
+             [&](int b, int b2) { return Qg[b2 * k + b]; },
+             [&](int e, int b2, float v) { WQg[b2 * n + e] = v; });
+    __syncthreads();
+    //     F[e][a] = (sum_b' WQ[e][b'] A[a][b']) / (lam_a - lam_e)   for e >= k, a < k
+    const int nc = n - k;
+    cta_gemm(nc, k, k,
+             [&](int e, int b2) { return WQg[b2 * n + k + e]; },
+             [&](int b2, int a) { return Wg[b2 * n + a]; },
+             [&](int e, int a, float v) { Fg[a * n + k + e] = v / (lam_s[a] - lam_s[k + e]); });
+    __syncthreads();
+    // (f) T1[e][c'] = sum_a F[e][a] Vs[a][c']
+    cta_gemm(nc, n, k,
+             [&](int e, int a) { return Fg[a * n + k + e]; },
+             [&](int a, int c2) { return Vs_km[a * n + c2]; },
+             [&](int e, int c2, float v) { T1g[c2 * n + k + e] = v; });
+    __syncthreads();
+    //     Gamma[c][c'] = sum_{e>=k} Vs[e][c] T1[e][c']
+    cta_gemm(n, n, nc,
+             [&](int c, int e) { return Vs_km[(k + e) * n + c]; },
+             [&](int e, int c2) { return T1g[c2 * n + k + e]; },
+             [&](int c, int c2, float v) { Gg[c2 * n + c] = v; });
+    __syncthreads();
+    for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
+        const int c = t / n, c2 = t % n;
+        gam[t] = Gg[c2 * n + c] + Gg[c * n + c2];
+    }
+}
+
+// w = softmax(-d2 / softplus(log_temperature))   one warp per extraction point
+__global__ void mix_weights_kernel(const float* __restrict__ d2, const float* __restrict__ log_temp, int Lt, int P,
+                                   float* __restrict__ w) {
+    const int i = blockIdx.x;
+    if (i >= P) return;
+    const float lt = log_temp[i];
+    const float tau = lt > 20.f ? lt : log1pf(expf(lt));
+    float mx = -CUDART_INF_F;
+    for (int j = threadIdx.x; j < Lt; j += 32) mx = fmaxf(mx, -d2[i * Lt + j] / tau);
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float s = 0.f;
+    for (int j = threadIdx.x; j < Lt; j += 32) s += expf(-d2[i * Lt + j] / tau - mx);
+    s = warp_sum(s);
+    for (int j = threadIdx.x; j < Lt; j += 32) {
+        const float d = d2[i * Lt + j];
+        w[i * Lt + j] = (d == d) ? expf(-d / tau - mx) / s : CUDART_NAN_F;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// procrustes_kernel: persistent CTAs loop over the P*B (extraction point, sample) problems.
+// Factor side = teacher token Gram (requires Ds <= Ns); see DESIGN.md "Procrustes core".
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSpectralThreads, 1)
+procrustes_kernel(ProcrustesArgs g) {
+    extern __shared__ float sm[];
+    const int N = g.Ns, D = g.Ds;
+    const int ld = jacobi_ld(N);
+    const int ncol = max(N, D);
+    float* A = sm;                                   // ld x ncol
+    float* a_s = A + static_cast<size_t>(ld) * ncol; // [N]
+    float* q_s = a_s + N;
+    float* m_s = q_s + N;                            // Ktt a
+    float* ktd = m_s + N;                            // diag(K_t)
+    float* ksd = ktd + N;                            // diag(K_s)
+    float* dots = ksd + N;                           // s_w,n . G_sw,n
+    float* mu_s = dots + N;                          // [D]
+    float* sig = mu_s + D;                           // [D]
+    float* red = sig + D;                            // 40
+    __shared__ int s_bad;
+
+    const size_t scr_per = procrustes_scratch_floats(N, D);
+    float* scr = g.scratch + static_cast<size_t>(blockIdx.x) * scr_per;
+    float* Lg = scr;                                 // [c][r] column-major, ld
+    float* SWr = Lg + static_cast<size_t>(ld) * N;   // [n][d] row-major
+    float* Y0r = SWr + static_cast<size_t>(N) * D;   // [n][d]
+    float* Og = Y0r + static_cast<size_t>(N) * D;    // [m][n]
+    float* Xg = Og + static_cast<size_t>(N) * N;
+    float* T2r = Xg + static_cast<size_t>(N) * N;    // [n][d]
+    float* Linvg = T2r + static_cast<size_t>(N) * D; // [c][r] column-major, ld
+    float* T3T = Linvg + static_cast<size_t>(ld) * N;// [m'][n]
+
+    for (int prob = blockIdx.x; prob < g.n_problems; prob += gridDim.x) {
+        const int i = prob / g.B, b = prob % g.B;
+        const float* Ktt = g.Ktt + static_cast<size_t>(prob) * N * N;
+        const float* a_in = g.a + static_cast<size_t>(prob) * N;
+        const __nv_bfloat16* S = g.student[i] + static_cast<size_t>(b) * g.student_batch_stride;
+        if (threadIdx.x == 0) s_bad = 0;
+        for (int n = threadIdx.x; n < N; n += blockDim.x) {
+            a_s[n] = a_in[n];
+            q_s[n] = sqrtf(a_in[n]);
+            dots[n] = 0.f;
+        }
+        __syncthreads();
+        // ---- S0: weighted mean, s_w, diag(K_s)
+        for (int d = threadIdx.x; d < D; d += blockDim.x) {
+            float mu = 0.f;
+            for (int n = 0; n < N; ++n) mu = fmaf(a_s[n], __bfloat162float(S[static_cast<size_t>(n) * D + d]), mu);
+            mu_s[d] = mu;
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < N * D; t += blockDim.x) {
+            const int n = t / D, d = t % D;
+            SWr[t] = q_s[n] * (__bfloat162float(S[t]) - mu_s[d]);
+        }
+        __syncthreads();
+        {
+            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+            for (int n = warp; n < N; n += nw) {
+                float s = 0.f;
+                for (int d = lane; d < D; d += 32) { const float v = SWr[n * D + d]; s = fmaf(v, v, s); }
+                s = warp_sum(s);
+                if (lane == 0) ksd[n] = s;
+            }
+        }
+        // ---- S1: m = Ktt a, centred + weighted teacher token Gram
+        for (int n = threadIdx.x; n < N; n += blockDim.x) {
+            float s = 0.f;
+            for (int m = 0; m < N; ++m) s = fmaf(Ktt[static_cast<size_t>(m) * N + n], a_s[m], s);
+            m_s[n] = s;
+        }
+        __syncthreads();
+        float part = 0.f;
+        for (int n = threadIdx.x; n < N; n += blockDim.x) part += a_s[n] * m_s[n];
+        const float mm = cta_sum(part, red);
+        part = 0.f;
+        for (int n = threadIdx.x; n < N; n += blockDim.x) {
+            const float v = a_s[n] * (Ktt[static_cast<size_t>(n) * N + n] - 2.f * m_s[n] + mm);
+            ktd[n] = v;
+            part += v;
+        }
+        const float tr_t = cta_sum(part, red);
+        part = 0.f;
+        for (int n = threadIdx.x; n < N; n += blockDim.x) part += ksd[n];
+        const float tr_s = cta_sum(part, red);
+        const float creg = tr_t / static_cast<float>(N);
+        for (int t = threadIdx.x; t < ld * N; t += blockDim.x) {
+            const int c = t / ld, r = t % ld;
+            float v = 0.f;
+            if (r < N) {
+                const float kk = 0.5f * (Ktt[static_cast<size_t>(r) * N + c] + Ktt[static_cast<size_t>(c) * N + r]);
+                v = q_s[r] * q_s[c] * (kk - m_s[r] - m_s[c] + mm + creg);
+            }
+            A[c * ld + r] = v;
+        }
+        __syncthreads();
+        // ---- S2: Cholesky K' = L L^T, keep a copy of L
+        cta_cholesky_lower(A, ld, N, &s_bad);
+        for (int t = threadIdx.x; t < ld * N; t += blockDim.x) Lg[t] = A[t];
+        __syncthreads();
+        // ---- S3: Y0^T[d][n] = sum_r SW[r][d] L[r][n]
+        cta_gemm(D, N, N,
+                 [&](int d, int r) { return SWr[r * D + d]; },
+                 [&](int r, int n) { return A[n * ld + r]; },
+                 [&](int d, int n, float v) { Y0r[n * D + d] = v; });
+        __syncthreads();
+        for (int t = threadIdx.x; t < ld * D; t += blockDim.x) {
+            const int d = t / ld, n = t % ld;
+            A[t] = n < N ? Y0r[n * D + d] : 0.f;
+        }
+        __syncthreads();
+        // ---- S4: one-sided Jacobi on the D columns of Y (length N)
+        const int nsweeps = run_jacobi(A, ld, D);
+        column_norms(A, ld, N, D, sig);
+        __syncthreads();
+        float smax = 0.f;
+        for (int d = threadIdx.x; d < D; d += blockDim.x) smax = fmaxf(smax, sig[d]);
+        for (int o = 16; o > 0; o >>= 1) smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, o));
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = smax;
+        __syncthreads();
+        smax = 0.f;
+        for (int wv = 0; wv < (blockDim.x >> 5); ++wv) smax = fmaxf(smax, red[wv]);
+        __syncthreads();
+        const float floor_sig = 1e-6f * smax;
+        part = 0.f;
+        for (int d = threadIdx.x; d < D; d += blockDim.x) part += sig[d] > floor_sig ? sig[d] : 0.f;
+        const float nuc = cta_sum(part, red);
+        // ---- S5: Omega = U S^-1 U^T, Xi = U S U^T   (columns of A are sigma_d u_d)
+        cta_gemm(N, N, D,
+                 [&](int n, int d) { return A[d * ld + n]; },
+                 [&](int d, int m) { const float s = sig[d]; return s > floor_sig ? A[d * ld + m] / (s * s * s) : 0.f; },
+                 [&](int n, int m, float v) { Og[m * N + n] = v; });
+        cta_gemm(N, N, D,
+                 [&](int n, int d) { return A[d * ld + n]; },
+                 [&](int d, int m) { const float s = sig[d]; return s > floor_sig ? A[d * ld + m] / s : 0.f; },
+                 [&](int n, int m, float v) { Xg[m * N + n] = v; });
+        __syncthreads();
+        // ---- S6: T2 = Omega Y0 (= polar factor of Y0), G_sw = L T2, outputs of the direct path
+        cta_gemm(N, D, N,
+                 [&](int n, int m) { return Og[m * N + n]; },
+                 [&](int m, int d) { return Y0r[m * D + d]; },
+                 [&](int n, int d, float v) { T2r[n * D + d] = v; });
+        __syncthreads();
+        float* gdir = g.gdir + static_cast<size_t>(prob) * N * D;
+        cta_gemm(N, D, N,
+                 [&](int n, int r) { return Lg[r * ld + n]; },
+                 [&](int r, int d) { return T2r[r * D + d]; },
+                 [&](int n, int d, float gsw) {
+                     const float sw = SWr[n * D + d];
+                     gdir[n * D + d] = q_s[n] * (2.f * sw - 2.f * gsw);
+                     atomicAdd(&dots[n], sw * gsw);
+                 });
+        __syncthreads();
+        // ---- S7: Psi = L^-T Xi L^-1, Theta' = 2 (diag(a) - q Psi q - a a^T)
+        for (int t = threadIdx.x; t < ld * N; t += blockDim.x) A[t] = Lg[t];
+        __syncthreads();
+        cta_lower_inverse(A, ld, N, Linvg, ld);
+        cta_gemm(N, N, N,
+                 [&](int mp, int m) { return Xg[m * N + mp]; },
+                 [&](int m, int n) { return m >= n ? Linvg[n * ld + m] : 0.f; },
+                 [&](int mp, int n, float v) { T3T[mp * N + n] = v; });
+        __syncthreads();
+        __nv_bfloat16* theta = g.theta + static_cast<size_t>(prob) * N * g.NsPad;
+        cta_gemm(N, N, N,
+                 [&](int np, int m) { return T3T[m * N + np]; },
+                 [&](int m, int n) { return m >= n ? Linvg[n * ld + m] : 0.f; },
+                 [&](int np, int n, float psi) {
+                     float v = -q_s[np] * psi * q_s[n] - a_s[np] * a_s[n];
+                     if (np == n) v += a_s[n];
+                     theta[static_cast<size_t>(n) * g.NsPad + np] = __float2bfloat16(2.f * v);
+                 });
+        for (int t = threadIdx.x; t < N * (g.NsPad - N); t += blockDim.x) {
+            const int n = t / (g.NsPad - N), c = N + t % (g.NsPad - N);
+            theta[static_cast<size_t>(n) * g.NsPad + c] = __float2bfloat16(0.f);
+        }
+        __syncthreads();
+        // ---- S8: importance gradient and scalars
+        part = 0.f;
+        for (int n = threadIdx.x; n < N; n += blockDim.x) {
+            const float ga = (ksd[n] + ktd[n] - 2.f * dots[n]) / a_s[n];
+            m_s[n] = ga;                                  // reuse
+            part += ga * a_s[n];
+        }
+        const float gdot = cta_sum(part, red);
+        const float inv_ssum = 1.f / g.ssum[prob];
+        for (int n = threadIdx.x; n < N; n += blockDim.x) g.gwt[static_cast<size_t>(prob) * N + n] = (m_s[n] - gdot) * inv_ssum;
+        if (threadIdx.x == 0) {
+            g.loss_b[prob] = tr_s + tr_t - 2.f * nuc;
+            if (g.dbg) {
+                g.dbg[prob * 5 + 0] = nuc; g.dbg[prob * 5 + 1] = tr_s; g.dbg[prob * 5 + 2] = tr_t;
+                g.dbg[prob * 5 + 3] = static_cast<float>(nsweeps); g.dbg[prob * 5 + 4] = static_cast<float>(s_bad);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// selector_bwd_kernel: grid (tiles, P).  gd_j = d L / d d2_ij from d L / d w, then
+//   Gamma'_i = sum_j gd_j Gamma_sym_ij  -> bf16 hi/lo;  corr_i = mu_i^T Gamma'_i;  grad log_temperature.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+selector_bwd_kernel(int n, int Lt, int P, const float* __restrict__ gw_raw, const float* __restrict__ scale_ptr,
+                    float scale_host, const float* __restrict__ w, const float* __restrict__ d2,
+                    const float* __restrict__ log_temp, const float* __restrict__ gamma,
+                    const float* __restrict__ stats, float M_student,
+                    __nv_bfloat16* __restrict__ gam_hi, __nv_bfloat16* __restrict__ gam_lo, float* __restrict__ corr,
+                    float* __restrict__ grad_log_temp) {
+    __shared__ float gd[64];
+    const int i = blockIdx.y;
+    const float scale = scale_host * (scale_ptr ? *scale_ptr : 1.f);
+    const float lt = log_temp[i];
+    const float tau = lt > 20.f ? lt : log1pf(expf(lt));
+    if (threadIdx.x < 32) {
+        float dotw = 0.f;
+        for (int j = threadIdx.x; j < Lt; j += 32) dotw += w[i * Lt + j] * gw_raw[i * Lt + j] * scale;
+        dotw = warp_sum(dotw);
+        float gtau = 0.f;
+        for (int j = threadIdx.x; j < Lt; j += 32) {
+            const float gx = w[i * Lt + j] * (gw_raw[i * Lt + j] * scale - dotw);
+            gd[j] = -gx / tau;
+            gtau += gx * d2[i * Lt + j] / (tau * tau);
+        }
+        gtau = warp_sum(gtau);
+        if (threadIdx.x == 0 && blockIdx.x == 0) grad_log_temp[i] = gtau / (1.f + expf(-lt));
+    }
+    __syncthreads();
+    const float* csum = stats + static_cast<size_t>(Lt + i) * (n * n + n) + n * n;
+    const float invM = 1.f / M_student;
+    // each CTA handles a strip of rows c; every thread a few (c, c') entries
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n * n; t += gridDim.x * blockDim.x) {
+        float acc = 0.f;
+        for (int j = 0; j < Lt; ++j) acc = fmaf(gd[j], gamma[(static_cast<size_t>(i) * Lt + j) * n * n + t], acc);
+        const __nv_bfloat16 hi = __float2bfloat16(acc);
+        gam_hi[static_cast<size_t>(i) * n * n + t] = hi;
+        gam_lo[static_cast<size_t>(i) * n * n + t] = __float2bfloat16(acc - __bfloat162float(hi));
+        // corr[c'] += mu[c] * Gamma'[c][c']   (Gamma' symmetric: index t = c*n + c')
+        const int c = t / n, c2 = t % n;
+        atomicAdd(&corr[i * n + c2], csum[c] * invM * acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+static size_t pooled_smem(int n) { return (static_cast<size_t>(jacobi_ld(n)) * n + 3 * n + 64) * sizeof(float); }
+static size_t angles_smem(int n) { return (static_cast<size_t>(jacobi_ld(n - 1)) * (n - 1) + 3 * n + 128) * sizeof(float); }
+static size_t procrustes_smem(int N, int D) {
+    return (static_cast<size_t>(jacobi_ld(N)) * (N > D ? N : D) + 6 * N + 2 * D + 64) * sizeof(float);
+}
+
+size_t spectral_max_smem(int N, int D) {
+    size_t a = pooled_smem(D), b = angles_smem(D), c = procrustes_smem(N, D);
+    return a > b ? (a > c ? a : c) : (b > c ? b : c);
+}
+
+cudaError_t launch_pooled_eig(const float* stats, int n, int Lt, int P, float Mt, float Ms, int* ranks, float* evals,
+                              float* evecs_km, float* evecs_cm, int* sweeps, cudaStream_t st) {
+    const size_t smem = pooled_smem(n);
+    cudaError_t e = cudaFuncSetAttribute(pooled_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    pooled_eig_kernel<<<2 * Lt + P, kSpectralThreads, smem, st>>>(stats, n, Lt, P, Mt, Ms, ranks, evals, evecs_km, evecs_cm, sweeps);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_angles(int n, int Lt, int P, const int* ranks, const float* evals, const float* evecs_km,
+                          const float* evecs_cm, const float* proj_s, float* scratch, float* d2, float* gamma,
+                          float* cos_out, const float* log_temp, float* w, cudaStream_t st) {
+    const size_t smem = angles_smem(n);
+    cudaError_t e = cudaFuncSetAttribute(angles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    angles_kernel<<<dim3(Lt, P), kSpectralThreads, smem, st>>>(n, Lt, P, ranks, evals, evecs_km, evecs_cm, proj_s, scratch, d2, gamma, cos_out);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    mix_weights_kernel<<<P, 32, 0, st>>>(d2, log_temp, Lt, P, w);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_procrustes(const ProcrustesArgs& args, int n_ctas, cudaStream_t st) {
+    const size_t smem = procrustes_smem(args.Ns, args.Ds);
+    cudaError_t e = cudaFuncSetAttribute(procrustes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    procrustes_kernel<<<n_ctas, kSpectralThreads, smem, st>>>(args);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_selector_bwd(int n, int Lt, int P, const float* gw_raw, const float* scale_ptr, float scale_host,
+                                const float* w, const float* d2, const float* log_temp, const float* gamma,
+                                const float* stats, float Ms, __nv_bfloat16* gam_hi, __nv_bfloat16* gam_lo, float* corr,
+                                float* grad_log_temp, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(corr, 0, sizeof(float) * P * n, st);
+    if (e != cudaSuccess) return e;
+    const int tiles = (n * n + 255) / 256;
+    selector_bwd_kernel<<<dim3(tiles < 64 ? tiles : 64, P), 256, 0, st>>>(n, Lt, P, gw_raw, scale_ptr, scale_host, w, d2, log_temp,
+                                                                          gamma, stats, Ms, gam_hi, gam_lo, corr, grad_log_temp);
+    return cudaGetLastError();
+}
+
+}  // namespace basd

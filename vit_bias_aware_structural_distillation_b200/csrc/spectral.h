@@ -1,0 +1,89 @@
+// Internal declarations shared by the kernels and the C-ABI orchestration (not part of the public ABI).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace basd {
+
+constexpr int kSpectralThreads = 768;
+constexpr int kMaxPoints = 8;         // extraction points P
+constexpr int kMaxLayers = 64;        // teacher layers Lt
+
+__host__ __device__ inline int jacobi_ld_host(int m) {
+    int ld = ((m + 31) / 32) * 32 + 16;
+    if (ld - 32 >= m) ld -= 32;
+    return ld;
+}
+__host__ __device__ inline size_t procrustes_scratch_floats(int N, int D) {
+    const size_t ld = jacobi_ld_host(N);
+    return 2 * ld * N + 3 * static_cast<size_t>(N) * D + 3 * static_cast<size_t>(N) * N;
+}
+
+struct ProcrustesArgs {
+    int Ns, Ds, B, NsPad, n_problems;
+    const float* Ktt;                     // [P*B][Ns][Ns]
+    const float* a;                       // [P*B][Ns]
+    const float* ssum;                    // [P*B]
+    const __nv_bfloat16* student[kMaxPoints];   // per extraction point, [B][Ns][Ds]
+    long long student_batch_stride;       // elements
+    float* scratch;
+    float* gdir;                          // [P*B][Ns][Ds]
+    __nv_bfloat16* theta;                 // [P*B][Ns][NsPad]
+    float* gwt;                           // [P*B][Ns]
+    float* loss_b;                        // [P*B]
+    float* dbg;                           // [P*B][5] or null
+};
+
+size_t spectral_max_smem(int N, int D);
+cudaError_t launch_pooled_eig(const float* stats, int n, int Lt, int P, float Mt, float Ms, int* ranks, float* evals,
+                              float* evecs_km, float* evecs_cm, int* sweeps, cudaStream_t st);
+cudaError_t launch_angles(int n, int Lt, int P, const int* ranks, const float* evals, const float* evecs_km,
+                          const float* evecs_cm, const float* proj_s, float* scratch, float* d2, float* gamma,
+                          float* cos_out, const float* log_temp, float* w, cudaStream_t st);
+cudaError_t launch_procrustes(const ProcrustesArgs& args, int n_ctas, cudaStream_t st);
+cudaError_t launch_selector_bwd(int n, int Lt, int P, const float* gw_raw, const float* scale_ptr, float scale_host,
+                                const float* w, const float* d2, const float* log_temp, const float* gamma,
+                                const float* stats, float Ms, __nv_bfloat16* gam_hi, __nv_bfloat16* gam_lo, float* corr,
+                                float* grad_log_temp, cudaStream_t st);
+
+// ---- streaming kernels (stream_ops.cu)
+struct PtrTable {                         // small by-value pointer tables for per-layer tensors
+    const void* p[kMaxLayers];
+};
+cudaError_t launch_importance_rows(const PtrTable& attn, int attn_is_bf16, int Lt, int B, int H, int Nt, int has_cls,
+                                   const long long* strides /*[b,h,q,k] elements*/, float* rows, cudaStream_t st);
+cudaError_t launch_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t n, cudaStream_t st);
+cudaError_t launch_pack_bf16(const void* src, int src_is_bf16, long long sb, long long sn, long long sd, int B, int N,
+                             int D, __nv_bfloat16* dst, cudaStream_t st);
+cudaError_t launch_colsum(const __nv_bfloat16* X, size_t rows, int D, float* out /*[D], pre-zeroed*/, cudaStream_t st);
+cudaError_t launch_importance_mix(const float* rows, const float* w, int Lt, int P, int B, int Nt, int Ns, float* a,
+                                  float* ssum, cudaStream_t st);
+cudaError_t launch_mix_teacher(const PtrTable& teacher, const float* w, int Lt, int P, int B, int Nt, int Ns, int Dt,
+                               __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st);
+cudaError_t launch_wgrad_dots(const PtrTable& teacher, const __nv_bfloat16* Dtm, const float* gwt, const float* rows,
+                              int Lt, int P, int B, int Nt, int Ns, int Dt, float* gw /*[P][Lt], pre-zeroed*/,
+                              cudaStream_t st);
+cudaError_t launch_loss_reduce(const float* loss_b, int P, int B, float* geo_i, float* geo, cudaStream_t st);
+
+// ---- tcgen05 GEMM launchers (gemm_ops.cu)
+int gemm_init_driver_api();               // resolves cuTensorMapEncodeTiled; 0 on success
+cudaError_t gemm_project(const __nv_bfloat16* X, size_t M, int Dt, const __nv_bfloat16* Phi, const __nv_bfloat16* Plo,
+                         int Ds, __nv_bfloat16* Z, cudaStream_t st);
+cudaError_t gemm_gram(const __nv_bfloat16* Z, size_t M, int Ds, float* G /*[Ds][Ds] pre-zeroed*/, cudaStream_t st);
+cudaError_t gemm_gram_batched(const __nv_bfloat16* Z, size_t M, int Ds, int batches, float* G, long long g_stride,
+                              cudaStream_t st);
+cudaError_t gemm_token_gram(const __nv_bfloat16* Thi, const __nv_bfloat16* Tlo, int batches, int Ns, int Dt, float* Ktt,
+                            cudaStream_t st);
+cudaError_t gemm_theta_apply(const __nv_bfloat16* theta, int NsPad, const __nv_bfloat16* Thi, int batches, int Ns, int Dt,
+                             __nv_bfloat16* Dtm, cudaStream_t st);
+cudaError_t gemm_student_grad(const __nv_bfloat16* S, size_t M, int Ds, const __nv_bfloat16* Ghi, const __nv_bfloat16* Glo,
+                              const float* gdir, const float* corr, const float* scale_ptr, float scale_host, void* out,
+                              int out_is_bf16, cudaStream_t st);
+// generic test hook: C[M][N] (fp32) = A[M][K] * B[N][K]^T or with MN-major operands (see basd_b200.h selftest)
+cudaError_t gemm_selftest(int variant, const __nv_bfloat16* A, const __nv_bfloat16* B, float* C, int M, int N, int K,
+                          cudaStream_t st);
+const char* gemm_last_error();
+
+}  // namespace basd

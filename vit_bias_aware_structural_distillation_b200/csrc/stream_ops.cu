@@ -1,0 +1,362 @@
+// Bandwidth-bound kernels of the BASD loss path: coalesced, 128-bit vectorised, fp32 accumulation.
+//   importance_rows   teacher attention -> per-layer token importance       (relational.py:22-27, before mixing)
+//   importance_mix    mix + resample + normalise importance                 (layer_selector.py:112, relational.py:29-34)
+//   mix_teacher       mix + token-grid resample of teacher tokens (hi/lo)   (layer_selector.py:111, combined.py:9-14)
+//   wgrad_dots        d loss / d mixing weights                             
+//   colsum, split_bf16, pack_bf16, loss_reduce  small helpers
+#include "cta_linalg.cuh"
+#include "spectral.h"
+
+namespace basd {
+
+__device__ __forceinline__ uint4 ld_nc_16(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void bf16x8_to_float(const uint4& v, float* f) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 t = __bfloat1622float2(h[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// linear resampling index along the token axis (align_corners = False), combined.py:12-14
+__device__ __forceinline__ void interp_index(int n, int n_in, int n_out, int& i0, int& i1, float& lam) {
+    if (n_in == n_out) { i0 = n; i1 = n; lam = 0.f; return; }
+    const float scale = static_cast<float>(n_in) / static_cast<float>(n_out);
+    float x = scale * (static_cast<float>(n) + 0.5f) - 0.5f;
+    x = fmaxf(x, 0.f);
+    i0 = min(static_cast<int>(x), n_in - 1);
+    i1 = min(i0 + 1, n_in - 1);
+    lam = x - static_cast<float>(i0);
+}
+
+// ---------------------------------------------------------------------------------------------- importance rows
+template <typename T>
+__device__ __forceinline__ float ld_as_float(const T* p);
+template <>
+__device__ __forceinline__ float ld_as_float<float>(const float* p) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float ld_as_float<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+template <typename T>
+__global__ void importance_rows_kernel(PtrTable attn, int B, int H, int Nt, int has_cls, long long sb, long long sh,
+                                       long long sq, long long sk, float* __restrict__ rows) {
+    const int b = blockIdx.x, j = blockIdx.y;
+    const T* A = reinterpret_cast<const T*>(attn.p[j]) + static_cast<long long>(b) * sb;
+    float* out = rows + (static_cast<size_t>(j) * B + b) * Nt;
+    if (has_cls) {
+        for (int n = threadIdx.x; n < Nt; n += blockDim.x) {
+            float s = 0.f;
+            for (int h = 0; h < H; ++h) s += ld_as_float(A + h * sh + (1 + n) * sk);     // query 0 (CLS), keys 1..Nt
+            out[n] = s / static_cast<float>(H);
+        }
+    } else {
+        for (int n = threadIdx.x; n < Nt; n += blockDim.x) {
+            float s = 0.f;
+            for (int h = 0; h < H; ++h)
+                for (int q = 0; q < Nt; ++q) s += ld_as_float(A + h * sh + q * sq + n * sk);
+            out[n] = s / static_cast<float>(H * Nt);
+        }
+    }
+}
+
+cudaError_t launch_importance_rows(const PtrTable& attn, int attn_is_bf16, int Lt, int B, int H, int Nt, int has_cls,
+                                   const long long* s, float* rows, cudaStream_t st) {
+    if (attn_is_bf16)
+        importance_rows_kernel<__nv_bfloat16><<<dim3(B, Lt), 256, 0, st>>>(attn, B, H, Nt, has_cls, s[0], s[1], s[2], s[3], rows);
+    else
+        importance_rows_kernel<float><<<dim3(B, Lt), 256, 0, st>>>(attn, B, H, Nt, has_cls, s[0], s[1], s[2], s[3], rows);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------- small helpers
+__global__ void split_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, size_t n) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const float v = src[i];
+        const __nv_bfloat16 h = __float2bfloat16(v);
+        hi[i] = h;
+        lo[i] = __float2bfloat16(v - __bfloat162float(h));
+    }
+}
+cudaError_t launch_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t n, cudaStream_t st) {
+    const int blocks = static_cast<int>((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+    split_bf16_kernel<<<blocks, 256, 0, st>>>(src, hi, lo, n);
+    return cudaGetLastError();
+}
+
+template <typename T>
+__global__ void pack_bf16_kernel(const T* __restrict__ src, long long sb, long long sn, long long sd, int B, int N, int D,
+                                 __nv_bfloat16* __restrict__ dst) {
+    const size_t total = static_cast<size_t>(B) * N * D;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int d = static_cast<int>(i % D);
+        const size_t r = i / D;
+        const int n = static_cast<int>(r % N), b = static_cast<int>(r / N);
+        dst[i] = __float2bfloat16(static_cast<float>(src[b * sb + n * sn + d * sd]));
+    }
+}
+cudaError_t launch_pack_bf16(const void* src, int src_is_bf16, long long sb, long long sn, long long sd, int B, int N, int D,
+                             __nv_bfloat16* dst, cudaStream_t st) {
+    const size_t total = static_cast<size_t>(B) * N * D;
+    const int blocks = static_cast<int>((total + 255) / 256 < 2368 ? (total + 255) / 256 : 2368);
+    if (src_is_bf16)
+        pack_bf16_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), sb, sn, sd, B, N, D, dst);
+    else
+        pack_bf16_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(src), sb, sn, sd, B, N, D, dst);
+    return cudaGetLastError();
+}
+
+// out[d] += sum over rows of X[row][d]; D % 8 == 0.  Thread = one 8-wide column vector of a row subset.
+__global__ void colsum_kernel(const __nv_bfloat16* __restrict__ X, size_t rows, int D, float* __restrict__ out) {
+    const int vpr = D / 8;                                   // vectors per row
+    const int rows_per_pass = blockDim.x / vpr;              // >= 1 (D <= 8 * blockDim)
+    const int lr = threadIdx.x / vpr, cv = threadIdx.x % vpr;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (lr < rows_per_pass) {
+        for (size_t r = static_cast<size_t>(blockIdx.x) * rows_per_pass + lr; r < rows; r += static_cast<size_t>(gridDim.x) * rows_per_pass) {
+            float f[8];
+            bf16x8_to_float(ld_nc_16(X + r * D + cv * 8), f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += f[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicAdd(out + cv * 8 + i, acc[i]);
+    }
+}
+cudaError_t launch_colsum(const __nv_bfloat16* X, size_t rows, int D, float* out, cudaStream_t st) {
+    if (D % 8 != 0 || D > 2048) return cudaErrorInvalidValue;
+    colsum_kernel<<<148, 256, 0, st>>>(X, rows, D, out);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------- importance mix
+// a[i][b][n] = normalise_n( interp( sum_j w[i][j] rows[j][b][:] )[n] );  ssum[i][b] = sum before normalising
+__global__ void importance_mix_kernel(const float* __restrict__ rows, const float* __restrict__ w, int Lt, int P, int B, int Nt,
+                                      int Ns, float* __restrict__ a, float* __restrict__ ssum) {
+    __shared__ float red[40];
+    const int i = blockIdx.x / B, b = blockIdx.x % B;
+    float part = 0.f;
+    float* out = a + static_cast<size_t>(blockIdx.x) * Ns;
+    for (int n = threadIdx.x; n < Ns; n += blockDim.x) {
+        int i0, i1; float lam;
+        interp_index(n, Nt, Ns, i0, i1, lam);
+        float v = 0.f;
+        for (int j = 0; j < Lt; ++j) {
+            const float* r = rows + (static_cast<size_t>(j) * B + b) * Nt;
+            v = fmaf(w[i * Lt + j], (1.f - lam) * r[i0] + lam * r[i1], v);
+        }
+        out[n] = v;
+        part += v;
+    }
+    const float tot = cta_sum(part, red);
+    for (int n = threadIdx.x; n < Ns; n += blockDim.x) out[n] = out[n] / tot;
+    if (threadIdx.x == 0) ssum[blockIdx.x] = tot;
+}
+cudaError_t launch_importance_mix(const float* rows, const float* w, int Lt, int P, int B, int Nt, int Ns, float* a, float* ssum,
+                                  cudaStream_t st) {
+    importance_mix_kernel<<<P * B, 256, 0, st>>>(rows, w, Lt, P, B, Nt, Ns, a, ssum);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------- mix teacher
+// Tbar[i][b][n][:] = sum_j w[i][j] * interp(T_j[b])[n][:]  -> bf16 hi + lo.  One thread = one 8-wide vector.
+template <int PMAX>
+__global__ void __launch_bounds__(256)
+mix_teacher_kernel(PtrTable teacher, const float* __restrict__ w, int Lt, int P, int B, int Nt, int Ns, int Dt,
+                   __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    __shared__ float ws[PMAX * kMaxLayers];
+    for (int t = threadIdx.x; t < P * Lt; t += blockDim.x) ws[t] = w[t];
+    __syncthreads();
+    const int vpr = Dt / 8;
+    const size_t per_sample = static_cast<size_t>(Ns) * vpr;
+    const size_t total = per_sample * B;
+    for (size_t v = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; v < total; v += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int b = static_cast<int>(v / per_sample);
+        const size_t rem = v % per_sample;
+        const int n = static_cast<int>(rem / vpr), dv = static_cast<int>(rem % vpr);
+        int i0, i1; float lam;
+        interp_index(n, Nt, Ns, i0, i1, lam);
+        float acc[PMAX][8];
+#pragma unroll
+        for (int i = 0; i < PMAX; ++i)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[i][e] = 0.f;
+        for (int j = 0; j < Lt; ++j) {
+            const __nv_bfloat16* T = reinterpret_cast<const __nv_bfloat16*>(teacher.p[j]) + (static_cast<size_t>(b) * Nt) * Dt + dv * 8;
+            float f[8];
+            bf16x8_to_float(ld_nc_16(T + static_cast<size_t>(i0) * Dt), f);
+            if (lam != 0.f) {
+                float g[8];
+                bf16x8_to_float(ld_nc_16(T + static_cast<size_t>(i1) * Dt), g);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = (1.f - lam) * f[e] + lam * g[e];
+            }
+#pragma unroll
+            for (int i = 0; i < PMAX; ++i) {
+                if (i < P) {
+                    const float wi = ws[i * Lt + j];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[i][e] = fmaf(wi, f[e], acc[i][e]);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < PMAX; ++i) {
+            if (i < P) {
+                const size_t off = ((static_cast<size_t>(i) * B + b) * Ns + n) * Dt + dv * 8;
+                float l[8];
+                uint4 h4, l4;
+                uint32_t* hp = reinterpret_cast<uint32_t*>(&h4);
+                uint32_t* lp = reinterpret_cast<uint32_t*>(&l4);
+#pragma unroll
+                for (int e = 0; e < 8; e += 2) {
+                    const __nv_bfloat16 h0 = __float2bfloat16(acc[i][e]), h1 = __float2bfloat16(acc[i][e + 1]);
+                    l[e] = acc[i][e] - __bfloat162float(h0);
+                    l[e + 1] = acc[i][e + 1] - __bfloat162float(h1);
+                    __nv_bfloat162 hv; hv.x = h0; hv.y = h1;
+                    hp[e / 2] = *reinterpret_cast<uint32_t*>(&hv);
+                    lp[e / 2] = pack2(l[e], l[e + 1]);
+                }
+                *reinterpret_cast<uint4*>(hi + off) = h4;
+                *reinterpret_cast<uint4*>(lo + off) = l4;
+            }
+        }
+    }
+}
+cudaError_t launch_mix_teacher(const PtrTable& teacher, const float* w, int Lt, int P, int B, int Nt, int Ns, int Dt,
+                               __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st) {
+    if (Dt % 8 != 0 || P > kMaxPoints) return cudaErrorInvalidValue;
+    const size_t total = static_cast<size_t>(B) * Ns * (Dt / 8);
+    const int blocks = static_cast<int>((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+    if (P <= 4)
+        mix_teacher_kernel<4><<<blocks, 256, 0, st>>>(teacher, w, Lt, P, B, Nt, Ns, Dt, hi, lo);
+    else
+        mix_teacher_kernel<8><<<blocks, 256, 0, st>>>(teacher, w, Lt, P, B, Nt, Ns, Dt, hi, lo);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------- d loss / d w
+// gw[i][j] += sum_{b,n,d} Dtm[i][b][n][d] * interp(T_j[b])[n][d]      blockIdx.y selects a (point-chunk, layer-chunk)
+constexpr int WG_PC = 4, WG_JC = 12;
+__global__ void __launch_bounds__(256)
+wgrad_dots_kernel(PtrTable teacher, const __nv_bfloat16* __restrict__ Dtm, int Lt, int P, int B, int Nt, int Ns, int Dt,
+                  float* __restrict__ gw) {
+    const int n_jc = (Lt + WG_JC - 1) / WG_JC;
+    const int i_base = (blockIdx.y / n_jc) * WG_PC, j_base = (blockIdx.y % n_jc) * WG_JC;
+    float acc[WG_PC][WG_JC];
+#pragma unroll
+    for (int i = 0; i < WG_PC; ++i)
+#pragma unroll
+        for (int j = 0; j < WG_JC; ++j) acc[i][j] = 0.f;
+    const int vpr = Dt / 8;
+    const size_t per_sample = static_cast<size_t>(Ns) * vpr;
+    const size_t total = per_sample * B;
+    for (size_t v = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; v < total; v += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int b = static_cast<int>(v / per_sample);
+        const size_t rem = v % per_sample;
+        const int n = static_cast<int>(rem / vpr), dv = static_cast<int>(rem % vpr);
+        int i0, i1; float lam;
+        interp_index(n, Nt, Ns, i0, i1, lam);
+        float dtv[WG_PC][8];
+#pragma unroll
+        for (int i = 0; i < WG_PC; ++i) {
+            if (i_base + i < P) {
+                bf16x8_to_float(ld_nc_16(Dtm + ((static_cast<size_t>(i_base + i) * B + b) * Ns + n) * Dt + dv * 8), dtv[i]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) dtv[i][e] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < WG_JC; ++j) {
+            if (j_base + j < Lt) {
+                const __nv_bfloat16* T = reinterpret_cast<const __nv_bfloat16*>(teacher.p[j_base + j]) + (static_cast<size_t>(b) * Nt) * Dt + dv * 8;
+                float f[8];
+                bf16x8_to_float(ld_nc_16(T + static_cast<size_t>(i0) * Dt), f);
+                if (lam != 0.f) {
+                    float g[8];
+                    bf16x8_to_float(ld_nc_16(T + static_cast<size_t>(i1) * Dt), g);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = (1.f - lam) * f[e] + lam * g[e];
+                }
+#pragma unroll
+                for (int i = 0; i < WG_PC; ++i) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) s = fmaf(dtv[i][e], f[e], s);
+                    acc[i][j] += s;
+                }
+            }
+        }
+    }
+    __shared__ float red[WG_PC * WG_JC];
+    for (int t = threadIdx.x; t < WG_PC * WG_JC; t += blockDim.x) red[t] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < WG_PC; ++i)
+#pragma unroll
+        for (int j = 0; j < WG_JC; ++j) {
+            const float s = warp_sum(acc[i][j]);
+            if ((threadIdx.x & 31) == 0) atomicAdd(&red[i * WG_JC + j], s);
+        }
+    __syncthreads();
+    for (int t = threadIdx.x; t < WG_PC * WG_JC; t += blockDim.x) {
+        const int i = i_base + t / WG_JC, j = j_base + t % WG_JC;
+        if (i < P && j < Lt) atomicAdd(&gw[i * Lt + j], red[t]);
+    }
+}
+// gw[i][j] += sum_{b,n} gwt[i][b][n] * interp(rows[j][b])[n]
+__global__ void wgrad_importance_kernel(const float* __restrict__ gwt, const float* __restrict__ rows, int Lt, int P, int B, int Nt,
+                                        int Ns, float* __restrict__ gw) {
+    __shared__ float red[40];
+    const int i = blockIdx.x / Lt, j = blockIdx.x % Lt;
+    float part = 0.f;
+    for (int t = threadIdx.x; t < B * Ns; t += blockDim.x) {
+        const int b = t / Ns, n = t % Ns;
+        int i0, i1; float lam;
+        interp_index(n, Nt, Ns, i0, i1, lam);
+        const float* r = rows + (static_cast<size_t>(j) * B + b) * Nt;
+        part = fmaf(gwt[(static_cast<size_t>(i) * B + b) * Ns + n], (1.f - lam) * r[i0] + lam * r[i1], part);
+    }
+    const float tot = cta_sum(part, red);
+    if (threadIdx.x == 0) atomicAdd(&gw[i * Lt + j], tot);
+}
+cudaError_t launch_wgrad_dots(const PtrTable& teacher, const __nv_bfloat16* Dtm, const float* gwt, const float* rows, int Lt, int P,
+                              int B, int Nt, int Ns, int Dt, float* gw, cudaStream_t st) {
+    if (Dt % 8 != 0) return cudaErrorInvalidValue;
+    const int ny = ((P + WG_PC - 1) / WG_PC) * ((Lt + WG_JC - 1) / WG_JC);
+    wgrad_dots_kernel<<<dim3(148 * 4, ny), 256, 0, st>>>(teacher, Dtm, Lt, P, B, Nt, Ns, Dt, gw);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    wgrad_importance_kernel<<<P * Lt, 256, 0, st>>>(gwt, rows, Lt, P, B, Nt, Ns, gw);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------- loss reduce
+__global__ void loss_reduce_kernel(const float* __restrict__ loss_b, int P, int B, float* __restrict__ geo_i, float* __restrict__ geo) {
+    __shared__ float red[40];
+    float total = 0.f;
+    for (int i = 0; i < P; ++i) {
+        float part = 0.f;
+        for (int b = threadIdx.x; b < B; b += blockDim.x) part += loss_b[i * B + b];
+        const float s = cta_sum(part, red) / static_cast<float>(B);
+        if (threadIdx.x == 0) geo_i[i] = s;
+        total += s;
+    }
+    if (threadIdx.x == 0) *geo = total / static_cast<float>(P);
+}
+cudaError_t launch_loss_reduce(const float* loss_b, int P, int B, float* geo_i, float* geo, cudaStream_t st) {
+    loss_reduce_kernel<<<1, 256, 0, st>>>(loss_b, P, B, geo_i, geo);
+    return cudaGetLastError();
+}
+
+}  // namespace basd

@@ -1,0 +1,310 @@
+// Warp-specialised tcgen05 GEMM for sm_100a: TMA (SWIZZLE_128B) -> shared memory ring -> tcgen05.mma
+// (bf16 x bf16 -> fp32 in TMEM) -> tcgen05.ld epilogue.  One CTA = MT x (128 x BN) output tiles.
+//
+// Every dense contraction of the BASD loss path is an instance (see gemm_ops.cu):
+//   project      Z = X P_t^T                 (replaces layer_selector.py:72,135)      A,B K-major
+//   gram         G += Z_chunk^T Z_chunk      (replaces layer_selector.py:13,36,92)    A,B MN-major, split-K
+//   token_gram   K = T T^T per sample        (relational.py:47 moved to token space)  A,B K-major, B aliases A
+//   theta_apply  D = Theta T per sample      (closed-form backward)    A K-major, B MN-major
+//   student_grad dS = S Gamma + ...                                    A,B K-major
+// "Split-bf16" terms (hi/lo operand pairs) accumulate into the same TMEM tile to recover fp32-class
+// accuracy from bf16 tensor-core passes.
+#pragma once
+#include "ptx.cuh"
+
+namespace basd {
+
+constexpr int GEMM_BK = 64;           // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int GEMM_THREADS = 192;     // warp0 TMA, warp1 MMA, warps2-5 epilogue
+
+struct GemmMaps {                     // up to two A and two B operand buffers (hi / lo)
+    CUtensorMap a[2];
+    CUtensorMap b[2];
+};
+
+struct GemmArgs {
+    int kb_total;        // number of 64-wide k-blocks
+    int kb_per_split;    // split-K: k-blocks per split (0 = no split, blockIdx.z is the batch index)
+    int n_splits;        // split-K: blockIdx.z = batch * n_splits + split
+    int a_batched;       // A uses blockIdx.z as 3rd TMA coordinate
+    int b_batched;       // B uses blockIdx.z as 3rd TMA coordinate
+    // epilogue
+    void* out;           // primary output
+    long long out_batch_stride;   // elements
+    int ld_out;          // elements
+    int rows_valid;      // rows of the (per-batch) output that exist
+    int cols_valid;
+    const void* aux0;    // epilogue specific
+    const void* aux1;
+    const void* aux2;
+    long long aux_batch_stride;
+    float alpha;
+    float beta;
+};
+
+template <bool A_MN, bool B_MN, int BN, int MT, int NA, int NB, int NTERMS, bool B_ALIAS_A, int STAGES>
+struct GemmCfg {
+    static constexpr bool kAMN = A_MN, kBMN = B_MN, kAlias = B_ALIAS_A;
+    static constexpr int kBN = BN, kMT = MT, kNA = NA, kNB = NB, kTerms = NTERMS, kStages = STAGES;
+    static constexpr int kABytes = MT * 128 * 128;                    // per A buffer per stage
+    static constexpr int kBBytes = B_ALIAS_A ? 0 : BN * 128;          // per B buffer per stage
+    static constexpr int kStageBytes = NA * kABytes + NB * kBBytes;
+    static constexpr int kTmemCols = (MT * BN <= 32) ? 32 : (MT * BN <= 64) ? 64 : (MT * BN <= 128) ? 128 : (MT * BN <= 256) ? 256 : 512;
+    static constexpr int kSmemBytes = STAGES * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+    static_assert(MT * BN <= 512, "accumulators exceed TMEM");
+    static_assert(BN % 16 == 0 && BN <= 256, "invalid UMMA N");
+    static_assert(!B_MN || BN % 64 == 0, "MN-major B needs 64-wide groups");
+    static_assert(!B_ALIAS_A || (!A_MN && !B_MN && BN <= MT * 128), "alias needs K-major operands");
+    static_assert(kSmemBytes <= 232448, "shared memory budget");
+};
+
+// term t multiplies A[a_sel] by B[b_sel]:  t=0 (0,0)  t=1 (0,1)  t=2 (1,0)   (hi*hi, hi*lo, lo*hi)
+__device__ __forceinline__ int term_a(int t) { return t == 2 ? 1 : 0; }
+__device__ __forceinline__ int term_b(int t) { return t == 1 ? 1 : 0; }
+
+template <class Cfg, class Epi>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+umma_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+    uint64_t* empty_bar = full_bar + Cfg::kStages;
+    uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int z = blockIdx.z;
+    int kb0 = 0, kb1 = args.kb_total;
+    int batch = z;
+    if (args.kb_per_split > 0) {
+        batch = z / args.n_splits;
+        kb0 = (z % args.n_splits) * args.kb_per_split;
+        kb1 = min(args.kb_total, kb0 + args.kb_per_split);
+    }
+    const int a_row0 = blockIdx.y * (Cfg::kMT * 128);
+    const int b_row0 = blockIdx.x * Cfg::kBN;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < Cfg::kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        fence_mbar_init();
+        for (int i = 0; i < Cfg::kNA; ++i) tma_prefetch_desc(&maps.a[i]);
+        if (!Cfg::kAlias)
+            for (int i = 0; i < Cfg::kNB; ++i) tma_prefetch_desc(&maps.b[i]);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            const int za = args.a_batched ? batch : 0;
+            const int zb = args.b_batched ? batch : 0;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                const int it = kb - kb0;
+                const int s = it % Cfg::kStages;
+                const uint32_t ph = (it / Cfg::kStages) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+                uint8_t* st = smem + s * Cfg::kStageBytes;
+#pragma unroll
+                for (int i = 0; i < Cfg::kNA; ++i) {
+                    uint8_t* dst = st + i * Cfg::kABytes;
+                    if (Cfg::kAMN) {
+#pragma unroll
+                        for (int g = 0; g < Cfg::kMT * 2; ++g)
+                            tma_load_3d(dst + g * 8192, &maps.a[i], &full_bar[s], a_row0 + g * 64, kb * GEMM_BK, za);
+                    } else {
+#pragma unroll
+                        for (int mt = 0; mt < Cfg::kMT; ++mt)
+                            tma_load_3d(dst + mt * 16384, &maps.a[i], &full_bar[s], kb * GEMM_BK, a_row0 + mt * 128, za);
+                    }
+                }
+                if (!Cfg::kAlias) {
+#pragma unroll
+                    for (int i = 0; i < Cfg::kNB; ++i) {
+                        uint8_t* dst = st + Cfg::kNA * Cfg::kABytes + i * Cfg::kBBytes;
+                        if (Cfg::kBMN) {
+#pragma unroll
+                            for (int g = 0; g < Cfg::kBN / 64; ++g)
+                                tma_load_3d(dst + g * 8192, &maps.b[i], &full_bar[s], b_row0 + g * 64, kb * GEMM_BK, zb);
+                        } else {
+                            tma_load_3d(dst, &maps.b[i], &full_bar[s], kb * GEMM_BK, b_row0, zb);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (one elected lane)
+        constexpr uint32_t idesc = umma_idesc_bf16(128, Cfg::kBN, Cfg::kAMN, Cfg::kBMN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+            const int it = kb - kb0;
+            const int s = it % Cfg::kStages;
+            const uint32_t ph = (it / Cfg::kStages) & 1;
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t st = smem_u32(smem + s * Cfg::kStageBytes);
+#pragma unroll
+                for (int mt = 0; mt < Cfg::kMT; ++mt) {
+#pragma unroll
+                    for (int t = 0; t < Cfg::kTerms; ++t) {
+                        const uint32_t a_base = st + term_a(t) * Cfg::kABytes + mt * 16384;
+                        const uint32_t b_base = Cfg::kAlias ? (st + term_b(t) * Cfg::kABytes)
+                                                            : (st + Cfg::kNA * Cfg::kABytes + term_b(t) * Cfg::kBBytes);
+#pragma unroll
+                        for (int ks = 0; ks < GEMM_BK / 16; ++ks) {
+                            const uint64_t adesc = Cfg::kAMN ? umma_smem_desc(a_base + ks * 2048, 8192, 1024)
+                                                             : umma_smem_desc(a_base + ks * 32, 16, 1024);
+                            const uint64_t bdesc = Cfg::kBMN ? umma_smem_desc(b_base + ks * 2048, 8192, 1024)
+                                                             : umma_smem_desc(b_base + ks * 32, 16, 1024);
+                            umma_bf16(tmem_base + mt * Cfg::kBN, adesc, bdesc, idesc, (it > 0 || t > 0 || ks > 0) ? 1u : 0u);
+                        }
+                    }
+                }
+                umma_commit(&empty_bar[s]);                 // frees the smem slot when these MMAs retire
+                if (kb == kb1 - 1) umma_commit(tmem_full_bar);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
+        if (kb1 > kb0) {
+            mbar_wait(tmem_full_bar, 0);
+            tc_fence_after();
+            const int q = warp & 3;                          // TMEM lane quadrant this warp may read
+            Epi epi(args, batch, z);
+#pragma unroll 1
+            for (int mt = 0; mt < Cfg::kMT; ++mt) {
+                const int row = a_row0 + mt * 128 + q * 32 + lane;
+#pragma unroll 1
+                for (int c = 0; c < Cfg::kBN; c += 16) {
+                    float v[16];
+                    tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + mt * Cfg::kBN + c, v);
+                    epi(row, b_row0 + c, v);
+                }
+            }
+            tc_fence_before();
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Epilogues.  operator()(row, col0, v[16]) handles 16 consecutive columns of one output row.
+// ---------------------------------------------------------------------------------------------------
+struct EpiStoreBf16 {                     // out[batch][row][col] = bf16(alpha * acc)
+    __nv_bfloat16* out; int ld, rows, cols; float alpha;
+    __device__ EpiStoreBf16(const GemmArgs& a, int batch, int) {
+        out = reinterpret_cast<__nv_bfloat16*>(a.out) + batch * a.out_batch_stride;
+        ld = a.ld_out; rows = a.rows_valid; cols = a.cols_valid; alpha = a.alpha;
+    }
+    __device__ void operator()(int row, int col0, const float* v) const {
+        if (row >= rows || col0 >= cols) return;
+        __nv_bfloat16* p = out + static_cast<long long>(row) * ld + col0;
+        if (col0 + 16 <= cols) {
+            uint4 w0, w1;
+            w0.x = pack_bf16x2(alpha * v[0], alpha * v[1]);   w0.y = pack_bf16x2(alpha * v[2], alpha * v[3]);
+            w0.z = pack_bf16x2(alpha * v[4], alpha * v[5]);   w0.w = pack_bf16x2(alpha * v[6], alpha * v[7]);
+            w1.x = pack_bf16x2(alpha * v[8], alpha * v[9]);   w1.y = pack_bf16x2(alpha * v[10], alpha * v[11]);
+            w1.z = pack_bf16x2(alpha * v[12], alpha * v[13]); w1.w = pack_bf16x2(alpha * v[14], alpha * v[15]);
+            reinterpret_cast<uint4*>(p)[0] = w0;
+            reinterpret_cast<uint4*>(p)[1] = w1;
+        } else {
+            for (int i = 0; i < 16 && col0 + i < cols; ++i) p[i] = __float2bfloat16(alpha * v[i]);
+        }
+    }
+};
+
+struct EpiStoreF32 {                      // out[batch][row][col] = alpha * acc
+    float* out; int ld, rows, cols; float alpha;
+    __device__ EpiStoreF32(const GemmArgs& a, int batch, int) {
+        out = reinterpret_cast<float*>(a.out) + batch * a.out_batch_stride;
+        ld = a.ld_out; rows = a.rows_valid; cols = a.cols_valid; alpha = a.alpha;
+    }
+    __device__ void operator()(int row, int col0, const float* v) const {
+        if (row >= rows || col0 >= cols) return;
+        float* p = out + static_cast<long long>(row) * ld + col0;
+        if (col0 + 16 <= cols && (ld & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                reinterpret_cast<float4*>(p)[i] = make_float4(alpha * v[4 * i], alpha * v[4 * i + 1], alpha * v[4 * i + 2], alpha * v[4 * i + 3]);
+        } else {
+            for (int i = 0; i < 16 && col0 + i < cols; ++i) p[i] = alpha * v[i];
+        }
+    }
+};
+
+struct EpiAtomicAddF32 {                  // split-K partial: out[row][col] += acc   (out pre-zeroed)
+    float* out; int ld, rows, cols;
+    __device__ EpiAtomicAddF32(const GemmArgs& a, int batch, int) {
+        out = reinterpret_cast<float*>(a.out) + batch * a.out_batch_stride; ld = a.ld_out; rows = a.rows_valid; cols = a.cols_valid;
+    }
+    __device__ void operator()(int row, int col0, const float* v) const {
+        if (row >= rows) return;
+        float* p = out + static_cast<long long>(row) * ld + col0;
+        for (int i = 0; i < 16 && col0 + i < cols; ++i) atomicAdd(p + i, v[i]);
+    }
+};
+
+// theta_apply: out = bf16( 2 * (acc - a[row] * mu_t[col]) )    aux0 = a [batch][rows], aux1 = mu_t [batch][cols]
+struct EpiThetaApply {
+    __nv_bfloat16* out; const float* a; const float* mu; int ld, rows, cols;
+    __device__ EpiThetaApply(const GemmArgs& g, int batch, int) {
+        out = reinterpret_cast<__nv_bfloat16*>(g.out) + batch * g.out_batch_stride;
+        a = reinterpret_cast<const float*>(g.aux0) + static_cast<long long>(batch) * g.rows_valid;
+        mu = reinterpret_cast<const float*>(g.aux1) + static_cast<long long>(batch) * g.cols_valid;
+        ld = g.ld_out; rows = g.rows_valid; cols = g.cols_valid;
+    }
+    __device__ void operator()(int row, int col0, const float* v) const {
+        if (row >= rows || col0 >= cols) return;
+        const float ar = a[row];
+        __nv_bfloat16* p = out + static_cast<long long>(row) * ld + col0;
+        for (int i = 0; i < 16 && col0 + i < cols; i += 2) {
+            const float x0 = 2.f * (v[i] - ar * mu[col0 + i]);
+            const float x1 = 2.f * (v[i + 1] - ar * mu[col0 + i + 1]);
+            *reinterpret_cast<uint32_t*>(p + i) = pack_bf16x2(x0, x1);
+        }
+    }
+};
+
+// student_grad: out[row][col] = alpha * gdir[row][col] + acc - corr[col]
+//   aux0 = gdir fp32 [rows][cols] (direct-path gradient, unscaled), aux1 = corr fp32 [cols] (= mu^T Gamma)
+//   out dtype: beta == 0 -> fp32, beta == 1 -> bf16
+struct EpiStudentGrad {
+    void* out; const float* gdir; const float* corr; int ld, rows, cols; float alpha; bool bf16_out;
+    __device__ EpiStudentGrad(const GemmArgs& g, int, int) {
+        out = g.out; gdir = reinterpret_cast<const float*>(g.aux0); corr = reinterpret_cast<const float*>(g.aux1);
+        ld = g.ld_out; rows = g.rows_valid; cols = g.cols_valid; bf16_out = g.beta != 0.f;
+        alpha = g.alpha * (g.aux2 ? *reinterpret_cast<const float*>(g.aux2) : 1.f);
+    }
+    __device__ void operator()(int row, int col0, const float* v) const {
+        if (row >= rows || col0 >= cols) return;
+        const long long off = static_cast<long long>(row) * ld + col0;
+        float r[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = 0.f;
+        for (int i = 0; i < 16 && col0 + i < cols; ++i) r[i] = alpha * gdir[static_cast<long long>(row) * cols + col0 + i] + v[i] - corr[col0 + i];
+        if (bf16_out) {
+            __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(out) + off;
+            for (int i = 0; i < 16 && col0 + i < cols; ++i) p[i] = __float2bfloat16(r[i]);
+        } else {
+            float* p = reinterpret_cast<float*>(out) + off;
+            for (int i = 0; i < 16 && col0 + i < cols; ++i) p[i] = r[i];
+        }
+    }
+};
+
+}  // namespace basd

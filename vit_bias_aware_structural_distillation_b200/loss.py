@@ -1,0 +1,304 @@
+"""Drop-in replacement for the reference's `src/losses` package (BASD distillation loss), running the whole
+selector + interpolation + Procrustes path and its analytic backward as sm_100a CUDA kernels behind the C ABI of
+include/basd_b200.h.
+
+Mirrors, with the same names / argument meaning / state_dict keys:
+  * BASDLoss                      /root/reference/src/losses/combined.py:17-85
+  * GrassmannianLayerSelector     /root/reference/src/losses/layer_selector.py:40-152
+  * marchenko_pastur_rank         /root/reference/src/losses/layer_selector.py:8-20
+  * geometric_relational_loss is not exposed on its own: it is fused with the selector (shared statistics).
+
+CE (`base_criterion`) and the two-scalar UW-SO weighting (combined.py:56,78-85) stay stock PyTorch so that any
+criterion and soft or hard targets keep working; everything between them is one custom op, `basd_b200::geo_forward`,
+with a registered backward op `basd_b200::geo_backward` (no autograd through LAPACK).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import List, Sequence
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+from ._lib import DTYPE_BF16, DTYPE_F32, Inputs, Shape
+
+
+# --------------------------------------------------------------------------------------------- low-level plumbing
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return DTYPE_F32
+    if t.dtype == torch.bfloat16:
+        return DTYPE_BF16
+    raise _lib.BasdError(f"unsupported dtype {t.dtype} (float32 or bfloat16 expected)")
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _prepare(students: Sequence[torch.Tensor], teachers: Sequence[torch.Tensor], attns: Sequence[torch.Tensor],
+             proj_s: torch.Tensor, proj_t: torch.Tensor, log_temperatures: torch.Tensor, has_cls: bool, world_size: int):
+    """Builds the C structs.  Returns (shape, inputs, keepalive) — keepalive holds every tensor whose pointer is used."""
+    if not students or not teachers or len(teachers) != len(attns):
+        raise _lib.BasdError("need >= 1 student tensor, >= 1 teacher tensor and one attention map per teacher layer")
+    dev = students[0].device
+    if dev.type != "cuda":
+        raise _lib.BasdError("the BASD loss path runs on a CUDA device only (no CPU fallback); got tensors on " + str(dev))
+    act_dt = students[0].dtype
+    if act_dt not in (torch.float32, torch.bfloat16):
+        students = [s.float() for s in students]
+        act_dt = torch.float32
+    teachers = [t if t.dtype == act_dt else t.to(act_dt) for t in teachers]
+    students = [s if s.dtype == act_dt else s.to(act_dt) for s in students]
+    if act_dt == torch.bfloat16:            # bf16 operands are consumed in place by TMA and must be dense
+        students = [s.contiguous() for s in students]
+        teachers = [t.contiguous() for t in teachers]
+    else:                                   # fp32: the pack kernel reads through arbitrary strides; equalise them
+        if len({s.stride() for s in students}) > 1:
+            students = [s.contiguous() for s in students]
+        if len({t.stride() for t in teachers}) > 1:
+            teachers = [t.contiguous() for t in teachers]
+    att_dt = attns[0].dtype if attns[0].dtype in (torch.float32, torch.bfloat16) else torch.float32
+    attns = [a if a.dtype == att_dt else a.to(att_dt) for a in attns]
+    if len({a.stride() for a in attns}) > 1:
+        attns = [a.contiguous() for a in attns]
+    B, Ns, Ds = students[0].shape
+    Bt, Nt, Dt = teachers[0].shape
+    if Bt != B:
+        raise _lib.BasdError("student and teacher batch sizes differ")
+    H = attns[0].shape[1]
+    exp_attn = (B, H, Nt + 1, Nt + 1) if has_cls else (B, H, Nt, Nt)
+    if tuple(attns[0].shape) != exp_attn:
+        raise _lib.BasdError(f"attention shape {tuple(attns[0].shape)} != expected {exp_attn}")
+    proj_s = proj_s.detach().to(device=dev, dtype=torch.float32).contiguous()
+    proj_t = proj_t.detach().to(device=dev, dtype=torch.float32).contiguous()
+    logt = log_temperatures.detach().to(device=dev, dtype=torch.float32).contiguous()
+    shape = Shape(B=B, Ns=Ns, Nt=Nt, Ds=Ds, Dt=Dt, Lt=len(teachers), P=len(students), H=H, has_cls=int(has_cls),
+                  act_dtype=_dtype_code(students[0]), attn_dtype=_dtype_code(attns[0]), world_size=world_size)
+    inp = Inputs()
+    for i, s in enumerate(students):
+        inp.student[i] = s.data_ptr()
+    for j, (t, a) in enumerate(zip(teachers, attns)):
+        inp.teacher[j] = t.data_ptr()
+        inp.attn[j] = a.data_ptr()
+    for k in range(3):
+        inp.student_strides[k] = students[0].stride(k)
+        inp.teacher_strides[k] = teachers[0].stride(k)
+    for k in range(4):
+        inp.attn_strides[k] = attns[0].stride(k)
+    inp.proj_s, inp.proj_t, inp.log_temperatures = proj_s.data_ptr(), proj_t.data_ptr(), logt.data_ptr()
+    keep = (students, teachers, attns, proj_s, proj_t, logt)
+    return shape, inp, keep
+
+
+def workspace_view(shape: Shape, ws: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
+    """Typed view of a named workspace region (tests, collectives)."""
+    lib = _lib.load()
+    ptr, cnt = ctypes.c_void_p(), ctypes.c_size_t()
+    _lib.check(lib.basd_view(ctypes.byref(shape), ws.data_ptr(), name.encode(), ctypes.byref(ptr), ctypes.byref(cnt)), "basd_view")
+    off = ptr.value - ws.data_ptr()
+    nbytes = cnt.value * torch.empty((), dtype=dtype).element_size()
+    return ws[off:off + nbytes].view(dtype)
+
+
+def _world():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist, dist.get_world_size()
+    return None, 1
+
+
+def _allreduce_sum(dist, t: torch.Tensor):
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+
+# --------------------------------------------------------------------------------------------- custom ops
+@torch.library.custom_op("basd_b200::geo_forward", mutates_args=())
+def geo_forward(students: List[torch.Tensor], teachers: List[torch.Tensor], attns: List[torch.Tensor], proj_s: torch.Tensor,
+                proj_t: torch.Tensor, log_temperatures: torch.Tensor, has_cls: bool) -> List[torch.Tensor]:
+    """Returns [geo_loss (0-dim fp32), workspace (uint8), ranks (int32 [Lt]), mixing weights (fp32 [P, Lt])]."""
+    lib = _lib.load()
+    dist, world = _world()
+    shape, inp, keep = _prepare(students, teachers, attns, proj_s, proj_t, log_temperatures, has_cls, world)
+    nbytes = ctypes.c_size_t()
+    _lib.check(lib.basd_workspace_bytes(ctypes.byref(shape), ctypes.byref(nbytes)), "basd_workspace_bytes")
+    dev = students[0].device
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+    geo = torch.empty((), dtype=torch.float32, device=dev)
+    st = _stream_ptr()
+    _lib.check(lib.basd_forward_stats(ctypes.byref(shape), ctypes.byref(inp), ws.data_ptr(), st), "basd_forward_stats")
+    if dist is not None:
+        _allreduce_sum(dist, workspace_view(shape, ws, "stats"))
+    _lib.check(lib.basd_forward_solve(ctypes.byref(shape), ctypes.byref(inp), ws.data_ptr(), geo.data_ptr(), st), "basd_forward_solve")
+    ranks = workspace_view(shape, ws, "ranks", torch.int32).clone()
+    w = workspace_view(shape, ws, "w").clone().view(shape.P, shape.Lt)
+    del keep
+    return [geo, ws, ranks, w]
+
+
+@geo_forward.register_fake
+def _(students, teachers, attns, proj_s, proj_t, log_temperatures, has_cls):
+    dev = students[0].device
+    return [torch.empty((), dtype=torch.float32, device=dev), torch.empty(1, dtype=torch.uint8, device=dev),
+            torch.empty(len(teachers), dtype=torch.int32, device=dev),
+            torch.empty(len(students), len(teachers), dtype=torch.float32, device=dev)]
+
+
+@torch.library.custom_op("basd_b200::geo_backward", mutates_args=("workspace",))
+def geo_backward(grad_geo: torch.Tensor, workspace: torch.Tensor, students: List[torch.Tensor], teachers: List[torch.Tensor],
+                 attns: List[torch.Tensor], proj_s: torch.Tensor, proj_t: torch.Tensor, log_temperatures: torch.Tensor,
+                 has_cls: bool) -> List[torch.Tensor]:
+    """Returns [grad_log_temperatures, grad_student_0, ..., grad_student_{P-1}]."""
+    lib = _lib.load()
+    dist, world = _world()
+    shape, inp, keep = _prepare(students, teachers, attns, proj_s, proj_t, log_temperatures, has_cls, world)
+    dev = students[0].device
+    st = _stream_ptr()
+    g = grad_geo.detach().to(device=dev, dtype=torch.float32).contiguous()
+    _lib.check(lib.basd_backward_dots(ctypes.byref(shape), ctypes.byref(inp), workspace.data_ptr(), st), "basd_backward_dots")
+    if dist is not None:
+        _allreduce_sum(dist, workspace_view(shape, workspace, "gw"))
+    out_dtype = students[0].dtype if students[0].dtype in (torch.float32, torch.bfloat16) else torch.float32
+    grads = [torch.empty(s.shape, dtype=out_dtype, device=dev) for s in students]
+    glt = torch.empty(shape.P, dtype=torch.float32, device=dev)
+    ptrs = (ctypes.c_void_p * len(grads))(*[t.data_ptr() for t in grads])
+    _lib.check(lib.basd_backward_finish(ctypes.byref(shape), ctypes.byref(inp), workspace.data_ptr(), g.data_ptr(), ptrs,
+                                        DTYPE_BF16 if out_dtype == torch.bfloat16 else DTYPE_F32, glt.data_ptr(), st),
+               "basd_backward_finish")
+    if world > 1:
+        glt = glt / world          # every rank holds the summed gradient; keep the DDP-average convention
+    del keep
+    return [glt] + grads
+
+
+@geo_backward.register_fake
+def _(grad_geo, workspace, students, teachers, attns, proj_s, proj_t, log_temperatures, has_cls):
+    return [torch.empty_like(log_temperatures, dtype=torch.float32)] + [torch.empty_like(s) for s in students]
+
+
+def _setup_context(ctx, inputs, output):
+    students, teachers, attns, proj_s, proj_t, log_temperatures, has_cls = inputs
+    ctx.n_students, ctx.n_teachers = len(students), len(teachers)
+    ctx.has_cls = has_cls
+    ctx.student_dtypes = [s.dtype for s in students]
+    ctx.save_for_backward(output[1], proj_s, proj_t, log_temperatures, *students, *teachers, *attns)
+
+
+def _backward(ctx, grads):
+    grad_geo = grads[0]
+    saved = ctx.saved_tensors
+    ws, proj_s, proj_t, logt = saved[:4]
+    P, Lt = ctx.n_students, ctx.n_teachers
+    students = list(saved[4:4 + P])
+    teachers = list(saved[4 + P:4 + P + Lt])
+    attns = list(saved[4 + P + Lt:4 + P + 2 * Lt])
+    if grad_geo is None:
+        grad_geo = torch.zeros((), device=ws.device)
+    out = geo_backward(grad_geo, ws, students, teachers, attns, proj_s, proj_t, logt, ctx.has_cls)
+    gs = [g.to(dt) if g.dtype != dt else g for g, dt in zip(out[1:], ctx.student_dtypes)]
+    return gs, None, None, None, None, out[0].to(logt.dtype), None
+
+
+geo_forward.register_autograd(_backward, setup_context=_setup_context)
+
+
+# --------------------------------------------------------------------------------------------- reference API
+def marchenko_pastur_rank(features: torch.Tensor) -> int:
+    """layer_selector.py:8-20 on the GPU (tcgen05 Gram + shared-memory Jacobi).  features: [M, D], D <= 224."""
+    lib = _lib.load()
+    if features.device.type != "cuda":
+        raise _lib.BasdError("marchenko_pastur_rank: CUDA tensor required (no CPU fallback)")
+    if features.dtype not in (torch.float32, torch.bfloat16):
+        features = features.float()
+    if features.stride(1) != 1:
+        features = features.contiguous()
+    M, D = features.shape
+    nb = ctypes.c_size_t()
+    _lib.check(lib.basd_mp_rank_workspace_bytes(M, D, ctypes.byref(nb)), "basd_mp_rank_workspace_bytes")
+    ws = torch.empty(nb.value, dtype=torch.uint8, device=features.device)
+    out = torch.zeros(1, dtype=torch.int32, device=features.device)
+    _lib.check(lib.basd_mp_rank(features.data_ptr(), M, D, _dtype_code(features), features.stride(0), out.data_ptr(), ws.data_ptr(),
+                                _stream_ptr()), "basd_mp_rank")
+    return int(out.item())
+
+
+class GrassmannianLayerSelector(nn.Module):
+    """Same constructor, buffers (`proj_s`, `proj_t`) and parameter (`log_temperatures`) as layer_selector.py:40-63."""
+
+    def __init__(self, num_extraction_points: int, student_dim: int, teacher_dim: int):
+        super().__init__()
+        self.student_dim = student_dim
+        self._ranks_dev = None
+        self._rank_keys: list[int] = []
+        self.last_mixing_weights = None
+        proj_s = torch.empty(student_dim, student_dim)
+        proj_t = torch.empty(student_dim, teacher_dim)
+        nn.init.orthogonal_(proj_s)
+        nn.init.orthogonal_(proj_t)
+        self.register_buffer("proj_s", proj_s)
+        self.register_buffer("proj_t", proj_t)
+        self.log_temperatures = nn.Parameter(torch.full((num_extraction_points,), math.log(math.exp(1.0) - 1)))
+
+    @property
+    def temperatures(self) -> torch.Tensor:
+        return F.softplus(self.log_temperatures)
+
+    @property
+    def subspace_ranks(self) -> dict:
+        """layer_selector.py:49,74 — ranks of the last forward.  Kept on the device; reading this syncs once."""
+        if self._ranks_dev is None:
+            return {}
+        return dict(zip(self._rank_keys, self._ranks_dev.tolist()))
+
+
+class BASDLoss(nn.Module):
+    """Drop-in for combined.py:17-85 (same constructor and forward signature, `token_layers`, state_dict keys)."""
+
+    def __init__(self, base_criterion: nn.Module, student_dim: int, teacher_dim: int, student_depth: int,
+                 num_student_tokens: int, *, config, teacher_has_cls_token: bool):
+        super().__init__()
+        self.base_criterion = base_criterion
+        self.teacher_has_cls_token = teacher_has_cls_token
+        self.num_student_tokens = num_student_tokens
+        if config.num_extraction_points == 1:
+            self.token_layers = [student_depth - 1]
+        else:
+            self.token_layers = [round(i * (student_depth - 1) / (config.num_extraction_points - 1))
+                                 for i in range(config.num_extraction_points)]
+        self.layer_selector = GrassmannianLayerSelector(num_extraction_points=len(self.token_layers),
+                                                        student_dim=student_dim, teacher_dim=teacher_dim)
+        self.last_geo_loss = None
+        self.last_ce_loss = None
+
+    def geo_loss(self, student_intermediates, all_teacher_tokens, all_teacher_attns) -> torch.Tensor:
+        sel = self.layer_selector
+        t_idx = sorted(all_teacher_tokens.keys())
+        students = [student_intermediates[l] for l in self.token_layers]
+        if students[0].shape[1] != self.num_student_tokens:
+            raise _lib.BasdError(f"student tensors carry {students[0].shape[1]} tokens, module was built for {self.num_student_tokens}")
+        teachers = [all_teacher_tokens[j] for j in t_idx]
+        attns = [all_teacher_attns[j] for j in t_idx]
+        geo, _ws, ranks, w = geo_forward(students, teachers, attns, sel.proj_s, sel.proj_t, sel.log_temperatures,
+                                         bool(self.teacher_has_cls_token))
+        sel._ranks_dev, sel._rank_keys = ranks, t_idx
+        sel.last_mixing_weights = w
+        return geo
+
+    def forward(self, student_output, targets, student_intermediates, all_teacher_tokens, all_teacher_attns):
+        ce_loss = self.base_criterion(student_output, targets)
+        geo_loss = self.geo_loss(student_intermediates, all_teacher_tokens, all_teacher_attns)
+        self.last_geo_loss, self.last_ce_loss = geo_loss.detach(), ce_loss.detach()
+        vals = [ce_loss, geo_loss.to(ce_loss.dtype) if ce_loss.dtype != geo_loss.dtype else geo_loss]
+        det = [v.detach() for v in vals]
+        dist, world = _world()
+        if dist is not None:               # UW-SO weights from the global means (single-process semantics)
+            pair = torch.stack([d.float() for d in det])
+            dist.all_reduce(pair, op=dist.ReduceOp.SUM)
+            det = [(pair[i] / world).to(vals[i].dtype) for i in range(2)]
+        eps = torch.finfo(vals[0].dtype).eps
+        inv = torch.stack([1.0 / d.clamp(min=eps) for d in det])            # combined.py:78-85
+        wts = inv / inv.sum()
+        return sum(wts[i] * vals[i] for i in range(len(vals)))
