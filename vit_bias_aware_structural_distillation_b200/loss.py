@@ -199,7 +199,7 @@ def _backward(ctx, grads):
         grad_geo = torch.zeros((), device=ws.device)
     out = geo_backward(grad_geo, ws, students, teachers, attns, proj_s, proj_t, logt, ctx.has_cls)
     gs = [g.to(dt) if g.dtype != dt else g for g, dt in zip(out[1:], ctx.student_dtypes)]
-    return gs, None, None, None, None, out[0].to(logt.dtype), None
+    return gs, [None] * Lt, [None] * Lt, None, None, out[0].to(logt.dtype), None
 
 
 geo_forward.register_autograd(_backward, setup_context=_setup_context)
