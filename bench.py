@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py — BASD loss fwd+bwd samples/s (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path  (one JSON line on rank 0)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own PyTorch loss on the host CPU cores
+
+A "step" is one forward + backward of the BASD loss (selector + interpolation + Procrustes + UW-SO, gradients to the P
+student tensors and log_temperatures) on synthetic activations of BASELINE.json configs[1]
+(DeiT-Ti <- DeiT-B, 224 px, 196 tokens, batch 256 per GPU, bf16 tokens).  Backbones are excluded.
+`value` is measured with the inputs resident in HBM; `e2e` goes through the same public module call but copies every
+input from pinned host memory each step and reads the loss back.  Multi-GPU: weak scaling, batch sharded, pooled
+statistics all-reduced over NCCL (two small collectives per step).
+"""
+from __future__ import annotations
+
+import argparse
+import dataclasses
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.nn as nn  # noqa: E402
+
+METRIC = "BASD loss fwd+bwd samples/s (DeiT-Ti<-DeiT-B, 224px)"
+UNIT = "samples/s"
+
+
+# ------------------------------------------------------------------------------------------------ workload
+def workload(batch: int):
+    from oracle import synth
+    return dataclasses.replace(synth.CONFIGS["cfg2"], B=batch)
+
+
+def algorithmic_bytes(w, act_bytes=2, attn_bytes=2):
+    """W_alg = 2 X_T + 4 X_S + A_needed (per step)."""
+    xt = w.Lt * w.B * w.Nt * w.Dt * act_bytes
+    xs = w.P * w.B * w.Ns * w.Ds * act_bytes
+    an = w.Lt * w.B * w.H * w.Nt * attn_bytes if w.has_cls else w.Lt * w.B * w.H * w.Nt * w.Nt * attn_bytes
+    return 2 * xt + 4 * xs + an
+
+
+def tensor_flops(w):
+    """F_tc (algorithmic tensor-core flops per step)."""
+    return 2 * w.B * (w.Lt * w.Nt * w.Ds * (w.Dt + w.Ds) + 2 * w.P * w.Ns * w.Ds ** 2 + 3 * w.P * w.Ns * w.Ds * w.Dt)
+
+
+def device_inputs(w, dev, seed):
+    """Spiked synthetic activations generated on the device."""
+    g = torch.Generator(device=dev).manual_seed(seed)
+
+    def spiked(B, N, D, r):
+        basis = torch.linalg.qr(torch.randn(D, r, generator=g, device=dev))[0]
+        amp = 4.0 * torch.linspace(1.0, 0.2, r, device=dev)
+        return ((torch.randn(B, N, r, generator=g, device=dev) * amp) @ basis.T + torch.randn(B, N, D, generator=g, device=dev)).bfloat16()
+
+    def geometric(B, N, D, rho=0.985, amp=3.0):
+        basis = torch.linalg.qr(torch.randn(D, D, generator=g, device=dev))[0]
+        return ((torch.randn(B, N, D, generator=g, device=dev) * (amp * rho ** torch.arange(D, device=dev))) @ basis.T).bfloat16()
+
+    logits = torch.randn(w.B, w.num_classes, generator=g, device=dev)
+    targets = torch.randint(0, w.num_classes, (w.B,), generator=g, device=dev)
+    student = {l: geometric(w.B, w.Ns, w.Ds) for l in w.token_layers()}
+    teacher = {j: spiked(w.B, w.Nt, w.Dt, (16 + 4 * j) if w.Lt > 1 else 64) for j in range(w.Lt)}
+    attn = {j: torch.softmax(2 * torch.randn(w.B, w.H, w.Nt + 1, w.Nt + 1, generator=g, device=dev), -1).bfloat16() for j in range(w.Lt)}
+    return logits, targets, student, teacher, attn
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._halt = index, [], threading.Event()
+
+    def run(self):
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def finish(self):
+        self._halt.set()
+        self.join(timeout=6)
+        sm = sorted(int(float(s[1])) for s in self.samples if len(s) > 2 and s[1].replace(".", "").isdigit())
+        mx = [int(float(s[2])) for s in self.samples if len(s) > 2 and s[2].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------ reference / CPU arm
+def cpu_reference_step_fn(w, sample_batch):
+    """Returns (step callable, kind, description).  kind 'reference' = the unmodified reference module copied by the
+    survey into the git-ignored baseline/_ref (travels with gpurun); 'port' = oracle/basd_oracle.py."""
+    from oracle import basd_oracle, synth
+    ws = dataclasses.replace(w, B=sample_batch)
+    inp = synth.make_inputs(ws)
+    ref_root = os.path.join(ROOT, "baseline", "_ref")
+    kind = "port"
+    if os.path.isdir(os.path.join(ref_root, "src", "losses")):
+        try:
+            sys.path.insert(0, ref_root)
+            from src.losses.combined import BASDLoss as RefLoss  # the reference itself
+            kind = "reference"
+        except Exception:
+            kind = "port"
+    torch.manual_seed(0)
+    if kind == "reference":
+        m = RefLoss(nn.CrossEntropyLoss(label_smoothing=0.001), ws.Ds, ws.Dt, ws.student_depth, ws.Ns,
+                    config=synth.module_config(ws), teacher_has_cls_token=ws.has_cls)
+        S = {l: v.float().requires_grad_() for l, v in inp["student"].items()}
+        T = {j: v.float() for j, v in inp["teacher"].items()}
+        logits = inp["logits"].clone().requires_grad_()
+
+        def step():
+            for t in S.values():
+                t.grad = None
+            m.zero_grad(set_to_none=True)
+            loss = m(logits, inp["targets"], S, T, inp["attn"])
+            loss.backward()
+            return float(loss)
+    else:
+        proj_s = torch.empty(ws.Ds, ws.Ds); proj_t = torch.empty(ws.Ds, ws.Dt)
+        nn.init.orthogonal_(proj_s); nn.init.orthogonal_(proj_t)
+        import math
+        logt = torch.full((ws.P,), math.log(math.e - 1))
+
+        def step():
+            out = basd_oracle.run_case(inp, proj_s, proj_t, logt, ws.token_layers(), has_cls=ws.has_cls, n_student_tokens=ws.Ns,
+                                       label_smoothing=0.001)
+            return float(out["loss"])
+    desc = f"{ws.name.replace(str(w.B), str(sample_batch))}: batch {sample_batch} of the same shapes, fp32, no autocast"
+    return step, kind, desc
+
+
+def time_cpu(step, steps, warmup):
+    for _ in range(warmup):
+        step()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    return sum(ts) / len(ts)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    w = workload(args.batch)
+    sample = args.cpu_sample_batch
+    step, kind, desc = cpu_reference_step_fn(w, sample)
+    sec = time_cpu(step, max(1, args.steps), max(1, min(args.warmup, 2)))
+    val = sample / sec
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w.name, "sample": desc, "l2": "cpu"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind, "sample": desc},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (weak scaling)")
+    ap.add_argument("--cpu-sample-batch", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback for the product path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import __graft_entry__ as graft
+    if not os.path.exists(graft.LIB):
+        graft.build()
+    import vit_bias_aware_structural_distillation_b200 as pkg
+    from vit_bias_aware_structural_distillation_b200 import _lib
+    lib = pkg.load()
+
+    w = workload(args.batch)
+    from oracle import synth
+    logits, targets, student, teacher, attn = device_inputs(w, dev, seed=1234 + rank)
+    torch.manual_seed(0)
+    m = pkg.BASDLoss(nn.CrossEntropyLoss(label_smoothing=0.001), w.Ds, w.Dt, w.student_depth, w.Ns, config=synth.module_config(w),
+                     teacher_has_cls_token=w.has_cls).to(dev)
+    logits.requires_grad_()
+    for t in student.values():
+        t.requires_grad_()
+
+    def step(lg, tg, st, te, at):
+        for t in st.values():
+            t.grad = None
+        m.zero_grad(set_to_none=True)
+        lg.grad = None
+        loss = m(lg, tg, st, te, at)
+        loss.backward()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(logits, targets, student, teacher, attn)
+    barrier()
+    lib.basd_timing_reset()
+    lib.basd_timing_enable(1)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(logits, targets, student, teacher, attn)
+    e1.record()
+    barrier()
+    clocks = sampler.finish()
+    ms_total = e0.elapsed_time(e1)
+    launches = int(lib.basd_launch_count())
+    lib.basd_timing_enable(0)
+    kern = _lib.timing_read()
+    t_ms = torch.tensor([ms_total], device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_step = t_ms.item() / args.steps
+    value = world * w.B / (ms_step * 1e-3)
+    loss_val = float(loss)
+
+    # ---- end to end: pinned host inputs copied every step, loss read back
+    e2e = None
+    if not args.no_e2e:
+        host = {"logits": logits.detach().cpu().pin_memory(), "targets": targets.cpu().pin_memory(),
+                "student": {k: v.detach().cpu().pin_memory() for k, v in student.items()},
+                "teacher": {k: v.cpu().pin_memory() for k, v in teacher.items()},
+                "attn": {k: v.cpu().pin_memory() for k, v in attn.items()}}
+        h2d = (host["logits"].numel() * 4 + host["targets"].numel() * 8 + sum(v.numel() * v.element_size() for v in host["student"].values())
+               + sum(v.numel() * v.element_size() for v in host["teacher"].values()) + sum(v.numel() * v.element_size() for v in host["attn"].values()))
+        d_logits = torch.empty_like(logits.detach()); d_targets = torch.empty_like(targets)
+        d_student = {k: torch.empty_like(v.detach()) for k, v in student.items()}
+        d_teacher = {k: torch.empty_like(v) for k, v in teacher.items()}
+        d_attn = {k: torch.empty_like(v) for k, v in attn.items()}
+
+        def e2e_step():
+            d_logits.copy_(host["logits"], non_blocking=True); d_targets.copy_(host["targets"], non_blocking=True)
+            for k in d_student:
+                d_student[k].copy_(host["student"][k], non_blocking=True)
+            for k in d_teacher:
+                d_teacher[k].copy_(host["teacher"][k], non_blocking=True)
+            for k in d_attn:
+                d_attn[k].copy_(host["attn"][k], non_blocking=True)
+            lg = d_logits.detach().requires_grad_()
+            st = {k: v.detach().requires_grad_() for k, v in d_student.items()}
+            out = step(lg, d_targets, st, d_teacher, d_attn)
+            return out.item()                      # device -> host read of the step's result
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * w.B * args.steps / dt.item(), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4}
+        del host, d_attn, d_teacher
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    tc_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    per_step = {k: v[0] / args.steps for k, v in kern.items() if v[1] > 0}
+    dom = max(per_step, key=per_step.get) if per_step else None
+    w_alg = algorithmic_bytes(w)
+    f_tc = tensor_flops(w)
+    achieved = w_alg / (ms_step * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                "scope": "whole step: W_alg = 2 X_T + 4 X_S + A_needed (SURVEY.md §8d) over the step time", "peak_source": peak_src,
+                "algorithmic_bytes_per_step": w_alg,
+                "tensor": {"achieved": f_tc / (ms_step * 1e-3) / 1e12, "peak": tc_peak, "unit": "TFLOP/s", "frac": f_tc / (ms_step * 1e-3) / 1e12 / tc_peak,
+                           "algorithmic_flops_per_step": f_tc},
+                "dominant_kernel": dom, "dominant_kernel_ms_per_step": per_step.get(dom) if dom else None,
+                "dominant_kernel_share": (per_step[dom] / ms_step) if dom else None,
+                "kernel_ms_per_step": {k: round(v, 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])}}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        stepfn, kind, desc = cpu_reference_step_fn(w, args.cpu_sample_batch)
+        sec = time_cpu(stepfn, 2, 1)
+        cpu_baseline = {"value": args.cpu_sample_batch / sec, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind, "sample": desc}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 tokens / fp32 accumulate + fp32 spectral",
+            "data": "synthetic",
+            "config": {"workload": w.name, "per_gpu_batch": w.B, "global_batch": w.B * world, "Ns": w.Ns, "Nt": w.Nt, "Ds": w.Ds, "Dt": w.Dt,
+                       "Lt": w.Lt, "H": w.H, "P": w.P, "parallelism": f"dp{world} (batch-sharded, pooled statistics all-reduced)",
+                       "l2": "inputs (3.9 GB per step) exceed the 126 MB L2; no explicit flush"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "loss": loss_val}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -89,6 +89,14 @@ int basd_mp_rank(const void* features, int64_t M, int D, int dtype, int64_t row_
 int basd_selftest_gemm(int variant, const void* A, const void* B, float* C, int M, int N, int K, void* stream);
 int basd_selftest_eig(const float* G, int n, float* evals, float* evecs, int* sweeps, void* workspace, void* stream);
 
+/* Live timing (CUDA events on the launching stream around each kernel group) and launch counting, for bench.py. */
+void basd_timing_enable(int on);
+void basd_timing_reset(void);
+long long basd_launch_count(void);
+int basd_timing_slots(void);
+const char* basd_timing_name(int slot);
+int basd_timing_read(int slot, float* ms_total, int* brackets);
+
 const char* basd_last_error(void);
 const char* basd_version(void);
 

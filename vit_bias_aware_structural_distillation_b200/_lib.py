@@ -35,7 +35,8 @@ class Inputs(ctypes.Structure):
 EXPORTS = [
     "basd_workspace_bytes", "basd_forward_stats", "basd_forward_solve", "basd_backward_dots", "basd_backward_finish",
     "basd_view", "basd_mp_rank_workspace_bytes", "basd_mp_rank", "basd_selftest_gemm", "basd_selftest_eig",
-    "basd_last_error", "basd_version",
+    "basd_last_error", "basd_version", "basd_timing_enable", "basd_timing_reset", "basd_launch_count", "basd_timing_slots",
+    "basd_timing_name", "basd_timing_read",
 ]
 
 _lib = None
@@ -67,6 +68,11 @@ def load():
     lib.basd_mp_rank.argtypes = [vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int64, vp, vp, vp]
     lib.basd_selftest_gemm.argtypes = [ctypes.c_int, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]
     lib.basd_selftest_eig.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp]
+    lib.basd_launch_count.restype = ctypes.c_longlong
+    lib.basd_timing_name.restype = ctypes.c_char_p
+    lib.basd_timing_name.argtypes = [ctypes.c_int]
+    lib.basd_timing_enable.argtypes = [ctypes.c_int]
+    lib.basd_timing_read.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]
     for name in EXPORTS:
         getattr(lib, name)          # fail loudly on a stale library
     _lib = lib
@@ -76,3 +82,14 @@ def load():
 def check(rc: int, what: str):
     if rc != 0:
         raise BasdError(f"{what} failed: {load().basd_last_error().decode()}")
+
+
+def timing_read():
+    """{kernel group: (total ms, brackets)} recorded since the last basd_timing_reset()."""
+    lib = load()
+    out = {}
+    for i in range(lib.basd_timing_slots()):
+        ms, n = ctypes.c_float(), ctypes.c_int()
+        check(lib.basd_timing_read(i, ctypes.byref(ms), ctypes.byref(n)), "basd_timing_read")
+        out[lib.basd_timing_name(i).decode()] = (ms.value, n.value)
+    return out

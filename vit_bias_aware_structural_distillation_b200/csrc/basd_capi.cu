@@ -24,6 +24,52 @@ static int fail(const char* fmt, ...) {
     } while (0)
 
 extern "C" const char* basd_last_error(void) { return g_err; }
+
+// ---------------------------------------------------------------------------------------------- live kernel timing
+// Optional CUDA-event brackets around each kernel group, recorded on the launching stream inside the caller's timed
+// region (bench.py's roofline numbers come from here, not from a profiler).  Also counts kernel launches.
+namespace {
+constexpr int kTimeSlots = 16;
+constexpr int kMaxPairs = 2048;
+const char* kSlotNames[kTimeSlots] = {"importance_rows", "split_pack", "project", "gram", "colsum", "pooled_eig", "angles",
+                                      "importance_mix", "mix_teacher", "token_gram", "procrustes", "loss_reduce", "theta_apply",
+                                      "wgrad_dots", "selector_bwd", "student_grad"};
+struct TimeSlot { cudaEvent_t ev[kMaxPairs][2]; int created = 0; int used = 0; };
+TimeSlot g_slots[kTimeSlots];
+bool g_timing = false;
+long long g_launches = 0;
+struct Scope {
+    int slot; cudaStream_t st; bool on;
+    Scope(int slot_, cudaStream_t st_, int n_launches) : slot(slot_), st(st_), on(false) {
+        g_launches += n_launches;
+        TimeSlot& t = g_slots[slot];
+        if (!g_timing || t.used >= kMaxPairs) return;
+        if (t.used >= t.created) { cudaEventCreate(&t.ev[t.created][0]); cudaEventCreate(&t.ev[t.created][1]); ++t.created; }
+        cudaEventRecord(t.ev[t.used][0], st);
+        on = true;
+    }
+    ~Scope() { if (on) { TimeSlot& t = g_slots[slot]; cudaEventRecord(t.ev[t.used][1], st); ++t.used; } }
+};
+}  // namespace
+extern "C" void basd_timing_enable(int on) { g_timing = on != 0; }
+extern "C" void basd_timing_reset(void) { for (auto& t : g_slots) t.used = 0; g_launches = 0; }
+extern "C" long long basd_launch_count(void) { return g_launches; }
+extern "C" int basd_timing_slots(void) { return kTimeSlots; }
+extern "C" const char* basd_timing_name(int slot) { return (slot >= 0 && slot < kTimeSlots) ? kSlotNames[slot] : ""; }
+// total milliseconds and number of timed brackets of a slot (synchronises on the recorded events)
+extern "C" int basd_timing_read(int slot, float* ms_total, int* brackets) {
+    if (slot < 0 || slot >= kTimeSlots || !ms_total || !brackets) return fail("bad timing slot");
+    TimeSlot& t = g_slots[slot];
+    float tot = 0.f;
+    for (int i = 0; i < t.used; ++i) {
+        float ms = 0.f;
+        cudaEventSynchronize(t.ev[i][1]);
+        if (cudaEventElapsedTime(&ms, t.ev[i][0], t.ev[i][1]) == cudaSuccess) tot += ms;
+    }
+    *ms_total = tot; *brackets = t.used;
+    return 0;
+}
+#define TIMED(slot, n, stmt) do { Scope _sc(slot, st, n); stmt; } while (0)
 extern "C" const char* basd_version(void) { return "basd_b200 0.1 (sm_100a)"; }
 
 namespace {
@@ -84,6 +130,7 @@ Layout make_layout(const basd_shape& s) {
 
 int check_shape(const basd_shape& s) {
     if (s.B < 1 || s.Ns < 2 || s.Nt < 1 || s.Lt < 1 || s.P < 1) return fail("invalid shape");
+    if (s.world_size < 1) return fail("world_size must be >= 1");
     if (s.P > BASD_MAX_POINTS || s.Lt > BASD_MAX_LAYERS) return fail("P <= %d and Lt <= %d required", BASD_MAX_POINTS, BASD_MAX_LAYERS);
     if (s.Ds % 8 || s.Dt % 8) return fail("Ds and Dt must be multiples of 8 (16-byte rows), got %d, %d", s.Ds, s.Dt);
     if (s.Ds > 224) return fail("Ds=%d > 224: pooled eigenproblems larger than one SM's shared memory are not built yet", s.Ds);
@@ -91,7 +138,6 @@ int check_shape(const basd_shape& s) {
     if (s.Ds > s.Ns) return fail("Ds=%d > Ns=%d: the student-side factorisation of the Procrustes core is not built yet", s.Ds, s.Ns);
     if (static_cast<long long>(s.B) * s.Nt * s.world_size < s.Ds)
         return fail("pooled rows M < Ds (layer_selector.py:14-15 branch) is not supported");
-    if (s.world_size < 1) return fail("world_size must be >= 1");
     return 0;
 }
 
@@ -169,10 +215,12 @@ extern "C" int basd_forward_stats(const basd_shape* shape, const basd_inputs* in
     memset(&attn, 0, sizeof attn);
     for (int j = 0; j < s.Lt; ++j) attn.p[j] = in.attn[j];
     long long as[4] = {in.attn_strides[0], in.attn_strides[1], in.attn_strides[2], in.attn_strides[3]};
-    CK(launch_importance_rows(attn, s.attn_dtype == BASD_DTYPE_BF16, s.Lt, s.B, s.H, s.Nt, s.has_cls, as,
-                              reinterpret_cast<float*>(ws + L.rows), st));
+    TIMED(0, 1, CK(launch_importance_rows(attn, s.attn_dtype == BASD_DTYPE_BF16, s.Lt, s.B, s.H, s.Nt, s.has_cls, as,
+                              reinterpret_cast<float*>(ws + L.rows), st)));
     __nv_bfloat16* pt_hi = reinterpret_cast<__nv_bfloat16*>(ws + L.pt_hi);
     __nv_bfloat16* pt_lo = reinterpret_cast<__nv_bfloat16*>(ws + L.pt_lo);
+    Scope* pack_scope = new Scope(1, st, 1 + (s.act_dtype == BASD_DTYPE_F32 ? s.Lt + s.P : 0));
+    struct ScopeDel { Scope* p; ~ScopeDel() { delete p; } } pack_del{pack_scope};
     CK(launch_split_bf16(in.proj_t, pt_hi, pt_lo, static_cast<size_t>(s.Ds) * s.Dt, st));
     if (s.act_dtype == BASD_DTYPE_F32) {
         for (int j = 0; j < s.Lt; ++j)
@@ -182,17 +230,25 @@ extern "C" int basd_forward_stats(const basd_shape* shape, const basd_inputs* in
             CK(launch_pack_bf16(in.student[i], 0, in.student_strides[0], in.student_strides[1], in.student_strides[2], s.B, s.Ns, s.Ds,
                                 reinterpret_cast<__nv_bfloat16*>(ws + L.spk) + static_cast<size_t>(i) * Ms * s.Ds, st));
     }
+    delete pack_scope; pack_del.p = nullptr;
     Resolved r;
     if (resolve(s, in, ws, L, &r)) return 1;
     __nv_bfloat16* z = reinterpret_cast<__nv_bfloat16*>(ws + L.z);
-    for (int j = 0; j < s.Lt; ++j) CK(gemm_project(r.teacher[j], Mt, s.Dt, pt_hi, pt_lo, s.Ds, z + static_cast<size_t>(j) * Mt * s.Ds, st));
-    CK(gemm_gram_batched(z, Mt, s.Ds, s.Lt, stats, static_cast<long long>(stat_stride), st));
-    for (int j = 0; j < s.Lt; ++j)
-        CK(launch_colsum(z + static_cast<size_t>(j) * Mt * s.Ds, Mt, s.Ds, stats + j * stat_stride + static_cast<size_t>(s.Ds) * s.Ds, st));
-    for (int i = 0; i < s.P; ++i) {
-        float* g = stats + (s.Lt + i) * stat_stride;
-        CK(gemm_gram(r.student[i], Ms, s.Ds, g, st));
-        CK(launch_colsum(r.student[i], Ms, s.Ds, g + static_cast<size_t>(s.Ds) * s.Ds, st));
+    {
+        Scope sc(2, st, s.Lt);
+        for (int j = 0; j < s.Lt; ++j) CK(gemm_project(r.teacher[j], Mt, s.Dt, pt_hi, pt_lo, s.Ds, z + static_cast<size_t>(j) * Mt * s.Ds, st));
+    }
+    {
+        Scope sc(3, st, 1 + s.P);
+        CK(gemm_gram_batched(z, Mt, s.Ds, s.Lt, stats, static_cast<long long>(stat_stride), st));
+        for (int i = 0; i < s.P; ++i) CK(gemm_gram(r.student[i], Ms, s.Ds, stats + (s.Lt + i) * stat_stride, st));
+    }
+    {
+        Scope sc(4, st, s.Lt + s.P);
+        for (int j = 0; j < s.Lt; ++j)
+            CK(launch_colsum(z + static_cast<size_t>(j) * Mt * s.Ds, Mt, s.Ds, stats + j * stat_stride + static_cast<size_t>(s.Ds) * s.Ds, st));
+        for (int i = 0; i < s.P; ++i)
+            CK(launch_colsum(r.student[i], Ms, s.Ds, stats + (s.Lt + i) * stat_stride + static_cast<size_t>(s.Ds) * s.Ds, st));
     }
     return 0;
 }
@@ -216,20 +272,20 @@ extern "C" int basd_forward_solve(const basd_shape* shape, const basd_inputs* in
     float* d2 = reinterpret_cast<float*>(ws + L.d2);
     float* w = reinterpret_cast<float*>(ws + L.w);
 
-    CK(launch_pooled_eig(stats, s.Ds, s.Lt, s.P, Mt, Ms, ranks, evals, evk, evc, reinterpret_cast<int*>(ws + L.sweeps), st));
-    CK(launch_angles(s.Ds, s.Lt, s.P, ranks, evals, evk, evc, in.proj_s, reinterpret_cast<float*>(ws + L.ang_scr), d2,
-                     reinterpret_cast<float*>(ws + L.gamma), reinterpret_cast<float*>(ws + L.cosv), in.log_temperatures, w, st));
+    TIMED(5, 1, CK(launch_pooled_eig(stats, s.Ds, s.Lt, s.P, Mt, Ms, ranks, evals, evk, evc, reinterpret_cast<int*>(ws + L.sweeps), st)));
+    TIMED(6, 2, CK(launch_angles(s.Ds, s.Lt, s.P, ranks, evals, evk, evc, in.proj_s, reinterpret_cast<float*>(ws + L.ang_scr), d2,
+                     reinterpret_cast<float*>(ws + L.gamma), reinterpret_cast<float*>(ws + L.cosv), in.log_temperatures, w, st)));
     float* a = reinterpret_cast<float*>(ws + L.a);
     float* ssum = reinterpret_cast<float*>(ws + L.ssum);
-    CK(launch_importance_mix(reinterpret_cast<float*>(ws + L.rows), w, s.Lt, s.P, s.B, s.Nt, s.Ns, a, ssum, st));
+    TIMED(7, 1, CK(launch_importance_mix(reinterpret_cast<float*>(ws + L.rows), w, s.Lt, s.P, s.B, s.Nt, s.Ns, a, ssum, st)));
     PtrTable tt;
     memset(&tt, 0, sizeof tt);
     for (int j = 0; j < s.Lt; ++j) tt.p[j] = r.teacher[j];
     __nv_bfloat16* thi = reinterpret_cast<__nv_bfloat16*>(ws + L.tbar_hi);
     __nv_bfloat16* tlo = reinterpret_cast<__nv_bfloat16*>(ws + L.tbar_lo);
-    CK(launch_mix_teacher(tt, w, s.Lt, s.P, s.B, s.Nt, s.Ns, s.Dt, thi, tlo, st));
+    TIMED(8, 1, CK(launch_mix_teacher(tt, w, s.Lt, s.P, s.B, s.Nt, s.Ns, s.Dt, thi, tlo, st)));
     float* ktt = reinterpret_cast<float*>(ws + L.ktt);
-    CK(gemm_token_gram(thi, tlo, s.P * s.B, s.Ns, s.Dt, ktt, st));
+    TIMED(9, 1, CK(gemm_token_gram(thi, tlo, s.P * s.B, s.Ns, s.Dt, ktt, st)));
 
     ProcrustesArgs pa;
     memset(&pa, 0, sizeof pa);
@@ -248,9 +304,9 @@ extern "C" int basd_forward_solve(const basd_shape* shape, const basd_inputs* in
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     int ctas = pa.n_problems < sms ? pa.n_problems : sms;
     if (ctas > kProcCtasMax) ctas = kProcCtasMax;
-    CK(launch_procrustes(pa, ctas, st));
+    TIMED(10, 1, CK(launch_procrustes(pa, ctas, st)));
     float* geo_i = reinterpret_cast<float*>(ws + L.geo_i);
-    CK(launch_loss_reduce(pa.loss_b, s.P, s.B, geo_i, geo_i + s.P, st));
+    TIMED(11, 1, CK(launch_loss_reduce(pa.loss_b, s.P, s.B, geo_i, geo_i + s.P, st)));
     CK(cudaMemcpyAsync(geo_loss, geo_i + s.P, sizeof(float), cudaMemcpyDeviceToDevice, st));
     return 0;
 }
@@ -269,11 +325,11 @@ extern "C" int basd_backward_dots(const basd_shape* shape, const basd_inputs* in
     for (int j = 0; j < s.Lt; ++j) tt.p[j] = r.teacher[j];
     __nv_bfloat16* thi = reinterpret_cast<__nv_bfloat16*>(ws + L.tbar_hi);
     __nv_bfloat16* dtm = reinterpret_cast<__nv_bfloat16*>(ws + L.tbar_lo);     // lo half is dead after the token Gram
-    CK(gemm_theta_apply(reinterpret_cast<__nv_bfloat16*>(ws + L.theta), L.NsPad, thi, s.P * s.B, s.Ns, s.Dt, dtm, st));
+    TIMED(12, 1, CK(gemm_theta_apply(reinterpret_cast<__nv_bfloat16*>(ws + L.theta), L.NsPad, thi, s.P * s.B, s.Ns, s.Dt, dtm, st)));
     float* gw = reinterpret_cast<float*>(ws + L.gw);
     CK(cudaMemsetAsync(gw, 0, sizeof(float) * s.P * s.Lt, st));
-    CK(launch_wgrad_dots(tt, dtm, reinterpret_cast<float*>(ws + L.gwt), reinterpret_cast<float*>(ws + L.rows), s.Lt, s.P, s.B, s.Nt,
-                         s.Ns, s.Dt, gw, st));
+    TIMED(13, 2, CK(launch_wgrad_dots(tt, dtm, reinterpret_cast<float*>(ws + L.gwt), reinterpret_cast<float*>(ws + L.rows), s.Lt, s.P, s.B, s.Nt,
+                         s.Ns, s.Dt, gw, st)));
     return 0;
 }
 
@@ -293,10 +349,11 @@ extern "C" int basd_backward_finish(const basd_shape* shape, const basd_inputs* 
     __nv_bfloat16* ghi = reinterpret_cast<__nv_bfloat16*>(ws + L.gam_hi);
     __nv_bfloat16* glo = reinterpret_cast<__nv_bfloat16*>(ws + L.gam_lo);
     float* corr = reinterpret_cast<float*>(ws + L.corr);
-    CK(launch_selector_bwd(s.Ds, s.Lt, s.P, reinterpret_cast<float*>(ws + L.gw), grad_geo, scale, reinterpret_cast<float*>(ws + L.w),
+    TIMED(14, 1, CK(launch_selector_bwd(s.Ds, s.Lt, s.P, reinterpret_cast<float*>(ws + L.gw), grad_geo, scale, reinterpret_cast<float*>(ws + L.w),
                            reinterpret_cast<float*>(ws + L.d2), in.log_temperatures, reinterpret_cast<float*>(ws + L.gamma),
-                           reinterpret_cast<float*>(ws + L.stats), Ms, ghi, glo, corr, grad_log_temperatures, st));
+                           reinterpret_cast<float*>(ws + L.stats), Ms, ghi, glo, corr, grad_log_temperatures, st)));
     const size_t MsL = static_cast<size_t>(s.B) * s.Ns;
+    Scope sg(15, st, s.P);
     for (int i = 0; i < s.P; ++i) {
         if (!grad_student[i]) return fail("null grad_student[%d]", i);
         CK(gemm_student_grad(r.student[i], MsL, s.Ds, ghi + static_cast<size_t>(i) * s.Ds * s.Ds, glo + static_cast<size_t>(i) * s.Ds * s.Ds,
