@@ -74,12 +74,11 @@ extern "C" const char* basd_version(void) { return "basd_b200 0.1 (sm_100a)"; }
 
 namespace {
 
-constexpr int kProcCtasMax = 160;
-
 struct Layout {
     size_t rows, pt_hi, pt_lo, tpk, spk, z, stats, ranks, sweeps, evals, evecs_km, evecs_cm, d2, w, cosv, gamma, ang_scr, a, ssum,
-        tbar_hi, tbar_lo, ktt, proc_scr, gdir, theta, gwt, loss_b, dbg, geo_i, gw, gam_hi, gam_lo, corr, total;
-    int NsPad;
+        tbar_hi, tbar_lo, ktt, gdir, theta, gwt, loss_b, dbg, geo_i, gw, gam_hi, gam_lo, corr,
+        pw, pw2, pt, pa, pa2, pb, pkt, psw, gsw, pvec, pscal, pfro, theta_lo, dtm, total;
+    int NsPad, Np;
 };
 
 size_t align_up(size_t x) { return (x + 1023) & ~static_cast<size_t>(1023); }
@@ -96,7 +95,7 @@ Layout make_layout(const basd_shape& s) {
     const bool pack = s.act_dtype == BASD_DTYPE_F32;
     L.tpk = take(pack ? 2 * Lt * B * Nt * Dt : 0);
     L.spk = take(pack ? 2 * P * B * Ns * Ds : 0);
-    L.z = take(2 * Lt * B * Nt * Ds);
+    L.z = take(2 * 2 * Lt * B * Nt * Ds);          // projected teacher tokens, split pair: hi block then lo block
     L.stats = take(4 * (Lt + P) * (Ds * Ds + Ds));
     L.ranks = take(4 * Lt);
     L.sweeps = take(4 * (2 * Lt + P));
@@ -113,9 +112,26 @@ Layout make_layout(const basd_shape& s) {
     L.tbar_hi = take(2 * P * B * Ns * Dt);
     L.tbar_lo = take(2 * P * B * Ns * Dt);
     L.ktt = take(4 * P * B * Ns * Ns);
-    L.proc_scr = take(4 * kProcCtasMax * procrustes_scratch_floats(s.Ns, s.Ds));
+    // Newton-Schulz polar iteration (polar.cu): split-bf16 matrices per (point, sample) problem, hi then lo
+    L.Np = static_cast<int>((Ns + 63) / 64 * 64);      // column-block tiled storage: columns padded to 64
+    const size_t nprob = P * B, Np = L.Np;
+    const size_t Dp = (Ds + 63) / 64 * 64;
+    L.pw = take(2 * 2 * nprob * Ds * Np);
+    L.pw2 = take(2 * 2 * nprob * Ds * Np);
+    L.pt = take(2 * 2 * nprob * Ds * Np);
+    L.pa = take(2 * 2 * nprob * Ds * Dp);
+    L.pa2 = take(2 * 2 * nprob * Ds * Dp);
+    L.pb = take(2 * 2 * nprob * Ds * Dp);
+    L.pkt = take(2 * 2 * nprob * Ns * Np);
+    L.psw = take(2 * 2 * nprob * Ns * Dp);
+    L.gsw = take(4 * nprob * Ns * Ds);
+    L.pvec = take(4 * nprob * 4 * Ns);
+    L.pscal = take(4 * nprob * 4);
+    L.pfro = take(4 * nprob);
     L.gdir = take(4 * P * B * Ns * Ds);
     L.theta = take(2 * P * B * Ns * L.NsPad);
+    L.theta_lo = take(2 * P * B * Ns * L.NsPad);
+    L.dtm = take(2 * P * B * Ns * Dt);
     L.gwt = take(4 * P * B * Ns);
     L.loss_b = take(4 * P * B);
     L.dbg = take(4 * P * B * 5);
@@ -134,8 +150,14 @@ int check_shape(const basd_shape& s) {
     if (s.P > BASD_MAX_POINTS || s.Lt > BASD_MAX_LAYERS) return fail("P <= %d and Lt <= %d required", BASD_MAX_POINTS, BASD_MAX_LAYERS);
     if (s.Ds % 8 || s.Dt % 8) return fail("Ds and Dt must be multiples of 8 (16-byte rows), got %d, %d", s.Ds, s.Dt);
     if (s.Ds > 224) return fail("Ds=%d > 224: pooled eigenproblems larger than one SM's shared memory are not built yet", s.Ds);
-    if (s.Ns > 224) return fail("Ns=%d > 224: per-sample problems larger than one SM's shared memory are not built yet", s.Ns);
-    if (s.Ds > s.Ns) return fail("Ds=%d > Ns=%d: the student-side factorisation of the Procrustes core is not built yet", s.Ds, s.Ns);
+    if (s.Ns > 256) return fail("Ns=%d > 256: per-sample products larger than one CTA tile are not built yet", s.Ns);
+    {
+        // rank of the weighted, centred (and, if Nt < Ns, up-sampled) teacher token matrix
+        const int rank_t = (s.Nt < s.Ns ? s.Nt : s.Ns) - 1;
+        if (s.Ds > rank_t)
+            return fail("Ds=%d > min(Ns, Nt)-1=%d: the cross-covariance is rank deficient on the student side; the token-space form of "
+                        "the polar iteration is not built yet", s.Ds, rank_t);
+    }
     if (static_cast<long long>(s.B) * s.Nt * s.world_size < s.Ds)
         return fail("pooled rows M < Ds (layer_selector.py:14-15 branch) is not supported");
     return 0;
@@ -192,6 +214,10 @@ extern "C" int basd_view(const basd_shape* shape, void* workspace, const char* n
         {"gdir", L.gdir, P * B * Ns * Ds}, {"ktt", L.ktt, P * B * Ns * Ns}, {"sweeps", L.sweeps, 2 * Lt + P},
         {"gamma", L.gamma, P * Lt * Ds * Ds}, {"gwt", L.gwt, P * B * Ns}, {"evecs", L.evecs_km, (Lt + P) * Ds * Ds},
         {"corr", L.corr, P * Ds}, {"ssum", L.ssum, P * B},
+        // polar iteration state (bf16 pairs: count is in bf16 elements, hi block then lo block)
+        {"polar_w", (11 % 2) ? L.pw2 : L.pw, 2 * P * B * Ds * L.Np}, {"polar_kt", L.pkt, 2 * P * B * Ns * L.Np},
+        {"polar_sw", L.psw, 2 * P * B * Ns * ((Ds + 63) / 64 * 64)}, {"polar_a", L.pa, 2 * P * B * Ds * ((Ds + 63) / 64 * 64)}, {"polar_gsw", L.gsw, P * B * Ns * Ds}, {"polar_fro2", L.pfro, P * B},
+        {"theta", L.theta, P * B * Ns * L.NsPad},
     };
     for (const E& e : table)
         if (!strcmp(e.n, name)) { *ptr = ws + e.off; *count = e.cnt; return 0; }
@@ -225,30 +251,45 @@ extern "C" int basd_forward_stats(const basd_shape* shape, const basd_inputs* in
     if (s.act_dtype == BASD_DTYPE_F32) {
         for (int j = 0; j < s.Lt; ++j)
             CK(launch_pack_bf16(in.teacher[j], 0, in.teacher_strides[0], in.teacher_strides[1], in.teacher_strides[2], s.B, s.Nt, s.Dt,
-                                reinterpret_cast<__nv_bfloat16*>(ws + L.tpk) + static_cast<size_t>(j) * Mt * s.Dt, st));
+                                reinterpret_cast<__nv_bfloat16*>(ws + L.tpk) + static_cast<size_t>(j) * Mt * s.Dt, nullptr, st));
         for (int i = 0; i < s.P; ++i)
             CK(launch_pack_bf16(in.student[i], 0, in.student_strides[0], in.student_strides[1], in.student_strides[2], s.B, s.Ns, s.Ds,
-                                reinterpret_cast<__nv_bfloat16*>(ws + L.spk) + static_cast<size_t>(i) * Ms * s.Ds, st));
+                                reinterpret_cast<__nv_bfloat16*>(ws + L.spk) + static_cast<size_t>(i) * Ms * s.Ds, nullptr, st));
     }
     delete pack_scope; pack_del.p = nullptr;
     Resolved r;
     if (resolve(s, in, ws, L, &r)) return 1;
     __nv_bfloat16* z = reinterpret_cast<__nv_bfloat16*>(ws + L.z);
+    __nv_bfloat16* zlo = z + static_cast<size_t>(s.Lt) * Mt * s.Ds;
     {
         Scope sc(2, st, s.Lt);
-        for (int j = 0; j < s.Lt; ++j) CK(gemm_project(r.teacher[j], Mt, s.Dt, pt_hi, pt_lo, s.Ds, z + static_cast<size_t>(j) * Mt * s.Ds, st));
+        for (int j = 0; j < s.Lt; ++j)
+            CK(gemm_project(r.teacher[j], Mt, s.Dt, pt_hi, pt_lo, s.Ds, z + static_cast<size_t>(j) * Mt * s.Ds, zlo + static_cast<size_t>(j) * Mt * s.Ds, st));
     }
     {
         Scope sc(3, st, 1 + s.P);
-        CK(gemm_gram_batched(z, Mt, s.Ds, s.Lt, stats, static_cast<long long>(stat_stride), st));
-        for (int i = 0; i < s.P; ++i) CK(gemm_gram(r.student[i], Ms, s.Ds, stats + (s.Lt + i) * stat_stride, st));
+        CK(gemm_gram_batched(z, zlo, Mt, s.Ds, s.Lt, stats, static_cast<long long>(stat_stride), st));
+        for (int i = 0; i < s.P; ++i) CK(gemm_gram(r.student[i], nullptr, Ms, s.Ds, stats + (s.Lt + i) * stat_stride, st));
     }
     {
-        Scope sc(4, st, s.Lt + s.P);
-        for (int j = 0; j < s.Lt; ++j)
-            CK(launch_colsum(z + static_cast<size_t>(j) * Mt * s.Ds, Mt, s.Ds, stats + j * stat_stride + static_cast<size_t>(s.Ds) * s.Ds, st));
-        for (int i = 0; i < s.P; ++i)
-            CK(launch_colsum(r.student[i], Ms, s.Ds, stats + (s.Lt + i) * stat_stride + static_cast<size_t>(s.Ds) * s.Ds, st));
+        Scope sc(4, st, Mt == Ms ? 1 : 2);
+        ColsumJobs jt, js;
+        memset(&jt, 0, sizeof jt); memset(&js, 0, sizeof js);
+        for (int j = 0; j < s.Lt; ++j) {
+            jt.hi[j] = z + static_cast<size_t>(j) * Mt * s.Ds; jt.lo[j] = zlo + static_cast<size_t>(j) * Mt * s.Ds;
+            jt.out[j] = stats + j * stat_stride + static_cast<size_t>(s.Ds) * s.Ds;
+        }
+        for (int i = 0; i < s.P; ++i) {
+            js.hi[i] = r.student[i]; js.lo[i] = nullptr;
+            js.out[i] = stats + (s.Lt + i) * stat_stride + static_cast<size_t>(s.Ds) * s.Ds;
+        }
+        if (Mt == Ms) {                     // same row count: one launch covers teacher and student jobs
+            for (int i = 0; i < s.P; ++i) { jt.hi[s.Lt + i] = js.hi[i]; jt.lo[s.Lt + i] = nullptr; jt.out[s.Lt + i] = js.out[i]; }
+            CK(launch_colsum(jt, s.Lt + s.P, Mt, s.Ds, st));
+        } else {
+            CK(launch_colsum(jt, s.Lt, Mt, s.Ds, st));
+            CK(launch_colsum(js, s.P, Ms, s.Ds, st));
+        }
     }
     return 0;
 }
@@ -287,24 +328,45 @@ extern "C" int basd_forward_solve(const basd_shape* shape, const basd_inputs* in
     float* ktt = reinterpret_cast<float*>(ws + L.ktt);
     TIMED(9, 1, CK(gemm_token_gram(thi, tlo, s.P * s.B, s.Ns, s.Dt, ktt, st)));
 
-    ProcrustesArgs pa;
+    PolarArgs pa;
     memset(&pa, 0, sizeof pa);
-    pa.Ns = s.Ns; pa.Ds = s.Ds; pa.B = s.B; pa.NsPad = L.NsPad; pa.n_problems = s.P * s.B;
-    pa.Ktt = ktt; pa.a = a; pa.ssum = ssum;
+    pa.Ns = s.Ns; pa.Ds = s.Ds; pa.B = s.B; pa.P = s.P; pa.NsPad = L.NsPad; pa.n_problems = s.P * s.B;
     for (int i = 0; i < s.P; ++i) pa.student[i] = r.student[i];
-    pa.student_batch_stride = static_cast<long long>(s.Ns) * s.Ds;
-    pa.scratch = reinterpret_cast<float*>(ws + L.proc_scr);
+    pa.Ktt = ktt; pa.a = a; pa.ssum = ssum;
+    {
+        const long long nprob = pa.n_problems;
+        auto split = [&](size_t off, int rows, int inner) {      // tiled: [problem][col block][row][64], hi block then lo block
+            SplitMat m;
+            m.rows = rows; m.inner = inner; m.batch_stride = static_cast<long long>((inner + 63) / 64) * rows * 64;
+            m.hi = reinterpret_cast<__nv_bfloat16*>(ws + off);
+            m.lo = m.hi + nprob * m.batch_stride;
+            return m;
+        };
+        pa.W = split(L.pw, s.Ds, s.Ns);
+        pa.W2 = split(L.pw2, s.Ds, s.Ns);
+        pa.T = split(L.pt, s.Ds, s.Ns);
+        pa.A = split(L.pa, s.Ds, s.Ds);
+        pa.A2 = split(L.pa2, s.Ds, s.Ds);
+        pa.Bm = split(L.pb, s.Ds, s.Ds);
+        pa.Kt = split(L.pkt, s.Ns, s.Ns);
+        pa.SW = split(L.psw, s.Ns, s.Ds);
+    }
+    pa.Gsw = reinterpret_cast<float*>(ws + L.gsw);
+    pa.vec = reinterpret_cast<float*>(ws + L.pvec);
+    pa.scal = reinterpret_cast<float*>(ws + L.pscal);
+    pa.fro2 = reinterpret_cast<float*>(ws + L.pfro);
     pa.gdir = reinterpret_cast<float*>(ws + L.gdir);
     pa.theta = reinterpret_cast<__nv_bfloat16*>(ws + L.theta);
+    pa.theta_lo = reinterpret_cast<__nv_bfloat16*>(ws + L.theta_lo);
     pa.gwt = reinterpret_cast<float*>(ws + L.gwt);
     pa.loss_b = reinterpret_cast<float*>(ws + L.loss_b);
     pa.dbg = reinterpret_cast<float*>(ws + L.dbg);
-    int dev = 0, sms = 148;
-    CK(cudaGetDevice(&dev));
-    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    int ctas = pa.n_problems < sms ? pa.n_problems : sms;
-    if (ctas > kProcCtasMax) ctas = kProcCtasMax;
-    TIMED(10, 1, CK(launch_procrustes(pa, ctas, st)));
+    {
+        int n_launch = 0;
+        Scope sc(10, st, 0);
+        CK(launch_polar_procrustes(pa, st, &n_launch));
+        g_launches += n_launch;
+    }
     float* geo_i = reinterpret_cast<float*>(ws + L.geo_i);
     TIMED(11, 1, CK(launch_loss_reduce(pa.loss_b, s.P, s.B, geo_i, geo_i + s.P, st)));
     CK(cudaMemcpyAsync(geo_loss, geo_i + s.P, sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -324,8 +386,10 @@ extern "C" int basd_backward_dots(const basd_shape* shape, const basd_inputs* in
     memset(&tt, 0, sizeof tt);
     for (int j = 0; j < s.Lt; ++j) tt.p[j] = r.teacher[j];
     __nv_bfloat16* thi = reinterpret_cast<__nv_bfloat16*>(ws + L.tbar_hi);
-    __nv_bfloat16* dtm = reinterpret_cast<__nv_bfloat16*>(ws + L.tbar_lo);     // lo half is dead after the token Gram
-    TIMED(12, 1, CK(gemm_theta_apply(reinterpret_cast<__nv_bfloat16*>(ws + L.theta), L.NsPad, thi, s.P * s.B, s.Ns, s.Dt, dtm, st)));
+    __nv_bfloat16* tlo = reinterpret_cast<__nv_bfloat16*>(ws + L.tbar_lo);
+    __nv_bfloat16* dtm = reinterpret_cast<__nv_bfloat16*>(ws + L.dtm);
+    TIMED(12, 1, CK(gemm_theta_apply(reinterpret_cast<__nv_bfloat16*>(ws + L.theta), reinterpret_cast<__nv_bfloat16*>(ws + L.theta_lo), L.NsPad,
+                                     thi, tlo, s.P * s.B, s.Ns, s.Dt, dtm, st)));
     float* gw = reinterpret_cast<float*>(ws + L.gw);
     CK(cudaMemsetAsync(gw, 0, sizeof(float) * s.P * s.Lt, st));
     TIMED(13, 2, CK(launch_wgrad_dots(tt, dtm, reinterpret_cast<float*>(ws + L.gwt), reinterpret_cast<float*>(ws + L.rows), s.Lt, s.P, s.B, s.Nt,
@@ -366,7 +430,7 @@ extern "C" int basd_backward_finish(const basd_shape* shape, const basd_inputs* 
 // ------------------------------------------------------------------------------------------- marchenko_pastur_rank
 extern "C" int basd_mp_rank_workspace_bytes(int64_t M, int D, size_t* bytes) {
     if (!bytes || M < 1 || D < 8) return fail("invalid argument");
-    *bytes = align_up(2 * static_cast<size_t>(M) * D) + align_up(4 * 2 * (static_cast<size_t>(D) * D + D)) + align_up(4 * 2 * D) +
+    *bytes = 2 * align_up(2 * static_cast<size_t>(M) * D) + align_up(4 * 2 * (static_cast<size_t>(D) * D + D)) + align_up(4 * 2 * D) +
              2 * align_up(4 * 2 * static_cast<size_t>(D) * D) + 4096;
     return 0;
 }
@@ -380,14 +444,16 @@ extern "C" int basd_mp_rank(const void* features, int64_t M, int D, int dtype, i
     uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
     size_t off = 0;
     __nv_bfloat16* zb = reinterpret_cast<__nv_bfloat16*>(ws + off); off += align_up(2 * static_cast<size_t>(M) * D);
+    __nv_bfloat16* zl = reinterpret_cast<__nv_bfloat16*>(ws + off); off += align_up(2 * static_cast<size_t>(M) * D);
     float* stats = reinterpret_cast<float*>(ws + off); off += align_up(4 * 2 * (static_cast<size_t>(D) * D + D));
     float* evals = reinterpret_cast<float*>(ws + off); off += align_up(4 * 2 * D);
     float* evk = reinterpret_cast<float*>(ws + off); off += align_up(4 * 2 * static_cast<size_t>(D) * D);
     float* evc = reinterpret_cast<float*>(ws + off); off += align_up(4 * 2 * static_cast<size_t>(D) * D);
     int* ranks = reinterpret_cast<int*>(ws + off);
-    CK(launch_pack_bf16(features, dtype == BASD_DTYPE_BF16, 0, row_stride, 1, 1, static_cast<int>(M), D, zb, st));
+    const bool exact = dtype == BASD_DTYPE_BF16;             // fp32 features keep fp32-class precision as a split pair
+    CK(launch_pack_bf16(features, exact, 0, row_stride, 1, 1, static_cast<int>(M), D, zb, exact ? nullptr : zl, st));
     CK(cudaMemsetAsync(stats, 0, 4 * 2 * (static_cast<size_t>(D) * D + D), st));
-    CK(gemm_gram(zb, static_cast<size_t>(M), D, stats, st));
+    CK(gemm_gram(zb, exact ? nullptr : zl, static_cast<size_t>(M), D, stats, st));
     CK(launch_pooled_eig(stats, D, 1, 0, static_cast<float>(M), 1.f, ranks, evals, evk, evc, nullptr, st));
     CK(cudaMemcpyAsync(rank_out, ranks, sizeof(int), cudaMemcpyDeviceToDevice, st));
     return 0;

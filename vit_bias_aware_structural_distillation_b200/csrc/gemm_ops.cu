@@ -7,6 +7,7 @@
 #include <cstring>
 
 #include "spectral.h"
+#include "polar_gemm.cuh"
 #include "umma_gemm.cuh"
 
 namespace basd {
@@ -56,6 +57,29 @@ static int make_map(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t 
     return 0;
 }
 
+// bf16 split matrix stored column-block tiled: [batch][col / 64][row][col % 64]; box = [1][1][box_rows][64].
+static int make_map_tiled(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t col_blocks, uint64_t batch, uint64_t batch_pitch_elems,
+                          uint32_t box_rows) {
+    if (gemm_init_driver_api()) return 1;
+    if ((reinterpret_cast<uintptr_t>(ptr) & 127) || (batch_pitch_elems * 2) % 16) {
+        snprintf(g_gemm_err, sizeof g_gemm_err, "tiled TMA operand misaligned: ptr=%p batch_pitch=%llu", ptr, (unsigned long long)batch_pitch_elems);
+        return 1;
+    }
+    cuuint64_t dims[4] = {64, rows, col_blocks, batch};
+    cuuint64_t strides[3] = {128, rows * 128, batch_pitch_elems * 2};
+    cuuint32_t box[4] = {64, box_rows, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        snprintf(g_gemm_err, sizeof g_gemm_err, "cuTensorMapEncodeTiled (tiled) failed (%d) rows=%llu blocks=%llu batch=%llu box_rows=%u", (int)r,
+                 (unsigned long long)rows, (unsigned long long)col_blocks, (unsigned long long)batch, box_rows);
+        return 1;
+    }
+    return 0;
+}
+
 template <class Cfg, class Epi>
 static cudaError_t launch(const GemmMaps& maps, const GemmArgs& args, dim3 grid, cudaStream_t st) {
     auto kern = umma_gemm_kernel<Cfg, Epi>;
@@ -74,12 +98,14 @@ static inline int cdiv(long long a, long long b) { return static_cast<int>((a + 
 //                      A_MN   B_MN   BN   MT NA NB T  alias  stages
 using CfgProject = GemmCfg<false, false, 192, 1, 1, 2, 2, false, 3>;
 using CfgGram    = GemmCfg<true,  true,  192, 2, 1, 1, 1, false, 3>;
-using CfgTheta   = GemmCfg<false, true,  128, 2, 1, 1, 1, false, 4>;
+using CfgGram3   = GemmCfg<true,  true,  192, 2, 2, 2, 3, false, 2>;      // split operands: hi*hi + hi*lo + lo*hi
+using CfgTheta   = GemmCfg<false, true,  128, 2, 1, 1, 1, false, 4>;      // self test (single operands)
+using CfgTheta3  = GemmCfg<false, true,  128, 2, 2, 2, 3, false, 2>;      // split Theta x split mixed teacher
 template <int BN> using CfgTokenGram = GemmCfg<false, false, BN, 2, 2, 2, 3, true, 3>;
 using CfgTestTN  = GemmCfg<false, false, 192, 1, 1, 1, 1, false, 4>;
 
 cudaError_t gemm_project(const __nv_bfloat16* X, size_t M, int Dt, const __nv_bfloat16* Phi, const __nv_bfloat16* Plo, int Ds,
-                         __nv_bfloat16* Z, cudaStream_t st) {
+                         __nv_bfloat16* Z, __nv_bfloat16* Zlo, cudaStream_t st) {
     GemmMaps maps;
     memset(&maps, 0, sizeof maps);
     if (make_map(&maps.a[0], X, Dt, M, 1, Dt, M * Dt, 128)) return cudaErrorInvalidValue;
@@ -88,16 +114,21 @@ cudaError_t gemm_project(const __nv_bfloat16* X, size_t M, int Dt, const __nv_bf
     GemmArgs a;
     memset(&a, 0, sizeof a);
     a.kb_total = cdiv(Dt, GEMM_BK);
-    a.out = Z; a.ld_out = Ds; a.rows_valid = static_cast<int>(M); a.cols_valid = Ds; a.alpha = 1.f;
-    return launch<CfgProject, EpiStoreBf16>(maps, a, dim3(cdiv(Ds, CfgProject::kBN), cdiv(M, 128), 1), st);
+    a.out = Z; a.aux0 = Zlo; a.ld_out = Ds; a.rows_valid = static_cast<int>(M); a.cols_valid = Ds; a.alpha = 1.f;
+    return launch<CfgProject, EpiStoreSplit>(maps, a, dim3(cdiv(Ds, CfgProject::kBN), cdiv(M, 128), 1), st);
 }
 
-// G[batch] += Z[batch]^T Z[batch]; Z = [batches][M][Ds] contiguous; G batch stride given in floats.
-static cudaError_t gram_impl(const __nv_bfloat16* Z, size_t M, int Ds, int batches, float* G, long long g_stride, cudaStream_t st) {
+// G[batch] += Z[batch]^T Z[batch]; Z = [batches][M][Ds] contiguous (optionally a split hi/lo pair); G batch stride in floats.
+static cudaError_t gram_impl(const __nv_bfloat16* Z, const __nv_bfloat16* Zlo, size_t M, int Ds, int batches, float* G, long long g_stride,
+                             cudaStream_t st) {
     GemmMaps maps;
     memset(&maps, 0, sizeof maps);
     if (make_map(&maps.a[0], Z, Ds, M, batches, Ds, M * Ds, 64)) return cudaErrorInvalidValue;
     maps.b[0] = maps.a[0];
+    if (Zlo) {
+        if (make_map(&maps.a[1], Zlo, Ds, M, batches, Ds, M * Ds, 64)) return cudaErrorInvalidValue;
+        maps.b[1] = maps.a[1];
+    }
     GemmArgs a;
     memset(&a, 0, sizeof a);
     a.kb_total = cdiv(M, GEMM_BK);
@@ -105,11 +136,16 @@ static cudaError_t gram_impl(const __nv_bfloat16* Z, size_t M, int Ds, int batch
     a.n_splits = cdiv(a.kb_total, a.kb_per_split);
     a.a_batched = 1; a.b_batched = 1;
     a.out = G; a.out_batch_stride = g_stride; a.ld_out = Ds; a.rows_valid = Ds; a.cols_valid = Ds;
-    return launch<CfgGram, EpiAtomicAddF32>(maps, a, dim3(cdiv(Ds, CfgGram::kBN), cdiv(Ds, CfgGram::kMT * 128), batches * a.n_splits), st);
+    const dim3 grid(cdiv(Ds, CfgGram::kBN), cdiv(Ds, CfgGram::kMT * 128), batches * a.n_splits);
+    if (Zlo) return launch<CfgGram3, EpiAtomicAddF32>(maps, a, grid, st);
+    return launch<CfgGram, EpiAtomicAddF32>(maps, a, grid, st);
 }
-cudaError_t gemm_gram(const __nv_bfloat16* Z, size_t M, int Ds, float* G, cudaStream_t st) { return gram_impl(Z, M, Ds, 1, G, 0, st); }
-cudaError_t gemm_gram_batched(const __nv_bfloat16* Z, size_t M, int Ds, int batches, float* G, long long g_stride, cudaStream_t st) {
-    return gram_impl(Z, M, Ds, batches, G, g_stride, st);
+cudaError_t gemm_gram(const __nv_bfloat16* Z, const __nv_bfloat16* Zlo, size_t M, int Ds, float* G, cudaStream_t st) {
+    return gram_impl(Z, Zlo, M, Ds, 1, G, 0, st);
+}
+cudaError_t gemm_gram_batched(const __nv_bfloat16* Z, const __nv_bfloat16* Zlo, size_t M, int Ds, int batches, float* G, long long g_stride,
+                              cudaStream_t st) {
+    return gram_impl(Z, Zlo, M, Ds, batches, G, g_stride, st);
 }
 
 template <int BN>
@@ -135,22 +171,25 @@ cudaError_t gemm_token_gram(const __nv_bfloat16* Thi, const __nv_bfloat16* Tlo, 
     return cudaErrorInvalidValue;
 }
 
-cudaError_t gemm_theta_apply(const __nv_bfloat16* theta, int NsPad, const __nv_bfloat16* Thi, int batches, int Ns, int Dt,
-                             __nv_bfloat16* Dtm, cudaStream_t st) {
+cudaError_t gemm_theta_apply(const __nv_bfloat16* theta, const __nv_bfloat16* theta_lo, int NsPad, const __nv_bfloat16* Thi,
+                             const __nv_bfloat16* Tlo, int batches, int Ns, int Dt, __nv_bfloat16* Dtm, cudaStream_t st) {
     if (Ns > 256) {
         snprintf(g_gemm_err, sizeof g_gemm_err, "theta_apply: Ns=%d > 256 not supported yet", Ns);
         return cudaErrorInvalidValue;
     }
     GemmMaps maps;
     memset(&maps, 0, sizeof maps);
-    if (make_map(&maps.a[0], theta, NsPad, Ns, batches, NsPad, static_cast<uint64_t>(Ns) * NsPad, 128)) return cudaErrorInvalidValue;
+    // inner extent Ns (not NsPad): the pad columns are never read, TMA zero-fills them
+    if (make_map(&maps.a[0], theta, Ns, Ns, batches, NsPad, static_cast<uint64_t>(Ns) * NsPad, 128)) return cudaErrorInvalidValue;
+    if (make_map(&maps.a[1], theta_lo, Ns, Ns, batches, NsPad, static_cast<uint64_t>(Ns) * NsPad, 128)) return cudaErrorInvalidValue;
     if (make_map(&maps.b[0], Thi, Dt, Ns, batches, Dt, static_cast<uint64_t>(Ns) * Dt, 64)) return cudaErrorInvalidValue;
+    if (make_map(&maps.b[1], Tlo, Dt, Ns, batches, Dt, static_cast<uint64_t>(Ns) * Dt, 64)) return cudaErrorInvalidValue;
     GemmArgs a;
     memset(&a, 0, sizeof a);
     a.kb_total = cdiv(Ns, GEMM_BK);
     a.a_batched = 1; a.b_batched = 1;
     a.out = Dtm; a.out_batch_stride = static_cast<long long>(Ns) * Dt; a.ld_out = Dt; a.rows_valid = Ns; a.cols_valid = Dt; a.alpha = 1.f;
-    return launch<CfgTheta, EpiStoreBf16>(maps, a, dim3(cdiv(Dt, CfgTheta::kBN), 1, batches), st);
+    return launch<CfgTheta3, EpiStoreBf16>(maps, a, dim3(cdiv(Dt, CfgTheta3::kBN), 1, batches), st);
 }
 
 cudaError_t gemm_student_grad(const __nv_bfloat16* S, size_t M, int Ds, const __nv_bfloat16* Ghi, const __nv_bfloat16* Glo,
@@ -167,6 +206,61 @@ cudaError_t gemm_student_grad(const __nv_bfloat16* S, size_t M, int Ds, const __
     a.out = out; a.ld_out = Ds; a.rows_valid = static_cast<int>(M); a.cols_valid = Ds;
     a.aux0 = gdir; a.aux1 = corr; a.aux2 = scale_ptr; a.alpha = scale_host; a.beta = out_is_bf16 ? 1.f : 0.f;
     return launch<CfgProject, EpiStudentGrad>(maps, a, dim3(cdiv(Ds, CfgProject::kBN), cdiv(M, 128), 1), st);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// polar_gemm: one CTA per problem, run-time tile sizes (polar_gemm.cuh)
+// ---------------------------------------------------------------------------------------------------
+cudaError_t polar_gemm(bool b_mn, const SplitMat& A, const SplitMat& B, int batches, PolarGemmArgs& a, cudaStream_t st) {
+    const int m_rows = A.rows, K = A.inner;
+    const int n_cols = b_mn ? B.inner : B.rows;
+    if (m_rows > 256 || n_cols > 256 || (b_mn ? B.rows : B.inner) != K) {
+        snprintf(g_gemm_err, sizeof g_gemm_err, "polar_gemm: unsupported sizes m=%d n=%d k=%d", m_rows, n_cols, K);
+        return cudaErrorInvalidValue;
+    }
+    a.m_rows = m_rows; a.n_cols = n_cols; a.k_total = K;
+    a.n_mt = (m_rows + 127) / 128;
+    a.n_items = batches * a.n_mt;
+    a.a_rows_tile[0] = m_rows >= 128 ? 128 : (m_rows + 63) / 64 * 64;
+    a.a_rows_tile[1] = m_rows > 128 ? (m_rows - 128 + 63) / 64 * 64 : 0;
+    a.bn_mma = (n_cols + 15) / 16 * 16;
+    a.b_groups = (a.bn_mma + 63) / 64;
+    PolarGemmMaps maps;
+    memset(&maps, 0, sizeof maps);
+    const __nv_bfloat16* ap[2] = {A.hi, A.lo};
+    const __nv_bfloat16* bp[2] = {B.hi, B.lo};
+    for (int i = 0; i < 2; ++i) {
+        if (make_map_tiled(&maps.a[i], ap[i], A.rows, (A.inner + 63) / 64, batches, A.batch_stride, 64)) return cudaErrorInvalidValue;
+        // K-major B: one box of bn_mma rows per k-block; MN-major B: 64 (k) x 64 (n) boxes of the [K][n_cols] matrix
+        if (make_map_tiled(&maps.b[i], bp[i], B.rows, (B.inner + 63) / 64, batches, B.batch_stride, b_mn ? 64 : a.bn_mma)) return cudaErrorInvalidValue;
+    }
+    const int b_bytes = b_mn ? a.b_groups * 8192 : a.bn_mma * 128;
+    const int stage_bytes = 2 * 16384 + 2 * b_bytes;
+    int stages = (232448 - 1024 - 256) / stage_bytes;
+    if (stages > 4) stages = 4;
+    if (stages < 1) {
+        snprintf(g_gemm_err, sizeof g_gemm_err, "polar_gemm: one stage (%d B) exceeds shared memory", stage_bytes);
+        return cudaErrorInvalidValue;
+    }
+    a.stages = stages;
+    const int smem = stages * stage_bytes + 1024 + 256;
+    auto kern = b_mn ? polar_gemm_kernel<true> : polar_gemm_kernel<false>;
+    static bool configured[2] = {false, false};
+    static int sm_count = 0;
+    if (!configured[b_mn]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        if (e != cudaSuccess) return e;
+        configured[b_mn] = true;
+    }
+    if (!sm_count) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (sm_count <= 0) sm_count = 148;
+    }
+    const int grid = a.n_items < sm_count ? a.n_items : sm_count;
+    kern<<<grid, PG_THREADS, smem, st>>>(maps, a);
+    return cudaGetLastError();
 }
 
 // variant 0: C[M][N] = A[M][K] B[N][K]^T          (both K-major)

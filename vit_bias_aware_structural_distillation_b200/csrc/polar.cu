@@ -1,0 +1,278 @@
+// Procrustes core of the BASD loss (relational.py:36-50 and its backward) as a Newton-Schulz polar
+// iteration on the tensor cores.
+//
+// Per (extraction point, sample):  C = s_w^T t_w  (D_s x D_t),  loss_b = tr_s + tr_t - 2 ||C||_*.
+// The polar factor R of C (C = R H) gives ||C||_* = <R, C>, d||C||_*/ds_w = t_w R^T, d||C||_*/dt_w = s_w R.
+// R is never formed: the iterate is kept factored as X_k = W_k t_w with W_k (D_s x N), so that with the weighted,
+// centred teacher token Gram K_t = t_w t_w^T (N x N)
+//     A_k = X_k X_k^T = W_k K_t W_k^T,      W_{k+1} = (a_k I + b_k A_k + c_k A_k^2) W_k,      W_0 = s_w^T / ||C||_F
+// and at convergence   ||C||_* = <K_t W^T, s_w>,   d/ds_w = K_t W^T,   d/dt_w = (s_w W) t_w.
+// (a_k, b_k, c_k) are the minimax odd quintics for the shrinking interval [l_k, 1.03] starting at l_0 = 1e-5
+// (relative to ||C||_F): every singular value above l_0 ends within 4e-6 of 1 after 11 steps; the 3 % head room
+// above 1 keeps rounding from pushing the top singular value into the divergent region.
+// All products are one-CTA-per-problem tcgen05 GEMMs on split-bf16 operands (polar_gemm.cuh).
+// Requires rank(C) = D_s, i.e. D_s <= N - 1 and a teacher token Gram of rank >= D_s.
+#include "cta_linalg.cuh"
+#include "polar_gemm.cuh"
+#include "spectral.h"
+
+namespace basd {
+
+namespace {
+
+constexpr int kPolarSteps = 11;
+// python: minimax odd quintic on [l_k, 1.03], rescaled to max 1 (tools/ns_schedule.py)
+const float kPolarCoef[kPolarSteps][3] = {
+    {4.133133694f, -11.568007891f, 8.094329945f},
+    {4.133075743f, -11.567549897f, 8.093949730f},
+    {4.132823273f, -11.565542164f, 8.092281565f},
+    {4.131776586f, -11.557237244f, 8.085383350f},
+    {4.127460592f, -11.523021954f, 8.056966863f},
+    {4.109607285f, -11.382227351f, 7.940116878f},
+    {4.035887013f, -10.813078843f, 7.469139329f},
+    {3.739866666f, -8.719702318f, 5.758941425f},
+    {2.851310847f, -4.084405728f, 2.179200157f},
+    {1.975041429f, -1.454643745f, 0.478951299f},
+    {1.848140342f, -1.196846510f, 0.348702652f},
+};
+
+__device__ __forceinline__ void store_split(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t idx, float v) {
+    const __nv_bfloat16 h = __float2bfloat16(v);
+    hi[idx] = h;
+    lo[idx] = __float2bfloat16(v - __bfloat162float(h));
+}
+
+// ------------------------------------------------------------------------------------------------
+// prep_student: s_w = sqrt(a) (s - mu_s)  ->  SW [N][Ds] (split), W_0 = s_w^T [Ds][Np] (split), ksd, tr_s
+// one CTA per problem; the whole s_w tile lives in shared memory (fp32, padded rows)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+polar_prep_student_kernel(PolarArgs g) {
+    extern __shared__ float sm[];
+    const int N = g.Ns, D = g.Ds, ldS = D + 1;
+    float* sw = sm;                                   // [N][D+1]
+    float* a_s = sw + static_cast<size_t>(N) * ldS;   // [N]
+    float* q_s = a_s + N;
+    float* mu = q_s + N;                              // [D]
+    float* red = mu + D;                              // 40
+    const int prob = blockIdx.x;
+    const int i = prob / g.B, b = prob % g.B;
+    const __nv_bfloat16* S = g.student[i] + static_cast<size_t>(b) * N * D;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        const float a = g.a[static_cast<size_t>(prob) * N + n];
+        a_s[n] = a;
+        q_s[n] = sqrtf(a);
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float m = 0.f;
+        for (int n = 0; n < N; ++n) m = fmaf(a_s[n], __bfloat162float(S[static_cast<size_t>(n) * D + d]), m);
+        mu[d] = m;
+    }
+    __syncthreads();
+    __nv_bfloat16* swh = g.SW.hi + prob * g.SW.batch_stride;
+    __nv_bfloat16* swl = g.SW.lo + prob * g.SW.batch_stride;
+    for (int t = threadIdx.x; t < N * D; t += blockDim.x) {
+        const int n = t / D, d = t % D;
+        const float v = q_s[n] * (__bfloat162float(S[t]) - mu[d]);
+        sw[n * ldS + d] = v;
+        store_split(swh, swl, g.SW.at(n, d), v);
+    }
+    __syncthreads();
+    float* ksd = g.vec + static_cast<size_t>(prob) * 4 * N;
+    float part = 0.f;
+    {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+        for (int n = warp; n < N; n += nw) {
+            float s = 0.f;
+            for (int d = lane; d < D; d += 32) { const float v = sw[n * ldS + d]; s = fmaf(v, v, s); }
+            s = warp_sum(s);
+            if (lane == 0) { ksd[n] = s; part += s; }
+        }
+    }
+    const float tr_s = cta_sum(part, red);
+    if (threadIdx.x == 0) g.scal[prob * 4 + 1] = tr_s;
+    __nv_bfloat16* wh = g.W.hi + prob * g.W.batch_stride;
+    __nv_bfloat16* wl = g.W.lo + prob * g.W.batch_stride;
+    const int Np = (N + 63) / 64 * 64;                   // padding columns of the last block are stored as zeros
+    for (int t = threadIdx.x; t < D * Np; t += blockDim.x) {
+        const int n = t % 64 + (t / (64 * D)) * 64, d = (t / 64) % D;        // t runs in storage order
+        store_split(wh, wl, t, n < N ? sw[n * ldS + d] : 0.f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// prep_teacher: K_t = q (Ktt - m 1^T - 1 m^T + mm) q  (weighted + centred token Gram, split), diag, tr_t
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+polar_prep_teacher_kernel(PolarArgs g) {
+    extern __shared__ float sm[];
+    const int N = g.Ns;
+    float* a_s = sm;                 // [N]
+    float* q_s = a_s + N;
+    float* m_s = q_s + N;
+    float* red = m_s + N;            // 40
+    const int prob = blockIdx.x;
+    const float* Ktt = g.Ktt + static_cast<size_t>(prob) * N * N;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        const float a = g.a[static_cast<size_t>(prob) * N + n];
+        a_s[n] = a;
+        q_s[n] = sqrtf(a);
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int n = warp; n < N; n += nw) {
+        float s = 0.f;
+        for (int m = lane; m < N; m += 32) s = fmaf(Ktt[static_cast<size_t>(n) * N + m], a_s[m], s);
+        s = warp_sum(s);
+        if (lane == 0) m_s[n] = s;
+    }
+    __syncthreads();
+    float part = 0.f;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) part += a_s[n] * m_s[n];
+    const float mm = cta_sum(part, red);
+    float* ktd = g.vec + static_cast<size_t>(prob) * 4 * N + N;
+    part = 0.f;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        const float v = a_s[n] * (Ktt[static_cast<size_t>(n) * N + n] - 2.f * m_s[n] + mm);
+        ktd[n] = v;
+        part += v;
+    }
+    const float tr_t = cta_sum(part, red);
+    if (threadIdx.x == 0) g.scal[prob * 4 + 2] = tr_t;
+    __nv_bfloat16* kh = g.Kt.hi + prob * g.Kt.batch_stride;
+    __nv_bfloat16* kl = g.Kt.lo + prob * g.Kt.batch_stride;
+    const int Np = (N + 63) / 64 * 64;
+    for (int t = threadIdx.x; t < N * Np; t += blockDim.x) {
+        const int m = t % 64 + (t / (64 * N)) * 64, n = (t / 64) % N;        // storage order: [col block][row n][64]
+        float v = 0.f;
+        if (m < N) v = q_s[n] * q_s[m] * (Ktt[static_cast<size_t>(n) * N + m] - m_s[n] - m_s[m] + mm);
+        store_split(kh, kl, t, v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// finish: nuclear norm, direct student gradient, importance gradient, per-sample loss
+//   Gsw = K_t W^T = d nuc / d s_w  [N][Ds]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+polar_finish_kernel(PolarArgs g) {
+    extern __shared__ float sm[];
+    const int N = g.Ns, D = g.Ds;
+    float* dots = sm;                // [N]
+    float* ga = dots + N;            // [N]
+    float* red = ga + N;             // 40
+    const int prob = blockIdx.x;
+    const float* G = g.Gsw + static_cast<size_t>(prob) * N * D;
+    const __nv_bfloat16* swh = g.SW.hi + prob * g.SW.batch_stride;
+    const __nv_bfloat16* swl = g.SW.lo + prob * g.SW.batch_stride;
+    const float* a = g.a + static_cast<size_t>(prob) * N;
+    float* gdir = g.gdir + static_cast<size_t>(prob) * N * D;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int n = warp; n < N; n += nw) {
+        const float qn = sqrtf(a[n]);
+        float s = 0.f;
+        for (int d = lane; d < D; d += 32) {
+            const size_t idx = g.SW.at(n, d);
+            const float sw = __bfloat162float(swh[idx]) + __bfloat162float(swl[idx]);
+            const float gv = G[static_cast<size_t>(n) * D + d];
+            s = fmaf(sw, gv, s);
+            gdir[static_cast<size_t>(n) * D + d] = qn * (2.f * sw - 2.f * gv);
+        }
+        s = warp_sum(s);
+        if (lane == 0) dots[n] = s;
+    }
+    __syncthreads();
+    const float* ksd = g.vec + static_cast<size_t>(prob) * 4 * N;
+    const float* ktd = ksd + N;
+    float p_nuc = 0.f, p_gdot = 0.f;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        p_nuc += dots[n];
+        const float v = (ksd[n] + ktd[n] - 2.f * dots[n]) / a[n];
+        ga[n] = v;
+        p_gdot += v * a[n];
+    }
+    const float nuc = cta_sum(p_nuc, red);
+    const float gdot = cta_sum(p_gdot, red);
+    const float inv_ssum = 1.f / g.ssum[prob];
+    for (int n = threadIdx.x; n < N; n += blockDim.x) g.gwt[static_cast<size_t>(prob) * N + n] = (ga[n] - gdot) * inv_ssum;
+    if (threadIdx.x == 0) {
+        const float tr_s = g.scal[prob * 4 + 1], tr_t = g.scal[prob * 4 + 2];
+        g.loss_b[prob] = tr_s + tr_t - 2.f * nuc;
+        if (g.dbg) {
+            g.dbg[prob * 5 + 0] = nuc; g.dbg[prob * 5 + 1] = tr_s; g.dbg[prob * 5 + 2] = tr_t;
+            g.dbg[prob * 5 + 3] = static_cast<float>(kPolarSteps); g.dbg[prob * 5 + 4] = g.fro2[prob];
+        }
+    }
+}
+
+}  // namespace
+
+#define PCK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return _e; } while (0)
+
+cudaError_t launch_polar_procrustes(const PolarArgs& g, cudaStream_t st, int* launches) {
+    const int N = g.Ns, D = g.Ds, nprob = g.n_problems;
+    int count = 0;
+    {
+        const size_t smem = (static_cast<size_t>(N) * (D + 1) + 2 * N + D + 64) * sizeof(float);
+        PCK(cudaFuncSetAttribute(polar_prep_student_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        polar_prep_student_kernel<<<nprob, 256, smem, st>>>(g);
+        PCK(cudaGetLastError());
+        polar_prep_teacher_kernel<<<nprob, 256, (3 * N + 64) * sizeof(float), st>>>(g);
+        PCK(cudaGetLastError());
+        count += 2;
+    }
+    float* fro2_dense = g.fro2;                // ||C||_F^2 per problem, accumulated by the first A = T W^T
+    PCK(cudaMemsetAsync(fro2_dense, 0, sizeof(float) * nprob, st));
+
+    // Step 0 runs on the unnormalised W_0 = s_w^T; r = 1 / ||C||_F^2 (trace of W_0 K_t W_0^T, accumulated by the first
+    // product) enters the later epilogues of that step as a per-problem scalar.
+    SplitMat Wc = g.W, Wn = g.W2;
+    for (int k = 0; k < kPolarSteps; ++k) {
+        const float ca = kPolarCoef[k][0], cb = kPolarCoef[k][1], cc = kPolarCoef[k][2];
+        const bool first = k == 0;
+        const float* norm = first ? fro2_dense : nullptr;
+        PolarGemmArgs a;
+        // G1: T = W K_t                      (step 0: ||C||_F^2 = <T, W_0>)
+        memset(&a, 0, sizeof a);
+        a.epi = PG_EPI_SPLIT; a.out_hi = g.T.hi; a.out_lo = g.T.lo; a.out_stride = g.T.batch_stride; a.scale_c = 1.f;
+        if (first) { a.trace = fro2_dense; a.trace_mode = 2; a.aux_hi = Wc.hi; a.aux_lo = Wc.lo; }
+        PCK(polar_gemm(false, Wc, g.Kt, nprob, a, st));
+        // G2: A = T W^T,  A2 = b I + c r A
+        memset(&a, 0, sizeof a);
+        a.epi = PG_EPI_SPLIT; a.out_hi = g.A.hi; a.out_lo = g.A.lo; a.out_stride = g.A.batch_stride; a.scale_c = 1.f;
+        a.out2_hi = g.A2.hi; a.out2_lo = g.A2.lo; a.d1 = cb; a.d2 = cc; a.p2 = first ? 1.f : 0.f; a.norm2 = norm;
+        PCK(polar_gemm(false, g.T, Wc, nprob, a, st));
+        // G3: Bm = a I + r A A2              (= a I + b (rA) + c (rA)^2)
+        memset(&a, 0, sizeof a);
+        a.epi = PG_EPI_SPLIT; a.out_hi = g.Bm.hi; a.out_lo = g.Bm.lo; a.out_stride = g.Bm.batch_stride;
+        a.scale_c = 1.f; a.scale_p = first ? 1.f : 0.f; a.diag_add = ca; a.norm2 = norm;
+        PCK(polar_gemm(false, g.A, g.A2, nprob, a, st));
+        // G4: W_next = sqrt(r) Bm W          (W enters as the MN-major B operand; ping-pong buffers)
+        memset(&a, 0, sizeof a);
+        a.epi = PG_EPI_SPLIT; a.out_hi = Wn.hi; a.out_lo = Wn.lo; a.out_stride = Wn.batch_stride;
+        a.scale_c = 1.f; a.scale_p = first ? 0.5f : 0.f; a.norm2 = norm;
+        PCK(polar_gemm(true, g.Bm, Wc, nprob, a, st));
+        const SplitMat tmp = Wc; Wc = Wn; Wn = tmp;
+        count += 4;
+    }
+    {
+        PolarGemmArgs a;
+        // Gsw = K_t W^T  [N][Ds]
+        memset(&a, 0, sizeof a);
+        a.epi = PG_EPI_F32; a.out_f32 = g.Gsw; a.out_f32_stride = static_cast<long long>(N) * D; a.ld_f32 = D;
+        PCK(polar_gemm(false, g.Kt, Wc, nprob, a, st));
+        // Psi = s_w W  [N][N]  -> Theta' = 2 (diag(a) - q Psi q - a a^T), stored as a split pair
+        memset(&a, 0, sizeof a);
+        a.epi = PG_EPI_THETA; a.out_hi = g.theta; a.out_lo = g.theta_lo; a.out_stride = static_cast<long long>(N) * g.NsPad; a.ld_out = g.NsPad;
+        a.vec_a = g.a;
+        PCK(polar_gemm(true, g.SW, Wc, nprob, a, st));
+        polar_finish_kernel<<<nprob, 256, (2 * N + 64) * sizeof(float), st>>>(g);
+        PCK(cudaGetLastError());
+        count += 3;
+    }
+    if (launches) *launches = count;
+    return cudaSuccess;
+}
+
+}  // namespace basd

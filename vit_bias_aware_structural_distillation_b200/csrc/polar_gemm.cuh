@@ -1,0 +1,271 @@
+// Persistent batched small-matrix tcgen05 GEMM with run-time tile sizes, for the Newton-Schulz polar iteration of
+// the Procrustes core (polar.cu).  A launch computes, for every problem z of a batch,
+//     out[z] (m_rows x n_cols)  =  A[z] (m_rows x K)  *  B[z] (n_cols x K)^T
+// on bf16 "split" operand pairs (hi, lo = bf16(x - hi)): the three MMAs hi*hi + hi*lo + lo*hi accumulate into the
+// same TMEM tile and give fp32-class products (relative error ~2^-17) at bf16 tensor-core rate.
+//   A : K-major ([m_rows][K]), loaded as 64-row TMA boxes, SWIZZLE_128B
+//   B : K-major ([n_cols][K]) or MN-major ([K][n_cols]: the same buffer used transposed)
+// Global layout of every split matrix is COLUMN-BLOCK TILED: [problem][col / 64][row][col % 64], so that each TMA box
+// (rows x 64 columns) is one contiguous run of HBM (row-major storage with a 400-byte pitch measured 37 % of the
+// copy bandwidth: every 128-byte box row opened its own DRAM page).
+// Work item = (problem, 128-row tile of the output).  One CTA per SM loops over its items; the shared-memory operand
+// ring and two TMEM accumulator buffers are carried across items, so the TMA loads and MMAs of item i+1 overlap the
+// epilogue of item i.  Warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue (one TMEM lane quadrant each).
+// Epilogues only store (no global reads on the critical path) except the one-off Frobenius trace of step 0.
+#pragma once
+#include "ptx.cuh"
+
+namespace basd {
+
+constexpr int PG_THREADS = 192;
+constexpr int PG_BK = 64;
+
+enum PolarEpi : int {
+    PG_EPI_SPLIT = 0,       // out = split(scale * acc + diag_add * I); optional out2 = split(d1 * I + d2 r^p2 * acc); optional trace
+    PG_EPI_F32 = 2,         // out_f32 = acc
+    PG_EPI_THETA = 3,       // out = split(2 (diag(a) - q acc q^T - a a^T))   (teacher side)
+};
+
+struct PolarGemmMaps {
+    CUtensorMap a[2];
+    CUtensorMap b[2];
+};
+
+struct PolarGemmArgs {
+    int m_rows, n_cols, k_total;     // valid sizes
+    int n_mt;                        // 128-row tiles per problem
+    int n_items;                     // batches * n_mt
+    int a_rows_tile[2];              // rows of A loaded for tile 0 / 1 (multiples of 64)
+    int bn_mma;                      // UMMA N (multiple of 16, >= n_cols)
+    int b_groups;                    // MN-major B: 64-column groups loaded per k-block
+    int stages;
+    int epi;
+    // primary output (split pair, per-problem stride in elements)
+    __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; long long out_stride; int ld_out;   // tiled (SPLIT) or row-major with ld_out (THETA)
+    const float* norm2;              // if non-null r = 1 / norm2[z], else r = 1
+    float scale_c, scale_p;          // scale = scale_c * r^scale_p
+    float diag_add;
+    // secondary output, same layout as the primary
+    __nv_bfloat16* out2_hi; __nv_bfloat16* out2_lo; float d1, d2, p2;
+    // trace[z] += sum(diag(acc)) (mode 1) or sum(acc .* aux) (mode 2; aux = split pair laid out like the primary output)
+    float* trace; int trace_mode; const __nv_bfloat16* aux_hi; const __nv_bfloat16* aux_lo;
+    float* out_f32; long long out_f32_stride; int ld_f32;
+    const float* vec_a;              // THETA: importance a [z][m_rows]
+};
+
+__device__ __forceinline__ void pg_store_split16(__nv_bfloat16* ph, __nv_bfloat16* pl, const float* v, int nv) {
+    if (nv == 16) {
+        uint32_t hw[8], lw[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const __nv_bfloat16 h0 = __float2bfloat16(v[2 * i]), h1 = __float2bfloat16(v[2 * i + 1]);
+            __nv_bfloat162 hv; hv.x = h0; hv.y = h1;
+            hw[i] = *reinterpret_cast<uint32_t*>(&hv);
+            lw[i] = pack_bf16x2(v[2 * i] - __bfloat162float(h0), v[2 * i + 1] - __bfloat162float(h1));
+        }
+        reinterpret_cast<uint4*>(ph)[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        reinterpret_cast<uint4*>(ph)[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+        reinterpret_cast<uint4*>(pl)[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        reinterpret_cast<uint4*>(pl)[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+    } else {
+        for (int i = 0; i < nv; ++i) {
+            const __nv_bfloat16 h = __float2bfloat16(v[i]);
+            ph[i] = h;
+            pl[i] = __float2bfloat16(v[i] - __bfloat162float(h));
+        }
+    }
+}
+
+template <bool B_MN>
+__global__ void __launch_bounds__(PG_THREADS, 1)
+polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArgs args) {
+    extern __shared__ uint8_t pg_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(pg_smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int kABytes = 128 * 128;                 // one 128-row A tile per operand buffer
+    const int b_bytes = B_MN ? args.b_groups * 8192 : args.bn_mma * 128;
+    const int stage_bytes = 2 * kABytes + 2 * b_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + args.stages * stage_bytes);
+    uint64_t* empty_bar = full_bar + args.stages;
+    uint64_t* tmem_full_bar = empty_bar + args.stages;         // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;              // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_kb = (args.k_total + PG_BK - 1) / PG_BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < args.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 4); }
+        fence_mbar_init();
+        tma_prefetch_desc(&maps.a[0]); tma_prefetch_desc(&maps.a[1]);
+        tma_prefetch_desc(&maps.b[0]); tma_prefetch_desc(&maps.b[1]);
+    }
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < static_cast<uint32_t>(2 * args.bn_mma)) tmem_cols <<= 1;
+    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int it = 0;
+            for (int w = blockIdx.x; w < args.n_items; w += gridDim.x) {
+                const int z = w / args.n_mt, mt = w % args.n_mt;
+                const int a_rows = args.a_rows_tile[mt];
+                const uint32_t tx = 2 * a_rows * 128 + 2 * b_bytes;
+                for (int kb = 0; kb < n_kb; ++kb, ++it) {
+                    const int s = it % args.stages;
+                    const uint32_t ph = (it / args.stages) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[s], tx);
+                    uint8_t* st = smem + s * stage_bytes;
+                    for (int i = 0; i < 2; ++i) {
+                        uint8_t* dst = st + i * kABytes;
+                        for (int g = 0; g < a_rows / 64; ++g)
+                            tma_load_4d(dst + g * 8192, &maps.a[i], &full_bar[s], 0, mt * 128 + g * 64, kb, z);
+                    }
+                    for (int i = 0; i < 2; ++i) {
+                        uint8_t* dst = st + 2 * kABytes + i * b_bytes;
+                        if (B_MN) {
+                            for (int g = 0; g < args.b_groups; ++g)
+                                tma_load_4d(dst + g * 8192, &maps.b[i], &full_bar[s], 0, kb * PG_BK, g, z);
+                        } else {
+                            tma_load_4d(dst, &maps.b[i], &full_bar[s], 0, 0, kb, z);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        const uint32_t idesc = umma_idesc_bf16(128, args.bn_mma, false, B_MN);
+        int it = 0, item = 0;
+        for (int w = blockIdx.x; w < args.n_items; w += gridDim.x, ++item) {
+            const int acc = item & 1;
+            const uint32_t acc_ph = (item >> 1) & 1;
+            mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);           // epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * args.bn_mma;
+            for (int kb = 0; kb < n_kb; ++kb, ++it) {
+                const int s = it % args.stages;
+                const uint32_t ph = (it / args.stages) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t st = smem_u32(smem + s * stage_bytes);
+                    int ksteps = (args.k_total - kb * PG_BK + 15) / 16;
+                    if (ksteps > 4) ksteps = 4;
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) {                // hi*hi, hi*lo, lo*hi
+                        const uint32_t a_base = st + (t == 2 ? kABytes : 0);
+                        const uint32_t b_base = st + 2 * kABytes + (t == 1 ? b_bytes : 0);
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            const uint64_t adesc = umma_smem_desc(a_base + ks * 32, 16, 1024);
+                            const uint64_t bdesc = B_MN ? umma_smem_desc(b_base + ks * 2048, 8192, 1024)
+                                                        : umma_smem_desc(b_base + ks * 32, 16, 1024);
+                            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > 0 || t > 0 || ks > 0) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(&empty_bar[s]);
+                    if (kb == n_kb - 1) umma_commit(&tmem_full_bar[acc]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
+        const int q = warp & 3;
+        int item = 0;
+        for (int w = blockIdx.x; w < args.n_items; w += gridDim.x, ++item) {
+            const int z = w / args.n_mt, mt = w % args.n_mt;
+            const int acc = item & 1;
+            const uint32_t acc_ph = (item >> 1) & 1;
+            mbar_wait(&tmem_full_bar[acc], acc_ph);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * args.bn_mma;
+            const int row = mt * 128 + q * 32 + lane;
+            const bool row_ok = row < args.m_rows;
+            float r = 1.f;
+            if (args.norm2) r = 1.f / args.norm2[z];
+            const float scale = args.scale_c * (args.scale_p == 0.f ? 1.f : powf(r, args.scale_p));
+            const float d2r = args.d2 * (args.p2 == 0.f ? 1.f : powf(r, args.p2));
+            float a_row = 0.f, q_row = 0.f;
+            if (args.epi == PG_EPI_THETA && row_ok) {
+                a_row = args.vec_a[static_cast<long long>(z) * args.m_rows + row];
+                q_row = sqrtf(a_row);
+            }
+            float tr_part = 0.f;
+            for (int c = 0; c < args.bn_mma; c += 16) {
+                float v[16];
+                tmem_ld16(t_addr + c, v);
+                if (!row_ok || (c >= args.n_cols && args.epi != PG_EPI_SPLIT)) continue;
+                const int nv = min(16, args.n_cols - c);
+                if (args.epi == PG_EPI_F32) {
+                    float* p = args.out_f32 + z * args.out_f32_stride + static_cast<long long>(row) * args.ld_f32 + c;
+                    if (nv == 16 && (args.ld_f32 & 3) == 0) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            reinterpret_cast<float4*>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    } else {
+                        for (int i = 0; i < nv; ++i) p[i] = v[i];
+                    }
+                    continue;
+                }
+                if (args.epi == PG_EPI_THETA) {
+                    const long long off = z * args.out_stride + static_cast<long long>(row) * args.ld_out + c;
+                    const float* av = args.vec_a + static_cast<long long>(z) * args.m_rows;
+                    float x[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        x[i] = 0.f;
+                        if (i < nv) {
+                            const float ac = av[c + i];
+                            float t = -q_row * v[i] * sqrtf(ac) - a_row * ac;
+                            if (c + i == row) t += a_row;
+                            x[i] = 2.f * t;
+                        }
+                    }
+                    pg_store_split16(args.out_hi + off, args.out_lo + off, x, nv);
+                    continue;
+                }
+                // tiled split output: [col block][row][64]; the zero accumulators of the padding columns are stored too
+                const long long off = z * args.out_stride + (static_cast<long long>(c >> 6) * args.m_rows + row) * 64 + (c & 63);
+                if (args.trace) {
+                    if (args.trace_mode == 1) {
+                        if (row >= c && row < c + nv) tr_part += v[row - c];
+                    } else {
+                        for (int i = 0; i < nv; ++i)
+                            tr_part = fmaf(v[i], __bfloat162float(args.aux_hi[off + i]) + __bfloat162float(args.aux_lo[off + i]), tr_part);
+                    }
+                }
+                if (args.out2_hi) {
+                    float y[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) y[i] = d2r * v[i] + ((c + i == row) ? args.d1 : 0.f);
+                    pg_store_split16(args.out2_hi + off, args.out2_lo + off, y, 16);
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = scale * v[i] + ((c + i == row) ? args.diag_add : 0.f);
+                pg_store_split16(args.out_hi + off, args.out_lo + off, v, 16);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            if (args.trace) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) tr_part += __shfl_xor_sync(0xffffffffu, tr_part, o);
+                if (lane == 0) atomicAdd(args.trace + z, tr_part);
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+}  // namespace basd

@@ -3,8 +3,7 @@
 //   angles_kernel       principal angles, Grassmann distance and its pre-computed backward
 //                       (layer_selector.py:95-105)
 //   mix_weights_kernel  softmax mixing weights                              (layer_selector.py:107-108)
-//   procrustes_kernel   per-sample nuclear norm + closed-form gradients in token space
-//                       (relational.py:36-50)
+//   (the per-sample Procrustes core lives in polar.cu)
 //   selector_bwd_kernel softmax/temperature backward + Gamma assembly       
 #include "spectral.h"
 
@@ -253,205 +252,6 @@ __global__ void mix_weights_kernel(const float* __restrict__ d2, const float* __
 }
 
 // ------------------------------------------------------------------------------------------------
-// procrustes_kernel: persistent CTAs loop over the P*B (extraction point, sample) problems.
-// Factor side = teacher token Gram (requires Ds <= Ns); see DESIGN.md "Procrustes core".
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kSpectralThreads, 1)
-procrustes_kernel(ProcrustesArgs g) {
-    extern __shared__ float sm[];
-    const int N = g.Ns, D = g.Ds;
-    const int ld = jacobi_ld(N);
-    const int ncol = max(N, D);
-    float* A = sm;                                   // ld x ncol
-    float* a_s = A + static_cast<size_t>(ld) * ncol; // [N]
-    float* q_s = a_s + N;
-    float* m_s = q_s + N;                            // Ktt a
-    float* ktd = m_s + N;                            // diag(K_t)
-    float* ksd = ktd + N;                            // diag(K_s)
-    float* dots = ksd + N;                           // s_w,n . G_sw,n
-    float* mu_s = dots + N;                          // [D]
-    float* sig = mu_s + D;                           // [D]
-    float* red = sig + D;                            // 40
-    __shared__ int s_bad;
-
-    const size_t scr_per = procrustes_scratch_floats(N, D);
-    float* scr = g.scratch + static_cast<size_t>(blockIdx.x) * scr_per;
-    float* Lg = scr;                                 // [c][r] column-major, ld
-    float* SWr = Lg + static_cast<size_t>(ld) * N;   // [n][d] row-major
-    float* Y0r = SWr + static_cast<size_t>(N) * D;   // [n][d]
-    float* Og = Y0r + static_cast<size_t>(N) * D;    // [m][n]
-    float* Xg = Og + static_cast<size_t>(N) * N;
-    float* T2r = Xg + static_cast<size_t>(N) * N;    // [n][d]
-    float* Linvg = T2r + static_cast<size_t>(N) * D; // [c][r] column-major, ld
-    float* T3T = Linvg + static_cast<size_t>(ld) * N;// [m'][n]
-
-    for (int prob = blockIdx.x; prob < g.n_problems; prob += gridDim.x) {
-        const int i = prob / g.B, b = prob % g.B;
-        const float* Ktt = g.Ktt + static_cast<size_t>(prob) * N * N;
-        const float* a_in = g.a + static_cast<size_t>(prob) * N;
-        const __nv_bfloat16* S = g.student[i] + static_cast<size_t>(b) * g.student_batch_stride;
-        if (threadIdx.x == 0) s_bad = 0;
-        for (int n = threadIdx.x; n < N; n += blockDim.x) {
-            a_s[n] = a_in[n];
-            q_s[n] = sqrtf(a_in[n]);
-            dots[n] = 0.f;
-        }
-        __syncthreads();
-        // ---- S0: weighted mean, s_w, diag(K_s)
-        for (int d = threadIdx.x; d < D; d += blockDim.x) {
-            float mu = 0.f;
-            for (int n = 0; n < N; ++n) mu = fmaf(a_s[n], __bfloat162float(S[static_cast<size_t>(n) * D + d]), mu);
-            mu_s[d] = mu;
-        }
-        __syncthreads();
-        for (int t = threadIdx.x; t < N * D; t += blockDim.x) {
-            const int n = t / D, d = t % D;
-            SWr[t] = q_s[n] * (__bfloat162float(S[t]) - mu_s[d]);
-        }
-        __syncthreads();
-        {
-            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-            for (int n = warp; n < N; n += nw) {
-                float s = 0.f;
-                for (int d = lane; d < D; d += 32) { const float v = SWr[n * D + d]; s = fmaf(v, v, s); }
-                s = warp_sum(s);
-                if (lane == 0) ksd[n] = s;
-            }
-        }
-        // ---- S1: m = Ktt a, centred + weighted teacher token Gram
-        for (int n = threadIdx.x; n < N; n += blockDim.x) {
-            float s = 0.f;
-            for (int m = 0; m < N; ++m) s = fmaf(Ktt[static_cast<size_t>(m) * N + n], a_s[m], s);
-            m_s[n] = s;
-        }
-        __syncthreads();
-        float part = 0.f;
-        for (int n = threadIdx.x; n < N; n += blockDim.x) part += a_s[n] * m_s[n];
-        const float mm = cta_sum(part, red);
-        part = 0.f;
-        for (int n = threadIdx.x; n < N; n += blockDim.x) {
-            const float v = a_s[n] * (Ktt[static_cast<size_t>(n) * N + n] - 2.f * m_s[n] + mm);
-            ktd[n] = v;
-            part += v;
-        }
-        const float tr_t = cta_sum(part, red);
-        part = 0.f;
-        for (int n = threadIdx.x; n < N; n += blockDim.x) part += ksd[n];
-        const float tr_s = cta_sum(part, red);
-        const float creg = tr_t / static_cast<float>(N);
-        for (int t = threadIdx.x; t < ld * N; t += blockDim.x) {
-            const int c = t / ld, r = t % ld;
-            float v = 0.f;
-            if (r < N) {
-                const float kk = 0.5f * (Ktt[static_cast<size_t>(r) * N + c] + Ktt[static_cast<size_t>(c) * N + r]);
-                v = q_s[r] * q_s[c] * (kk - m_s[r] - m_s[c] + mm + creg);
-            }
-            A[c * ld + r] = v;
-        }
-        __syncthreads();
-        // ---- S2: Cholesky K' = L L^T, keep a copy of L
-        cta_cholesky_lower(A, ld, N, &s_bad);
-        for (int t = threadIdx.x; t < ld * N; t += blockDim.x) Lg[t] = A[t];
-        __syncthreads();
-        // ---- S3: Y0^T[d][n] = sum_r SW[r][d] L[r][n]
-        cta_gemm(D, N, N,
-                 [&](int d, int r) { return SWr[r * D + d]; },
-                 [&](int r, int n) { return A[n * ld + r]; },
-                 [&](int d, int n, float v) { Y0r[n * D + d] = v; });
-        __syncthreads();
-        for (int t = threadIdx.x; t < ld * D; t += blockDim.x) {
-            const int d = t / ld, n = t % ld;
-            A[t] = n < N ? Y0r[n * D + d] : 0.f;
-        }
-        __syncthreads();
-        // ---- S4: one-sided Jacobi on the D columns of Y (length N)
-        const int nsweeps = run_jacobi(A, ld, D);
-        column_norms(A, ld, N, D, sig);
-        __syncthreads();
-        float smax = 0.f;
-        for (int d = threadIdx.x; d < D; d += blockDim.x) smax = fmaxf(smax, sig[d]);
-        for (int o = 16; o > 0; o >>= 1) smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, o));
-        __syncthreads();
-        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = smax;
-        __syncthreads();
-        smax = 0.f;
-        for (int wv = 0; wv < (blockDim.x >> 5); ++wv) smax = fmaxf(smax, red[wv]);
-        __syncthreads();
-        const float floor_sig = 1e-6f * smax;
-        part = 0.f;
-        for (int d = threadIdx.x; d < D; d += blockDim.x) part += sig[d] > floor_sig ? sig[d] : 0.f;
-        const float nuc = cta_sum(part, red);
-        // ---- S5: Omega = U S^-1 U^T, Xi = U S U^T   (columns of A are sigma_d u_d)
-        cta_gemm(N, N, D,
-                 [&](int n, int d) { return A[d * ld + n]; },
-                 [&](int d, int m) { const float s = sig[d]; return s > floor_sig ? A[d * ld + m] / (s * s * s) : 0.f; },
-                 [&](int n, int m, float v) { Og[m * N + n] = v; });
-        cta_gemm(N, N, D,
-                 [&](int n, int d) { return A[d * ld + n]; },
-                 [&](int d, int m) { const float s = sig[d]; return s > floor_sig ? A[d * ld + m] / s : 0.f; },
-                 [&](int n, int m, float v) { Xg[m * N + n] = v; });
-        __syncthreads();
-        // ---- S6: T2 = Omega Y0 (= polar factor of Y0), G_sw = L T2, outputs of the direct path
-        cta_gemm(N, D, N,
-                 [&](int n, int m) { return Og[m * N + n]; },
-                 [&](int m, int d) { return Y0r[m * D + d]; },
-                 [&](int n, int d, float v) { T2r[n * D + d] = v; });
-        __syncthreads();
-        float* gdir = g.gdir + static_cast<size_t>(prob) * N * D;
-        cta_gemm(N, D, N,
-                 [&](int n, int r) { return Lg[r * ld + n]; },
-                 [&](int r, int d) { return T2r[r * D + d]; },
-                 [&](int n, int d, float gsw) {
-                     const float sw = SWr[n * D + d];
-                     gdir[n * D + d] = q_s[n] * (2.f * sw - 2.f * gsw);
-                     atomicAdd(&dots[n], sw * gsw);
-                 });
-        __syncthreads();
-        // ---- S7: Psi = L^-T Xi L^-1, Theta' = 2 (diag(a) - q Psi q - a a^T)
-        for (int t = threadIdx.x; t < ld * N; t += blockDim.x) A[t] = Lg[t];
-        __syncthreads();
-        cta_lower_inverse(A, ld, N, Linvg, ld);
-        cta_gemm(N, N, N,
-                 [&](int mp, int m) { return Xg[m * N + mp]; },
-                 [&](int m, int n) { return m >= n ? Linvg[n * ld + m] : 0.f; },
-                 [&](int mp, int n, float v) { T3T[mp * N + n] = v; });
-        __syncthreads();
-        __nv_bfloat16* theta = g.theta + static_cast<size_t>(prob) * N * g.NsPad;
-        cta_gemm(N, N, N,
-                 [&](int np, int m) { return T3T[m * N + np]; },
-                 [&](int m, int n) { return m >= n ? Linvg[n * ld + m] : 0.f; },
-                 [&](int np, int n, float psi) {
-                     float v = -q_s[np] * psi * q_s[n] - a_s[np] * a_s[n];
-                     if (np == n) v += a_s[n];
-                     theta[static_cast<size_t>(n) * g.NsPad + np] = __float2bfloat16(2.f * v);
-                 });
-        for (int t = threadIdx.x; t < N * (g.NsPad - N); t += blockDim.x) {
-            const int n = t / (g.NsPad - N), c = N + t % (g.NsPad - N);
-            theta[static_cast<size_t>(n) * g.NsPad + c] = __float2bfloat16(0.f);
-        }
-        __syncthreads();
-        // ---- S8: importance gradient and scalars
-        part = 0.f;
-        for (int n = threadIdx.x; n < N; n += blockDim.x) {
-            const float ga = (ksd[n] + ktd[n] - 2.f * dots[n]) / a_s[n];
-            m_s[n] = ga;                                  // reuse
-            part += ga * a_s[n];
-        }
-        const float gdot = cta_sum(part, red);
-        const float inv_ssum = 1.f / g.ssum[prob];
-        for (int n = threadIdx.x; n < N; n += blockDim.x) g.gwt[static_cast<size_t>(prob) * N + n] = (m_s[n] - gdot) * inv_ssum;
-        if (threadIdx.x == 0) {
-            g.loss_b[prob] = tr_s + tr_t - 2.f * nuc;
-            if (g.dbg) {
-                g.dbg[prob * 5 + 0] = nuc; g.dbg[prob * 5 + 1] = tr_s; g.dbg[prob * 5 + 2] = tr_t;
-                g.dbg[prob * 5 + 3] = static_cast<float>(nsweeps); g.dbg[prob * 5 + 4] = static_cast<float>(s_bad);
-            }
-        }
-        __syncthreads();
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // selector_bwd_kernel: grid (tiles, P).  gd_j = d L / d d2_ij from d L / d w, then
 //   Gamma'_i = sum_j gd_j Gamma_sym_ij  -> bf16 hi/lo;  corr_i = mu_i^T Gamma'_i;  grad log_temperature.
 // ------------------------------------------------------------------------------------------------
@@ -499,14 +299,6 @@ selector_bwd_kernel(int n, int Lt, int P, const float* __restrict__ gw_raw, cons
 // ------------------------------------------------------------------------------------------------ launchers
 static size_t pooled_smem(int n) { return (static_cast<size_t>(jacobi_ld(n)) * n + 3 * n + 64) * sizeof(float); }
 static size_t angles_smem(int n) { return (static_cast<size_t>(jacobi_ld(n - 1)) * (n - 1) + 3 * n + 128) * sizeof(float); }
-static size_t procrustes_smem(int N, int D) {
-    return (static_cast<size_t>(jacobi_ld(N)) * (N > D ? N : D) + 6 * N + 2 * D + 64) * sizeof(float);
-}
-
-size_t spectral_max_smem(int N, int D) {
-    size_t a = pooled_smem(D), b = angles_smem(D), c = procrustes_smem(N, D);
-    return a > b ? (a > c ? a : c) : (b > c ? b : c);
-}
 
 cudaError_t launch_pooled_eig(const float* stats, int n, int Lt, int P, float Mt, float Ms, int* ranks, float* evals,
                               float* evecs_km, float* evecs_cm, int* sweeps, cudaStream_t st) {
@@ -527,14 +319,6 @@ cudaError_t launch_angles(int n, int Lt, int P, const int* ranks, const float* e
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     mix_weights_kernel<<<P, 32, 0, st>>>(d2, log_temp, Lt, P, w);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_procrustes(const ProcrustesArgs& args, int n_ctas, cudaStream_t st) {
-    const size_t smem = procrustes_smem(args.Ns, args.Ds);
-    cudaError_t e = cudaFuncSetAttribute(procrustes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return e;
-    procrustes_kernel<<<n_ctas, kSpectralThreads, smem, st>>>(args);
     return cudaGetLastError();
 }
 

@@ -16,33 +16,12 @@ __host__ __device__ inline int jacobi_ld_host(int m) {
     if (ld - 32 >= m) ld -= 32;
     return ld;
 }
-__host__ __device__ inline size_t procrustes_scratch_floats(int N, int D) {
-    const size_t ld = jacobi_ld_host(N);
-    return 2 * ld * N + 3 * static_cast<size_t>(N) * D + 3 * static_cast<size_t>(N) * N;
-}
 
-struct ProcrustesArgs {
-    int Ns, Ds, B, NsPad, n_problems;
-    const float* Ktt;                     // [P*B][Ns][Ns]
-    const float* a;                       // [P*B][Ns]
-    const float* ssum;                    // [P*B]
-    const __nv_bfloat16* student[kMaxPoints];   // per extraction point, [B][Ns][Ds]
-    long long student_batch_stride;       // elements
-    float* scratch;
-    float* gdir;                          // [P*B][Ns][Ds]
-    __nv_bfloat16* theta;                 // [P*B][Ns][NsPad]
-    float* gwt;                           // [P*B][Ns]
-    float* loss_b;                        // [P*B]
-    float* dbg;                           // [P*B][5] or null
-};
-
-size_t spectral_max_smem(int N, int D);
 cudaError_t launch_pooled_eig(const float* stats, int n, int Lt, int P, float Mt, float Ms, int* ranks, float* evals,
                               float* evecs_km, float* evecs_cm, int* sweeps, cudaStream_t st);
 cudaError_t launch_angles(int n, int Lt, int P, const int* ranks, const float* evals, const float* evecs_km,
                           const float* evecs_cm, const float* proj_s, float* scratch, float* d2, float* gamma,
                           float* cos_out, const float* log_temp, float* w, cudaStream_t st);
-cudaError_t launch_procrustes(const ProcrustesArgs& args, int n_ctas, cudaStream_t st);
 cudaError_t launch_selector_bwd(int n, int Lt, int P, const float* gw_raw, const float* scale_ptr, float scale_host,
                                 const float* w, const float* d2, const float* log_temp, const float* gamma,
                                 const float* stats, float Ms, __nv_bfloat16* gam_hi, __nv_bfloat16* gam_lo, float* corr,
@@ -56,8 +35,13 @@ cudaError_t launch_importance_rows(const PtrTable& attn, int attn_is_bf16, int L
                                    const long long* strides /*[b,h,q,k] elements*/, float* rows, cudaStream_t st);
 cudaError_t launch_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t n, cudaStream_t st);
 cudaError_t launch_pack_bf16(const void* src, int src_is_bf16, long long sb, long long sn, long long sd, int B, int N,
-                             int D, __nv_bfloat16* dst, cudaStream_t st);
-cudaError_t launch_colsum(const __nv_bfloat16* X, size_t rows, int D, float* out /*[D], pre-zeroed*/, cudaStream_t st);
+                             int D, __nv_bfloat16* dst, __nv_bfloat16* dst_lo /*null: round to bf16*/, cudaStream_t st);
+struct ColsumJobs {                       // out[j][d] += sum_rows (hi[j] + lo[j])[row][d]; lo may be null
+    const __nv_bfloat16* hi[kMaxLayers + kMaxPoints];
+    const __nv_bfloat16* lo[kMaxLayers + kMaxPoints];
+    float* out[kMaxLayers + kMaxPoints];
+};
+cudaError_t launch_colsum(const ColsumJobs& jobs, int n_jobs, size_t rows, int D, cudaStream_t st);
 cudaError_t launch_importance_mix(const float* rows, const float* w, int Lt, int P, int B, int Nt, int Ns, float* a,
                                   float* ssum, cudaStream_t st);
 cudaError_t launch_mix_teacher(const PtrTable& teacher, const float* w, int Lt, int P, int B, int Nt, int Ns, int Dt,
@@ -70,14 +54,16 @@ cudaError_t launch_loss_reduce(const float* loss_b, int P, int B, float* geo_i, 
 // ---- tcgen05 GEMM launchers (gemm_ops.cu)
 int gemm_init_driver_api();               // resolves cuTensorMapEncodeTiled; 0 on success
 cudaError_t gemm_project(const __nv_bfloat16* X, size_t M, int Dt, const __nv_bfloat16* Phi, const __nv_bfloat16* Plo,
-                         int Ds, __nv_bfloat16* Z, cudaStream_t st);
-cudaError_t gemm_gram(const __nv_bfloat16* Z, size_t M, int Ds, float* G /*[Ds][Ds] pre-zeroed*/, cudaStream_t st);
-cudaError_t gemm_gram_batched(const __nv_bfloat16* Z, size_t M, int Ds, int batches, float* G, long long g_stride,
-                              cudaStream_t st);
+                         int Ds, __nv_bfloat16* Zhi, __nv_bfloat16* Zlo, cudaStream_t st);
+// Zlo may be null (exact bf16 input); otherwise Z = Zhi + Zlo and the Gram uses hi*hi + hi*lo + lo*hi
+cudaError_t gemm_gram(const __nv_bfloat16* Z, const __nv_bfloat16* Zlo, size_t M, int Ds, float* G /*[Ds][Ds] pre-zeroed*/,
+                      cudaStream_t st);
+cudaError_t gemm_gram_batched(const __nv_bfloat16* Z, const __nv_bfloat16* Zlo, size_t M, int Ds, int batches, float* G,
+                              long long g_stride, cudaStream_t st);
 cudaError_t gemm_token_gram(const __nv_bfloat16* Thi, const __nv_bfloat16* Tlo, int batches, int Ns, int Dt, float* Ktt,
                             cudaStream_t st);
-cudaError_t gemm_theta_apply(const __nv_bfloat16* theta, int NsPad, const __nv_bfloat16* Thi, int batches, int Ns, int Dt,
-                             __nv_bfloat16* Dtm, cudaStream_t st);
+cudaError_t gemm_theta_apply(const __nv_bfloat16* theta_hi, const __nv_bfloat16* theta_lo, int NsPad, const __nv_bfloat16* Thi,
+                             const __nv_bfloat16* Tlo, int batches, int Ns, int Dt, __nv_bfloat16* Dtm, cudaStream_t st);
 cudaError_t gemm_student_grad(const __nv_bfloat16* S, size_t M, int Ds, const __nv_bfloat16* Ghi, const __nv_bfloat16* Glo,
                               const float* gdir, const float* corr, const float* scale_ptr, float scale_host, void* out,
                               int out_is_bf16, cudaStream_t st);
@@ -85,5 +71,39 @@ cudaError_t gemm_student_grad(const __nv_bfloat16* S, size_t M, int Ds, const __
 cudaError_t gemm_selftest(int variant, const __nv_bfloat16* A, const __nv_bfloat16* B, float* C, int M, int N, int K,
                           cudaStream_t st);
 const char* gemm_last_error();
+
+// ---- Newton-Schulz polar iteration of the Procrustes core (polar.cu + polar_gemm.cuh)
+struct SplitMat {                         // bf16 hi/lo pair, column-block tiled: [batch][col / 64][row][col % 64]
+    __nv_bfloat16* hi; __nv_bfloat16* lo;
+    int rows, inner;                      // valid rows / columns
+    long long batch_stride;               // elements per problem = ceil(inner / 64) * rows * 64
+    __host__ __device__ size_t at(int r, int c) const { return (static_cast<size_t>(c >> 6) * rows + r) * 64 + (c & 63); }
+};
+struct PolarGemmArgs;
+// out = A (rows x K, K-major) * B^T; B is K-major ([n_cols][K]) or, with b_mn, the row-major [K][n_cols] buffer.
+cudaError_t polar_gemm(bool b_mn, const SplitMat& A, const SplitMat& B, int batches, PolarGemmArgs& args, cudaStream_t st);
+
+struct PolarArgs {
+    int Ns, Ds, B, P, NsPad;
+    int n_problems;                       // P * B
+    const __nv_bfloat16* student[kMaxPoints];   // [B][Ns][Ds] dense bf16
+    const float* Ktt;                     // [P*B][Ns][Ns]   uncentred token Gram of the mixed teacher
+    const float* a;                       // [P*B][Ns]       normalised importance
+    const float* ssum;                    // [P*B]
+    // scratch (all per problem)
+    SplitMat W, W2, T, A, A2, Bm, Kt, SW;
+    float* Gsw;                           // [P*B][Ns][Ds]   d nuc / d s_w
+    float* vec;                           // [P*B][4][Ns]    ksd, ktd, (spare), (spare)
+    float* scal;                          // [P*B][4]        (spare), tr_s, tr_t, (spare)
+    float* fro2;                          // [P*B]           ||C||_F^2
+    // outputs
+    float* gdir;                          // [P*B][Ns][Ds]
+    __nv_bfloat16* theta;                 // [P*B][Ns][NsPad] hi
+    __nv_bfloat16* theta_lo;              // [P*B][Ns][NsPad] lo
+    float* gwt;                           // [P*B][Ns]
+    float* loss_b;                        // [P*B]
+    float* dbg;                           // [P*B][5]
+};
+cudaError_t launch_polar_procrustes(const PolarArgs& args, cudaStream_t st, int* launches);
 
 }  // namespace basd

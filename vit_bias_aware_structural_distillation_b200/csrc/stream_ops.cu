@@ -95,46 +95,97 @@ cudaError_t launch_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16
 
 template <typename T>
 __global__ void pack_bf16_kernel(const T* __restrict__ src, long long sb, long long sn, long long sd, int B, int N, int D,
-                                 __nv_bfloat16* __restrict__ dst) {
+                                 __nv_bfloat16* __restrict__ dst, __nv_bfloat16* __restrict__ dst_lo) {
     const size_t total = static_cast<size_t>(B) * N * D;
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
         const int d = static_cast<int>(i % D);
         const size_t r = i / D;
         const int n = static_cast<int>(r % N), b = static_cast<int>(r / N);
-        dst[i] = __float2bfloat16(static_cast<float>(src[b * sb + n * sn + d * sd]));
+        const float v = static_cast<float>(src[b * sb + n * sn + d * sd]);
+        const __nv_bfloat16 h = __float2bfloat16(v);
+        dst[i] = h;
+        if (dst_lo) dst_lo[i] = __float2bfloat16(v - __bfloat162float(h));
     }
 }
 cudaError_t launch_pack_bf16(const void* src, int src_is_bf16, long long sb, long long sn, long long sd, int B, int N, int D,
-                             __nv_bfloat16* dst, cudaStream_t st) {
+                             __nv_bfloat16* dst, __nv_bfloat16* dst_lo, cudaStream_t st) {
     const size_t total = static_cast<size_t>(B) * N * D;
     const int blocks = static_cast<int>((total + 255) / 256 < 2368 ? (total + 255) / 256 : 2368);
     if (src_is_bf16)
-        pack_bf16_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), sb, sn, sd, B, N, D, dst);
+        pack_bf16_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), sb, sn, sd, B, N, D, dst, dst_lo);
     else
-        pack_bf16_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(src), sb, sn, sd, B, N, D, dst);
+        pack_bf16_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(src), sb, sn, sd, B, N, D, dst, dst_lo);
     return cudaGetLastError();
 }
 
-// out[d] += sum over rows of X[row][d]; D % 8 == 0.  Thread = one 8-wide column vector of a row subset.
-__global__ void colsum_kernel(const __nv_bfloat16* __restrict__ X, size_t rows, int D, float* __restrict__ out) {
-    const int vpr = D / 8;                                   // vectors per row
-    const int rows_per_pass = blockDim.x / vpr;              // >= 1 (D <= 8 * blockDim)
+// out[j][d] += sum over rows of (hi[j] + lo[j])[row][d]; D % 8 == 0.  grid = (row chunks, jobs): every CTA streams a
+// contiguous chunk of rows with 16-byte loads (4 in flight per thread), reduces across its row lanes in shared
+// memory and issues D atomics.
+constexpr int kColsumThreads = 256;
+__global__ void __launch_bounds__(kColsumThreads)
+colsum_kernel(ColsumJobs jobs, size_t rows, int D) {
+    __shared__ float red[kColsumThreads * 8];
+    const int j = blockIdx.y;
+    const __nv_bfloat16* Xh = jobs.hi[j];
+    const __nv_bfloat16* Xl = jobs.lo[j];
+    const int vpr = D / 8;                                   // 16-byte vectors per row
+    const int rpp = kColsumThreads / vpr;                    // rows per pass
     const int lr = threadIdx.x / vpr, cv = threadIdx.x % vpr;
+    const size_t chunk = (rows + gridDim.x - 1) / gridDim.x;
+    const size_t r0 = blockIdx.x * chunk, r1 = r0 + chunk < rows ? r0 + chunk : rows;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (lr < rows_per_pass) {
-        for (size_t r = static_cast<size_t>(blockIdx.x) * rows_per_pass + lr; r < rows; r += static_cast<size_t>(gridDim.x) * rows_per_pass) {
+    if (lr < rpp) {
+        size_t r = r0 + lr;
+        for (; r + 3 * static_cast<size_t>(rpp) < r1; r += 4 * static_cast<size_t>(rpp)) {
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = ld_nc_16(Xh + (r + static_cast<size_t>(u) * rpp) * D + cv * 8);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float f[8];
+                bf16x8_to_float(v[u], f);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] += f[i];
+            }
+            if (Xl) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = ld_nc_16(Xl + (r + static_cast<size_t>(u) * rpp) * D + cv * 8);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float f[8];
+                    bf16x8_to_float(v[u], f);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[i] += f[i];
+                }
+            }
+        }
+        for (; r < r1; r += rpp) {
             float f[8];
-            bf16x8_to_float(ld_nc_16(X + r * D + cv * 8), f);
+            bf16x8_to_float(ld_nc_16(Xh + r * D + cv * 8), f);
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc[i] += f[i];
-        }
+            if (Xl) {
+                bf16x8_to_float(ld_nc_16(Xl + r * D + cv * 8), f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) atomicAdd(out + cv * 8 + i, acc[i]);
+                for (int i = 0; i < 8; ++i) acc[i] += f[i];
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = acc[i];
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+        const int v = c / 8, e = c % 8;
+        float s = 0.f;
+        for (int l = 0; l < rpp; ++l) s += red[(l * vpr + v) * 8 + e];
+        atomicAdd(jobs.out[j] + c, s);
     }
 }
-cudaError_t launch_colsum(const __nv_bfloat16* X, size_t rows, int D, float* out, cudaStream_t st) {
-    if (D % 8 != 0 || D > 2048) return cudaErrorInvalidValue;
-    colsum_kernel<<<148, 256, 0, st>>>(X, rows, D, out);
+cudaError_t launch_colsum(const ColsumJobs& jobs, int n_jobs, size_t rows, int D, cudaStream_t st) {
+    if (D % 8 != 0 || D > 8 * kColsumThreads || n_jobs < 1) return cudaErrorInvalidValue;
+    int chunks = (148 * 8 + n_jobs - 1) / n_jobs;
+    if (static_cast<size_t>(chunks) * 64 > rows) chunks = static_cast<int>((rows + 63) / 64);
+    colsum_kernel<<<dim3(chunks, n_jobs), kColsumThreads, 0, st>>>(jobs, rows, D);
     return cudaGetLastError();
 }
 

@@ -228,6 +228,39 @@ struct EpiStoreBf16 {                     // out[batch][row][col] = bf16(alpha *
     }
 };
 
+struct EpiStoreSplit {                    // out = hi, aux0 = lo:  hi = bf16(acc), lo = bf16(acc - hi)   (fp32-class storage)
+    __nv_bfloat16* hi; __nv_bfloat16* lo; int ld, rows, cols;
+    __device__ EpiStoreSplit(const GemmArgs& a, int batch, int) {
+        hi = reinterpret_cast<__nv_bfloat16*>(a.out) + batch * a.out_batch_stride;
+        lo = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(a.aux0)) + batch * a.out_batch_stride;
+        ld = a.ld_out; rows = a.rows_valid; cols = a.cols_valid;
+    }
+    __device__ void operator()(int row, int col0, const float* v) const {
+        if (row >= rows || col0 >= cols) return;
+        const long long off = static_cast<long long>(row) * ld + col0;
+        if (col0 + 16 <= cols) {
+            uint32_t hw[8], lw[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const __nv_bfloat16 h0 = __float2bfloat16(v[2 * i]), h1 = __float2bfloat16(v[2 * i + 1]);
+                __nv_bfloat162 hv; hv.x = h0; hv.y = h1;
+                hw[i] = *reinterpret_cast<uint32_t*>(&hv);
+                lw[i] = pack_bf16x2(v[2 * i] - __bfloat162float(h0), v[2 * i + 1] - __bfloat162float(h1));
+            }
+            reinterpret_cast<uint4*>(hi + off)[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            reinterpret_cast<uint4*>(hi + off)[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+            reinterpret_cast<uint4*>(lo + off)[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            reinterpret_cast<uint4*>(lo + off)[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+        } else {
+            for (int i = 0; i < 16 && col0 + i < cols; ++i) {
+                const __nv_bfloat16 h = __float2bfloat16(v[i]);
+                hi[off + i] = h;
+                lo[off + i] = __float2bfloat16(v[i] - __bfloat162float(h));
+            }
+        }
+    }
+};
+
 struct EpiStoreF32 {                      // out[batch][row][col] = alpha * acc
     float* out; int ld, rows, cols; float alpha;
     __device__ EpiStoreF32(const GemmArgs& a, int batch, int) {
