@@ -269,7 +269,7 @@ def test_bf16_attention_maps(lib, cuda_dev):
     # tolerance of it, and the polar factor amplifies that by its condition number (~1e4 here) -> a few 1e-4, which is
     # the sensitivity the reference's own fp32 LAPACK path has on these inputs.
     for l in a["grad_student"]:
-        assert rel(a["grad_student"][l], b["grad_student"][l]) < 3e-3
+        assert rel(a["grad_student"][l], b["grad_student"][l]) < TOL_SGRAD
     assert_parity(b, oracle_case(m, inp, w), w)
 
 
@@ -374,3 +374,29 @@ def test_two_rank_sharding_matches_single_process(lib, cuda_dev, tmp_path):
         # per-rank loss is the mean over the local half batch -> local gradients are 2x the global-mean gradients
         cat = torch.cat([parts[0]["grad_student"][l], parts[1]["grad_student"][l]]) / 2
         assert rel(cat, single["grad_student"][l]) < TOL_SGRAD
+
+
+def test_host_stager_matches_device_path(lib, cuda_dev):
+    """The host-buffer entry (HostStager: CLS-row gather, copy stream, double-buffered slots) gives the same loss and
+    gradients as handing device tensors to the module, for two consecutive submissions that reuse the slots."""
+    import vit_bias_aware_structural_distillation_b200 as pkg
+    w = dataclasses.replace(synth.CONFIGS["cfg1"], B=4)
+    m = build_module(w, cuda_dev)
+    stager = pkg.HostStager(m)
+    for seed in (1234, 99, 7):
+        inp = synth.make_inputs(w, seed=seed, attn_dtype=torch.bfloat16)
+        ref = run_module(m, inp, cuda_dev, attn_dtype=torch.bfloat16)
+        pin = lambda t: t.pin_memory()
+        h = stager.submit(pin(inp["logits"]), pin(inp["targets"]), {l: pin(v) for l, v in inp["student"].items()},
+                          {j: pin(v) for j, v in inp["teacher"].items()}, {j: pin(v) for j, v in inp["attn"].items()})
+        m.zero_grad(set_to_none=True)
+        loss = stager.run(h)
+        loss.backward()
+        torch.cuda.synchronize()
+        assert abs(loss.item() - ref["loss"].item()) <= 1e-5 * abs(ref["loss"].item())
+        assert rel(m.layer_selector.log_temperatures.grad.cpu(), ref["grad_log_temperatures"]) < TOL_TGRAD
+        for l in ref["grad_student"]:
+            # two separate executions: bf16 gradient rounding + the run-to-run sensitivity documented in test_bf16_attention_maps
+            assert rel(h["leaf_student"][l].grad.float().cpu(), ref["grad_student"][l]) < TOL_SGRAD
+        assert stager.h2d_bytes_last < 1.05 * (sum(v.numel() * 2 for v in inp["teacher"].values()) + sum(v.numel() * 2 for v in inp["student"].values())
+                                               + inp["logits"].numel() * 4 + 8 * w.B + w.Lt * w.B * w.H * (w.Nt + 1) * 2)

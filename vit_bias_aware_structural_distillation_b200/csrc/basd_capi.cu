@@ -215,7 +215,7 @@ extern "C" int basd_view(const basd_shape* shape, void* workspace, const char* n
         {"gamma", L.gamma, P * Lt * Ds * Ds}, {"gwt", L.gwt, P * B * Ns}, {"evecs", L.evecs_km, (Lt + P) * Ds * Ds},
         {"corr", L.corr, P * Ds}, {"ssum", L.ssum, P * B},
         // polar iteration state (bf16 pairs: count is in bf16 elements, hi block then lo block)
-        {"polar_w", (11 % 2) ? L.pw2 : L.pw, 2 * P * B * Ds * L.Np}, {"polar_kt", L.pkt, 2 * P * B * Ns * L.Np},
+        {"polar_w", (polar_steps() % 2) ? L.pw2 : L.pw, 2 * P * B * Ds * L.Np}, {"polar_kt", L.pkt, 2 * P * B * Ns * L.Np},
         {"polar_sw", L.psw, 2 * P * B * Ns * ((Ds + 63) / 64 * 64)}, {"polar_a", L.pa, 2 * P * B * Ds * ((Ds + 63) / 64 * 64)}, {"polar_gsw", L.gsw, P * B * Ns * Ds}, {"polar_fro2", L.pfro, P * B},
         {"theta", L.theta, P * B * Ns * L.NsPad},
     };

@@ -77,11 +77,11 @@ __device__ __forceinline__ float cta_sum(float v, float* scratch) {
 // In-place Cholesky (lower) of the SPD matrix stored column-major in shared memory: A[c*ld + r].
 // On exit the lower triangle holds L, the strict upper triangle is zeroed.  Returns false-ish flag through
 // *bad (shared int) if a non-positive pivot was met (pivot is then clamped).
-__device__ inline void cta_cholesky_lower(float* __restrict__ A, int ld, int n, int* bad) {
+__device__ inline void cta_cholesky_lower(float* __restrict__ A, int ld, int n, int* bad, float pivot_floor = 0.f) {
     for (int j = 0; j < n; ++j) {
         __syncthreads();
         float d = A[j * ld + j];
-        if (!(d > 0.f)) { d = 1e-30f; if (threadIdx.x == 0) *bad = 1; }
+        if (!(d > pivot_floor)) { d = fmaxf(pivot_floor, 1e-30f); if (threadIdx.x == 0) *bad = 1; }
         const float inv = rsqrtf(d);
         __syncthreads();
         for (int r = j + threadIdx.x; r < n; r += blockDim.x) A[j * ld + r] *= inv;   // column j (incl. diag -> sqrt(d))

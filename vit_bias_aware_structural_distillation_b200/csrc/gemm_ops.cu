@@ -234,16 +234,26 @@ cudaError_t polar_gemm(bool b_mn, const SplitMat& A, const SplitMat& B, int batc
         // K-major B: one box of bn_mma rows per k-block; MN-major B: 64 (k) x 64 (n) boxes of the [K][n_cols] matrix
         if (make_map_tiled(&maps.b[i], bp[i], B.rows, (B.inner + 63) / 64, batches, B.batch_stride, b_mn ? 64 : a.bn_mma)) return cudaErrorInvalidValue;
     }
+    if (a.epi == PG_EPI_SPLIT) {                       // TMA-store maps: 32-row x 64-column boxes of the tiled outputs
+        const int ocb = (n_cols + 63) / 64;
+        if (make_map_tiled(&maps.o[0], a.out_hi, m_rows, ocb, batches, a.out_stride, 32)) return cudaErrorInvalidValue;
+        if (make_map_tiled(&maps.o[1], a.out_lo, m_rows, ocb, batches, a.out_stride, 32)) return cudaErrorInvalidValue;
+        if (a.out2_hi) {
+            if (make_map_tiled(&maps.o[2], a.out2_hi, m_rows, ocb, batches, a.out_stride, 32)) return cudaErrorInvalidValue;
+            if (make_map_tiled(&maps.o[3], a.out2_lo, m_rows, ocb, batches, a.out_stride, 32)) return cudaErrorInvalidValue;
+        }
+    }
     const int b_bytes = b_mn ? a.b_groups * 8192 : a.bn_mma * 128;
     const int stage_bytes = 2 * 16384 + 2 * b_bytes;
-    int stages = (232448 - 1024 - 256) / stage_bytes;
+    constexpr int kTail = 1024 /*alignment*/ + 1024 /*barriers*/ + 4 * 8192 /*epilogue staging*/;
+    int stages = (232448 - kTail) / stage_bytes;
     if (stages > 4) stages = 4;
     if (stages < 1) {
         snprintf(g_gemm_err, sizeof g_gemm_err, "polar_gemm: one stage (%d B) exceeds shared memory", stage_bytes);
         return cudaErrorInvalidValue;
     }
     a.stages = stages;
-    const int smem = stages * stage_bytes + 1024 + 256;
+    const int smem = stages * stage_bytes + kTail;
     auto kern = b_mn ? polar_gemm_kernel<true> : polar_gemm_kernel<false>;
     static bool configured[2] = {false, false};
     static int sm_count = 0;

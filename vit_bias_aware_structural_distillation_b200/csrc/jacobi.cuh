@@ -8,23 +8,23 @@
 // /root/reference/src/losses/layer_selector.py:16,36,92,99 and relational.py:48.
 //
 // Parallel ordering: round-robin tournament (n-1 steps per sweep, n/2 disjoint pairs per step).  A pair is
-// owned by a 16-lane group: each lane keeps its slice of both columns in registers (128-bit shared loads),
-// the three inner products are reduced with 4 xor-shuffles, the rotation is applied from registers.
-// ld must be a multiple of 4 with ld % 32 == 16 so the two groups of a warp hit disjoint banks.
+// owned by an 8-lane group: each lane keeps its slice of both columns in registers (128-bit shared loads; a
+// quarter warp reads 128 contiguous bytes, so the accesses are bank-conflict free), the three inner products are
+// reduced with 3 xor-shuffles, the rotation is applied from registers.  The kernel is instruction-issue bound, so the
+// group is kept small: 768 threads = 96 groups cover the 96 pairs of an n = 192 step in ONE pass, and the per-pair
+// shuffle / rotation-parameter overhead is amortised over 24 rows per lane (16-lane groups needed two passes per step).
+// ld must be a multiple of 4.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace basd {
 
-constexpr int JAC_GROUP = 16;
-constexpr int JAC_MAX_CHUNKS = 4;      // 4 chunks x 64 rows -> m <= 256
+constexpr int JAC_GROUP = 8;
+constexpr int JAC_CHUNK_ROWS = JAC_GROUP * 4;
+constexpr int JAC_MAX_CHUNKS = 8;      // 8 chunks x 32 rows -> m <= 256
 
-__host__ __device__ inline int jacobi_ld(int m) {     // smallest ld >= m with ld % 32 == 16
-    int ld = ((m + 31) / 32) * 32 + 16;
-    if (ld - 32 >= m) ld -= 32;
-    return ld;
-}
+__host__ __device__ inline int jacobi_ld(int m) { return (m + 3) & ~3; }     // 128-bit rows; no bank constraint (see above)
 
 // pair k (0 <= k < n/2) at step s (0 <= s < n-1); n even.
 __device__ __forceinline__ void jacobi_pair(int n, int s, int k, int& p, int& q) {
@@ -43,7 +43,7 @@ __device__ int jacobi_orthogonalize(float* __restrict__ A, int ld, int n_cols, f
     const int gl = threadIdx.x % JAC_GROUP;
     const int n_groups = blockDim.x / JAC_GROUP;
     const int half = n / 2;
-    const unsigned gmask = 0xFFFFu << (threadIdx.x & 16);   // the 16 lanes of this group (groups may diverge)
+    const unsigned gmask = 0xFFu << (threadIdx.x & 24);     // the 8 lanes of this group (groups may diverge)
     int sweep = 0;
     if (n_cols < 2) return 0;
     for (; sweep < max_sweeps; ++sweep) {
@@ -59,7 +59,7 @@ __device__ int jacobi_orthogonalize(float* __restrict__ A, int ld, int n_cols, f
                 float al = 0.f, be = 0.f, ga = 0.f;
 #pragma unroll
                 for (int c = 0; c < CHUNKS; ++c) {
-                    const int r = c * 64 + gl * 4;
+                    const int r = c * JAC_CHUNK_ROWS + gl * 4;
                     if (r < ld) {
                         x[c] = *reinterpret_cast<const float4*>(cp + r);
                         y[c] = *reinterpret_cast<const float4*>(cq + r);
@@ -85,7 +85,7 @@ __device__ int jacobi_orthogonalize(float* __restrict__ A, int ld, int n_cols, f
                     const float sn = cs * t;
 #pragma unroll
                     for (int c = 0; c < CHUNKS; ++c) {
-                        const int r = c * 64 + gl * 4;
+                        const int r = c * JAC_CHUNK_ROWS + gl * 4;
                         if (r < ld) {
                             float4 xn, yn;
                             xn.x = cs * x[c].x - sn * y[c].x; yn.x = sn * x[c].x + cs * y[c].x;

@@ -7,9 +7,10 @@
 // centred teacher token Gram K_t = t_w t_w^T (N x N)
 //     A_k = X_k X_k^T = W_k K_t W_k^T,      W_{k+1} = (a_k I + b_k A_k + c_k A_k^2) W_k,      W_0 = s_w^T / ||C||_F
 // and at convergence   ||C||_* = <K_t W^T, s_w>,   d/ds_w = K_t W^T,   d/dt_w = (s_w W) t_w.
-// (a_k, b_k, c_k) are the minimax odd quintics for the shrinking interval [l_k, 1.03] starting at l_0 = 1e-5
-// (relative to ||C||_F): every singular value above l_0 ends within 4e-6 of 1 after 11 steps; the 3 % head room
-// above 1 keeps rounding from pushing the top singular value into the divergent region.
+// (a_k, b_k, c_k) are the minimax odd quintics for the shrinking interval [l_k, 1.03] starting at l_0 = 3e-5
+// (relative to ||C||_F): every singular value above l_0 ends within 4e-6 of 1 after 10 steps (smaller ones are left
+// partially converged - they carry no weight in the nuclear norm); the 3 % head room above 1 keeps rounding from
+// pushing the top singular value into the divergent region.
 // All products are one-CTA-per-problem tcgen05 GEMMs on split-bf16 operands (polar_gemm.cuh).
 // Requires rank(C) = D_s, i.e. D_s <= N - 1 and a teacher token Gram of rank >= D_s.
 #include "cta_linalg.cuh"
@@ -20,20 +21,20 @@ namespace basd {
 
 namespace {
 
-constexpr int kPolarSteps = 11;
-// python: minimax odd quintic on [l_k, 1.03], rescaled to max 1 (tools/ns_schedule.py)
+constexpr int kPolarSteps = 10;
+// minimax odd quintics on [l_k, 1.03] (l_0 = 3e-5), each rescaled to a maximum of 1: tools/ns_schedule.py 3e-5 10 1.03
+// l_k: 3.0e-5 1.0e-4 4.2e-4 1.7e-3 7.1e-3 2.9e-2 0.118 0.42 0.906 0.99967 -> 0.999996
 const float kPolarCoef[kPolarSteps][3] = {
-    {4.133133694f, -11.568007891f, 8.094329945f},
-    {4.133075743f, -11.567549897f, 8.093949730f},
-    {4.132823273f, -11.565542164f, 8.092281565f},
-    {4.131776586f, -11.557237244f, 8.085383350f},
-    {4.127460592f, -11.523021954f, 8.056966863f},
-    {4.109607285f, -11.382227351f, 7.940116878f},
-    {4.035887013f, -10.813078843f, 7.469139329f},
-    {3.739866666f, -8.719702318f, 5.758941425f},
-    {2.851310847f, -4.084405728f, 2.179200157f},
-    {1.975041429f, -1.454643745f, 0.478951299f},
-    {1.848140342f, -1.196846510f, 0.348702652f},
+    {4.133071044f, -11.567471663f, 8.093880162f},
+    {4.132779328f, -11.565168373f, 8.091968276f},
+    {4.131589050f, -11.555734998f, 8.084133962f},
+    {4.126671962f, -11.516778686f, 8.051782671f},
+    {4.106352567f, -11.356677293f, 7.918925272f},
+    {4.022478221f, -10.711657944f, 7.385453943f},
+    {3.688471560f, -8.386451534f, 5.490484485f},
+    {2.745572830f, -3.677073572f, 1.889197392f},
+    {1.941173422f, -1.383242341f, 0.441739912f},
+    {1.847826056f, -1.196240433f, 0.348410606f},
 };
 
 __device__ __forceinline__ void store_split(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t idx, float v) {
@@ -207,6 +208,8 @@ polar_finish_kernel(PolarArgs g) {
 }
 
 }  // namespace
+
+int polar_steps() { return kPolarSteps; }
 
 #define PCK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return _e; } while (0)
 

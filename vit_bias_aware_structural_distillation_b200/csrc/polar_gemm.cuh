@@ -11,7 +11,9 @@
 // Work item = (problem, 128-row tile of the output).  One CTA per SM loops over its items; the shared-memory operand
 // ring and two TMEM accumulator buffers are carried across items, so the TMA loads and MMAs of item i+1 overlap the
 // epilogue of item i.  Warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue (one TMEM lane quadrant each).
-// Epilogues only store (no global reads on the critical path) except the one-off Frobenius trace of step 0.
+// Epilogues only store (no global reads on the critical path) except the one-off Frobenius trace of step 0; the split
+// outputs go through a 128B-swizzled shared-memory staging tile per warp and leave as TMA tensor stores (per-lane
+// 16-byte stores of one row each saturated the L1TEX->XBAR request path: 32 requests per instruction).
 #pragma once
 #include "ptx.cuh"
 
@@ -29,6 +31,7 @@ enum PolarEpi : int {
 struct PolarGemmMaps {
     CUtensorMap a[2];
     CUtensorMap b[2];
+    CUtensorMap o[4];                // SPLIT outputs: out hi, out lo, out2 hi, out2 lo (box = 32 rows x 64 columns)
 };
 
 struct PolarGemmArgs {
@@ -76,6 +79,32 @@ __device__ __forceinline__ void pg_store_split16(__nv_bfloat16* ph, __nv_bfloat1
     }
 }
 
+// 16 fp32 values -> bf16 hi / lo halves of staging row `row` (32 rows x 128 B, SWIZZLE_128B: 16-byte chunk j of row r
+// lives at chunk position j ^ (r & 7)); chunk0 = first of the two 16-byte chunks the 16 columns occupy.
+__device__ __forceinline__ void pg_stage_split16(uint8_t* stg_hi, uint8_t* stg_lo, int row, int chunk0, const float* v) {
+    uint32_t hw[8], lw[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const __nv_bfloat16 h0 = __float2bfloat16(v[2 * i]), h1 = __float2bfloat16(v[2 * i + 1]);
+        __nv_bfloat162 hv; hv.x = h0; hv.y = h1;
+        hw[i] = *reinterpret_cast<uint32_t*>(&hv);
+        lw[i] = pack_bf16x2(v[2 * i] - __bfloat162float(h0), v[2 * i + 1] - __bfloat162float(h1));
+    }
+    const int p0 = (chunk0 ^ (row & 7)) * 16, p1 = ((chunk0 + 1) ^ (row & 7)) * 16;
+    *reinterpret_cast<uint4*>(stg_hi + row * 128 + p0) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    *reinterpret_cast<uint4*>(stg_hi + row * 128 + p1) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+    *reinterpret_cast<uint4*>(stg_lo + row * 128 + p0) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    *reinterpret_cast<uint4*>(stg_lo + row * 128 + p1) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+}
+__device__ __forceinline__ void pg_stage_zero16(uint8_t* stg_hi, uint8_t* stg_lo, int row, int chunk0) {
+    const int p0 = (chunk0 ^ (row & 7)) * 16, p1 = ((chunk0 + 1) ^ (row & 7)) * 16;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(stg_hi + row * 128 + p0) = z;
+    *reinterpret_cast<uint4*>(stg_hi + row * 128 + p1) = z;
+    *reinterpret_cast<uint4*>(stg_lo + row * 128 + p0) = z;
+    *reinterpret_cast<uint4*>(stg_lo + row * 128 + p1) = z;
+}
+
 template <bool B_MN>
 __global__ void __launch_bounds__(PG_THREADS, 1)
 polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArgs args) {
@@ -89,6 +118,7 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
     uint64_t* tmem_full_bar = empty_bar + args.stages;         // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;              // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    uint8_t* staging = smem + args.stages * stage_bytes + 1024;          // 4 warps x (hi 4 KB + lo 4 KB), 1024-aligned
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_kb = (args.k_total + PG_BK - 1) / PG_BK;
@@ -99,6 +129,7 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
         fence_mbar_init();
         tma_prefetch_desc(&maps.a[0]); tma_prefetch_desc(&maps.a[1]);
         tma_prefetch_desc(&maps.b[0]); tma_prefetch_desc(&maps.b[1]);
+        if (args.epi == PG_EPI_SPLIT) { tma_prefetch_desc(&maps.o[0]); tma_prefetch_desc(&maps.o[1]); }
     }
     uint32_t tmem_cols = 32;
     while (tmem_cols < static_cast<uint32_t>(2 * args.bn_mma)) tmem_cols <<= 1;
@@ -198,58 +229,96 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
                 q_row = sqrtf(a_row);
             }
             float tr_part = 0.f;
-            for (int c = 0; c < args.bn_mma; c += 16) {
-                float v[16];
-                tmem_ld16(t_addr + c, v);
-                if (!row_ok || (c >= args.n_cols && args.epi != PG_EPI_SPLIT)) continue;
-                const int nv = min(16, args.n_cols - c);
-                if (args.epi == PG_EPI_F32) {
-                    float* p = args.out_f32 + z * args.out_f32_stride + static_cast<long long>(row) * args.ld_f32 + c;
-                    if (nv == 16 && (args.ld_f32 & 3) == 0) {
+            if (args.epi == PG_EPI_SPLIT) {
+                // convert into the warp's swizzled staging tile; every 64-column block leaves as one TMA store per half
+                uint8_t* stg_hi = staging + (warp - 2) * 8192;
+                uint8_t* stg_lo = stg_hi + 4096;
+                const bool warp_rows_ok = mt * 128 + q * 32 < args.m_rows;       // uniform: this warp owns at least one valid row
+                const bool has2 = args.out2_hi != nullptr;
+                for (int cbk = 0; cbk * 64 < args.bn_mma; ++cbk) {
+                    float y2[64];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            reinterpret_cast<float4*>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                    } else {
-                        for (int i = 0; i < nv; ++i) p[i] = v[i];
-                    }
-                    continue;
-                }
-                if (args.epi == PG_EPI_THETA) {
-                    const long long off = z * args.out_stride + static_cast<long long>(row) * args.ld_out + c;
-                    const float* av = args.vec_a + static_cast<long long>(z) * args.m_rows;
-                    float x[16];
+                    for (int jc = 0; jc < 4; ++jc) {
+                        const int c = cbk * 64 + jc * 16;
+                        if (c < args.bn_mma) {
+                            float v[16];
+                            tmem_ld16(t_addr + c, v);
+                            if (args.trace && row_ok) {
+                                if (args.trace_mode == 1) {
+                                    if (row >= c && row < c + 16) tr_part += v[row - c];
+                                } else {
+                                    const long long off = z * args.out_stride + (static_cast<long long>(cbk) * args.m_rows + row) * 64 + jc * 16;
+                                    for (int i = 0; i < 16; ++i)
+                                        tr_part = fmaf(v[i], __bfloat162float(args.aux_hi[off + i]) + __bfloat162float(args.aux_lo[off + i]), tr_part);
+                                }
+                            }
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        x[i] = 0.f;
-                        if (i < nv) {
-                            const float ac = av[c + i];
-                            float t = -q_row * v[i] * sqrtf(ac) - a_row * ac;
-                            if (c + i == row) t += a_row;
-                            x[i] = 2.f * t;
+                            for (int i = 0; i < 16; ++i) {
+                                y2[jc * 16 + i] = d2r * v[i] + ((c + i == row) ? args.d1 : 0.f);
+                                v[i] = scale * v[i] + ((c + i == row) ? args.diag_add : 0.f);
+                            }
+                            pg_stage_split16(stg_hi, stg_lo, lane, jc * 2, v);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) y2[jc * 16 + i] = 0.f;
+                            pg_stage_zero16(stg_hi, stg_lo, lane, jc * 2);          // padding columns of the last block
                         }
                     }
-                    pg_store_split16(args.out_hi + off, args.out_lo + off, x, nv);
-                    continue;
-                }
-                // tiled split output: [col block][row][64]; the zero accumulators of the padding columns are stored too
-                const long long off = z * args.out_stride + (static_cast<long long>(c >> 6) * args.m_rows + row) * 64 + (c & 63);
-                if (args.trace) {
-                    if (args.trace_mode == 1) {
-                        if (row >= c && row < c + nv) tr_part += v[row - c];
-                    } else {
-                        for (int i = 0; i < nv; ++i)
-                            tr_part = fmaf(v[i], __bfloat162float(args.aux_hi[off + i]) + __bfloat162float(args.aux_lo[off + i]), tr_part);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0 && warp_rows_ok) {
+                        tma_store_4d(&maps.o[0], stg_hi, 0, mt * 128 + q * 32, cbk, z);
+                        tma_store_4d(&maps.o[1], stg_lo, 0, mt * 128 + q * 32, cbk, z);
+                        tma_store_commit();
+                        tma_store_wait_read();
+                    }
+                    __syncwarp();
+                    if (has2) {
+#pragma unroll
+                        for (int jc = 0; jc < 4; ++jc) pg_stage_split16(stg_hi, stg_lo, lane, jc * 2, y2 + jc * 16);
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0 && warp_rows_ok) {
+                            tma_store_4d(&maps.o[2], stg_hi, 0, mt * 128 + q * 32, cbk, z);
+                            tma_store_4d(&maps.o[3], stg_lo, 0, mt * 128 + q * 32, cbk, z);
+                            tma_store_commit();
+                            tma_store_wait_read();
+                        }
+                        __syncwarp();
                     }
                 }
-                if (args.out2_hi) {
-                    float y[16];
+            } else {
+                for (int c = 0; c < args.bn_mma; c += 16) {
+                    float v[16];
+                    tmem_ld16(t_addr + c, v);
+                    if (!row_ok || c >= args.n_cols) continue;
+                    const int nv = min(16, args.n_cols - c);
+                    if (args.epi == PG_EPI_F32) {
+                        float* p = args.out_f32 + z * args.out_f32_stride + static_cast<long long>(row) * args.ld_f32 + c;
+                        if (nv == 16 && (args.ld_f32 & 3) == 0) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) y[i] = d2r * v[i] + ((c + i == row) ? args.d1 : 0.f);
-                    pg_store_split16(args.out2_hi + off, args.out2_lo + off, y, 16);
+                            for (int i = 0; i < 4; ++i)
+                                reinterpret_cast<float4*>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                        } else {
+                            for (int i = 0; i < nv; ++i) p[i] = v[i];
+                        }
+                    } else {                                               // PG_EPI_THETA, row-major [m_rows][ld_out]
+                        const long long off = z * args.out_stride + static_cast<long long>(row) * args.ld_out + c;
+                        const float* av = args.vec_a + static_cast<long long>(z) * args.m_rows;
+                        float x[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            x[i] = 0.f;
+                            if (i < nv) {
+                                const float ac = av[c + i];
+                                float t = -q_row * v[i] * sqrtf(ac) - a_row * ac;
+                                if (c + i == row) t += a_row;
+                                x[i] = 2.f * t;
+                            }
+                        }
+                        pg_store_split16(args.out_hi + off, args.out_lo + off, x, nv);
+                    }
                 }
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = scale * v[i] + ((c + i == row) ? args.diag_add : 0.f);
-                pg_store_split16(args.out_hi + off, args.out_lo + off, v, 16);
             }
             tc_fence_before();
             __syncwarp();
@@ -260,6 +329,7 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
                 if (lane == 0) atomicAdd(args.trace + z, tr_part);
             }
         }
+        if (lane == 0) tma_store_wait_all();          // global writes of this CTA complete before it exits
     }
     __syncthreads();
     if (warp == 1) {

@@ -23,10 +23,17 @@ __device__ __forceinline__ int run_jacobi_chunks(float* A, int ld, int n) {
     return jacobi_orthogonalize<CHUNKS>(A, ld, n, kJacobiTol, kJacobiMaxSweeps);
 }
 __device__ __forceinline__ int run_jacobi(float* A, int ld, int n) {
-    if (ld <= 64) return run_jacobi_chunks<1>(A, ld, n);
-    if (ld <= 128) return run_jacobi_chunks<2>(A, ld, n);
-    if (ld <= 192) return run_jacobi_chunks<3>(A, ld, n);
-    return run_jacobi_chunks<4>(A, ld, n);
+    const int chunks = (ld + JAC_CHUNK_ROWS - 1) / JAC_CHUNK_ROWS;
+    switch (chunks) {
+        case 1: return run_jacobi_chunks<1>(A, ld, n);
+        case 2: return run_jacobi_chunks<2>(A, ld, n);
+        case 3: return run_jacobi_chunks<3>(A, ld, n);
+        case 4: return run_jacobi_chunks<4>(A, ld, n);
+        case 5: return run_jacobi_chunks<5>(A, ld, n);
+        case 6: return run_jacobi_chunks<6>(A, ld, n);
+        case 7: return run_jacobi_chunks<7>(A, ld, n);
+        default: return run_jacobi_chunks<8>(A, ld, n);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -70,8 +77,40 @@ pooled_eig_kernel(const float* __restrict__ stats, int n, int Lt, int P, float M
         A[c * ld + r] = v;
     }
     __syncthreads();
+    // Veselic-Hari preconditioning: G = L L^T, then one-sided Jacobi on the Cholesky factor instead of on G.  The
+    // singular values of L are the square roots of the eigenvalues (half the condition number in digits), the rotated
+    // columns L V = U Sigma are still sigma_i times the eigenvectors of G, and the sweep count roughly halves.
+    // A non-positive pivot (numerically singular Gram) falls back to Jacobi on G itself.
+    __shared__ int s_bad;
+    if (threadIdx.x == 0) s_bad = 0;
+    __syncthreads();
+    float dmax = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dmax = fmaxf(dmax, A[i * ld + i]);
+    for (int o = 16; o > 0; o >>= 1) dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    if ((threadIdx.x & 31) == 0) vals[threadIdx.x >> 5] = dmax;
+    __syncthreads();
+    dmax = 0.f;
+    for (int wv = 0; wv < (blockDim.x >> 5); ++wv) dmax = fmaxf(dmax, vals[wv]);
+    __syncthreads();
+    cta_cholesky_lower(A, ld, n, &s_bad, 1e-6f * dmax);       // pivots below 1e-6 of the largest diagonal: not trusted in fp32
+    const bool use_chol = s_bad == 0;
+    if (!use_chol) {                       // rebuild G from the statistics
+        for (int t = threadIdx.x; t < ld * n; t += blockDim.x) {
+            const int c = t / ld, r = t % ld;
+            float v = 0.f;
+            if (r < n) {
+                const float g = 0.5f * (G[r * n + c] + G[c * n + r]);
+                v = mp_mode ? g * invM : (g - csum[r] * csum[c] * invM);
+            }
+            A[c * ld + r] = v;
+        }
+    }
+    __syncthreads();
     const int nsweeps = run_jacobi(A, ld, n);
-    column_norms(A, ld, n, n, vals);
+    column_norms(A, ld, n, n, vals);        // sigma_i (Cholesky route) or lambda_i (fallback)
+    __syncthreads();
+    if (use_chol)
+        for (int i = threadIdx.x; i < n; i += blockDim.x) vals[i] = vals[i] * vals[i];
     __syncthreads();
     rank_descending(vals, n, order);
     __syncthreads();
@@ -97,13 +136,13 @@ pooled_eig_kernel(const float* __restrict__ stats, int n, int Lt, int P, float M
     for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
         const int e = t / n, c = t % n;
         const int col = order[e];
-        const float nv = vals[col];
+        const float nv = use_chol ? sqrtf(vals[col]) : vals[col];   // norm of the rotated column
         vk[e * n + c] = nv > 0.f ? A[col * ld + c] / nv : 0.f;
     }
     for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
         const int c = t / n, e = t % n;
         const int col = order[e];
-        const float nv = vals[col];
+        const float nv = use_chol ? sqrtf(vals[col]) : vals[col];
         vc[c * n + e] = nv > 0.f ? A[col * ld + c] / nv : 0.f;
     }
 }

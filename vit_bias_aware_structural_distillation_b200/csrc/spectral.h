@@ -11,11 +11,6 @@ constexpr int kSpectralThreads = 768;
 constexpr int kMaxPoints = 8;         // extraction points P
 constexpr int kMaxLayers = 64;        // teacher layers Lt
 
-__host__ __device__ inline int jacobi_ld_host(int m) {
-    int ld = ((m + 31) / 32) * 32 + 16;
-    if (ld - 32 >= m) ld -= 32;
-    return ld;
-}
 
 cudaError_t launch_pooled_eig(const float* stats, int n, int Lt, int P, float Mt, float Ms, int* ranks, float* evals,
                               float* evecs_km, float* evecs_cm, int* sweeps, cudaStream_t st);
@@ -105,5 +100,6 @@ struct PolarArgs {
     float* dbg;                           // [P*B][5]
 };
 cudaError_t launch_polar_procrustes(const PolarArgs& args, cudaStream_t st, int* launches);
+int polar_steps();                        // Newton-Schulz steps (the final iterate lives in W2 when odd, W when even)
 
 }  // namespace basd

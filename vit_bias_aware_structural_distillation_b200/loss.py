@@ -71,7 +71,8 @@ def _prepare(students: Sequence[torch.Tensor], teachers: Sequence[torch.Tensor],
         raise _lib.BasdError("student and teacher batch sizes differ")
     H = attns[0].shape[1]
     exp_attn = (B, H, Nt + 1, Nt + 1) if has_cls else (B, H, Nt, Nt)
-    if tuple(attns[0].shape) != exp_attn:
+    cls_rows_only = (B, H, 1, Nt + 1)          # HostStager hands over just the CLS query row (all relational.py:24 reads)
+    if tuple(attns[0].shape) != exp_attn and not (has_cls and tuple(attns[0].shape) == cls_rows_only):
         raise _lib.BasdError(f"attention shape {tuple(attns[0].shape)} != expected {exp_attn}")
     proj_s = proj_s.detach().to(device=dev, dtype=torch.float32).contiguous()
     proj_t = proj_t.detach().to(device=dev, dtype=torch.float32).contiguous()
@@ -203,6 +204,85 @@ def _backward(ctx, grads):
 
 
 geo_forward.register_autograd(_backward, setup_context=_setup_context)
+
+
+# --------------------------------------------------------------------------------------------- host staging
+class HostStager:
+    """Feeds the loss from HOST buffers (what `trainer.py:133-136` does for images, done here for the activations of an
+    offline / CPU-resident teacher): double-buffered device slots, copies issued on a dedicated copy stream so that the
+    transfer of step i+1 overlaps the loss of step i.  Of every teacher attention map `[B,H,N+1,N+1]` only the CLS query
+    row is gathered and copied (relational.py:24 reads nothing else): 14.5 MB instead of 2.9 GB per step at
+    BASELINE.json configs[1].  CNN teachers (no CLS, relational.py:27) need the whole map and get it.
+
+        stager = HostStager(loss_module)
+        h = stager.submit(logits, targets, student, teacher_tokens, teacher_attns)   # host tensors (pinned = async)
+        loss = stager.run(h); loss.backward()
+    """
+
+    def __init__(self, module: "BASDLoss", device=None, depth: int = 2):
+        self.module = module
+        self.device = torch.device(device) if device is not None else next(module.buffers()).device
+        if self.device.type != "cuda":
+            raise _lib.BasdError("HostStager needs the loss module on a CUDA device")
+        self.depth = depth
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self._slots = [dict() for _ in range(depth)]
+        self._next = 0
+        self.h2d_bytes_last = 0
+
+    def _dev(self, slot, key, like, shape=None):
+        shape = tuple(shape if shape is not None else like.shape)
+        buf = slot.get(key)
+        if buf is None or buf.shape != shape or buf.dtype != like.dtype:
+            buf = torch.empty(shape, dtype=like.dtype, device=self.device)
+            slot[key] = buf
+        return buf
+
+    def _pinned(self, slot, key, like, shape):
+        buf = slot.get(key)
+        if buf is None or buf.shape != tuple(shape) or buf.dtype != like.dtype:
+            buf = torch.empty(tuple(shape), dtype=like.dtype, pin_memory=True)
+            slot[key] = buf
+        return buf
+
+    def submit(self, student_output, targets, student_intermediates, all_teacher_tokens, all_teacher_attns):
+        slot = self._slots[self._next]
+        self._next = (self._next + 1) % self.depth
+        has_cls = bool(self.module.teacher_has_cls_token)
+        # host-side gather of the attention rows the loss reads
+        host_attn = {}
+        for j, a in all_teacher_attns.items():
+            if has_cls:
+                rows = self._pinned(slot, ("pin_attn", j), a, (a.shape[0], a.shape[1], 1, a.shape[3]))
+                rows.copy_(a[:, :, 0:1, :])
+                host_attn[j] = rows
+            else:
+                host_attn[j] = a
+        nbytes = 0
+        self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))     # the slot's previous consumer has been queued
+        with torch.cuda.stream(self.copy_stream):
+            def put(key, t):
+                nonlocal nbytes
+                d = self._dev(slot, key, t)
+                d.copy_(t, non_blocking=True)
+                nbytes += t.numel() * t.element_size()
+                return d
+            d_logits = put("logits", student_output)
+            d_targets = put("targets", targets)
+            d_student = {l: put(("s", l), t) for l, t in student_intermediates.items()}
+            d_teacher = {j: put(("t", j), t) for j, t in all_teacher_tokens.items()}
+            d_attn = {j: put(("a", j), t) for j, t in host_attn.items()}
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        self.h2d_bytes_last = nbytes
+        return dict(event=ev, logits=d_logits, targets=d_targets, student=d_student, teacher=d_teacher, attn=d_attn)
+
+    def run(self, handle):
+        torch.cuda.current_stream(self.device).wait_event(handle["event"])
+        logits = handle["logits"].detach().requires_grad_(handle["logits"].is_floating_point())
+        student = {l: t.detach().requires_grad_() for l, t in handle["student"].items()}
+        handle["leaf_logits"], handle["leaf_student"] = logits, student
+        return self.module(logits, handle["targets"], student, handle["teacher"], handle["attn"])
 
 
 # --------------------------------------------------------------------------------------------- reference API
