@@ -176,7 +176,13 @@ def procrustes_core(s, tbar, a, factor_side="teacher", Ktt=None, eig_floor=1e-6)
 # Whole path: forward + closed-form backward (no autograd anywhere)
 # ---------------------------------------------------------------------------------------------
 def forward_backward(inputs, proj_s, proj_t, log_temperatures, token_layers, *, has_cls, n_student_tokens,
-                     dtype=torch.float64, emulate_bf16=False, ce=None, factor_side=None):
+                     dtype=torch.float64, emulate_bf16=False, ce=None, factor_side=None, allreduce=None, world=1):
+    """`allreduce` (in-place sum over ranks) and `world` model the batch-sharded path: every rank
+    calls this on its shard; the pooled statistics, d loss / d w and the two UW-SO scalars are summed at exactly the
+    points where loss.py issues its collectives.  Returned student gradients follow the CUDA path's convention
+    (gradient of the rank-local mean, i.e. world x the global-mean gradient); log_temperature gradients are global."""
+    if allreduce is None:
+        allreduce = lambda t: t
     dt = dtype
     student = {l: v.to(dt) for l, v in inputs["student"].items()}
     teacher = {j: v.to(dt) for j, v in inputs["teacher"].items()}
@@ -195,6 +201,7 @@ def forward_backward(inputs, proj_s, proj_t, log_temperatures, token_layers, *, 
     ranks, Urot, sws = [], [], []
     for j in t_idx:
         G, c, M = teacher_stats(teacher[j], proj_t, dt, emulate_bf16)
+        allreduce(G); allreduce(c); M = M * world                     # collective 1 ("stats")
         k = mp_rank_from_gram(G, M, Ds - 1)
         lam, V = centred_eig(G, c, M)
         ranks.append(k)
@@ -209,6 +216,7 @@ def forward_backward(inputs, proj_s, proj_t, log_temperatures, token_layers, *, 
     for i, layer in enumerate(token_layers):
         S = student[layer]
         G, c, M = student_stats(S, dt)
+        allreduce(G); allreduce(c); M = M * world                     # collective 1 ("stats")
         lam, V = centred_eig(G, c, M)
         d2, gammas = [], []
         for jj in range(Lt):
@@ -237,8 +245,10 @@ def forward_backward(inputs, proj_s, proj_t, log_temperatures, token_layers, *, 
     geo = torch.stack(out["geo_i"]).mean()
     out["geo"] = geo
     if ce is not None:
-        inv = torch.stack([1.0 / ce.to(dt).clamp(min=torch.finfo(torch.float32).eps),
-                           1.0 / geo.clamp(min=torch.finfo(torch.float32).eps)])
+        pair = torch.stack([ce.to(dt).detach(), geo.detach()])       # UW-SO weights from the GLOBAL means (loss.py forward)
+        allreduce(pair); pair = pair / world
+        inv = torch.stack([1.0 / pair[0].clamp(min=torch.finfo(torch.float32).eps),
+                           1.0 / pair[1].clamp(min=torch.finfo(torch.float32).eps)])
         omega = inv / inv.sum()
         out["loss"] = omega[0] * ce.to(dt) + omega[1] * geo
         g_geo = omega[1]
@@ -257,9 +267,10 @@ def forward_backward(inputs, proj_s, proj_t, log_temperatures, token_layers, *, 
         Dt_ = 2 * (Theta @ sv["tbar"] - sv["a"].unsqueeze(-1) * mu_t.unsqueeze(1))   # K10: [B,N,Dt]
         gwt = (ga - (ga * sv["a"]).sum(-1, keepdim=True)) / sv["ssum"]            # d/d w~
         gw = (Dt_.unsqueeze(0) * T_al).sum(dim=(1, 2, 3)) + (gwt.unsqueeze(0) * rows_i).sum(dim=(1, 2))   # K11
+        allreduce(gw)                                                  # collective 2 ("gw")
         gw = gw * scale
         gd, glt = mixing_weights_backward(gw, sv["w"], sv["d2"], sv["tau"], logT[i])
-        grad_logT[i] = glt
+        grad_logT[i] = glt / world
         Gam = sum(gd[jj] * sv["gammas"][jj] for jj in range(Lt))                  # K12
         S = sv["S"]
         mu = sv["c"] / sv["M"]
