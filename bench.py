@@ -74,36 +74,46 @@ def device_inputs(w, dev, seed):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler(threading.Thread):
+    """One streaming `nvidia-smi -lms 50` process (a fresh nvidia-smi per sample takes longer than a short timed region)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.samples, self._halt = index, [], threading.Event()
+        self.index, self.samples, self.proc = index, [], None
+        self.t_start = None
 
     def run(self):
-        while not self._halt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self._halt.wait(0.2)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.samples.append((time.perf_counter(), [x.strip() for x in line.strip().split(",")]))
+        except Exception:
+            pass
+
+    def mark(self):
+        """Start of the timed region: only samples taken after this are reported."""
+        self.t_start = time.perf_counter()
 
     def finish(self):
-        self._halt.set()
-        self.join(timeout=6)
-        sm = sorted(int(float(s[1])) for s in self.samples if len(s) > 2 and s[1].replace(".", "").isdigit())
-        mx = [int(float(s[2])) for s in self.samples if len(s) > 2 and s[2].replace(".", "").isdigit()]
+        t_end = time.perf_counter()
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=3)
+        rows = [s for t, s in self.samples if self.t_start is None or (self.t_start <= t <= t_end + 0.05)]
+        if not rows:
+            rows = [s for _, s in self.samples[-1:]]
+        sm = sorted(int(float(s[1])) for s in rows if len(s) > 2 and s[1].replace(".", "").isdigit())
+        mx = [int(float(s[2])) for s in rows if len(s) > 2 and s[2].replace(".", "").isdigit()]
+        pw = [float(s[3]) for s in rows if len(s) > 3 and s[3].replace(".", "").isdigit()]
         reasons = set()
-        for s in self.samples:
+        for s in rows:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(self.samples)}
+                "samples": len(rows), "power_w_max": max(pw) if pw else None}
 
 
 # ------------------------------------------------------------------------------------------------ reference / CPU arm
@@ -246,8 +256,10 @@ def main():
     lib.basd_timing_enable(1)
     sampler = ClockSampler(local_rank)
     sampler.start()
+    time.sleep(0.3)                       # let the streaming nvidia-smi come up before the timed region
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark()
     e0.record()
     for _ in range(args.steps):
         loss = step(logits, targets, student, teacher, attn)
@@ -322,15 +334,45 @@ def main():
     dom = max(per_step, key=per_step.get) if per_step else None
     w_alg = algorithmic_bytes(w)
     f_tc = tensor_flops(w)
-    achieved = w_alg / (ms_step * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
-                "scope": "whole step: W_alg = 2 X_T + 4 X_S + A_needed (SURVEY.md §8d) over the step time", "peak_source": peak_src,
-                "algorithmic_bytes_per_step": w_alg,
-                "tensor": {"achieved": f_tc / (ms_step * 1e-3) / 1e12, "peak": tc_peak, "unit": "TFLOP/s", "frac": f_tc / (ms_step * 1e-3) / 1e12 / tc_peak,
-                           "algorithmic_flops_per_step": f_tc},
-                "dominant_kernel": dom, "dominant_kernel_ms_per_step": per_step.get(dom) if dom else None,
-                "dominant_kernel_share": (per_step[dom] / ms_step) if dom else None,
-                "kernel_ms_per_step": {k: round(v, 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])}}
+    # dominant kernel: algorithmic work per launch / its average launch duration (CUDA events on the launching stream)
+    n_prob = w.P * w.B
+    ksteps = int(lib.basd_polar_steps())
+    polar_launches = 4 * ksteps + 2
+    polar_flops = n_prob * (ksteps * (2 * w.Ds * w.Ns * w.Ns + 2 * w.Ds * w.Ds * w.Ns + 2 * w.Ds ** 3 + 2 * w.Ds * w.Ds * w.Ns)
+                            + 2 * w.Ns * w.Ns * w.Ds + 2 * w.Ns * w.Ds * w.Ns)
+    table = {   # slot -> (bound, algorithmic units per step, launches per step, description)
+        "polar_gemm": ("tensor", polar_flops, polar_launches,
+                       "Newton-Schulz polar iteration: (4 x steps + 2) products of D_s x N_s x {N_s, D_s} per (point, sample); plain 2mnk "
+                       "flops - the 3 split-bf16 MMAs per product are not counted"),
+        "pooled_eig": ("tensor", 0, 1, "fp32 Jacobi on CUDA cores: no HBM / tensor roofline applies"),
+    }
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tr.get(dom, {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    if dom in table and table[dom][1] > 0:
+        bound, units, launches, what = table[dom]
+        ms_launch = per_step[dom] / launches
+        ach = units / launches / (ms_launch * 1e-3) / 1e12
+        roofline = {"bound": bound, "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach / tc_peak, "traffic": traffic,
+                    "kernel": dom, "what": what, "launches_per_step": launches, "avg_launch_ms": ms_launch,
+                    "algorithmic_flops_per_launch": units / launches}
+    else:
+        achieved = w_alg / (ms_step * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
+                    "kernel": "whole step"}
+    roofline.update({
+        "peak_source": peak_src,
+        "step": {"hbm": {"algorithmic_bytes_per_step": w_alg, "achieved_gbs": w_alg / (ms_step * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                         "frac": w_alg / (ms_step * 1e-3) / 1e9 / hbm_peak},
+                 "tensor": {"algorithmic_flops_per_step": f_tc, "achieved_tflops": f_tc / (ms_step * 1e-3) / 1e12, "peak_tflops": tc_peak,
+                            "frac": f_tc / (ms_step * 1e-3) / 1e12 / tc_peak},
+                 "scope": "W_alg = 2 X_T + 4 X_S + A_needed and F_tc of SURVEY.md section 8d over the whole step time"},
+        "dominant_kernel": dom, "dominant_kernel_ms_per_step": per_step.get(dom) if dom else None,
+        "dominant_kernel_share": (per_step[dom] / ms_step) if dom else None,
+        "kernel_ms_per_step": {k: round(v, 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])}})
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -344,6 +386,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": w.name, "per_gpu_batch": w.B, "global_batch": w.B * world, "Ns": w.Ns, "Nt": w.Nt, "Ds": w.Ds, "Dt": w.Dt,
                        "Lt": w.Lt, "H": w.H, "P": w.P, "parallelism": f"dp{world} (batch-sharded, pooled statistics all-reduced)",
+                       "arithmetic": "bf16 tokens, fp32 accumulation, split-bf16 (hi+lo) tensor-core products, fp32 Jacobi",
                        "l2": "inputs (3.9 GB per step) exceed the 126 MB L2; no explicit flush"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "loss": loss_val}
     print(json.dumps(line), flush=True)

@@ -76,7 +76,8 @@ int basd_backward_finish(const basd_shape* shape, const basd_inputs* in, void* w
 
 /* Named views into the workspace (for the collectives and for tests).  Names: "stats" [(Lt+P)*(Ds*Ds+Ds)] f32,
  * "gw" [P*Lt] f32, "ranks" [Lt] i32, "w" [P*Lt], "d2" [P*Lt], "geo_i" [P], "loss_b" [P*B], "rows" [Lt*B*Nt],
- * "a" [P*B*Ns], "evals" [(Lt+P)*Ds], "cos" [P*Lt*Ds], "dbg" [P*B*5] (nuc, tr_s, tr_t, sweeps, chol flag), "gdir", "ktt". */
+ * "a" [P*B*Ns], "evals" [(Lt+P)*Ds], "cos" [P*Lt*Ds], "dbg" [P*B*5] (nuc, tr_s, tr_t, polar steps, ||C||_F^2), "gdir", "ktt",
+ * "polar_*" (state of the polar iteration; bf16 views count hi then lo elements). */
 int basd_view(const basd_shape* shape, void* workspace, const char* name, void** ptr, size_t* count);
 
 /* marchenko_pastur_rank(features[M,D]) (layer_selector.py:8-20), rank written to device int; D <= 224, M >= D.
@@ -96,6 +97,9 @@ long long basd_launch_count(void);
 int basd_timing_slots(void);
 const char* basd_timing_name(int slot);
 int basd_timing_read(int slot, float* ms_total, int* brackets);
+
+/* Number of Newton-Schulz steps of the Procrustes polar iteration (4 tensor-core products per step + 2 final ones). */
+int basd_polar_steps(void);
 
 const char* basd_last_error(void);
 const char* basd_version(void);

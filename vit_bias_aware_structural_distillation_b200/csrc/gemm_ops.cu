@@ -238,14 +238,19 @@ cudaError_t polar_gemm(bool b_mn, const SplitMat& A, const SplitMat& B, int batc
         const int ocb = (n_cols + 63) / 64;
         if (make_map_tiled(&maps.o[0], a.out_hi, m_rows, ocb, batches, a.out_stride, 32)) return cudaErrorInvalidValue;
         if (make_map_tiled(&maps.o[1], a.out_lo, m_rows, ocb, batches, a.out_stride, 32)) return cudaErrorInvalidValue;
-        if (a.out2_hi) {
-            if (make_map_tiled(&maps.o[2], a.out2_hi, m_rows, ocb, batches, a.out_stride, 32)) return cudaErrorInvalidValue;
-            if (make_map_tiled(&maps.o[3], a.out2_lo, m_rows, ocb, batches, a.out_stride, 32)) return cudaErrorInvalidValue;
+        if (a.aux_mode) {
+            if (make_map_tiled(&maps.o[2], a.aux_hi, m_rows, ocb, batches, a.out_stride, 32)) return cudaErrorInvalidValue;
+            if (make_map_tiled(&maps.o[3], a.aux_lo, m_rows, ocb, batches, a.out_stride, 32)) return cudaErrorInvalidValue;
         }
     }
+    if (a.a_alias_b && (b_mn || A.hi != B.hi || m_rows != n_cols)) {
+        snprintf(g_gemm_err, sizeof g_gemm_err, "polar_gemm: a_alias_b needs the same K-major matrix on both sides");
+        return cudaErrorInvalidValue;
+    }
     const int b_bytes = b_mn ? a.b_groups * 8192 : a.bn_mma * 128;
-    const int stage_bytes = 2 * 16384 + 2 * b_bytes;
-    constexpr int kTail = 1024 /*alignment*/ + 1024 /*barriers*/ + 4 * 8192 /*epilogue staging*/;
+    const int stage_bytes = (a.a_alias_b ? 0 : 2 * 16384) + 2 * b_bytes;
+    const int kTail = 1024 /*alignment*/ + 1024 /*barriers*/ + 4 * 8192 /*epilogue staging*/ + (a.aux_mode ? 4 * 8192 : 0) /*aux tiles*/
+                      + (a.a_alias_b ? 16384 : 0) /*aliased A tile of the last rows reads past its B tile*/;
     int stages = (232448 - kTail) / stage_bytes;
     if (stages > 4) stages = 4;
     if (stages < 1) {

@@ -47,7 +47,15 @@ __device__ __forceinline__ void store_split(__nv_bfloat16* hi, __nv_bfloat16* lo
 // prep_student: s_w = sqrt(a) (s - mu_s)  ->  SW [N][Ds] (split), W_0 = s_w^T [Ds][Np] (split), ksd, tr_s
 // one CTA per problem; the whole s_w tile lives in shared memory (fp32, padded rows)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ void store_split2(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t idx, float v0, float v1) {   // idx even
+    const __nv_bfloat16 h0 = __float2bfloat16(v0), h1 = __float2bfloat16(v1);
+    __nv_bfloat162 hv; hv.x = h0; hv.y = h1;
+    *reinterpret_cast<__nv_bfloat162*>(hi + idx) = hv;
+    *reinterpret_cast<__nv_bfloat162*>(lo + idx) = __floats2bfloat162_rn(v0 - __bfloat162float(h0), v1 - __bfloat162float(h1));
+}
+
+constexpr int kPrepThreads = 512;
+__global__ void __launch_bounds__(kPrepThreads)
 polar_prep_student_kernel(PolarArgs g) {
     extern __shared__ float sm[];
     const int N = g.Ns, D = g.Ds, ldS = D + 1;
@@ -64,20 +72,23 @@ polar_prep_student_kernel(PolarArgs g) {
         a_s[n] = a;
         q_s[n] = sqrtf(a);
     }
+    // raw tokens -> shared memory (bf16x2 loads, D is even)
+    for (int t = threadIdx.x; t < N * D / 2; t += blockDim.x) {
+        const float2 v = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(S)[t]);
+        const int n = (2 * t) / D, d = (2 * t) % D;
+        sw[n * ldS + d] = v.x;
+        sw[n * ldS + d + 1] = v.y;
+    }
     __syncthreads();
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
         float m = 0.f;
-        for (int n = 0; n < N; ++n) m = fmaf(a_s[n], __bfloat162float(S[static_cast<size_t>(n) * D + d]), m);
+        for (int n = 0; n < N; ++n) m = fmaf(a_s[n], sw[n * ldS + d], m);
         mu[d] = m;
     }
     __syncthreads();
-    __nv_bfloat16* swh = g.SW.hi + prob * g.SW.batch_stride;
-    __nv_bfloat16* swl = g.SW.lo + prob * g.SW.batch_stride;
     for (int t = threadIdx.x; t < N * D; t += blockDim.x) {
         const int n = t / D, d = t % D;
-        const float v = q_s[n] * (__bfloat162float(S[t]) - mu[d]);
-        sw[n * ldS + d] = v;
-        store_split(swh, swl, g.SW.at(n, d), v);
+        sw[n * ldS + d] = q_s[n] * (sw[n * ldS + d] - mu[d]);
     }
     __syncthreads();
     float* ksd = g.vec + static_cast<size_t>(prob) * 4 * N;
@@ -93,12 +104,23 @@ polar_prep_student_kernel(PolarArgs g) {
     }
     const float tr_s = cta_sum(part, red);
     if (threadIdx.x == 0) g.scal[prob * 4 + 1] = tr_s;
+    // SW = s_w  [N][Ds], tiled [d block][n][64]: pairs of consecutive d
+    __nv_bfloat16* swh = g.SW.hi + prob * g.SW.batch_stride;
+    __nv_bfloat16* swl = g.SW.lo + prob * g.SW.batch_stride;
+    const int Dp = (D + 63) / 64 * 64;
+    for (int t = threadIdx.x; t < N * Dp / 2; t += blockDim.x) {
+        const int e = 2 * t;                                  // storage index: ((cb * N + n) * 64 + j)
+        const int j = e % 64, n = (e / 64) % N, d = (e / (64 * N)) * 64 + j;
+        store_split2(swh, swl, e, d < D ? sw[n * ldS + d] : 0.f, d + 1 < D ? sw[n * ldS + d + 1] : 0.f);
+    }
+    // W_0 = s_w^T [Ds][N], tiled [n block][d][64]: pairs of consecutive n; padding columns stored as zeros
     __nv_bfloat16* wh = g.W.hi + prob * g.W.batch_stride;
     __nv_bfloat16* wl = g.W.lo + prob * g.W.batch_stride;
-    const int Np = (N + 63) / 64 * 64;                   // padding columns of the last block are stored as zeros
-    for (int t = threadIdx.x; t < D * Np; t += blockDim.x) {
-        const int n = t % 64 + (t / (64 * D)) * 64, d = (t / 64) % D;        // t runs in storage order
-        store_split(wh, wl, t, n < N ? sw[n * ldS + d] : 0.f);
+    const int Np = (N + 63) / 64 * 64;
+    for (int t = threadIdx.x; t < D * Np / 2; t += blockDim.x) {
+        const int e = 2 * t;                                  // storage index: ((nb * D + d) * 64 + j)
+        const int j = e % 64, d = (e / 64) % D, n = (e / (64 * D)) * 64 + j;
+        store_split2(wh, wl, e, n < N ? sw[n * ldS + d] : 0.f, n + 1 < N ? sw[(n + 1) * ldS + d] : 0.f);
     }
 }
 
@@ -217,9 +239,10 @@ cudaError_t launch_polar_procrustes(const PolarArgs& g, cudaStream_t st, int* la
     const int N = g.Ns, D = g.Ds, nprob = g.n_problems;
     int count = 0;
     {
+        TimingScope ts(kSlotPolarPrep, st, 2);
         const size_t smem = (static_cast<size_t>(N) * (D + 1) + 2 * N + D + 64) * sizeof(float);
         PCK(cudaFuncSetAttribute(polar_prep_student_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        polar_prep_student_kernel<<<nprob, 256, smem, st>>>(g);
+        polar_prep_student_kernel<<<nprob, kPrepThreads, smem, st>>>(g);
         PCK(cudaGetLastError());
         polar_prep_teacher_kernel<<<nprob, 256, (3 * N + 64) * sizeof(float), st>>>(g);
         PCK(cudaGetLastError());
@@ -231,6 +254,8 @@ cudaError_t launch_polar_procrustes(const PolarArgs& g, cudaStream_t st, int* la
     // Step 0 runs on the unnormalised W_0 = s_w^T; r = 1 / ||C||_F^2 (trace of W_0 K_t W_0^T, accumulated by the first
     // product) enters the later epilogues of that step as a per-problem scalar.
     SplitMat Wc = g.W, Wn = g.W2;
+    TimingScope* gemm_scope = new TimingScope(kSlotPolarGemm, st, 4 * kPolarSteps + 2);
+    struct Del { TimingScope*& p; ~Del() { delete p; } } gemm_del{gemm_scope};
     for (int k = 0; k < kPolarSteps; ++k) {
         const float ca = kPolarCoef[k][0], cb = kPolarCoef[k][1], cc = kPolarCoef[k][2];
         const bool first = k == 0;
@@ -241,16 +266,17 @@ cudaError_t launch_polar_procrustes(const PolarArgs& g, cudaStream_t st, int* la
         a.epi = PG_EPI_SPLIT; a.out_hi = g.T.hi; a.out_lo = g.T.lo; a.out_stride = g.T.batch_stride; a.scale_c = 1.f;
         if (first) { a.trace = fro2_dense; a.trace_mode = 2; a.aux_hi = Wc.hi; a.aux_lo = Wc.lo; }
         PCK(polar_gemm(false, Wc, g.Kt, nprob, a, st));
-        // G2: A = T W^T,  A2 = b I + c r A
+        // G2: A = T W^T
         memset(&a, 0, sizeof a);
         a.epi = PG_EPI_SPLIT; a.out_hi = g.A.hi; a.out_lo = g.A.lo; a.out_stride = g.A.batch_stride; a.scale_c = 1.f;
-        a.out2_hi = g.A2.hi; a.out2_lo = g.A2.lo; a.d1 = cb; a.d2 = cc; a.p2 = first ? 1.f : 0.f; a.norm2 = norm;
         PCK(polar_gemm(false, g.T, Wc, nprob, a, st));
-        // G3: Bm = a I + r A A2              (= a I + b (rA) + c (rA)^2)
+        // G3: Bm = a I + b (rA) + c (rA)^2   (A is both operands: the A tile aliases the B tile; the b A term is added from a
+        //     TMA-loaded copy of the output-shaped tile of A in the epilogue)
         memset(&a, 0, sizeof a);
         a.epi = PG_EPI_SPLIT; a.out_hi = g.Bm.hi; a.out_lo = g.Bm.lo; a.out_stride = g.Bm.batch_stride;
-        a.scale_c = 1.f; a.scale_p = first ? 1.f : 0.f; a.diag_add = ca; a.norm2 = norm;
-        PCK(polar_gemm(false, g.A, g.A2, nprob, a, st));
+        a.a_alias_b = 1; a.aux_mode = 1; a.aux_hi = g.A.hi; a.aux_lo = g.A.lo;
+        a.aux_c = cb; a.aux_p = first ? 1.f : 0.f; a.scale_c = cc; a.scale_p = first ? 2.f : 0.f; a.diag_add = ca; a.norm2 = norm;
+        PCK(polar_gemm(false, g.A, g.A, nprob, a, st));
         // G4: W_next = sqrt(r) Bm W          (W enters as the MN-major B operand; ping-pong buffers)
         memset(&a, 0, sizeof a);
         a.epi = PG_EPI_SPLIT; a.out_hi = Wn.hi; a.out_lo = Wn.lo; a.out_stride = Wn.batch_stride;
@@ -270,6 +296,8 @@ cudaError_t launch_polar_procrustes(const PolarArgs& g, cudaStream_t st, int* la
         a.epi = PG_EPI_THETA; a.out_hi = g.theta; a.out_lo = g.theta_lo; a.out_stride = static_cast<long long>(N) * g.NsPad; a.ld_out = g.NsPad;
         a.vec_a = g.a;
         PCK(polar_gemm(true, g.SW, Wc, nprob, a, st));
+        delete gemm_scope; gemm_scope = nullptr;
+        TimingScope tf(kSlotPolarFinish, st, 1);
         polar_finish_kernel<<<nprob, 256, (2 * N + 64) * sizeof(float), st>>>(g);
         PCK(cudaGetLastError());
         count += 3;

@@ -23,7 +23,7 @@ constexpr int PG_THREADS = 192;
 constexpr int PG_BK = 64;
 
 enum PolarEpi : int {
-    PG_EPI_SPLIT = 0,       // out = split(scale * acc + diag_add * I); optional out2 = split(d1 * I + d2 r^p2 * acc); optional trace
+    PG_EPI_SPLIT = 0,       // out = split(scale * acc + aux_scale * aux + diag_add * I); optional trace
     PG_EPI_F32 = 2,         // out_f32 = acc
     PG_EPI_THETA = 3,       // out = split(2 (diag(a) - q acc q^T - a a^T))   (teacher side)
 };
@@ -31,7 +31,7 @@ enum PolarEpi : int {
 struct PolarGemmMaps {
     CUtensorMap a[2];
     CUtensorMap b[2];
-    CUtensorMap o[4];                // SPLIT outputs: out hi, out lo, out2 hi, out2 lo (box = 32 rows x 64 columns)
+    CUtensorMap o[4];                // SPLIT: out hi, out lo (TMA stores), aux hi, aux lo (TMA loads); box = 32 rows x 64 columns
 };
 
 struct PolarGemmArgs {
@@ -48,8 +48,9 @@ struct PolarGemmArgs {
     const float* norm2;              // if non-null r = 1 / norm2[z], else r = 1
     float scale_c, scale_p;          // scale = scale_c * r^scale_p
     float diag_add;
-    // secondary output, same layout as the primary
-    __nv_bfloat16* out2_hi; __nv_bfloat16* out2_lo; float d1, d2, p2;
+    // auxiliary split matrix laid out like the output, added in the epilogue: out += aux_c * r^aux_p * aux (TMA-loaded)
+    int aux_mode; float aux_c, aux_p;
+    int a_alias_b;                   // A == B (K-major, same matrix): the A tile is read out of the B tile, no A loads
     // trace[z] += sum(diag(acc)) (mode 1) or sum(acc .* aux) (mode 2; aux = split pair laid out like the primary output)
     float* trace; int trace_mode; const __nv_bfloat16* aux_hi; const __nv_bfloat16* aux_lo;
     float* out_f32; long long out_f32_stride; int ld_f32;
@@ -96,6 +97,23 @@ __device__ __forceinline__ void pg_stage_split16(uint8_t* stg_hi, uint8_t* stg_l
     *reinterpret_cast<uint4*>(stg_lo + row * 128 + p0) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
     *reinterpret_cast<uint4*>(stg_lo + row * 128 + p1) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
 }
+// inverse of pg_stage_split16: 16 values hi + lo of a TMA-loaded (swizzled) 32 x 64 tile
+__device__ __forceinline__ void pg_read_split16(const uint8_t* t_hi, const uint8_t* t_lo, int row, int chunk0, float* x) {
+    const int p0 = (chunk0 ^ (row & 7)) * 16, p1 = ((chunk0 + 1) ^ (row & 7)) * 16;
+    const uint4 h0 = *reinterpret_cast<const uint4*>(t_hi + row * 128 + p0), h1 = *reinterpret_cast<const uint4*>(t_hi + row * 128 + p1);
+    const uint4 l0 = *reinterpret_cast<const uint4*>(t_lo + row * 128 + p0), l1 = *reinterpret_cast<const uint4*>(t_lo + row * 128 + p1);
+    const __nv_bfloat162* a0 = reinterpret_cast<const __nv_bfloat162*>(&h0);
+    const __nv_bfloat162* a1 = reinterpret_cast<const __nv_bfloat162*>(&h1);
+    const __nv_bfloat162* b0 = reinterpret_cast<const __nv_bfloat162*>(&l0);
+    const __nv_bfloat162* b1 = reinterpret_cast<const __nv_bfloat162*>(&l1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 u0 = __bfloat1622float2(a0[i]), w0 = __bfloat1622float2(b0[i]);
+        const float2 u1 = __bfloat1622float2(a1[i]), w1 = __bfloat1622float2(b1[i]);
+        x[2 * i] = u0.x + w0.x; x[2 * i + 1] = u0.y + w0.y;
+        x[8 + 2 * i] = u1.x + w1.x; x[8 + 2 * i + 1] = u1.y + w1.y;
+    }
+}
 __device__ __forceinline__ void pg_stage_zero16(uint8_t* stg_hi, uint8_t* stg_lo, int row, int chunk0) {
     const int p0 = (chunk0 ^ (row & 7)) * 16, p1 = ((chunk0 + 1) ^ (row & 7)) * 16;
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
@@ -110,15 +128,17 @@ __global__ void __launch_bounds__(PG_THREADS, 1)
 polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArgs args) {
     extern __shared__ uint8_t pg_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(pg_smem_raw) + 1023) & ~uintptr_t(1023));
-    constexpr int kABytes = 128 * 128;                 // one 128-row A tile per operand buffer
+    const int kABytes = args.a_alias_b ? 0 : 128 * 128;    // one 128-row A tile per operand buffer (none when aliased)
     const int b_bytes = B_MN ? args.b_groups * 8192 : args.bn_mma * 128;
     const int stage_bytes = 2 * kABytes + 2 * b_bytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + args.stages * stage_bytes);
     uint64_t* empty_bar = full_bar + args.stages;
     uint64_t* tmem_full_bar = empty_bar + args.stages;         // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;              // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    uint64_t* aux_bar = tmem_empty_bar + 2;                    // [4] one per epilogue warp
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 4);
     uint8_t* staging = smem + args.stages * stage_bytes + 1024;          // 4 warps x (hi 4 KB + lo 4 KB), 1024-aligned
+    uint8_t* aux_staging = staging + 4 * 8192;                           // same shape, only allocated when aux_mode
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_kb = (args.k_total + PG_BK - 1) / PG_BK;
@@ -126,6 +146,7 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
     if (threadIdx.x == 0) {
         for (int s = 0; s < args.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 4); }
+        for (int i = 0; i < 4; ++i) mbar_init(&aux_bar[i], 1);
         fence_mbar_init();
         tma_prefetch_desc(&maps.a[0]); tma_prefetch_desc(&maps.a[1]);
         tma_prefetch_desc(&maps.b[0]); tma_prefetch_desc(&maps.b[1]);
@@ -146,14 +167,14 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
             for (int w = blockIdx.x; w < args.n_items; w += gridDim.x) {
                 const int z = w / args.n_mt, mt = w % args.n_mt;
                 const int a_rows = args.a_rows_tile[mt];
-                const uint32_t tx = 2 * a_rows * 128 + 2 * b_bytes;
+                const uint32_t tx = (args.a_alias_b ? 0 : 2 * a_rows * 128) + 2 * b_bytes;
                 for (int kb = 0; kb < n_kb; ++kb, ++it) {
                     const int s = it % args.stages;
                     const uint32_t ph = (it / args.stages) & 1;
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     mbar_arrive_expect_tx(&full_bar[s], tx);
                     uint8_t* st = smem + s * stage_bytes;
-                    for (int i = 0; i < 2; ++i) {
+                    for (int i = 0; i < 2 && !args.a_alias_b; ++i) {
                         uint8_t* dst = st + i * kABytes;
                         for (int g = 0; g < a_rows / 64; ++g)
                             tma_load_4d(dst + g * 8192, &maps.a[i], &full_bar[s], 0, mt * 128 + g * 64, kb, z);
@@ -177,6 +198,7 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
         for (int w = blockIdx.x; w < args.n_items; w += gridDim.x, ++item) {
             const int acc = item & 1;
             const uint32_t acc_ph = (item >> 1) & 1;
+            const int mt_mma = w % args.n_mt;
             mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);           // epilogue has drained this accumulator
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * args.bn_mma;
@@ -191,8 +213,9 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
                     if (ksteps > 4) ksteps = 4;
 #pragma unroll
                     for (int t = 0; t < 3; ++t) {                // hi*hi, hi*lo, lo*hi
-                        const uint32_t a_base = st + (t == 2 ? kABytes : 0);
                         const uint32_t b_base = st + 2 * kABytes + (t == 1 ? b_bytes : 0);
+                        // aliased: rows mt*128.. of the (hi or lo) B tile are the A tile
+                        const uint32_t a_base = args.a_alias_b ? st + (t == 2 ? b_bytes : 0) + mt_mma * 16384 : st + (t == 2 ? kABytes : 0);
                         for (int ks = 0; ks < ksteps; ++ks) {
                             const uint64_t adesc = umma_smem_desc(a_base + ks * 32, 16, 1024);
                             const uint64_t bdesc = B_MN ? umma_smem_desc(b_base + ks * 2048, 8192, 1024)
@@ -210,10 +233,20 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
         // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
         const int q = warp & 3;
         int item = 0;
+        uint32_t aux_phase = 0;
         for (int w = blockIdx.x; w < args.n_items; w += gridDim.x, ++item) {
             const int z = w / args.n_mt, mt = w % args.n_mt;
             const int acc = item & 1;
             const uint32_t acc_ph = (item >> 1) & 1;
+            const bool warp_rows_ok = mt * 128 + q * 32 < args.m_rows;       // uniform: this warp owns at least one valid row
+            uint8_t* aux_hi_s = aux_staging + (warp - 2) * 8192;
+            uint8_t* aux_lo_s = aux_hi_s + 4096;
+            const bool use_aux = args.aux_mode != 0 && warp_rows_ok;
+            if (use_aux && lane == 0) {                                    // block 0 of the auxiliary tile, hidden behind the main loop
+                mbar_arrive_expect_tx(&aux_bar[warp - 2], 8192);
+                tma_load_4d(aux_hi_s, &maps.o[2], &aux_bar[warp - 2], 0, mt * 128 + q * 32, 0, z);
+                tma_load_4d(aux_lo_s, &maps.o[3], &aux_bar[warp - 2], 0, mt * 128 + q * 32, 0, z);
+            }
             mbar_wait(&tmem_full_bar[acc], acc_ph);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * args.bn_mma;
@@ -222,7 +255,7 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
             float r = 1.f;
             if (args.norm2) r = 1.f / args.norm2[z];
             const float scale = args.scale_c * (args.scale_p == 0.f ? 1.f : powf(r, args.scale_p));
-            const float d2r = args.d2 * (args.p2 == 0.f ? 1.f : powf(r, args.p2));
+            const float aux_scale = args.aux_c * (args.aux_p == 0.f ? 1.f : powf(r, args.aux_p));
             float a_row = 0.f, q_row = 0.f;
             if (args.epi == PG_EPI_THETA && row_ok) {
                 a_row = args.vec_a[static_cast<long long>(z) * args.m_rows + row];
@@ -233,10 +266,12 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
                 // convert into the warp's swizzled staging tile; every 64-column block leaves as one TMA store per half
                 uint8_t* stg_hi = staging + (warp - 2) * 8192;
                 uint8_t* stg_lo = stg_hi + 4096;
-                const bool warp_rows_ok = mt * 128 + q * 32 < args.m_rows;       // uniform: this warp owns at least one valid row
-                const bool has2 = args.out2_hi != nullptr;
-                for (int cbk = 0; cbk * 64 < args.bn_mma; ++cbk) {
-                    float y2[64];
+                const int n_cb = (args.bn_mma + 63) / 64;
+                for (int cbk = 0; cbk < n_cb; ++cbk) {
+                    if (use_aux) {
+                        mbar_wait(&aux_bar[warp - 2], aux_phase);
+                        aux_phase ^= 1;
+                    }
 #pragma unroll
                     for (int jc = 0; jc < 4; ++jc) {
                         const int c = cbk * 64 + jc * 16;
@@ -252,40 +287,34 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
                                         tr_part = fmaf(v[i], __bfloat162float(args.aux_hi[off + i]) + __bfloat162float(args.aux_lo[off + i]), tr_part);
                                 }
                             }
+                            if (use_aux) {
+                                float x[16];
+                                pg_read_split16(aux_hi_s, aux_lo_s, lane, jc * 2, x);
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                y2[jc * 16 + i] = d2r * v[i] + ((c + i == row) ? args.d1 : 0.f);
-                                v[i] = scale * v[i] + ((c + i == row) ? args.diag_add : 0.f);
+                                for (int i = 0; i < 16; ++i) v[i] = fmaf(aux_scale, x[i], scale * v[i]) + ((c + i == row) ? args.diag_add : 0.f);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) v[i] = scale * v[i] + ((c + i == row) ? args.diag_add : 0.f);
                             }
                             pg_stage_split16(stg_hi, stg_lo, lane, jc * 2, v);
                         } else {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) y2[jc * 16 + i] = 0.f;
                             pg_stage_zero16(stg_hi, stg_lo, lane, jc * 2);          // padding columns of the last block
                         }
                     }
                     fence_proxy_async_smem();
-                    __syncwarp();
+                    __syncwarp();                                               // staging complete; aux tile fully consumed
                     if (lane == 0 && warp_rows_ok) {
+                        if (use_aux && cbk + 1 < n_cb) {                        // next auxiliary block overlaps this block's store
+                            mbar_arrive_expect_tx(&aux_bar[warp - 2], 8192);
+                            tma_load_4d(aux_hi_s, &maps.o[2], &aux_bar[warp - 2], 0, mt * 128 + q * 32, cbk + 1, z);
+                            tma_load_4d(aux_lo_s, &maps.o[3], &aux_bar[warp - 2], 0, mt * 128 + q * 32, cbk + 1, z);
+                        }
                         tma_store_4d(&maps.o[0], stg_hi, 0, mt * 128 + q * 32, cbk, z);
                         tma_store_4d(&maps.o[1], stg_lo, 0, mt * 128 + q * 32, cbk, z);
                         tma_store_commit();
                         tma_store_wait_read();
                     }
                     __syncwarp();
-                    if (has2) {
-#pragma unroll
-                        for (int jc = 0; jc < 4; ++jc) pg_stage_split16(stg_hi, stg_lo, lane, jc * 2, y2 + jc * 16);
-                        fence_proxy_async_smem();
-                        __syncwarp();
-                        if (lane == 0 && warp_rows_ok) {
-                            tma_store_4d(&maps.o[2], stg_hi, 0, mt * 128 + q * 32, cbk, z);
-                            tma_store_4d(&maps.o[3], stg_lo, 0, mt * 128 + q * 32, cbk, z);
-                            tma_store_commit();
-                            tma_store_wait_read();
-                        }
-                        __syncwarp();
-                    }
                 }
             } else {
                 for (int c = 0; c < args.bn_mma; c += 16) {

@@ -67,6 +67,16 @@ cudaError_t gemm_selftest(int variant, const __nv_bfloat16* A, const __nv_bfloat
                           cudaStream_t st);
 const char* gemm_last_error();
 
+// CUDA-event bracket + launch counter of basd_capi.cu (live timing for bench.py), usable from every translation unit
+struct TimingScope {
+    void* impl;
+    TimingScope(int slot, cudaStream_t st, int n_launches);
+    ~TimingScope();
+    TimingScope(const TimingScope&) = delete;
+    TimingScope& operator=(const TimingScope&) = delete;
+};
+constexpr int kSlotPolarPrep = 10, kSlotPolarGemm = 16, kSlotPolarFinish = 17;
+
 // ---- Newton-Schulz polar iteration of the Procrustes core (polar.cu + polar_gemm.cuh)
 struct SplitMat {                         // bf16 hi/lo pair, column-block tiled: [batch][col / 64][row][col % 64]
     __nv_bfloat16* hi; __nv_bfloat16* lo;
@@ -86,7 +96,7 @@ struct PolarArgs {
     const float* a;                       // [P*B][Ns]       normalised importance
     const float* ssum;                    // [P*B]
     // scratch (all per problem)
-    SplitMat W, W2, T, A, A2, Bm, Kt, SW;
+    SplitMat W, W2, T, A, Bm, Kt, SW;
     float* Gsw;                           // [P*B][Ns][Ds]   d nuc / d s_w
     float* vec;                           // [P*B][4][Ns]    ksd, ktd, (spare), (spare)
     float* scal;                          // [P*B][4]        (spare), tr_s, tr_t, (spare)
