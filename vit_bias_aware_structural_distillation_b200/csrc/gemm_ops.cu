@@ -221,6 +221,7 @@ cudaError_t polar_gemm(bool b_mn, const SplitMat& A, const SplitMat& B, int batc
     a.m_rows = m_rows; a.n_cols = n_cols; a.k_total = K;
     a.n_mt = (m_rows + 127) / 128;
     a.n_items = batches * a.n_mt;
+    a.n_batches = batches;
     a.a_rows_tile[0] = m_rows >= 128 ? 128 : (m_rows + 63) / 64 * 64;
     a.a_rows_tile[1] = m_rows > 128 ? (m_rows - 128 + 63) / 64 * 64 : 0;
     a.bn_mma = (n_cols + 15) / 16 * 16;

@@ -51,6 +51,7 @@ struct PolarGemmArgs {
     // auxiliary split matrix laid out like the output, added in the epilogue: out += aux_c * r^aux_p * aux (TMA-loaded)
     int aux_mode; float aux_c, aux_p;
     int a_alias_b;                   // A == B (K-major, same matrix): the A tile is read out of the B tile, no A loads
+    int reverse, n_batches;          // reverse: walk the problems last-to-first (what the previous launch wrote last is still in L2)
     // trace[z] += sum(diag(acc)) (mode 1) or sum(acc .* aux) (mode 2; aux = split pair laid out like the primary output)
     float* trace; int trace_mode; const __nv_bfloat16* aux_hi; const __nv_bfloat16* aux_lo;
     float* out_f32; long long out_f32_stride; int ld_f32;
@@ -165,7 +166,8 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
         if (lane == 0) {
             int it = 0;
             for (int w = blockIdx.x; w < args.n_items; w += gridDim.x) {
-                const int z = w / args.n_mt, mt = w % args.n_mt;
+                const int mt = w % args.n_mt;
+                const int z = args.reverse ? args.n_batches - 1 - w / args.n_mt : w / args.n_mt;
                 const int a_rows = args.a_rows_tile[mt];
                 const uint32_t tx = (args.a_alias_b ? 0 : 2 * a_rows * 128) + 2 * b_bytes;
                 for (int kb = 0; kb < n_kb; ++kb, ++it) {
@@ -235,7 +237,8 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
         int item = 0;
         uint32_t aux_phase = 0;
         for (int w = blockIdx.x; w < args.n_items; w += gridDim.x, ++item) {
-            const int z = w / args.n_mt, mt = w % args.n_mt;
+            const int mt = w % args.n_mt;
+            const int z = args.reverse ? args.n_batches - 1 - w / args.n_mt : w / args.n_mt;
             const int acc = item & 1;
             const uint32_t acc_ph = (item >> 1) & 1;
             const bool warp_rows_ok = mt * 128 + q * 32 < args.m_rows;       // uniform: this warp owns at least one valid row

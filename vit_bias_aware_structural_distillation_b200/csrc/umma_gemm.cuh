@@ -327,9 +327,32 @@ struct EpiStudentGrad {
         if (row >= rows || col0 >= cols) return;
         const long long off = static_cast<long long>(row) * ld + col0;
         float r[16];
+        const float* gp = gdir + static_cast<long long>(row) * cols + col0;
+        if (col0 + 16 <= cols && (cols & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 g4 = __ldg(reinterpret_cast<const float4*>(gp) + i);
+                const float4 c4 = __ldg(reinterpret_cast<const float4*>(corr + col0) + i);
+                r[4 * i] = alpha * g4.x + v[4 * i] - c4.x;         r[4 * i + 1] = alpha * g4.y + v[4 * i + 1] - c4.y;
+                r[4 * i + 2] = alpha * g4.z + v[4 * i + 2] - c4.z; r[4 * i + 3] = alpha * g4.w + v[4 * i + 3] - c4.w;
+            }
+            if (bf16_out) {
+                __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(out) + off;
+                uint4 w0, w1;
+                w0.x = pack_bf16x2(r[0], r[1]);   w0.y = pack_bf16x2(r[2], r[3]);   w0.z = pack_bf16x2(r[4], r[5]);   w0.w = pack_bf16x2(r[6], r[7]);
+                w1.x = pack_bf16x2(r[8], r[9]);   w1.y = pack_bf16x2(r[10], r[11]); w1.z = pack_bf16x2(r[12], r[13]); w1.w = pack_bf16x2(r[14], r[15]);
+                reinterpret_cast<uint4*>(p)[0] = w0;
+                reinterpret_cast<uint4*>(p)[1] = w1;
+            } else {
+                float* p = reinterpret_cast<float*>(out) + off;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(p)[i] = make_float4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+            }
+            return;
+        }
 #pragma unroll
         for (int i = 0; i < 16; ++i) r[i] = 0.f;
-        for (int i = 0; i < 16 && col0 + i < cols; ++i) r[i] = alpha * gdir[static_cast<long long>(row) * cols + col0 + i] + v[i] - corr[col0 + i];
+        for (int i = 0; i < 16 && col0 + i < cols; ++i) r[i] = alpha * gp[i] + v[i] - corr[col0 + i];
         if (bf16_out) {
             __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(out) + off;
             for (int i = 0; i < 16 && col0 + i < cols; ++i) p[i] = __float2bfloat16(r[i]);
