@@ -28,6 +28,10 @@ TINY = {
     "tiny_cls": synth.Workload("tiny_cls", 4, 64, 64, 48, 96, 3, 2, True),
     "tiny_interp": synth.Workload("tiny_interp", 4, 64, 36, 48, 96, 3, 2, True),
     "tiny_cnn": synth.Workload("tiny_cnn", 6, 64, 16, 48, 128, 1, 1, False),
+    # token-count resampling and CNN (no-CLS) teachers whose resampled token Gram keeps rank >= D_s (the form built so far)
+    "tiny_up": synth.Workload("tiny_up", 4, 64, 56, 48, 96, 3, 2, True),            # 56 -> 64 tokens (up-sampling)
+    "tiny_down": synth.Workload("tiny_down", 4, 64, 100, 48, 96, 3, 2, True),        # 100 -> 64 tokens (the DINOv2 256 -> 196 case)
+    "tiny_cnn_down": synth.Workload("tiny_cnn_down", 6, 64, 81, 48, 128, 1, 1, False),   # 9x9 CNN grid -> 64 student tokens
 }
 
 

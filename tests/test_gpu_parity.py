@@ -200,10 +200,12 @@ def test_phase_buffers_match_kernel_model(lib, cuda_dev):
 NOT_BUILT = {"tiny_interp", "tiny_cnn"}      # D_s > N_t - 1: needs the token-space form of the polar iteration
 
 
-@pytest.mark.parametrize("name", ["tiny_cls", "tiny_interp", "tiny_cnn"])
+@pytest.mark.parametrize("name", ["tiny_cls", "tiny_up", "tiny_down", "tiny_cnn_down", "tiny_interp", "tiny_cnn"])
 def test_tiny_cases_against_oracle_and_reference_golden(lib, cuda_dev, name):
-    """Edge cases of SURVEY.md §4: token-count interpolation 36->64, single-layer CNN teacher without CLS
-    (w == 1, zero temperature gradient), plus the plain CLS case; full reference gradients are in the fixture."""
+    """Edge cases of SURVEY.md §4 with the reference's full gradients in the fixtures: the plain CLS case, token-count
+    resampling up (56 -> 64) and down (100 -> 64, the DINOv2 256 -> 196 situation), a single-layer CNN teacher without
+    CLS (w == 1, zero temperature gradient, attention averaged over queries).  tiny_interp / tiny_cnn up-sample so few
+    teacher tokens that the cross-covariance is rank deficient: rejected loudly until the token-space form exists."""
     g, w = load_golden(name)
     inp = synth.make_inputs(w, seed=g["seed"])
     m = build_module(w, cuda_dev)
@@ -218,8 +220,9 @@ def test_tiny_cases_against_oracle_and_reference_golden(lib, cuda_dev, name):
     assert abs(out["loss"].item() - g["loss"].item()) <= TOL_LOSS * abs(g["loss"].item())
     for l in g["token_layers"]:
         assert rel(out["grad_student"][l], g["grad_student"][l]) < TOL_SGRAD
-    if name == "tiny_cnn":
-        assert out["grad_log_temperatures"].abs().max() == 0 and (out["w"] == 1).all()
+    if name.startswith("tiny_cnn"):
+        # softmax over a single layer: w == 1 and no temperature gradient (an fma leaves ~1e-7 of rounding, the reference 0)
+        assert out["grad_log_temperatures"].abs().max() < 1e-6 and (out["w"] == 1).all()
     else:
         # 256 pooled rows only: the bf16 rounding of the projected teacher tokens does not average out as it does at
         # the BASELINE sizes (>= 6272 rows, where 1e-3 holds) -> 3e-3 here
