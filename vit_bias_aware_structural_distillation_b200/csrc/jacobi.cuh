@@ -34,9 +34,58 @@ __device__ __forceinline__ void jacobi_pair(int n, int s, int k, int& p, int& q)
     q = s - k; if (q < 0) q += m1;
 }
 
+template <int CHUNKS>
+__device__ __forceinline__ void jac_load(const float* __restrict__ col, int ld, int gl, float4 (&v)[CHUNKS]) {
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+        const int r = c * JAC_CHUNK_ROWS + gl * 4;
+        v[c] = r < ld ? *reinterpret_cast<const float4*>(col + r) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+// rotates the pair held in (x, y) and writes it back if it was not already orthogonal; returns 1 if it rotated
+template <int CHUNKS>
+__device__ __forceinline__ int jac_rotate_store(float4 (&x)[CHUNKS], float4 (&y)[CHUNKS], float* __restrict__ cp, float* __restrict__ cq,
+                                                int ld, int gl, unsigned gmask, float tol) {
+    float al = 0.f, be = 0.f, ga = 0.f;
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+        al = fmaf(x[c].x, x[c].x, fmaf(x[c].y, x[c].y, fmaf(x[c].z, x[c].z, fmaf(x[c].w, x[c].w, al))));
+        be = fmaf(y[c].x, y[c].x, fmaf(y[c].y, y[c].y, fmaf(y[c].z, y[c].z, fmaf(y[c].w, y[c].w, be))));
+        ga = fmaf(x[c].x, y[c].x, fmaf(x[c].y, y[c].y, fmaf(x[c].z, y[c].z, fmaf(x[c].w, y[c].w, ga))));
+    }
+#pragma unroll
+    for (int o = JAC_GROUP / 2; o > 0; o >>= 1) {
+        al += __shfl_xor_sync(gmask, al, o);
+        be += __shfl_xor_sync(gmask, be, o);
+        ga += __shfl_xor_sync(gmask, ga, o);
+    }
+    if (!(fabsf(ga) > tol * sqrtf(al * be))) return 0;
+    const float zeta = (be - al) / (2.f * ga);
+    const float t = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(fmaf(zeta, zeta, 1.f)));
+    const float cs = rsqrtf(fmaf(t, t, 1.f));
+    const float sn = cs * t;
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+        const int r = c * JAC_CHUNK_ROWS + gl * 4;
+        if (r < ld) {
+            float4 xn, yn;
+            xn.x = cs * x[c].x - sn * y[c].x; yn.x = sn * x[c].x + cs * y[c].x;
+            xn.y = cs * x[c].y - sn * y[c].y; yn.y = sn * x[c].y + cs * y[c].y;
+            xn.z = cs * x[c].z - sn * y[c].z; yn.z = sn * x[c].z + cs * y[c].z;
+            xn.w = cs * x[c].w - sn * y[c].w; yn.w = sn * x[c].w + cs * y[c].w;
+            *reinterpret_cast<float4*>(cp + r) = xn;
+            *reinterpret_cast<float4*>(cq + r) = yn;
+        }
+    }
+    return 1;
+}
+
 // Returns the number of sweeps executed.  All threads of the CTA must call it (contains __syncthreads).
 // n_cols may be odd (the virtual last column is skipped).  Rows [m, ld) of every column must be zero.
-template <int CHUNKS>
+// A group takes TWO pairs per pass with the loads of both issued before the first rotation, so the shared-memory
+// phase of one pair overlaps the arithmetic of the other (with one pair per group every warp sat in the same phase
+// at the same time: load, compute, store, barrier - the SM alternated between an idle LSU and an idle FMA pipe).
+template <int CHUNKS, bool TWO_PAIRS>
 __device__ int jacobi_orthogonalize(float* __restrict__ A, int ld, int n_cols, float tol, int max_sweeps) {
     const int n = (n_cols + 1) & ~1;
     const int group = threadIdx.x / JAC_GROUP;
@@ -49,54 +98,21 @@ __device__ int jacobi_orthogonalize(float* __restrict__ A, int ld, int n_cols, f
     for (; sweep < max_sweeps; ++sweep) {
         int rotated = 0;
         for (int s = 0; s < n - 1; ++s) {
-            for (int k = group; k < half; k += n_groups) {
-                int p, q;
+            for (int k = group; k < half; k += (TWO_PAIRS ? 2 : 1) * n_groups) {
+                int p, q, p2 = n_cols, q2 = n_cols;
                 jacobi_pair(n, s, k, p, q);
-                if (p >= n_cols || q >= n_cols) continue;          // virtual padding column
-                float4 x[CHUNKS], y[CHUNKS];
-                float* cp = A + static_cast<size_t>(p) * ld;
-                float* cq = A + static_cast<size_t>(q) * ld;
-                float al = 0.f, be = 0.f, ga = 0.f;
-#pragma unroll
-                for (int c = 0; c < CHUNKS; ++c) {
-                    const int r = c * JAC_CHUNK_ROWS + gl * 4;
-                    if (r < ld) {
-                        x[c] = *reinterpret_cast<const float4*>(cp + r);
-                        y[c] = *reinterpret_cast<const float4*>(cq + r);
-                    } else {
-                        x[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        y[c] = x[c];
-                    }
-                    al = fmaf(x[c].x, x[c].x, fmaf(x[c].y, x[c].y, fmaf(x[c].z, x[c].z, fmaf(x[c].w, x[c].w, al))));
-                    be = fmaf(y[c].x, y[c].x, fmaf(y[c].y, y[c].y, fmaf(y[c].z, y[c].z, fmaf(y[c].w, y[c].w, be))));
-                    ga = fmaf(x[c].x, y[c].x, fmaf(x[c].y, y[c].y, fmaf(x[c].z, y[c].z, fmaf(x[c].w, y[c].w, ga))));
-                }
-#pragma unroll
-                for (int o = JAC_GROUP / 2; o > 0; o >>= 1) {
-                    al += __shfl_xor_sync(gmask, al, o);
-                    be += __shfl_xor_sync(gmask, be, o);
-                    ga += __shfl_xor_sync(gmask, ga, o);
-                }
-                if (fabsf(ga) > tol * sqrtf(al * be)) {
-                    rotated = 1;
-                    const float zeta = (be - al) / (2.f * ga);
-                    const float t = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(fmaf(zeta, zeta, 1.f)));
-                    const float cs = rsqrtf(fmaf(t, t, 1.f));
-                    const float sn = cs * t;
-#pragma unroll
-                    for (int c = 0; c < CHUNKS; ++c) {
-                        const int r = c * JAC_CHUNK_ROWS + gl * 4;
-                        if (r < ld) {
-                            float4 xn, yn;
-                            xn.x = cs * x[c].x - sn * y[c].x; yn.x = sn * x[c].x + cs * y[c].x;
-                            xn.y = cs * x[c].y - sn * y[c].y; yn.y = sn * x[c].y + cs * y[c].y;
-                            xn.z = cs * x[c].z - sn * y[c].z; yn.z = sn * x[c].z + cs * y[c].z;
-                            xn.w = cs * x[c].w - sn * y[c].w; yn.w = sn * x[c].w + cs * y[c].w;
-                            *reinterpret_cast<float4*>(cp + r) = xn;
-                            *reinterpret_cast<float4*>(cq + r) = yn;
-                        }
-                    }
-                }
+                const int k2 = k + n_groups;
+                if (TWO_PAIRS && k2 < half) jacobi_pair(n, s, k2, p2, q2);
+                const bool ok1 = p < n_cols && q < n_cols, ok2 = TWO_PAIRS && p2 < n_cols && q2 < n_cols;   // else: virtual padding column
+                float* cp = A + static_cast<size_t>(ok1 ? p : 0) * ld;
+                float* cq = A + static_cast<size_t>(ok1 ? q : 0) * ld;
+                float* cp2 = A + static_cast<size_t>(ok2 ? p2 : 0) * ld;
+                float* cq2 = A + static_cast<size_t>(ok2 ? q2 : 0) * ld;
+                float4 x[CHUNKS], y[CHUNKS], x2[CHUNKS], y2[CHUNKS];
+                if (ok1) { jac_load<CHUNKS>(cp, ld, gl, x); jac_load<CHUNKS>(cq, ld, gl, y); }
+                if (ok2) { jac_load<CHUNKS>(cp2, ld, gl, x2); jac_load<CHUNKS>(cq2, ld, gl, y2); }
+                if (ok1) rotated |= jac_rotate_store<CHUNKS>(x, y, cp, cq, ld, gl, gmask, tol);
+                if (ok2) rotated |= jac_rotate_store<CHUNKS>(x2, y2, cp2, cq2, ld, gl, gmask, tol);
             }
             __syncthreads();
         }

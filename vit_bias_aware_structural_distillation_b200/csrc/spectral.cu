@@ -18,21 +18,23 @@ constexpr float kJacobiTol = 3.0e-7f;
 constexpr int kJacobiMaxSweeps = 40;
 constexpr float kFp32Eps = 1.1920929e-7f;
 
-template <int CHUNKS>
+template <int CHUNKS, bool TWO>
 __device__ __forceinline__ int run_jacobi_chunks(float* A, int ld, int n) {
-    return jacobi_orthogonalize<CHUNKS>(A, ld, n, kJacobiTol, kJacobiMaxSweeps);
+    return jacobi_orthogonalize<CHUNKS, TWO>(A, ld, n, kJacobiTol, kJacobiMaxSweeps);
 }
+// TWO = two pairs in flight per 8-lane group (needs ~170 registers: for the 384-thread pooled kernel only)
+template <bool TWO>
 __device__ __forceinline__ int run_jacobi(float* A, int ld, int n) {
     const int chunks = (ld + JAC_CHUNK_ROWS - 1) / JAC_CHUNK_ROWS;
     switch (chunks) {
-        case 1: return run_jacobi_chunks<1>(A, ld, n);
-        case 2: return run_jacobi_chunks<2>(A, ld, n);
-        case 3: return run_jacobi_chunks<3>(A, ld, n);
-        case 4: return run_jacobi_chunks<4>(A, ld, n);
-        case 5: return run_jacobi_chunks<5>(A, ld, n);
-        case 6: return run_jacobi_chunks<6>(A, ld, n);
-        case 7: return run_jacobi_chunks<7>(A, ld, n);
-        default: return run_jacobi_chunks<8>(A, ld, n);
+        case 1: return run_jacobi_chunks<1, TWO>(A, ld, n);
+        case 2: return run_jacobi_chunks<2, TWO>(A, ld, n);
+        case 3: return run_jacobi_chunks<3, TWO>(A, ld, n);
+        case 4: return run_jacobi_chunks<4, TWO>(A, ld, n);
+        case 5: return run_jacobi_chunks<5, TWO>(A, ld, n);
+        case 6: return run_jacobi_chunks<6, TWO>(A, ld, n);
+        case 7: return run_jacobi_chunks<7, TWO>(A, ld, n);
+        default: return run_jacobi_chunks<8, TWO>(A, ld, n);
     }
 }
 
@@ -43,7 +45,11 @@ __device__ __forceinline__ int run_jacobi(float* A, int ld, int n) {
 //   problem p in [2Lt, 2Lt + P) : centred eigen-decomposition of student extraction point p - 2Lt
 // stats layout: [(Lt + P)][n*n + n]  (Gram row-major, then column sums)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kSpectralThreads, 1)
+// 96 eight-lane groups = the 96 pairs of an n = 192 step in one pass.  Measured alternatives on B200 (cfg2, ms for the
+// 28 pooled problems): 16-lane groups / two passes 5.6, this 4.6, 384 threads with two pairs in flight per group 5.4,
+// block-2 ordering (four columns per 16-lane group, half the shared-memory round trips) 5.0.
+constexpr int kPooledThreads = 768;
+__global__ void __launch_bounds__(kPooledThreads, 1)
 pooled_eig_kernel(const float* __restrict__ stats, int n, int Lt, int P, float M_teacher, float M_student,
                   int* __restrict__ ranks, float* __restrict__ evals, float* __restrict__ evecs_km,
                   float* __restrict__ evecs_cm, int* __restrict__ sweeps_out) {
@@ -106,7 +112,7 @@ pooled_eig_kernel(const float* __restrict__ stats, int n, int Lt, int P, float M
         }
     }
     __syncthreads();
-    const int nsweeps = run_jacobi(A, ld, n);
+    const int nsweeps = run_jacobi<false>(A, ld, n);
     column_norms(A, ld, n, n, vals);        // sigma_i (Cholesky route) or lambda_i (fallback)
     __syncthreads();
     if (use_chol)
@@ -208,7 +214,7 @@ angles_kernel(int n, int Lt, int P, const int* __restrict__ ranks, const float* 
              [&](int a, int b2) { return WgR[a * k + b2]; },
              [&](int b, int b2, float v) { J[b2 * ld + b] = v; });
     __syncthreads();
-    run_jacobi(J, ld, k);
+    run_jacobi<false>(J, ld, k);
     column_norms(J, ld, k, k, vals);          // vals = sigma^2
     __syncthreads();
     rank_descending(vals, k, order);
@@ -344,7 +350,7 @@ cudaError_t launch_pooled_eig(const float* stats, int n, int Lt, int P, float Mt
     const size_t smem = pooled_smem(n);
     cudaError_t e = cudaFuncSetAttribute(pooled_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    pooled_eig_kernel<<<2 * Lt + P, kSpectralThreads, smem, st>>>(stats, n, Lt, P, Mt, Ms, ranks, evals, evecs_km, evecs_cm, sweeps);
+    pooled_eig_kernel<<<2 * Lt + P, kPooledThreads, smem, st>>>(stats, n, Lt, P, Mt, Ms, ranks, evals, evecs_km, evecs_cm, sweeps);
     return cudaGetLastError();
 }
 
