@@ -86,6 +86,14 @@ int basd_mp_rank_workspace_bytes(int64_t M, int D, size_t* bytes);
 int basd_mp_rank(const void* features, int64_t M, int D, int dtype, int64_t row_stride, int* rank_out, void* workspace,
                  void* stream);
 
+/* SURVEY.md section 8(f) rank 1 - teacher attention capture (src/models/teacher.py:27-39 recomputes the full
+ * softmax(Q K^T * scale) map per block; the loss reads only its CLS query row, relational.py:24).  Emits that row:
+ * out[b,h,:] = softmax_s(q[b,h,0,:] . k[b,h,s,:] * scale), fp32 [B,H,S].  q, k: [B,H,S,dh] with element strides
+ * (b,h,s,d), d stride 1 (views into a fused qkv tensor are fine).  The result, viewed as [B,H,1,S], is accepted
+ * by basd_forward_stats in place of the [B,H,S,S] map (attn_strides accordingly). */
+int basd_cls_attention_rows(const void* q, const void* k, int dtype, int B, int H, int S, int dh, const int64_t* q_strides,
+                            const int64_t* k_strides, float scale, float* out, void* stream);
+
 /* Test hooks (used by tests/ only). */
 int basd_selftest_gemm(int variant, const void* A, const void* B, float* C, int M, int N, int K, void* stream);
 int basd_selftest_eig(const float* G, int n, float* evals, float* evecs, int* sweeps, void* workspace, void* stream);

@@ -405,3 +405,33 @@ def test_host_stager_matches_device_path(lib, cuda_dev):
             assert rel(h["leaf_student"][l].grad.float().cpu(), ref["grad_student"][l]) < 3 * TOL_SGRAD
         assert stager.h2d_bytes_last < 1.05 * (sum(v.numel() * 2 for v in inp["teacher"].values()) + sum(v.numel() * 2 for v in inp["student"].values())
                                                + inp["logits"].numel() * 4 + 8 * w.B + w.Lt * w.B * w.H * (w.Nt + 1) * 2)
+
+
+def test_cls_attention_rows_from_q_k(lib, cuda_dev):
+    """the CLS attention row straight from q and k equals row 0 of the reference hook's
+    softmax(q k^T * scale) (src/models/teacher.py:33-37), for fp32 and bf16, contiguous and fused-qkv strided views; and
+    feeding those rows to the loss gives the same result as feeding the full maps."""
+    import vit_bias_aware_structural_distillation_b200 as pkg
+    w = dataclasses.replace(synth.CONFIGS["cfg1"], B=4)
+    B, H, S, dh = w.B, w.H, w.Nt + 1, 64
+    g = torch.Generator().manual_seed(3)
+    qkv = torch.randn(B, S, 3, H, dh, generator=g).bfloat16()          # timm layout: reshape(B, S, 3, H, dh).permute(2, 0, 3, 1, 4)
+    q, k, _ = qkv.permute(2, 0, 3, 1, 4).unbind(0)                      # strided views [B, H, S, dh]
+    full = torch.softmax((q.float() @ k.float().transpose(-2, -1)) * dh ** -0.5, dim=-1)
+    for dt in (torch.float32, torch.bfloat16):
+        for contiguous in (False, True):
+            qd, kd = q.to(dt).to(cuda_dev), k.to(dt).to(cuda_dev)
+            if contiguous:
+                qd, kd = qd.contiguous(), kd.contiguous()
+            rows = pkg.cls_attention_rows(qd, kd)
+            assert rows.shape == (B, H, 1, S)
+            assert (rows.cpu() - full[:, :, 0:1, :]).abs().max() < 2e-6
+    inp = synth.make_inputs(w)
+    m = build_module(w, cuda_dev)
+    S_ = {l: v.to(cuda_dev) for l, v in inp["student"].items()}
+    T_ = {j: v.to(cuda_dev) for j, v in inp["teacher"].items()}
+    maps = {j: full.to(cuda_dev) for j in T_}
+    rows_only = {j: pkg.cls_attention_rows(q.to(cuda_dev), k.to(cuda_dev)) for j in T_}
+    a = m.geo_loss(S_, T_, maps)
+    b = m.geo_loss(S_, T_, rows_only)
+    assert abs(a.item() - b.item()) <= 1e-5 * abs(a.item())

@@ -36,7 +36,7 @@ EXPORTS = [
     "basd_workspace_bytes", "basd_forward_stats", "basd_forward_solve", "basd_backward_dots", "basd_backward_finish",
     "basd_view", "basd_mp_rank_workspace_bytes", "basd_mp_rank", "basd_selftest_gemm", "basd_selftest_eig",
     "basd_last_error", "basd_version", "basd_timing_enable", "basd_timing_reset", "basd_launch_count", "basd_timing_slots",
-    "basd_timing_name", "basd_timing_read", "basd_polar_steps",
+    "basd_timing_name", "basd_timing_read", "basd_polar_steps", "basd_cls_attention_rows",
 ]
 
 _lib = None
@@ -68,6 +68,8 @@ def load():
     lib.basd_mp_rank.argtypes = [vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int64, vp, vp, vp]
     lib.basd_selftest_gemm.argtypes = [ctypes.c_int, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]
     lib.basd_selftest_eig.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp]
+    lib.basd_cls_attention_rows.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                            ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64), ctypes.c_float, vp, vp]
     lib.basd_launch_count.restype = ctypes.c_longlong
     lib.basd_timing_name.restype = ctypes.c_char_p
     lib.basd_timing_name.argtypes = [ctypes.c_int]

@@ -458,6 +458,18 @@ extern "C" int basd_mp_rank(const void* features, int64_t M, int D, int dtype, i
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------- CLS attention rows
+extern "C" int basd_cls_attention_rows(const void* q, const void* k, int dtype, int B, int H, int S, int dh, const int64_t* q_strides,
+                                       const int64_t* k_strides, float scale, float* out, void* stream) {
+    if (!q || !k || !out || !q_strides || !k_strides) return fail("null argument");
+    if (B < 1 || H < 1 || S < 2 || dh < 1) return fail("invalid attention shape");
+    if (q_strides[3] != 1 || k_strides[3] != 1) return fail("basd_cls_attention_rows: the head-dim stride of q and k must be 1");
+    const long long qs[2] = {q_strides[0], q_strides[1]};
+    const long long ks[3] = {k_strides[0], k_strides[1], k_strides[2]};
+    CK(launch_cls_attention_rows(q, k, dtype == BASD_DTYPE_BF16, B, H, S, dh, qs, ks, scale, out, reinterpret_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------- test hooks
 extern "C" int basd_selftest_gemm(int variant, const void* A, const void* B, float* C, int M, int N, int K, void* stream) {
     CK(gemm_selftest(variant, reinterpret_cast<const __nv_bfloat16*>(A), reinterpret_cast<const __nv_bfloat16*>(B), C, M, N, K,

@@ -44,6 +44,9 @@ cudaError_t launch_mix_teacher(const PtrTable& teacher, const float* w, int Lt, 
 cudaError_t launch_wgrad_dots(const PtrTable& teacher, const __nv_bfloat16* Dtm, const float* gwt, const float* rows,
                               int Lt, int P, int B, int Nt, int Ns, int Dt, float* gw /*[P][Lt], pre-zeroed*/,
                               cudaStream_t st);
+cudaError_t launch_cls_attention_rows(const void* q, const void* k, int is_bf16, int B, int H, int S, int dh,
+                                      const long long* q_strides /*[b,h]*/, const long long* k_strides /*[b,h,s]*/, float scale,
+                                      float* out /*[B,H,S]*/, cudaStream_t st);
 cudaError_t launch_loss_reduce(const float* loss_b, int P, int B, float* geo_i, float* geo, cudaStream_t st);
 
 // ---- tcgen05 GEMM launchers (gemm_ops.cu)

@@ -78,6 +78,54 @@ cudaError_t launch_importance_rows(const PtrTable& attn, int attn_is_bf16, int L
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------- CLS attention rows
+// the reference's teacher hook (src/models/teacher.py:27-39) recomputes the full
+// softmax(Q K^T / sqrt(d)) [B,H,N+1,N+1] per block only for the loss to read its CLS query row (relational.py:24).
+// This kernel emits that row directly from Q and K: out[b,h,0,:] = softmax_s(q[b,h,0,:] . k[b,h,s,:] * scale).
+// One warp per (b, h); a lane owns keys s = lane, lane + 32, ...; fp32 accumulation; d stride must be 1.
+template <typename T>
+__global__ void __launch_bounds__(128)
+cls_attention_rows_kernel(const T* __restrict__ q, const T* __restrict__ k, int B, int H, int S, int dh, long long qb, long long qh,
+                          long long kb, long long kh, long long ks, float scale, float* __restrict__ out) {
+    extern __shared__ float qs[];                       // [warps][dh]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bh = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (bh >= B * H) return;
+    const int b = bh / H, h = bh % H;
+    float* q0 = qs + warp * dh;
+    const T* qp = q + b * qb + h * qh;                  // query 0 = CLS
+    for (int d = lane; d < dh; d += 32) q0[d] = static_cast<float>(qp[d]) * scale;
+    __syncwarp();
+    const T* kp = k + b * kb + h * kh;
+    float* o = out + static_cast<size_t>(bh) * S;
+    float mx = -3.0e38f;
+    for (int s0 = lane; s0 < S; s0 += 32) {
+        const T* kr = kp + s0 * ks;
+        float acc = 0.f;
+        for (int d = 0; d < dh; ++d) acc = fmaf(q0[d], static_cast<float>(kr[d]), acc);
+        o[s0] = acc;                                    // scores parked in the output row
+        mx = fmaxf(mx, acc);
+    }
+    for (int of = 16; of > 0; of >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, of));
+    float sum = 0.f;
+    for (int s0 = lane; s0 < S; s0 += 32) { const float e = __expf(o[s0] - mx); o[s0] = e; sum += e; }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    for (int s0 = lane; s0 < S; s0 += 32) o[s0] *= inv;
+}
+cudaError_t launch_cls_attention_rows(const void* q, const void* k, int is_bf16, int B, int H, int S, int dh, const long long* qst,
+                                      const long long* kst, float scale, float* out, cudaStream_t st) {
+    const int warps = 4, blocks = (B * H + warps - 1) / warps;
+    const size_t smem = sizeof(float) * warps * dh;
+    if (is_bf16)
+        cls_attention_rows_kernel<__nv_bfloat16><<<blocks, warps * 32, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
+                                                                                  B, H, S, dh, qst[0], qst[1], kst[0], kst[1], kst[2], scale, out);
+    else
+        cls_attention_rows_kernel<float><<<blocks, warps * 32, smem, st>>>(reinterpret_cast<const float*>(q), reinterpret_cast<const float*>(k), B, H, S, dh,
+                                                                           qst[0], qst[1], kst[0], kst[1], kst[2], scale, out);
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------- small helpers
 __global__ void split_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, size_t n) {
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {

@@ -285,6 +285,31 @@ class HostStager:
         return self.module(logits, handle["targets"], student, handle["teacher"], handle["attn"])
 
 
+# --------------------------------------------------------------------------------------------- teacher attention capture
+def cls_attention_rows(q: torch.Tensor, k: torch.Tensor, scale: float | None = None) -> torch.Tensor:
+    """CLS query row of softmax(q k^T * scale), shape [B, H, 1, S] fp32, straight from q and k [B, H, S, dh] (strided views
+    of a fused qkv tensor are fine).  What the reference's attention hook (src/models/teacher.py:27-39) materialises as a
+    full [B, H, S, S] map per block only for relational.py:24 to read row 0; pass the result as `all_teacher_attns[j]`."""
+    lib = _lib.load()
+    if q.device.type != "cuda" or k.device.type != "cuda":
+        raise _lib.BasdError("cls_attention_rows: CUDA tensors required (no CPU fallback)")
+    if q.dtype != k.dtype or q.dtype not in (torch.float32, torch.bfloat16):
+        q, k = q.float(), k.float()
+    if q.stride(3) != 1:
+        q = q.contiguous()
+    if k.stride(3) != 1:
+        k = k.contiguous()
+    B, H, S, dh = q.shape
+    if scale is None:
+        scale = dh ** -0.5
+    out = torch.empty(B, H, 1, S, dtype=torch.float32, device=q.device)
+    qs = (ctypes.c_int64 * 4)(*q.stride())
+    ks = (ctypes.c_int64 * 4)(*k.stride())
+    _lib.check(lib.basd_cls_attention_rows(q.data_ptr(), k.data_ptr(), _dtype_code(q), B, H, S, dh, qs, ks, float(scale), out.data_ptr(),
+                                           _stream_ptr()), "basd_cls_attention_rows")
+    return out
+
+
 # --------------------------------------------------------------------------------------------- reference API
 def marchenko_pastur_rank(features: torch.Tensor) -> int:
     """layer_selector.py:8-20 on the GPU (tcgen05 Gram + shared-memory Jacobi).  features: [M, D], D <= 224."""
