@@ -244,6 +244,10 @@ cudaError_t polar_gemm(bool b_mn, const SplitMat& A, const SplitMat& B, int batc
             if (make_map_tiled(&maps.o[3], a.aux_lo, m_rows, ocb, batches, a.out_stride, 32)) return cudaErrorInvalidValue;
         }
     }
+    if (a.epi == PG_EPI_THETA) {                       // row-major [m_rows][ld_out] outputs, 32 x 64 boxes, columns clipped at n_cols
+        if (make_map(&maps.o[0], a.out_hi, n_cols, m_rows, batches, a.ld_out, a.out_stride, 32)) return cudaErrorInvalidValue;
+        if (make_map(&maps.o[1], a.out_lo, n_cols, m_rows, batches, a.ld_out, a.out_stride, 32)) return cudaErrorInvalidValue;
+    }
     if (a.a_alias_b && (b_mn || A.hi != B.hi || m_rows != n_cols)) {
         snprintf(g_gemm_err, sizeof g_gemm_err, "polar_gemm: a_alias_b needs the same K-major matrix on both sides");
         return cudaErrorInvalidValue;

@@ -262,15 +262,15 @@ cudaError_t launch_polar_procrustes(const PolarArgs& g, cudaStream_t st, int* la
         const bool first = k == 0;
         const float* norm = first ? fro2_dense : nullptr;
         PolarGemmArgs a;
-        // G1: T = W K_t                      (step 0: ||C||_F^2 = <T, W_0>)
+        // G1: T = W K_t
         memset(&a, 0, sizeof a);
         a.epi = PG_EPI_SPLIT; a.out_hi = g.T.hi; a.out_lo = g.T.lo; a.out_stride = g.T.batch_stride; a.scale_c = 1.f;
-        if (first) { a.trace = fro2_dense; a.trace_mode = 2; a.aux_hi = Wc.hi; a.aux_lo = Wc.lo; }
         a.reverse = (dir++) & 1;
         PCK(polar_gemm(false, Wc, g.Kt, nprob, a, st));
-        // G2: A = T W^T
+        // G2: A = T W^T                    (step 0: trace(A) = ||C||_F^2, read by the epilogues of G3 / G4 of that step)
         memset(&a, 0, sizeof a);
         a.epi = PG_EPI_SPLIT; a.out_hi = g.A.hi; a.out_lo = g.A.lo; a.out_stride = g.A.batch_stride; a.scale_c = 1.f;
+        if (first) { a.trace = fro2_dense; a.trace_mode = 1; }
         a.reverse = (dir++) & 1;
         PCK(polar_gemm(false, g.T, Wc, nprob, a, st));
         // G3: Bm = a I + b (rA) + c (rA)^2   (A is both operands: the A tile aliases the B tile; the b A term is added from a

@@ -25,7 +25,7 @@ constexpr int PG_BK = 64;
 enum PolarEpi : int {
     PG_EPI_SPLIT = 0,       // out = split(scale * acc + aux_scale * aux + diag_add * I); optional trace
     PG_EPI_F32 = 2,         // out_f32 = acc
-    PG_EPI_THETA = 3,       // out = split(2 (diag(a) - q acc q^T - a a^T))   (teacher side)
+    PG_EPI_THETA = 3,       // out = split(2 (diag(a) - q acc q^T - a a^T)), ROW-MAJOR [m_rows][ld_out]   (teacher side)
 };
 
 struct PolarGemmMaps {
@@ -151,7 +151,7 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
         fence_mbar_init();
         tma_prefetch_desc(&maps.a[0]); tma_prefetch_desc(&maps.a[1]);
         tma_prefetch_desc(&maps.b[0]); tma_prefetch_desc(&maps.b[1]);
-        if (args.epi == PG_EPI_SPLIT) { tma_prefetch_desc(&maps.o[0]); tma_prefetch_desc(&maps.o[1]); }
+        if (args.epi == PG_EPI_SPLIT || args.epi == PG_EPI_THETA) { tma_prefetch_desc(&maps.o[0]); tma_prefetch_desc(&maps.o[1]); }
     }
     uint32_t tmem_cols = 32;
     while (tmem_cols < static_cast<uint32_t>(2 * args.bn_mma)) tmem_cols <<= 1;
@@ -265,7 +265,9 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
                 q_row = sqrtf(a_row);
             }
             float tr_part = 0.f;
-            if (args.epi == PG_EPI_SPLIT) {
+            if (args.epi == PG_EPI_SPLIT || args.epi == PG_EPI_THETA) {
+                const bool theta = args.epi == PG_EPI_THETA;
+                const float* av = theta ? args.vec_a + static_cast<long long>(z) * args.m_rows : nullptr;
                 // convert into the warp's swizzled staging tile; every 64-column block leaves as one TMA store per half
                 uint8_t* stg_hi = staging + (warp - 2) * 8192;
                 uint8_t* stg_lo = stg_hi + 4096;
@@ -290,7 +292,18 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
                                         tr_part = fmaf(v[i], __bfloat162float(args.aux_hi[off + i]) + __bfloat162float(args.aux_lo[off + i]), tr_part);
                                 }
                             }
-                            if (use_aux) {
+                            if (theta) {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) {
+                                    float t = 0.f;
+                                    if (c + i < args.n_cols) {
+                                        const float ac = av[c + i];
+                                        t = -q_row * v[i] * sqrtf(ac) - a_row * ac;
+                                        if (c + i == row) t += a_row;
+                                    }
+                                    v[i] = 2.f * t;
+                                }
+                            } else if (use_aux) {
                                 float x[16];
                                 pg_read_split16(aux_hi_s, aux_lo_s, lane, jc * 2, x);
 #pragma unroll
@@ -312,8 +325,13 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
                             tma_load_4d(aux_hi_s, &maps.o[2], &aux_bar[warp - 2], 0, mt * 128 + q * 32, cbk + 1, z);
                             tma_load_4d(aux_lo_s, &maps.o[3], &aux_bar[warp - 2], 0, mt * 128 + q * 32, cbk + 1, z);
                         }
-                        tma_store_4d(&maps.o[0], stg_hi, 0, mt * 128 + q * 32, cbk, z);
-                        tma_store_4d(&maps.o[1], stg_lo, 0, mt * 128 + q * 32, cbk, z);
+                        if (theta) {                                            // row-major output, columns past n_cols are clipped
+                            tma_store_3d(&maps.o[0], stg_hi, cbk * 64, mt * 128 + q * 32, z);
+                            tma_store_3d(&maps.o[1], stg_lo, cbk * 64, mt * 128 + q * 32, z);
+                        } else {
+                            tma_store_4d(&maps.o[0], stg_hi, 0, mt * 128 + q * 32, cbk, z);
+                            tma_store_4d(&maps.o[1], stg_lo, 0, mt * 128 + q * 32, cbk, z);
+                        }
                         tma_store_commit();
                         tma_store_wait_read();
                     }
@@ -334,21 +352,6 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
                         } else {
                             for (int i = 0; i < nv; ++i) p[i] = v[i];
                         }
-                    } else {                                               // PG_EPI_THETA, row-major [m_rows][ld_out]
-                        const long long off = z * args.out_stride + static_cast<long long>(row) * args.ld_out + c;
-                        const float* av = args.vec_a + static_cast<long long>(z) * args.m_rows;
-                        float x[16];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            x[i] = 0.f;
-                            if (i < nv) {
-                                const float ac = av[c + i];
-                                float t = -q_row * v[i] * sqrtf(ac) - a_row * ac;
-                                if (c + i == row) t += a_row;
-                                x[i] = 2.f * t;
-                            }
-                        }
-                        pg_store_split16(args.out_hi + off, args.out_lo + off, x, nv);
                     }
                 }
             }
