@@ -195,11 +195,11 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (weak scaling)")
-    ap.add_argument("--cpu-sample-batch", type=int, default=16)
+    ap.add_argument("--cpu-sample-batch", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -378,11 +378,11 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
         stepfn, kind, desc = cpu_reference_step_fn(w, args.cpu_sample_batch)
-        sec = time_cpu(stepfn, 2, 1)
+        sec = time_cpu(stepfn, 3, 1)
         cpu_baseline = {"value": args.cpu_sample_batch / sec, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind, "sample": desc}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 tokens / fp32 accumulate + fp32 spectral",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
             "config": {"workload": w.name, "per_gpu_batch": w.B, "global_batch": w.B * world, "Ns": w.Ns, "Nt": w.Nt, "Ds": w.Ds, "Dt": w.Dt,
                        "Lt": w.Lt, "H": w.H, "P": w.P, "parallelism": f"dp{world} (batch-sharded, pooled statistics all-reduced)",

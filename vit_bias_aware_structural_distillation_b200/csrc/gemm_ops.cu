@@ -254,8 +254,7 @@ cudaError_t polar_gemm(bool b_mn, const SplitMat& A, const SplitMat& B, int batc
     }
     const int b_bytes = b_mn ? a.b_groups * 8192 : a.bn_mma * 128;
     const int stage_bytes = (a.a_alias_b ? 0 : 2 * 16384) + 2 * b_bytes;
-    const int kTail = 1024 /*alignment*/ + 1024 /*barriers*/ + 4 * 8192 /*epilogue staging*/ + (a.aux_mode ? 4 * 8192 : 0) /*aux tiles*/
-                      + (a.a_alias_b ? 16384 : 0) /*aliased A tile of the last rows reads past its B tile*/;
+    const int kTail = 1024 /*alignment*/ + 1024 /*barriers*/ + 4 * 8192 /*epilogue staging*/ + (a.aux_mode ? 4 * 8192 * ((a.bn_mma + 63) / 64) : 0) /*aux tiles: every column block of an item*/;   // (the aliased A tile of the last rows reads up to 8 KB past its B tile: into the barrier / staging area, rows never used)
     int stages = (232448 - kTail) / stage_bytes;
     if (stages > 4) stages = 4;
     if (stages < 1) {
@@ -264,13 +263,19 @@ cudaError_t polar_gemm(bool b_mn, const SplitMat& A, const SplitMat& B, int batc
     }
     a.stages = stages;
     const int smem = stages * stage_bytes + kTail;
-    auto kern = b_mn ? polar_gemm_kernel<true> : polar_gemm_kernel<false>;
-    static bool configured[2] = {false, false};
+    // epilogue kind -> kernel instantiation (polar_gemm.cuh)
+    const int kind = a.epi == PG_EPI_F32 ? 3 : a.epi == PG_EPI_THETA ? 2 : a.aux_mode ? 1 : 0;
+    using Kern = void (*)(const PolarGemmMaps, const PolarGemmArgs);
+    static const Kern kerns[2][4] = {
+        {polar_gemm_kernel<false, 0>, polar_gemm_kernel<false, 1>, polar_gemm_kernel<false, 2>, polar_gemm_kernel<false, 3>},
+        {polar_gemm_kernel<true, 0>, polar_gemm_kernel<true, 1>, polar_gemm_kernel<true, 2>, polar_gemm_kernel<true, 3>}};
+    const Kern kern = kerns[b_mn][kind];
+    static bool configured[2][4] = {{false, false, false, false}, {false, false, false, false}};
     static int sm_count = 0;
-    if (!configured[b_mn]) {
+    if (!configured[b_mn][kind]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         if (e != cudaSuccess) return e;
-        configured[b_mn] = true;
+        configured[b_mn][kind] = true;
     }
     if (!sm_count) {
         int dev = 0;

@@ -13,6 +13,8 @@
 // pushing the top singular value into the divergent region.
 // All products are one-CTA-per-problem tcgen05 GEMMs on split-bf16 operands (polar_gemm.cuh).
 // Requires rank(C) = D_s, i.e. D_s <= N - 1 and a teacher token Gram of rank >= D_s.
+#include <cstdlib>
+
 #include "cta_linalg.cuh"
 #include "polar_gemm.cuh"
 #include "spectral.h"
@@ -22,6 +24,7 @@ namespace basd {
 namespace {
 
 constexpr int kPolarSteps = 10;
+constexpr int kPolarChunk = 0;            // problems per launch of the product chain (0 = all); BASD_POLAR_CHUNK overrides
 // minimax odd quintics on [l_k, 1.03] (l_0 = 3e-5), each rescaled to a maximum of 1: tools/ns_schedule.py 3e-5 10 1.03
 // l_k: 3.0e-5 1.0e-4 4.2e-4 1.7e-3 7.1e-3 2.9e-2 0.118 0.42 0.906 0.99967 -> 0.999996
 const float kPolarCoef[kPolarSteps][3] = {
@@ -233,6 +236,9 @@ polar_finish_kernel(PolarArgs g) {
 
 int polar_steps() { return kPolarSteps; }
 
+__device__ long long g_polar_dbg[4][16 * 8];
+long long* polar_dbg_ptr(int which) { long long* p = nullptr; cudaGetSymbolAddress(reinterpret_cast<void**>(&p), g_polar_dbg); return p + which * 128; }
+
 #define PCK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return _e; } while (0)
 
 cudaError_t launch_polar_procrustes(const PolarArgs& g, cudaStream_t st, int* launches) {
@@ -251,63 +257,85 @@ cudaError_t launch_polar_procrustes(const PolarArgs& g, cudaStream_t st, int* la
     float* fro2_dense = g.fro2;                // ||C||_F^2 per problem, accumulated by the first A = T W^T
     PCK(cudaMemsetAsync(fro2_dense, 0, sizeof(float) * nprob, st));
 
-    // Step 0 runs on the unnormalised W_0 = s_w^T; r = 1 / ||C||_F^2 (trace of W_0 K_t W_0^T, accumulated by the first
-    // product) enters the later epilogues of that step as a per-problem scalar.
-    SplitMat Wc = g.W, Wn = g.W2;
-    int dir = 0;                               // alternate the problem order launch by launch (L2 reuse of the previous output)
-    TimingScope* gemm_scope = new TimingScope(kSlotPolarGemm, st, 4 * kPolarSteps + 2);
-    struct Del { TimingScope*& p; ~Del() { delete p; } } gemm_del{gemm_scope};
-    for (int k = 0; k < kPolarSteps; ++k) {
-        const float ca = kPolarCoef[k][0], cb = kPolarCoef[k][1], cc = kPolarCoef[k][2];
-        const bool first = k == 0;
-        const float* norm = first ? fro2_dense : nullptr;
-        PolarGemmArgs a;
-        // G1: T = W K_t
-        memset(&a, 0, sizeof a);
-        a.epi = PG_EPI_SPLIT; a.out_hi = g.T.hi; a.out_lo = g.T.lo; a.out_stride = g.T.batch_stride; a.scale_c = 1.f;
-        a.reverse = (dir++) & 1;
-        PCK(polar_gemm(false, Wc, g.Kt, nprob, a, st));
-        // G2: A = T W^T                    (step 0: trace(A) = ||C||_F^2, read by the epilogues of G3 / G4 of that step)
-        memset(&a, 0, sizeof a);
-        a.epi = PG_EPI_SPLIT; a.out_hi = g.A.hi; a.out_lo = g.A.lo; a.out_stride = g.A.batch_stride; a.scale_c = 1.f;
-        if (first) { a.trace = fro2_dense; a.trace_mode = 1; }
-        a.reverse = (dir++) & 1;
-        PCK(polar_gemm(false, g.T, Wc, nprob, a, st));
-        // G3: Bm = a I + b (rA) + c (rA)^2   (A is both operands: the A tile aliases the B tile; the b A term is added from a
-        //     TMA-loaded copy of the output-shaped tile of A in the epilogue)
-        memset(&a, 0, sizeof a);
-        a.epi = PG_EPI_SPLIT; a.out_hi = g.Bm.hi; a.out_lo = g.Bm.lo; a.out_stride = g.Bm.batch_stride;
-        a.a_alias_b = 1; a.aux_mode = 1; a.aux_hi = g.A.hi; a.aux_lo = g.A.lo;
-        a.aux_c = cb; a.aux_p = first ? 1.f : 0.f; a.scale_c = cc; a.scale_p = first ? 2.f : 0.f; a.diag_add = ca; a.norm2 = norm;
-        a.reverse = (dir++) & 1;
-        PCK(polar_gemm(false, g.A, g.A, nprob, a, st));
-        // G4: W_next = sqrt(r) Bm W          (W enters as the MN-major B operand; ping-pong buffers)
-        memset(&a, 0, sizeof a);
-        a.epi = PG_EPI_SPLIT; a.out_hi = Wn.hi; a.out_lo = Wn.lo; a.out_stride = Wn.batch_stride;
-        a.scale_c = 1.f; a.scale_p = first ? 0.5f : 0.f; a.norm2 = norm;
-        a.reverse = (dir++) & 1;
-        PCK(polar_gemm(true, g.Bm, Wc, nprob, a, st));
-        const SplitMat tmp = Wc; Wc = Wn; Wn = tmp;
-        count += 4;
+    // The chain of products is sequentially dependent per problem but every launch batches many problems.  Problems are
+    // walked in chunks small enough for a chunk's matrices (~0.8 MB live per problem) to stay in the 126 MB L2 from one
+    // launch to the next; one chunk = one full Newton-Schulz run.  chunk = 0: all problems per launch (HBM streaming).
+    static int chunk_cfg = -1;
+    if (chunk_cfg < 0) {
+        const char* e = getenv("BASD_POLAR_CHUNK");
+        chunk_cfg = e ? atoi(e) : kPolarChunk;
     }
-    {
+    const int chunk = (chunk_cfg <= 0 || chunk_cfg > nprob) ? nprob : chunk_cfg;
+    const int n_chunks = (nprob + chunk - 1) / chunk;
+    auto at = [](const SplitMat& m, int z0) { SplitMat r = m; r.hi += z0 * m.batch_stride; r.lo += z0 * m.batch_stride; return r; };
+    TimingScope* gemm_scope = new TimingScope(kSlotPolarGemm, st, n_chunks * (4 * kPolarSteps + 2));
+    struct Del { TimingScope*& p; ~Del() { delete p; } } gemm_del{gemm_scope};
+    for (int z0 = 0; z0 < nprob; z0 += chunk) {
+        const int nz = nprob - z0 < chunk ? nprob - z0 : chunk;
+        // Step 0 runs on the unnormalised W_0 = s_w^T; r = 1 / ||C||_F^2 (trace of W_0 K_t W_0^T, accumulated by the first
+        // A product) enters the later epilogues of that step as a per-problem scalar.
+        SplitMat Wc = at(g.W, z0), Wn = at(g.W2, z0);
+        const SplitMat T = at(g.T, z0), A = at(g.A, z0), Bm = at(g.Bm, z0), Kt = at(g.Kt, z0), SW = at(g.SW, z0);
+        float* fro2 = fro2_dense + z0;
+        int dir = 0;                           // alternate the problem order launch by launch (L2 reuse of the previous output)
+        for (int k = 0; k < kPolarSteps; ++k) {
+            const float ca = kPolarCoef[k][0], cb = kPolarCoef[k][1], cc = kPolarCoef[k][2];
+            const bool first = k == 0;
+            const float* norm = first ? fro2 : nullptr;
+            PolarGemmArgs a;
+            // G1: T = W K_t
+            memset(&a, 0, sizeof a);
+            a.epi = PG_EPI_SPLIT; a.out_hi = T.hi; a.out_lo = T.lo; a.out_stride = T.batch_stride; a.scale_c = 1.f;
+            if (k == 3 && z0 == 0 && getenv("BASD_POLAR_DBG")) a.dbg_clock = polar_dbg_ptr(0);
+            a.reverse = (dir++) & 1;
+            PCK(polar_gemm(false, Wc, Kt, nz, a, st));
+            // G2: A = T W^T                (step 0: trace(A) = ||C||_F^2, read by the epilogues of G3 / G4 of that step)
+            memset(&a, 0, sizeof a);
+            a.epi = PG_EPI_SPLIT; a.out_hi = A.hi; a.out_lo = A.lo; a.out_stride = A.batch_stride; a.scale_c = 1.f;
+            if (first) { a.trace = fro2; a.trace_mode = 1; }
+            if (k == 3 && z0 == 0 && getenv("BASD_POLAR_DBG")) a.dbg_clock = polar_dbg_ptr(1);
+            a.reverse = (dir++) & 1;
+            PCK(polar_gemm(false, T, Wc, nz, a, st));
+            // G3: Bm = a I + b (rA) + c (rA)^2   (A is both operands: the A tile aliases the B tile; the b A term is added from
+            //     a TMA-loaded copy of the output-shaped tile of A in the epilogue)
+            memset(&a, 0, sizeof a);
+            a.epi = PG_EPI_SPLIT; a.out_hi = Bm.hi; a.out_lo = Bm.lo; a.out_stride = Bm.batch_stride;
+            a.a_alias_b = 1; a.aux_mode = 1; a.aux_hi = A.hi; a.aux_lo = A.lo;
+            a.aux_c = cb; a.aux_p = first ? 1.f : 0.f; a.scale_c = cc; a.scale_p = first ? 2.f : 0.f; a.diag_add = ca; a.norm2 = norm;
+            if (k == 3 && z0 == 0 && getenv("BASD_POLAR_DBG")) a.dbg_clock = polar_dbg_ptr(2);
+            a.reverse = (dir++) & 1;
+            PCK(polar_gemm(false, A, A, nz, a, st));
+            // G4: W_next = sqrt(r) Bm W      (W enters as the MN-major B operand; ping-pong buffers)
+            memset(&a, 0, sizeof a);
+            a.epi = PG_EPI_SPLIT; a.out_hi = Wn.hi; a.out_lo = Wn.lo; a.out_stride = Wn.batch_stride;
+            a.scale_c = 1.f; a.scale_p = first ? 0.5f : 0.f; a.norm2 = norm;
+            if (k == 3 && z0 == 0 && getenv("BASD_POLAR_DBG")) a.dbg_clock = polar_dbg_ptr(3);
+            a.reverse = (dir++) & 1;
+            PCK(polar_gemm(true, Bm, Wc, nz, a, st));
+            const SplitMat tmp = Wc; Wc = Wn; Wn = tmp;
+            count += 4;
+        }
         PolarGemmArgs a;
         // Gsw = K_t W^T  [N][Ds]
         memset(&a, 0, sizeof a);
-        a.epi = PG_EPI_F32; a.out_f32 = g.Gsw; a.out_f32_stride = static_cast<long long>(N) * D; a.ld_f32 = D;
+        a.epi = PG_EPI_F32; a.out_f32 = g.Gsw + static_cast<size_t>(z0) * N * D; a.out_f32_stride = static_cast<long long>(N) * D; a.ld_f32 = D;
         a.reverse = (dir++) & 1;
-        PCK(polar_gemm(false, g.Kt, Wc, nprob, a, st));
+        PCK(polar_gemm(false, Kt, Wc, nz, a, st));
         // Psi = s_w W  [N][N]  -> Theta' = 2 (diag(a) - q Psi q - a a^T), stored as a split pair
         memset(&a, 0, sizeof a);
-        a.epi = PG_EPI_THETA; a.out_hi = g.theta; a.out_lo = g.theta_lo; a.out_stride = static_cast<long long>(N) * g.NsPad; a.ld_out = g.NsPad;
-        a.vec_a = g.a;
+        a.epi = PG_EPI_THETA; a.out_hi = g.theta + static_cast<size_t>(z0) * N * g.NsPad; a.out_lo = g.theta_lo + static_cast<size_t>(z0) * N * g.NsPad;
+        a.out_stride = static_cast<long long>(N) * g.NsPad; a.ld_out = g.NsPad;
+        a.vec_a = g.a + static_cast<size_t>(z0) * N;
         a.reverse = (dir++) & 1;
-        PCK(polar_gemm(true, g.SW, Wc, nprob, a, st));
+        PCK(polar_gemm(true, SW, Wc, nz, a, st));
+        count += 2;
+    }
+    {
         delete gemm_scope; gemm_scope = nullptr;
         TimingScope tf(kSlotPolarFinish, st, 1);
         polar_finish_kernel<<<nprob, 256, (2 * N + 64) * sizeof(float), st>>>(g);
         PCK(cudaGetLastError());
-        count += 3;
+        count += 1;
     }
     if (launches) *launches = count;
     return cudaSuccess;

@@ -13,7 +13,8 @@
 // epilogue of item i.  Warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue (one TMEM lane quadrant each).
 // Epilogues only store (no global reads on the critical path) except the one-off Frobenius trace of step 0; the split
 // outputs go through a 128B-swizzled shared-memory staging tile per warp and leave as TMA tensor stores (per-lane
-// 16-byte stores of one row each saturated the L1TEX->XBAR request path: 32 requests per instruction).
+// 16-byte stores of one row each saturated the L1TEX->XBAR request path: 32 requests per instruction; coalesced
+// 512-byte-per-instruction stores out of the same staging tile measured the same as the TMA stores).
 #pragma once
 #include "ptx.cuh"
 
@@ -51,9 +52,11 @@ struct PolarGemmArgs {
     // auxiliary split matrix laid out like the output, added in the epilogue: out += aux_c * r^aux_p * aux (TMA-loaded)
     int aux_mode; float aux_c, aux_p;
     int a_alias_b;                   // A == B (K-major, same matrix): the A tile is read out of the B tile, no A loads
+    long long* dbg_clock;            // development aid: CTA 0 records clock64() per phase of its first items ([item][8])
     int reverse, n_batches;          // reverse: walk the problems last-to-first (what the previous launch wrote last is still in L2)
-    // trace[z] += sum(diag(acc)) (mode 1) or sum(acc .* aux) (mode 2; aux = split pair laid out like the primary output)
-    float* trace; int trace_mode; const __nv_bfloat16* aux_hi; const __nv_bfloat16* aux_lo;
+    float* trace;                    // if non-null: trace[z] += sum(diag(acc))
+    int trace_mode;                  // (unused)
+    const __nv_bfloat16* aux_hi; const __nv_bfloat16* aux_lo;
     float* out_f32; long long out_f32_stride; int ld_f32;
     const float* vec_a;              // THETA: importance a [z][m_rows]
 };
@@ -83,20 +86,33 @@ __device__ __forceinline__ void pg_store_split16(__nv_bfloat16* ph, __nv_bfloat1
 
 // 16 fp32 values -> bf16 hi / lo halves of staging row `row` (32 rows x 128 B, SWIZZLE_128B: 16-byte chunk j of row r
 // lives at chunk position j ^ (r & 7)); chunk0 = first of the two 16-byte chunks the 16 columns occupy.
-__device__ __forceinline__ void pg_stage_split16(uint8_t* stg_hi, uint8_t* stg_lo, int row, int chunk0, const float* v) {
+// Packed conversions (two values per cvt) and st.shared with 32-bit addresses: the epilogue runs one warp per scheduler,
+// so its cost is its instruction count.
+__device__ __forceinline__ void st_shared_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void pg_stage_split16(uint32_t stg_hi, uint32_t stg_lo, int row, int chunk0, const float* v) {
     uint32_t hw[8], lw[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const __nv_bfloat16 h0 = __float2bfloat16(v[2 * i]), h1 = __float2bfloat16(v[2 * i + 1]);
-        __nv_bfloat162 hv; hv.x = h0; hv.y = h1;
-        hw[i] = *reinterpret_cast<uint32_t*>(&hv);
-        lw[i] = pack_bf16x2(v[2 * i] - __bfloat162float(h0), v[2 * i + 1] - __bfloat162float(h1));
+        const __nv_bfloat162 hv = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        const float2 hf = __bfloat1622float2(hv);
+        const __nv_bfloat162 lv = __floats2bfloat162_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+        hw[i] = *reinterpret_cast<const uint32_t*>(&hv);
+        lw[i] = *reinterpret_cast<const uint32_t*>(&lv);
     }
-    const int p0 = (chunk0 ^ (row & 7)) * 16, p1 = ((chunk0 + 1) ^ (row & 7)) * 16;
-    *reinterpret_cast<uint4*>(stg_hi + row * 128 + p0) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-    *reinterpret_cast<uint4*>(stg_hi + row * 128 + p1) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
-    *reinterpret_cast<uint4*>(stg_lo + row * 128 + p0) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-    *reinterpret_cast<uint4*>(stg_lo + row * 128 + p1) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+    const uint32_t base = row * 128, p0 = base + ((chunk0 ^ (row & 7)) << 4), p1 = base + (((chunk0 + 1) ^ (row & 7)) << 4);
+    st_shared_v4(stg_hi + p0, hw[0], hw[1], hw[2], hw[3]);
+    st_shared_v4(stg_hi + p1, hw[4], hw[5], hw[6], hw[7]);
+    st_shared_v4(stg_lo + p0, lw[0], lw[1], lw[2], lw[3]);
+    st_shared_v4(stg_lo + p1, lw[4], lw[5], lw[6], lw[7]);
+}
+__device__ __forceinline__ void pg_stage_zero16(uint32_t stg_hi, uint32_t stg_lo, int row, int chunk0) {
+    const uint32_t base = row * 128, p0 = base + ((chunk0 ^ (row & 7)) << 4), p1 = base + (((chunk0 + 1) ^ (row & 7)) << 4);
+    st_shared_v4(stg_hi + p0, 0u, 0u, 0u, 0u);
+    st_shared_v4(stg_hi + p1, 0u, 0u, 0u, 0u);
+    st_shared_v4(stg_lo + p0, 0u, 0u, 0u, 0u);
+    st_shared_v4(stg_lo + p1, 0u, 0u, 0u, 0u);
 }
 // inverse of pg_stage_split16: 16 values hi + lo of a TMA-loaded (swizzled) 32 x 64 tile
 __device__ __forceinline__ void pg_read_split16(const uint8_t* t_hi, const uint8_t* t_lo, int row, int chunk0, float* x) {
@@ -115,18 +131,13 @@ __device__ __forceinline__ void pg_read_split16(const uint8_t* t_hi, const uint8
         x[8 + 2 * i] = u1.x + w1.x; x[8 + 2 * i + 1] = u1.y + w1.y;
     }
 }
-__device__ __forceinline__ void pg_stage_zero16(uint8_t* stg_hi, uint8_t* stg_lo, int row, int chunk0) {
-    const int p0 = (chunk0 ^ (row & 7)) * 16, p1 = ((chunk0 + 1) ^ (row & 7)) * 16;
-    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    *reinterpret_cast<uint4*>(stg_hi + row * 128 + p0) = z;
-    *reinterpret_cast<uint4*>(stg_hi + row * 128 + p1) = z;
-    *reinterpret_cast<uint4*>(stg_lo + row * 128 + p0) = z;
-    *reinterpret_cast<uint4*>(stg_lo + row * 128 + p1) = z;
-}
-
-template <bool B_MN>
+// KIND specialises the epilogue at compile time (one compact code path per instantiation: with every variant in one
+// body the epilogue was ~3900 SASS instructions of mostly-skipped branches executed by a single warp per scheduler):
+//   0 = SPLIT (scale, diagonal, optional trace of the diagonal)   1 = SPLIT + auxiliary tile   2 = THETA   3 = F32
+template <bool B_MN, int KIND>
 __global__ void __launch_bounds__(PG_THREADS, 1)
 polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArgs args) {
+    constexpr bool kStaged = KIND != 3, kTheta = KIND == 2, kAux = KIND == 1;
     extern __shared__ uint8_t pg_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(pg_smem_raw) + 1023) & ~uintptr_t(1023));
     const int kABytes = args.a_alias_b ? 0 : 128 * 128;    // one 128-row A tile per operand buffer (none when aliased)
@@ -139,7 +150,7 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
     uint64_t* aux_bar = tmem_empty_bar + 2;                    // [4] one per epilogue warp
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 4);
     uint8_t* staging = smem + args.stages * stage_bytes + 1024;          // 4 warps x (hi 4 KB + lo 4 KB), 1024-aligned
-    uint8_t* aux_staging = staging + 4 * 8192;                           // same shape, only allocated when aux_mode
+    uint8_t* aux_staging = staging + 4 * 8192;                           // [4 warps][col blocks][hi 4 KB + lo 4 KB], only with aux_mode
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_kb = (args.k_total + PG_BK - 1) / PG_BK;
@@ -151,7 +162,7 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
         fence_mbar_init();
         tma_prefetch_desc(&maps.a[0]); tma_prefetch_desc(&maps.a[1]);
         tma_prefetch_desc(&maps.b[0]); tma_prefetch_desc(&maps.b[1]);
-        if (args.epi == PG_EPI_SPLIT || args.epi == PG_EPI_THETA) { tma_prefetch_desc(&maps.o[0]); tma_prefetch_desc(&maps.o[1]); }
+        if (kStaged) { tma_prefetch_desc(&maps.o[0]); tma_prefetch_desc(&maps.o[1]); }
     }
     uint32_t tmem_cols = 32;
     while (tmem_cols < static_cast<uint32_t>(2 * args.bn_mma)) tmem_cols <<= 1;
@@ -170,6 +181,8 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
                 const int z = args.reverse ? args.n_batches - 1 - w / args.n_mt : w / args.n_mt;
                 const int a_rows = args.a_rows_tile[mt];
                 const uint32_t tx = (args.a_alias_b ? 0 : 2 * a_rows * 128) + 2 * b_bytes;
+                const int item_p = (w - blockIdx.x) / gridDim.x;
+                if (args.dbg_clock && blockIdx.x == 0 && item_p < 16) args.dbg_clock[item_p * 8 + 0] = clock64();
                 for (int kb = 0; kb < n_kb; ++kb, ++it) {
                     const int s = it % args.stages;
                     const uint32_t ph = (it / args.stages) & 1;
@@ -191,6 +204,7 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
                         }
                     }
                 }
+                if (args.dbg_clock && blockIdx.x == 0 && item_p < 16) args.dbg_clock[item_p * 8 + 1] = clock64();
             }
         }
     } else if (warp == 1) {
@@ -201,8 +215,10 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
             const int acc = item & 1;
             const uint32_t acc_ph = (item >> 1) & 1;
             const int mt_mma = w % args.n_mt;
+            if (args.dbg_clock && blockIdx.x == 0 && item < 16 && lane == 0) args.dbg_clock[item * 8 + 2] = clock64();
             mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);           // epilogue has drained this accumulator
             tc_fence_after();
+            if (args.dbg_clock && blockIdx.x == 0 && item < 16 && lane == 0) args.dbg_clock[item * 8 + 3] = clock64();
             const uint32_t d_tmem = tmem_base + acc * args.bn_mma;
             for (int kb = 0; kb < n_kb; ++kb, ++it) {
                 const int s = it % args.stages;
@@ -227,6 +243,7 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
                     }
                     umma_commit(&empty_bar[s]);
                     if (kb == n_kb - 1) umma_commit(&tmem_full_bar[acc]);
+                    if (args.dbg_clock && blockIdx.x == 0 && item < 16 && kb == n_kb - 1) args.dbg_clock[item * 8 + 4] = clock64();
                 }
                 __syncwarp();
             }
@@ -242,16 +259,20 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
             const int acc = item & 1;
             const uint32_t acc_ph = (item >> 1) & 1;
             const bool warp_rows_ok = mt * 128 + q * 32 < args.m_rows;       // uniform: this warp owns at least one valid row
-            uint8_t* aux_hi_s = aux_staging + (warp - 2) * 8192;
-            uint8_t* aux_lo_s = aux_hi_s + 4096;
-            const bool use_aux = args.aux_mode != 0 && warp_rows_ok;
-            if (use_aux && lane == 0) {                                    // block 0 of the auxiliary tile, hidden behind the main loop
-                mbar_arrive_expect_tx(&aux_bar[warp - 2], 8192);
-                tma_load_4d(aux_hi_s, &maps.o[2], &aux_bar[warp - 2], 0, mt * 128 + q * 32, 0, z);
-                tma_load_4d(aux_lo_s, &maps.o[3], &aux_bar[warp - 2], 0, mt * 128 + q * 32, 0, z);
+            const int n_cb_aux = (args.bn_mma + 63) / 64;
+            uint8_t* aux_base = aux_staging + (warp - 2) * n_cb_aux * 8192;
+            const bool use_aux = kAux && warp_rows_ok;
+            if (use_aux && lane == 0) {                                    // the whole auxiliary tile of this item, hidden behind the main loop
+                mbar_arrive_expect_tx(&aux_bar[warp - 2], n_cb_aux * 8192);
+                for (int cb = 0; cb < n_cb_aux; ++cb) {
+                    tma_load_4d(aux_base + cb * 8192, &maps.o[2], &aux_bar[warp - 2], 0, mt * 128 + q * 32, cb, z);
+                    tma_load_4d(aux_base + cb * 8192 + 4096, &maps.o[3], &aux_bar[warp - 2], 0, mt * 128 + q * 32, cb, z);
+                }
             }
+            if (args.dbg_clock && blockIdx.x == 0 && item < 16 && warp == 2 && lane == 0) args.dbg_clock[item * 8 + 5] = clock64();
             mbar_wait(&tmem_full_bar[acc], acc_ph);
             tc_fence_after();
+            if (args.dbg_clock && blockIdx.x == 0 && item < 16 && warp == 2 && lane == 0) args.dbg_clock[item * 8 + 6] = clock64();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * args.bn_mma;
             const int row = mt * 128 + q * 32 + lane;
             const bool row_ok = row < args.m_rows;
@@ -260,39 +281,51 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
             const float scale = args.scale_c * (args.scale_p == 0.f ? 1.f : powf(r, args.scale_p));
             const float aux_scale = args.aux_c * (args.aux_p == 0.f ? 1.f : powf(r, args.aux_p));
             float a_row = 0.f, q_row = 0.f;
-            if (args.epi == PG_EPI_THETA && row_ok) {
+            if (kTheta && row_ok) {
                 a_row = args.vec_a[static_cast<long long>(z) * args.m_rows + row];
                 q_row = sqrtf(a_row);
             }
             float tr_part = 0.f;
-            if (args.epi == PG_EPI_SPLIT || args.epi == PG_EPI_THETA) {
-                const bool theta = args.epi == PG_EPI_THETA;
+            if constexpr (kStaged) {
+                constexpr bool theta = kTheta;
                 const float* av = theta ? args.vec_a + static_cast<long long>(z) * args.m_rows : nullptr;
                 // convert into the warp's swizzled staging tile; every 64-column block leaves as one TMA store per half
                 uint8_t* stg_hi = staging + (warp - 2) * 8192;
                 uint8_t* stg_lo = stg_hi + 4096;
+                const uint32_t stg_hi_s = smem_u32(stg_hi), stg_lo_s = smem_u32(stg_lo);
+                const bool diag_work = args.diag_add != 0.f;           // uniform: most launches have no diagonal term
                 const int n_cb = (args.bn_mma + 63) / 64;
+                if (use_aux) {
+                    mbar_wait(&aux_bar[warp - 2], aux_phase);
+                    aux_phase ^= 1;
+                }
                 for (int cbk = 0; cbk < n_cb; ++cbk) {
-                    if (use_aux) {
-                        mbar_wait(&aux_bar[warp - 2], aux_phase);
-                        aux_phase ^= 1;
+                    const uint8_t* aux_hi_s = aux_base + cbk * 8192;
+                    const uint8_t* aux_lo_s = aux_hi_s + 4096;
+                    // whole 64-column block in one tcgen05.ld (the last block of a 208-wide tile has 16 columns)
+                    const bool dbg_here = args.dbg_clock && blockIdx.x == 0 && item == 5 && cbk == 1 && warp == 2 && lane == 0;
+                    if (dbg_here) args.dbg_clock[120] = clock64();
+                    float vb[64];
+                    const int cols_here = min(64, args.bn_mma - cbk * 64);
+                    if (cols_here == 64) {
+                        tmem_ld64(t_addr + cbk * 64, vb);
+                    } else {
+#pragma unroll
+                        for (int jc = 0; jc < 4; ++jc) {
+                            if (jc * 16 < cols_here) tmem_ld16(t_addr + cbk * 64 + jc * 16, vb + jc * 16);
+                        }
                     }
+                    if (dbg_here) args.dbg_clock[121] = clock64();
 #pragma unroll
                     for (int jc = 0; jc < 4; ++jc) {
                         const int c = cbk * 64 + jc * 16;
+                        float* v = vb + jc * 16;
                         if (c < args.bn_mma) {
-                            float v[16];
-                            tmem_ld16(t_addr + c, v);
-                            if (args.trace && row_ok) {
-                                if (args.trace_mode == 1) {
-                                    if (row >= c && row < c + 16) tr_part += v[row - c];
-                                } else {
-                                    const long long off = z * args.out_stride + (static_cast<long long>(cbk) * args.m_rows + row) * 64 + jc * 16;
-                                    for (int i = 0; i < 16; ++i)
-                                        tr_part = fmaf(v[i], __bfloat162float(args.aux_hi[off + i]) + __bfloat162float(args.aux_lo[off + i]), tr_part);
-                                }
+                            if (KIND == 0 && args.trace && row_ok) {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) tr_part += (c + i == row) ? v[i] : 0.f;
                             }
-                            if (theta) {
+                            if constexpr (theta) {
 #pragma unroll
                                 for (int i = 0; i < 16; ++i) {
                                     float t = 0.f;
@@ -303,29 +336,29 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
                                     }
                                     v[i] = 2.f * t;
                                 }
-                            } else if (use_aux) {
+                            } else if constexpr (kAux) {
                                 float x[16];
                                 pg_read_split16(aux_hi_s, aux_lo_s, lane, jc * 2, x);
 #pragma unroll
                                 for (int i = 0; i < 16; ++i) v[i] = fmaf(aux_scale, x[i], scale * v[i]) + ((c + i == row) ? args.diag_add : 0.f);
-                            } else {
+                            } else if (diag_work) {
 #pragma unroll
                                 for (int i = 0; i < 16; ++i) v[i] = scale * v[i] + ((c + i == row) ? args.diag_add : 0.f);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) v[i] *= scale;
                             }
-                            pg_stage_split16(stg_hi, stg_lo, lane, jc * 2, v);
+                            pg_stage_split16(stg_hi_s, stg_lo_s, lane, jc * 2, v);
                         } else {
-                            pg_stage_zero16(stg_hi, stg_lo, lane, jc * 2);          // padding columns of the last block
+                            pg_stage_zero16(stg_hi_s, stg_lo_s, lane, jc * 2);      // padding columns of the last block
                         }
                     }
+                    if (dbg_here) args.dbg_clock[122] = clock64();
                     fence_proxy_async_smem();
                     __syncwarp();                                               // staging complete; aux tile fully consumed
+                    if (dbg_here) args.dbg_clock[123] = clock64();
                     if (lane == 0 && warp_rows_ok) {
-                        if (use_aux && cbk + 1 < n_cb) {                        // next auxiliary block overlaps this block's store
-                            mbar_arrive_expect_tx(&aux_bar[warp - 2], 8192);
-                            tma_load_4d(aux_hi_s, &maps.o[2], &aux_bar[warp - 2], 0, mt * 128 + q * 32, cbk + 1, z);
-                            tma_load_4d(aux_lo_s, &maps.o[3], &aux_bar[warp - 2], 0, mt * 128 + q * 32, cbk + 1, z);
-                        }
-                        if (theta) {                                            // row-major output, columns past n_cols are clipped
+                        if constexpr (theta) {                                  // row-major output, columns past n_cols are clipped
                             tma_store_3d(&maps.o[0], stg_hi, cbk * 64, mt * 128 + q * 32, z);
                             tma_store_3d(&maps.o[1], stg_lo, cbk * 64, mt * 128 + q * 32, z);
                         } else {
@@ -333,7 +366,9 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
                             tma_store_4d(&maps.o[1], stg_lo, 0, mt * 128 + q * 32, cbk, z);
                         }
                         tma_store_commit();
+                        if (dbg_here) args.dbg_clock[124] = clock64();
                         tma_store_wait_read();
+                        if (dbg_here) args.dbg_clock[125] = clock64();
                     }
                     __syncwarp();
                 }
@@ -357,6 +392,7 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
             }
             tc_fence_before();
             __syncwarp();
+            if (args.dbg_clock && blockIdx.x == 0 && item < 16 && warp == 2 && lane == 0) args.dbg_clock[item * 8 + 7] = clock64();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
             if (args.trace) {
 #pragma unroll
