@@ -121,6 +121,120 @@ __device__ int jacobi_orthogonalize(float* __restrict__ A, int ld, int n_cols, f
     return sweep;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Odd-even variant with register-resident columns (for the big pooled problems).
+// Positions 0..n-1 hold the columns; group g owns positions 2g (registers P) and 2g+1 (registers Q).  A sweep is n
+// steps of the odd-even transposition network, every step followed by a swap of the two columns it paired, so that
+// after n steps every pair of columns has met exactly once:
+//   even step : rotate (P, Q) in registers - no shared memory, no barrier;
+//   odd step  : positions (2g+1, 2g+2): group g keeps its odd column, borrows the even column of group g+1 through
+//               that group's mailbox (column 2g+2 of A), rotates, keeps the borrowed one and mails the other back.
+// Shared-memory traffic and barriers per step are half of the round-robin version above (which streams both columns of
+// every pair through shared memory every step and is bound by exactly that).
+// Requires n/2 <= blockDim.x / 8 groups.  Column ORDER on exit is a permutation of the input order (irrelevant to the
+// callers, which sort by eigenvalue).
+// ------------------------------------------------------------------------------------------------------------------
+template <int CHUNKS>
+__device__ __forceinline__ int jac_rotate_regs(float4 (&x)[CHUNKS], float4 (&y)[CHUNKS], unsigned gmask, float tol) {
+    float al = 0.f, be = 0.f, ga = 0.f;
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+        al = fmaf(x[c].x, x[c].x, fmaf(x[c].y, x[c].y, fmaf(x[c].z, x[c].z, fmaf(x[c].w, x[c].w, al))));
+        be = fmaf(y[c].x, y[c].x, fmaf(y[c].y, y[c].y, fmaf(y[c].z, y[c].z, fmaf(y[c].w, y[c].w, be))));
+        ga = fmaf(x[c].x, y[c].x, fmaf(x[c].y, y[c].y, fmaf(x[c].z, y[c].z, fmaf(x[c].w, y[c].w, ga))));
+    }
+#pragma unroll
+    for (int o = JAC_GROUP / 2; o > 0; o >>= 1) {
+        al += __shfl_xor_sync(gmask, al, o);
+        be += __shfl_xor_sync(gmask, be, o);
+        ga += __shfl_xor_sync(gmask, ga, o);
+    }
+    if (!(fabsf(ga) > tol * sqrtf(al * be))) return 0;
+    const float zeta = (be - al) / (2.f * ga);
+    const float t = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(fmaf(zeta, zeta, 1.f)));
+    const float cs = rsqrtf(fmaf(t, t, 1.f));
+    const float sn = cs * t;
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+        float4 xn, yn;
+        xn.x = cs * x[c].x - sn * y[c].x; yn.x = sn * x[c].x + cs * y[c].x;
+        xn.y = cs * x[c].y - sn * y[c].y; yn.y = sn * x[c].y + cs * y[c].y;
+        xn.z = cs * x[c].z - sn * y[c].z; yn.z = sn * x[c].z + cs * y[c].z;
+        xn.w = cs * x[c].w - sn * y[c].w; yn.w = sn * x[c].w + cs * y[c].w;
+        x[c] = xn; y[c] = yn;
+    }
+    return 1;
+}
+template <int CHUNKS>
+__device__ __forceinline__ void jac_ld(const float* __restrict__ col, int ld, int gl, bool valid, float4 (&v)[CHUNKS]) {
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+        const int r = c * JAC_CHUNK_ROWS + gl * 4;
+        v[c] = (valid && r < ld) ? *reinterpret_cast<const float4*>(col + r) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+template <int CHUNKS>
+__device__ __forceinline__ void jac_st(float* __restrict__ col, int ld, int gl, bool valid, const float4 (&v)[CHUNKS]) {
+    if (!valid) return;
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+        const int r = c * JAC_CHUNK_ROWS + gl * 4;
+        if (r < ld) *reinterpret_cast<float4*>(col + r) = v[c];
+    }
+}
+
+template <int CHUNKS>
+__device__ int jacobi_orthogonalize_oddeven(float* __restrict__ A, int ld, int n_cols, float tol, int max_sweeps) {
+    const int n = (n_cols + 1) & ~1;
+    const int m = n / 2;                                    // groups needed
+    const int g = threadIdx.x / JAC_GROUP;
+    const int gl = threadIdx.x % JAC_GROUP;
+    const unsigned gmask = 0xFFu << (threadIdx.x & 24);
+    const bool active = g < m;
+    const bool q_real = active && (2 * g + 1 < n_cols);     // the virtual last column of an odd n_cols is all zeros
+    const bool has_next = active && g + 1 < m;              // an odd-step partner exists
+    const bool next_real = has_next;                        // column 2g+2 < n_cols always holds when g+1 < m
+    float* colP = A + static_cast<size_t>(active ? 2 * g : 0) * ld;          // own mailbox = own even column
+    float* colQ = A + static_cast<size_t>(q_real ? 2 * g + 1 : 0) * ld;
+    float* colN = A + static_cast<size_t>(has_next ? 2 * g + 2 : 0) * ld;    // mailbox of group g+1
+    float4 P[CHUNKS], Q[CHUNKS];
+    jac_ld<CHUNKS>(colP, ld, gl, active, P);
+    jac_ld<CHUNKS>(colQ, ld, gl, q_real, Q);
+    __syncthreads();
+    int sweep = 0;
+    if (n_cols < 2) return 0;
+    for (; sweep < max_sweeps; ++sweep) {
+        int rotated = 0;
+        for (int pairstep = 0; pairstep < m; ++pairstep) {
+            // even step: positions (2g, 2g+1) = (P, Q); afterwards position 2g holds Q, position 2g+1 holds P
+            if (active) rotated |= jac_rotate_regs<CHUNKS>(P, Q, gmask, tol);
+            // odd step: positions (2g+1, 2g+2) = (P, even column of group g+1)
+            jac_st<CHUNKS>(colP, ld, gl, active, Q);        // mail own position-2g column (held in Q)
+            __syncthreads();
+            if (has_next) {
+                jac_ld<CHUNKS>(colN, ld, gl, next_real, Q); // borrow position 2g+2
+                rotated |= jac_rotate_regs<CHUNKS>(P, Q, gmask, tol);
+                jac_st<CHUNKS>(colN, ld, gl, true, P);      // rotated old 2g+1 goes to position 2g+2; Q stays as position 2g+1
+            }
+            __syncthreads();
+            if (has_next) {
+                jac_ld<CHUNKS>(colP, ld, gl, active, P);    // new position 2g from the mailbox; (P, Q) = (2g, 2g+1) again
+            } else if (active) {
+                // last group: its odd column (in P) was idle; restore the roles (P, Q) = (2g, 2g+1) with a register swap
+#pragma unroll
+                for (int c = 0; c < CHUNKS; ++c) { const float4 t = P[c]; P[c] = Q[c]; Q[c] = t; }
+                jac_ld<CHUNKS>(colP, ld, gl, true, P);      // (its own mailbox may have been rewritten by group g-1)
+            }
+        }
+        if (!__syncthreads_or(rotated)) { ++sweep; break; }
+    }
+    __syncthreads();
+    jac_st<CHUNKS>(colP, ld, gl, active, P);
+    jac_st<CHUNKS>(colQ, ld, gl, q_real, Q);
+    __syncthreads();
+    return sweep;
+}
+
 // Column norms (sqrt of sum of squares) of the first n_cols columns -> out[n_cols].  One warp per column.
 __device__ inline void column_norms(const float* __restrict__ A, int ld, int m, int n_cols, float* __restrict__ out) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;

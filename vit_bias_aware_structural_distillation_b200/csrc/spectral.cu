@@ -38,6 +38,21 @@ __device__ __forceinline__ int run_jacobi(float* A, int ld, int n) {
     }
 }
 
+// odd-even ordering with register-resident columns (jacobi.cuh); needs an even column count and n/2 <= 96 groups
+__device__ __forceinline__ int run_jacobi_oddeven(float* A, int ld, int n) {
+    const int chunks = (ld + JAC_CHUNK_ROWS - 1) / JAC_CHUNK_ROWS;
+    switch (chunks) {
+        case 1: return jacobi_orthogonalize_oddeven<1>(A, ld, n, kJacobiTol, kJacobiMaxSweeps);
+        case 2: return jacobi_orthogonalize_oddeven<2>(A, ld, n, kJacobiTol, kJacobiMaxSweeps);
+        case 3: return jacobi_orthogonalize_oddeven<3>(A, ld, n, kJacobiTol, kJacobiMaxSweeps);
+        case 4: return jacobi_orthogonalize_oddeven<4>(A, ld, n, kJacobiTol, kJacobiMaxSweeps);
+        case 5: return jacobi_orthogonalize_oddeven<5>(A, ld, n, kJacobiTol, kJacobiMaxSweeps);
+        case 6: return jacobi_orthogonalize_oddeven<6>(A, ld, n, kJacobiTol, kJacobiMaxSweeps);
+        case 7: return jacobi_orthogonalize_oddeven<7>(A, ld, n, kJacobiTol, kJacobiMaxSweeps);
+        default: return jacobi_orthogonalize_oddeven<8>(A, ld, n, kJacobiTol, kJacobiMaxSweeps);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // pooled_eig_kernel: one CTA per symmetric problem of size n = Ds.
 //   problem p in [0, Lt)        : MP rank of teacher layer p   (uncentred G / M)
@@ -112,7 +127,8 @@ pooled_eig_kernel(const float* __restrict__ stats, int n, int Lt, int P, float M
         }
     }
     __syncthreads();
-    const int nsweeps = run_jacobi<false>(A, ld, n);
+    const bool oddeven_ok = (n % 2 == 0) && (n / 2 <= static_cast<int>(blockDim.x) / JAC_GROUP);
+    const int nsweeps = oddeven_ok ? run_jacobi_oddeven(A, ld, n) : run_jacobi<false>(A, ld, n);
     column_norms(A, ld, n, n, vals);        // sigma_i (Cholesky route) or lambda_i (fallback)
     __syncthreads();
     if (use_chol)
