@@ -340,11 +340,20 @@ def main():
     polar_launches = 4 * ksteps + 2
     polar_flops = n_prob * (ksteps * (2 * w.Ds * w.Ns * w.Ns + 2 * w.Ds * w.Ds * w.Ns + 2 * w.Ds ** 3 + 2 * w.Ds * w.Ds * w.Ns)
                             + 2 * w.Ns * w.Ns * w.Ds + 2 * w.Ns * w.Ds * w.Ns)
+    # polar_gemm as launched: every product streams its split-bf16 (hi + lo = 4 B per element) operands in and its result
+    # out once per launch; these are the algorithmic bytes of the MULTI-LAUNCH formulation (unpadded), DESIGN.md section 5
+    D, N = w.Ds, w.Ns
+    polar_bytes = n_prob * 4 * (ksteps * ((2 * D * N + N * N) + (2 * D * N + D * D) + 2 * D * D + (D * D + 2 * D * N))
+                                + (N * N + D * N + N * D) + (2 * N * D + N * N))
+    eig_bytes = 4 * ((2 * w.Lt + w.P) * (D * D + D) + (w.Lt + w.P) * (2 * D * D + D))
     table = {   # slot -> (bound, algorithmic units per step, launches per step, description)
-        "polar_gemm": ("tensor", polar_flops, polar_launches,
-                       "Newton-Schulz polar iteration: (4 x steps + 2) products of D_s x N_s x {N_s, D_s} per (point, sample); plain 2mnk "
-                       "flops - the 3 split-bf16 MMAs per product are not counted"),
-        "pooled_eig": ("tensor", 0, 1, "fp32 Jacobi on CUDA cores: no HBM / tensor roofline applies"),
+        "polar_gemm": ("hbm", polar_bytes, polar_launches,
+                       "Newton-Schulz polar iteration, (4 x steps + 2) batched products per step: split-bf16 operands read once and the "
+                       "result written once per launch (4 B per element, unpadded).  Tensor view of the same kernel: "
+                       f"{polar_flops / polar_launches / 1e9:.1f} GFLOP of plain 2mnk per launch (3 split MMAs per product not counted)"),
+        "pooled_eig": ("hbm", eig_bytes, 1,
+                       "28 shared-memory eigenproblems (Cholesky + one-sided Jacobi, fp32 CUDA cores) on 28 SMs: latency / issue bound, "
+                       "neither roofline applies; bytes = Gram statistics in, eigenpairs out"),
     }
     traffic = None
     try:
@@ -355,10 +364,13 @@ def main():
     if dom in table and table[dom][1] > 0:
         bound, units, launches, what = table[dom]
         ms_launch = per_step[dom] / launches
-        ach = units / launches / (ms_launch * 1e-3) / 1e12
-        roofline = {"bound": bound, "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach / tc_peak, "traffic": traffic,
+        ach = units / launches / (ms_launch * 1e-3) / 1e9
+        roofline = {"bound": bound, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
                     "kernel": dom, "what": what, "launches_per_step": launches, "avg_launch_ms": ms_launch,
-                    "algorithmic_flops_per_launch": units / launches}
+                    "algorithmic_bytes_per_launch": units / launches}
+        if dom == "polar_gemm":
+            tf = polar_flops / polar_launches / (ms_launch * 1e-3) / 1e12
+            roofline["tensor_view"] = {"achieved_tflops": tf, "peak_tflops": tc_peak, "frac": tf / tc_peak}
     else:
         achieved = w_alg / (ms_step * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
@@ -370,6 +382,9 @@ def main():
                  "tensor": {"algorithmic_flops_per_step": f_tc, "achieved_tflops": f_tc / (ms_step * 1e-3) / 1e12, "peak_tflops": tc_peak,
                             "frac": f_tc / (ms_step * 1e-3) / 1e12 / tc_peak},
                  "scope": "W_alg = 2 X_T + 4 X_S + A_needed and F_tc of SURVEY.md section 8d over the whole step time"},
+        "other_kernels": {k: {"bound": table[k][0], "achieved_gbs": table[k][1] / table[k][2] / (per_step[k] / table[k][2] * 1e-3) / 1e9,
+                              "frac": table[k][1] / table[k][2] / (per_step[k] / table[k][2] * 1e-3) / 1e9 / hbm_peak,
+                              "ms_per_step": per_step[k]} for k in table if k != dom and k in per_step},
         "dominant_kernel": dom, "dominant_kernel_ms_per_step": per_step.get(dom) if dom else None,
         "dominant_kernel_share": (per_step[dom] / ms_step) if dom else None,
         "kernel_ms_per_step": {k: round(v, 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])}})

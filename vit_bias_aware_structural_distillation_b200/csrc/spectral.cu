@@ -48,8 +48,7 @@ __device__ __forceinline__ int run_jacobi_oddeven(float* A, int ld, int n) {
         case 4: return jacobi_orthogonalize_oddeven<4>(A, ld, n, kJacobiTol, kJacobiMaxSweeps);
         case 5: return jacobi_orthogonalize_oddeven<5>(A, ld, n, kJacobiTol, kJacobiMaxSweeps);
         case 6: return jacobi_orthogonalize_oddeven<6>(A, ld, n, kJacobiTol, kJacobiMaxSweeps);
-        case 7: return jacobi_orthogonalize_oddeven<7>(A, ld, n, kJacobiTol, kJacobiMaxSweeps);
-        default: return jacobi_orthogonalize_oddeven<8>(A, ld, n, kJacobiTol, kJacobiMaxSweeps);
+        default: return run_jacobi<false>(A, ld, n);       // 7-8 chunks (n > 192) would spill at 80 registers per thread
     }
 }
 
