@@ -435,3 +435,28 @@ def test_cls_attention_rows_from_q_k(lib, cuda_dev):
     a = m.geo_loss(S_, T_, maps)
     b = m.geo_loss(S_, T_, rows_only)
     assert abs(a.item() - b.item()) <= 1e-5 * abs(a.item())
+
+
+@pytest.mark.parametrize("shape", [
+    dict(B=3, Ns=50, Nt=50, Ds=40, Dt=72, Lt=2, H=3, P=3),          # nothing a multiple of 16; three extraction points
+    dict(B=5, Ns=36, Nt=36, Ds=32, Dt=32, Lt=4, H=1, P=1),          # a single extraction point (combined.py:34-36), D_t == D_s
+    dict(B=2, Ns=130, Nt=130, Ds=96, Dt=200, Lt=3, H=2, P=2),       # N > 128: two 128-row output tiles in the N x N products
+    dict(B=2, Ns=70, Nt=90, Ds=64, Dt=136, Lt=2, H=2, P=4),         # down-sampling 90 -> 70 with D_s exactly one column block
+    dict(B=9, Ns=210, Nt=210, Ds=200, Dt=256, Lt=2, H=2, P=2),      # D_s > 192: round-robin Jacobi path, 4 column blocks
+])
+def test_irregular_shapes_against_oracle(lib, cuda_dev, shape):
+    """Shapes off the BASELINE grid: padding, tails and tile boundaries of every kernel against the fp32 oracle."""
+    w = synth.Workload("irregular", shape["B"], shape["Ns"], shape["Nt"], shape["Ds"], shape["Dt"], shape["Lt"], shape["H"], True, P=shape["P"])
+    inp = synth.make_inputs(w, seed=11)
+    m = build_module(w, cuda_dev)
+    out = run_module(m, inp, cuda_dev)
+    ref = oracle_case(m, inp, w)
+    assert out["ranks"] == ref["ranks"]
+    assert abs(out["loss"].item() - ref["loss"].item()) <= TOL_LOSS * abs(ref["loss"].item())
+    assert (out["w"] - ref["w"].float()).abs().max() < 2e-4
+    # few pooled rows: small eigen-gaps, so the referee-scaled tolerances of the tiny fixtures apply
+    gt, rt = out["grad_log_temperatures"], ref["grad_log_temperatures"].float()
+    # (entries that are themselves a cancellation to ~5 % of the largest one are judged against the largest)
+    assert ((gt - rt).abs() <= 5e-3 * rt.abs().max()).all(), f"temperature grads {gt} vs {rt}"
+    for l in ref["grad_student"]:
+        assert rel(out["grad_student"][l], ref["grad_student"][l]) < 3 * TOL_SGRAD, f"student grad layer {l}"
