@@ -292,7 +292,7 @@ cudaError_t launch_polar_procrustes(const PolarArgs& g, cudaStream_t st, int* la
             // G2: A = T W^T                (step 0: trace(A) = ||C||_F^2, read by the epilogues of G3 / G4 of that step)
             memset(&a, 0, sizeof a);
             a.epi = PG_EPI_SPLIT; a.out_hi = A.hi; a.out_lo = A.lo; a.out_stride = A.batch_stride; a.scale_c = 1.f;
-            if (first) { a.trace = fro2; a.trace_mode = 1; }
+            if (first) a.trace = fro2;
             if (k == 3 && z0 == 0 && getenv("BASD_POLAR_DBG")) a.dbg_clock = polar_dbg_ptr(1);
             a.reverse = (dir++) & 1;
             PCK(polar_gemm(false, T, Wc, nz, a, st));

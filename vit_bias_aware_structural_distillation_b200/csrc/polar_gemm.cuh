@@ -55,34 +55,10 @@ struct PolarGemmArgs {
     long long* dbg_clock;            // development aid: CTA 0 records clock64() per phase of its first items ([item][8])
     int reverse, n_batches;          // reverse: walk the problems last-to-first (what the previous launch wrote last is still in L2)
     float* trace;                    // if non-null: trace[z] += sum(diag(acc))
-    int trace_mode;                  // (unused)
     const __nv_bfloat16* aux_hi; const __nv_bfloat16* aux_lo;
     float* out_f32; long long out_f32_stride; int ld_f32;
     const float* vec_a;              // THETA: importance a [z][m_rows]
 };
-
-__device__ __forceinline__ void pg_store_split16(__nv_bfloat16* ph, __nv_bfloat16* pl, const float* v, int nv) {
-    if (nv == 16) {
-        uint32_t hw[8], lw[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const __nv_bfloat16 h0 = __float2bfloat16(v[2 * i]), h1 = __float2bfloat16(v[2 * i + 1]);
-            __nv_bfloat162 hv; hv.x = h0; hv.y = h1;
-            hw[i] = *reinterpret_cast<uint32_t*>(&hv);
-            lw[i] = pack_bf16x2(v[2 * i] - __bfloat162float(h0), v[2 * i + 1] - __bfloat162float(h1));
-        }
-        reinterpret_cast<uint4*>(ph)[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-        reinterpret_cast<uint4*>(ph)[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
-        reinterpret_cast<uint4*>(pl)[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-        reinterpret_cast<uint4*>(pl)[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
-    } else {
-        for (int i = 0; i < nv; ++i) {
-            const __nv_bfloat16 h = __float2bfloat16(v[i]);
-            ph[i] = h;
-            pl[i] = __float2bfloat16(v[i] - __bfloat162float(h));
-        }
-    }
-}
 
 // 16 fp32 values -> bf16 hi / lo halves of staging row `row` (32 rows x 128 B, SWIZZLE_128B: 16-byte chunk j of row r
 // lives at chunk position j ^ (r & 7)); chunk0 = first of the two 16-byte chunks the 16 columns occupy.
