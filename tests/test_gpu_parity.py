@@ -78,7 +78,7 @@ def assert_parity(out, ref, w, tgrad_floor=1e-7, tgrad_tol=TOL_TGRAD):
     assert abs(out["loss"].item() - ref["loss"].item()) <= TOL_LOSS * abs(ref["loss"].item())
     assert (out["w"] - ref["w"].float()).abs().max() < 1e-4
     gt, rt = out["grad_log_temperatures"], ref["grad_log_temperatures"].float()
-    assert ((gt - rt).abs() <= tgrad_tol * rt.abs() + tgrad_floor).all(), f"temperature grads {gt} vs {rt}"
+    assert ((gt - rt).abs() <= tgrad_tol * rt.abs() + tgrad_floor).all(), f"temperature grads {gt.tolist()} vs {rt.tolist()}"
     for l in ref["grad_student"]:
         assert rel(out["grad_student"][l], ref["grad_student"][l]) < TOL_SGRAD, f"student grad layer {l}"
     assert rel(out["grad_logits"], ref["grad_logits"]) < 1e-3
@@ -457,6 +457,6 @@ def test_irregular_shapes_against_oracle(lib, cuda_dev, shape):
     # few pooled rows: small eigen-gaps, so the referee-scaled tolerances of the tiny fixtures apply
     gt, rt = out["grad_log_temperatures"], ref["grad_log_temperatures"].float()
     # (entries that are themselves a cancellation to ~5 % of the largest one are judged against the largest)
-    assert ((gt - rt).abs() <= 5e-3 * rt.abs().max()).all(), f"temperature grads {gt} vs {rt}"
+    assert ((gt - rt).abs() <= 5e-3 * rt.abs().max()).all(), f"temperature grads {gt.tolist()} vs {rt.tolist()}"
     for l in ref["grad_student"]:
         assert rel(out["grad_student"][l], ref["grad_student"][l]) < 3 * TOL_SGRAD, f"student grad layer {l}"

@@ -136,52 +136,89 @@ __device__ int jacobi_orthogonalize(float* __restrict__ A, int ld, int n_cols, f
 // 4.7 for the round-robin version; exchanging the three in-warp neighbours by shuffle instead of through the mailboxes
 // was slower again (4.7: 48 shuffles per lane per odd step cost more issue slots than the shared-memory traffic saved).
 // ------------------------------------------------------------------------------------------------------------------
+// Packed fp32 arithmetic (sm_100 FFMA2 / FMUL2: two fp32 lanes per instruction).  The kernel is bound by instruction
+// issue between barriers, so the columns live in registers as row PAIRS and every dot product / rotation instruction
+// handles two rows.
+using jac_f2 = unsigned long long;
+__device__ __forceinline__ jac_f2 jac_pack(float lo, float hi) {
+    jac_f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float jac_hsum(jac_f2 v) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return lo + hi;
+}
+__device__ __forceinline__ jac_f2 jac_fma2(jac_f2 a, jac_f2 b, jac_f2 c) {
+    jac_f2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ jac_f2 jac_mul2(jac_f2 a, jac_f2 b) {
+    jac_f2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ float jac_sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float jac_rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 template <int CHUNKS>
-__device__ __forceinline__ int jac_rotate_regs(float4 (&x)[CHUNKS], float4 (&y)[CHUNKS], unsigned gmask, float tol) {
-    float al = 0.f, be = 0.f, ga = 0.f;
+__device__ __forceinline__ int jac_rotate_regs(ulonglong2 (&x)[CHUNKS], ulonglong2 (&y)[CHUNKS], unsigned gmask, float tol) {
+    jac_f2 al2 = 0ull, be2 = 0ull, ga2 = 0ull;            // 0ull = (+0.f, +0.f)
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) {
-        al = fmaf(x[c].x, x[c].x, fmaf(x[c].y, x[c].y, fmaf(x[c].z, x[c].z, fmaf(x[c].w, x[c].w, al))));
-        be = fmaf(y[c].x, y[c].x, fmaf(y[c].y, y[c].y, fmaf(y[c].z, y[c].z, fmaf(y[c].w, y[c].w, be))));
-        ga = fmaf(x[c].x, y[c].x, fmaf(x[c].y, y[c].y, fmaf(x[c].z, y[c].z, fmaf(x[c].w, y[c].w, ga))));
+        al2 = jac_fma2(x[c].x, x[c].x, jac_fma2(x[c].y, x[c].y, al2));
+        be2 = jac_fma2(y[c].x, y[c].x, jac_fma2(y[c].y, y[c].y, be2));
+        ga2 = jac_fma2(x[c].x, y[c].x, jac_fma2(x[c].y, y[c].y, ga2));
     }
+    float al = jac_hsum(al2), be = jac_hsum(be2), ga = jac_hsum(ga2);
 #pragma unroll
     for (int o = JAC_GROUP / 2; o > 0; o >>= 1) {
         al += __shfl_xor_sync(gmask, al, o);
         be += __shfl_xor_sync(gmask, be, o);
         ga += __shfl_xor_sync(gmask, ga, o);
     }
-    if (!(fabsf(ga) > tol * sqrtf(al * be))) return 0;
-    const float zeta = (be - al) / (2.f * ga);
-    const float t = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(fmaf(zeta, zeta, 1.f)));
+    // MUFU approximations (2 ulp) instead of IEEE sqrt / divide with their slow-path calls: an error in t only leaves a
+    // residual of relative size 1e-7 in the annihilated entry (the next sweep removes it); orthogonality of the
+    // rotation rests on cs, sn alone, as before.  Overflow of zeta^2 gives sqrt = inf, t = 0: no rotation.
+    if (!(fabsf(ga) > tol * jac_sqrt_approx(al * be))) return 0;
+    const float zeta = (be - al) * jac_rcp_approx(2.f * ga);
+    const float t = copysignf(jac_rcp_approx(fabsf(zeta) + jac_sqrt_approx(fmaf(zeta, zeta, 1.f))), zeta);
     const float cs = rsqrtf(fmaf(t, t, 1.f));
     const float sn = cs * t;
+    const jac_f2 cs2 = jac_pack(cs, cs), sn2 = jac_pack(sn, sn), nsn2 = jac_pack(-sn, -sn);
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) {
-        float4 xn, yn;
-        xn.x = cs * x[c].x - sn * y[c].x; yn.x = sn * x[c].x + cs * y[c].x;
-        xn.y = cs * x[c].y - sn * y[c].y; yn.y = sn * x[c].y + cs * y[c].y;
-        xn.z = cs * x[c].z - sn * y[c].z; yn.z = sn * x[c].z + cs * y[c].z;
-        xn.w = cs * x[c].w - sn * y[c].w; yn.w = sn * x[c].w + cs * y[c].w;
+        ulonglong2 xn, yn;
+        xn.x = jac_fma2(cs2, x[c].x, jac_mul2(nsn2, y[c].x)); yn.x = jac_fma2(sn2, x[c].x, jac_mul2(cs2, y[c].x));
+        xn.y = jac_fma2(cs2, x[c].y, jac_mul2(nsn2, y[c].y)); yn.y = jac_fma2(sn2, x[c].y, jac_mul2(cs2, y[c].y));
         x[c] = xn; y[c] = yn;
     }
     return 1;
 }
 template <int CHUNKS>
-__device__ __forceinline__ void jac_ld(const float* __restrict__ col, int ld, int gl, bool valid, float4 (&v)[CHUNKS]) {
+__device__ __forceinline__ void jac_ld(const float* __restrict__ col, int ld, int gl, bool valid, ulonglong2 (&v)[CHUNKS]) {
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) {
         const int r = c * JAC_CHUNK_ROWS + gl * 4;
-        v[c] = (valid && r < ld) ? *reinterpret_cast<const float4*>(col + r) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[c] = (valid && r < ld) ? *reinterpret_cast<const ulonglong2*>(col + r) : make_ulonglong2(0ull, 0ull);
     }
 }
 template <int CHUNKS>
-__device__ __forceinline__ void jac_st(float* __restrict__ col, int ld, int gl, bool valid, const float4 (&v)[CHUNKS]) {
+__device__ __forceinline__ void jac_st(float* __restrict__ col, int ld, int gl, bool valid, const ulonglong2 (&v)[CHUNKS]) {
     if (!valid) return;
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) {
         const int r = c * JAC_CHUNK_ROWS + gl * 4;
-        if (r < ld) *reinterpret_cast<float4*>(col + r) = v[c];
+        if (r < ld) *reinterpret_cast<ulonglong2*>(col + r) = v[c];
     }
 }
 
@@ -199,7 +236,7 @@ __device__ int jacobi_orthogonalize_oddeven(float* __restrict__ A, int ld, int n
     float* colP = A + static_cast<size_t>(active ? 2 * g : 0) * ld;          // own mailbox = own even column
     float* colQ = A + static_cast<size_t>(q_real ? 2 * g + 1 : 0) * ld;
     float* colN = A + static_cast<size_t>(has_next ? 2 * g + 2 : 0) * ld;    // mailbox of group g+1
-    float4 P[CHUNKS], Q[CHUNKS];
+    ulonglong2 P[CHUNKS], Q[CHUNKS];
     jac_ld<CHUNKS>(colP, ld, gl, active, P);
     jac_ld<CHUNKS>(colQ, ld, gl, q_real, Q);
     __syncthreads();
@@ -224,7 +261,7 @@ __device__ int jacobi_orthogonalize_oddeven(float* __restrict__ A, int ld, int n
             } else if (active) {
                 // last group: its odd column (in P) was idle; restore the roles (P, Q) = (2g, 2g+1) with a register swap
 #pragma unroll
-                for (int c = 0; c < CHUNKS; ++c) { const float4 t = P[c]; P[c] = Q[c]; Q[c] = t; }
+                for (int c = 0; c < CHUNKS; ++c) { const ulonglong2 t = P[c]; P[c] = Q[c]; Q[c] = t; }
                 jac_ld<CHUNKS>(colP, ld, gl, true, P);      // (its own mailbox may have been rewritten by group g-1)
             }
         }
