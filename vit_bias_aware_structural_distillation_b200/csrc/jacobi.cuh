@@ -15,8 +15,11 @@
 // shuffle / rotation-parameter overhead is amortised over 24 rows per lane (16-lane groups needed two passes per step).
 // ld must be a multiple of 4.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include "ptx.cuh"
 
 namespace basd {
 
@@ -271,6 +274,144 @@ __device__ int jacobi_orthogonalize_oddeven(float* __restrict__ A, int ld, int n
     jac_st<CHUNKS>(colP, ld, gl, active, P);
     jac_st<CHUNKS>(colQ, ld, gl, q_real, Q);
     __syncthreads();
+    return sweep;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// The same odd-even network spread over a thread-block CLUSTER: the n/2 groups are dealt to the CTAs of the cluster in
+// contiguous runs, so one SM issues the instructions and carries the shared-memory traffic of n/(2C) pairs instead of
+// n/2 (with all 96 pairs of an n = 192 problem on one SM a pair-step cost ~6.6k cycles, four times its dependent
+// latency chain: six warps per scheduler and 295 KB of shared-memory traffic per pair-step).
+// Inside a CTA nothing changes except that the two barriers per pair-step are a named barrier over the active warps.
+// Across a CTA boundary (last group g of CTA k, first group g+1 of CTA k+1) the column exchange is pushed through
+// distributed shared memory with st.async, which signals an mbarrier of the RECEIVING CTA with the bytes it delivered:
+//   group g+1 pushes its even column into CTA k's inbox   -> bar_in  of CTA k   (instead of mailing it locally)
+//   group g   rotates against the inbox and pushes the column that moves on into group g+1's mailbox -> bar_back of CTA k+1
+// so no cluster-wide barrier sits in the pair-step (barrier.cluster with release/acquire compiles to MEMBAR.ALL.GPU +
+// CCTL.IVALL and made the cluster version slower than one CTA: measured 4.07 against 3.79 ms).
+// The matrix lives in the shared memory of cluster rank 0 (same offset `A` in every CTA); the other CTAs use their own
+// copy of that region for mailboxes only.  One cluster barrier per sweep ORs the convergence flags.
+// All threads of all CTAs of the cluster must call it; returns the sweep count (identical in every CTA).
+// inbox: ld floats, bars: 2 mbarriers, flags: 16 ints - shared memory at the same offsets in every CTA.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void jac_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t jac_mapa(uint32_t saddr, int rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+// 16 bytes to the shared memory of another CTA; the receiver's mbarrier is credited with 16 bytes on arrival
+__device__ __forceinline__ void jac_st_async(uint32_t raddr, ulonglong2 v, uint32_t rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];" ::"r"(raddr), "l"(v.x), "l"(v.y),
+                 "r"(rbar)
+                 : "memory");
+}
+template <int CHUNKS>
+__device__ __forceinline__ void jac_push(uint32_t rcol, uint32_t rbar, int ld, int gl, const ulonglong2 (&v)[CHUNKS]) {
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+        const int r = c * JAC_CHUNK_ROWS + gl * 4;
+        if (r < ld) jac_st_async(rcol + r * 4, v[c], rbar);
+    }
+}
+__device__ __forceinline__ void jac_bar_active(int nthreads) {
+    __syncwarp();                                           // (8-lane groups of a warp take different branches)
+    asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
+
+template <int CHUNKS>
+__device__ int jacobi_orthogonalize_oddeven_cluster(float* __restrict__ A, int ld, int n_cols, float tol, int max_sweeps, float* inbox,
+                                                    uint64_t* bars, int* flags) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = static_cast<int>(cluster.num_blocks()), crank = static_cast<int>(cluster.block_rank());
+    const int n = (n_cols + 1) & ~1;
+    const int m = n / 2;                                    // groups in the whole cluster
+    const int gpc = (m + C - 1) / C;                        // groups per CTA
+    const int n_active = (gpc * JAC_GROUP + 31) & ~31;      // threads of the warps that hold groups
+    const int gloc = threadIdx.x / JAC_GROUP;
+    const int gl = threadIdx.x % JAC_GROUP;
+    const int g = crank * gpc + gloc;
+    const unsigned gmask = 0xFFu << (threadIdx.x & 24);
+    const bool active = gloc < gpc && g < m;
+    const bool q_real = active && (2 * g + 1 < n_cols);
+    const bool has_next = active && g + 1 < m;
+    const bool next_remote = has_next && gloc == gpc - 1;   // the odd-step partner lives in CTA crank + 1
+    const bool prev_remote = active && gloc == 0 && crank > 0;   // this group is such a partner for CTA crank - 1
+    uint64_t* bar_in = bars;                                // credited by group g+1's pushes into `inbox`
+    uint64_t* bar_back = bars + 1;                          // credited by group g-1's pushes into this group's mailbox
+    if (threadIdx.x == 0) {
+        mbar_init(bar_in, 1);
+        mbar_init(bar_back, 1);
+        fence_mbar_init();
+    }
+    float* A0 = cluster.map_shared_rank(A, 0);                                           // the matrix itself
+    float* colP = A + static_cast<size_t>(active ? 2 * g : 0) * ld;                      // own mailbox (local)
+    float* colN = A + static_cast<size_t>(has_next && !next_remote ? 2 * g + 2 : 0) * ld;    // mailbox of a local group g+1
+    // remote addresses (shared::cluster window)
+    const uint32_t r_inbox = jac_mapa(smem_u32(inbox), prev_remote ? crank - 1 : crank);
+    const uint32_t r_bar_in = jac_mapa(smem_u32(bar_in), prev_remote ? crank - 1 : crank);
+    const uint32_t r_mail = jac_mapa(smem_u32(A + static_cast<size_t>(next_remote ? 2 * g + 2 : 0) * ld), next_remote ? crank + 1 : crank);
+    const uint32_t r_bar_back = jac_mapa(smem_u32(bar_back), next_remote ? crank + 1 : crank);
+    const uint32_t col_bytes = static_cast<uint32_t>(ld) * 4u;
+    ulonglong2 P[CHUNKS], Q[CHUNKS];
+    jac_ld<CHUNKS>(A0 + static_cast<size_t>(active ? 2 * g : 0) * ld, ld, gl, active, P);
+    jac_ld<CHUNKS>(A0 + static_cast<size_t>(q_real ? 2 * g + 1 : 0) * ld, ld, gl, q_real, Q);
+    jac_cluster_sync();                                     // mbarriers initialised everywhere, initial loads done
+    int sweep = 0;
+    uint32_t phase = 0;
+    if (n_cols >= 2) {
+        for (; sweep < max_sweeps; ++sweep) {
+            int rotated = 0;
+            if (static_cast<int>(threadIdx.x) < n_active) {
+                for (int pairstep = 0; pairstep < m; ++pairstep, phase ^= 1) {
+                    if (gl == 0) {                          // arm this pair-step's deliveries
+                        if (next_remote) mbar_arrive_expect_tx(bar_in, col_bytes);
+                        if (prev_remote) mbar_arrive_expect_tx(bar_back, col_bytes);
+                    }
+                    // even step: positions (2g, 2g+1) = (P, Q); afterwards position 2g holds Q, position 2g+1 holds P
+                    if (active) rotated |= jac_rotate_regs<CHUNKS>(P, Q, gmask, tol);
+                    if (prev_remote) jac_push<CHUNKS>(r_inbox, r_bar_in, ld, gl, Q);      // to the last group of the previous CTA
+                    else jac_st<CHUNKS>(colP, ld, gl, active, Q);                         // mail own position-2g column
+                    jac_bar_active(n_active);
+                    // odd step: positions (2g+1, 2g+2) = (P, even column of group g+1)
+                    if (next_remote) {
+                        mbar_wait(bar_in, phase);
+                        jac_ld<CHUNKS>(inbox, ld, gl, true, Q);
+                        rotated |= jac_rotate_regs<CHUNKS>(P, Q, gmask, tol);
+                        jac_push<CHUNKS>(r_mail, r_bar_back, ld, gl, P);
+                    } else if (has_next) {
+                        jac_ld<CHUNKS>(colN, ld, gl, true, Q);
+                        rotated |= jac_rotate_regs<CHUNKS>(P, Q, gmask, tol);
+                        jac_st<CHUNKS>(colN, ld, gl, true, P);
+                    }
+                    jac_bar_active(n_active);
+                    if (prev_remote) mbar_wait(bar_back, phase);
+                    if (has_next) {
+                        jac_ld<CHUNKS>(colP, ld, gl, true, P);   // new position 2g from the mailbox; (P, Q) = (2g, 2g+1) again
+                    } else if (active) {
+                        // last group of all: its odd column (in P) was idle; restore the roles with a register swap
+#pragma unroll
+                        for (int c = 0; c < CHUNKS; ++c) { const ulonglong2 t = P[c]; P[c] = Q[c]; Q[c] = t; }
+                        jac_ld<CHUNKS>(colP, ld, gl, true, P);
+                    }
+                }
+            }
+            // did any CTA of the cluster rotate in this sweep?  (flags double-buffered by sweep parity)
+            const int any_local = __syncthreads_or(rotated);
+            int* fl = flags + (sweep & 1) * 8;
+            if (threadIdx.x < C) cluster.map_shared_rank(fl, threadIdx.x)[crank] = any_local;
+            jac_cluster_sync();
+            int any = 0;
+            for (int r = 0; r < C; ++r) any |= fl[r];
+            if (!any) { ++sweep; break; }
+        }
+    }
+    jac_st<CHUNKS>(A0 + static_cast<size_t>(active ? 2 * g : 0) * ld, ld, gl, active, P);
+    jac_st<CHUNKS>(A0 + static_cast<size_t>(q_real ? 2 * g + 1 : 0) * ld, ld, gl, q_real, Q);
+    jac_cluster_sync();
     return sweep;
 }
 

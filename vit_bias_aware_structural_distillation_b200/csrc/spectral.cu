@@ -52,8 +52,23 @@ __device__ __forceinline__ int run_jacobi_oddeven(float* A, int ld, int n) {
     }
 }
 
+// the same over the CTAs of the cluster (all CTAs call; false = shape not supported, nothing done)
+__device__ __forceinline__ bool run_jacobi_oddeven_cluster(float* A, int ld, int n, float* inbox, uint64_t* bars, int* flags, int* nsweeps) {
+    const int chunks = (ld + JAC_CHUNK_ROWS - 1) / JAC_CHUNK_ROWS;
+    switch (chunks) {
+        case 1: *nsweeps = jacobi_orthogonalize_oddeven_cluster<1>(A, ld, n, kJacobiTol, kJacobiMaxSweeps, inbox, bars, flags); return true;
+        case 2: *nsweeps = jacobi_orthogonalize_oddeven_cluster<2>(A, ld, n, kJacobiTol, kJacobiMaxSweeps, inbox, bars, flags); return true;
+        case 3: *nsweeps = jacobi_orthogonalize_oddeven_cluster<3>(A, ld, n, kJacobiTol, kJacobiMaxSweeps, inbox, bars, flags); return true;
+        case 4: *nsweeps = jacobi_orthogonalize_oddeven_cluster<4>(A, ld, n, kJacobiTol, kJacobiMaxSweeps, inbox, bars, flags); return true;
+        case 5: *nsweeps = jacobi_orthogonalize_oddeven_cluster<5>(A, ld, n, kJacobiTol, kJacobiMaxSweeps, inbox, bars, flags); return true;
+        case 6: *nsweeps = jacobi_orthogonalize_oddeven_cluster<6>(A, ld, n, kJacobiTol, kJacobiMaxSweeps, inbox, bars, flags); return true;
+        default: return false;                             // 7-8 chunks (n > 192) would spill at 80 registers per thread
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
-// pooled_eig_kernel: one CTA per symmetric problem of size n = Ds.
+// pooled_eig_kernel: one CLUSTER of kPooledCluster CTAs per symmetric problem of size n = Ds.  Rank 0 of the cluster
+// holds the matrix and runs every phase; the other ranks only take their share of the Jacobi pairs (jacobi.cuh).
 //   problem p in [0, Lt)        : MP rank of teacher layer p   (uncentred G / M)
 //   problem p in [Lt, 2Lt)      : centred eigen-decomposition of teacher layer p - Lt
 //   problem p in [2Lt, 2Lt + P) : centred eigen-decomposition of student extraction point p - 2Lt
@@ -63,6 +78,7 @@ __device__ __forceinline__ int run_jacobi_oddeven(float* A, int ld, int n) {
 // 28 pooled problems): 16-lane groups / two passes 5.6, this 4.6, 384 threads with two pairs in flight per group 5.4,
 // block-2 ordering (four columns per 16-lane group, half the shared-memory round trips) 5.0.
 constexpr int kPooledThreads = 768;
+constexpr int kPooledCluster = 4;           // 28 problems x 4 = 112 of the 148 SMs
 __global__ void __launch_bounds__(kPooledThreads, 1)
 pooled_eig_kernel(const float* __restrict__ stats, int n, int Lt, int P, float M_teacher, float M_student,
                   int* __restrict__ ranks, float* __restrict__ evals, float* __restrict__ evecs_km,
@@ -73,19 +89,25 @@ pooled_eig_kernel(const float* __restrict__ stats, int n, int Lt, int P, float M
     float* vals = A + static_cast<size_t>(ld) * n;
     float* csum = vals + n;
     int* order = reinterpret_cast<int*>(csum + n);
+    float* inbox = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(order + n + 64) + 15) & ~uintptr_t(15));   // one column (Jacobi across CTAs)
     __shared__ int s_count;
+    __shared__ int s_flags[16];
+    __shared__ __align__(8) uint64_t s_bars[2];
+    __shared__ int s_bad;
 
-    const int p = blockIdx.x;
+    const int crank = static_cast<int>(cooperative_groups::this_cluster().block_rank());
+    const int p = blockIdx.x / static_cast<int>(cooperative_groups::this_cluster().num_blocks());
     const bool mp_mode = p < Lt;
     const int gram_idx = mp_mode ? p : (p - Lt);                  // index into stats (teacher 0..Lt-1, student Lt..)
     const float Mrows = gram_idx < Lt ? M_teacher : M_student;
     const float* G = stats + static_cast<size_t>(gram_idx) * (n * n + n);
     const float* cs = G + n * n;
-
+    const float invM = 1.f / Mrows;
+    bool use_chol = false;
+    if (crank == 0) {
     for (int i = threadIdx.x; i < n; i += blockDim.x) csum[i] = cs[i];
     if (threadIdx.x == 0) s_count = 0;
     __syncthreads();
-    const float invM = 1.f / Mrows;
     for (int t = threadIdx.x; t < ld * n; t += blockDim.x) {
         const int c = t / ld, r = t % ld;
         float v = 0.f;
@@ -101,7 +123,6 @@ pooled_eig_kernel(const float* __restrict__ stats, int n, int Lt, int P, float M
     // singular values of L are the square roots of the eigenvalues (half the condition number in digits), the rotated
     // columns L V = U Sigma are still sigma_i times the eigenvectors of G, and the sweep count roughly halves.
     // A non-positive pivot (numerically singular Gram) falls back to Jacobi on G itself.
-    __shared__ int s_bad;
     if (threadIdx.x == 0) s_bad = 0;
     __syncthreads();
     float dmax = 0.f;
@@ -113,7 +134,7 @@ pooled_eig_kernel(const float* __restrict__ stats, int n, int Lt, int P, float M
     for (int wv = 0; wv < (blockDim.x >> 5); ++wv) dmax = fmaxf(dmax, vals[wv]);
     __syncthreads();
     cta_cholesky_lower(A, ld, n, &s_bad, 1e-6f * dmax);       // pivots below 1e-6 of the largest diagonal: not trusted in fp32
-    const bool use_chol = s_bad == 0;
+    use_chol = s_bad == 0;
     if (!use_chol) {                       // rebuild G from the statistics
         for (int t = threadIdx.x; t < ld * n; t += blockDim.x) {
             const int c = t / ld, r = t % ld;
@@ -126,8 +147,15 @@ pooled_eig_kernel(const float* __restrict__ stats, int n, int Lt, int P, float M
         }
     }
     __syncthreads();
-    const bool oddeven_ok = (n % 2 == 0) && (n / 2 <= static_cast<int>(blockDim.x) / JAC_GROUP);
-    const int nsweeps = oddeven_ok ? run_jacobi_oddeven(A, ld, n) : run_jacobi<false>(A, ld, n);
+    }   // crank == 0
+    jac_cluster_sync();                     // the matrix is ready in rank 0's shared memory
+    int nsweeps = 0;
+    const int groups_per_cta = ((n + 1) / 2 + kPooledCluster - 1) / kPooledCluster;
+    const bool cluster_ok = static_cast<int>(cooperative_groups::this_cluster().num_blocks()) == kPooledCluster &&
+                            groups_per_cta * JAC_GROUP <= static_cast<int>(blockDim.x) &&
+                            run_jacobi_oddeven_cluster(A, ld, n, inbox, s_bars, s_flags, &nsweeps);      // uniform over the cluster
+    if (crank != 0) return;                 // (the Jacobi routine ends with a cluster barrier: nobody touches this CTA again)
+    if (!cluster_ok) nsweeps = run_jacobi<false>(A, ld, n);
     column_norms(A, ld, n, n, vals);        // sigma_i (Cholesky route) or lambda_i (fallback)
     __syncthreads();
     if (use_chol)
@@ -357,7 +385,7 @@ selector_bwd_kernel(int n, int Lt, int P, const float* __restrict__ gw_raw, cons
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
-static size_t pooled_smem(int n) { return (static_cast<size_t>(jacobi_ld(n)) * n + 3 * n + 64) * sizeof(float); }
+static size_t pooled_smem(int n) { return (static_cast<size_t>(jacobi_ld(n)) * n + 3 * n + 64 + jacobi_ld(n) + 8) * sizeof(float); }
 static size_t angles_smem(int n) { return (static_cast<size_t>(jacobi_ld(n - 1)) * (n - 1) + 3 * n + 128) * sizeof(float); }
 
 cudaError_t launch_pooled_eig(const float* stats, int n, int Lt, int P, float Mt, float Ms, int* ranks, float* evals,
@@ -365,8 +393,18 @@ cudaError_t launch_pooled_eig(const float* stats, int n, int Lt, int P, float Mt
     const size_t smem = pooled_smem(n);
     cudaError_t e = cudaFuncSetAttribute(pooled_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    pooled_eig_kernel<<<2 * Lt + P, kPooledThreads, smem, st>>>(stats, n, Lt, P, Mt, Ms, ranks, evals, evecs_km, evecs_cm, sweeps);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((2 * Lt + P) * kPooledCluster);
+    cfg.blockDim = dim3(kPooledThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = kPooledCluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, pooled_eig_kernel, stats, n, Lt, P, Mt, Ms, ranks, evals, evecs_km, evecs_cm, sweeps);
 }
 
 cudaError_t launch_angles(int n, int Lt, int P, const int* ranks, const float* evals, const float* evecs_km,
