@@ -25,3 +25,19 @@ for n in (36, 50, 64, 100, 192):
     print(f"n={n}: bitwise identical over 12 launches: {same}; sweeps {sorted(set(o[2] for o in outs))}; "
           f"eval err {((outs[0][0].double() - ref).abs().max() / ref.max()).item():.2e}; "
           f"orth {(V @ V.T - torch.eye(n, dtype=torch.float64)).abs().max().item():.2e}")
+
+for n in (48, 96, 192):
+    # time per launch (one problem = one cluster) -> cycles per pair-step
+    torch.manual_seed(n)
+    X = torch.randn(4 * n, n) * (0.97 ** torch.arange(n)); G = (X.T @ X).to(dev)
+    ev = torch.zeros(n, device=dev); evec = torch.zeros(n, n, device=dev); sw = torch.zeros(4, dtype=torch.int32, device=dev)
+    ws = torch.zeros(4 * (2 * n * n + n) + 8192, dtype=torch.uint8, device=dev)
+    for _ in range(3): lib.basd_selftest_eig(G.data_ptr(), n, ev.data_ptr(), evec.data_ptr(), sw.data_ptr(), ws.data_ptr(), st)
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20): lib.basd_selftest_eig(G.data_ptr(), n, ev.data_ptr(), evec.data_ptr(), sw.data_ptr(), ws.data_ptr(), st)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 20
+    steps = sw[0].item() * n // 2
+    print(f"cluster={os.environ.get('BASD_EIG_CLUSTER', 'default')}: {ms*1e3:.0f} us per launch, {sw[0].item()} sweeps, {steps} pair-steps -> {ms*1e-3*1.965e9/steps:.0f} cycles per pair-step (all phases included)")
+    print("phase cycles (pre-Jacobi, Jacobi, norms+sort):", [v * 16 for v in sw[1:4].tolist()])

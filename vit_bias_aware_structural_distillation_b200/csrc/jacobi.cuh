@@ -125,24 +125,40 @@ __device__ int jacobi_orthogonalize(float* __restrict__ A, int ld, int n_cols, f
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Odd-even variant with register-resident columns (for the big pooled problems).
+// Odd-even variant with register-resident columns, spread over a thread-block CLUSTER (the big pooled problems).
 // Positions 0..n-1 hold the columns; group g owns positions 2g (registers P) and 2g+1 (registers Q).  A sweep is n
 // steps of the odd-even transposition network, every step followed by a swap of the two columns it paired, so that
 // after n steps every pair of columns has met exactly once:
 //   even step : rotate (P, Q) in registers - no shared memory, no barrier;
 //   odd step  : positions (2g+1, 2g+2): group g keeps its odd column, borrows the even column of group g+1 through
 //               that group's mailbox (column 2g+2 of A), rotates, keeps the borrowed one and mails the other back.
-// Shared-memory traffic and barriers per step are half of the round-robin version above (which streams both columns of
-// every pair through shared memory every step and is bound by exactly that).
-// Requires an even n and n/2 <= blockDim.x / 8 groups.  Column ORDER on exit is a permutation of the input order
-// (irrelevant to the callers, which sort by eigenvalue).  Measured on the 28 pooled 192 x 192 problems: 4.1 ms against
-// 4.7 for the round-robin version; exchanging the three in-warp neighbours by shuffle instead of through the mailboxes
-// was slower again (4.7: 48 shuffles per lane per odd step cost more issue slots than the shared-memory traffic saved).
+// The n/2 groups are dealt to the CTAs of the cluster in contiguous runs, so one SM issues the instructions and carries
+// the shared-memory traffic of n/(2C) pairs.  Inside a CTA the two barriers per pair-step are a named barrier over the
+// warps that hold groups.  Across a CTA boundary (last group g of CTA k, first group g+1 of CTA k+1) the exchange is
+// pushed through distributed shared memory with st.async, which credits an mbarrier of the RECEIVING CTA with the bytes
+// it delivered:
+//   group g+1 pushes its even column into CTA k's inbox   -> bar_in  of CTA k   (instead of mailing it locally)
+//   group g   rotates against the inbox and pushes the column that moves on into group g+1's mailbox -> bar_back of CTA k+1
+// so no cluster-wide barrier sits in the pair-step (barrier.cluster with release/acquire compiles to MEMBAR.ALL.GPU +
+// CCTL.IVALL; with two of them per pair-step the cluster version was slower than one CTA).
+// The matrix lives in the shared memory of cluster rank 0 (same offset `A` in every CTA); the other CTAs use their own
+// copy of that region for mailboxes only.  One cluster barrier per sweep ORs the convergence flags.
+//
+// The pair-step is a dependent chain (measured ~1.8k cycles with six warps on an SM, whatever the column length), so
+// the chain is what the code below shortens:
+//  * every lane of a warp runs the same instruction stream (inactive groups rotate zero columns; memory operations are
+//    predicated), so the 8-lane reductions are full-mask shuffles - with per-group masks the compiler routes every
+//    shuffle through a divergent WARPSYNC.COLLECTIVE path that serialises the four groups of the warp;
+//  * the rotation comes from d = beta - alpha, h = 2 gamma through two dependent rsqrt (cos 2theta = |d| / hypot(d, h)),
+//    not from the five-MUFU tan(theta) chain, is computed speculatively and discarded if the pair is already orthogonal;
+//  * packed fp32 (FFMA2 / FMUL2) for the dot products and the rotation.
+// Column ORDER on exit is a permutation of the input order (irrelevant to the callers, which sort by eigenvalue).
+// Measured on the 28 pooled 192 x 192 problems of cfg2 (ms): round-robin 4.7, odd-even on one CTA 4.1, + packed fp32
+// 3.8, 4-CTA cluster 2.8; exchanging in-warp neighbours by shuffle instead of mailboxes was slower (4.7).
+// All threads of all CTAs of the cluster must call it; returns the sweep count (identical in every CTA).
+// inbox: ld floats, bars: 2 mbarriers, flags: 16 ints - shared memory at the same offsets in every CTA.
 // ------------------------------------------------------------------------------------------------------------------
-// Packed fp32 arithmetic (sm_100 FFMA2 / FMUL2: two fp32 lanes per instruction).  The kernel is bound by instruction
-// issue between barriers, so the columns live in registers as row PAIRS and every dot product / rotation instruction
-// handles two rows.
-using jac_f2 = unsigned long long;
+using jac_f2 = unsigned long long;          // two fp32 lanes (sm_100 FFMA2 / FMUL2 operands)
 __device__ __forceinline__ jac_f2 jac_pack(float lo, float hi) {
     jac_f2 r;
     asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
@@ -163,40 +179,50 @@ __device__ __forceinline__ jac_f2 jac_mul2(jac_f2 a, jac_f2 b) {
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
+__device__ __forceinline__ jac_f2 jac_add2(jac_f2 a, jac_f2 b) {
+    jac_f2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
 __device__ __forceinline__ float jac_sqrt_approx(float x) {
     float r;
     asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-__device__ __forceinline__ float jac_rcp_approx(float x) {
-    float r;
-    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
+// rsqrt with one Newton step: the rotation's cs^2 + sn^2 = 1 rests on it, and the 2-ulp MUFU result alone lets the
+// column norms (= the eigenvalues) drift by a random walk of ~3e-7 per rotation over ~2000 rotations per column
+__device__ __forceinline__ float jac_rsqrt_refined(float x) {
+    const float r = rsqrtf(x);
+    return r * fmaf(-0.5f * x, r * r, 1.5f);
 }
+// One rotation of the column pairs held by the four 8-lane groups of this warp.  ALL 32 lanes must call it together.
 template <int CHUNKS>
-__device__ __forceinline__ int jac_rotate_regs(ulonglong2 (&x)[CHUNKS], ulonglong2 (&y)[CHUNKS], unsigned gmask, float tol) {
-    jac_f2 al2 = 0ull, be2 = 0ull, ga2 = 0ull;            // 0ull = (+0.f, +0.f)
+__device__ __forceinline__ int jac_rotate_regs(ulonglong2 (&x)[CHUNKS], ulonglong2 (&y)[CHUNKS], float tol) {
+    jac_f2 al2 = 0ull, be2 = 0ull, ga2 = 0ull, al2b = 0ull, be2b = 0ull, ga2b = 0ull;      // 0ull = (+0.f, +0.f)
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) {
-        al2 = jac_fma2(x[c].x, x[c].x, jac_fma2(x[c].y, x[c].y, al2));
-        be2 = jac_fma2(y[c].x, y[c].x, jac_fma2(y[c].y, y[c].y, be2));
-        ga2 = jac_fma2(x[c].x, y[c].x, jac_fma2(x[c].y, y[c].y, ga2));
+        al2 = jac_fma2(x[c].x, x[c].x, al2); al2b = jac_fma2(x[c].y, x[c].y, al2b);
+        be2 = jac_fma2(y[c].x, y[c].x, be2); be2b = jac_fma2(y[c].y, y[c].y, be2b);
+        ga2 = jac_fma2(x[c].x, y[c].x, ga2); ga2b = jac_fma2(x[c].y, y[c].y, ga2b);
     }
-    float al = jac_hsum(al2), be = jac_hsum(be2), ga = jac_hsum(ga2);
+    float al = jac_hsum(jac_add2(al2, al2b)), be = jac_hsum(jac_add2(be2, be2b)), ga = jac_hsum(jac_add2(ga2, ga2b));
 #pragma unroll
     for (int o = JAC_GROUP / 2; o > 0; o >>= 1) {
-        al += __shfl_xor_sync(gmask, al, o);
-        be += __shfl_xor_sync(gmask, be, o);
-        ga += __shfl_xor_sync(gmask, ga, o);
+        al += __shfl_xor_sync(0xffffffffu, al, o);
+        be += __shfl_xor_sync(0xffffffffu, be, o);
+        ga += __shfl_xor_sync(0xffffffffu, ga, o);
     }
-    // MUFU approximations (2 ulp) instead of IEEE sqrt / divide with their slow-path calls: an error in t only leaves a
-    // residual of relative size 1e-7 in the annihilated entry (the next sweep removes it); orthogonality of the
-    // rotation rests on cs, sn alone, as before.  Overflow of zeta^2 gives sqrt = inf, t = 0: no rotation.
-    if (!(fabsf(ga) > tol * jac_sqrt_approx(al * be))) return 0;
-    const float zeta = (be - al) * jac_rcp_approx(2.f * ga);
-    const float t = copysignf(jac_rcp_approx(fabsf(zeta) + jac_sqrt_approx(fmaf(zeta, zeta, 1.f))), zeta);
-    const float cs = rsqrtf(fmaf(t, t, 1.f));
-    const float sn = cs * t;
+    // |theta| <= pi/4 with tan 2theta = h / d:  cos 2theta = |d| / r,  sin 2theta = sign(d) h / r,  r = hypot(d, h)
+    const float d = be - al, h = ga + ga;
+    const float r2 = fmaf(d, d, h * h);
+    const float rinv = jac_rsqrt_refined(r2);
+    const float y2 = fmaf(0.5f * fabsf(d), rinv, 0.5f);               // cos^2 theta, in [0.5, 1]
+    const float icy = jac_rsqrt_refined(y2);
+    const float sn_abs = 0.5f * h * rinv * icy;                       // sin 2theta / (2 cos theta), sign of h
+    // (off the chain) already orthogonal, or d^2 + h^2 outside the fp32 range: leave the pair alone
+    const bool rot = fabsf(ga) > tol * jac_sqrt_approx(al * be) && r2 > 1e-36f && r2 < 1e36f;
+    const float cs = rot ? y2 * icy : 1.f;
+    const float sn = rot ? (d < 0.f ? -sn_abs : sn_abs) : 0.f;
     const jac_f2 cs2 = jac_pack(cs, cs), sn2 = jac_pack(sn, sn), nsn2 = jac_pack(-sn, -sn);
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) {
@@ -205,8 +231,9 @@ __device__ __forceinline__ int jac_rotate_regs(ulonglong2 (&x)[CHUNKS], ulonglon
         xn.y = jac_fma2(cs2, x[c].y, jac_mul2(nsn2, y[c].y)); yn.y = jac_fma2(sn2, x[c].y, jac_mul2(cs2, y[c].y));
         x[c] = xn; y[c] = yn;
     }
-    return 1;
+    return rot ? 1 : 0;
 }
+// generic-pointer column load / store (initial load from and final store to cluster rank 0)
 template <int CHUNKS>
 __device__ __forceinline__ void jac_ld(const float* __restrict__ col, int ld, int gl, bool valid, ulonglong2 (&v)[CHUNKS]) {
 #pragma unroll
@@ -224,76 +251,25 @@ __device__ __forceinline__ void jac_st(float* __restrict__ col, int ld, int gl, 
         if (r < ld) *reinterpret_cast<ulonglong2*>(col + r) = v[c];
     }
 }
-
+// the same on 32-bit shared-memory addresses of this CTA (the mailboxes; predicated, no branch around the warp)
 template <int CHUNKS>
-__device__ int jacobi_orthogonalize_oddeven(float* __restrict__ A, int ld, int n_cols, float tol, int max_sweeps) {
-    const int n = (n_cols + 1) & ~1;
-    const int m = n / 2;                                    // groups needed
-    const int g = threadIdx.x / JAC_GROUP;
-    const int gl = threadIdx.x % JAC_GROUP;
-    const unsigned gmask = 0xFFu << (threadIdx.x & 24);
-    const bool active = g < m;
-    const bool q_real = active && (2 * g + 1 < n_cols);     // the virtual last column of an odd n_cols is all zeros
-    const bool has_next = active && g + 1 < m;              // an odd-step partner exists
-    const bool next_real = has_next;                        // column 2g+2 < n_cols always holds when g+1 < m
-    float* colP = A + static_cast<size_t>(active ? 2 * g : 0) * ld;          // own mailbox = own even column
-    float* colQ = A + static_cast<size_t>(q_real ? 2 * g + 1 : 0) * ld;
-    float* colN = A + static_cast<size_t>(has_next ? 2 * g + 2 : 0) * ld;    // mailbox of group g+1
-    ulonglong2 P[CHUNKS], Q[CHUNKS];
-    jac_ld<CHUNKS>(colP, ld, gl, active, P);
-    jac_ld<CHUNKS>(colQ, ld, gl, q_real, Q);
-    __syncthreads();
-    int sweep = 0;
-    if (n_cols < 2) return 0;
-    for (; sweep < max_sweeps; ++sweep) {
-        int rotated = 0;
-        for (int pairstep = 0; pairstep < m; ++pairstep) {
-            // even step: positions (2g, 2g+1) = (P, Q); afterwards position 2g holds Q, position 2g+1 holds P
-            if (active) rotated |= jac_rotate_regs<CHUNKS>(P, Q, gmask, tol);
-            // odd step: positions (2g+1, 2g+2) = (P, even column of group g+1)
-            jac_st<CHUNKS>(colP, ld, gl, active, Q);        // mail own position-2g column (held in Q)
-            __syncthreads();
-            if (has_next) {
-                jac_ld<CHUNKS>(colN, ld, gl, next_real, Q); // borrow position 2g+2
-                rotated |= jac_rotate_regs<CHUNKS>(P, Q, gmask, tol);
-                jac_st<CHUNKS>(colN, ld, gl, true, P);      // rotated old 2g+1 goes to position 2g+2; Q stays as position 2g+1
-            }
-            __syncthreads();
-            if (has_next) {
-                jac_ld<CHUNKS>(colP, ld, gl, active, P);    // new position 2g from the mailbox; (P, Q) = (2g, 2g+1) again
-            } else if (active) {
-                // last group: its odd column (in P) was idle; restore the roles (P, Q) = (2g, 2g+1) with a register swap
+__device__ __forceinline__ void jac_lds(uint32_t col, int ld, int gl, bool valid, ulonglong2 (&v)[CHUNKS]) {
 #pragma unroll
-                for (int c = 0; c < CHUNKS; ++c) { const ulonglong2 t = P[c]; P[c] = Q[c]; Q[c] = t; }
-                jac_ld<CHUNKS>(colP, ld, gl, true, P);      // (its own mailbox may have been rewritten by group g-1)
-            }
-        }
-        if (!__syncthreads_or(rotated)) { ++sweep; break; }
+    for (int c = 0; c < CHUNKS; ++c) {
+        const int r = c * JAC_CHUNK_ROWS + gl * 4;
+        ulonglong2 t = make_ulonglong2(0ull, 0ull);
+        if (valid && r < ld) asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(t.x), "=l"(t.y) : "r"(col + r * 4) : "memory");
+        v[c] = t;
     }
-    __syncthreads();
-    jac_st<CHUNKS>(colP, ld, gl, active, P);
-    jac_st<CHUNKS>(colQ, ld, gl, q_real, Q);
-    __syncthreads();
-    return sweep;
 }
-
-// ------------------------------------------------------------------------------------------------------------------
-// The same odd-even network spread over a thread-block CLUSTER: the n/2 groups are dealt to the CTAs of the cluster in
-// contiguous runs, so one SM issues the instructions and carries the shared-memory traffic of n/(2C) pairs instead of
-// n/2 (with all 96 pairs of an n = 192 problem on one SM a pair-step cost ~6.6k cycles, four times its dependent
-// latency chain: six warps per scheduler and 295 KB of shared-memory traffic per pair-step).
-// Inside a CTA nothing changes except that the two barriers per pair-step are a named barrier over the active warps.
-// Across a CTA boundary (last group g of CTA k, first group g+1 of CTA k+1) the column exchange is pushed through
-// distributed shared memory with st.async, which signals an mbarrier of the RECEIVING CTA with the bytes it delivered:
-//   group g+1 pushes its even column into CTA k's inbox   -> bar_in  of CTA k   (instead of mailing it locally)
-//   group g   rotates against the inbox and pushes the column that moves on into group g+1's mailbox -> bar_back of CTA k+1
-// so no cluster-wide barrier sits in the pair-step (barrier.cluster with release/acquire compiles to MEMBAR.ALL.GPU +
-// CCTL.IVALL and made the cluster version slower than one CTA: measured 4.07 against 3.79 ms).
-// The matrix lives in the shared memory of cluster rank 0 (same offset `A` in every CTA); the other CTAs use their own
-// copy of that region for mailboxes only.  One cluster barrier per sweep ORs the convergence flags.
-// All threads of all CTAs of the cluster must call it; returns the sweep count (identical in every CTA).
-// inbox: ld floats, bars: 2 mbarriers, flags: 16 ints - shared memory at the same offsets in every CTA.
-// ------------------------------------------------------------------------------------------------------------------
+template <int CHUNKS>
+__device__ __forceinline__ void jac_sts(uint32_t col, int ld, int gl, bool valid, const ulonglong2 (&v)[CHUNKS]) {
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+        const int r = c * JAC_CHUNK_ROWS + gl * 4;
+        if (valid && r < ld) asm volatile("st.shared.v2.u64 [%0], {%1, %2};" ::"r"(col + r * 4), "l"(v[c].x), "l"(v[c].y) : "memory");
+    }
+}
 __device__ __forceinline__ void jac_cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -309,17 +285,14 @@ __device__ __forceinline__ void jac_st_async(uint32_t raddr, ulonglong2 v, uint3
                  : "memory");
 }
 template <int CHUNKS>
-__device__ __forceinline__ void jac_push(uint32_t rcol, uint32_t rbar, int ld, int gl, const ulonglong2 (&v)[CHUNKS]) {
+__device__ __forceinline__ void jac_push(uint32_t rcol, uint32_t rbar, int ld, int gl, bool valid, const ulonglong2 (&v)[CHUNKS]) {
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) {
         const int r = c * JAC_CHUNK_ROWS + gl * 4;
-        if (r < ld) jac_st_async(rcol + r * 4, v[c], rbar);
+        if (valid && r < ld) jac_st_async(rcol + r * 4, v[c], rbar);
     }
 }
-__device__ __forceinline__ void jac_bar_active(int nthreads) {
-    __syncwarp();                                           // (8-lane groups of a warp take different branches)
-    asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
-}
+__device__ __forceinline__ void jac_bar_active(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 
 template <int CHUNKS>
 __device__ int jacobi_orthogonalize_oddeven_cluster(float* __restrict__ A, int ld, int n_cols, float tol, int max_sweeps, float* inbox,
@@ -334,11 +307,11 @@ __device__ int jacobi_orthogonalize_oddeven_cluster(float* __restrict__ A, int l
     const int gloc = threadIdx.x / JAC_GROUP;
     const int gl = threadIdx.x % JAC_GROUP;
     const int g = crank * gpc + gloc;
-    const unsigned gmask = 0xFFu << (threadIdx.x & 24);
     const bool active = gloc < gpc && g < m;
-    const bool q_real = active && (2 * g + 1 < n_cols);
-    const bool has_next = active && g + 1 < m;
-    const bool next_remote = has_next && gloc == gpc - 1;   // the odd-step partner lives in CTA crank + 1
+    const bool q_real = active && (2 * g + 1 < n_cols);     // the virtual last column of an odd n_cols is all zeros
+    const bool has_next = active && g + 1 < m;              // an odd-step partner exists
+    const bool next_remote = has_next && gloc == gpc - 1;   // ... and lives in CTA crank + 1
+    const bool next_local = has_next && !next_remote;
     const bool prev_remote = active && gloc == 0 && crank > 0;   // this group is such a partner for CTA crank - 1
     uint64_t* bar_in = bars;                                // credited by group g+1's pushes into `inbox`
     uint64_t* bar_back = bars + 1;                          // credited by group g-1's pushes into this group's mailbox
@@ -348,12 +321,13 @@ __device__ int jacobi_orthogonalize_oddeven_cluster(float* __restrict__ A, int l
         fence_mbar_init();
     }
     float* A0 = cluster.map_shared_rank(A, 0);                                           // the matrix itself
-    float* colP = A + static_cast<size_t>(active ? 2 * g : 0) * ld;                      // own mailbox (local)
-    float* colN = A + static_cast<size_t>(has_next && !next_remote ? 2 * g + 2 : 0) * ld;    // mailbox of a local group g+1
-    // remote addresses (shared::cluster window)
+    const uint32_t a_s = smem_u32(A);
+    const uint32_t colP = a_s + static_cast<uint32_t>(active ? 2 * g : 0) * ld * 4;      // own mailbox = own even column slot
+    const uint32_t colN = next_remote ? smem_u32(inbox) : a_s + static_cast<uint32_t>(next_local ? 2 * g + 2 : 0) * ld * 4;
+    // addresses in the shared::cluster window of the neighbouring CTAs
     const uint32_t r_inbox = jac_mapa(smem_u32(inbox), prev_remote ? crank - 1 : crank);
     const uint32_t r_bar_in = jac_mapa(smem_u32(bar_in), prev_remote ? crank - 1 : crank);
-    const uint32_t r_mail = jac_mapa(smem_u32(A + static_cast<size_t>(next_remote ? 2 * g + 2 : 0) * ld), next_remote ? crank + 1 : crank);
+    const uint32_t r_mail = jac_mapa(a_s + static_cast<uint32_t>(next_remote ? 2 * g + 2 : 0) * ld * 4, next_remote ? crank + 1 : crank);
     const uint32_t r_bar_back = jac_mapa(smem_u32(bar_back), next_remote ? crank + 1 : crank);
     const uint32_t col_bytes = static_cast<uint32_t>(ld) * 4u;
     ulonglong2 P[CHUNKS], Q[CHUNKS];
@@ -372,31 +346,26 @@ __device__ int jacobi_orthogonalize_oddeven_cluster(float* __restrict__ A, int l
                         if (prev_remote) mbar_arrive_expect_tx(bar_back, col_bytes);
                     }
                     // even step: positions (2g, 2g+1) = (P, Q); afterwards position 2g holds Q, position 2g+1 holds P
-                    if (active) rotated |= jac_rotate_regs<CHUNKS>(P, Q, gmask, tol);
-                    if (prev_remote) jac_push<CHUNKS>(r_inbox, r_bar_in, ld, gl, Q);      // to the last group of the previous CTA
-                    else jac_st<CHUNKS>(colP, ld, gl, active, Q);                         // mail own position-2g column
+                    rotated |= jac_rotate_regs<CHUNKS>(P, Q, tol);
+                    jac_push<CHUNKS>(r_inbox, r_bar_in, ld, gl, prev_remote, Q);          // to the last group of the previous CTA, or
+                    jac_sts<CHUNKS>(colP, ld, gl, active && !prev_remote, Q);             // mail own position-2g column locally
                     jac_bar_active(n_active);
-                    // odd step: positions (2g+1, 2g+2) = (P, even column of group g+1)
-                    if (next_remote) {
-                        mbar_wait(bar_in, phase);
-                        jac_ld<CHUNKS>(inbox, ld, gl, true, Q);
-                        rotated |= jac_rotate_regs<CHUNKS>(P, Q, gmask, tol);
-                        jac_push<CHUNKS>(r_mail, r_bar_back, ld, gl, P);
-                    } else if (has_next) {
-                        jac_ld<CHUNKS>(colN, ld, gl, true, Q);
-                        rotated |= jac_rotate_regs<CHUNKS>(P, Q, gmask, tol);
-                        jac_st<CHUNKS>(colN, ld, gl, true, P);
-                    }
+                    // odd step: positions (2g+1, 2g+2) = (P, even column of group g+1); groups without a partner rotate
+                    // against a zero column (a no-op) to keep the warp converged
+                    if (next_remote) mbar_wait(bar_in, phase);
+                    __syncwarp();
+                    jac_lds<CHUNKS>(colN, ld, gl, has_next, Q);
+                    rotated |= jac_rotate_regs<CHUNKS>(P, Q, tol);
+                    jac_push<CHUNKS>(r_mail, r_bar_back, ld, gl, next_remote, P);         // rotated old 2g+1 moves on to position 2g+2;
+                    jac_sts<CHUNKS>(colN, ld, gl, next_local, P);                         // Q stays as position 2g+1
                     jac_bar_active(n_active);
                     if (prev_remote) mbar_wait(bar_back, phase);
-                    if (has_next) {
-                        jac_ld<CHUNKS>(colP, ld, gl, true, P);   // new position 2g from the mailbox; (P, Q) = (2g, 2g+1) again
-                    } else if (active) {
-                        // last group of all: its odd column (in P) was idle; restore the roles with a register swap
+                    __syncwarp();
+                    if (!has_next) {                        // last group of all: its odd column (in P) was idle
 #pragma unroll
-                        for (int c = 0; c < CHUNKS; ++c) { const ulonglong2 t = P[c]; P[c] = Q[c]; Q[c] = t; }
-                        jac_ld<CHUNKS>(colP, ld, gl, true, P);
+                        for (int c = 0; c < CHUNKS; ++c) Q[c] = P[c];
                     }
+                    jac_lds<CHUNKS>(colP, ld, gl, active, P);   // new position 2g from the mailbox; (P, Q) = (2g, 2g+1) again
                 }
             }
             // did any CTA of the cluster rotate in this sweep?  (flags double-buffered by sweep parity)

@@ -8,6 +8,8 @@
 #include "spectral.h"
 
 #include <math_constants.h>
+#include <cstdlib>
+#include <cstring>
 
 #include "cta_linalg.cuh"
 #include "jacobi.cuh"
@@ -38,21 +40,8 @@ __device__ __forceinline__ int run_jacobi(float* A, int ld, int n) {
     }
 }
 
-// odd-even ordering with register-resident columns (jacobi.cuh); needs an even column count and n/2 <= 96 groups
-__device__ __forceinline__ int run_jacobi_oddeven(float* A, int ld, int n) {
-    const int chunks = (ld + JAC_CHUNK_ROWS - 1) / JAC_CHUNK_ROWS;
-    switch (chunks) {
-        case 1: return jacobi_orthogonalize_oddeven<1>(A, ld, n, kJacobiTol, kJacobiMaxSweeps);
-        case 2: return jacobi_orthogonalize_oddeven<2>(A, ld, n, kJacobiTol, kJacobiMaxSweeps);
-        case 3: return jacobi_orthogonalize_oddeven<3>(A, ld, n, kJacobiTol, kJacobiMaxSweeps);
-        case 4: return jacobi_orthogonalize_oddeven<4>(A, ld, n, kJacobiTol, kJacobiMaxSweeps);
-        case 5: return jacobi_orthogonalize_oddeven<5>(A, ld, n, kJacobiTol, kJacobiMaxSweeps);
-        case 6: return jacobi_orthogonalize_oddeven<6>(A, ld, n, kJacobiTol, kJacobiMaxSweeps);
-        default: return run_jacobi<false>(A, ld, n);       // 7-8 chunks (n > 192) would spill at 80 registers per thread
-    }
-}
-
-// the same over the CTAs of the cluster (all CTAs call; false = shape not supported, nothing done)
+// odd-even ordering with register-resident columns over the CTAs of the cluster (jacobi.cuh); all CTAs call;
+// false = shape not supported, nothing done
 __device__ __forceinline__ bool run_jacobi_oddeven_cluster(float* A, int ld, int n, float* inbox, uint64_t* bars, int* flags, int* nsweeps) {
     const int chunks = (ld + JAC_CHUNK_ROWS - 1) / JAC_CHUNK_ROWS;
     switch (chunks) {
@@ -62,7 +51,9 @@ __device__ __forceinline__ bool run_jacobi_oddeven_cluster(float* A, int ld, int
         case 4: *nsweeps = jacobi_orthogonalize_oddeven_cluster<4>(A, ld, n, kJacobiTol, kJacobiMaxSweeps, inbox, bars, flags); return true;
         case 5: *nsweeps = jacobi_orthogonalize_oddeven_cluster<5>(A, ld, n, kJacobiTol, kJacobiMaxSweeps, inbox, bars, flags); return true;
         case 6: *nsweeps = jacobi_orthogonalize_oddeven_cluster<6>(A, ld, n, kJacobiTol, kJacobiMaxSweeps, inbox, bars, flags); return true;
-        default: return false;                             // 7-8 chunks (n > 192) would spill at 80 registers per thread
+        case 7: *nsweeps = jacobi_orthogonalize_oddeven_cluster<7>(A, ld, n, kJacobiTol, kJacobiMaxSweeps, inbox, bars, flags); return true;
+        case 8: *nsweeps = jacobi_orthogonalize_oddeven_cluster<8>(A, ld, n, kJacobiTol, kJacobiMaxSweeps, inbox, bars, flags); return true;
+        default: return false;
     }
 }
 
@@ -74,10 +65,10 @@ __device__ __forceinline__ bool run_jacobi_oddeven_cluster(float* A, int ld, int
 //   problem p in [2Lt, 2Lt + P) : centred eigen-decomposition of student extraction point p - 2Lt
 // stats layout: [(Lt + P)][n*n + n]  (Gram row-major, then column sums)
 // ------------------------------------------------------------------------------------------------
-// 96 eight-lane groups = the 96 pairs of an n = 192 step in one pass.  Measured alternatives on B200 (cfg2, ms for the
-// 28 pooled problems): 16-lane groups / two passes 5.6, this 4.6, 384 threads with two pairs in flight per group 5.4,
-// block-2 ordering (four columns per 16-lane group, half the shared-memory round trips) 5.0.
-constexpr int kPooledThreads = 768;
+// History of the Jacobi phase on B200 (cfg2, ms for the 28 pooled problems), one 768-thread CTA per problem, round-robin
+// ordering: 16-lane groups / two passes 5.6, 8-lane groups 4.6, two pairs in flight per group 5.4, block-2 ordering 5.0;
+// then the odd-even / cluster versions of jacobi.cuh.
+constexpr int kPooledThreads = 256;        // 32 eight-lane groups per CTA x 4 CTAs: n <= 256; 255 registers per thread, no spills
 constexpr int kPooledCluster = 4;           // 28 problems x 4 = 112 of the 148 SMs
 __global__ void __launch_bounds__(kPooledThreads, 1)
 pooled_eig_kernel(const float* __restrict__ stats, int n, int Lt, int P, float M_teacher, float M_student,
@@ -95,6 +86,7 @@ pooled_eig_kernel(const float* __restrict__ stats, int n, int Lt, int P, float M
     __shared__ __align__(8) uint64_t s_bars[2];
     __shared__ int s_bad;
 
+    const long long t_begin = clock64();
     const int crank = static_cast<int>(cooperative_groups::this_cluster().block_rank());
     const int p = blockIdx.x / static_cast<int>(cooperative_groups::this_cluster().num_blocks());
     const bool mp_mode = p < Lt;
@@ -148,14 +140,16 @@ pooled_eig_kernel(const float* __restrict__ stats, int n, int Lt, int P, float M
     }
     __syncthreads();
     }   // crank == 0
+    const long long t_pre = clock64();
     jac_cluster_sync();                     // the matrix is ready in rank 0's shared memory
     int nsweeps = 0;
-    const int groups_per_cta = ((n + 1) / 2 + kPooledCluster - 1) / kPooledCluster;
-    const bool cluster_ok = static_cast<int>(cooperative_groups::this_cluster().num_blocks()) == kPooledCluster &&
-                            groups_per_cta * JAC_GROUP <= static_cast<int>(blockDim.x) &&
+    const int n_cluster = static_cast<int>(cooperative_groups::this_cluster().num_blocks());
+    const int groups_per_cta = ((n + 1) / 2 + n_cluster - 1) / n_cluster;
+    const bool cluster_ok = groups_per_cta * JAC_GROUP <= static_cast<int>(blockDim.x) &&
                             run_jacobi_oddeven_cluster(A, ld, n, inbox, s_bars, s_flags, &nsweeps);      // uniform over the cluster
     if (crank != 0) return;                 // (the Jacobi routine ends with a cluster barrier: nobody touches this CTA again)
     if (!cluster_ok) nsweeps = run_jacobi<false>(A, ld, n);
+    const long long t_jac = clock64();
     column_norms(A, ld, n, n, vals);        // sigma_i (Cholesky route) or lambda_i (fallback)
     __syncthreads();
     if (use_chol)
@@ -181,18 +175,25 @@ pooled_eig_kernel(const float* __restrict__ stats, int n, int Lt, int P, float M
     float* ev = evals + static_cast<size_t>(q) * n;
     float* vk = evecs_km + static_cast<size_t>(q) * n * n;        // [eig][component]
     float* vc = evecs_cm + static_cast<size_t>(q) * n * n;        // [component][eig]
-    for (int i = threadIdx.x; i < n; i += blockDim.x) ev[i] = vals[order[i]];
-    for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
-        const int e = t / n, c = t % n;
-        const int col = order[e];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int col = order[i];
+        ev[i] = vals[col];
         const float nv = use_chol ? sqrtf(vals[col]) : vals[col];   // norm of the rotated column
-        vk[e * n + c] = nv > 0.f ? A[col * ld + c] / nv : 0.f;
+        csum[i] = nv > 0.f ? 1.f / nv : 0.f;                        // (csum is free now) 1 / norm of eigenvector i's column
     }
-    for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
-        const int c = t / n, e = t % n;
-        const int col = order[e];
-        const float nv = use_chol ? sqrtf(vals[col]) : vals[col];
-        vc[c * n + e] = nv > 0.f ? A[col * ld + c] / nv : 0.f;
+    __syncthreads();
+    // eigenvector e = column order[e] of A, normalised; one warp per eigenvector, lanes over components (conflict-free
+    // shared reads; the [eig][comp] store is coalesced, the [comp][eig] one is a 4-byte scatter that L2 merges)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    if (threadIdx.x == 0 && sweeps_out && Lt == 0 && P == 1) { sweeps_out[1] = int((t_pre - t_begin) >> 4); sweeps_out[2] = int((t_jac - t_pre) >> 4); sweeps_out[3] = int((clock64() - t_jac) >> 4); }
+    for (int e = warp; e < n; e += nwarps) {
+        const float* col = A + static_cast<size_t>(order[e]) * ld;
+        const float s = csum[e];
+        for (int c = lane; c < n; c += 32) {
+            const float v = col[c] * s;
+            vk[e * n + c] = v;
+            vc[c * n + e] = v;
+        }
     }
 }
 
@@ -395,13 +396,19 @@ cudaError_t launch_pooled_eig(const float* stats, int n, int Lt, int P, float Mt
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
-    cfg.gridDim = dim3((2 * Lt + P) * kPooledCluster);
+    static int cluster = 0;                   // BASD_EIG_CLUSTER: development knob (1, 2, 4 or 8 CTAs per problem)
+    if (!cluster) {
+        const char* env = getenv("BASD_EIG_CLUSTER");
+        cluster = env ? atoi(env) : kPooledCluster;
+        if (cluster != 1 && cluster != 2 && cluster != 4 && cluster != 8) cluster = kPooledCluster;
+    }
+    cfg.gridDim = dim3((2 * Lt + P) * cluster);
     cfg.blockDim = dim3(kPooledThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr;
     attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = kPooledCluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    attr.val.clusterDim.x = cluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, pooled_eig_kernel, stats, n, Lt, P, Mt, Ms, ranks, evals, evecs_km, evecs_cm, sweeps);
