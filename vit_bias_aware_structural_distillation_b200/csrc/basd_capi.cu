@@ -83,6 +83,9 @@ extern "C" int basd_debug_polar_clocks(int which, long long* host_out) {
     return cudaMemcpy(host_out, basd::polar_dbg_ptr(which), sizeof(long long) * 128, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 1;
 }
 
+namespace basd { int spectral_debug_clocks(long long* host_out); }
+extern "C" int basd_debug_spectral_clocks(long long* host_out) { return basd::spectral_debug_clocks(host_out); }
+
 namespace {
 
 struct Layout {

@@ -7,13 +7,11 @@
 // so no separate rotation accumulator is needed.  Replaces the LAPACK calls at
 // /root/reference/src/losses/layer_selector.py:16,36,92,99 and relational.py:48.
 //
-// Parallel ordering: round-robin tournament (n-1 steps per sweep, n/2 disjoint pairs per step).  A pair is
-// owned by an 8-lane group: each lane keeps its slice of both columns in registers (128-bit shared loads; a
-// quarter warp reads 128 contiguous bytes, so the accesses are bank-conflict free), the three inner products are
-// reduced with 3 xor-shuffles, the rotation is applied from registers.  The kernel is instruction-issue bound, so the
-// group is kept small: 768 threads = 96 groups cover the 96 pairs of an n = 192 step in ONE pass, and the per-pair
-// shuffle / rotation-parameter overhead is amortised over 24 rows per lane (16-lane groups needed two passes per step).
-// ld must be a multiple of 4.
+// A pair of columns is owned by an 8-lane group: each lane keeps its slice of both columns in registers (128-bit
+// shared accesses; a quarter warp touches 128 contiguous bytes, so they are bank-conflict free), the three inner
+// products are reduced with 3 xor-shuffles, the rotation is applied from registers in packed fp32.  Two orderings:
+// odd-even transposition with register-resident columns over a thread-block cluster (the big pooled problems) and a
+// round-robin tournament on one CTA (small problems).  ld must be a multiple of 4.
 #pragma once
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
@@ -35,93 +33,6 @@ __device__ __forceinline__ void jacobi_pair(int n, int s, int k, int& p, int& q)
     const int m1 = n - 1;
     p = s + k; if (p >= m1) p -= m1;
     q = s - k; if (q < 0) q += m1;
-}
-
-template <int CHUNKS>
-__device__ __forceinline__ void jac_load(const float* __restrict__ col, int ld, int gl, float4 (&v)[CHUNKS]) {
-#pragma unroll
-    for (int c = 0; c < CHUNKS; ++c) {
-        const int r = c * JAC_CHUNK_ROWS + gl * 4;
-        v[c] = r < ld ? *reinterpret_cast<const float4*>(col + r) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-}
-// rotates the pair held in (x, y) and writes it back if it was not already orthogonal; returns 1 if it rotated
-template <int CHUNKS>
-__device__ __forceinline__ int jac_rotate_store(float4 (&x)[CHUNKS], float4 (&y)[CHUNKS], float* __restrict__ cp, float* __restrict__ cq,
-                                                int ld, int gl, unsigned gmask, float tol) {
-    float al = 0.f, be = 0.f, ga = 0.f;
-#pragma unroll
-    for (int c = 0; c < CHUNKS; ++c) {
-        al = fmaf(x[c].x, x[c].x, fmaf(x[c].y, x[c].y, fmaf(x[c].z, x[c].z, fmaf(x[c].w, x[c].w, al))));
-        be = fmaf(y[c].x, y[c].x, fmaf(y[c].y, y[c].y, fmaf(y[c].z, y[c].z, fmaf(y[c].w, y[c].w, be))));
-        ga = fmaf(x[c].x, y[c].x, fmaf(x[c].y, y[c].y, fmaf(x[c].z, y[c].z, fmaf(x[c].w, y[c].w, ga))));
-    }
-#pragma unroll
-    for (int o = JAC_GROUP / 2; o > 0; o >>= 1) {
-        al += __shfl_xor_sync(gmask, al, o);
-        be += __shfl_xor_sync(gmask, be, o);
-        ga += __shfl_xor_sync(gmask, ga, o);
-    }
-    if (!(fabsf(ga) > tol * sqrtf(al * be))) return 0;
-    const float zeta = (be - al) / (2.f * ga);
-    const float t = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(fmaf(zeta, zeta, 1.f)));
-    const float cs = rsqrtf(fmaf(t, t, 1.f));
-    const float sn = cs * t;
-#pragma unroll
-    for (int c = 0; c < CHUNKS; ++c) {
-        const int r = c * JAC_CHUNK_ROWS + gl * 4;
-        if (r < ld) {
-            float4 xn, yn;
-            xn.x = cs * x[c].x - sn * y[c].x; yn.x = sn * x[c].x + cs * y[c].x;
-            xn.y = cs * x[c].y - sn * y[c].y; yn.y = sn * x[c].y + cs * y[c].y;
-            xn.z = cs * x[c].z - sn * y[c].z; yn.z = sn * x[c].z + cs * y[c].z;
-            xn.w = cs * x[c].w - sn * y[c].w; yn.w = sn * x[c].w + cs * y[c].w;
-            *reinterpret_cast<float4*>(cp + r) = xn;
-            *reinterpret_cast<float4*>(cq + r) = yn;
-        }
-    }
-    return 1;
-}
-
-// Returns the number of sweeps executed.  All threads of the CTA must call it (contains __syncthreads).
-// n_cols may be odd (the virtual last column is skipped).  Rows [m, ld) of every column must be zero.
-// A group takes TWO pairs per pass with the loads of both issued before the first rotation, so the shared-memory
-// phase of one pair overlaps the arithmetic of the other (with one pair per group every warp sat in the same phase
-// at the same time: load, compute, store, barrier - the SM alternated between an idle LSU and an idle FMA pipe).
-template <int CHUNKS, bool TWO_PAIRS>
-__device__ int jacobi_orthogonalize(float* __restrict__ A, int ld, int n_cols, float tol, int max_sweeps) {
-    const int n = (n_cols + 1) & ~1;
-    const int group = threadIdx.x / JAC_GROUP;
-    const int gl = threadIdx.x % JAC_GROUP;
-    const int n_groups = blockDim.x / JAC_GROUP;
-    const int half = n / 2;
-    const unsigned gmask = 0xFFu << (threadIdx.x & 24);     // the 8 lanes of this group (groups may diverge)
-    int sweep = 0;
-    if (n_cols < 2) return 0;
-    for (; sweep < max_sweeps; ++sweep) {
-        int rotated = 0;
-        for (int s = 0; s < n - 1; ++s) {
-            for (int k = group; k < half; k += (TWO_PAIRS ? 2 : 1) * n_groups) {
-                int p, q, p2 = n_cols, q2 = n_cols;
-                jacobi_pair(n, s, k, p, q);
-                const int k2 = k + n_groups;
-                if (TWO_PAIRS && k2 < half) jacobi_pair(n, s, k2, p2, q2);
-                const bool ok1 = p < n_cols && q < n_cols, ok2 = TWO_PAIRS && p2 < n_cols && q2 < n_cols;   // else: virtual padding column
-                float* cp = A + static_cast<size_t>(ok1 ? p : 0) * ld;
-                float* cq = A + static_cast<size_t>(ok1 ? q : 0) * ld;
-                float* cp2 = A + static_cast<size_t>(ok2 ? p2 : 0) * ld;
-                float* cq2 = A + static_cast<size_t>(ok2 ? q2 : 0) * ld;
-                float4 x[CHUNKS], y[CHUNKS], x2[CHUNKS], y2[CHUNKS];
-                if (ok1) { jac_load<CHUNKS>(cp, ld, gl, x); jac_load<CHUNKS>(cq, ld, gl, y); }
-                if (ok2) { jac_load<CHUNKS>(cp2, ld, gl, x2); jac_load<CHUNKS>(cq2, ld, gl, y2); }
-                if (ok1) rotated |= jac_rotate_store<CHUNKS>(x, y, cp, cq, ld, gl, gmask, tol);
-                if (ok2) rotated |= jac_rotate_store<CHUNKS>(x2, y2, cp2, cq2, ld, gl, gmask, tol);
-            }
-            __syncthreads();
-        }
-        if (!__syncthreads_or(rotated)) { ++sweep; break; }
-    }
-    return sweep;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -293,6 +204,67 @@ __device__ __forceinline__ void jac_push(uint32_t rcol, uint32_t rbar, int ld, i
     }
 }
 __device__ __forceinline__ void jac_bar_active(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
+// OR over the threads of named barrier 1
+__device__ __forceinline__ int jac_bar_active_or(int nthreads, int v) {
+    uint32_t r;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.u32 q, %1, 0;\n\t"
+        "bar.red.or.pred p, 1, %2, q;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(r)
+        : "r"(v), "r"(nthreads)
+        : "memory");
+    return static_cast<int>(r);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Round-robin variant on ONE CTA, columns in shared memory (the small k x k problems of the angles kernel and any
+// shape the cluster variant does not take).  n-1 steps per sweep, n/2 disjoint pairs per step, one 8-lane group per
+// pair; only the warps that hold pairs take part (named barrier), the rest of the CTA waits at the final barrier
+// instead of walking through ~(n-1) x sweeps full-CTA barriers (that was 21 % of the angles kernel's samples).
+// Returns the number of sweeps executed (valid in thread 0).  All threads of the CTA must call it.
+// n_cols may be odd (the virtual last column is skipped).  Rows [m, ld) of every column must be zero.
+// ------------------------------------------------------------------------------------------------------------------
+template <int CHUNKS>
+__device__ int jacobi_orthogonalize(float* __restrict__ A, int ld, int n_cols, float tol, int max_sweeps) {
+    const int n = (n_cols + 1) & ~1;
+    const int half = n / 2;
+    const int group = threadIdx.x / JAC_GROUP;
+    const int gl = threadIdx.x % JAC_GROUP;
+    const int n_groups = min(half, static_cast<int>(blockDim.x) / JAC_GROUP);
+    const int n_active = min((n_groups * JAC_GROUP + 31) & ~31, static_cast<int>(blockDim.x));
+    const int act_groups = n_active / JAC_GROUP;            // groups in the participating warps (a multiple of 4)
+    const uint32_t a_s = smem_u32(A);
+    int sweep = 0;
+    if (n_cols >= 2 && static_cast<int>(threadIdx.x) < n_active) {
+        for (; sweep < max_sweeps; ++sweep) {
+            int rotated = 0;
+            for (int s = 0; s < n - 1; ++s) {
+                for (int kb = 0; kb < half; kb += act_groups) {         // same trip count for every lane of a warp
+                    const int k = kb + group;
+                    int p = 0, q = 0;
+                    if (k < half) jacobi_pair(n, s, k, p, q);
+                    const bool ok = k < half && p < n_cols && q < n_cols;   // else: no pair, or the virtual padding column
+                    const uint32_t cp = a_s + static_cast<uint32_t>(ok ? p : 0) * ld * 4;
+                    const uint32_t cq = a_s + static_cast<uint32_t>(ok ? q : 0) * ld * 4;
+                    ulonglong2 x[CHUNKS], y[CHUNKS];
+                    jac_lds<CHUNKS>(cp, ld, gl, ok, x);
+                    jac_lds<CHUNKS>(cq, ld, gl, ok, y);
+                    const int r = jac_rotate_regs<CHUNKS>(x, y, tol);
+                    rotated |= r;
+                    jac_sts<CHUNKS>(cp, ld, gl, ok && r, x);
+                    jac_sts<CHUNKS>(cq, ld, gl, ok && r, y);
+                }
+                jac_bar_active(n_active);
+            }
+            if (!jac_bar_active_or(n_active, rotated)) { ++sweep; break; }
+        }
+    }
+    __syncthreads();
+    return sweep;
+}
+
 
 template <int CHUNKS>
 __device__ int jacobi_orthogonalize_oddeven_cluster(float* __restrict__ A, int ld, int n_cols, float tol, int max_sweeps, float* inbox,

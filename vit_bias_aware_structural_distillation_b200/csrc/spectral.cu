@@ -16,27 +16,28 @@
 
 namespace basd {
 
+// development aid (tools/gpu_debug_eig.py): phase clocks of the first pooled_eig cluster [0..7] and of angles CTA (0,0) [8..23]
+__device__ long long g_spectral_clk[32];
+int spectral_debug_clocks(long long* host_out) {
+    return cudaMemcpyFromSymbol(host_out, g_spectral_clk, sizeof(long long) * 32) == cudaSuccess ? 0 : 1;
+}
+
 constexpr float kJacobiTol = 3.0e-7f;
 constexpr int kJacobiMaxSweeps = 40;
 constexpr float kFp32Eps = 1.1920929e-7f;
 
-template <int CHUNKS, bool TWO>
-__device__ __forceinline__ int run_jacobi_chunks(float* A, int ld, int n) {
-    return jacobi_orthogonalize<CHUNKS, TWO>(A, ld, n, kJacobiTol, kJacobiMaxSweeps);
-}
-// TWO = two pairs in flight per 8-lane group (needs ~170 registers: for the 384-thread pooled kernel only)
-template <bool TWO>
+// round-robin Jacobi on one CTA, dispatched on the column length (jacobi.cuh)
 __device__ __forceinline__ int run_jacobi(float* A, int ld, int n) {
     const int chunks = (ld + JAC_CHUNK_ROWS - 1) / JAC_CHUNK_ROWS;
     switch (chunks) {
-        case 1: return run_jacobi_chunks<1, TWO>(A, ld, n);
-        case 2: return run_jacobi_chunks<2, TWO>(A, ld, n);
-        case 3: return run_jacobi_chunks<3, TWO>(A, ld, n);
-        case 4: return run_jacobi_chunks<4, TWO>(A, ld, n);
-        case 5: return run_jacobi_chunks<5, TWO>(A, ld, n);
-        case 6: return run_jacobi_chunks<6, TWO>(A, ld, n);
-        case 7: return run_jacobi_chunks<7, TWO>(A, ld, n);
-        default: return run_jacobi_chunks<8, TWO>(A, ld, n);
+        case 1: return jacobi_orthogonalize<1>(A, ld, n, kJacobiTol, kJacobiMaxSweeps);
+        case 2: return jacobi_orthogonalize<2>(A, ld, n, kJacobiTol, kJacobiMaxSweeps);
+        case 3: return jacobi_orthogonalize<3>(A, ld, n, kJacobiTol, kJacobiMaxSweeps);
+        case 4: return jacobi_orthogonalize<4>(A, ld, n, kJacobiTol, kJacobiMaxSweeps);
+        case 5: return jacobi_orthogonalize<5>(A, ld, n, kJacobiTol, kJacobiMaxSweeps);
+        case 6: return jacobi_orthogonalize<6>(A, ld, n, kJacobiTol, kJacobiMaxSweeps);
+        case 7: return jacobi_orthogonalize<7>(A, ld, n, kJacobiTol, kJacobiMaxSweeps);
+        default: return jacobi_orthogonalize<8>(A, ld, n, kJacobiTol, kJacobiMaxSweeps);
     }
 }
 
@@ -148,7 +149,7 @@ pooled_eig_kernel(const float* __restrict__ stats, int n, int Lt, int P, float M
     const bool cluster_ok = groups_per_cta * JAC_GROUP <= static_cast<int>(blockDim.x) &&
                             run_jacobi_oddeven_cluster(A, ld, n, inbox, s_bars, s_flags, &nsweeps);      // uniform over the cluster
     if (crank != 0) return;                 // (the Jacobi routine ends with a cluster barrier: nobody touches this CTA again)
-    if (!cluster_ok) nsweeps = run_jacobi<false>(A, ld, n);
+    if (!cluster_ok) nsweeps = run_jacobi(A, ld, n);
     const long long t_jac = clock64();
     column_norms(A, ld, n, n, vals);        // sigma_i (Cholesky route) or lambda_i (fallback)
     __syncthreads();
@@ -185,7 +186,7 @@ pooled_eig_kernel(const float* __restrict__ stats, int n, int Lt, int P, float M
     // eigenvector e = column order[e] of A, normalised; one warp per eigenvector, lanes over components (conflict-free
     // shared reads; the [eig][comp] store is coalesced, the [comp][eig] one is a 4-byte scatter that L2 merges)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    if (threadIdx.x == 0 && sweeps_out && Lt == 0 && P == 1) { sweeps_out[1] = int((t_pre - t_begin) >> 4); sweeps_out[2] = int((t_jac - t_pre) >> 4); sweeps_out[3] = int((clock64() - t_jac) >> 4); }
+    if (threadIdx.x == 0 && p == Lt) { g_spectral_clk[0] = t_pre - t_begin; g_spectral_clk[1] = t_jac - t_pre; g_spectral_clk[2] = clock64() - t_jac; g_spectral_clk[3] = nsweeps; }
     for (int e = warp; e < n; e += nwarps) {
         const float* col = A + static_cast<size_t>(order[e]) * ld;
         const float s = csum[e];
@@ -226,50 +227,52 @@ angles_kernel(int n, int Lt, int P, const int* __restrict__ ranks, const float* 
     float* scratch = scratch_all + (static_cast<size_t>(i) * Lt + j) * (8 * static_cast<size_t>(n) * n);
     float* Ur = scratch;                      // [b][c]   k x n
     float* Wg = Ur + n * n;                   // [b][e]   column b contiguous in e
-    float* WgR = Wg + n * n;                  // [e][b]
-    float* Qg = WgR + n * n;                  // [b'][b]
+    float* Qg = Wg + 2 * n * n;               // [b'][b]
     float* WQg = Qg + n * n;                  // [b'][e]
     float* Fg = WQg + n * n;                  // [a][e]
-    float* T1g = Fg + n * n;                  // [c'][e]
-    float* Gg = T1g + n * n;                  // [c'][c]
+    float* T1g = Fg + n * n;                  // H [a][c]
 
+    const bool dbg = blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
+    if (dbg) g_spectral_clk[31] = k;
     if (k == 0) {                              // reference: 0/0 -> NaN (layer_selector.py:105)
         if (threadIdx.x == 0) d2_out[i * Lt + j] = CUDART_NAN_F;
         for (int t = threadIdx.x; t < n * n; t += blockDim.x) gam[t] = 0.f;
         return;
     }
+    if (dbg) g_spectral_clk[8 + 0] = clock64();
     // (a) Ur[b][c] = sum_r Ut[b][r] P_s[r][c]
     cta_gemm(n, k, n,
              [&](int c, int r) { return proj_s[r * n + c]; },
              [&](int r, int b) { return Ut[b * n + r]; },
              [&](int c, int b, float v) { Ur[b * n + c] = v; });
     __syncthreads();
-    // (b) W[e][b] = sum_c Vs[e][c] Ur[b][c]
+    for (int t = threadIdx.x; t < ld * k; t += blockDim.x) J[t] = 0.f;
+    __syncthreads();
+    if (dbg) g_spectral_clk[8 + 1] = clock64();
+    // (b) W[e][b] = sum_c Vs[e][c] Ur[b][c];   its top k x k block is A = V_s[:, :k]^T (P_s^T U_t)
+    //     J = A^T goes straight to shared memory: column a of J = row a of A
     cta_gemm(n, k, n,
              [&](int e, int c) { return Vs_cm[c * n + e]; },
              [&](int c, int b) { return Ur[b * n + c]; },
-             [&](int e, int b, float v) { Wg[b * n + e] = v; WgR[e * k + b] = v; });
+             [&](int e, int b, float v) { Wg[b * n + e] = v; if (e < k) J[e * ld + b] = v; });
     __syncthreads();
-    // (c) J = A^T A,  A = W[:k,:k]
-    for (int t = threadIdx.x; t < ld * k; t += blockDim.x) J[t] = 0.f;
-    __syncthreads();
-    cta_gemm(k, k, k,
-             [&](int b, int a) { return WgR[a * k + b]; },
-             [&](int a, int b2) { return WgR[a * k + b2]; },
-             [&](int b, int b2, float v) { J[b2 * ld + b] = v; });
-    __syncthreads();
-    run_jacobi<false>(J, ld, k);
-    column_norms(J, ld, k, k, vals);          // vals = sigma^2
+    if (dbg) g_spectral_clk[8 + 2] = clock64();
+    if (dbg) g_spectral_clk[8 + 3] = clock64();
+    // (c) one-sided Jacobi on A^T:  A^T R = Y Sigma  =>  A^T A = Y Sigma^2 Y^T.  The rotated columns are sigma_m y_m: their
+    //     norms are the cosines themselves (no squaring through A^T A) and their directions the right singular vectors.
+    run_jacobi(J, ld, k);
+    column_norms(J, ld, k, k, vals);          // vals = sigma
     __syncthreads();
     rank_descending(vals, k, order);
     __syncthreads();
+    if (dbg) g_spectral_clk[8 + 4] = clock64();
     // (d) distances and d(d2)/dsigma
     float swsum = 0.f, acc = 0.f;
     for (int r = threadIdx.x; r < k; r += blockDim.x) swsum += sqrtf(fmaxf(lam_t[r], 0.f));
     swsum = cta_sum(swsum, red);
     for (int r = threadIdx.x; r < k; r += blockDim.x) {
         const int col = order[r];
-        const float sig = sqrtf(vals[col]);
+        const float sig = vals[col];
         const float sw = sqrtf(fmaxf(lam_t[r], 0.f));
         const float clampv = 1.f - kFp32Eps;
         const float sc = fminf(sig, clampv);
@@ -277,25 +280,28 @@ angles_kernel(int n, int Lt, int P, const int* __restrict__ ranks, const float* 
         acc += sw * th * th;
         float ds = 0.f;
         if (sig <= clampv) ds = sw * 2.f * th * (-rsqrtf(fmaxf(1.f - sc * sc, 1e-30f))) / swsum;
-        // Q = Y diag(dsigma / sigma) Y^T with Y = normalised columns (column norm = sigma^2)
+        // Q = Y diag(dsigma / sigma) Y^T with Y = normalised columns (column norm = sigma)
         coef[col] = (sig > 1e-20f) ? ds / (sig * vals[col] * vals[col]) : 0.f;
         if (cos_out) cos_out[(static_cast<size_t>(i) * Lt + j) * n + r] = sig;
     }
     acc = cta_sum(acc, red);
     if (threadIdx.x == 0) d2_out[i * Lt + j] = acc / swsum;
     __syncthreads();
+    if (dbg) g_spectral_clk[8 + 5] = clock64();
     // Q[b][b'] = sum_m J[b][m] coef_m J[b'][m]
     cta_gemm(k, k, k,
              [&](int b, int m) { return J[m * ld + b] * coef[m]; },
              [&](int m, int b2) { return J[m * ld + b2]; },
              [&](int b, int b2, float v) { Qg[b2 * k + b] = v; });
     __syncthreads();
+    if (dbg) g_spectral_clk[8 + 6] = clock64();
     // (e) WQ[e][b'] = sum_b W[e][b] Q[b][b']
     cta_gemm(n, k, k,
              [&](int e, int b) { return Wg[b * n + e]; },
              [&](int b, int b2) { return Qg[b2 * k + b]; },
              [&](int e, int b2, float v) { WQg[b2 * n + e] = v; });
     __syncthreads();
+    if (dbg) g_spectral_clk[8 + 7] = clock64();
     //     F[e][a] = (sum_b' WQ[e][b'] A[a][b']) / (lam_a - lam_e)   for e >= k, a < k
     const int nc = n - k;
     cta_gemm(nc, k, k,
@@ -303,22 +309,28 @@ angles_kernel(int n, int Lt, int P, const int* __restrict__ ranks, const float* 
              [&](int b2, int a) { return Wg[b2 * n + a]; },
              [&](int e, int a, float v) { Fg[a * n + k + e] = v / (lam_s[a] - lam_s[k + e]); });
     __syncthreads();
-    // (f) T1[e][c'] = sum_a F[e][a] Vs[a][c']
-    cta_gemm(nc, n, k,
-             [&](int e, int a) { return Fg[a * n + k + e]; },
-             [&](int a, int c2) { return Vs_km[a * n + c2]; },
-             [&](int e, int c2, float v) { T1g[c2 * n + k + e] = v; });
-    __syncthreads();
-    //     Gamma[c][c'] = sum_{e>=k} Vs[e][c] T1[e][c']
-    cta_gemm(n, n, nc,
+    if (dbg) g_spectral_clk[8 + 8] = clock64();
+    // (f) Gamma = V_hi^T F V_lo  (V_hi = eigenvectors e >= k, V_lo = a < k), associated as (V_hi^T F) V_lo: n k (n + nc)
+    //     multiply-adds instead of the n n nc of V_hi^T (F V_lo), k << nc.
+    //     H[c][a] = sum_{e>=k} Vs[e][c] F[e][a]
+    cta_gemm(n, k, nc,
              [&](int c, int e) { return Vs_km[(k + e) * n + c]; },
-             [&](int e, int c2) { return T1g[c2 * n + k + e]; },
-             [&](int c, int c2, float v) { Gg[c2 * n + c] = v; });
+             [&](int e, int a) { return Fg[a * n + k + e]; },
+             [&](int c, int a, float v) { T1g[a * n + c] = v; });
     __syncthreads();
-    for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
-        const int c = t / n, c2 = t % n;
-        gam[t] = Gg[c2 * n + c] + Gg[c * n + c2];
+    if (dbg) g_spectral_clk[8 + 9] = clock64();
+    //     Gamma_sym[c][c'] = sum_a H[c][a] Vs[a][c'] + Vs[a][c] H[c'][a]   (one product of inner size 2k; symmetric, so the
+    //     store may run along c)
+    if ((n & 3) == 0) {
+        cta_gemm_sym2(n, k, T1g, Vs_km, n, [&](int c, int c2, float v) { gam[c2 * n + c] = v; });
+    } else {
+        cta_gemm(n, n, 2 * k,
+                 [&](int c, int a) { return a < k ? T1g[a * n + c] : Vs_km[(a - k) * n + c]; },
+                 [&](int a, int c2) { return a < k ? Vs_km[a * n + c2] : T1g[(a - k) * n + c2]; },
+                 [&](int c, int c2, float v) { gam[c2 * n + c] = v; });
     }
+    if (dbg) g_spectral_clk[8 + 10] = clock64();
+    if (dbg) g_spectral_clk[8 + 11] = clock64();
 }
 
 // w = softmax(-d2 / softplus(log_temperature))   one warp per extraction point
