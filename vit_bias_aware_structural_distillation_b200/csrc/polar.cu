@@ -40,12 +40,6 @@ const float kPolarCoef[kPolarSteps][3] = {
     {1.847826056f, -1.196240433f, 0.348410606f},
 };
 
-__device__ __forceinline__ void store_split(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t idx, float v) {
-    const __nv_bfloat16 h = __float2bfloat16(v);
-    hi[idx] = h;
-    lo[idx] = __float2bfloat16(v - __bfloat162float(h));
-}
-
 // ------------------------------------------------------------------------------------------------
 // prep_student: s_w = sqrt(a) (s - mu_s)  ->  SW [N][Ds] (split), W_0 = s_w^T [Ds][Np] (split), ksd, tr_s
 // one CTA per problem; the whole s_w tile lives in shared memory (fp32, padded rows)
@@ -55,6 +49,32 @@ __device__ __forceinline__ void store_split2(__nv_bfloat16* hi, __nv_bfloat16* l
     __nv_bfloat162 hv; hv.x = h0; hv.y = h1;
     *reinterpret_cast<__nv_bfloat162*>(hi + idx) = hv;
     *reinterpret_cast<__nv_bfloat162*>(lo + idx) = __floats2bfloat162_rn(v0 - __bfloat162float(h0), v1 - __bfloat162float(h1));
+}
+
+// eight consecutive values -> one 16-byte store per half (idx a multiple of 8)
+__device__ __forceinline__ void store_split8(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t idx, const float* v) {
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 hv = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        const float2 hf = __bfloat1622float2(hv);
+        const __nv_bfloat162 lv = __floats2bfloat162_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+        hw[i] = *reinterpret_cast<const uint32_t*>(&hv);
+        lw[i] = *reinterpret_cast<const uint32_t*>(&lv);
+    }
+    *reinterpret_cast<uint4*>(hi + idx) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    *reinterpret_cast<uint4*>(lo + idx) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+}
+// eight consecutive split values hi + lo -> fp32
+__device__ __forceinline__ void load_split8(const __nv_bfloat16* hi, const __nv_bfloat16* lo, size_t idx, float* v) {
+    const uint4 h = *reinterpret_cast<const uint4*>(hi + idx), l = *reinterpret_cast<const uint4*>(lo + idx);
+    const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&h);
+    const __nv_bfloat162* lp = reinterpret_cast<const __nv_bfloat162*>(&l);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 a = __bfloat1622float2(hp[i]), b = __bfloat1622float2(lp[i]);
+        v[2 * i] = a.x + b.x; v[2 * i + 1] = a.y + b.y;
+    }
 }
 
 constexpr int kPrepThreads = 512;
@@ -128,6 +148,126 @@ polar_prep_student_kernel(PolarArgs g) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// prep_student, D_s a multiple of 8: the raw bf16 tile stays in shared memory as it was read (16-byte loads, 78 KB
+// instead of 151 KB of fp32 -> two CTAs per SM overlap each other's load / compute / store phases) and
+// s_w = sqrt(a) (s - mu) is recomputed where it is consumed; every global access is 16 bytes wide.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPrepThreads, 2)
+polar_prep_student_vec_kernel(PolarArgs g) {
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    const int N = g.Ns, D = g.Ds, pitch = D + 8, oct = D / 8;      // pitch in bf16: rows stay 16-byte aligned
+    __nv_bfloat16* raw = reinterpret_cast<__nv_bfloat16*>(sm_raw);  // [N][pitch]
+    float* a_s = reinterpret_cast<float*>(sm_raw + ((static_cast<size_t>(N) * pitch * 2 + 15) & ~size_t(15)));
+    float* q_s = a_s + N;
+    float* mu = q_s + N;                                            // [D]
+    float* red = mu + D;                                            // 40
+    float* partial = red + 40;                                      // [slices][D]
+    const int prob = blockIdx.x;
+    const int i = prob / g.B, b = prob % g.B;
+    const __nv_bfloat16* S = g.student[i] + static_cast<size_t>(b) * N * D;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        const float a = g.a[static_cast<size_t>(prob) * N + n];
+        a_s[n] = a;
+        q_s[n] = sqrtf(a);
+    }
+    for (int t = threadIdx.x; t < N * oct; t += blockDim.x) {
+        const int n = t / oct, o = t - n * oct;
+        *reinterpret_cast<uint4*>(raw + n * pitch + o * 8) = *reinterpret_cast<const uint4*>(S + static_cast<size_t>(n) * D + o * 8);
+    }
+    __syncthreads();
+    // mu[d] = sum_n a[n] s[n][d]: thread = (octet of d, slice of n)
+    const int slices = blockDim.x / oct;
+    {
+        const int o = threadIdx.x % oct, sl = threadIdx.x / oct;
+        if (sl < slices) {
+            float m[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int n = sl; n < N; n += slices) {
+                const uint4 v = *reinterpret_cast<const uint4*>(raw + n * pitch + o * 8);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+                const float an = a_s[n];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 f = __bfloat1622float2(h[e]);
+                    m[2 * e] = fmaf(an, f.x, m[2 * e]);
+                    m[2 * e + 1] = fmaf(an, f.y, m[2 * e + 1]);
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) partial[sl * D + o * 8 + e] = m[e];
+        }
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float m = 0.f;
+        for (int sl = 0; sl < slices; ++sl) m += partial[sl * D + d];
+        mu[d] = m;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    // row norms of s_w
+    float* ksd = g.vec + static_cast<size_t>(prob) * 4 * N;
+    float part = 0.f;
+    for (int n = warp; n < N; n += nw) {
+        float s = 0.f;
+        const float qn = q_s[n];
+        for (int o = lane; o < oct; o += 32) {
+            const uint4 v = *reinterpret_cast<const uint4*>(raw + n * pitch + o * 8);
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(h[e]);
+                const float x = qn * (f.x - mu[o * 8 + 2 * e]), y = qn * (f.y - mu[o * 8 + 2 * e + 1]);
+                s = fmaf(x, x, fmaf(y, y, s));
+            }
+        }
+        s = warp_sum(s);
+        if (lane == 0) { ksd[n] = s; part += s; }
+    }
+    const float tr_s = cta_sum(part, red);
+    if (threadIdx.x == 0) g.scal[prob * 4 + 1] = tr_s;
+    // SW = s_w [N][Ds], tiled [d block][n][64]: a thread takes 8 consecutive d of one row
+    __nv_bfloat16* swh = g.SW.hi + prob * g.SW.batch_stride;
+    __nv_bfloat16* swl = g.SW.lo + prob * g.SW.batch_stride;
+    const int n_cb = (D + 63) / 64;
+    for (int t = threadIdx.x; t < n_cb * N * 8; t += blockDim.x) {
+        const int j0 = (t & 7) * 8, n = (t >> 3) % N, cb = (t >> 3) / N;
+        const int d0 = cb * 64 + j0;
+        float v[8];
+        if (d0 < D) {
+            const uint4 r = *reinterpret_cast<const uint4*>(raw + n * pitch + d0);
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+            const float qn = q_s[n];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(h[e]);
+                v[2 * e] = qn * (f.x - mu[d0 + 2 * e]);
+                v[2 * e + 1] = qn * (f.y - mu[d0 + 2 * e + 1]);
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = 0.f;
+        }
+        store_split8(swh, swl, (static_cast<size_t>(cb) * N + n) * 64 + j0, v);
+    }
+    // W_0 = s_w^T [Ds][N], tiled [n block][d][64], padding columns zero: a thread takes 8 consecutive n of one d; lanes run
+    // along d (conflict-free 2-byte shared reads; the 16-byte stores of a warp land 128 B apart and are merged in L2)
+    __nv_bfloat16* wh = g.W.hi + prob * g.W.batch_stride;
+    __nv_bfloat16* wl = g.W.lo + prob * g.W.batch_stride;
+    const int n_nb = (N + 63) / 64;
+    for (int t = threadIdx.x; t < n_nb * 8 * D; t += blockDim.x) {
+        const int d = t % D, j0 = ((t / D) & 7) * 8, nb = t / (8 * D);
+        const float md = mu[d];
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int n = nb * 64 + j0 + e;
+            v[e] = n < N ? q_s[n] * (__bfloat162float(raw[n * pitch + d]) - md) : 0.f;
+        }
+        store_split8(wh, wl, (static_cast<size_t>(nb) * D + d) * 64 + j0, v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // prep_teacher: K_t = q (Ktt - m 1^T - 1 m^T + mm) q  (weighted + centred token Gram, split), diag, tr_t
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -168,12 +308,29 @@ polar_prep_teacher_kernel(PolarArgs g) {
     if (threadIdx.x == 0) g.scal[prob * 4 + 2] = tr_t;
     __nv_bfloat16* kh = g.Kt.hi + prob * g.Kt.batch_stride;
     __nv_bfloat16* kl = g.Kt.lo + prob * g.Kt.batch_stride;
-    const int Np = (N + 63) / 64 * 64;
-    for (int t = threadIdx.x; t < N * Np; t += blockDim.x) {
-        const int m = t % 64 + (t / (64 * N)) * 64, n = (t / 64) % N;        // storage order: [col block][row n][64]
-        float v = 0.f;
-        if (m < N) v = q_s[n] * q_s[m] * (Ktt[static_cast<size_t>(n) * N + m] - m_s[n] - m_s[m] + mm);
-        store_split(kh, kl, t, v);
+    // storage order [col block][row n][64]: a thread takes 8 consecutive columns of one row (two 16-byte loads of Ktt when
+    // N is a multiple of 4, one 16-byte store per half); the second read of Ktt comes from L2
+    const int n_cb = (N + 63) / 64;
+    const bool vec_ok = (N & 3) == 0;
+    for (int t = threadIdx.x; t < n_cb * N * 8; t += blockDim.x) {
+        const int j0 = (t & 7) * 8, n = (t >> 3) % N, cb = (t >> 3) / N;
+        const int m0 = cb * 64 + j0;
+        float v[8];
+        const float* row = Ktt + static_cast<size_t>(n) * N;
+        if (vec_ok && m0 + 8 <= N) {
+            const float4 k0 = *reinterpret_cast<const float4*>(row + m0), k1 = *reinterpret_cast<const float4*>(row + m0 + 4);
+            v[0] = k0.x; v[1] = k0.y; v[2] = k0.z; v[3] = k0.w; v[4] = k1.x; v[5] = k1.y; v[6] = k1.z; v[7] = k1.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = m0 + e < N ? row[m0 + e] : 0.f;
+        }
+        const float qn = q_s[n], mn = m_s[n] - mm;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int m = m0 + e;
+            v[e] = m < N ? qn * q_s[m] * (v[e] - mn - m_s[m]) : 0.f;
+        }
+        store_split8(kh, kl, (static_cast<size_t>(cb) * N + n) * 64 + j0, v);
     }
 }
 
@@ -195,18 +352,42 @@ polar_finish_kernel(PolarArgs g) {
     const float* a = g.a + static_cast<size_t>(prob) * N;
     float* gdir = g.gdir + static_cast<size_t>(prob) * N * D;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    for (int n = warp; n < N; n += nw) {
-        const float qn = sqrtf(a[n]);
-        float s = 0.f;
-        for (int d = lane; d < D; d += 32) {
-            const size_t idx = g.SW.at(n, d);
-            const float sw = __bfloat162float(swh[idx]) + __bfloat162float(swl[idx]);
-            const float gv = G[static_cast<size_t>(n) * D + d];
-            s = fmaf(sw, gv, s);
-            gdir[static_cast<size_t>(n) * D + d] = qn * (2.f * sw - 2.f * gv);
+    if ((D & 7) == 0) {
+        // a lane takes 8 consecutive d of one row: 16-byte loads of both halves of s_w, 2 x 16-byte loads of Gsw, 2 x 16-byte
+        // stores of gdir; a warp covers 256 columns per pass
+        for (int n = warp; n < N; n += nw) {
+            const float qn = sqrtf(a[n]);
+            float s = 0.f;
+            for (int d0 = lane * 8; d0 < D; d0 += 256) {
+                float sw[8];
+                load_split8(swh, swl, g.SW.at(n, d0), sw);
+                const float4 g0 = *reinterpret_cast<const float4*>(G + static_cast<size_t>(n) * D + d0);
+                const float4 g1 = *reinterpret_cast<const float4*>(G + static_cast<size_t>(n) * D + d0 + 4);
+                const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { s = fmaf(sw[e], gv[e], s); o[e] = qn * (2.f * sw[e] - 2.f * gv[e]); }
+                float* od = gdir + static_cast<size_t>(n) * D + d0;
+                *reinterpret_cast<float4*>(od) = make_float4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<float4*>(od + 4) = make_float4(o[4], o[5], o[6], o[7]);
+            }
+            s = warp_sum(s);
+            if (lane == 0) dots[n] = s;
         }
-        s = warp_sum(s);
-        if (lane == 0) dots[n] = s;
+    } else {
+        for (int n = warp; n < N; n += nw) {
+            const float qn = sqrtf(a[n]);
+            float s = 0.f;
+            for (int d = lane; d < D; d += 32) {
+                const size_t idx = g.SW.at(n, d);
+                const float sw = __bfloat162float(swh[idx]) + __bfloat162float(swl[idx]);
+                const float gv = G[static_cast<size_t>(n) * D + d];
+                s = fmaf(sw, gv, s);
+                gdir[static_cast<size_t>(n) * D + d] = qn * (2.f * sw - 2.f * gv);
+            }
+            s = warp_sum(s);
+            if (lane == 0) dots[n] = s;
+        }
     }
     __syncthreads();
     const float* ksd = g.vec + static_cast<size_t>(prob) * 4 * N;
@@ -246,9 +427,16 @@ cudaError_t launch_polar_procrustes(const PolarArgs& g, cudaStream_t st, int* la
     int count = 0;
     {
         TimingScope ts(kSlotPolarPrep, st, 2);
-        const size_t smem = (static_cast<size_t>(N) * (D + 1) + 2 * N + D + 64) * sizeof(float);
-        PCK(cudaFuncSetAttribute(polar_prep_student_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        polar_prep_student_kernel<<<nprob, kPrepThreads, smem, st>>>(g);
+        if (D % 8 == 0) {
+            const int slices = kPrepThreads / (D / 8);
+            const size_t smem = ((static_cast<size_t>(N) * (D + 8) * 2 + 15) & ~size_t(15)) + (2 * N + D + 40 + static_cast<size_t>(slices) * D) * sizeof(float);
+            PCK(cudaFuncSetAttribute(polar_prep_student_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            polar_prep_student_vec_kernel<<<nprob, kPrepThreads, smem, st>>>(g);
+        } else {
+            const size_t smem = (static_cast<size_t>(N) * (D + 1) + 2 * N + D + 64) * sizeof(float);
+            PCK(cudaFuncSetAttribute(polar_prep_student_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            polar_prep_student_kernel<<<nprob, kPrepThreads, smem, st>>>(g);
+        }
         PCK(cudaGetLastError());
         polar_prep_teacher_kernel<<<nprob, 256, (3 * N + 64) * sizeof(float), st>>>(g);
         PCK(cudaGetLastError());

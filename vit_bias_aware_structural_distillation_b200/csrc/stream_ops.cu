@@ -11,7 +11,7 @@ namespace basd {
 
 __device__ __forceinline__ uint4 ld_nc_16(const void* p) {
     uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
 __device__ __forceinline__ void bf16x8_to_float(const uint4& v, float* f) {
@@ -346,6 +346,9 @@ cudaError_t launch_mix_teacher(const PtrTable& teacher, const float* w, int Lt, 
 // ---------------------------------------------------------------------------------------------- d loss / d w
 // gw[i][j] += sum_{b,n,d} Dtm[i][b][n][d] * interp(T_j[b])[n][d]      blockIdx.y selects a (point-chunk, layer-chunk)
 constexpr int WG_PC = 4, WG_JC = 12;
+// All 16-byte loads of a position (WG_PC gradient vectors, WG_JC teacher vectors, twice that when interpolating) are issued
+// before the first use: with a load and its use alternating per layer the kernel ran at 2 TB/s, one L2/HBM latency per layer.
+template <bool INTERP>
 __global__ void __launch_bounds__(256)
 wgrad_dots_kernel(PtrTable teacher, const __nv_bfloat16* __restrict__ Dtm, int Lt, int P, int B, int Nt, int Ns, int Dt,
                   float* __restrict__ gw) {
@@ -356,44 +359,44 @@ wgrad_dots_kernel(PtrTable teacher, const __nv_bfloat16* __restrict__ Dtm, int L
     for (int i = 0; i < WG_PC; ++i)
 #pragma unroll
         for (int j = 0; j < WG_JC; ++j) acc[i][j] = 0.f;
-    const int vpr = Dt / 8;
-    const size_t per_sample = static_cast<size_t>(Ns) * vpr;
-    const size_t total = per_sample * B;
-    for (size_t v = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; v < total; v += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int b = static_cast<int>(v / per_sample);
-        const size_t rem = v % per_sample;
-        const int n = static_cast<int>(rem / vpr), dv = static_cast<int>(rem % vpr);
+    const uint32_t vpr = static_cast<uint32_t>(Dt) / 8u;
+    const uint32_t total = static_cast<uint32_t>(B) * Ns * vpr;            // < 2^32 (checked by the launcher)
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < total; v += gridDim.x * blockDim.x) {
+        const uint32_t row = v / vpr, dv = v - row * vpr;
+        const uint32_t b = row / static_cast<uint32_t>(Ns), n = row - b * Ns;
         int i0, i1; float lam;
-        interp_index(n, Nt, Ns, i0, i1, lam);
-        float dtv[WG_PC][8];
+        interp_index(static_cast<int>(n), Nt, Ns, i0, i1, lam);
+        uint4 draw[WG_PC], t0[WG_JC], t1[INTERP ? WG_JC : 1];
 #pragma unroll
-        for (int i = 0; i < WG_PC; ++i) {
-            if (i_base + i < P) {
-                bf16x8_to_float(ld_nc_16(Dtm + ((static_cast<size_t>(i_base + i) * B + b) * Ns + n) * Dt + dv * 8), dtv[i]);
-            } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) dtv[i][e] = 0.f;
-            }
-        }
+        for (int i = 0; i < WG_PC; ++i)
+            draw[i] = i_base + i < P ? ld_nc_16(Dtm + ((static_cast<size_t>(i_base + i) * B + b) * Ns + n) * Dt + dv * 8) : zero4;
 #pragma unroll
         for (int j = 0; j < WG_JC; ++j) {
-            if (j_base + j < Lt) {
-                const __nv_bfloat16* T = reinterpret_cast<const __nv_bfloat16*>(teacher.p[j_base + j]) + (static_cast<size_t>(b) * Nt) * Dt + dv * 8;
-                float f[8];
-                bf16x8_to_float(ld_nc_16(T + static_cast<size_t>(i0) * Dt), f);
-                if (lam != 0.f) {
-                    float g[8];
-                    bf16x8_to_float(ld_nc_16(T + static_cast<size_t>(i1) * Dt), g);
+            const bool ok = j_base + j < Lt;
+            const __nv_bfloat16* T = reinterpret_cast<const __nv_bfloat16*>(teacher.p[ok ? j_base + j : 0]) + (static_cast<size_t>(b) * Nt) * Dt + dv * 8;
+            t0[j] = ok ? ld_nc_16(T + static_cast<size_t>(i0) * Dt) : zero4;
+            if (INTERP) t1[j] = ok ? ld_nc_16(T + static_cast<size_t>(i1) * Dt) : zero4;
+        }
+        float dtv[WG_PC][8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) f[e] = (1.f - lam) * f[e] + lam * g[e];
-                }
+        for (int i = 0; i < WG_PC; ++i) bf16x8_to_float(draw[i], dtv[i]);
 #pragma unroll
-                for (int i = 0; i < WG_PC; ++i) {
-                    float s = 0.f;
+        for (int j = 0; j < WG_JC; ++j) {
+            float f[8];
+            bf16x8_to_float(t0[j], f);
+            if (INTERP) {
+                float g[8];
+                bf16x8_to_float(t1[j], g);
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) s = fmaf(dtv[i][e], f[e], s);
-                    acc[i][j] += s;
-                }
+                for (int e = 0; e < 8; ++e) f[e] = (1.f - lam) * f[e] + lam * g[e];
+            }
+#pragma unroll
+            for (int i = 0; i < WG_PC; ++i) {
+                float s = 0.f;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) s = fmaf(dtv[i][e], f[e], s);
+                acc[i][j] += s;
             }
         }
     }
@@ -419,24 +422,30 @@ __global__ void wgrad_importance_kernel(const float* __restrict__ gwt, const flo
     __shared__ float red[40];
     const int i = blockIdx.x / Lt, j = blockIdx.x % Lt;
     float part = 0.f;
-    for (int t = threadIdx.x; t < B * Ns; t += blockDim.x) {
-        const int b = t / Ns, n = t % Ns;
-        int i0, i1; float lam;
-        interp_index(n, Nt, Ns, i0, i1, lam);
+    // blockIdx.y strides over the samples (48 CTAs walking 50k elements each was 0.1 ms of pure latency)
+    for (int b = blockIdx.y; b < B; b += gridDim.y) {
         const float* r = rows + (static_cast<size_t>(j) * B + b) * Nt;
-        part = fmaf(gwt[(static_cast<size_t>(i) * B + b) * Ns + n], (1.f - lam) * r[i0] + lam * r[i1], part);
+        const float* gq = gwt + (static_cast<size_t>(i) * B + b) * Ns;
+        for (int n = threadIdx.x; n < Ns; n += blockDim.x) {
+            int i0, i1; float lam;
+            interp_index(n, Nt, Ns, i0, i1, lam);
+            part = fmaf(gq[n], (1.f - lam) * r[i0] + lam * r[i1], part);
+        }
     }
     const float tot = cta_sum(part, red);
     if (threadIdx.x == 0) atomicAdd(&gw[i * Lt + j], tot);
 }
 cudaError_t launch_wgrad_dots(const PtrTable& teacher, const __nv_bfloat16* Dtm, const float* gwt, const float* rows, int Lt, int P,
                               int B, int Nt, int Ns, int Dt, float* gw, cudaStream_t st) {
-    if (Dt % 8 != 0) return cudaErrorInvalidValue;
+    if (Dt % 8 != 0 || static_cast<unsigned long long>(B) * Ns * (Dt / 8) >= (1ull << 32)) return cudaErrorInvalidValue;
     const int ny = ((P + WG_PC - 1) / WG_PC) * ((Lt + WG_JC - 1) / WG_JC);
-    wgrad_dots_kernel<<<dim3(148 * 4, ny), 256, 0, st>>>(teacher, Dtm, Lt, P, B, Nt, Ns, Dt, gw);
+    if (Nt == Ns)
+        wgrad_dots_kernel<false><<<dim3(148 * 4, ny), 256, 0, st>>>(teacher, Dtm, Lt, P, B, Nt, Ns, Dt, gw);
+    else
+        wgrad_dots_kernel<true><<<dim3(148 * 4, ny), 256, 0, st>>>(teacher, Dtm, Lt, P, B, Nt, Ns, Dt, gw);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    wgrad_importance_kernel<<<P * Lt, 256, 0, st>>>(gwt, rows, Lt, P, B, Nt, Ns, gw);
+    wgrad_importance_kernel<<<dim3(P * Lt, B < 16 ? B : 16), 256, 0, st>>>(gwt, rows, Lt, P, B, Nt, Ns, gw);
     return cudaGetLastError();
 }
 
