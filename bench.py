@@ -252,14 +252,13 @@ def main():
     for _ in range(args.warmup):
         step(logits, targets, student, teacher, attn)
     barrier()
-    lib.basd_timing_reset()
-    lib.basd_timing_enable(1)
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.3)                       # let the streaming nvidia-smi come up before the timed region
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     sampler.mark()
+    lib.basd_timing_reset()               # (resets the launch counter too; the per-kernel event brackets stay off here)
     e0.record()
     for _ in range(args.steps):
         loss = step(logits, targets, student, teacher, attn)
@@ -268,6 +267,14 @@ def main():
     clocks = sampler.finish()
     ms_total = e0.elapsed_time(e1)
     launches = int(lib.basd_launch_count())
+    # per-kernel breakdown: the same steps again with a CUDA-event bracket around every launch group (kept out of the
+    # timed region above: ~150 event records per step cost 0.1-0.2 ms and keep consecutive kernels from overlapping)
+    lib.basd_timing_reset()
+    lib.basd_timing_enable(1)
+    breakdown_steps = min(args.steps, 10)
+    for _ in range(breakdown_steps):
+        step(logits, targets, student, teacher, attn)
+    barrier()
     lib.basd_timing_enable(0)
     kern = _lib.timing_read()
     t_ms = torch.tensor([ms_total], device=dev)
@@ -330,7 +337,7 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     tc_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-    per_step = {k: v[0] / args.steps for k, v in kern.items() if v[1] > 0}
+    per_step = {k: v[0] / breakdown_steps for k, v in kern.items() if v[1] > 0}
     dom = max(per_step, key=per_step.get) if per_step else None
     w_alg = algorithmic_bytes(w)
     f_tc = tensor_flops(w)
@@ -362,12 +369,12 @@ def main():
     except Exception:
         pass
     if dom in table and table[dom][1] > 0:
-        bound, units, launches, what = table[dom]
-        ms_launch = per_step[dom] / launches
-        ach = units / launches / (ms_launch * 1e-3) / 1e9
+        bound, units, n_l, what = table[dom]
+        ms_launch = per_step[dom] / n_l
+        ach = units / n_l / (ms_launch * 1e-3) / 1e9
         roofline = {"bound": bound, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
-                    "kernel": dom, "what": what, "launches_per_step": launches, "avg_launch_ms": ms_launch,
-                    "algorithmic_bytes_per_launch": units / launches}
+                    "kernel": dom, "what": what, "launches_per_step": n_l, "avg_launch_ms": ms_launch,
+                    "algorithmic_bytes_per_launch": units / n_l}
         if dom == "polar_gemm":
             tf = polar_flops / polar_launches / (ms_launch * 1e-3) / 1e12
             roofline["tensor_view"] = {"achieved_tflops": tf, "peak_tflops": tc_peak, "frac": tf / tc_peak}

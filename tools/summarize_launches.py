@@ -4,7 +4,7 @@
 import collections, csv, json, sys
 
 SLOT = {"polar_gemm_kernel": "polar_gemm", "pooled_eig_kernel": "pooled_eig", "angles_kernel": "angles", "wgrad_dots_kernel": "wgrad_dots",
-        "mix_teacher_kernel": "mix_teacher", "colsum_kernel": "colsum", "polar_prep_student_kernel": "polar_prep",
+        "mix_teacher_kernel": "mix_teacher", "colsum_kernel": "colsum", "polar_prep_student_kernel": "polar_prep", "polar_prep_student_vec_kernel": "polar_prep",
         "polar_prep_teacher_kernel": "polar_prep", "polar_finish_kernel": "polar_finish", "importance_rows_kernel": "importance_rows"}
 
 

@@ -185,6 +185,9 @@ def _setup_context(ctx, inputs, output):
     ctx.n_students, ctx.n_teachers = len(students), len(teachers)
     ctx.has_cls = has_cls
     ctx.student_dtypes = [s.dtype for s in students]
+    # only geo_loss carries a gradient; without this autograd materialises zeros_like() for every other output in
+    # backward, the multi-GB uint8 workspace included (0.85 ms of fill kernels per step at B=256)
+    ctx.set_materialize_grads(False)
     ctx.save_for_backward(output[1], proj_s, proj_t, log_temperatures, *students, *teachers, *attns)
 
 
