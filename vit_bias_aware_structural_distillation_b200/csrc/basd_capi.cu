@@ -275,9 +275,10 @@ extern "C" int basd_forward_stats(const basd_shape* shape, const basd_inputs* in
     __nv_bfloat16* z = reinterpret_cast<__nv_bfloat16*>(ws + L.z);
     __nv_bfloat16* zlo = z + static_cast<size_t>(s.Lt) * Mt * s.Ds;
     {
-        Scope sc(2, st, s.Lt);
-        for (int j = 0; j < s.Lt; ++j)
-            CK(gemm_project(r.teacher[j], Mt, s.Dt, pt_hi, pt_lo, s.Ds, z + static_cast<size_t>(j) * Mt * s.Ds, zlo + static_cast<size_t>(j) * Mt * s.Ds, st));
+        Scope sc(2, st, (s.Lt + 15) / 16);
+        const void* layers[kMaxLayers];
+        for (int j = 0; j < s.Lt; ++j) layers[j] = r.teacher[j];
+        CK(gemm_project(layers, s.Lt, Mt, s.Dt, pt_hi, pt_lo, s.Ds, z, zlo, st));
     }
     {
         Scope sc(3, st, 1 + s.P);

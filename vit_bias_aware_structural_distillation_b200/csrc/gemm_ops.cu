@@ -96,7 +96,8 @@ static cudaError_t launch(const GemmMaps& maps, const GemmArgs& args, dim3 grid,
 static inline int cdiv(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 
 //                      A_MN   B_MN   BN   MT NA NB T  alias  stages
-using CfgProject = GemmCfg<false, false, 192, 1, 1, 2, 2, false, 3>;
+using CfgProject = GemmCfg<false, false, 192, 2, 1, 2, 2, false, 2>;     // 256-row tiles: the split P_t tile (49 KB per k-block) is re-read half as often
+using CfgStudentGrad = GemmCfg<false, false, 192, 1, 1, 2, 2, false, 3>;
 using CfgGram    = GemmCfg<true,  true,  192, 2, 1, 1, 1, false, 3>;
 using CfgGram3   = GemmCfg<true,  true,  192, 2, 2, 2, 3, false, 2>;      // split operands: hi*hi + hi*lo + lo*hi
 using CfgTheta   = GemmCfg<false, true,  128, 2, 1, 1, 1, false, 4>;      // self test (single operands)
@@ -104,18 +105,28 @@ using CfgTheta3  = GemmCfg<false, true,  128, 2, 2, 2, 3, false, 2>;      // spl
 template <int BN> using CfgTokenGram = GemmCfg<false, false, BN, 2, 2, 2, 3, true, 3>;
 using CfgTestTN  = GemmCfg<false, false, 192, 1, 1, 1, 1, false, 4>;
 
-cudaError_t gemm_project(const __nv_bfloat16* X, size_t M, int Dt, const __nv_bfloat16* Phi, const __nv_bfloat16* Plo, int Ds,
+// Z[j] = X[j] P_t^T for all L_t teacher layers in ONE launch (blockIdx.z = layer; the layers are separate tensors, so each
+// has its own tensor map in maps.a_table).  12 launches of 392 CTAs each left the last wave of every launch 65 % empty.
+cudaError_t gemm_project(const void* const* X, int n_layers, size_t M, int Dt, const __nv_bfloat16* Phi, const __nv_bfloat16* Plo, int Ds,
                          __nv_bfloat16* Z, __nv_bfloat16* Zlo, cudaStream_t st) {
-    GemmMaps maps;
-    memset(&maps, 0, sizeof maps);
-    if (make_map(&maps.a[0], X, Dt, M, 1, Dt, M * Dt, 128)) return cudaErrorInvalidValue;
-    if (make_map(&maps.b[0], Phi, Dt, Ds, 1, Dt, static_cast<uint64_t>(Ds) * Dt, CfgProject::kBN)) return cudaErrorInvalidValue;
-    if (make_map(&maps.b[1], Plo, Dt, Ds, 1, Dt, static_cast<uint64_t>(Ds) * Dt, CfgProject::kBN)) return cudaErrorInvalidValue;
     GemmArgs a;
     memset(&a, 0, sizeof a);
     a.kb_total = cdiv(Dt, GEMM_BK);
-    a.out = Z; a.aux0 = Zlo; a.ld_out = Ds; a.rows_valid = static_cast<int>(M); a.cols_valid = Ds; a.alpha = 1.f;
-    return launch<CfgProject, EpiStoreSplit>(maps, a, dim3(cdiv(Ds, CfgProject::kBN), cdiv(M, 128), 1), st);
+    a.ld_out = Ds; a.rows_valid = static_cast<int>(M); a.cols_valid = Ds; a.alpha = 1.f;
+    a.out_batch_stride = static_cast<long long>(M) * Ds; a.a_table = 1;
+    for (int j0 = 0; j0 < n_layers; j0 += GEMM_MAX_A_TABLE) {
+        const int nl = n_layers - j0 < GEMM_MAX_A_TABLE ? n_layers - j0 : GEMM_MAX_A_TABLE;
+        GemmMaps maps;
+        memset(&maps, 0, sizeof maps);
+        for (int j = 0; j < nl; ++j)
+            if (make_map(&maps.a_table[j], X[j0 + j], Dt, M, 1, Dt, M * Dt, 128)) return cudaErrorInvalidValue;
+        if (make_map(&maps.b[0], Phi, Dt, Ds, 1, Dt, static_cast<uint64_t>(Ds) * Dt, CfgProject::kBN)) return cudaErrorInvalidValue;
+        if (make_map(&maps.b[1], Plo, Dt, Ds, 1, Dt, static_cast<uint64_t>(Ds) * Dt, CfgProject::kBN)) return cudaErrorInvalidValue;
+        a.out = Z + static_cast<size_t>(j0) * M * Ds; a.aux0 = Zlo + static_cast<size_t>(j0) * M * Ds;
+        cudaError_t e = launch<CfgProject, EpiStoreSplit>(maps, a, dim3(cdiv(Ds, CfgProject::kBN), cdiv(M, CfgProject::kMT * 128), nl), st);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 // G[batch] += Z[batch]^T Z[batch]; Z = [batches][M][Ds] contiguous (optionally a split hi/lo pair); G batch stride in floats.
@@ -198,14 +209,14 @@ cudaError_t gemm_student_grad(const __nv_bfloat16* S, size_t M, int Ds, const __
     GemmMaps maps;
     memset(&maps, 0, sizeof maps);
     if (make_map(&maps.a[0], S, Ds, M, 1, Ds, M * Ds, 128)) return cudaErrorInvalidValue;
-    if (make_map(&maps.b[0], Ghi, Ds, Ds, 1, Ds, static_cast<uint64_t>(Ds) * Ds, CfgProject::kBN)) return cudaErrorInvalidValue;
-    if (make_map(&maps.b[1], Glo, Ds, Ds, 1, Ds, static_cast<uint64_t>(Ds) * Ds, CfgProject::kBN)) return cudaErrorInvalidValue;
+    if (make_map(&maps.b[0], Ghi, Ds, Ds, 1, Ds, static_cast<uint64_t>(Ds) * Ds, CfgStudentGrad::kBN)) return cudaErrorInvalidValue;
+    if (make_map(&maps.b[1], Glo, Ds, Ds, 1, Ds, static_cast<uint64_t>(Ds) * Ds, CfgStudentGrad::kBN)) return cudaErrorInvalidValue;
     GemmArgs a;
     memset(&a, 0, sizeof a);
     a.kb_total = cdiv(Ds, GEMM_BK);
     a.out = out; a.ld_out = Ds; a.rows_valid = static_cast<int>(M); a.cols_valid = Ds;
     a.aux0 = gdir; a.aux1 = corr; a.aux2 = scale_ptr; a.alpha = scale_host; a.beta = out_is_bf16 ? 1.f : 0.f;
-    return launch<CfgProject, EpiStudentGrad>(maps, a, dim3(cdiv(Ds, CfgProject::kBN), cdiv(M, 128), 1), st);
+    return launch<CfgStudentGrad, EpiStudentGrad>(maps, a, dim3(cdiv(Ds, CfgStudentGrad::kBN), cdiv(M, 128), 1), st);
 }
 
 // ---------------------------------------------------------------------------------------------------

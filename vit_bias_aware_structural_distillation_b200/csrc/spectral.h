@@ -51,7 +51,8 @@ cudaError_t launch_loss_reduce(const float* loss_b, int P, int B, float* geo_i, 
 
 // ---- tcgen05 GEMM launchers (gemm_ops.cu)
 int gemm_init_driver_api();               // resolves cuTensorMapEncodeTiled; 0 on success
-cudaError_t gemm_project(const __nv_bfloat16* X, size_t M, int Dt, const __nv_bfloat16* Phi, const __nv_bfloat16* Plo,
+// Z[j] = X[j] P^T for n_layers separate [M][Dt] bf16 tensors; Zhi / Zlo are [n_layers][M][Ds]
+cudaError_t gemm_project(const void* const* X, int n_layers, size_t M, int Dt, const __nv_bfloat16* Phi, const __nv_bfloat16* Plo,
                          int Ds, __nv_bfloat16* Zhi, __nv_bfloat16* Zlo, cudaStream_t st);
 // Zlo may be null (exact bf16 input); otherwise Z = Zhi + Zlo and the Gram uses hi*hi + hi*lo + lo*hi
 cudaError_t gemm_gram(const __nv_bfloat16* Z, const __nv_bfloat16* Zlo, size_t M, int Ds, float* G /*[Ds][Ds] pre-zeroed*/,

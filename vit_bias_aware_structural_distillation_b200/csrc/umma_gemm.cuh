@@ -17,9 +17,11 @@ namespace basd {
 constexpr int GEMM_BK = 64;           // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int GEMM_THREADS = 192;     // warp0 TMA, warp1 MMA, warps2-5 epilogue
 
+constexpr int GEMM_MAX_A_TABLE = 16;
 struct GemmMaps {                     // up to two A and two B operand buffers (hi / lo)
     CUtensorMap a[2];
     CUtensorMap b[2];
+    CUtensorMap a_table[GEMM_MAX_A_TABLE];   // GemmArgs::a_table: A operand of batch z when the batches are separate allocations
 };
 
 struct GemmArgs {
@@ -28,6 +30,7 @@ struct GemmArgs {
     int n_splits;        // split-K: blockIdx.z = batch * n_splits + split
     int a_batched;       // A uses blockIdx.z as 3rd TMA coordinate
     int b_batched;       // B uses blockIdx.z as 3rd TMA coordinate
+    int a_table;         // A (single buffer) comes from maps.a_table[batch] (teacher layers live in separate tensors)
     // epilogue
     void* out;           // primary output
     long long out_batch_stride;   // elements
@@ -92,7 +95,7 @@ umma_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
         }
         mbar_init(tmem_full_bar, 1);
         fence_mbar_init();
-        for (int i = 0; i < Cfg::kNA; ++i) tma_prefetch_desc(&maps.a[i]);
+        for (int i = 0; i < Cfg::kNA; ++i) tma_prefetch_desc(args.a_table ? &maps.a_table[batch] : &maps.a[i]);
         if (!Cfg::kAlias)
             for (int i = 0; i < Cfg::kNB; ++i) tma_prefetch_desc(&maps.b[i]);
     }
@@ -117,14 +120,15 @@ umma_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
 #pragma unroll
                 for (int i = 0; i < Cfg::kNA; ++i) {
                     uint8_t* dst = st + i * Cfg::kABytes;
+                    const CUtensorMap* amap = args.a_table ? &maps.a_table[batch] : &maps.a[i];
                     if (Cfg::kAMN) {
 #pragma unroll
                         for (int g = 0; g < Cfg::kMT * 2; ++g)
-                            tma_load_3d(dst + g * 8192, &maps.a[i], &full_bar[s], a_row0 + g * 64, kb * GEMM_BK, za);
+                            tma_load_3d(dst + g * 8192, amap, &full_bar[s], a_row0 + g * 64, kb * GEMM_BK, za);
                     } else {
 #pragma unroll
                         for (int mt = 0; mt < Cfg::kMT; ++mt)
-                            tma_load_3d(dst + mt * 16384, &maps.a[i], &full_bar[s], kb * GEMM_BK, a_row0 + mt * 128, za);
+                            tma_load_3d(dst + mt * 16384, amap, &full_bar[s], kb * GEMM_BK, a_row0 + mt * 128, za);
                     }
                 }
                 if (!Cfg::kAlias) {
