@@ -344,18 +344,20 @@ def main():
     # dominant kernel: algorithmic work per launch / its average launch duration (CUDA events on the launching stream)
     n_prob = w.P * w.B
     ksteps = int(lib.basd_polar_steps())
-    polar_launches = 4 * ksteps + 2
+    per_ns_step = int(lib.basd_polar_launches_per_step(w.Ds, w.Ns))      # 3: A = T W^T and the polynomial in A fused (A stays on chip)
+    polar_launches = per_ns_step * ksteps + 2
     polar_flops = n_prob * (ksteps * (2 * w.Ds * w.Ns * w.Ns + 2 * w.Ds * w.Ds * w.Ns + 2 * w.Ds ** 3 + 2 * w.Ds * w.Ds * w.Ns)
                             + 2 * w.Ns * w.Ns * w.Ds + 2 * w.Ns * w.Ds * w.Ns)
     # polar_gemm as launched: every product streams its split-bf16 (hi + lo = 4 B per element) operands in and its result
     # out once per launch; these are the algorithmic bytes of the MULTI-LAUNCH formulation (unpadded), DESIGN.md section 5
     D, N = w.Ds, w.Ns
-    polar_bytes = n_prob * 4 * (ksteps * ((2 * D * N + N * N) + (2 * D * N + D * D) + 2 * D * D + (D * D + 2 * D * N))
+    ab_bytes = (2 * D * N + D * D) if per_ns_step == 3 else (2 * D * N + D * D) + 2 * D * D      # fused: T, W in, Bm out
+    polar_bytes = n_prob * 4 * (ksteps * ((2 * D * N + N * N) + ab_bytes + (D * D + 2 * D * N))
                                 + (N * N + D * N + N * D) + (2 * N * D + N * N))
     eig_bytes = 4 * ((2 * w.Lt + w.P) * (D * D + D) + (w.Lt + w.P) * (2 * D * D + D))
     table = {   # slot -> (bound, algorithmic units per step, launches per step, description)
         "polar_gemm": ("hbm", polar_bytes, polar_launches,
-                       "Newton-Schulz polar iteration, (4 x steps + 2) batched products per step: split-bf16 operands read once and the "
+                       f"Newton-Schulz polar iteration, ({per_ns_step} x steps + 2) batched launches per step: split-bf16 operands read once and the "
                        "result written once per launch (4 B per element, unpadded).  Tensor view of the same kernel: "
                        f"{polar_flops / polar_launches / 1e9:.1f} GFLOP of plain 2mnk per launch (3 split MMAs per product not counted)"),
         "pooled_eig": ("hbm", eig_bytes, 1,

@@ -106,8 +106,11 @@ int basd_timing_slots(void);
 const char* basd_timing_name(int slot);
 int basd_timing_read(int slot, float* ms_total, int* brackets);
 
-/* Number of Newton-Schulz steps of the Procrustes polar iteration (4 tensor-core products per step + 2 final ones). */
+/* Number of Newton-Schulz steps of the Procrustes polar iteration. */
 int basd_polar_steps(void);
+/* Products launched per Newton-Schulz step for these sizes: 3 when A = T W^T and the polynomial in A are fused into one
+ * kernel (D_s <= 192), 4 otherwise.  For bench.py's launch and byte counts. */
+int basd_polar_launches_per_step(int Ds, int Ns);
 
 const char* basd_last_error(void);
 const char* basd_version(void);

@@ -36,7 +36,7 @@ EXPORTS = [
     "basd_workspace_bytes", "basd_forward_stats", "basd_forward_solve", "basd_backward_dots", "basd_backward_finish",
     "basd_view", "basd_mp_rank_workspace_bytes", "basd_mp_rank", "basd_selftest_gemm", "basd_selftest_eig",
     "basd_last_error", "basd_version", "basd_timing_enable", "basd_timing_reset", "basd_launch_count", "basd_timing_slots",
-    "basd_timing_name", "basd_timing_read", "basd_polar_steps", "basd_cls_attention_rows",
+    "basd_timing_name", "basd_timing_read", "basd_polar_steps", "basd_polar_launches_per_step", "basd_cls_attention_rows",
 ]
 
 _lib = None

@@ -77,6 +77,8 @@ TimingScope::~TimingScope() { delete static_cast<Scope*>(impl); }
 }  // namespace basd
 extern "C" const char* basd_version(void) { return "basd_b200 0.1 (sm_100a)"; }
 extern "C" int basd_polar_steps(void) { return basd::polar_steps(); }
+namespace basd { int polar_launches_per_step(int Ds, int Ns); }
+extern "C" int basd_polar_launches_per_step(int Ds, int Ns) { return basd::polar_launches_per_step(Ds, Ns); }
 namespace basd { long long* polar_dbg_ptr(int which); }
 // development aid (not in the public header): copies the phase clocks recorded by CTA 0 of one polar GEMM launch
 extern "C" int basd_debug_polar_clocks(int which, long long* host_out) {

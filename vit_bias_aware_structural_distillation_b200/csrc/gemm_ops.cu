@@ -8,6 +8,7 @@
 
 #include "spectral.h"
 #include "polar_gemm.cuh"
+#include "polar_fused.cuh"
 #include "umma_gemm.cuh"
 
 namespace basd {
@@ -59,7 +60,7 @@ static int make_map(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t 
 
 // bf16 split matrix stored column-block tiled: [batch][col / 64][row][col % 64]; box = [1][1][box_rows][64].
 static int make_map_tiled(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t col_blocks, uint64_t batch, uint64_t batch_pitch_elems,
-                          uint32_t box_rows) {
+                          uint32_t box_rows, uint32_t box_inner = 64) {
     if (gemm_init_driver_api()) return 1;
     if ((reinterpret_cast<uintptr_t>(ptr) & 127) || (batch_pitch_elems * 2) % 16) {
         snprintf(g_gemm_err, sizeof g_gemm_err, "tiled TMA operand misaligned: ptr=%p batch_pitch=%llu", ptr, (unsigned long long)batch_pitch_elems);
@@ -67,11 +68,11 @@ static int make_map_tiled(CUtensorMap* map, const void* ptr, uint64_t rows, uint
     }
     cuuint64_t dims[4] = {64, rows, col_blocks, batch};
     cuuint64_t strides[3] = {128, rows * 128, batch_pitch_elems * 2};
-    cuuint32_t box[4] = {64, box_rows, 1, 1};
+    cuuint32_t box[4] = {box_inner, box_rows, 1, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, box_inner == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         snprintf(g_gemm_err, sizeof g_gemm_err, "cuTensorMapEncodeTiled (tiled) failed (%d) rows=%llu blocks=%llu batch=%llu box_rows=%u", (int)r,
                  (unsigned long long)rows, (unsigned long long)col_blocks, (unsigned long long)batch, box_rows);
@@ -296,6 +297,55 @@ cudaError_t polar_gemm(bool b_mn, const SplitMat& A, const SplitMat& B, int batc
     }
     const int grid = a.n_items < sm_count ? a.n_items : sm_count;
     kern<<<grid, PG_THREADS, smem, st>>>(maps, a);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// polar_fused_abm: Bm = ca I + cb (rA) + cc (rA)^2 with A = T W^T kept on chip (polar_fused.cuh); D_s <= 192
+// ---------------------------------------------------------------------------------------------------
+bool polar_fused_supported(int n, int k) { return n <= 192 && k <= 256 && n >= 16; }
+cudaError_t polar_fused_abm(const SplitMat& T, const SplitMat& W, const SplitMat& Bm, int batches, PolarFusedArgs& a, cudaStream_t st) {
+    const int n = T.rows, K = T.inner;
+    if (!polar_fused_supported(n, K) || W.rows != n || W.inner != K || Bm.rows != n || Bm.inner != n) {
+        snprintf(g_gemm_err, sizeof g_gemm_err, "polar_fused_abm: unsupported sizes n=%d k=%d", n, K);
+        return cudaErrorInvalidValue;
+    }
+    a.n = n; a.k_total = K; a.bn = (n + 15) / 16 * 16; a.rows_ld = (n + 63) / 64 * 64; a.n_mt = (n + 127) / 128; a.n_problems = batches;
+    PolarFusedMaps maps;
+    memset(&maps, 0, sizeof maps);
+    const __nv_bfloat16* tp[2] = {T.hi, T.lo};
+    const __nv_bfloat16* wp[2] = {W.hi, W.lo};
+    __nv_bfloat16* op[2] = {Bm.hi, Bm.lo};
+    for (int i = 0; i < 2; ++i) {
+        if (make_map_tiled(&maps.t[i], tp[i], T.rows, (T.inner + 63) / 64, batches, T.batch_stride, 64)) return cudaErrorInvalidValue;
+        if (make_map_tiled(&maps.w[i], wp[i], W.rows, (W.inner + 63) / 64, batches, W.batch_stride, a.bn)) return cudaErrorInvalidValue;
+        if (make_map_tiled(&maps.o[i], op[i], Bm.rows, (Bm.inner + 63) / 64, batches, Bm.batch_stride, 32, 32)) return cudaErrorInvalidValue;
+    }
+    const int stage_bytes = 2 * a.rows_ld * 128 + 2 * a.bn * 128;
+    const int ring_bytes = PF_STAGES * stage_bytes;
+    const int copy_bytes = 2 * ((n + 63) / 64) * a.rows_ld * 128;
+    if (copy_bytes + 8192 > ring_bytes) {                      // (tile 1 of the last block reads up to 64 rows past the copy)
+        snprintf(g_gemm_err, sizeof g_gemm_err, "polar_fused_abm: operand copy (%d B) does not fit the ring (%d B)", copy_bytes, ring_bytes);
+        return cudaErrorInvalidValue;
+    }
+    const int smem = ring_bytes + 1024 /*alignment*/ + 1024 /*barriers*/ + 8 * 4096 /*staging*/;
+    if (smem > 232448) {
+        snprintf(g_gemm_err, sizeof g_gemm_err, "polar_fused_abm: %d B of shared memory needed", smem);
+        return cudaErrorInvalidValue;
+    }
+    static bool configured = false;
+    static int sm_count = 0;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(polar_fused_abm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        if (e != cudaSuccess) return e;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (sm_count <= 0) sm_count = 148;
+        configured = true;
+    }
+    const int grid = batches < sm_count ? batches : sm_count;
+    polar_fused_abm_kernel<<<grid, PF_THREADS, smem, st>>>(maps, a);
     return cudaGetLastError();
 }
 

@@ -416,6 +416,15 @@ polar_finish_kernel(PolarArgs g) {
 }  // namespace
 
 int polar_steps() { return kPolarSteps; }
+static bool polar_use_fused(int D, int N) {      // BASD_POLAR_FUSED=0: keep G2 and G3 as two launches (development knob)
+    static int fused_cfg = -1;
+    if (fused_cfg < 0) {
+        const char* e = getenv("BASD_POLAR_FUSED");
+        fused_cfg = e ? atoi(e) : 1;
+    }
+    return fused_cfg != 0 && polar_fused_supported(D, N);
+}
+int polar_launches_per_step(int Ds, int Ns) { return polar_use_fused(Ds, Ns) ? 3 : 4; }
 
 __device__ long long g_polar_dbg[4][16 * 8];
 long long* polar_dbg_ptr(int which) { long long* p = nullptr; cudaGetSymbolAddress(reinterpret_cast<void**>(&p), g_polar_dbg); return p + which * 128; }
@@ -455,8 +464,9 @@ cudaError_t launch_polar_procrustes(const PolarArgs& g, cudaStream_t st, int* la
     }
     const int chunk = (chunk_cfg <= 0 || chunk_cfg > nprob) ? nprob : chunk_cfg;
     const int n_chunks = (nprob + chunk - 1) / chunk;
+    const bool fused = polar_use_fused(D, N);
     auto at = [](const SplitMat& m, int z0) { SplitMat r = m; r.hi += z0 * m.batch_stride; r.lo += z0 * m.batch_stride; return r; };
-    TimingScope* gemm_scope = new TimingScope(kSlotPolarGemm, st, n_chunks * (4 * kPolarSteps + 2));
+    TimingScope* gemm_scope = new TimingScope(kSlotPolarGemm, st, n_chunks * ((fused ? 3 : 4) * kPolarSteps + 2));
     struct Del { TimingScope*& p; ~Del() { delete p; } } gemm_del{gemm_scope};
     for (int z0 = 0; z0 < nprob; z0 += chunk) {
         const int nz = nprob - z0 < chunk ? nprob - z0 : chunk;
@@ -477,22 +487,33 @@ cudaError_t launch_polar_procrustes(const PolarArgs& g, cudaStream_t st, int* la
             if (k == 3 && z0 == 0 && getenv("BASD_POLAR_DBG")) a.dbg_clock = polar_dbg_ptr(0);
             a.reverse = (dir++) & 1;
             PCK(polar_gemm(false, Wc, Kt, nz, a, st));
-            // G2: A = T W^T                (step 0: trace(A) = ||C||_F^2, read by the epilogues of G3 / G4 of that step)
-            memset(&a, 0, sizeof a);
-            a.epi = PG_EPI_SPLIT; a.out_hi = A.hi; a.out_lo = A.lo; a.out_stride = A.batch_stride; a.scale_c = 1.f;
-            if (first) a.trace = fro2;
-            if (k == 3 && z0 == 0 && getenv("BASD_POLAR_DBG")) a.dbg_clock = polar_dbg_ptr(1);
-            a.reverse = (dir++) & 1;
-            PCK(polar_gemm(false, T, Wc, nz, a, st));
-            // G3: Bm = a I + b (rA) + c (rA)^2   (A is both operands: the A tile aliases the B tile; the b A term is added from
-            //     a TMA-loaded copy of the output-shaped tile of A in the epilogue)
-            memset(&a, 0, sizeof a);
-            a.epi = PG_EPI_SPLIT; a.out_hi = Bm.hi; a.out_lo = Bm.lo; a.out_stride = Bm.batch_stride;
-            a.a_alias_b = 1; a.aux_mode = 1; a.aux_hi = A.hi; a.aux_lo = A.lo;
-            a.aux_c = cb; a.aux_p = first ? 1.f : 0.f; a.scale_c = cc; a.scale_p = first ? 2.f : 0.f; a.diag_add = ca; a.norm2 = norm;
-            if (k == 3 && z0 == 0 && getenv("BASD_POLAR_DBG")) a.dbg_clock = polar_dbg_ptr(2);
-            a.reverse = (dir++) & 1;
-            PCK(polar_gemm(false, A, A, nz, a, st));
+            if (fused) {
+                // G2 + G3 in one kernel: A = T W^T stays in TMEM / shared memory, Bm = a I + b (rA) + c (rA)^2 leaves
+                // (step 0: trace(A) = ||C||_F^2 is reduced inside and written to fro2 for G4's epilogue)
+                PolarFusedArgs f;
+                memset(&f, 0, sizeof f);
+                f.ca = ca; f.cb = cb; f.cc = cc; f.first = first ? 1 : 0; f.fro2 = fro2;
+                f.reverse = (dir++) & 1;
+                PCK(polar_fused_abm(T, Wc, Bm, nz, f, st));
+                count -= 1;
+            } else {
+                // G2: A = T W^T                (step 0: trace(A) = ||C||_F^2, read by the epilogues of G3 / G4 of that step)
+                memset(&a, 0, sizeof a);
+                a.epi = PG_EPI_SPLIT; a.out_hi = A.hi; a.out_lo = A.lo; a.out_stride = A.batch_stride; a.scale_c = 1.f;
+                if (first) a.trace = fro2;
+                if (k == 3 && z0 == 0 && getenv("BASD_POLAR_DBG")) a.dbg_clock = polar_dbg_ptr(1);
+                a.reverse = (dir++) & 1;
+                PCK(polar_gemm(false, T, Wc, nz, a, st));
+                // G3: Bm = a I + b (rA) + c (rA)^2   (A is both operands: the A tile aliases the B tile; the b A term is added from
+                //     a TMA-loaded copy of the output-shaped tile of A in the epilogue)
+                memset(&a, 0, sizeof a);
+                a.epi = PG_EPI_SPLIT; a.out_hi = Bm.hi; a.out_lo = Bm.lo; a.out_stride = Bm.batch_stride;
+                a.a_alias_b = 1; a.aux_mode = 1; a.aux_hi = A.hi; a.aux_lo = A.lo;
+                a.aux_c = cb; a.aux_p = first ? 1.f : 0.f; a.scale_c = cc; a.scale_p = first ? 2.f : 0.f; a.diag_add = ca; a.norm2 = norm;
+                if (k == 3 && z0 == 0 && getenv("BASD_POLAR_DBG")) a.dbg_clock = polar_dbg_ptr(2);
+                a.reverse = (dir++) & 1;
+                PCK(polar_gemm(false, A, A, nz, a, st));
+            }
             // G4: W_next = sqrt(r) Bm W      (W enters as the MN-major B operand; ping-pong buffers)
             memset(&a, 0, sizeof a);
             a.epi = PG_EPI_SPLIT; a.out_hi = Wn.hi; a.out_lo = Wn.lo; a.out_stride = Wn.batch_stride;

@@ -88,6 +88,20 @@ struct SplitMat {                         // bf16 hi/lo pair, column-block tiled
     long long batch_stride;               // elements per problem = ceil(inner / 64) * rows * 64
     __host__ __device__ size_t at(int r, int c) const { return (static_cast<size_t>(c >> 6) * rows + r) * 64 + (c & 63); }
 };
+struct PolarFusedArgs {
+    int n;                           // D_s: rows of T and W, order of A
+    int k_total;                     // N_s
+    int bn;                          // n rounded up to 16 (UMMA N)
+    int rows_ld;                     // n rounded up to 64 (rows loaded / copied per k-block)
+    int n_mt;                        // 128-row tiles (1 or 2)
+    int n_problems, reverse;
+    float ca, cb, cc;                // Bm = ca I + cb (rA) + cc (rA)^2
+    int first;                       // step 0: r = 1 / trace(A) (written to fro2); otherwise r = 1
+    float* fro2;                     // [problem]
+};
+// Bm = ca I + cb (rA) + cc (rA)^2 with A = T W^T kept on chip (polar_fused.cuh); needs polar_fused_supported(D_s, N_s)
+bool polar_fused_supported(int n, int k);
+cudaError_t polar_fused_abm(const SplitMat& T, const SplitMat& W, const SplitMat& Bm, int batches, PolarFusedArgs& args, cudaStream_t st);
 struct PolarGemmArgs;
 // out = A (rows x K, K-major) * B^T; B is K-major ([n_cols][K]) or, with b_mn, the row-major [K][n_cols] buffer.
 cudaError_t polar_gemm(bool b_mn, const SplitMat& A, const SplitMat& B, int batches, PolarGemmArgs& args, cudaStream_t st);
