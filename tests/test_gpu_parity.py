@@ -117,7 +117,7 @@ def test_tcgen05_gemm_variants(lib, cuda_dev, variant, M, N, Kd):
     assert (C.cpu() - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
 
 
-@pytest.mark.parametrize("n", [16, 48, 100, 192, 224])
+@pytest.mark.parametrize("n", [16, 48, 51, 100, 130, 192, 224])
 def test_jacobi_eigensolver(lib, cuda_dev, n):
     """Shared-memory one-sided Jacobi vs LAPACK (fp64): eigenvalues, residual, orthogonality."""
     torch.manual_seed(n)
@@ -446,7 +446,8 @@ def test_cls_attention_rows_from_q_k(lib, cuda_dev):
     dict(B=5, Ns=36, Nt=36, Ds=32, Dt=32, Lt=4, H=1, P=1),          # a single extraction point (combined.py:34-36), D_t == D_s
     dict(B=2, Ns=130, Nt=130, Ds=96, Dt=200, Lt=3, H=2, P=2),       # N > 128: two 128-row output tiles in the N x N products
     dict(B=2, Ns=70, Nt=90, Ds=64, Dt=136, Lt=2, H=2, P=4),         # down-sampling 90 -> 70 with D_s exactly one column block
-    dict(B=9, Ns=210, Nt=210, Ds=200, Dt=256, Lt=2, H=2, P=2),      # D_s > 192: round-robin Jacobi path, 4 column blocks
+    dict(B=9, Ns=210, Nt=210, Ds=200, Dt=256, Lt=2, H=2, P=2),      # D_s > 192: 7-chunk cluster Jacobi, unfused polar products, 4 column blocks
+    dict(B=3, Ns=160, Nt=160, Ds=144, Dt=192, Lt=2, H=2, P=2),      # fused polar kernel with a partial second row tile (144 = 128 + 16)
 ])
 def test_irregular_shapes_against_oracle(lib, cuda_dev, shape):
     """Shapes off the BASELINE grid: padding, tails and tile boundaries of every kernel against the fp32 oracle."""

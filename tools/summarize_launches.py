@@ -3,7 +3,7 @@
     python tools/summarize_launches.py --traffic traffic.csv [steps] out.json   DRAM bytes per launch per kernel -> json"""
 import collections, csv, json, sys
 
-SLOT = {"polar_gemm_kernel": "polar_gemm", "pooled_eig_kernel": "pooled_eig", "angles_kernel": "angles", "wgrad_dots_kernel": "wgrad_dots",
+SLOT = {"polar_gemm_kernel": "polar_gemm", "polar_fused_abm_kernel": "polar_gemm", "pooled_eig_kernel": "pooled_eig", "angles_kernel": "angles", "wgrad_dots_kernel": "wgrad_dots",
         "mix_teacher_kernel": "mix_teacher", "colsum_kernel": "colsum", "polar_prep_student_kernel": "polar_prep", "polar_prep_student_vec_kernel": "polar_prep",
         "polar_prep_teacher_kernel": "polar_prep", "polar_finish_kernel": "polar_finish", "importance_rows_kernel": "importance_rows"}
 
