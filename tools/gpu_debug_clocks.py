@@ -26,6 +26,12 @@ for which in range(4):
     print("   " + " ".join(f"{c:>12s}" for c in cols))
     for i in range(14):
         print(f"{i:2d} " + " ".join(f"{(v - t0):12d}" for v in t[i].tolist()))
+    if which == 1 and lib.basd_polar_launches_per_step(w.Ds, w.Ns) == 3:
+        print("   (fused A/Bm kernel: columns = loads_start, loads_issued, phase1_start, phase1_issued, copy_seen, phase2_issued, store_start, store_done)")
+        continue
+    if which == 2 and lib.basd_polar_launches_per_step(w.Ds, w.Ns) == 3:
+        print("   (not launched: fused into the previous kernel)")
+        continue
     e = t[15].tolist()
     print(f"   epilogue of item 5, column block 1 (cycles): tmem ld {e[1]-e[0]}, convert+stage {e[2]-e[1]}, fence+syncwarp {e[3]-e[2]}, "
           f"tma store issue {e[4]-e[3]}, wait_group.read {e[5]-e[4]}")

@@ -493,6 +493,7 @@ cudaError_t launch_polar_procrustes(const PolarArgs& g, cudaStream_t st, int* la
                 PolarFusedArgs f;
                 memset(&f, 0, sizeof f);
                 f.ca = ca; f.cb = cb; f.cc = cc; f.first = first ? 1 : 0; f.fro2 = fro2;
+                if (k == 3 && z0 == 0 && getenv("BASD_POLAR_DBG")) f.dbg_clock = polar_dbg_ptr(1);
                 f.reverse = (dir++) & 1;
                 PCK(polar_fused_abm(T, Wc, Bm, nz, f, st));
                 count -= 1;

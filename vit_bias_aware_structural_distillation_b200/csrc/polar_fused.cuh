@@ -68,8 +68,8 @@ polar_fused_abm_kernel(const __grid_constant__ PolarFusedMaps maps, const PolarF
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + ring_bytes);
     uint64_t* empty_bar = full_bar + PF_STAGES;
     uint64_t* acc1_bar = empty_bar + PF_STAGES;                // A complete in TMEM
-    uint64_t* copy_bar = acc1_bar + 1;                         // operand copy written (4 n_mt warps)
-    uint64_t* acc2_bar = copy_bar + 1;                         // A + (c r / b) A^2 complete in TMEM
+    uint64_t* copy_bar = acc1_bar + 1;                         // [4] 64-column block kb of the operand copy written (4 n_mt warps)
+    uint64_t* acc2_bar = copy_bar + 4;                         // A + (c r / b) A^2 complete in TMEM
     uint64_t* p2done_bar = acc2_bar + 1;                       // phase 2 retired: the ring memory is free again
     uint64_t* tmem_empty_bar = p2done_bar + 1;                 // accumulators drained (4 n_mt warps)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 1);
@@ -80,7 +80,8 @@ polar_fused_abm_kernel(const __grid_constant__ PolarFusedMaps maps, const PolarF
     if (threadIdx.x == 0) {
         for (int s = 0; s < PF_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(acc1_bar, 1); mbar_init(acc2_bar, 1); mbar_init(p2done_bar, 1);
-        mbar_init(copy_bar, 4 * args.n_mt); mbar_init(tmem_empty_bar, 4 * args.n_mt);
+        for (int i = 0; i < 4; ++i) mbar_init(&copy_bar[i], 4 * args.n_mt);
+        mbar_init(tmem_empty_bar, 4 * args.n_mt);
         trace_s[0] = 0.f; trace_s[1] = 0.f;
         fence_mbar_init();
         tma_prefetch_desc(&maps.t[0]); tma_prefetch_desc(&maps.t[1]);
@@ -103,6 +104,7 @@ polar_fused_abm_kernel(const __grid_constant__ PolarFusedMaps maps, const PolarF
             for (int w = blockIdx.x; w < args.n_problems; w += gridDim.x, ++item) {
                 const int z = args.reverse ? args.n_problems - 1 - w : w;
                 if (item > 0) mbar_wait(p2done_bar, (item - 1) & 1);       // the operand copy of the previous problem is dead
+                if (args.dbg_clock && blockIdx.x == 0 && item < 16) args.dbg_clock[item * 8 + 0] = clock64();
                 for (int kb = 0; kb < n_kb; ++kb, ++it) {
                     const int s = it % PF_STAGES;
                     const uint32_t ph = (it / PF_STAGES) & 1;
@@ -115,6 +117,7 @@ polar_fused_abm_kernel(const __grid_constant__ PolarFusedMaps maps, const PolarF
                         tma_load_4d(st + 2 * a_bytes + i * b_bytes, &maps.w[i], &full_bar[s], 0, 0, kb, z);
                     }
                 }
+                if (args.dbg_clock && blockIdx.x == 0 && item < 16) args.dbg_clock[item * 8 + 1] = clock64();
             }
         }
     } else if (warp == 1) {
@@ -126,6 +129,8 @@ polar_fused_abm_kernel(const __grid_constant__ PolarFusedMaps maps, const PolarF
             const uint32_t ph_item = item & 1;
             mbar_wait(tmem_empty_bar, ph_item ^ 1);               // the store phase of the previous problem has drained TMEM
             tc_fence_after();
+            const bool dbg_m = args.dbg_clock && blockIdx.x == 0 && item < 16 && lane == 0;
+            if (dbg_m) args.dbg_clock[item * 8 + 2] = clock64();
             for (int kb = 0; kb < n_kb; ++kb, ++it) {             // phase 1: A = T W^T
                 const int s = it % PF_STAGES;
                 const uint32_t ph = (it / PF_STAGES) & 1;
@@ -146,14 +151,17 @@ polar_fused_abm_kernel(const __grid_constant__ PolarFusedMaps maps, const PolarF
                         }
                     }
                     umma_commit(&empty_bar[s]);
-                    if (kb == n_kb - 1) umma_commit(acc1_bar);
+                    if (kb == n_kb - 1) { umma_commit(acc1_bar); if (dbg_m) args.dbg_clock[item * 8 + 3] = clock64(); }
                 }
                 __syncwarp();
             }
-            mbar_wait(copy_bar, ph_item);                         // A~ is in shared memory (generic-proxy writes, fenced)
-            tc_fence_after();
             if (lane == 0) {                                      // phase 2: acc += (-A~) A~
                 const uint32_t cp = smem_u32(smem);
+                // every block of A~ must be in shared memory first: the MMAs overwrite the accumulator columns the copy
+                // is still reading (generic-proxy writes, fenced by the writers)
+                for (int kb = 0; kb < n_kb2; ++kb) mbar_wait(&copy_bar[kb], ph_item);
+                tc_fence_after();
+                if (dbg_m) args.dbg_clock[item * 8 + 4] = clock64();
                 for (int kb = 0; kb < n_kb2; ++kb) {
                     int ksteps = (args.n - kb * 64 + 15) / 16;
                     if (ksteps > 4) ksteps = 4;
@@ -170,6 +178,7 @@ polar_fused_abm_kernel(const __grid_constant__ PolarFusedMaps maps, const PolarF
                 }
                 umma_commit(acc2_bar);
                 umma_commit(p2done_bar);
+                if (dbg_m) args.dbg_clock[item * 8 + 5] = clock64();
             }
             __syncwarp();
         }
@@ -209,8 +218,8 @@ polar_fused_abm_kernel(const __grid_constant__ PolarFusedMaps maps, const PolarF
             }
             // ---- copy: A~ = s A as a split pair, K-major SWIZZLE_128B operand layout [half][64-column block][row]
             const float s_copy = sqrtf(args.cc * r / fabsf(args.cb));
-            if (row0 < args.rows_ld) {
-                for (int cbk = 0; cbk < n_kb2; ++cbk) {
+            for (int cbk = 0; cbk < n_kb2; ++cbk) {
+                if (row0 < args.rows_ld) {
                     float vb[64];
                     const int cols_here = min(64, args.bn - cbk * 64);
                     if (cols_here == 64) {
@@ -233,13 +242,15 @@ polar_fused_abm_kernel(const __grid_constant__ PolarFusedMaps maps, const PolarF
                         }
                     }
                 }
+                fence_proxy_async_smem();                         // generic-proxy writes -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&copy_bar[cbk]);
             }
-            fence_proxy_async_smem();                             // generic-proxy writes -> visible to the tensor core
-            __syncwarp();
-            if (lane == 0) mbar_arrive(copy_bar);
             // ---- store: Bm = ca I + (cb r) acc
             mbar_wait(acc2_bar, ph_item);
             tc_fence_after();
+            const bool dbg_e = args.dbg_clock && blockIdx.x == 0 && item < 16 && e == 0 && lane == 0;
+            if (dbg_e) args.dbg_clock[item * 8 + 6] = clock64();
             const float sc = args.cb * r;
             const int n_ch = (args.bn + 31) / 32;
             for (int ch = 0; ch < n_ch; ++ch) {
@@ -252,12 +263,25 @@ polar_fused_abm_kernel(const __grid_constant__ PolarFusedMaps maps, const PolarF
                     const int c = c0 + jc * 16;
                     float* v = vb + jc * 16;
                     if (c < args.bn) {
+                        if (c0 == row0) {                          // the only chunk of this warp that holds diagonal entries
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = sc * v[i] + ((c + i == row) ? args.ca : 0.f);
-                        pf_stage_split16_sw64(stg_hi_s, stg_lo_s, lane, jc * 2, v);
-                    } else {
-                        pf_stage_zero16_sw64(stg_hi_s, stg_lo_s, lane, jc * 2);
+                            for (int i = 0; i < 16; ++i) v[i] = sc * v[i] + ((c + i == row) ? args.ca : 0.f);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] *= sc;
+                        }
                     }
+                }
+                // the TMA store of the previous chunk may still be reading the staging tile: wait only now, after this
+                // chunk's TMEM load and arithmetic
+                if (ch > 0) {
+                    if (lane == 0 && warp_rows_ok) tma_store_wait_read();
+                    __syncwarp();
+                }
+#pragma unroll
+                for (int jc = 0; jc < 2; ++jc) {
+                    if (c0 + jc * 16 < args.bn) pf_stage_split16_sw64(stg_hi_s, stg_lo_s, lane, jc * 2, vb + jc * 16);
+                    else pf_stage_zero16_sw64(stg_hi_s, stg_lo_s, lane, jc * 2);
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
@@ -265,12 +289,13 @@ polar_fused_abm_kernel(const __grid_constant__ PolarFusedMaps maps, const PolarF
                     tma_store_4d(&maps.o[0], stg_hi, (ch & 1) * 32, row0, ch >> 1, z);
                     tma_store_4d(&maps.o[1], stg_lo, (ch & 1) * 32, row0, ch >> 1, z);
                     tma_store_commit();
-                    tma_store_wait_read();
                 }
-                __syncwarp();
             }
+            if (lane == 0 && warp_rows_ok) tma_store_wait_read();     // (the next problem's first chunk overwrites the tile)
+            __syncwarp();
             tc_fence_before();
             __syncwarp();
+            if (dbg_e) args.dbg_clock[item * 8 + 7] = clock64();
             if (lane == 0) mbar_arrive(tmem_empty_bar);
         }
         if (lane == 0) tma_store_wait_all();

@@ -98,6 +98,7 @@ struct PolarFusedArgs {
     float ca, cb, cc;                // Bm = ca I + cb (rA) + cc (rA)^2
     int first;                       // step 0: r = 1 / trace(A) (written to fro2); otherwise r = 1
     float* fro2;                     // [problem]
+    long long* dbg_clock;            // development aid: CTA 0 records clock64() per phase of its first problems ([problem][8])
 };
 // Bm = ca I + cb (rA) + cc (rA)^2 with A = T W^T kept on chip (polar_fused.cuh); needs polar_fused_supported(D_s, N_s)
 bool polar_fused_supported(int n, int k);
