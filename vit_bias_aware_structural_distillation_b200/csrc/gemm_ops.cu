@@ -98,11 +98,11 @@ static inline int cdiv(long long a, long long b) { return static_cast<int>((a + 
 
 //                      A_MN   B_MN   BN   MT NA NB T  alias  stages
 using CfgProject = GemmCfg<false, false, 192, 2, 1, 2, 2, false, 2>;     // 256-row tiles: the split P_t tile (49 KB per k-block) is re-read half as often
-using CfgStudentGrad = GemmCfg<false, false, 192, 1, 1, 2, 2, false, 3>;
+using CfgStudentGrad = GemmCfg<false, false, 192, 1, 1, 2, 2, false, 1>;   // one stage (65 KB), 256 TMEM columns: two CTAs per SM overlap each other
 using CfgGram    = GemmCfg<true,  true,  192, 2, 1, 1, 1, false, 3>;
 using CfgGram3   = GemmCfg<true,  true,  192, 2, 2, 2, 3, false, 2>;      // split operands: hi*hi + hi*lo + lo*hi
 using CfgTheta   = GemmCfg<false, true,  128, 2, 1, 1, 1, false, 4>;      // self test (single operands)
-using CfgTheta3  = GemmCfg<false, true,  128, 2, 2, 2, 3, false, 2>;      // split Theta x split mixed teacher
+using CfgTheta3  = GemmCfg<false, true,  128, 2, 2, 2, 3, false, 1>;      // split Theta x split mixed teacher; one stage (96 KB), 256 TMEM columns: two CTAs per SM
 template <int BN> using CfgTokenGram = GemmCfg<false, false, BN, 2, 2, 2, 3, true, 3>;
 using CfgTestTN  = GemmCfg<false, false, 192, 1, 1, 1, 1, false, 4>;
 
