@@ -117,7 +117,7 @@ def test_tcgen05_gemm_variants(lib, cuda_dev, variant, M, N, Kd):
     assert (C.cpu() - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
 
 
-@pytest.mark.parametrize("n", [16, 48, 51, 100, 130, 192, 224])
+@pytest.mark.parametrize("n", [16, 33, 48, 51, 77, 100, 130, 191, 192, 224])
 def test_jacobi_eigensolver(lib, cuda_dev, n):
     """Shared-memory one-sided Jacobi vs LAPACK (fp64): eigenvalues, residual, orthogonality."""
     torch.manual_seed(n)

@@ -106,6 +106,10 @@ __device__ __forceinline__ float jac_rsqrt_refined(float x) {
     const float r = rsqrtf(x);
     return r * fmaf(-0.5f * x, r * r, 1.5f);
 }
+// Quadratic convergence: a sweep whose largest pre-rotation cosine was below kJacobiSmallAngle leaves cosines of the
+// order of its square (1e-9), far below the tolerance, so it is the last one - the sweep that only verifies that nothing
+// rotates any more (10 % of the pooled eigen-solver) is skipped.
+constexpr float kJacobiSmallAngle = 3.0e-5f;
 // One rotation of the column pairs held by the four 8-lane groups of this warp.  ALL 32 lanes must call it together.
 template <int CHUNKS>
 __device__ __forceinline__ int jac_rotate_regs(ulonglong2 (&x)[CHUNKS], ulonglong2 (&y)[CHUNKS], float tol) {
@@ -131,7 +135,9 @@ __device__ __forceinline__ int jac_rotate_regs(ulonglong2 (&x)[CHUNKS], ulonglon
     const float icy = jac_rsqrt_refined(y2);
     const float sn_abs = 0.5f * h * rinv * icy;                       // sin 2theta / (2 cos theta), sign of h
     // (off the chain) already orthogonal, or d^2 + h^2 outside the fp32 range: leave the pair alone
-    const bool rot = fabsf(ga) > tol * jac_sqrt_approx(al * be) && r2 > 1e-36f && r2 < 1e36f;
+    const float gn = jac_sqrt_approx(al * be);
+    const bool rot = fabsf(ga) > tol * gn && r2 > 1e-36f && r2 < 1e36f;
+    const bool big = fabsf(ga) > kJacobiSmallAngle * gn;              // a rotation that is not yet in the quadratic end game
     const float cs = rot ? y2 * icy : 1.f;
     const float sn = rot ? (d < 0.f ? -sn_abs : sn_abs) : 0.f;
     const jac_f2 cs2 = jac_pack(cs, cs), sn2 = jac_pack(sn, sn), nsn2 = jac_pack(-sn, -sn);
@@ -142,7 +148,7 @@ __device__ __forceinline__ int jac_rotate_regs(ulonglong2 (&x)[CHUNKS], ulonglon
         xn.y = jac_fma2(cs2, x[c].y, jac_mul2(nsn2, y[c].y)); yn.y = jac_fma2(sn2, x[c].y, jac_mul2(cs2, y[c].y));
         x[c] = xn; y[c] = yn;
     }
-    return rot ? 1 : 0;
+    return rot ? (big ? 3 : 1) : 0;                                   // bit 0: rotated, bit 1: by more than kJacobiSmallAngle
 }
 // generic-pointer column load / store (initial load from and final store to cluster rank 0)
 template <int CHUNKS>
@@ -253,12 +259,12 @@ __device__ int jacobi_orthogonalize(float* __restrict__ A, int ld, int n_cols, f
                     jac_lds<CHUNKS>(cq, ld, gl, ok, y);
                     const int r = jac_rotate_regs<CHUNKS>(x, y, tol);
                     rotated |= r;
-                    jac_sts<CHUNKS>(cp, ld, gl, ok && r, x);
-                    jac_sts<CHUNKS>(cq, ld, gl, ok && r, y);
+                    jac_sts<CHUNKS>(cp, ld, gl, ok && (r & 1), x);
+                    jac_sts<CHUNKS>(cq, ld, gl, ok && (r & 1), y);
                 }
                 jac_bar_active(n_active);
             }
-            if (!jac_bar_active_or(n_active, rotated)) { ++sweep; break; }
+            if (!jac_bar_active_or(n_active, rotated & 2)) { ++sweep; break; }     // see kJacobiSmallAngle
         }
     }
     __syncthreads();
@@ -341,17 +347,23 @@ __device__ int jacobi_orthogonalize_oddeven_cluster(float* __restrict__ A, int l
                 }
             }
             // did any CTA of the cluster rotate in this sweep?  (flags double-buffered by sweep parity)
-            const int any_local = __syncthreads_or(rotated);
+            const int any_local = (__syncthreads_or(rotated & 1) ? 1 : 0) | (__syncthreads_or(rotated & 2) ? 2 : 0);
             int* fl = flags + (sweep & 1) * 8;
             if (threadIdx.x < C) cluster.map_shared_rank(fl, threadIdx.x)[crank] = any_local;
             jac_cluster_sync();
             int any = 0;
             for (int r = 0; r < C; ++r) any |= fl[r];
-            if (!any) { ++sweep; break; }
+            if (!(any & 2)) { ++sweep; break; }             // nothing rotated, or only by end-game angles: converged
         }
     }
-    jac_st<CHUNKS>(A0 + static_cast<size_t>(active ? 2 * g : 0) * ld, ld, gl, active, P);
-    jac_st<CHUNKS>(A0 + static_cast<size_t>(q_real ? 2 * g + 1 : 0) * ld, ld, gl, q_real, Q);
+    // Every sweep reverses the order of the positions (n always-swap steps of the transposition network).  That only
+    // matters for an odd n_cols: the virtual zero column starts at the last position and sits at position 0 after an odd
+    // number of sweeps - the real columns are then positions 1 .. n-1 and go to columns 0 .. n_cols-1.
+    const bool reversed = (n_cols & 1) && (sweep & 1);
+    const int col_p = 2 * g - (reversed ? 1 : 0), col_q = 2 * g + 1 - (reversed ? 1 : 0);
+    const bool st_p = active && col_p >= 0 && col_p < n_cols, st_q = active && col_q < n_cols;
+    jac_st<CHUNKS>(A0 + static_cast<size_t>(st_p ? col_p : 0) * ld, ld, gl, st_p, P);
+    jac_st<CHUNKS>(A0 + static_cast<size_t>(st_q ? col_q : 0) * ld, ld, gl, st_q, Q);
     jac_cluster_sync();
     return sweep;
 }
