@@ -217,6 +217,9 @@ angles_kernel(int n, int Lt, int P, const int* __restrict__ ranks, const float* 
     float* coef = vals + n;
     float* red = coef + n;                                       // 33 floats
     int* order = reinterpret_cast<int*>(red + 40);
+    float* inbox = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(order + n + 8) + 15) & ~uintptr_t(15));   // odd-even Jacobi: one column
+    __shared__ int s_flags[16];
+    __shared__ __align__(8) uint64_t s_bars[2];
 
     const float* lam_t = evals + static_cast<size_t>(j) * n;
     const float* Ut = evecs_km + static_cast<size_t>(j) * n * n;             // [eig][comp]
@@ -260,7 +263,10 @@ angles_kernel(int n, int Lt, int P, const int* __restrict__ ranks, const float* 
     if (dbg) g_spectral_clk[8 + 3] = clock64();
     // (c) one-sided Jacobi on A^T:  A^T R = Y Sigma  =>  A^T A = Y Sigma^2 Y^T.  The rotated columns are sigma_m y_m: their
     //     norms are the cosines themselves (no squaring through A^T A) and their directions the right singular vectors.
-    run_jacobi(J, ld, k);
+    // odd-even ordering with register-resident columns (a "cluster" of this one CTA): half the shared-memory round trips
+    // and barriers of the round-robin version per rotation; k x k with k ~ 15-40 is a pure latency chain
+    int nsw = 0;
+    if (!run_jacobi_oddeven_cluster(J, ld, k, inbox, s_bars, s_flags, &nsw)) run_jacobi(J, ld, k);
     column_norms(J, ld, k, k, vals);          // vals = sigma
     __syncthreads();
     rank_descending(vals, k, order);
@@ -399,7 +405,7 @@ selector_bwd_kernel(int n, int Lt, int P, const float* __restrict__ gw_raw, cons
 
 // ------------------------------------------------------------------------------------------------ launchers
 static size_t pooled_smem(int n) { return (static_cast<size_t>(jacobi_ld(n)) * n + 3 * n + 64 + jacobi_ld(n) + 8) * sizeof(float); }
-static size_t angles_smem(int n) { return (static_cast<size_t>(jacobi_ld(n - 1)) * (n - 1) + 3 * n + 128) * sizeof(float); }
+static size_t angles_smem(int n) { return (static_cast<size_t>(jacobi_ld(n - 1)) * (n - 1) + 3 * n + 128 + n + 16 + jacobi_ld(n)) * sizeof(float); }
 
 cudaError_t launch_pooled_eig(const float* stats, int n, int Lt, int P, float Mt, float Ms, int* ranks, float* evals,
                               float* evecs_km, float* evecs_cm, int* sweeps, cudaStream_t st) {
@@ -408,11 +414,11 @@ cudaError_t launch_pooled_eig(const float* stats, int n, int Lt, int P, float Mt
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
-    static int cluster = 0;                   // BASD_EIG_CLUSTER: development knob (1, 2, 4 or 8 CTAs per problem)
+    static int cluster = 0;                   // BASD_EIG_CLUSTER: development knob (1..8 CTAs per problem)
     if (!cluster) {
         const char* env = getenv("BASD_EIG_CLUSTER");
         cluster = env ? atoi(env) : kPooledCluster;
-        if (cluster != 1 && cluster != 2 && cluster != 4 && cluster != 8) cluster = kPooledCluster;
+        if (cluster < 1 || cluster > 8) cluster = kPooledCluster;
     }
     cfg.gridDim = dim3((2 * Lt + P) * cluster);
     cfg.blockDim = dim3(kPooledThreads);
