@@ -283,9 +283,11 @@ extern "C" int basd_forward_stats(const basd_shape* shape, const basd_inputs* in
         CK(gemm_project(layers, s.Lt, Mt, s.Dt, pt_hi, pt_lo, s.Ds, z, zlo, st));
     }
     {
-        Scope sc(3, st, 1 + s.P);
+        Scope sc(3, st, 2);
         CK(gemm_gram_batched(z, zlo, Mt, s.Ds, s.Lt, stats, static_cast<long long>(stat_stride), st));
-        for (int i = 0; i < s.P; ++i) CK(gemm_gram(r.student[i], nullptr, Ms, s.Ds, stats + (s.Lt + i) * stat_stride, st));
+        const void* pts[kMaxPoints];
+        for (int i = 0; i < s.P; ++i) pts[i] = r.student[i];
+        CK(gemm_gram_table(pts, s.P, Ms, s.Ds, stats + s.Lt * stat_stride, static_cast<long long>(stat_stride), st));
     }
     {
         Scope sc(4, st, Mt == Ms ? 1 : 2);

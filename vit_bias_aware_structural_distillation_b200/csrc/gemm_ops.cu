@@ -155,6 +155,24 @@ static cudaError_t gram_impl(const __nv_bfloat16* Z, const __nv_bfloat16* Zlo, s
 cudaError_t gemm_gram(const __nv_bfloat16* Z, const __nv_bfloat16* Zlo, size_t M, int Ds, float* G, cudaStream_t st) {
     return gram_impl(Z, Zlo, M, Ds, 1, G, 0, st);
 }
+// G[i] += S_i^T S_i for n separate [M][Ds] bf16 tensors in ONE launch (blockIdx.z = tensor x split; a single Gram is 25
+// CTAs - four of them back to back were 4 x 50 us of latency)
+cudaError_t gemm_gram_table(const void* const* S, int n, size_t M, int Ds, float* G, long long g_stride, cudaStream_t st) {
+    if (n > GEMM_MAX_A_TABLE) return cudaErrorInvalidValue;
+    GemmMaps maps;
+    memset(&maps, 0, sizeof maps);
+    for (int i = 0; i < n; ++i)
+        if (make_map(&maps.a_table[i], S[i], Ds, M, 1, Ds, M * Ds, 64)) return cudaErrorInvalidValue;
+    GemmArgs a;
+    memset(&a, 0, sizeof a);
+    a.kb_total = cdiv(M, GEMM_BK);
+    a.kb_per_split = 32;
+    a.n_splits = cdiv(a.kb_total, a.kb_per_split);
+    a.a_table = 1; a.b_table = 1;
+    a.out = G; a.out_batch_stride = g_stride; a.ld_out = Ds; a.rows_valid = Ds; a.cols_valid = Ds;
+    const dim3 grid(cdiv(Ds, CfgGram::kBN), cdiv(Ds, CfgGram::kMT * 128), n * a.n_splits);
+    return launch<CfgGram, EpiAtomicAddF32>(maps, a, grid, st);
+}
 cudaError_t gemm_gram_batched(const __nv_bfloat16* Z, const __nv_bfloat16* Zlo, size_t M, int Ds, int batches, float* G, long long g_stride,
                               cudaStream_t st) {
     return gram_impl(Z, Zlo, M, Ds, batches, G, g_stride, st);

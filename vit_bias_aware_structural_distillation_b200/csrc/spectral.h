@@ -55,6 +55,8 @@ int gemm_init_driver_api();               // resolves cuTensorMapEncodeTiled; 0 
 cudaError_t gemm_project(const void* const* X, int n_layers, size_t M, int Dt, const __nv_bfloat16* Phi, const __nv_bfloat16* Plo,
                          int Ds, __nv_bfloat16* Zhi, __nv_bfloat16* Zlo, cudaStream_t st);
 // Zlo may be null (exact bf16 input); otherwise Z = Zhi + Zlo and the Gram uses hi*hi + hi*lo + lo*hi
+// G[i] (stride g_stride floats) += S_i^T S_i for n separate exact-bf16 [M][Ds] tensors, one launch
+cudaError_t gemm_gram_table(const void* const* S, int n, size_t M, int Ds, float* G, long long g_stride, cudaStream_t st);
 cudaError_t gemm_gram(const __nv_bfloat16* Z, const __nv_bfloat16* Zlo, size_t M, int Ds, float* G /*[Ds][Ds] pre-zeroed*/,
                       cudaStream_t st);
 cudaError_t gemm_gram_batched(const __nv_bfloat16* Z, const __nv_bfloat16* Zlo, size_t M, int Ds, int batches, float* G,

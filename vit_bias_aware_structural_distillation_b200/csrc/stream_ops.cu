@@ -268,43 +268,57 @@ cudaError_t launch_importance_mix(const float* rows, const float* w, int Lt, int
 
 // ---------------------------------------------------------------------------------------------- mix teacher
 // Tbar[i][b][n][:] = sum_j w[i][j] * interp(T_j[b])[n][:]  -> bf16 hi + lo.  One thread = one 8-wide vector.
-template <int PMAX>
+// Teacher vectors are loaded six layers at a time before the first use (one load and its use alternating per layer left one
+// request in flight per thread: 4.0 TB/s), 32-bit index arithmetic, no interpolation branch when N_t == N_s.
+constexpr int MT_JC = 6;
+template <int PMAX, bool INTERP>
 __global__ void __launch_bounds__(256)
 mix_teacher_kernel(PtrTable teacher, const float* __restrict__ w, int Lt, int P, int B, int Nt, int Ns, int Dt,
                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
     __shared__ float ws[PMAX * kMaxLayers];
     for (int t = threadIdx.x; t < P * Lt; t += blockDim.x) ws[t] = w[t];
     __syncthreads();
-    const int vpr = Dt / 8;
-    const size_t per_sample = static_cast<size_t>(Ns) * vpr;
-    const size_t total = per_sample * B;
-    for (size_t v = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; v < total; v += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int b = static_cast<int>(v / per_sample);
-        const size_t rem = v % per_sample;
-        const int n = static_cast<int>(rem / vpr), dv = static_cast<int>(rem % vpr);
+    const uint32_t vpr = static_cast<uint32_t>(Dt) / 8u;
+    const uint32_t total = static_cast<uint32_t>(B) * Ns * vpr;            // < 2^32 (checked by the launcher)
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < total; v += gridDim.x * blockDim.x) {
+        const uint32_t row = v / vpr, dv = v - row * vpr;
+        const uint32_t b = row / static_cast<uint32_t>(Ns), n = row - b * Ns;
         int i0, i1; float lam;
-        interp_index(n, Nt, Ns, i0, i1, lam);
+        interp_index(static_cast<int>(n), Nt, Ns, i0, i1, lam);
         float acc[PMAX][8];
 #pragma unroll
         for (int i = 0; i < PMAX; ++i)
 #pragma unroll
             for (int e = 0; e < 8; ++e) acc[i][e] = 0.f;
-        for (int j = 0; j < Lt; ++j) {
-            const __nv_bfloat16* T = reinterpret_cast<const __nv_bfloat16*>(teacher.p[j]) + (static_cast<size_t>(b) * Nt) * Dt + dv * 8;
-            float f[8];
-            bf16x8_to_float(ld_nc_16(T + static_cast<size_t>(i0) * Dt), f);
-            if (lam != 0.f) {
-                float g[8];
-                bf16x8_to_float(ld_nc_16(T + static_cast<size_t>(i1) * Dt), g);
+        for (int j0 = 0; j0 < Lt; j0 += MT_JC) {
+            uint4 t0[MT_JC], t1[INTERP ? MT_JC : 1];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = (1.f - lam) * f[e] + lam * g[e];
+            for (int jj = 0; jj < MT_JC; ++jj) {
+                const bool ok = j0 + jj < Lt;
+                const __nv_bfloat16* T = reinterpret_cast<const __nv_bfloat16*>(teacher.p[ok ? j0 + jj : 0]) + (static_cast<size_t>(b) * Nt) * Dt + dv * 8;
+                t0[jj] = ok ? ld_nc_16(T + static_cast<size_t>(i0) * Dt) : zero4;
+                if (INTERP) t1[jj] = ok ? ld_nc_16(T + static_cast<size_t>(i1) * Dt) : zero4;
             }
 #pragma unroll
-            for (int i = 0; i < PMAX; ++i) {
-                if (i < P) {
-                    const float wi = ws[i * Lt + j];
+            for (int jj = 0; jj < MT_JC; ++jj) {
+                if (j0 + jj < Lt) {
+                    float f[8];
+                    bf16x8_to_float(t0[jj], f);
+                    if (INTERP) {
+                        float g[8];
+                        bf16x8_to_float(t1[jj], g);
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) acc[i][e] = fmaf(wi, f[e], acc[i][e]);
+                        for (int e = 0; e < 8; ++e) f[e] = (1.f - lam) * f[e] + lam * g[e];
+                    }
+#pragma unroll
+                    for (int i = 0; i < PMAX; ++i) {
+                        if (i < P) {
+                            const float wi = ws[i * Lt + j0 + jj];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) acc[i][e] = fmaf(wi, f[e], acc[i][e]);
+                        }
+                    }
                 }
             }
         }
@@ -336,10 +350,15 @@ cudaError_t launch_mix_teacher(const PtrTable& teacher, const float* w, int Lt, 
     if (Dt % 8 != 0 || P > kMaxPoints) return cudaErrorInvalidValue;
     const size_t total = static_cast<size_t>(B) * Ns * (Dt / 8);
     const int blocks = static_cast<int>((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-    if (P <= 4)
-        mix_teacher_kernel<4><<<blocks, 256, 0, st>>>(teacher, w, Lt, P, B, Nt, Ns, Dt, hi, lo);
-    else
-        mix_teacher_kernel<8><<<blocks, 256, 0, st>>>(teacher, w, Lt, P, B, Nt, Ns, Dt, hi, lo);
+    if (static_cast<unsigned long long>(B) * Ns * (Dt / 8) >= (1ull << 32)) return cudaErrorInvalidValue;
+    const bool interp = Nt != Ns;
+    if (P <= 4) {
+        if (interp) mix_teacher_kernel<4, true><<<blocks, 256, 0, st>>>(teacher, w, Lt, P, B, Nt, Ns, Dt, hi, lo);
+        else mix_teacher_kernel<4, false><<<blocks, 256, 0, st>>>(teacher, w, Lt, P, B, Nt, Ns, Dt, hi, lo);
+    } else {
+        if (interp) mix_teacher_kernel<8, true><<<blocks, 256, 0, st>>>(teacher, w, Lt, P, B, Nt, Ns, Dt, hi, lo);
+        else mix_teacher_kernel<8, false><<<blocks, 256, 0, st>>>(teacher, w, Lt, P, B, Nt, Ns, Dt, hi, lo);
+    }
     return cudaGetLastError();
 }
 

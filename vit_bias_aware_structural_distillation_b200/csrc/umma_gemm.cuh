@@ -31,6 +31,7 @@ struct GemmArgs {
     int a_batched;       // A uses blockIdx.z as 3rd TMA coordinate
     int b_batched;       // B uses blockIdx.z as 3rd TMA coordinate
     int a_table;         // A (single buffer) comes from maps.a_table[batch] (teacher layers live in separate tensors)
+    int b_table;         // B (single buffer) comes from maps.a_table[batch] too (Gram of separate tensors: B = A)
     // epilogue
     void* out;           // primary output
     long long out_batch_stride;   // elements
@@ -135,12 +136,13 @@ umma_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
 #pragma unroll
                     for (int i = 0; i < Cfg::kNB; ++i) {
                         uint8_t* dst = st + Cfg::kNA * Cfg::kABytes + i * Cfg::kBBytes;
+                        const CUtensorMap* bmap = args.b_table ? &maps.a_table[batch] : &maps.b[i];
                         if (Cfg::kBMN) {
 #pragma unroll
                             for (int g = 0; g < Cfg::kBN / 64; ++g)
-                                tma_load_3d(dst + g * 8192, &maps.b[i], &full_bar[s], b_row0 + g * 64, kb * GEMM_BK, zb);
+                                tma_load_3d(dst + g * 8192, bmap, &full_bar[s], b_row0 + g * 64, kb * GEMM_BK, zb);
                         } else {
-                            tma_load_3d(dst, &maps.b[i], &full_bar[s], kb * GEMM_BK, b_row0, zb);
+                            tma_load_3d(dst, bmap, &full_bar[s], kb * GEMM_BK, b_row0, zb);
                         }
                     }
                 }
