@@ -11,6 +11,7 @@ $CMD > gpurun_out/plain_$TAG.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREGEX" -c 4000 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_$TAG.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k "$KREGEX" -c 4000 --csv --log-file gpurun_out/traffic_$TAG.csv $CMD > gpurun_out/ncu_traffic_$TAG.log 2>&1
 echo "profile rc=$?"
+[ -n "${PROFILE_LIGHT:-}" ] && exit 0     # PROFILE_LIGHT=1: launch list + traffic only
 #   3. every kernel of the process (torch's included), to account for the step time outside our kernels
 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches_all_$TAG.csv $CMD > gpurun_out/ncu_all_$TAG.log 2>&1
 echo "profile-all rc=$?"
