@@ -80,7 +80,7 @@ int basd_backward_finish(const basd_shape* shape, const basd_inputs* in, void* w
  * "polar_*" (state of the polar iteration; bf16 views count hi then lo elements). */
 int basd_view(const basd_shape* shape, void* workspace, const char* name, void** ptr, size_t* count);
 
-/* marchenko_pastur_rank(features[M,D]) (layer_selector.py:8-20), rank written to device int; D <= 224, M >= D.
+/* marchenko_pastur_rank(features[M,D]) (layer_selector.py:8-20), rank written to device int; D <= 224 and a multiple of 8; either branch of :12-15 (M >= D, M < D).
  * workspace: at least basd_mp_rank_workspace_bytes(M, D). */
 int basd_mp_rank_workspace_bytes(int64_t M, int D, size_t* bytes);
 int basd_mp_rank(const void* features, int64_t M, int D, int dtype, int64_t row_stride, int* rank_out, void* workspace,

@@ -138,7 +138,7 @@ def test_jacobi_eigensolver(lib, cuda_dev, n):
     assert 0 < sw[0].item() < 40
 
 
-@pytest.mark.parametrize("M,D,r", [(4096, 48, 5), (20000, 192, 24), (6000, 96, 11)])
+@pytest.mark.parametrize("M,D,r", [(4096, 48, 5), (20000, 192, 24), (6000, 96, 11), (120, 192, 6), (40, 64, 3)])   # last two: M < D branch (:14-15)
 def test_marchenko_pastur_rank_free_function(lib, cuda_dev, M, D, r):
     """layer_selector.py:8-20 (second consumer teacher.py:177): exact integer agreement with the oracle."""
     import vit_bias_aware_structural_distillation_b200 as pkg

@@ -451,7 +451,6 @@ extern "C" int basd_mp_rank(const void* features, int64_t M, int D, int dtype, i
                             void* stream) {
     if (!features || !rank_out || !workspace) return fail("null argument");
     if (D % 8 || D > 224) return fail("basd_mp_rank: D must be a multiple of 8 and <= 224 (got %d)", D);
-    if (M < D) return fail("basd_mp_rank: M < D branch (layer_selector.py:14-15) not supported");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
     size_t off = 0;

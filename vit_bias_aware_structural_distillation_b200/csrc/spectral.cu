@@ -161,12 +161,15 @@ pooled_eig_kernel(const float* __restrict__ stats, int n, int Lt, int P, float M
     if (threadIdx.x == 0 && sweeps_out) sweeps_out[p] = nsweeps;
 
     if (mp_mode) {
-        // ascending index (n-1)/2 == descending index n-1-(n-1)/2  (torch.median = lower middle)
-        const float med = vals[order[n - 1 - (n - 1) / 2]];
+        // M < D (layer_selector.py:14-15): the reference takes the M eigenvalues of F F^T / M - the top M of the D x D
+        // Gram used here (its other D - M are zero up to rounding and are left out of the median and the count).
+        const int m_eff = Mrows < static_cast<float>(n) ? max(1, static_cast<int>(Mrows + 0.5f)) : n;
+        // ascending index (m-1)/2 == descending index m-1-(m-1)/2  (torch.median = lower middle)
+        const float med = vals[order[m_eff - 1 - (m_eff - 1) / 2]];
         const float sq = 1.f + sqrtf(static_cast<float>(n) * invM);
         const float lam_plus = med * sq * sq;
         int local = 0;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) local += vals[i] > lam_plus;
+        for (int i = threadIdx.x; i < m_eff; i += blockDim.x) local += vals[order[i]] > lam_plus;
         atomicAdd(&s_count, local);
         __syncthreads();
         if (threadIdx.x == 0) ranks[p] = min(s_count, n - 1);
