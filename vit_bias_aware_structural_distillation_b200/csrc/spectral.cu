@@ -69,6 +69,35 @@ __device__ __forceinline__ bool run_jacobi_oddeven_cluster(float* A, int ld, int
 // History of the Jacobi phase on B200 (cfg2, ms for the 28 pooled problems), one 768-thread CTA per problem, round-robin
 // ordering: 16-lane groups / two passes 5.6, 8-lane groups 4.6, two pairs in flight per group 5.4, block-2 ordering 5.0;
 // then the odd-even / cluster versions of jacobi.cuh.
+// A (column-major, ld) = symmetrised Gram / M, centred unless mp_mode.  One warp per column, eight rows per lane in
+// flight: the element-per-iteration loop this replaces (a divide, a modulo and two dependent-latency L2 loads per
+// iteration) was half of the 0.1 ms the kernel spends before the Jacobi phase.
+__device__ __forceinline__ void pooled_load_gram(const float* __restrict__ G, const float* __restrict__ csum, int n, int ld, float invM,
+                                                 bool mp_mode, float* __restrict__ A) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int c = warp; c < n; c += nw) {
+        const float cc = csum[c];
+        for (int r0 = lane; r0 < ld; r0 += 32 * 8) {
+            float g0[8], g1[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int r = r0 + 32 * u;
+                g0[u] = r < n ? G[r * n + c] : 0.f;
+                g1[u] = r < n ? G[c * n + r] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int r = r0 + 32 * u;
+                if (r < ld) {
+                    // symmetrise the split-K atomics result (bitwise symmetric input keeps Jacobi well behaved)
+                    const float g = 0.5f * (g0[u] + g1[u]);
+                    A[c * ld + r] = r < n ? (mp_mode ? g * invM : (g - csum[r] * cc * invM)) : 0.f;      // (r, c)-symmetric rounding
+                }
+            }
+        }
+    }
+}
+
 constexpr int kPooledThreads = 256;        // 32 eight-lane groups per CTA x 4 CTAs: n <= 256; 255 registers per thread, no spills
 constexpr int kPooledCluster = 4;           // 28 problems x 4 = 112 of the 148 SMs
 __global__ void __launch_bounds__(kPooledThreads, 1)
@@ -101,16 +130,7 @@ pooled_eig_kernel(const float* __restrict__ stats, int n, int Lt, int P, float M
     for (int i = threadIdx.x; i < n; i += blockDim.x) csum[i] = cs[i];
     if (threadIdx.x == 0) s_count = 0;
     __syncthreads();
-    for (int t = threadIdx.x; t < ld * n; t += blockDim.x) {
-        const int c = t / ld, r = t % ld;
-        float v = 0.f;
-        if (r < n) {
-            // symmetrise the split-K atomics result (bitwise symmetric input keeps Jacobi well behaved)
-            const float g = 0.5f * (G[r * n + c] + G[c * n + r]);
-            v = mp_mode ? g * invM : (g - csum[r] * csum[c] * invM);
-        }
-        A[c * ld + r] = v;
-    }
+    pooled_load_gram(G, csum, n, ld, invM, mp_mode, A);
     __syncthreads();
     // Veselic-Hari preconditioning: G = L L^T, then one-sided Jacobi on the Cholesky factor instead of on G.  The
     // singular values of L are the square roots of the eigenvalues (half the condition number in digits), the rotated
@@ -129,15 +149,7 @@ pooled_eig_kernel(const float* __restrict__ stats, int n, int Lt, int P, float M
     cta_cholesky_lower(A, ld, n, &s_bad, 1e-6f * dmax);       // pivots below 1e-6 of the largest diagonal: not trusted in fp32
     use_chol = s_bad == 0;
     if (!use_chol) {                       // rebuild G from the statistics
-        for (int t = threadIdx.x; t < ld * n; t += blockDim.x) {
-            const int c = t / ld, r = t % ld;
-            float v = 0.f;
-            if (r < n) {
-                const float g = 0.5f * (G[r * n + c] + G[c * n + r]);
-                v = mp_mode ? g * invM : (g - csum[r] * csum[c] * invM);
-            }
-            A[c * ld + r] = v;
-        }
+        pooled_load_gram(G, csum, n, ld, invM, mp_mode, A);
     }
     __syncthreads();
     }   // crank == 0
