@@ -100,7 +100,9 @@ static inline int cdiv(long long a, long long b) { return static_cast<int>((a + 
 using CfgProject = GemmCfg<false, false, 192, 2, 1, 2, 2, false, 2>;     // 256-row tiles: the split P_t tile (49 KB per k-block) is re-read half as often
 using CfgStudentGrad = GemmCfg<false, false, 192, 1, 1, 2, 2, false, 1>;   // one stage (65 KB), 256 TMEM columns: two CTAs per SM overlap each other
 using CfgGram    = GemmCfg<true,  true,  192, 2, 1, 1, 1, false, 3>;
+using CfgGramA   = GemmCfg<true,  true,  192, 2, 1, 1, 1, true,  3>;      // D_s <= 192 (one output tile): the B tile is the A tile, one load per k-block
 using CfgGram3   = GemmCfg<true,  true,  192, 2, 2, 2, 3, false, 2>;      // split operands: hi*hi + hi*lo + lo*hi
+using CfgGram3A  = GemmCfg<true,  true,  192, 2, 2, 2, 3, true,  3>;      // the same with B aliased onto A (D_s <= 192)
 using CfgTheta   = GemmCfg<false, true,  128, 2, 1, 1, 1, false, 4>;      // self test (single operands)
 using CfgTheta3  = GemmCfg<false, true,  128, 2, 2, 2, 3, false, 1>;      // split Theta x split mixed teacher; one stage (96 KB), 256 TMEM columns: two CTAs per SM
 template <int BN> using CfgTokenGram = GemmCfg<false, false, BN, 2, 2, 2, 3, true, 3>;
@@ -149,8 +151,9 @@ static cudaError_t gram_impl(const __nv_bfloat16* Z, const __nv_bfloat16* Zlo, s
     a.a_batched = 1; a.b_batched = 1;
     a.out = G; a.out_batch_stride = g_stride; a.ld_out = Ds; a.rows_valid = Ds; a.cols_valid = Ds;
     const dim3 grid(cdiv(Ds, CfgGram::kBN), cdiv(Ds, CfgGram::kMT * 128), batches * a.n_splits);
-    if (Zlo) return launch<CfgGram3, EpiAtomicAddF32>(maps, a, grid, st);
-    return launch<CfgGram, EpiAtomicAddF32>(maps, a, grid, st);
+    const bool alias = Ds <= CfgGram::kBN;                    // a single output tile: A tile == B tile
+    if (Zlo) return alias ? launch<CfgGram3A, EpiAtomicAddF32>(maps, a, grid, st) : launch<CfgGram3, EpiAtomicAddF32>(maps, a, grid, st);
+    return alias ? launch<CfgGramA, EpiAtomicAddF32>(maps, a, grid, st) : launch<CfgGram, EpiAtomicAddF32>(maps, a, grid, st);
 }
 cudaError_t gemm_gram(const __nv_bfloat16* Z, const __nv_bfloat16* Zlo, size_t M, int Ds, float* G, cudaStream_t st) {
     return gram_impl(Z, Zlo, M, Ds, 1, G, 0, st);
@@ -171,7 +174,7 @@ cudaError_t gemm_gram_table(const void* const* S, int n, size_t M, int Ds, float
     a.a_table = 1; a.b_table = 1;
     a.out = G; a.out_batch_stride = g_stride; a.ld_out = Ds; a.rows_valid = Ds; a.cols_valid = Ds;
     const dim3 grid(cdiv(Ds, CfgGram::kBN), cdiv(Ds, CfgGram::kMT * 128), n * a.n_splits);
-    return launch<CfgGram, EpiAtomicAddF32>(maps, a, grid, st);
+    return Ds <= CfgGram::kBN ? launch<CfgGramA, EpiAtomicAddF32>(maps, a, grid, st) : launch<CfgGram, EpiAtomicAddF32>(maps, a, grid, st);
 }
 cudaError_t gemm_gram_batched(const __nv_bfloat16* Z, const __nv_bfloat16* Zlo, size_t M, int Ds, int batches, float* G, long long g_stride,
                               cudaStream_t st) {

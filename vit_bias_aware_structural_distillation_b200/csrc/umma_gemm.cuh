@@ -58,7 +58,7 @@ struct GemmCfg {
     static_assert(MT * BN <= 512, "accumulators exceed TMEM");
     static_assert(BN % 16 == 0 && BN <= 256, "invalid UMMA N");
     static_assert(!B_MN || BN % 64 == 0, "MN-major B needs 64-wide groups");
-    static_assert(!B_ALIAS_A || (!A_MN && !B_MN && BN <= MT * 128), "alias needs K-major operands");
+    static_assert(!B_ALIAS_A || (A_MN == B_MN && BN <= MT * 128), "alias: B = the first BN rows / columns of the A tile, same major");
     static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
