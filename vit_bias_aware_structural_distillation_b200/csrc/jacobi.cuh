@@ -64,8 +64,10 @@ __device__ __forceinline__ void jacobi_pair(int n, int s, int k, int& p, int& q)
 //    not from the five-MUFU tan(theta) chain, is computed speculatively and discarded if the pair is already orthogonal;
 //  * packed fp32 (FFMA2 / FMUL2) for the dot products and the rotation.
 // Column ORDER on exit is a permutation of the input order (irrelevant to the callers, which sort by eigenvalue).
-// Measured on the 28 pooled 192 x 192 problems of cfg2 (ms): round-robin 4.7, odd-even on one CTA 4.1, + packed fp32
-// 3.8, 4-CTA cluster 2.8; exchanging in-warp neighbours by shuffle instead of mailboxes was slower (4.7).
+// Measured on the 28 pooled 192 x 192 problems of cfg2 (ms, whole kernel): round-robin 4.7, odd-even on one CTA 4.1,
+// + packed fp32 3.8, 4-CTA cluster 2.8, + uniform pair-step / 256-thread CTAs 2.1, + panel Cholesky 1.8, + end-game exit
+// 1.5; exchanging in-warp neighbours by shuffle instead of mailboxes was slower (4.7); clusters of 3 and 4 CTAs measure
+// the same, 5 do not all fit the GPU at once (2.5).
 // All threads of all CTAs of the cluster must call it; returns the sweep count (identical in every CTA).
 // inbox: ld floats, bars: 2 mbarriers, flags: 16 ints - shared memory at the same offsets in every CTA.
 // ------------------------------------------------------------------------------------------------------------------

@@ -11,7 +11,9 @@
 //             A~ is both operands: the A tile is read out of the B tile), so TMEM holds  A - (c r / |b|) A^2 = A + (c r / b) A^2;
 //   store     warps 2-9:  Bm = a I + (b r) acc  -> split pair -> SWIZZLE_64B staging (32 x 32) -> TMA store.
 // The loads of the next problem start as soon as phase 2 has retired (they overlap the store phase); its MMAs wait for the
-// accumulators to be drained.  Requires m = n = D_s <= 192 (the operand copy must fit the ring) - larger D_s keeps the
+// accumulators to be drained.  Phase 2 cannot start before the WHOLE copy is written: its MMAs update every accumulator
+// column, including the ones the copy still has to read.  Timeline of one problem on B200 (cfg2, cycles): phase 1 10-12 k
+// (tensor bound), copy 3.8 k, phase 2 8 k (tensor bound), store 7.8 k, hand-overs 1-2 k.  Requires m = n = D_s <= 192 (the operand copy must fit the ring) - larger D_s keeps the
 // two-launch path.
 #pragma once
 #include "polar_gemm.cuh"
