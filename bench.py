@@ -361,7 +361,7 @@ def main():
                        "result written once per launch (4 B per element, unpadded).  Tensor view of the same kernel: "
                        f"{polar_flops / polar_launches / 1e9:.1f} GFLOP of plain 2mnk per launch (3 split MMAs per product not counted)"),
         "pooled_eig": ("hbm", eig_bytes, 1,
-                       "28 shared-memory eigenproblems (Cholesky + one-sided Jacobi, fp32 CUDA cores) on 28 SMs: latency / issue bound, "
+                       "28 eigenproblems (Cholesky + one-sided Jacobi, fp32 CUDA cores), one 4-CTA cluster each (112 SMs): a dependent-latency chain, "
                        "neither roofline applies; bytes = Gram statistics in, eigenpairs out"),
     }
     traffic = None
