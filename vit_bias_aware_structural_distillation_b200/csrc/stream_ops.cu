@@ -268,9 +268,10 @@ cudaError_t launch_importance_mix(const float* rows, const float* w, int Lt, int
 
 // ---------------------------------------------------------------------------------------------- mix teacher
 // Tbar[i][b][n][:] = sum_j w[i][j] * interp(T_j[b])[n][:]  -> bf16 hi + lo.  One thread = one 8-wide vector.
-// Teacher vectors are loaded six layers at a time before the first use (one load and its use alternating per layer left one
-// request in flight per thread: 4.0 TB/s), 32-bit index arithmetic, no interpolation branch when N_t == N_s.
-constexpr int MT_JC = 6;
+// Teacher vectors are loaded twelve layers at a time before the first use (one load and its use alternating per layer left
+// one request in flight per thread: 4.0 TB/s; six at a time 4.6, twelve 5.1), 32-bit index arithmetic, no interpolation
+// branch when N_t == N_s.
+constexpr int MT_JC = 12;
 template <int PMAX, bool INTERP>
 __global__ void __launch_bounds__(256)
 mix_teacher_kernel(PtrTable teacher, const float* __restrict__ w, int Lt, int P, int B, int Nt, int Ns, int Dt,
