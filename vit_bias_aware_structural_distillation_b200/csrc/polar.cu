@@ -355,24 +355,52 @@ polar_finish_kernel(PolarArgs g) {
     if ((D & 7) == 0) {
         // a lane takes 8 consecutive d of one row: 16-byte loads of both halves of s_w, 2 x 16-byte loads of Gsw, 2 x 16-byte
         // stores of gdir; a warp covers 256 columns per pass
-        for (int n = warp; n < N; n += nw) {
-            const float qn = sqrtf(a[n]);
-            float s = 0.f;
-            for (int d0 = lane * 8; d0 < D; d0 += 256) {
-                float sw[8];
-                load_split8(swh, swl, g.SW.at(n, d0), sw);
-                const float4 g0 = *reinterpret_cast<const float4*>(G + static_cast<size_t>(n) * D + d0);
-                const float4 g1 = *reinterpret_cast<const float4*>(G + static_cast<size_t>(n) * D + d0 + 4);
-                const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-                float o[8];
+        // (the grid is a single wave, so the kernel lasts as long as one warp's chain of rows: four rows are in flight)
+        constexpr int RU = 4;
+        for (int n0 = warp * RU; n0 < N; n0 += nw * RU) {
+            float s[RU];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) { s = fmaf(sw[e], gv[e], s); o[e] = qn * (2.f * sw[e] - 2.f * gv[e]); }
-                float* od = gdir + static_cast<size_t>(n) * D + d0;
-                *reinterpret_cast<float4*>(od) = make_float4(o[0], o[1], o[2], o[3]);
-                *reinterpret_cast<float4*>(od + 4) = make_float4(o[4], o[5], o[6], o[7]);
+            for (int u = 0; u < RU; ++u) s[u] = 0.f;
+            for (int d0 = lane * 8; d0 < D; d0 += 256) {
+                uint4 h[RU], l[RU];
+                float4 g0[RU], g1[RU];
+#pragma unroll
+                for (int u = 0; u < RU; ++u) {
+                    const int n = n0 + u < N ? n0 + u : N - 1;
+                    const size_t idx = g.SW.at(n, d0);
+                    h[u] = *reinterpret_cast<const uint4*>(swh + idx);
+                    l[u] = *reinterpret_cast<const uint4*>(swl + idx);
+                    g0[u] = *reinterpret_cast<const float4*>(G + static_cast<size_t>(n) * D + d0);
+                    g1[u] = *reinterpret_cast<const float4*>(G + static_cast<size_t>(n) * D + d0 + 4);
+                }
+#pragma unroll
+                for (int u = 0; u < RU; ++u) {
+                    if (n0 + u < N) {
+                        const int n = n0 + u;
+                        const float qn = sqrtf(a[n]);
+                        const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&h[u]);
+                        const __nv_bfloat162* lp = reinterpret_cast<const __nv_bfloat162*>(&l[u]);
+                        float sw[8];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 x = __bfloat1622float2(hp[e]), y = __bfloat1622float2(lp[e]);
+                            sw[2 * e] = x.x + y.x; sw[2 * e + 1] = x.y + y.y;
+                        }
+                        const float gv[8] = {g0[u].x, g0[u].y, g0[u].z, g0[u].w, g1[u].x, g1[u].y, g1[u].z, g1[u].w};
+                        float o[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) { s[u] = fmaf(sw[e], gv[e], s[u]); o[e] = qn * (2.f * sw[e] - 2.f * gv[e]); }
+                        float* od = gdir + static_cast<size_t>(n) * D + d0;
+                        *reinterpret_cast<float4*>(od) = make_float4(o[0], o[1], o[2], o[3]);
+                        *reinterpret_cast<float4*>(od + 4) = make_float4(o[4], o[5], o[6], o[7]);
+                    }
+                }
             }
-            s = warp_sum(s);
-            if (lane == 0) dots[n] = s;
+#pragma unroll
+            for (int u = 0; u < RU; ++u) {
+                const float t = warp_sum(s[u]);
+                if (lane == 0 && n0 + u < N) dots[n0 + u] = t;
+            }
         }
     } else {
         for (int n = warp; n < N; n += nw) {
