@@ -65,17 +65,6 @@ __device__ __forceinline__ void store_split8(__nv_bfloat16* hi, __nv_bfloat16* l
     *reinterpret_cast<uint4*>(hi + idx) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
     *reinterpret_cast<uint4*>(lo + idx) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
 }
-// eight consecutive split values hi + lo -> fp32
-__device__ __forceinline__ void load_split8(const __nv_bfloat16* hi, const __nv_bfloat16* lo, size_t idx, float* v) {
-    const uint4 h = *reinterpret_cast<const uint4*>(hi + idx), l = *reinterpret_cast<const uint4*>(lo + idx);
-    const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&h);
-    const __nv_bfloat162* lp = reinterpret_cast<const __nv_bfloat162*>(&l);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float2 a = __bfloat1622float2(hp[i]), b = __bfloat1622float2(lp[i]);
-        v[2 * i] = a.x + b.x; v[2 * i + 1] = a.y + b.y;
-    }
-}
 
 constexpr int kPrepThreads = 512;
 __global__ void __launch_bounds__(kPrepThreads)
