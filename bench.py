@@ -33,9 +33,11 @@ UNIT = "samples/s"
 
 
 # ------------------------------------------------------------------------------------------------ workload
-def workload(batch: int):
+def workload(batch, name: str = "cfg2"):
+    """BASELINE.json configs[1] (the configuration the metric is quoted on) unless another one is named."""
     from oracle import synth
-    return dataclasses.replace(synth.CONFIGS["cfg2"], B=batch)
+    w = synth.CONFIGS[name]
+    return dataclasses.replace(w, B=batch) if batch else w
 
 
 def algorithmic_bytes(w, act_bytes=2, attn_bytes=2):
@@ -68,7 +70,10 @@ def device_inputs(w, dev, seed):
     targets = torch.randint(0, w.num_classes, (w.B,), generator=g, device=dev)
     student = {l: geometric(w.B, w.Ns, w.Ds) for l in w.token_layers()}
     teacher = {j: spiked(w.B, w.Nt, w.Dt, (16 + 4 * j) if w.Lt > 1 else 64) for j in range(w.Lt)}
-    attn = {j: torch.softmax(2 * torch.randn(w.B, w.H, w.Nt + 1, w.Nt + 1, generator=g, device=dev), -1).bfloat16() for j in range(w.Lt)}
+    if w.has_cls:
+        attn = {j: torch.softmax(2 * torch.randn(w.B, w.H, w.Nt + 1, w.Nt + 1, generator=g, device=dev), -1).bfloat16() for j in range(w.Lt)}
+    else:                                  # CNN teachers: uniform attention (teacher.py:188-191)
+        attn = {j: (torch.ones(w.B, 1, w.Nt, w.Nt, device=dev) / w.Nt).bfloat16() for j in range(w.Lt)}
     return logits, targets, student, teacher, attn
 
 
@@ -177,8 +182,8 @@ def run_reference_arm(args):
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
-    w = workload(args.batch)
-    sample = args.cpu_sample_batch
+    w = workload(args.batch, args.workload)
+    sample = min(args.cpu_sample_batch, w.B)
     step, kind, desc = cpu_reference_step_fn(w, sample)
     sec = time_cpu(step, max(1, args.steps), max(1, min(args.warmup, 2)))
     val = sample / sec
@@ -198,7 +203,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (weak scaling)")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (weak scaling); 0 = the named configuration's own (256; cfg5: 128)")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"],
+                    help="BASELINE.json configs[0..4]; the metric is quoted on cfg2")
     ap.add_argument("--cpu-sample-batch", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -225,7 +232,7 @@ def main():
     from vit_bias_aware_structural_distillation_b200 import _lib
     lib = pkg.load()
 
-    w = workload(args.batch)
+    w = workload(args.batch, args.workload)
     from oracle import synth
     logits, targets, student, teacher, attn = device_inputs(w, dev, seed=1234 + rank)
     torch.manual_seed(0)
@@ -370,7 +377,8 @@ def main():
         traffic = tr.get(dom, {}).get("dram_bytes_per_launch")
     except Exception:
         pass
-    if dom in table and table[dom][1] > 0:
+    feature_form = w.Ds <= min(w.Ns, w.Nt) - 1          # the byte / flop model above is the student-feature form's
+    if dom in table and table[dom][1] > 0 and feature_form:
         bound, units, n_l, what = table[dom]
         ms_launch = per_step[dom] / n_l
         ach = units / n_l / (ms_launch * 1e-3) / 1e9
@@ -393,7 +401,7 @@ def main():
                  "scope": "W_alg = 2 X_T + 4 X_S + A_needed and F_tc of SURVEY.md section 8d over the whole step time"},
         "other_kernels": {k: {"bound": table[k][0], "achieved_gbs": table[k][1] / table[k][2] / (per_step[k] / table[k][2] * 1e-3) / 1e9,
                               "frac": table[k][1] / table[k][2] / (per_step[k] / table[k][2] * 1e-3) / 1e9 / hbm_peak,
-                              "ms_per_step": per_step[k]} for k in table if k != dom and k in per_step},
+                              "ms_per_step": per_step[k]} for k in table if k != dom and k in per_step and feature_form},
         "dominant_kernel": dom, "dominant_kernel_ms_per_step": per_step.get(dom) if dom else None,
         "dominant_kernel_share": (per_step[dom] / ms_step) if dom else None,
         "kernel_ms_per_step": {k: round(v, 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])}})
@@ -401,9 +409,10 @@ def main():
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
-        stepfn, kind, desc = cpu_reference_step_fn(w, args.cpu_sample_batch)
+        cpu_b = min(args.cpu_sample_batch, w.B)
+        stepfn, kind, desc = cpu_reference_step_fn(w, cpu_b)
         sec = time_cpu(stepfn, 3, 1)
-        cpu_baseline = {"value": args.cpu_sample_batch / sec, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind, "sample": desc}
+        cpu_baseline = {"value": cpu_b / sec, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind, "sample": desc}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -411,7 +420,7 @@ def main():
             "config": {"workload": w.name, "per_gpu_batch": w.B, "global_batch": w.B * world, "Ns": w.Ns, "Nt": w.Nt, "Ds": w.Ds, "Dt": w.Dt,
                        "Lt": w.Lt, "H": w.H, "P": w.P, "parallelism": f"dp{world} (batch-sharded, pooled statistics all-reduced)",
                        "arithmetic": "bf16 tokens, fp32 accumulation, split-bf16 (hi+lo) tensor-core products, fp32 Jacobi",
-                       "l2": "inputs (3.9 GB per step) exceed the 126 MB L2; no explicit flush"},
+                       "l2": f"inputs ({(w.Lt * w.B * w.Nt * w.Dt + w.P * w.B * w.Ns * w.Ds) * 2 / 1e9:.1f} GB of tokens per step) exceed the 126 MB L2; no explicit flush"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "loss": loss_val}
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -1,7 +1,7 @@
 """Generates tests/golden/*.pt by executing the UNMODIFIED reference (/root/reference/src/losses) on the synthetic
 inputs of oracle/synth.py.  Run in the build container only (the GPU box has no /root/reference):
 
-    python -m oracle.make_golden [tiny cfg1 cfg2]
+    python -m oracle.make_golden [tiny small cfg1 cfg2]
 
 Each fixture stores the workload, seeds and the reference's outputs: loss, MP ranks, log_temperature gradients, and —
 because full student gradients of the big configs are too large to commit — their norms, a strided subsample and
@@ -32,6 +32,15 @@ TINY = {
     "tiny_up": synth.Workload("tiny_up", 4, 64, 56, 48, 96, 3, 2, True),            # 56 -> 64 tokens (up-sampling)
     "tiny_down": synth.Workload("tiny_down", 4, 64, 100, 48, 96, 3, 2, True),        # 100 -> 64 tokens (the DINOv2 256 -> 196 case)
     "tiny_cnn_down": synth.Workload("tiny_cnn_down", 6, 64, 81, 48, 128, 1, 1, False),   # 9x9 CNN grid -> 64 student tokens
+}
+
+
+# BASELINE.json configs[2..4] at a reduced batch (the full-size reference step needs 20-100 GB of host RAM and minutes):
+# same token counts, widths, layer and head counts - only B differs.
+SMALL = {
+    "cfg3_b8": dataclasses.replace(synth.CONFIGS["cfg3"], name="cfg3_b8", B=8),      # 7x7 CNN grid -> 196 tokens, D_s = 384 > N_t - 1
+    "cfg4_b4": dataclasses.replace(synth.CONFIGS["cfg4"], name="cfg4_b4", B=4),      # D_s = 384 > N - 1 = 195, 24-way mixing
+    "cfg5_b2": dataclasses.replace(synth.CONFIGS["cfg5"], name="cfg5_b2", B=2),      # 576 tokens, D_s = 384
 }
 
 
@@ -73,5 +82,10 @@ if __name__ == "__main__":
         if k == "tiny":
             for n, w in TINY.items():
                 run(n, w, full=True)
+        elif k == "small":
+            for n, w in SMALL.items():
+                run(n, w)
+        elif k in SMALL:
+            run(k, SMALL[k])
         else:
             run(k, synth.CONFIGS[k])

@@ -32,14 +32,22 @@ def test_workspace_bytes_is_host_only(lib):
     n = ctypes.c_size_t()
     assert lib.basd_workspace_bytes(ctypes.byref(s), ctypes.byref(n)) == 0
     assert 1e9 < n.value < 4e9          # sized for 180 GB of HBM, not for minimal footprint
+    # BASELINE.json configs[2..4] are accepted: 7x7 CNN grid -> ViT-S, ViT-S <- ViT-L, 576 tokens at 384 px
+    for kw in (dict(B=256, Ns=196, Nt=49, Ds=384, Dt=2048, Lt=1, H=1, has_cls=0), dict(B=256, Ns=196, Nt=196, Ds=384, Dt=1024, Lt=24, H=16, has_cls=1),
+               dict(B=128, Ns=576, Nt=576, Ds=384, Dt=768, Lt=12, H=12, has_cls=1)):
+        s = Shape(P=4, act_dtype=1, attn_dtype=1, world_size=1, **kw)
+        assert lib.basd_workspace_bytes(ctypes.byref(s), ctypes.byref(n)) == 0, lib.basd_last_error().decode()
+        assert n.value < 40e9
 
 
-@pytest.mark.parametrize("field,value,needle", [("Ds", 190, "multiples of 8"), ("Ds", 384, "not built yet"), ("Lt", 100, "Lt <="),
-                                                ("world_size", 0, "world_size")])
+@pytest.mark.parametrize("field,value,needle", [("Ds", 190, "multiples of 8"), ("Ds", 2048, "not supported"), ("Lt", 100, "Lt <="),
+                                                ("world_size", 0, "world_size"), ("Nt", 256, "student-token-space form")])
 def test_unsupported_shapes_fail_loudly(lib, field, value, needle):
     from vit_bias_aware_structural_distillation_b200._lib import Shape
     kw = dict(B=8, Ns=196, Nt=196, Ds=192, Dt=768, Lt=12, P=4, H=12, has_cls=1, act_dtype=1, attn_dtype=1, world_size=1)
     kw[field] = value
+    if field == "Nt":
+        kw["Ds"] = 384          # D_s > N_s - 1 with more teacher than student tokens: the one remaining unbuilt form
     s = Shape(**kw)
     n = ctypes.c_size_t()
     assert lib.basd_workspace_bytes(ctypes.byref(s), ctypes.byref(n)) != 0

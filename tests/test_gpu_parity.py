@@ -117,28 +117,30 @@ def test_tcgen05_gemm_variants(lib, cuda_dev, variant, M, N, Kd):
     assert (C.cpu() - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
 
 
-@pytest.mark.parametrize("n", [16, 33, 48, 51, 77, 100, 130, 191, 192, 224])
+@pytest.mark.parametrize("n", [16, 33, 48, 51, 77, 100, 130, 191, 192, 224, 228, 256, 330, 384])
 def test_jacobi_eigensolver(lib, cuda_dev, n):
-    """Shared-memory one-sided Jacobi vs LAPACK (fp64): eigenvalues, residual, orthogonality."""
+    """One-sided Jacobi vs LAPACK (fp64): eigenvalues, residual, orthogonality.  n <= 224: cluster kernel with the matrix
+    in shared memory; larger: the global-memory variant (ViT-S students, D_s = 384)."""
     torch.manual_seed(n)
     X = torch.randn(4 * n, n) * (0.97 ** torch.arange(n))
     G = X.T @ X
     Gd = G.to(cuda_dev)
     ev = torch.zeros(n, device=cuda_dev); evec = torch.zeros(n, n, device=cuda_dev)
     sw = torch.zeros(4, dtype=torch.int32, device=cuda_dev)
-    ws = torch.zeros(4 * (2 * n * n + n) + 8192, dtype=torch.uint8, device=cuda_dev)
+    ws = torch.zeros(4 * (3 * n * n + 8 * n) + 16384, dtype=torch.uint8, device=cuda_dev)
     rc = lib.basd_selftest_eig(Gd.data_ptr(), n, ev.data_ptr(), evec.data_ptr(), sw.data_ptr(), ws.data_ptr(), _stream())
     assert rc == 0, lib.basd_last_error().decode()
     torch.cuda.synchronize()
     ref = torch.linalg.eigvalsh(G.double()).flip(0)
     V = evec.cpu().double()
-    assert ((ev.cpu().double() - ref).abs().max() / ref.max()).item() < 2e-5
-    assert ((G.double() @ V.T - V.T * ev.cpu().double()).norm() / G.double().norm()).item() < 2e-5
+    assert ((ev.cpu().double() - ref).abs().max() / ref.max()).item() < 3e-5
+    assert ((G.double() @ V.T - V.T * ev.cpu().double()).norm() / G.double().norm()).item() < 3e-5
     assert (V @ V.T - torch.eye(n, dtype=torch.float64)).abs().max().item() < 2e-5
     assert 0 < sw[0].item() < 40
 
 
-@pytest.mark.parametrize("M,D,r", [(4096, 48, 5), (20000, 192, 24), (6000, 96, 11), (120, 192, 6), (40, 64, 3)])   # last two: M < D branch (:14-15)
+@pytest.mark.parametrize("M,D,r", [(4096, 48, 5), (20000, 192, 24), (6000, 96, 11), (120, 192, 6), (40, 64, 3),   # last two: M < D branch (:14-15)
+                                   (8000, 384, 30), (6000, 768, 40), (300, 384, 8), (5000, 1024, 50)])   # unprojected D_t-wide features (teacher.py:177)
 def test_marchenko_pastur_rank_free_function(lib, cuda_dev, M, D, r):
     """layer_selector.py:8-20 (second consumer teacher.py:177): exact integer agreement with the oracle."""
     import vit_bias_aware_structural_distillation_b200 as pkg
@@ -197,23 +199,16 @@ def test_phase_buffers_match_kernel_model(lib, cuda_dev):
 
 
 # ------------------------------------------------------------------------------------------------ whole path
-NOT_BUILT = {"tiny_interp", "tiny_cnn"}      # D_s > N_t - 1: needs the token-space form of the polar iteration
-
-
 @pytest.mark.parametrize("name", ["tiny_cls", "tiny_up", "tiny_down", "tiny_cnn_down", "tiny_interp", "tiny_cnn"])
 def test_tiny_cases_against_oracle_and_reference_golden(lib, cuda_dev, name):
     """Edge cases of SURVEY.md §4 with the reference's full gradients in the fixtures: the plain CLS case, token-count
     resampling up (56 -> 64) and down (100 -> 64, the DINOv2 256 -> 196 situation), a single-layer CNN teacher without
     CLS (w == 1, zero temperature gradient, attention averaged over queries).  tiny_interp / tiny_cnn up-sample so few
-    teacher tokens that the cross-covariance is rank deficient: rejected loudly until the token-space form exists."""
+    teacher tokens (36 / 16 -> 64) that the cross-covariance is rank deficient (rank N_t - 1 < D_s, SURVEY.md hazard 13):
+    the polar iteration then runs in the teacher's token space."""
     g, w = load_golden(name)
     inp = synth.make_inputs(w, seed=g["seed"])
     m = build_module(w, cuda_dev)
-    if name in NOT_BUILT:
-        import vit_bias_aware_structural_distillation_b200 as pkg
-        with pytest.raises(pkg.BasdError, match="token-space form"):      # rejected loudly, never emulated
-            run_module(m, inp, cuda_dev)
-        return
     out = run_module(m, inp, cuda_dev)
     assert_parity(out, oracle_case(m, inp, w), w, tgrad_tol=3e-3 if name.startswith("tiny") else TOL_TGRAD)
     assert out["ranks"] == g["ranks"]
@@ -294,6 +289,28 @@ def test_cfg2_full_size_against_reference_golden(lib, cuda_dev):
     for l in g["token_layers"]:
         assert abs(out["grad_student"][l].norm() - g["grad_student_norm"][l]) <= TOL_SGRAD * g["grad_student_norm"][l]
         assert rel(out["grad_student"][l].flatten()[::997], g["grad_student_sub"][l]) < TOL_SGRAD
+
+
+@pytest.mark.parametrize("name", ["cfg3_b8", "cfg4_b4", "cfg5_b2"])
+def test_cfg345_reduced_batch_against_reference_golden(lib, cuda_dev, name):
+    """BASELINE.json configs[2..4] - ResNet-50 7x7 grid -> ViT-S (rank-deficient cross-covariance, 49 -> 196 resampling,
+    uniform attention), ViT-S <- ViT-L (D_s = 384 > N - 1, 24-way mixing), DeiT-S <- DeiT-B at 576 tokens - with every
+    dimension of the named configuration except the batch, against the UNMODIFIED reference (tests/golden, made by
+    `python -m oracle.make_golden small`) and the oracle, at the north-star tolerances."""
+    g, w = load_golden(name)
+    inp = synth.make_inputs(w, seed=g["seed"])
+    m = build_module(w, cuda_dev)
+    out = run_module(m, inp, cuda_dev)
+    assert out["ranks"] == g["ranks"]
+    assert abs(out["loss"].item() - g["loss"].item()) <= TOL_LOSS * abs(g["loss"].item())
+    gt, rt = out["grad_log_temperatures"], g["grad_log_temperatures"]
+    assert ((gt - rt).abs() <= TOL_TGRAD * rt.abs() + 1e-7).all(), f"temperature grads {gt.tolist()} vs {rt.tolist()}"
+    for l in g["token_layers"]:
+        assert abs(out["grad_student"][l].norm() - g["grad_student_norm"][l]) <= TOL_SGRAD * g["grad_student_norm"][l]
+        assert rel(out["grad_student"][l].flatten()[::997], g["grad_student_sub"][l]) < TOL_SGRAD
+        pr = torch.stack([(out["grad_student"][l] * p).sum() for p in _probes(out["grad_student"][l].shape)])
+        assert (pr - g["grad_student_probe"][l]).abs().max() <= TOL_SGRAD * g["grad_student_norm"][l] * math.sqrt(out["grad_student"][l].numel()) * 0.05
+    assert_parity(out, oracle_case(m, inp, w), w)
 
 
 # ------------------------------------------------------------------------------------------------ properties
@@ -448,6 +465,11 @@ def test_cls_attention_rows_from_q_k(lib, cuda_dev):
     dict(B=2, Ns=70, Nt=90, Ds=64, Dt=136, Lt=2, H=2, P=4),         # down-sampling 90 -> 70 with D_s exactly one column block
     dict(B=9, Ns=210, Nt=210, Ds=200, Dt=256, Lt=2, H=2, P=2),      # D_s > 192: 7-chunk cluster Jacobi, unfused polar products, 4 column blocks
     dict(B=3, Ns=160, Nt=160, Ds=144, Dt=192, Lt=2, H=2, P=2),      # fused polar kernel with a partial second row tile (144 = 128 + 16)
+    dict(B=4, Ns=320, Nt=320, Ds=192, Dt=384, Lt=3, H=2, P=2),      # N > 256: column-tiled polar products, tiled token Gram
+    dict(B=4, Ns=300, Nt=300, Ds=256, Dt=512, Lt=3, H=2, P=2),      # D_s > 224: global-memory eigen-solver, three row tiles
+    dict(B=4, Ns=100, Nt=100, Ds=136, Dt=160, Lt=2, H=2, P=2),      # D_s > N - 1 (teacher-token form), nothing a multiple of 64
+    dict(B=3, Ns=220, Nt=110, Ds=216, Dt=256, Lt=2, H=2, P=2),      # teacher-token form with resampling 110 -> 220, D_s % 16 == 8
+    dict(B=3, Ns=240, Nt=220, Ds=232, Dt=256, Lt=2, H=2, P=2),      # teacher-token form, N_t > 208: two column tiles in the polynomial product
 ])
 def test_irregular_shapes_against_oracle(lib, cuda_dev, shape):
     """Shapes off the BASELINE grid: padding, tails and tile boundaries of every kernel against the fp32 oracle."""

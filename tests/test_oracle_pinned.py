@@ -33,7 +33,8 @@ def rel(a, b):
     return ((a.double() - b.double()).norm() / b.double().norm().clamp(min=1e-30)).item()
 
 
-@pytest.mark.parametrize("name", ["tiny_cls", "tiny_interp", "tiny_cnn", "tiny_up", "tiny_down", "tiny_cnn_down", "cfg1"])
+@pytest.mark.parametrize("name", ["tiny_cls", "tiny_interp", "tiny_cnn", "tiny_up", "tiny_down", "tiny_cnn_down", "cfg1",
+                                  "cfg3_b8", "cfg4_b4", "cfg5_b2"])
 def test_oracle_reproduces_reference_golden(name):
     g, w = load_golden(name)
     inp = synth.make_inputs(w, seed=g["seed"])

@@ -90,11 +90,21 @@ extern "C" int basd_debug_spectral_clocks(long long* host_out) { return basd::sp
 
 namespace {
 
+// Which space the Procrustes polar iteration runs in (polar.cu):
+//   kPathFeature : student features (D_s x N_s iterate); needs rank(C) = D_s, i.e. D_s <= min(N_s, N_t) - 1
+//   kPathTeacherTokens : teacher tokens (N_t x D_s iterate), D_s > min(N_s, N_t) - 1 and N_t <= N_s
+enum { kPathFeature = 0, kPathTeacherTokens = 1 };
+int polar_path(const basd_shape& s) {
+    const int rank_t = (s.Nt < s.Ns ? s.Nt : s.Ns) - 1;
+    return s.Ds <= rank_t ? kPathFeature : kPathTeacherTokens;
+}
+
 struct Layout {
     size_t rows, pt_hi, pt_lo, tpk, spk, z, stats, ranks, sweeps, evals, evecs_km, evecs_cm, d2, w, cosv, gamma, ang_scr, a, ssum,
         tbar_hi, tbar_lo, ktt, gdir, theta, gwt, loss_b, dbg, geo_i, gw, gam_hi, gam_lo, corr,
-        pw, pw2, pt, pa, pb, pkt, psw, gsw, pvec, pscal, pfro, theta_lo, dtm, total;
-    int NsPad, Np;
+        pw, pw2, pt, pa, pb, pkt, psw, gsw, pvec, pscal, pfro, theta_lo, dtm, eig_scr,
+        vfg, vfgt, vginvc, vginvt, vx0, vx1, vx2, vh, vm2, vginv, vthraw, vftf, total;
+    int NsPad, Np, path, Nk, Dsp;    // Nk: token rows of the mixed teacher / Theta (Ns, or Nt in the teacher-token form)
 };
 
 size_t align_up(size_t x) { return (x + 1023) & ~static_cast<size_t>(1023); }
@@ -104,7 +114,12 @@ Layout make_layout(const basd_shape& s) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
     const size_t B = s.B, Ns = s.Ns, Nt = s.Nt, Ds = s.Ds, Dt = s.Dt, Lt = s.Lt, P = s.P;
-    L.NsPad = static_cast<int>((Ns + 7) / 8 * 8);
+    L.path = polar_path(s);
+    const bool vt = L.path == kPathTeacherTokens;
+    const size_t Nk = vt ? Nt : Ns;
+    L.Nk = static_cast<int>(Nk);
+    L.NsPad = static_cast<int>((Nk + 7) / 8 * 8);
+    L.Dsp = static_cast<int>((Ds + 15) / 16 * 16 + 8);
     L.rows = take(4 * Lt * B * Nt);
     L.pt_hi = take(2 * Ds * Dt);
     L.pt_lo = take(2 * Ds * Dt);
@@ -118,6 +133,7 @@ Layout make_layout(const basd_shape& s) {
     L.evals = take(4 * (Lt + P) * Ds);
     L.evecs_km = take(4 * (Lt + P) * Ds * Ds);
     L.evecs_cm = take(4 * (Lt + P) * Ds * Ds);
+    L.eig_scr = take(4 * pooled_eig_scratch_floats(s.Ds, 2 * s.Lt + s.P));   // D_s > 224: eigenproblem matrices in global memory
     L.d2 = take(4 * P * Lt);
     L.w = take(4 * P * Lt);
     L.cosv = take(4 * P * Lt * Ds);
@@ -125,28 +141,41 @@ Layout make_layout(const basd_shape& s) {
     L.ang_scr = take(4 * P * Lt * 8 * Ds * Ds);
     L.a = take(4 * P * B * Ns);
     L.ssum = take(4 * P * B);
-    L.tbar_hi = take(2 * P * B * Ns * Dt);
-    L.tbar_lo = take(2 * P * B * Ns * Dt);
-    L.ktt = take(4 * P * B * Ns * Ns);
+    L.tbar_hi = take(2 * P * B * Nk * Dt);
+    L.tbar_lo = take(2 * P * B * Nk * Dt);
+    L.ktt = take(4 * P * B * Nk * Nk);
     // Newton-Schulz polar iteration (polar.cu): split-bf16 matrices per (point, sample) problem, hi then lo
     L.Np = static_cast<int>((Ns + 63) / 64 * 64);      // column-block tiled storage: columns padded to 64
     const size_t nprob = P * B, Np = L.Np;
     const size_t Dp = (Ds + 63) / 64 * 64;
-    L.pw = take(2 * 2 * nprob * Ds * Np);
-    L.pw2 = take(2 * 2 * nprob * Ds * Np);
-    L.pt = take(2 * 2 * nprob * Ds * Np);
-    L.pa = take(2 * 2 * nprob * Ds * Dp);
-    L.pb = take(2 * 2 * nprob * Ds * Dp);
-    L.pkt = take(2 * 2 * nprob * Ns * Np);
+    const size_t Mp = (Nt + 63) / 64 * 64, Xp = (static_cast<size_t>(L.Dsp) + 63) / 64 * 64;
+    L.pw = take(vt ? 0 : 2 * 2 * nprob * Ds * Np);
+    L.pw2 = take(vt ? 0 : 2 * 2 * nprob * Ds * Np);
+    L.pt = take(vt ? 0 : 2 * 2 * nprob * Ds * Np);
+    L.pa = take(vt ? 2 * 2 * nprob * Nt * Mp : 2 * 2 * nprob * Ds * Dp);       // A  (core x core)
+    L.pb = take(vt ? 2 * 2 * nprob * Nt * Mp : 2 * 2 * nprob * Ds * Dp);       // Bm
+    L.pkt = take(vt ? 0 : 2 * 2 * nprob * Ns * Np);
     L.psw = take(2 * 2 * nprob * Ns * Dp);
+    L.vfg = take(vt ? 2 * 2 * nprob * Ns * Mp : 0);
+    L.vfgt = take(vt ? 2 * 2 * nprob * Nt * Np : 0);
+    L.vginvc = take(vt ? 2 * 2 * nprob * Nt * Mp : 0);
+    L.vginvt = take(vt ? 2 * 2 * nprob * Nt * Mp : 0);
+    L.vx0 = take(vt ? 2 * 2 * nprob * Nt * Xp : 0);
+    L.vx1 = take(vt ? 2 * 2 * nprob * Nt * Xp : 0);
+    L.vx2 = take(vt ? 2 * 2 * nprob * Nt * Xp : 0);
+    L.vh = take(vt ? 2 * 2 * nprob * Nt * Mp : 0);
+    L.vm2 = take(vt ? 2 * 2 * nprob * Nt * Mp : 0);
+    L.vginv = take(vt ? 4 * nprob * Nt * Nt : 0);
+    L.vthraw = take(vt ? 4 * nprob * Nt * Nt : 0);
+    L.vftf = take(vt ? 4 * nprob * Nt * Nt : 0);
     L.gsw = take(4 * nprob * Ns * Ds);
     L.pvec = take(4 * nprob * 4 * Ns);
     L.pscal = take(4 * nprob * 4);
     L.pfro = take(4 * nprob);
     L.gdir = take(4 * P * B * Ns * Ds);
-    L.theta = take(2 * P * B * Ns * L.NsPad);
-    L.theta_lo = take(2 * P * B * Ns * L.NsPad);
-    L.dtm = take(2 * P * B * Ns * Dt);
+    L.theta = take(2 * P * B * Nk * L.NsPad);
+    L.theta_lo = take(2 * P * B * Nk * L.NsPad);
+    L.dtm = take(2 * P * B * Nk * Dt);
     L.gwt = take(4 * P * B * Ns);
     L.loss_b = take(4 * P * B);
     L.dbg = take(4 * P * B * 5);
@@ -164,14 +193,14 @@ int check_shape(const basd_shape& s) {
     if (s.world_size < 1) return fail("world_size must be >= 1");
     if (s.P > BASD_MAX_POINTS || s.Lt > BASD_MAX_LAYERS) return fail("P <= %d and Lt <= %d required", BASD_MAX_POINTS, BASD_MAX_LAYERS);
     if (s.Ds % 8 || s.Dt % 8) return fail("Ds and Dt must be multiples of 8 (16-byte rows), got %d, %d", s.Ds, s.Dt);
-    if (s.Ds > 224) return fail("Ds=%d > 224: pooled eigenproblems larger than one SM's shared memory are not built yet", s.Ds);
-    if (s.Ns > 256) return fail("Ns=%d > 256: per-sample products larger than one CTA tile are not built yet", s.Ns);
-    {
-        // rank of the weighted, centred (and, if Nt < Ns, up-sampled) teacher token matrix
-        const int rank_t = (s.Nt < s.Ns ? s.Nt : s.Ns) - 1;
-        if (s.Ds > rank_t)
-            return fail("Ds=%d > min(Ns, Nt)-1=%d: the cross-covariance is rank deficient on the student side; the token-space form of "
-                        "the polar iteration is not built yet", s.Ds, rank_t);
+    if (s.Ds > 1024) return fail("Ds=%d > 1024 is not supported", s.Ds);
+    if (polar_path(s) == kPathTeacherTokens) {
+        // rank(C) = min(Ns, Nt) - 1 < Ds: the polar iteration runs in the teacher's token space
+        if (s.Nt > s.Ns)
+            return fail("Ds=%d > Ns-1=%d with Nt=%d > Ns: the student-token-space form of the polar iteration is not built yet", s.Ds, s.Ns - 1, s.Nt);
+        if (s.Nt > kVtMaxTokens)
+            return fail("Ds=%d > Nt-1 with Nt=%d > %d: the token-space Cholesky factor no longer fits shared memory", s.Ds, s.Nt, kVtMaxTokens);
+        if (s.Nt < 2) return fail("Nt >= 2 required");
     }
     if (static_cast<long long>(s.B) * s.Nt * s.world_size < s.Ds)
         return fail("pooled rows M < Ds (layer_selector.py:14-15 branch) is not supported");
@@ -226,13 +255,13 @@ extern "C" int basd_view(const basd_shape* shape, void* workspace, const char* n
         {"stats", L.stats, (Lt + P) * (Ds * Ds + Ds)}, {"gw", L.gw, P * Lt}, {"ranks", L.ranks, Lt}, {"w", L.w, P * Lt},
         {"d2", L.d2, P * Lt}, {"geo_i", L.geo_i, P + 1}, {"loss_b", L.loss_b, P * B}, {"rows", L.rows, Lt * B * Nt},
         {"a", L.a, P * B * Ns}, {"evals", L.evals, (Lt + P) * Ds}, {"cos", L.cosv, P * Lt * Ds}, {"dbg", L.dbg, P * B * 5},
-        {"gdir", L.gdir, P * B * Ns * Ds}, {"ktt", L.ktt, P * B * Ns * Ns}, {"sweeps", L.sweeps, 2 * Lt + P},
+        {"gdir", L.gdir, P * B * Ns * Ds}, {"ktt", L.ktt, P * B * L.Nk * L.Nk}, {"sweeps", L.sweeps, 2 * Lt + P},
         {"gamma", L.gamma, P * Lt * Ds * Ds}, {"gwt", L.gwt, P * B * Ns}, {"evecs", L.evecs_km, (Lt + P) * Ds * Ds},
         {"corr", L.corr, P * Ds}, {"ssum", L.ssum, P * B},
         // polar iteration state (bf16 pairs: count is in bf16 elements, hi block then lo block)
         {"polar_w", (polar_steps() % 2) ? L.pw2 : L.pw, 2 * P * B * Ds * L.Np}, {"polar_kt", L.pkt, 2 * P * B * Ns * L.Np},
         {"polar_sw", L.psw, 2 * P * B * Ns * ((Ds + 63) / 64 * 64)}, {"polar_a", L.pa, 2 * P * B * Ds * ((Ds + 63) / 64 * 64)}, {"polar_gsw", L.gsw, P * B * Ns * Ds}, {"polar_fro2", L.pfro, P * B},
-        {"theta", L.theta, P * B * Ns * L.NsPad},
+        {"theta", L.theta, P * B * L.Nk * L.NsPad},
     };
     for (const E& e : table)
         if (!strcmp(e.n, name)) { *ptr = ws + e.off; *count = e.cnt; return 0; }
@@ -331,7 +360,8 @@ extern "C" int basd_forward_solve(const basd_shape* shape, const basd_inputs* in
     float* d2 = reinterpret_cast<float*>(ws + L.d2);
     float* w = reinterpret_cast<float*>(ws + L.w);
 
-    TIMED(5, 1, CK(launch_pooled_eig(stats, s.Ds, s.Lt, s.P, Mt, Ms, ranks, evals, evk, evc, reinterpret_cast<int*>(ws + L.sweeps), st)));
+    TIMED(5, 1, CK(launch_pooled_eig(stats, s.Ds, s.Lt, s.P, Mt, Ms, ranks, evals, evk, evc, reinterpret_cast<int*>(ws + L.sweeps),
+                                  reinterpret_cast<float*>(ws + L.eig_scr), st)));
     TIMED(6, 2, CK(launch_angles(s.Ds, s.Lt, s.P, ranks, evals, evk, evc, in.proj_s, reinterpret_cast<float*>(ws + L.ang_scr), d2,
                      reinterpret_cast<float*>(ws + L.gamma), reinterpret_cast<float*>(ws + L.cosv), in.log_temperatures, w, st)));
     float* a = reinterpret_cast<float*>(ws + L.a);
@@ -342,9 +372,11 @@ extern "C" int basd_forward_solve(const basd_shape* shape, const basd_inputs* in
     for (int j = 0; j < s.Lt; ++j) tt.p[j] = r.teacher[j];
     __nv_bfloat16* thi = reinterpret_cast<__nv_bfloat16*>(ws + L.tbar_hi);
     __nv_bfloat16* tlo = reinterpret_cast<__nv_bfloat16*>(ws + L.tbar_lo);
-    TIMED(8, 1, CK(launch_mix_teacher(tt, w, s.Lt, s.P, s.B, s.Nt, s.Ns, s.Dt, thi, tlo, st)));
+    // teacher-token form: the mixed teacher stays on its own token grid (the resampling is folded into F, polar.cu)
+    const bool vt = L.path == kPathTeacherTokens;
+    TIMED(8, 1, CK(launch_mix_teacher(tt, w, s.Lt, s.P, s.B, s.Nt, L.Nk, s.Dt, thi, tlo, st)));
     float* ktt = reinterpret_cast<float*>(ws + L.ktt);
-    TIMED(9, 1, CK(gemm_token_gram(thi, tlo, s.P * s.B, s.Ns, s.Dt, ktt, st)));
+    TIMED(9, 1, CK(gemm_token_gram(thi, tlo, s.P * s.B, L.Nk, s.Dt, ktt, st)));
 
     PolarArgs pa;
     memset(&pa, 0, sizeof pa);
@@ -360,13 +392,31 @@ extern "C" int basd_forward_solve(const basd_shape* shape, const basd_inputs* in
             m.lo = m.hi + nprob * m.batch_stride;
             return m;
         };
-        pa.W = split(L.pw, s.Ds, s.Ns);
-        pa.W2 = split(L.pw2, s.Ds, s.Ns);
-        pa.T = split(L.pt, s.Ds, s.Ns);
-        pa.A = split(L.pa, s.Ds, s.Ds);
-        pa.Bm = split(L.pb, s.Ds, s.Ds);
-        pa.Kt = split(L.pkt, s.Ns, s.Ns);
         pa.SW = split(L.psw, s.Ns, s.Ds);
+        if (!vt) {
+            pa.W = split(L.pw, s.Ds, s.Ns);
+            pa.W2 = split(L.pw2, s.Ds, s.Ns);
+            pa.T = split(L.pt, s.Ds, s.Ns);
+            pa.A = split(L.pa, s.Ds, s.Ds);
+            pa.Bm = split(L.pb, s.Ds, s.Ds);
+            pa.Kt = split(L.pkt, s.Ns, s.Ns);
+        } else {
+            pa.vt = 1; pa.Nt = s.Nt; pa.NtPad = L.NsPad; pa.Dsp = L.Dsp;
+            pa.A = split(L.pa, s.Nt, s.Nt);
+            pa.Bm = split(L.pb, s.Nt, s.Nt);
+            pa.FG = split(L.vfg, s.Ns, s.Nt);
+            pa.FGt = split(L.vfgt, s.Nt, s.Ns);
+            pa.GinvC = split(L.vginvc, s.Nt, s.Nt);
+            pa.GinvT = split(L.vginvt, s.Nt, s.Nt);
+            pa.X0 = split(L.vx0, s.Nt, L.Dsp);
+            pa.X1 = split(L.vx1, s.Nt, L.Dsp);
+            pa.X2 = split(L.vx2, s.Nt, L.Dsp);
+            pa.Hm = split(L.vh, s.Nt, s.Nt);
+            pa.M2 = split(L.vm2, s.Nt, s.Nt);
+            pa.ginv = reinterpret_cast<float*>(ws + L.vginv);
+            pa.thraw = reinterpret_cast<float*>(ws + L.vthraw);
+            pa.ftf = reinterpret_cast<float*>(ws + L.vftf);
+        }
     }
     pa.Gsw = reinterpret_cast<float*>(ws + L.gsw);
     pa.vec = reinterpret_cast<float*>(ws + L.pvec);
@@ -378,7 +428,8 @@ extern "C" int basd_forward_solve(const basd_shape* shape, const basd_inputs* in
     pa.gwt = reinterpret_cast<float*>(ws + L.gwt);
     pa.loss_b = reinterpret_cast<float*>(ws + L.loss_b);
     pa.dbg = reinterpret_cast<float*>(ws + L.dbg);
-    CK(launch_polar_procrustes(pa, st, nullptr));      // timing slots 10 / 16 / 17 are bracketed inside
+    if (vt) CK(launch_polar_procrustes_vt(pa, st, nullptr));
+    else CK(launch_polar_procrustes(pa, st, nullptr));  // timing slots 10 / 16 / 17 are bracketed inside
     float* geo_i = reinterpret_cast<float*>(ws + L.geo_i);
     TIMED(11, 1, CK(launch_loss_reduce(pa.loss_b, s.P, s.B, geo_i, geo_i + s.P, st)));
     CK(cudaMemcpyAsync(geo_loss, geo_i + s.P, sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -400,12 +451,13 @@ extern "C" int basd_backward_dots(const basd_shape* shape, const basd_inputs* in
     __nv_bfloat16* thi = reinterpret_cast<__nv_bfloat16*>(ws + L.tbar_hi);
     __nv_bfloat16* tlo = reinterpret_cast<__nv_bfloat16*>(ws + L.tbar_lo);
     __nv_bfloat16* dtm = reinterpret_cast<__nv_bfloat16*>(ws + L.dtm);
+    // (teacher-token form: Theta, the mixed teacher and its gradient live on the teacher's own token grid, L.Nk = Nt rows)
     TIMED(12, 1, CK(gemm_theta_apply(reinterpret_cast<__nv_bfloat16*>(ws + L.theta), reinterpret_cast<__nv_bfloat16*>(ws + L.theta_lo), L.NsPad,
-                                     thi, tlo, s.P * s.B, s.Ns, s.Dt, dtm, st)));
+                                     thi, tlo, s.P * s.B, L.Nk, s.Dt, dtm, st)));
     float* gw = reinterpret_cast<float*>(ws + L.gw);
     CK(cudaMemsetAsync(gw, 0, sizeof(float) * s.P * s.Lt, st));
     TIMED(13, 2, CK(launch_wgrad_dots(tt, dtm, reinterpret_cast<float*>(ws + L.gwt), reinterpret_cast<float*>(ws + L.rows), s.Lt, s.P, s.B, s.Nt,
-                         s.Ns, s.Dt, gw, st)));
+                         s.Ns, s.Dt, gw, st, L.path == kPathTeacherTokens)));
     return 0;
 }
 
@@ -443,14 +495,14 @@ extern "C" int basd_backward_finish(const basd_shape* shape, const basd_inputs* 
 extern "C" int basd_mp_rank_workspace_bytes(int64_t M, int D, size_t* bytes) {
     if (!bytes || M < 1 || D < 8) return fail("invalid argument");
     *bytes = 2 * align_up(2 * static_cast<size_t>(M) * D) + align_up(4 * 2 * (static_cast<size_t>(D) * D + D)) + align_up(4 * 2 * D) +
-             2 * align_up(4 * 2 * static_cast<size_t>(D) * D) + 4096;
+             2 * align_up(4 * 2 * static_cast<size_t>(D) * D) + align_up(4 * pooled_eig_scratch_floats(D, 2)) + 4096;
     return 0;
 }
 
 extern "C" int basd_mp_rank(const void* features, int64_t M, int D, int dtype, int64_t row_stride, int* rank_out, void* workspace,
                             void* stream) {
     if (!features || !rank_out || !workspace) return fail("null argument");
-    if (D % 8 || D > 224) return fail("basd_mp_rank: D must be a multiple of 8 and <= 224 (got %d)", D);
+    if (D % 8 || D > 4096) return fail("basd_mp_rank: D must be a multiple of 8 and <= 4096 (got %d)", D);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
     size_t off = 0;
@@ -460,12 +512,13 @@ extern "C" int basd_mp_rank(const void* features, int64_t M, int D, int dtype, i
     float* evals = reinterpret_cast<float*>(ws + off); off += align_up(4 * 2 * D);
     float* evk = reinterpret_cast<float*>(ws + off); off += align_up(4 * 2 * static_cast<size_t>(D) * D);
     float* evc = reinterpret_cast<float*>(ws + off); off += align_up(4 * 2 * static_cast<size_t>(D) * D);
+    float* eig_scr = reinterpret_cast<float*>(ws + off); off += align_up(4 * pooled_eig_scratch_floats(D, 2));   // the launch runs the MP problem and the centred one
     int* ranks = reinterpret_cast<int*>(ws + off);
     const bool exact = dtype == BASD_DTYPE_BF16;             // fp32 features keep fp32-class precision as a split pair
     CK(launch_pack_bf16(features, exact, 0, row_stride, 1, 1, static_cast<int>(M), D, zb, exact ? nullptr : zl, st));
     CK(cudaMemsetAsync(stats, 0, 4 * 2 * (static_cast<size_t>(D) * D + D), st));
     CK(gemm_gram(zb, exact ? nullptr : zl, static_cast<size_t>(M), D, stats, st));
-    CK(launch_pooled_eig(stats, D, 1, 0, static_cast<float>(M), 1.f, ranks, evals, evk, evc, nullptr, st));
+    CK(launch_pooled_eig(stats, D, 1, 0, static_cast<float>(M), 1.f, ranks, evals, evk, evc, nullptr, eig_scr, st));
     CK(cudaMemcpyAsync(rank_out, ranks, sizeof(int), cudaMemcpyDeviceToDevice, st));
     return 0;
 }
@@ -490,16 +543,16 @@ extern "C" int basd_selftest_gemm(int variant, const void* A, const void* B, flo
 }
 
 // eigen-decomposition of a symmetric PSD matrix G [n][n]: evals [n] descending, evecs [n][n] (row e = e-th eigenvector).
-// workspace: 4 * (n*n + n) + 4 * n * n bytes (+ alignment slack 4096).
+// workspace: 4 * (n*n + n) + 4 * n * n bytes (+ alignment slack 4096), plus 4 * n * (n + 3) bytes when n > 224.
 extern "C" int basd_selftest_eig(const float* G, int n, float* evals, float* evecs, int* sweeps, void* workspace, void* stream) {
     if (!G || !evals || !evecs || !workspace) return fail("null argument");
-    if (n > 224) return fail("n > 224");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
     float* stats = reinterpret_cast<float*>(ws);
     float* evc = reinterpret_cast<float*>(ws + align_up(4 * (static_cast<size_t>(n) * n + n)));
+    float* eig_scr = reinterpret_cast<float*>(ws + align_up(4 * (static_cast<size_t>(n) * n + n)) + align_up(4 * static_cast<size_t>(n) * n));
     CK(cudaMemsetAsync(stats, 0, 4 * (static_cast<size_t>(n) * n + n), st));
     CK(cudaMemcpyAsync(stats, G, 4 * static_cast<size_t>(n) * n, cudaMemcpyDeviceToDevice, st));
-    CK(launch_pooled_eig(stats, n, 0, 1, 1.f, 1.f, nullptr, evals, evecs, evc, sweeps, st));
+    CK(launch_pooled_eig(stats, n, 0, 1, 1.f, 1.f, nullptr, evals, evecs, evc, sweeps, eig_scr, st));
     return 0;
 }

@@ -106,6 +106,7 @@ using CfgGram3A  = GemmCfg<true,  true,  192, 2, 2, 2, 3, true,  3>;      // the
 using CfgTheta   = GemmCfg<false, true,  128, 2, 1, 1, 1, false, 4>;      // self test (single operands)
 using CfgTheta3  = GemmCfg<false, true,  128, 2, 2, 2, 3, false, 1>;      // split Theta x split mixed teacher; one stage (96 KB), 256 TMEM columns: two CTAs per SM
 template <int BN> using CfgTokenGram = GemmCfg<false, false, BN, 2, 2, 2, 3, true, 3>;
+using CfgTokenGramTiled = GemmCfg<false, false, 192, 2, 2, 2, 3, false, 2>;   // N_s > 256: 256 x 192 output tiles, B loaded separately
 using CfgTestTN  = GemmCfg<false, false, 192, 1, 1, 1, 1, false, 4>;
 
 // Z[j] = X[j] P_t^T for all L_t teacher layers in ONE launch (blockIdx.z = layer; the layers are separate tensors, so each
@@ -200,16 +201,24 @@ cudaError_t gemm_token_gram(const __nv_bfloat16* Thi, const __nv_bfloat16* Tlo, 
     if (Ns <= 128) return token_gram_impl<128>(Thi, Tlo, batches, Ns, Dt, Ktt, st);
     if (Ns <= 208) return token_gram_impl<208>(Thi, Tlo, batches, Ns, Dt, Ktt, st);
     if (Ns <= 256) return token_gram_impl<256>(Thi, Tlo, batches, Ns, Dt, Ktt, st);
-    snprintf(g_gemm_err, sizeof g_gemm_err, "token_gram: Ns=%d > 256 not supported yet", Ns);
-    return cudaErrorInvalidValue;
+    // more than one output tile per sample (e.g. 576 tokens at 384 px)
+    GemmMaps maps;
+    memset(&maps, 0, sizeof maps);
+    const __nv_bfloat16* tp[2] = {Thi, Tlo};
+    for (int i = 0; i < 2; ++i) {
+        if (make_map(&maps.a[i], tp[i], Dt, Ns, batches, Dt, static_cast<uint64_t>(Ns) * Dt, 128)) return cudaErrorInvalidValue;
+        if (make_map(&maps.b[i], tp[i], Dt, Ns, batches, Dt, static_cast<uint64_t>(Ns) * Dt, CfgTokenGramTiled::kBN)) return cudaErrorInvalidValue;
+    }
+    GemmArgs a;
+    memset(&a, 0, sizeof a);
+    a.kb_total = cdiv(Dt, GEMM_BK);
+    a.a_batched = 1; a.b_batched = 1;
+    a.out = Ktt; a.out_batch_stride = static_cast<long long>(Ns) * Ns; a.ld_out = Ns; a.rows_valid = Ns; a.cols_valid = Ns; a.alpha = 1.f;
+    return launch<CfgTokenGramTiled, EpiStoreF32>(maps, a, dim3(cdiv(Ns, CfgTokenGramTiled::kBN), cdiv(Ns, CfgTokenGramTiled::kMT * 128), batches), st);
 }
 
 cudaError_t gemm_theta_apply(const __nv_bfloat16* theta, const __nv_bfloat16* theta_lo, int NsPad, const __nv_bfloat16* Thi,
                              const __nv_bfloat16* Tlo, int batches, int Ns, int Dt, __nv_bfloat16* Dtm, cudaStream_t st) {
-    if (Ns > 256) {
-        snprintf(g_gemm_err, sizeof g_gemm_err, "theta_apply: Ns=%d > 256 not supported yet", Ns);
-        return cudaErrorInvalidValue;
-    }
     GemmMaps maps;
     memset(&maps, 0, sizeof maps);
     // inner extent Ns (not NsPad): the pad columns are never read, TMA zero-fills them
@@ -222,7 +231,7 @@ cudaError_t gemm_theta_apply(const __nv_bfloat16* theta, const __nv_bfloat16* th
     a.kb_total = cdiv(Ns, GEMM_BK);
     a.a_batched = 1; a.b_batched = 1;
     a.out = Dtm; a.out_batch_stride = static_cast<long long>(Ns) * Dt; a.ld_out = Dt; a.rows_valid = Ns; a.cols_valid = Dt; a.alpha = 1.f;
-    return launch<CfgTheta3, EpiStoreBf16>(maps, a, dim3(cdiv(Dt, CfgTheta3::kBN), 1, batches), st);
+    return launch<CfgTheta3, EpiStoreBf16>(maps, a, dim3(cdiv(Dt, CfgTheta3::kBN), cdiv(Ns, CfgTheta3::kMT * 128), batches), st);
 }
 
 cudaError_t gemm_student_grad(const __nv_bfloat16* S, size_t M, int Ds, const __nv_bfloat16* Ghi, const __nv_bfloat16* Glo,
@@ -245,19 +254,27 @@ cudaError_t gemm_student_grad(const __nv_bfloat16* S, size_t M, int Ds, const __
 // polar_gemm: one CTA per problem, run-time tile sizes (polar_gemm.cuh)
 // ---------------------------------------------------------------------------------------------------
 cudaError_t polar_gemm(bool b_mn, const SplitMat& A, const SplitMat& B, int batches, PolarGemmArgs& a, cudaStream_t st) {
-    const int m_rows = A.rows, K = A.inner;
-    const int n_cols = b_mn ? B.inner : B.rows;
-    if (m_rows > 256 || n_cols > 256 || (b_mn ? B.rows : B.inner) != K) {
-        snprintf(g_gemm_err, sizeof g_gemm_err, "polar_gemm: unsupported sizes m=%d n=%d k=%d", m_rows, n_cols, K);
+    const int m_rows = A.rows, K = a.k_override > 0 ? a.k_override : A.inner;
+    const int n_cols = a.n_override > 0 ? a.n_override : (b_mn ? B.inner : B.rows);
+    if (m_rows < 1 || n_cols < 1 || n_cols > (b_mn ? B.inner : B.rows) || K < 1 || K > A.inner || (b_mn ? B.rows : B.inner) < K) {
+        snprintf(g_gemm_err, sizeof g_gemm_err, "polar_gemm: inconsistent sizes m=%d n=%d k=%d", m_rows, n_cols, K);
         return cudaErrorInvalidValue;
     }
     a.m_rows = m_rows; a.n_cols = n_cols; a.k_total = K;
     a.n_mt = (m_rows + 127) / 128;
-    a.n_items = batches * a.n_mt;
+    // column tiles: one tile of up to 256 columns, or equal tiles of a multiple of 64 columns (the auxiliary-tile epilogue
+    // keeps a whole tile of the auxiliary matrix per warp in shared memory: 128 columns at most there)
+    const int max_tile = a.aux_mode ? 128 : 256;
+    if (n_cols <= (a.aux_mode ? 208 : max_tile)) {
+        a.n_nt = 1;
+        a.bn_mma = (n_cols + 15) / 16 * 16;
+    } else {
+        a.n_nt = (n_cols + max_tile - 1) / max_tile;
+        a.bn_mma = ((n_cols + a.n_nt - 1) / a.n_nt + 63) / 64 * 64;
+        a.n_nt = (n_cols + a.bn_mma - 1) / a.bn_mma;
+    }
+    a.n_items = batches * a.n_mt * a.n_nt;
     a.n_batches = batches;
-    a.a_rows_tile[0] = m_rows >= 128 ? 128 : (m_rows + 63) / 64 * 64;
-    a.a_rows_tile[1] = m_rows > 128 ? (m_rows - 128 + 63) / 64 * 64 : 0;
-    a.bn_mma = (n_cols + 15) / 16 * 16;
     a.b_groups = (a.bn_mma + 63) / 64;
     PolarGemmMaps maps;
     memset(&maps, 0, sizeof maps);
@@ -285,6 +302,7 @@ cudaError_t polar_gemm(bool b_mn, const SplitMat& A, const SplitMat& B, int batc
         snprintf(g_gemm_err, sizeof g_gemm_err, "polar_gemm: a_alias_b needs the same K-major matrix on both sides");
         return cudaErrorInvalidValue;
     }
+    if (a.a_alias_b && a.n_nt > 1) a.a_alias_b = 0;      // the A tile is only inside the B tile when one tile spans all columns
     const int b_bytes = b_mn ? a.b_groups * 8192 : a.bn_mma * 128;
     const int stage_bytes = (a.a_alias_b ? 0 : 2 * 16384) + 2 * b_bytes;
     const int kTail = 1024 /*alignment*/ + 1024 /*barriers*/ + 4 * 8192 /*epilogue staging*/ + (a.aux_mode ? 4 * 8192 * ((a.bn_mma + 63) / 64) : 0) /*aux tiles: every column block of an item*/;   // (the aliased A tile of the last rows reads up to 8 KB past its B tile: into the barrier / staging area, rows never used)

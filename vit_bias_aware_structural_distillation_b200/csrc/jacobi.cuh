@@ -23,7 +23,7 @@ namespace basd {
 
 constexpr int JAC_GROUP = 8;
 constexpr int JAC_CHUNK_ROWS = JAC_GROUP * 4;
-constexpr int JAC_MAX_CHUNKS = 8;      // 8 chunks x 32 rows -> m <= 256
+constexpr int JAC_MAX_CHUNKS = 8;      // 8 chunks x 32 rows -> m <= 256 (register-resident variants)
 
 __host__ __device__ inline int jacobi_ld(int m) { return (m + 3) & ~3; }     // 128-bit rows; no bank constraint (see above)
 
@@ -367,6 +367,102 @@ __device__ int jacobi_orthogonalize_oddeven_cluster(float* __restrict__ A, int l
     jac_st<CHUNKS>(A0 + static_cast<size_t>(st_p ? col_p : 0) * ld, ld, gl, st_p, P);
     jac_st<CHUNKS>(A0 + static_cast<size_t>(st_q ? col_q : 0) * ld, ld, gl, st_q, Q);
     jac_cluster_sync();
+    return sweep;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Round-robin variant on ONE CTA with the columns in GLOBAL memory (L2-resident), for matrices that do not fit one
+// SM's shared memory (pooled eigenproblems of size 384, marchenko_pastur_rank on unprojected D_t-wide features) -
+// any column length.  A pair of columns is owned by a GL-lane group (GL = 4 or 8) and streamed twice: once for the
+// three inner products, once for the rotation.  Same rotation, tolerance and end-game exit as the variants above.
+// All threads of the CTA must call it; returns the sweep count.  ld a multiple of 4, A 16-byte aligned.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 jac_ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 jac_rot4(float c, float s, const float4& x, const float4& y) {      // c x + s y
+    return make_float4(fmaf(c, x.x, s * y.x), fmaf(c, x.y, s * y.y), fmaf(c, x.z, s * y.z), fmaf(c, x.w, s * y.w));
+}
+constexpr int JG_U = 6;                     // 16-byte loads per column in flight per lane
+template <int GL>
+__device__ int jacobi_orthogonalize_global(float* __restrict__ A, int ld, int n_cols, float tol, int max_sweeps) {
+    const int n = (n_cols + 1) & ~1;
+    const int half = n / 2;
+    const int group = threadIdx.x / GL;
+    const int gl = threadIdx.x % GL;
+    const int n_groups = static_cast<int>(blockDim.x) / GL;
+    int sweep = 0;
+    if (n_cols >= 2) {
+        for (; sweep < max_sweeps; ++sweep) {
+            int rotated = 0;
+            for (int s = 0; s < n - 1; ++s) {
+                for (int kb = 0; kb < half; kb += n_groups) {           // same trip count for every thread
+                    const int k = kb + group;
+                    int p = 0, q = 0;
+                    if (k < half) jacobi_pair(n, s, k, p, q);
+                    const bool ok = k < half && p < n_cols && q < n_cols;
+                    float* cp = A + static_cast<size_t>(ok ? p : 0) * ld;
+                    float* cq = A + static_cast<size_t>(ok ? q : 0) * ld;
+                    float al = 0.f, be = 0.f, ga = 0.f;
+                    if (ok) {
+                        int r = gl * 4;
+                        for (; r + (JG_U - 1) * GL * 4 < ld; r += JG_U * GL * 4) {  // JG_U 16-byte loads of each column in flight
+                            float4 x[JG_U], y[JG_U];
+#pragma unroll
+                            for (int u = 0; u < JG_U; ++u) { x[u] = jac_ldcg4(cp + r + u * GL * 4); y[u] = jac_ldcg4(cq + r + u * GL * 4); }
+#pragma unroll
+                            for (int u = 0; u < JG_U; ++u) {
+                                al = fmaf(x[u].x, x[u].x, fmaf(x[u].y, x[u].y, fmaf(x[u].z, x[u].z, fmaf(x[u].w, x[u].w, al))));
+                                be = fmaf(y[u].x, y[u].x, fmaf(y[u].y, y[u].y, fmaf(y[u].z, y[u].z, fmaf(y[u].w, y[u].w, be))));
+                                ga = fmaf(x[u].x, y[u].x, fmaf(x[u].y, y[u].y, fmaf(x[u].z, y[u].z, fmaf(x[u].w, y[u].w, ga))));
+                            }
+                        }
+                        for (; r < ld; r += GL * 4) {
+                            const float4 x = jac_ldcg4(cp + r), y = jac_ldcg4(cq + r);
+                            al = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, al))));
+                            be = fmaf(y.x, y.x, fmaf(y.y, y.y, fmaf(y.z, y.z, fmaf(y.w, y.w, be))));
+                            ga = fmaf(x.x, y.x, fmaf(x.y, y.y, fmaf(x.z, y.z, fmaf(x.w, y.w, ga))));
+                        }
+                    }
+#pragma unroll
+                    for (int o = GL / 2; o > 0; o >>= 1) {
+                        al += __shfl_xor_sync(0xffffffffu, al, o);
+                        be += __shfl_xor_sync(0xffffffffu, be, o);
+                        ga += __shfl_xor_sync(0xffffffffu, ga, o);
+                    }
+                    const float d = be - al, h = ga + ga;
+                    const float r2 = fmaf(d, d, h * h);
+                    const float rinv = jac_rsqrt_refined(r2);
+                    const float y2 = fmaf(0.5f * fabsf(d), rinv, 0.5f);
+                    const float icy = jac_rsqrt_refined(y2);
+                    const float sn_abs = 0.5f * h * rinv * icy;
+                    const float gn = jac_sqrt_approx(al * be);
+                    const bool rot = ok && fabsf(ga) > tol * gn && r2 > 1e-36f && r2 < 1e36f;
+                    if (rot) {
+                        rotated |= fabsf(ga) > kJacobiSmallAngle * gn ? 3 : 1;
+                        const float cs = y2 * icy, sn = d < 0.f ? -sn_abs : sn_abs;
+                        int r = gl * 4;
+                        for (; r + (JG_U - 1) * GL * 4 < ld; r += JG_U * GL * 4) {
+                            float4 x[JG_U], y[JG_U];
+#pragma unroll
+                            for (int u = 0; u < JG_U; ++u) { x[u] = jac_ldcg4(cp + r + u * GL * 4); y[u] = jac_ldcg4(cq + r + u * GL * 4); }
+#pragma unroll
+                            for (int u = 0; u < JG_U; ++u) {
+                                *reinterpret_cast<float4*>(cp + r + u * GL * 4) = jac_rot4(cs, -sn, x[u], y[u]);
+                                *reinterpret_cast<float4*>(cq + r + u * GL * 4) = jac_rot4(sn, cs, x[u], y[u]);
+                            }
+                        }
+                        for (; r < ld; r += GL * 4) {
+                            const float4 x = jac_ldcg4(cp + r), y = jac_ldcg4(cq + r);
+                            *reinterpret_cast<float4*>(cp + r) = jac_rot4(cs, -sn, x, y);
+                            *reinterpret_cast<float4*>(cq + r) = jac_rot4(sn, cs, x, y);
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+            if (!__syncthreads_or(rotated & 2)) { ++sweep; break; }     // see kJacobiSmallAngle
+        }
+    }
+    __syncthreads();
     return sweep;
 }
 

@@ -125,6 +125,7 @@ polar_prep_student_kernel(PolarArgs g) {
         const int j = e % 64, n = (e / 64) % N, d = (e / (64 * N)) * 64 + j;
         store_split2(swh, swl, e, d < D ? sw[n * ldS + d] : 0.f, d + 1 < D ? sw[n * ldS + d + 1] : 0.f);
     }
+    if (g.vt) return;
     // W_0 = s_w^T [Ds][N], tiled [n block][d][64]: pairs of consecutive n; padding columns stored as zeros
     __nv_bfloat16* wh = g.W.hi + prob * g.W.batch_stride;
     __nv_bfloat16* wl = g.W.lo + prob * g.W.batch_stride;
@@ -141,12 +142,14 @@ polar_prep_student_kernel(PolarArgs g) {
 // instead of 151 KB of fp32 -> two CTAs per SM overlap each other's load / compute / store phases) and
 // s_w = sqrt(a) (s - mu) is recomputed where it is consumed; every global access is 16 bytes wide.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kPrepThreads, 2)
+// STAGE = false (tiles that do not fit shared memory, e.g. 576 x 384): the same passes read the tokens straight from
+// global memory (L2-resident: 442 KB per problem).
+template <bool STAGE>
+__global__ void __launch_bounds__(kPrepThreads, STAGE ? 2 : 1)
 polar_prep_student_vec_kernel(PolarArgs g) {
     extern __shared__ __align__(16) uint8_t sm_raw[];
-    const int N = g.Ns, D = g.Ds, pitch = D + 8, oct = D / 8;      // pitch in bf16: rows stay 16-byte aligned
-    __nv_bfloat16* raw = reinterpret_cast<__nv_bfloat16*>(sm_raw);  // [N][pitch]
-    float* a_s = reinterpret_cast<float*>(sm_raw + ((static_cast<size_t>(N) * pitch * 2 + 15) & ~size_t(15)));
+    const int N = g.Ns, D = g.Ds, pitch = STAGE ? D + 8 : D, oct = D / 8;      // pitch in bf16: rows stay 16-byte aligned
+    float* a_s = reinterpret_cast<float*>(sm_raw + (STAGE ? ((static_cast<size_t>(N) * pitch * 2 + 15) & ~size_t(15)) : 0));
     float* q_s = a_s + N;
     float* mu = q_s + N;                                            // [D]
     float* red = mu + D;                                            // 40
@@ -154,14 +157,18 @@ polar_prep_student_vec_kernel(PolarArgs g) {
     const int prob = blockIdx.x;
     const int i = prob / g.B, b = prob % g.B;
     const __nv_bfloat16* S = g.student[i] + static_cast<size_t>(b) * N * D;
+    const __nv_bfloat16* raw = STAGE ? reinterpret_cast<const __nv_bfloat16*>(sm_raw) : S;      // [N][pitch]
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
         const float a = g.a[static_cast<size_t>(prob) * N + n];
         a_s[n] = a;
         q_s[n] = sqrtf(a);
     }
-    for (int t = threadIdx.x; t < N * oct; t += blockDim.x) {
-        const int n = t / oct, o = t - n * oct;
-        *reinterpret_cast<uint4*>(raw + n * pitch + o * 8) = *reinterpret_cast<const uint4*>(S + static_cast<size_t>(n) * D + o * 8);
+    if (STAGE) {
+        __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(sm_raw);
+        for (int t = threadIdx.x; t < N * oct; t += blockDim.x) {
+            const int n = t / oct, o = t - n * oct;
+            *reinterpret_cast<uint4*>(stage + n * pitch + o * 8) = *reinterpret_cast<const uint4*>(S + static_cast<size_t>(n) * D + o * 8);
+        }
     }
     __syncthreads();
     // mu[d] = sum_n a[n] s[n][d]: thread = (octet of d, slice of n)
@@ -238,6 +245,7 @@ polar_prep_student_vec_kernel(PolarArgs g) {
         }
         store_split8(swh, swl, (static_cast<size_t>(cb) * N + n) * 64 + j0, v);
     }
+    if (g.vt) return;
     // W_0 = s_w^T [Ds][N], tiled [n block][d][64], padding columns zero: a thread takes 8 consecutive n of one d; lanes run
     // along d (conflict-free 2-byte shared reads; the 16-byte stores of a warp land 128 B apart and are merged in L2)
     __nv_bfloat16* wh = g.W.hi + prob * g.W.batch_stride;
@@ -430,6 +438,243 @@ polar_finish_kernel(PolarArgs g) {
     }
 }
 
+// ================================================================================================
+// Teacher-token-space form  (D_s > min(N_s, N_t) - 1 with N_t <= N_s: the cross-covariance C = s_w^T t_w has rank
+// N_t - 1 < D_s, e.g. a 7 x 7 CNN grid against a ViT-S student, or ViT-S <- ViT-L at 196 tokens).
+//
+// t_w = F Tbar with F = diag(q)(I - 1 a^T) E  [N_s x N_t]  (E = the 2-tap token resampling, I when N_t == N_s),
+// Tbar the mixed teacher on its OWN token grid.  F 1 = 0, so C = s_w^T F Tbar_c with Tbar_c = (I - 1 1^T / N_t) Tbar.
+// With K_R = Tbar_c Tbar_c^T + c_r 1^ 1^^T = G G^T (Cholesky, N_t x N_t; 1^ = 1 / sqrt(N_t) decouples the common null
+// direction) the rows of Q^T = G^-1 [Tbar_c, sqrt(c_r) 1^] are orthonormal, so
+//     C^+ = X_0^T Q^T,   X_0 = G^T F^T s_w  (N_t x D_s)  plus one decoupled column beta z^ (z^ = G^T 1^ / sqrt(c_r)),
+//     polar(C) = X_inf^T G^-1 Tbar_c,     ||C||_* = <X_inf, X_0>,
+//     d||C||_* / d s_w = F G X_inf,       d L_b / d Tbar = [2 F^T F - 2 G^-T (X_0 X_inf^T) G^-1 (I - 1 1^T / N_t)] Tbar.
+// X_inf = polar factor of X_0^+ by the plain Newton-Schulz iteration on X itself (A = X X^T is symmetric positive
+// semi-definite by construction; the factored form W K W^T of the student-feature form loses definiteness to the
+// rounding of K when K is ill conditioned).  tools/scratch/vt_model.py states this pipeline in fp64 against autograd.
+// ================================================================================================
+constexpr int kVtThreads = 512;
+__global__ void __launch_bounds__(kVtThreads, 1)
+vt_prep_teacher_kernel(PolarArgs g) {
+    extern __shared__ __align__(16) float sm[];
+    const int N = g.Ns, M = g.Nt, ld = (M + 3) & ~3;
+    float* K = sm;                                        // [M][ld] column-major: element (r, c) at K[c * ld + r]
+    float* a_s = K + static_cast<size_t>(ld) * M;         // [N]
+    float* q_s = a_s + N;                                 // [N]
+    float* ebar = q_s + N;                                // [M]   E^T a
+    float* eg = ebar + M;                                 // [M]   ebar^T G
+    float* rowm = eg + M;                                 // [M]
+    float* red = rowm + M;                                // 40
+    __shared__ int s_bad;
+    const int prob = blockIdx.x;
+    const float* Ktt = g.Ktt + static_cast<size_t>(prob) * M * M;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        const float a = g.a[static_cast<size_t>(prob) * N + n];
+        a_s[n] = a;
+        q_s[n] = sqrtf(a);
+    }
+    for (int t = threadIdx.x; t < M * ld; t += blockDim.x) {
+        const int c = t / ld, r = t - c * ld;
+        K[t] = r < M ? 0.5f * (Ktt[static_cast<size_t>(r) * M + c] + Ktt[static_cast<size_t>(c) * M + r]) : 0.f;
+    }
+    if (threadIdx.x < M) ebar[threadIdx.x] = 0.f;
+    if (threadIdx.x == 0) s_bad = 0;
+    __syncthreads();
+    // double centring + the decoupling term: K_R = H K H + (tr(H K H) / M) 1^ 1^^T
+    for (int i = warp; i < M; i += nw) {
+        float sacc = 0.f;
+        for (int j = lane; j < M; j += 32) sacc += K[j * ld + i];
+        sacc = warp_sum(sacc);
+        if (lane == 0) rowm[i] = sacc / static_cast<float>(M);
+    }
+    __syncthreads();
+    float part = 0.f;
+    for (int i = threadIdx.x; i < M; i += blockDim.x) part += rowm[i];
+    const float tot = cta_sum(part, red) / static_cast<float>(M);
+    part = 0.f;
+    for (int i = threadIdx.x; i < M; i += blockDim.x) part += K[i * ld + i] - 2.f * rowm[i] + tot;
+    const float cr = cta_sum(part, red) / static_cast<float>(M);
+    const float shift = tot + cr / static_cast<float>(M);
+    for (int t = threadIdx.x; t < M * ld; t += blockDim.x) {
+        const int c = t / ld, r = t - c * ld;
+        if (r < M) K[t] += shift - rowm[r] - rowm[c];
+    }
+    __syncthreads();
+    float dmax = 0.f;
+    for (int i = threadIdx.x; i < M; i += blockDim.x) dmax = fmaxf(dmax, K[i * ld + i]);
+    for (int o = 16; o > 0; o >>= 1) dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    if (lane == 0) red[warp] = dmax;
+    __syncthreads();
+    dmax = 0.f;
+    for (int wv = 0; wv < nw; ++wv) dmax = fmaxf(dmax, red[wv]);
+    __syncthreads();
+    cta_cholesky_lower(K, ld, M, &s_bad, 1e-6f * dmax);   // K = G (lower), strict upper triangle zeroed
+    // ebar = E^T a
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        int i0, i1; float lam;
+        interp_index(n, M, N, i0, i1, lam);
+        atomicAdd(&ebar[i0], a_s[n] * (1.f - lam));
+        if (lam != 0.f) atomicAdd(&ebar[i1], a_s[n] * lam);
+    }
+    __syncthreads();
+    // eg[m] = sum_m' ebar[m'] G[m'][m];  z^[m] = sum_m' G[m'][m] / sqrt(M c_r)   (column m of G = K[m * ld + .])
+    float* zhat = g.vec + static_cast<size_t>(prob) * 4 * N + 2 * N;
+    for (int m = warp; m < M; m += nw) {
+        float se = 0.f, sz = 0.f;
+        for (int i = lane; i < M; i += 32) { const float gv = K[m * ld + i]; se = fmaf(ebar[i], gv, se); sz += gv; }
+        se = warp_sum(se); sz = warp_sum(sz);
+        if (lane == 0) { eg[m] = se; zhat[m] = sz * rsqrtf(static_cast<float>(M) * cr); }
+    }
+    __syncthreads();
+    // F G [N][M] -> FG (rows N, inner M) and FGt (rows M, inner N), padding columns zero; ktd[n] = |(F G)[n]|^2
+    float* ktd = g.vec + static_cast<size_t>(prob) * 4 * N + N;
+    part = 0.f;
+    for (int n = warp; n < N; n += nw) {
+        int i0, i1; float lam;
+        interp_index(n, M, N, i0, i1, lam);
+        float sacc = 0.f;
+        for (int m = lane; m < M; m += 32) {
+            const float v = q_s[n] * ((1.f - lam) * K[m * ld + i0] + lam * K[m * ld + i1] - eg[m]);
+            sacc = fmaf(v, v, sacc);
+        }
+        sacc = warp_sum(sacc);
+        if (lane == 0) { ktd[n] = sacc; part += sacc; }
+    }
+    const float tr_t = cta_sum(part, red);
+    if (threadIdx.x == 0) g.scal[prob * 4 + 2] = tr_t;
+    {
+        __nv_bfloat16* fh = g.FG.hi + prob * g.FG.batch_stride;
+        __nv_bfloat16* fl = g.FG.lo + prob * g.FG.batch_stride;
+        const int n_cb = (M + 63) / 64;
+        for (int t = threadIdx.x; t < n_cb * N * 8; t += blockDim.x) {
+            const int j0 = (t & 7) * 8, n = (t >> 3) % N, cb = (t >> 3) / N;
+            int i0, i1; float lam;
+            interp_index(n, M, N, i0, i1, lam);
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int m = cb * 64 + j0 + e;
+                v[e] = m < M ? q_s[n] * ((1.f - lam) * K[m * ld + i0] + lam * K[m * ld + i1] - eg[m]) : 0.f;
+            }
+            store_split8(fh, fl, (static_cast<size_t>(cb) * N + n) * 64 + j0, v);
+        }
+        __nv_bfloat16* th = g.FGt.hi + prob * g.FGt.batch_stride;
+        __nv_bfloat16* tl = g.FGt.lo + prob * g.FGt.batch_stride;
+        const int n_nb = (N + 63) / 64;
+        for (int t = threadIdx.x; t < n_nb * 8 * M; t += blockDim.x) {
+            const int m = t % M, j0 = ((t / M) & 7) * 8, nb = t / (8 * M);
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int n = nb * 64 + j0 + e;
+                float x = 0.f;
+                if (n < N) {
+                    int i0, i1; float lam;
+                    interp_index(n, M, N, i0, i1, lam);
+                    x = q_s[n] * ((1.f - lam) * K[m * ld + i0] + lam * K[m * ld + i1] - eg[m]);
+                }
+                v[e] = x;
+            }
+            store_split8(th, tl, (static_cast<size_t>(nb) * M + m) * 64 + j0, v);
+        }
+    }
+    // F^T F = E^T diag(a) E - ebar ebar^T   (banded + rank one; fp32, read by vt_theta_kernel)
+    float* ftf = g.ftf + static_cast<size_t>(prob) * M * M;
+    for (int t = threadIdx.x; t < M * M; t += blockDim.x) ftf[t] = -ebar[t / M] * ebar[t % M];
+    __syncthreads();
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        int i0, i1; float lam;
+        interp_index(n, M, N, i0, i1, lam);
+        const float w0 = 1.f - lam, a = a_s[n];
+        atomicAdd(&ftf[i0 * M + i0], a * w0 * w0);
+        if (lam != 0.f) {
+            atomicAdd(&ftf[i0 * M + i1], a * w0 * lam);
+            atomicAdd(&ftf[i1 * M + i0], a * w0 * lam);
+            atomicAdd(&ftf[i1 * M + i1], a * lam * lam);
+        }
+    }
+    // G^-1 (forward substitution, one thread per column, column-major fp32 in global memory), then its two operand forms
+    float* ginv = g.ginv + static_cast<size_t>(prob) * M * M;
+    cta_lower_inverse(K, ld, M, ginv, M);
+    __threadfence_block();
+    __syncthreads();
+    for (int r = threadIdx.x; r < M; r += blockDim.x) {
+        float sacc = 0.f;
+        for (int c = 0; c <= r; ++c) sacc += ginv[static_cast<size_t>(c) * M + r];
+        rowm[r] = sacc / static_cast<float>(M);
+    }
+    __syncthreads();
+    {
+        __nv_bfloat16* ch = g.GinvC.hi + prob * g.GinvC.batch_stride;
+        __nv_bfloat16* cl = g.GinvC.lo + prob * g.GinvC.batch_stride;
+        __nv_bfloat16* th = g.GinvT.hi + prob * g.GinvT.batch_stride;
+        __nv_bfloat16* tl = g.GinvT.lo + prob * g.GinvT.batch_stride;
+        const int n_cb = (M + 63) / 64;
+        for (int t = threadIdx.x; t < n_cb * M * 8; t += blockDim.x) {
+            const int r = t % M, j0 = ((t / M) & 7) * 8, cb = t / (8 * M);
+            float vc[8], vt[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int c = cb * 64 + j0 + e;
+                // GinvC[r][c] = Ginv(r, c) - rowmean(r);   GinvT[r][c] = Ginv(c, r)
+                vc[e] = c < M ? (c <= r ? ginv[static_cast<size_t>(c) * M + r] : 0.f) - rowm[r] : 0.f;
+                vt[e] = c < M ? (r <= c ? ginv[static_cast<size_t>(r) * M + c] : 0.f) : 0.f;
+            }
+            store_split8(ch, cl, (static_cast<size_t>(cb) * M + r) * 64 + j0, vc);
+            store_split8(th, tl, (static_cast<size_t>(cb) * M + r) * 64 + j0, vt);
+        }
+    }
+}
+
+// ||X_0||_F^2 -> the decoupled augmentation column beta z^ at column Ds16 of X_0 (beta = rms of the other singular values)
+__global__ void __launch_bounds__(256)
+vt_augment_kernel(PolarArgs g) {
+    __shared__ float red[40];
+    const int M = g.Nt, D = g.Ds, N = g.Ns;
+    const int prob = blockIdx.x;
+    __nv_bfloat16* xh = g.X0.hi + prob * g.X0.batch_stride;
+    __nv_bfloat16* xl = g.X0.lo + prob * g.X0.batch_stride;
+    float part = 0.f;
+    const int data_elems = ((D + 63) / 64) * M * 64;              // column blocks the product wrote (padding columns are zero)
+    for (int t = threadIdx.x; t < data_elems / 2; t += blockDim.x) {
+        const float2 h = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(xh)[t]);
+        const float2 l = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(xl)[t]);
+        const float x = h.x + l.x, y = h.y + l.y;
+        part = fmaf(x, x, fmaf(y, y, part));
+    }
+    const float fro2 = cta_sum(part, red);
+    const float beta = sqrtf(fro2 / static_cast<float>(M > 1 ? M - 1 : 1));
+    const float* zhat = g.vec + static_cast<size_t>(prob) * 4 * N + 2 * N;
+    const int d16 = (D + 15) & ~15, dend = (g.Dsp + 63) & ~63;
+    for (int t = threadIdx.x; t < M * (dend - D); t += blockDim.x) {
+        const int m = t % M, c = D + t / M;
+        const float v = c == d16 ? beta * zhat[m] : 0.f;
+        const size_t idx = g.X0.at(m, c);
+        const __nv_bfloat16 h = __float2bfloat16(v);
+        xh[idx] = h;
+        xl[idx] = __float2bfloat16(v - __bfloat162float(h));
+    }
+}
+
+// Theta'' = 2 F^T F - 2 G^-T (X_0 X_inf^T) G^-1 (I - 1 1^T / N_t)  -> row-major split pair [Nt][NtPad]
+__global__ void __launch_bounds__(256)
+vt_theta_kernel(PolarArgs g) {
+    const int M = g.Nt;
+    const size_t prob = blockIdx.y;
+    const float* ftf = g.ftf + prob * M * M;
+    const float* raw = g.thraw + prob * M * M;
+    __nv_bfloat16* oh = g.theta + prob * M * g.NtPad;
+    __nv_bfloat16* ol = g.theta_lo + prob * M * g.NtPad;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < M * M; t += gridDim.x * blockDim.x) {
+        const int i = t / M, j = t - i * M;
+        const float v = 2.f * ftf[t] - 2.f * raw[t];
+        const __nv_bfloat16 h = __float2bfloat16(v);
+        oh[static_cast<size_t>(i) * g.NtPad + j] = h;
+        ol[static_cast<size_t>(i) * g.NtPad + j] = __float2bfloat16(v - __bfloat162float(h));
+    }
+}
+
 }  // namespace
 
 int polar_steps() { return kPolarSteps; }
@@ -455,9 +700,15 @@ cudaError_t launch_polar_procrustes(const PolarArgs& g, cudaStream_t st, int* la
         TimingScope ts(kSlotPolarPrep, st, 2);
         if (D % 8 == 0) {
             const int slices = kPrepThreads / (D / 8);
-            const size_t smem = ((static_cast<size_t>(N) * (D + 8) * 2 + 15) & ~size_t(15)) + (2 * N + D + 40 + static_cast<size_t>(slices) * D) * sizeof(float);
-            PCK(cudaFuncSetAttribute(polar_prep_student_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-            polar_prep_student_vec_kernel<<<nprob, kPrepThreads, smem, st>>>(g);
+            const size_t small = (2 * N + D + 40 + static_cast<size_t>(slices) * D) * sizeof(float);
+            const size_t smem = ((static_cast<size_t>(N) * (D + 8) * 2 + 15) & ~size_t(15)) + small;
+            if (smem <= 227 * 1024) {
+                PCK(cudaFuncSetAttribute(polar_prep_student_vec_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+                polar_prep_student_vec_kernel<true><<<nprob, kPrepThreads, smem, st>>>(g);
+            } else {
+                PCK(cudaFuncSetAttribute(polar_prep_student_vec_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(small)));
+                polar_prep_student_vec_kernel<false><<<nprob, kPrepThreads, small, st>>>(g);
+            }
         } else {
             const size_t smem = (static_cast<size_t>(N) * (D + 1) + 2 * N + D + 64) * sizeof(float);
             PCK(cudaFuncSetAttribute(polar_prep_student_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -557,6 +808,102 @@ cudaError_t launch_polar_procrustes(const PolarArgs& g, cudaStream_t st, int* la
         PCK(polar_gemm(true, SW, Wc, nz, a, st));
         count += 2;
     }
+    {
+        delete gemm_scope; gemm_scope = nullptr;
+        TimingScope tf(kSlotPolarFinish, st, 1);
+        polar_finish_kernel<<<nprob, 256, (2 * N + 64) * sizeof(float), st>>>(g);
+        PCK(cudaGetLastError());
+        count += 1;
+    }
+    if (launches) *launches = count;
+    return cudaSuccess;
+}
+
+cudaError_t launch_polar_procrustes_vt(const PolarArgs& g, cudaStream_t st, int* launches) {
+    const int N = g.Ns, M = g.Nt, D = g.Ds, nprob = g.n_problems;
+    if (M > kVtMaxTokens || M > kVtThreads) return cudaErrorInvalidValue;
+    int count = 0;
+    {
+        TimingScope ts(kSlotPolarPrep, st, 3);
+        if (D % 8 != 0) return cudaErrorInvalidValue;
+        const int slices = kPrepThreads / (D / 8);
+        const size_t small = (2 * N + D + 40 + static_cast<size_t>(slices) * D) * sizeof(float);
+        const size_t smem = ((static_cast<size_t>(N) * (D + 8) * 2 + 15) & ~size_t(15)) + small;
+        if (smem <= 227 * 1024) {
+            PCK(cudaFuncSetAttribute(polar_prep_student_vec_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            polar_prep_student_vec_kernel<true><<<nprob, kPrepThreads, smem, st>>>(g);
+        } else {
+            PCK(cudaFuncSetAttribute(polar_prep_student_vec_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(small)));
+            polar_prep_student_vec_kernel<false><<<nprob, kPrepThreads, small, st>>>(g);
+        }
+        PCK(cudaGetLastError());
+        const int ld = (M + 3) & ~3;
+        const size_t smem_t = (static_cast<size_t>(ld) * M + 2 * N + 3 * M + 64) * sizeof(float);
+        PCK(cudaFuncSetAttribute(vt_prep_teacher_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_t)));
+        vt_prep_teacher_kernel<<<nprob, kVtThreads, smem_t, st>>>(g);
+        PCK(cudaGetLastError());
+        count += 2;
+    }
+    PCK(cudaMemsetAsync(g.fro2, 0, sizeof(float) * nprob, st));
+    TimingScope* gemm_scope = new TimingScope(kSlotPolarGemm, st, 3 * kPolarSteps + 7);
+    struct Del { TimingScope*& p; ~Del() { delete p; } } gemm_del{gemm_scope};
+    PolarGemmArgs a;
+    // X_0 = (F G)^T s_w   [Nt][Ds]  (s_w enters as the MN-major operand), then the augmentation column
+    memset(&a, 0, sizeof a);
+    a.epi = PG_EPI_SPLIT; a.out_hi = g.X0.hi; a.out_lo = g.X0.lo; a.out_stride = g.X0.batch_stride; a.scale_c = 1.f;
+    PCK(polar_gemm(true, g.FGt, g.SW, nprob, a, st));
+    vt_augment_kernel<<<nprob, 256, 0, st>>>(g);
+    PCK(cudaGetLastError());
+    count += 2;
+    SplitMat Xc = g.X0, Xn = g.X1;
+    int dir = 0;
+    for (int k = 0; k < kPolarSteps; ++k) {
+        const float ca = kPolarCoef[k][0], cb = kPolarCoef[k][1], cc = kPolarCoef[k][2];
+        const bool first = k == 0;
+        const float* norm = first ? g.fro2 : nullptr;
+        // A = X X^T   (step 0: trace(A) = ||X_0^+||_F^2)
+        memset(&a, 0, sizeof a);
+        a.epi = PG_EPI_SPLIT; a.out_hi = g.A.hi; a.out_lo = g.A.lo; a.out_stride = g.A.batch_stride; a.scale_c = 1.f;
+        a.a_alias_b = 1;
+        if (first) a.trace = g.fro2;
+        a.reverse = (dir++) & 1;
+        PCK(polar_gemm(false, Xc, Xc, nprob, a, st));
+        // Bm = a I + b (rA) + c (rA)^2
+        memset(&a, 0, sizeof a);
+        a.epi = PG_EPI_SPLIT; a.out_hi = g.Bm.hi; a.out_lo = g.Bm.lo; a.out_stride = g.Bm.batch_stride;
+        a.a_alias_b = 1; a.aux_mode = 1; a.aux_hi = g.A.hi; a.aux_lo = g.A.lo;
+        a.aux_c = cb; a.aux_p = first ? 1.f : 0.f; a.scale_c = cc; a.scale_p = first ? 2.f : 0.f; a.diag_add = ca; a.norm2 = norm;
+        a.reverse = (dir++) & 1;
+        PCK(polar_gemm(false, g.A, g.A, nprob, a, st));
+        // X_next = sqrt(r) Bm X
+        memset(&a, 0, sizeof a);
+        a.epi = PG_EPI_SPLIT; a.out_hi = Xn.hi; a.out_lo = Xn.lo; a.out_stride = Xn.batch_stride;
+        a.scale_c = 1.f; a.scale_p = first ? 0.5f : 0.f; a.norm2 = norm;
+        a.reverse = (dir++) & 1;
+        PCK(polar_gemm(true, g.Bm, Xc, nprob, a, st));
+        Xc = Xn;
+        Xn = (Xc.hi == g.X1.hi) ? g.X2 : g.X1;
+        count += 3;
+    }
+    const int d16 = (D + 15) & ~15;
+    // Gsw = F G X_inf[:, :Ds] = d nuc / d s_w   [Ns][Ds]
+    memset(&a, 0, sizeof a);
+    a.epi = PG_EPI_F32; a.out_f32 = g.Gsw; a.out_f32_stride = static_cast<long long>(N) * D; a.ld_f32 = D; a.n_override = D;
+    PCK(polar_gemm(true, g.FG, Xc, nprob, a, st));
+    // H = X_0 X_inf^T over the student features (the augmentation column left out)
+    memset(&a, 0, sizeof a);
+    a.epi = PG_EPI_SPLIT; a.out_hi = g.Hm.hi; a.out_lo = g.Hm.lo; a.out_stride = g.Hm.batch_stride; a.scale_c = 1.f; a.k_override = d16;
+    PCK(polar_gemm(false, g.X0, Xc, nprob, a, st));
+    // M2 = H G^-1 (I - 1 1^T / Nt),  Theta_raw = G^-T M2
+    memset(&a, 0, sizeof a);
+    a.epi = PG_EPI_SPLIT; a.out_hi = g.M2.hi; a.out_lo = g.M2.lo; a.out_stride = g.M2.batch_stride; a.scale_c = 1.f;
+    PCK(polar_gemm(true, g.Hm, g.GinvC, nprob, a, st));
+    memset(&a, 0, sizeof a);
+    a.epi = PG_EPI_F32; a.out_f32 = g.thraw; a.out_f32_stride = static_cast<long long>(M) * M; a.ld_f32 = M;
+    PCK(polar_gemm(true, g.GinvT, g.M2, nprob, a, st));
+    vt_theta_kernel<<<dim3((M * M + 255) / 256 < 8 ? (M * M + 255) / 256 : 8, nprob), 256, 0, st>>>(g);
+    PCK(cudaGetLastError());
+    count += 5;
     {
         delete gemm_scope; gemm_scope = nullptr;
         TimingScope tf(kSlotPolarFinish, st, 1);

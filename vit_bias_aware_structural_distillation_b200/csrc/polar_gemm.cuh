@@ -8,7 +8,8 @@
 // Global layout of every split matrix is COLUMN-BLOCK TILED: [problem][col / 64][row][col % 64], so that each TMA box
 // (rows x 64 columns) is one contiguous run of HBM (row-major storage with a 400-byte pitch measured 37 % of the
 // copy bandwidth: every 128-byte box row opened its own DRAM page).
-// Work item = (problem, 128-row tile of the output).  One CTA per SM loops over its items; the shared-memory operand
+// Work item = (problem, 128-row tile, column tile of at most 256 columns) of the output - any m_rows, n_cols, K.
+// One CTA per SM loops over its items; the shared-memory operand
 // ring and two TMEM accumulator buffers are carried across items, so the TMA loads and MMAs of item i+1 overlap the
 // epilogue of item i.  Warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue (one TMEM lane quadrant each).
 // Epilogues only store (no global reads on the critical path) except the one-off Frobenius trace of step 0; the split
@@ -37,10 +38,12 @@ struct PolarGemmMaps {
 
 struct PolarGemmArgs {
     int m_rows, n_cols, k_total;     // valid sizes
+    int k_override;                  // > 0: contract over the first k_override columns of A / B only
+    int n_override;                  // > 0: only the first n_override output columns (rows of B / columns of an MN-major B) exist
     int n_mt;                        // 128-row tiles per problem
-    int n_items;                     // batches * n_mt
-    int a_rows_tile[2];              // rows of A loaded for tile 0 / 1 (multiples of 64)
-    int bn_mma;                      // UMMA N (multiple of 16, >= n_cols)
+    int n_nt;                        // column tiles per problem (bn_mma columns each; bn_mma is a multiple of 64 when n_nt > 1)
+    int n_items;                     // batches * n_mt * n_nt
+    int bn_mma;                      // UMMA N = columns per tile (multiple of 16; >= n_cols when n_nt == 1)
     int b_groups;                    // MN-major B: 64-column groups loaded per k-block
     int stages;
     int epi;
@@ -107,6 +110,22 @@ __device__ __forceinline__ void pg_read_split16(const uint8_t* t_hi, const uint8
         x[8 + 2 * i] = u1.x + w1.x; x[8 + 2 * i + 1] = u1.y + w1.y;
     }
 }
+// work item w -> (problem z, row tile mt, column tile nt); the tiles of one problem are consecutive (operands stay in L2)
+struct PgItem { int z, mt, nt; };
+__device__ __forceinline__ PgItem pg_item(const PolarGemmArgs& a, int w) {
+    const int per = a.n_mt * a.n_nt;
+    const int zi = w / per, r = w - zi * per;
+    PgItem it;
+    it.z = a.reverse ? a.n_batches - 1 - zi : zi;
+    it.mt = r / a.n_nt;
+    it.nt = r - it.mt * a.n_nt;
+    return it;
+}
+// rows of A loaded for row tile mt (a multiple of 64, at most 128)
+__device__ __forceinline__ int pg_a_rows(const PolarGemmArgs& a, int mt) {
+    const int left = a.m_rows - mt * 128;
+    return left >= 128 ? 128 : (left + 63) & ~63;
+}
 // KIND specialises the epilogue at compile time (one compact code path per instantiation: with every variant in one
 // body the epilogue was ~3900 SASS instructions of mostly-skipped branches executed by a single warp per scheduler):
 //   0 = SPLIT (scale, diagonal, optional trace of the diagonal)   1 = SPLIT + auxiliary tile   2 = THETA   3 = F32
@@ -153,9 +172,9 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
         if (lane == 0) {
             int it = 0;
             for (int w = blockIdx.x; w < args.n_items; w += gridDim.x) {
-                const int mt = w % args.n_mt;
-                const int z = args.reverse ? args.n_batches - 1 - w / args.n_mt : w / args.n_mt;
-                const int a_rows = args.a_rows_tile[mt];
+                const PgItem itm = pg_item(args, w);
+                const int mt = itm.mt, z = itm.z;
+                const int a_rows = pg_a_rows(args, mt);
                 const uint32_t tx = (args.a_alias_b ? 0 : 2 * a_rows * 128) + 2 * b_bytes;
                 const int item_p = (w - blockIdx.x) / gridDim.x;
                 if (args.dbg_clock && blockIdx.x == 0 && item_p < 16) args.dbg_clock[item_p * 8 + 0] = clock64();
@@ -174,9 +193,9 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
                         uint8_t* dst = st + 2 * kABytes + i * b_bytes;
                         if (B_MN) {
                             for (int g = 0; g < args.b_groups; ++g)
-                                tma_load_4d(dst + g * 8192, &maps.b[i], &full_bar[s], 0, kb * PG_BK, g, z);
+                                tma_load_4d(dst + g * 8192, &maps.b[i], &full_bar[s], 0, kb * PG_BK, itm.nt * args.b_groups + g, z);
                         } else {
-                            tma_load_4d(dst, &maps.b[i], &full_bar[s], 0, 0, kb, z);
+                            tma_load_4d(dst, &maps.b[i], &full_bar[s], 0, itm.nt * args.bn_mma, kb, z);
                         }
                     }
                 }
@@ -190,7 +209,7 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
         for (int w = blockIdx.x; w < args.n_items; w += gridDim.x, ++item) {
             const int acc = item & 1;
             const uint32_t acc_ph = (item >> 1) & 1;
-            const int mt_mma = w % args.n_mt;
+            const int mt_mma = pg_item(args, w).mt;
             if (args.dbg_clock && blockIdx.x == 0 && item < 16 && lane == 0) args.dbg_clock[item * 8 + 2] = clock64();
             mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);           // epilogue has drained this accumulator
             tc_fence_after();
@@ -230,8 +249,10 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
         int item = 0;
         uint32_t aux_phase = 0;
         for (int w = blockIdx.x; w < args.n_items; w += gridDim.x, ++item) {
-            const int mt = w % args.n_mt;
-            const int z = args.reverse ? args.n_batches - 1 - w / args.n_mt : w / args.n_mt;
+            const PgItem itm = pg_item(args, w);
+            const int mt = itm.mt, z = itm.z;
+            const int c0 = itm.nt * args.bn_mma;                              // first output column of this tile
+            const int cb0 = c0 >> 6;                                          // ... as a 64-column block index
             const int acc = item & 1;
             const uint32_t acc_ph = (item >> 1) & 1;
             const bool warp_rows_ok = mt * 128 + q * 32 < args.m_rows;       // uniform: this warp owns at least one valid row
@@ -241,8 +262,8 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
             if (use_aux && lane == 0) {                                    // the whole auxiliary tile of this item, hidden behind the main loop
                 mbar_arrive_expect_tx(&aux_bar[warp - 2], n_cb_aux * 8192);
                 for (int cb = 0; cb < n_cb_aux; ++cb) {
-                    tma_load_4d(aux_base + cb * 8192, &maps.o[2], &aux_bar[warp - 2], 0, mt * 128 + q * 32, cb, z);
-                    tma_load_4d(aux_base + cb * 8192 + 4096, &maps.o[3], &aux_bar[warp - 2], 0, mt * 128 + q * 32, cb, z);
+                    tma_load_4d(aux_base + cb * 8192, &maps.o[2], &aux_bar[warp - 2], 0, mt * 128 + q * 32, cb0 + cb, z);
+                    tma_load_4d(aux_base + cb * 8192 + 4096, &maps.o[3], &aux_bar[warp - 2], 0, mt * 128 + q * 32, cb0 + cb, z);
                 }
             }
             if (args.dbg_clock && blockIdx.x == 0 && item < 16 && warp == 2 && lane == 0) args.dbg_clock[item * 8 + 5] = clock64();
@@ -276,6 +297,7 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
                     aux_phase ^= 1;
                 }
                 for (int cbk = 0; cbk < n_cb; ++cbk) {
+                    if (c0 + cbk * 64 >= ((args.n_cols + 63) & ~63)) break;    // column blocks past the matrix (last tile)
                     const uint8_t* aux_hi_s = aux_base + cbk * 8192;
                     const uint8_t* aux_lo_s = aux_hi_s + 4096;
                     // whole 64-column block in one tcgen05.ld (the last block of a 208-wide tile has 16 columns)
@@ -294,9 +316,9 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
                     if (dbg_here) args.dbg_clock[121] = clock64();
 #pragma unroll
                     for (int jc = 0; jc < 4; ++jc) {
-                        const int c = cbk * 64 + jc * 16;
+                        const int c = c0 + cbk * 64 + jc * 16;                  // global column of v[0]
                         float* v = vb + jc * 16;
-                        if (c < args.bn_mma) {
+                        if (cbk * 64 + jc * 16 < args.bn_mma) {
                             if (KIND == 0 && args.trace && row_ok) {
 #pragma unroll
                                 for (int i = 0; i < 16; ++i) tr_part += (c + i == row) ? v[i] : 0.f;
@@ -335,11 +357,11 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
                     if (dbg_here) args.dbg_clock[123] = clock64();
                     if (lane == 0 && warp_rows_ok) {
                         if constexpr (theta) {                                  // row-major output, columns past n_cols are clipped
-                            tma_store_3d(&maps.o[0], stg_hi, cbk * 64, mt * 128 + q * 32, z);
-                            tma_store_3d(&maps.o[1], stg_lo, cbk * 64, mt * 128 + q * 32, z);
+                            tma_store_3d(&maps.o[0], stg_hi, c0 + cbk * 64, mt * 128 + q * 32, z);
+                            tma_store_3d(&maps.o[1], stg_lo, c0 + cbk * 64, mt * 128 + q * 32, z);
                         } else {
-                            tma_store_4d(&maps.o[0], stg_hi, 0, mt * 128 + q * 32, cbk, z);
-                            tma_store_4d(&maps.o[1], stg_lo, 0, mt * 128 + q * 32, cbk, z);
+                            tma_store_4d(&maps.o[0], stg_hi, 0, mt * 128 + q * 32, cb0 + cbk, z);
+                            tma_store_4d(&maps.o[1], stg_lo, 0, mt * 128 + q * 32, cb0 + cbk, z);
                         }
                         tma_store_commit();
                         if (dbg_here) args.dbg_clock[124] = clock64();
@@ -349,9 +371,10 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
                     __syncwarp();
                 }
             } else {
-                for (int c = 0; c < args.bn_mma; c += 16) {
+                for (int cl = 0; cl < args.bn_mma; cl += 16) {
                     float v[16];
-                    tmem_ld16(t_addr + c, v);
+                    tmem_ld16(t_addr + cl, v);
+                    const int c = c0 + cl;
                     if (!row_ok || c >= args.n_cols) continue;
                     const int nv = min(16, args.n_cols - c);
                     if (args.epi == PG_EPI_F32) {

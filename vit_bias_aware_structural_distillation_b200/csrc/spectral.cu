@@ -100,14 +100,27 @@ __device__ __forceinline__ void pooled_load_gram(const float* __restrict__ G, co
 
 constexpr int kPooledThreads = 256;        // 32 eight-lane groups per CTA x 4 CTAs: n <= 256; 255 registers per thread, no spills
 constexpr int kPooledCluster = 4;           // 28 problems x 4 = 112 of the 148 SMs
-__global__ void __launch_bounds__(kPooledThreads, 1)
+constexpr int kPooledLargeThreads = 768;
+// global-memory Jacobi on one CTA: 4-lane groups when that puts every pair of a step in flight at once
+__device__ __forceinline__ int run_jacobi_global(float* A, int ld, int n) {
+    const int half = (n + 1) / 2;
+    if (half > static_cast<int>(blockDim.x) / 8 && half <= static_cast<int>(blockDim.x) / 4)
+        return jacobi_orthogonalize_global<4>(A, ld, n, kJacobiTol, kJacobiMaxSweeps);
+    return jacobi_orthogonalize_global<8>(A, ld, n, kJacobiTol, kJacobiMaxSweeps);
+}
+// LARGE = true (n > 224: the matrix no longer fits one SM's shared memory): one plain CTA of 768 threads per problem,
+// the matrix in `scratch` (global memory, L2-resident), Jacobi by jacobi_orthogonalize_global; every other phase is
+// the same code on a global pointer.  The Cholesky preconditioner needs one thread per row (n <= 768); larger
+// problems (marchenko_pastur_rank on unprojected teacher features) run Jacobi on the Gram itself.
+template <bool LARGE>
+__global__ void __launch_bounds__(LARGE ? kPooledLargeThreads : kPooledThreads, 1)
 pooled_eig_kernel(const float* __restrict__ stats, int n, int Lt, int P, float M_teacher, float M_student,
                   int* __restrict__ ranks, float* __restrict__ evals, float* __restrict__ evecs_km,
-                  float* __restrict__ evecs_cm, int* __restrict__ sweeps_out) {
+                  float* __restrict__ evecs_cm, int* __restrict__ sweeps_out, float* __restrict__ scratch) {
     extern __shared__ float sm[];
     const int ld = jacobi_ld(n);
-    float* A = sm;
-    float* vals = A + static_cast<size_t>(ld) * n;
+    float* A = LARGE ? scratch + static_cast<size_t>(blockIdx.x) * ld * n : sm;
+    float* vals = LARGE ? sm : A + static_cast<size_t>(ld) * n;
     float* csum = vals + n;
     int* order = reinterpret_cast<int*>(csum + n);
     float* inbox = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(order + n + 64) + 15) & ~uintptr_t(15));   // one column (Jacobi across CTAs)
@@ -117,8 +130,8 @@ pooled_eig_kernel(const float* __restrict__ stats, int n, int Lt, int P, float M
     __shared__ int s_bad;
 
     const long long t_begin = clock64();
-    const int crank = static_cast<int>(cooperative_groups::this_cluster().block_rank());
-    const int p = blockIdx.x / static_cast<int>(cooperative_groups::this_cluster().num_blocks());
+    const int crank = LARGE ? 0 : static_cast<int>(cooperative_groups::this_cluster().block_rank());
+    const int p = LARGE ? blockIdx.x : blockIdx.x / static_cast<int>(cooperative_groups::this_cluster().num_blocks());
     const bool mp_mode = p < Lt;
     const int gram_idx = mp_mode ? p : (p - Lt);                  // index into stats (teacher 0..Lt-1, student Lt..)
     const float Mrows = gram_idx < Lt ? M_teacher : M_student;
@@ -146,22 +159,27 @@ pooled_eig_kernel(const float* __restrict__ stats, int n, int Lt, int P, float M
     dmax = 0.f;
     for (int wv = 0; wv < (blockDim.x >> 5); ++wv) dmax = fmaxf(dmax, vals[wv]);
     __syncthreads();
-    cta_cholesky_lower(A, ld, n, &s_bad, 1e-6f * dmax);       // pivots below 1e-6 of the largest diagonal: not trusted in fp32
-    use_chol = s_bad == 0;
-    if (!use_chol) {                       // rebuild G from the statistics
+    const bool chol_fits = n <= static_cast<int>(blockDim.x);        // one matrix row per thread
+    if (chol_fits) cta_cholesky_lower(A, ld, n, &s_bad, 1e-6f * dmax);       // pivots below 1e-6 of the largest diagonal: not trusted in fp32
+    use_chol = chol_fits && s_bad == 0;
+    if (chol_fits && !use_chol) {          // rebuild G from the statistics
         pooled_load_gram(G, csum, n, ld, invM, mp_mode, A);
     }
     __syncthreads();
     }   // crank == 0
     const long long t_pre = clock64();
-    jac_cluster_sync();                     // the matrix is ready in rank 0's shared memory
     int nsweeps = 0;
-    const int n_cluster = static_cast<int>(cooperative_groups::this_cluster().num_blocks());
-    const int groups_per_cta = ((n + 1) / 2 + n_cluster - 1) / n_cluster;
-    const bool cluster_ok = groups_per_cta * JAC_GROUP <= static_cast<int>(blockDim.x) &&
-                            run_jacobi_oddeven_cluster(A, ld, n, inbox, s_bars, s_flags, &nsweeps);      // uniform over the cluster
-    if (crank != 0) return;                 // (the Jacobi routine ends with a cluster barrier: nobody touches this CTA again)
-    if (!cluster_ok) nsweeps = run_jacobi(A, ld, n);
+    if constexpr (LARGE) {
+        nsweeps = run_jacobi_global(A, ld, n);
+    } else {
+        jac_cluster_sync();                     // the matrix is ready in rank 0's shared memory
+        const int n_cluster = static_cast<int>(cooperative_groups::this_cluster().num_blocks());
+        const int groups_per_cta = ((n + 1) / 2 + n_cluster - 1) / n_cluster;
+        const bool cluster_ok = groups_per_cta * JAC_GROUP <= static_cast<int>(blockDim.x) &&
+                                run_jacobi_oddeven_cluster(A, ld, n, inbox, s_bars, s_flags, &nsweeps);      // uniform over the cluster
+        if (crank != 0) return;                 // (the Jacobi routine ends with a cluster barrier: nobody touches this CTA again)
+        if (!cluster_ok) nsweeps = run_jacobi(A, ld, n);
+    }
     const long long t_jac = clock64();
     column_norms(A, ld, n, n, vals);        // sigma_i (Cholesky route) or lambda_i (fallback)
     __syncthreads();
@@ -218,6 +236,8 @@ pooled_eig_kernel(const float* __restrict__ stats, int n, int Lt, int P, float M
 //   A = V_s[:, :k]^T (P_s^T U_t)   (k x k);  cos = svdvals(A) via Jacobi on A^T A;
 //   d2 = sum sw theta^2 / sum sw;  Gamma_sym = d(d2)/dG_s + transpose   (n x n, saved for backward)
 // ------------------------------------------------------------------------------------------------
+// LARGE = true (n > 224): the k x k Jacobi matrix lives in the spare n x n slot of the scratch area (global memory).
+template <bool LARGE>
 __global__ void __launch_bounds__(kSpectralThreads, 1)
 angles_kernel(int n, int Lt, int P, const int* __restrict__ ranks, const float* __restrict__ evals,
               const float* __restrict__ evecs_km, const float* __restrict__ evecs_cm, const float* __restrict__ proj_s,
@@ -227,8 +247,9 @@ angles_kernel(int n, int Lt, int P, const int* __restrict__ ranks, const float* 
     const int j = blockIdx.x, i = blockIdx.y;
     const int k = ranks[j];
     const int ld = jacobi_ld(max(k, 1));
-    float* J = sm;                                               // k x k Jacobi matrix (ld x k)
-    float* vals = J + static_cast<size_t>(jacobi_ld(n - 1)) * (n - 1);
+    float* J = LARGE ? scratch_all + (static_cast<size_t>(blockIdx.y) * Lt + blockIdx.x) * (8 * static_cast<size_t>(n) * n) + 7 * static_cast<size_t>(n) * n
+                     : sm;                                       // k x k Jacobi matrix (ld x k)
+    float* vals = LARGE ? sm : J + static_cast<size_t>(jacobi_ld(n - 1)) * (n - 1);
     float* coef = vals + n;
     float* red = coef + n;                                       // 33 floats
     int* order = reinterpret_cast<int*>(red + 40);
@@ -281,7 +302,12 @@ angles_kernel(int n, int Lt, int P, const int* __restrict__ ranks, const float* 
     // odd-even ordering with register-resident columns (a "cluster" of this one CTA): half the shared-memory round trips
     // and barriers of the round-robin version per rotation; k x k with k ~ 15-40 is a pure latency chain
     int nsw = 0;
-    if (!run_jacobi_oddeven_cluster(J, ld, k, inbox, s_bars, s_flags, &nsw)) run_jacobi(J, ld, k);
+    if constexpr (LARGE) {
+        __threadfence_block();
+        nsw = run_jacobi_global(J, ld, k);
+    } else {
+        if (!run_jacobi_oddeven_cluster(J, ld, k, inbox, s_bars, s_flags, &nsw)) run_jacobi(J, ld, k);
+    }
     column_norms(J, ld, k, k, vals);          // vals = sigma
     __syncthreads();
     rank_descending(vals, k, order);
@@ -419,13 +445,23 @@ selector_bwd_kernel(int n, int Lt, int P, const float* __restrict__ gw_raw, cons
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
-static size_t pooled_smem(int n) { return (static_cast<size_t>(jacobi_ld(n)) * n + 3 * n + 64 + jacobi_ld(n) + 8) * sizeof(float); }
-static size_t angles_smem(int n) { return (static_cast<size_t>(jacobi_ld(n - 1)) * (n - 1) + 3 * n + 128 + n + 16 + jacobi_ld(n)) * sizeof(float); }
+static size_t pooled_smem(int n, bool large) { return ((large ? 0 : static_cast<size_t>(jacobi_ld(n)) * n) + 3 * n + 64 + jacobi_ld(n) + 8) * sizeof(float); }
+static size_t angles_smem(int n, bool large) { return ((large ? 0 : static_cast<size_t>(jacobi_ld(n - 1)) * (n - 1)) + 3 * n + 128 + n + 16 + jacobi_ld(n)) * sizeof(float); }
+bool spectral_large(int n) { return n > kSpectralSmemMax; }
+size_t pooled_eig_scratch_floats(int n, int problems) { return spectral_large(n) ? static_cast<size_t>(problems) * jacobi_ld(n) * n : 0; }
 
 cudaError_t launch_pooled_eig(const float* stats, int n, int Lt, int P, float Mt, float Ms, int* ranks, float* evals,
-                              float* evecs_km, float* evecs_cm, int* sweeps, cudaStream_t st) {
-    const size_t smem = pooled_smem(n);
-    cudaError_t e = cudaFuncSetAttribute(pooled_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+                              float* evecs_km, float* evecs_cm, int* sweeps, float* scratch, cudaStream_t st) {
+    const bool large = spectral_large(n);
+    const size_t smem = pooled_smem(n, large);
+    if (large) {
+        if (!scratch) return cudaErrorInvalidValue;
+        cudaError_t e = cudaFuncSetAttribute(pooled_eig_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+        pooled_eig_kernel<true><<<2 * Lt + P, kPooledLargeThreads, smem, st>>>(stats, n, Lt, P, Mt, Ms, ranks, evals, evecs_km, evecs_cm, sweeps, scratch);
+        return cudaGetLastError();
+    }
+    cudaError_t e = cudaFuncSetAttribute(pooled_eig_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
@@ -444,16 +480,19 @@ cudaError_t launch_pooled_eig(const float* stats, int n, int Lt, int P, float Mt
     attr.val.clusterDim.x = cluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, pooled_eig_kernel, stats, n, Lt, P, Mt, Ms, ranks, evals, evecs_km, evecs_cm, sweeps);
+    return cudaLaunchKernelEx(&cfg, pooled_eig_kernel<false>, stats, n, Lt, P, Mt, Ms, ranks, evals, evecs_km, evecs_cm, sweeps, scratch);
 }
 
 cudaError_t launch_angles(int n, int Lt, int P, const int* ranks, const float* evals, const float* evecs_km,
                           const float* evecs_cm, const float* proj_s, float* scratch, float* d2, float* gamma,
                           float* cos_out, const float* log_temp, float* w, cudaStream_t st) {
-    const size_t smem = angles_smem(n);
-    cudaError_t e = cudaFuncSetAttribute(angles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    const bool large = spectral_large(n);
+    const size_t smem = angles_smem(n, large);
+    cudaError_t e = large ? cudaFuncSetAttribute(angles_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))
+                          : cudaFuncSetAttribute(angles_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    angles_kernel<<<dim3(Lt, P), kSpectralThreads, smem, st>>>(n, Lt, P, ranks, evals, evecs_km, evecs_cm, proj_s, scratch, d2, gamma, cos_out);
+    if (large) angles_kernel<true><<<dim3(Lt, P), kSpectralThreads, smem, st>>>(n, Lt, P, ranks, evals, evecs_km, evecs_cm, proj_s, scratch, d2, gamma, cos_out);
+    else angles_kernel<false><<<dim3(Lt, P), kSpectralThreads, smem, st>>>(n, Lt, P, ranks, evals, evecs_km, evecs_cm, proj_s, scratch, d2, gamma, cos_out);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     mix_weights_kernel<<<P, 32, 0, st>>>(d2, log_temp, Lt, P, w);

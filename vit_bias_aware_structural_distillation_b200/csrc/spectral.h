@@ -12,8 +12,11 @@ constexpr int kMaxPoints = 8;         // extraction points P
 constexpr int kMaxLayers = 64;        // teacher layers Lt
 
 
+constexpr int kSpectralSmemMax = 224;  // largest symmetric problem whose matrix fits one SM's shared memory
+bool spectral_large(int n);            // n > kSpectralSmemMax: matrices in global scratch (pooled_eig_scratch_floats)
+size_t pooled_eig_scratch_floats(int n, int problems);
 cudaError_t launch_pooled_eig(const float* stats, int n, int Lt, int P, float Mt, float Ms, int* ranks, float* evals,
-                              float* evecs_km, float* evecs_cm, int* sweeps, cudaStream_t st);
+                              float* evecs_km, float* evecs_cm, int* sweeps, float* scratch, cudaStream_t st);
 cudaError_t launch_angles(int n, int Lt, int P, const int* ranks, const float* evals, const float* evecs_km,
                           const float* evecs_cm, const float* proj_s, float* scratch, float* d2, float* gamma,
                           float* cos_out, const float* log_temp, float* w, cudaStream_t st);
@@ -21,6 +24,19 @@ cudaError_t launch_selector_bwd(int n, int Lt, int P, const float* gw_raw, const
                                 const float* w, const float* d2, const float* log_temp, const float* gamma,
                                 const float* stats, float Ms, __nv_bfloat16* gam_hi, __nv_bfloat16* gam_lo, float* corr,
                                 float* grad_log_temp, cudaStream_t st);
+
+// linear resampling index along the token axis (align_corners = False), combined.py:12-14
+#ifdef __CUDACC__
+__device__ __forceinline__ void interp_index(int n, int n_in, int n_out, int& i0, int& i1, float& lam) {
+    if (n_in == n_out) { i0 = n; i1 = n; lam = 0.f; return; }
+    const float scale = static_cast<float>(n_in) / static_cast<float>(n_out);
+    float x = scale * (static_cast<float>(n) + 0.5f) - 0.5f;
+    x = fmaxf(x, 0.f);
+    i0 = min(static_cast<int>(x), n_in - 1);
+    i1 = min(i0 + 1, n_in - 1);
+    lam = x - static_cast<float>(i0);
+}
+#endif
 
 // ---- streaming kernels (stream_ops.cu)
 struct PtrTable {                         // small by-value pointer tables for per-layer tensors
@@ -41,9 +57,11 @@ cudaError_t launch_importance_mix(const float* rows, const float* w, int Lt, int
                                   float* ssum, cudaStream_t st);
 cudaError_t launch_mix_teacher(const PtrTable& teacher, const float* w, int Lt, int P, int B, int Nt, int Ns, int Dt,
                                __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st);
+// Dtm is [P][B][Nd][Dt] with Nd = Ns (gradient w.r.t. the token-aligned mixed teacher) or, with dtm_unaligned, Nd = Nt
+// (gradient w.r.t. the mixed teacher on its own token grid: no resampling in the dots)
 cudaError_t launch_wgrad_dots(const PtrTable& teacher, const __nv_bfloat16* Dtm, const float* gwt, const float* rows,
                               int Lt, int P, int B, int Nt, int Ns, int Dt, float* gw /*[P][Lt], pre-zeroed*/,
-                              cudaStream_t st);
+                              cudaStream_t st, bool dtm_unaligned = false);
 cudaError_t launch_cls_attention_rows(const void* q, const void* k, int is_bf16, int B, int H, int S, int dh,
                                       const long long* q_strides /*[b,h]*/, const long long* k_strides /*[b,h,s]*/, float scale,
                                       float* out /*[B,H,S]*/, cudaStream_t st);
@@ -112,6 +130,17 @@ cudaError_t polar_gemm(bool b_mn, const SplitMat& A, const SplitMat& B, int batc
 struct PolarArgs {
     int Ns, Ds, B, P, NsPad;
     int n_problems;                       // P * B
+    // teacher-token-space form (launch_polar_procrustes_vt): D_s > min(N_s, N_t) - 1, N_t <= N_s
+    int vt;                               // 1: this form is running (prep_student skips W_0)
+    int Nt, NtPad;                        // unaligned teacher tokens; row pitch of theta in this form
+    int Dsp;                              // feature columns of X: D_s rounded up to 16, + 8 (the decoupled augmentation column sits at Ds16)
+    SplitMat FG, FGt;                     // F G [Ns][Nt] and its transpose [Nt][Ns]   (F = diag(q)(I - 1 a^T)E, G G^T = K_R)
+    SplitMat GinvC, GinvT;                // G^-1 (I - 1 1^T / Nt) [Nt][Nt] and G^-T [Nt][Nt]
+    SplitMat X0, X1, X2;                  // [Nt][Dsp]: whitened cross-covariance and the two iterates
+    SplitMat Hm, M2;                      // [Nt][Nt]
+    float* ginv;                          // [P*B][Nt*Nt] fp32 scratch (column-major inverse of the Cholesky factor)
+    float* thraw;                         // [P*B][Nt][Nt]
+    float* ftf;                           // [P*B][Nt][Nt]   F^T F
     const __nv_bfloat16* student[kMaxPoints];   // [B][Ns][Ds] dense bf16
     const float* Ktt;                     // [P*B][Ns][Ns]   uncentred token Gram of the mixed teacher
     const float* a;                       // [P*B][Ns]       normalised importance
@@ -131,6 +160,8 @@ struct PolarArgs {
     float* dbg;                           // [P*B][5]
 };
 cudaError_t launch_polar_procrustes(const PolarArgs& args, cudaStream_t st, int* launches);
+cudaError_t launch_polar_procrustes_vt(const PolarArgs& args, cudaStream_t st, int* launches);
+constexpr int kVtMaxTokens = 224;         // teacher tokens of the token-space form (Cholesky factor held in shared memory)
 int polar_steps();                        // Newton-Schulz steps (the final iterate lives in W2 when odd, W when even)
 
 }  // namespace basd

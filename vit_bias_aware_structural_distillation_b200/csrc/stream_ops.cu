@@ -28,17 +28,6 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
-// linear resampling index along the token axis (align_corners = False), combined.py:12-14
-__device__ __forceinline__ void interp_index(int n, int n_in, int n_out, int& i0, int& i1, float& lam) {
-    if (n_in == n_out) { i0 = n; i1 = n; lam = 0.f; return; }
-    const float scale = static_cast<float>(n_in) / static_cast<float>(n_out);
-    float x = scale * (static_cast<float>(n) + 0.5f) - 0.5f;
-    x = fmaxf(x, 0.f);
-    i0 = min(static_cast<int>(x), n_in - 1);
-    i1 = min(i0 + 1, n_in - 1);
-    lam = x - static_cast<float>(i0);
-}
-
 // ---------------------------------------------------------------------------------------------- importance rows
 template <typename T>
 __device__ __forceinline__ float ld_as_float(const T* p);
@@ -456,11 +445,11 @@ __global__ void wgrad_importance_kernel(const float* __restrict__ gwt, const flo
     if (threadIdx.x == 0) atomicAdd(&gw[i * Lt + j], tot);
 }
 cudaError_t launch_wgrad_dots(const PtrTable& teacher, const __nv_bfloat16* Dtm, const float* gwt, const float* rows, int Lt, int P,
-                              int B, int Nt, int Ns, int Dt, float* gw, cudaStream_t st) {
+                              int B, int Nt, int Ns, int Dt, float* gw, cudaStream_t st, bool dtm_unaligned) {
     if (Dt % 8 != 0 || static_cast<unsigned long long>(B) * Ns * (Dt / 8) >= (1ull << 32)) return cudaErrorInvalidValue;
     const int ny = ((P + WG_PC - 1) / WG_PC) * ((Lt + WG_JC - 1) / WG_JC);
-    if (Nt == Ns)
-        wgrad_dots_kernel<false><<<dim3(148 * 4, ny), 256, 0, st>>>(teacher, Dtm, Lt, P, B, Nt, Ns, Dt, gw);
+    if (Nt == Ns || dtm_unaligned)
+        wgrad_dots_kernel<false><<<dim3(148 * 4, ny), 256, 0, st>>>(teacher, Dtm, Lt, P, B, Nt, Nt, Dt, gw);
     else
         wgrad_dots_kernel<true><<<dim3(148 * 4, ny), 256, 0, st>>>(teacher, Dtm, Lt, P, B, Nt, Ns, Dt, gw);
     cudaError_t e = cudaGetLastError();
