@@ -304,13 +304,14 @@ def test_cfg345_reduced_batch_against_reference_golden(lib, cuda_dev, name):
     assert out["ranks"] == g["ranks"]
     assert abs(out["loss"].item() - g["loss"].item()) <= TOL_LOSS * abs(g["loss"].item())
     gt, rt = out["grad_log_temperatures"], g["grad_log_temperatures"]
-    assert ((gt - rt).abs() <= TOL_TGRAD * rt.abs() + 1e-7).all(), f"temperature grads {gt.tolist()} vs {rt.tolist()}"
+    # (single-layer teacher: w == 1 and the reference's temperature gradient is exactly 0; an fma leaves ~1e-7 of rounding here)
+    assert ((gt - rt).abs() <= TOL_TGRAD * rt.abs() + (1e-6 if w.Lt == 1 else 1e-7)).all(), f"temperature grads {gt.tolist()} vs {rt.tolist()}"
     for l in g["token_layers"]:
         assert abs(out["grad_student"][l].norm() - g["grad_student_norm"][l]) <= TOL_SGRAD * g["grad_student_norm"][l]
         assert rel(out["grad_student"][l].flatten()[::997], g["grad_student_sub"][l]) < TOL_SGRAD
         pr = torch.stack([(out["grad_student"][l] * p).sum() for p in _probes(out["grad_student"][l].shape)])
         assert (pr - g["grad_student_probe"][l]).abs().max() <= TOL_SGRAD * g["grad_student_norm"][l] * math.sqrt(out["grad_student"][l].numel()) * 0.05
-    assert_parity(out, oracle_case(m, inp, w), w)
+    assert_parity(out, oracle_case(m, inp, w), w, tgrad_floor=1e-6 if w.Lt == 1 else 1e-7)
 
 
 # ------------------------------------------------------------------------------------------------ properties

@@ -274,9 +274,13 @@ __device__ int jacobi_orthogonalize(float* __restrict__ A, int ld, int n_cols, f
 }
 
 
-template <int CHUNKS>
+// COMPACT = false: the matrix is in the shared memory of cluster rank 0 at `A` and every CTA uses its own copy of that
+//   region as mailboxes (slot of group g = column 2g).  COMPACT = true: the matrix is in GLOBAL memory at `A` (problems
+//   that do not fit one SM: n up to 384 with 12 chunks) and `mail` is this CTA's shared mailbox area of gpc x ld floats
+//   (slot of a group = its index inside the CTA).
+template <int CHUNKS, bool COMPACT = false>
 __device__ int jacobi_orthogonalize_oddeven_cluster(float* __restrict__ A, int ld, int n_cols, float tol, int max_sweeps, float* inbox,
-                                                    uint64_t* bars, int* flags) {
+                                                    uint64_t* bars, int* flags, float* mail = nullptr) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     const int C = static_cast<int>(cluster.num_blocks()), crank = static_cast<int>(cluster.block_rank());
@@ -300,14 +304,15 @@ __device__ int jacobi_orthogonalize_oddeven_cluster(float* __restrict__ A, int l
         mbar_init(bar_back, 1);
         fence_mbar_init();
     }
-    float* A0 = cluster.map_shared_rank(A, 0);                                           // the matrix itself
-    const uint32_t a_s = smem_u32(A);
-    const uint32_t colP = a_s + static_cast<uint32_t>(active ? 2 * g : 0) * ld * 4;      // own mailbox = own even column slot
-    const uint32_t colN = next_remote ? smem_u32(inbox) : a_s + static_cast<uint32_t>(next_local ? 2 * g + 2 : 0) * ld * 4;
+    float* A0 = COMPACT ? A : cluster.map_shared_rank(A, 0);                             // the matrix itself
+    const uint32_t a_s = smem_u32(COMPACT ? mail : A);
+    const int slotP = COMPACT ? gloc : 2 * g, slotN = COMPACT ? gloc + 1 : 2 * g + 2, slotR = COMPACT ? 0 : 2 * g + 2;
+    const uint32_t colP = a_s + static_cast<uint32_t>(active ? slotP : 0) * ld * 4;      // own mailbox = own even column slot
+    const uint32_t colN = next_remote ? smem_u32(inbox) : a_s + static_cast<uint32_t>(next_local ? slotN : 0) * ld * 4;
     // addresses in the shared::cluster window of the neighbouring CTAs
     const uint32_t r_inbox = jac_mapa(smem_u32(inbox), prev_remote ? crank - 1 : crank);
     const uint32_t r_bar_in = jac_mapa(smem_u32(bar_in), prev_remote ? crank - 1 : crank);
-    const uint32_t r_mail = jac_mapa(a_s + static_cast<uint32_t>(next_remote ? 2 * g + 2 : 0) * ld * 4, next_remote ? crank + 1 : crank);
+    const uint32_t r_mail = jac_mapa(a_s + static_cast<uint32_t>(next_remote ? slotR : 0) * ld * 4, next_remote ? crank + 1 : crank);
     const uint32_t r_bar_back = jac_mapa(smem_u32(bar_back), next_remote ? crank + 1 : crank);
     const uint32_t col_bytes = static_cast<uint32_t>(ld) * 4u;
     ulonglong2 P[CHUNKS], Q[CHUNKS];

@@ -116,7 +116,10 @@ template <bool LARGE>
 __global__ void __launch_bounds__(LARGE ? kPooledLargeThreads : kPooledThreads, 1)
 pooled_eig_kernel(const float* __restrict__ stats, int n, int Lt, int P, float M_teacher, float M_student,
                   int* __restrict__ ranks, float* __restrict__ evals, float* __restrict__ evecs_km,
-                  float* __restrict__ evecs_cm, int* __restrict__ sweeps_out, float* __restrict__ scratch) {
+                  float* __restrict__ evecs_cm, int* __restrict__ sweeps_out, float* __restrict__ scratch, int phase,
+                  int* __restrict__ chol_flags) {
+    // phase (LARGE only): 1 = everything in this launch; 0 = up to the Cholesky factor (the Jacobi sweeps then run in
+    // jacobi_cluster_global_kernel over a cluster per problem); 2 = from the rotated columns on
     extern __shared__ float sm[];
     const int ld = jacobi_ld(n);
     float* A = LARGE ? scratch + static_cast<size_t>(blockIdx.x) * ld * n : sm;
@@ -139,6 +142,11 @@ pooled_eig_kernel(const float* __restrict__ stats, int n, int Lt, int P, float M
     const float* cs = G + n * n;
     const float invM = 1.f / Mrows;
     bool use_chol = false;
+    if (LARGE && phase == 2) {
+        use_chol = chol_flags[blockIdx.x] != 0;
+        if (threadIdx.x == 0) s_count = 0;
+        __syncthreads();
+    } else
     if (crank == 0) {
     for (int i = threadIdx.x; i < n; i += blockDim.x) csum[i] = cs[i];
     if (threadIdx.x == 0) s_count = 0;
@@ -170,7 +178,11 @@ pooled_eig_kernel(const float* __restrict__ stats, int n, int Lt, int P, float M
     const long long t_pre = clock64();
     int nsweeps = 0;
     if constexpr (LARGE) {
-        nsweeps = run_jacobi_global(A, ld, n);
+        if (phase == 0) {
+            if (threadIdx.x == 0) chol_flags[blockIdx.x] = use_chol ? 1 : 0;
+            return;
+        }
+        if (phase == 1) nsweeps = run_jacobi_global(A, ld, n);
     } else {
         jac_cluster_sync();                     // the matrix is ready in rank 0's shared memory
         const int n_cluster = static_cast<int>(cooperative_groups::this_cluster().num_blocks());
@@ -188,7 +200,7 @@ pooled_eig_kernel(const float* __restrict__ stats, int n, int Lt, int P, float M
     __syncthreads();
     rank_descending(vals, n, order);
     __syncthreads();
-    if (threadIdx.x == 0 && sweeps_out) sweeps_out[p] = nsweeps;
+    if (threadIdx.x == 0 && sweeps_out && !(LARGE && phase == 2)) sweeps_out[p] = nsweeps;
 
     if (mp_mode) {
         // M < D (layer_selector.py:14-15): the reference takes the M eigenvalues of F F^T / M - the top M of the D x D
@@ -229,6 +241,27 @@ pooled_eig_kernel(const float* __restrict__ stats, int n, int Lt, int P, float M
             vc[c * n + e] = v;
         }
     }
+}
+
+// Jacobi sweeps of the LARGE path for n <= 384: a cluster of CTAs per problem, columns resident in registers (up to 12
+// chunks of 32 rows), the matrix in global memory, mailboxes in shared memory (jacobi.cuh, COMPACT).  One CTA streaming a
+// 384 x 384 matrix through its L2 port three times per Jacobi step took 70 ms for the 28 problems of cfg5.
+template <int CHUNKS>
+__global__ void __launch_bounds__(kPooledThreads, 1)
+jacobi_cluster_global_kernel(float* __restrict__ scratch, int n, int* __restrict__ sweeps_out) {
+    extern __shared__ __align__(16) float jsm[];
+    float* sm = jsm;
+    __shared__ int s_flags[16];
+    __shared__ __align__(8) uint64_t s_bars[2];
+    const int ld = jacobi_ld(n);
+    const int C = static_cast<int>(cooperative_groups::this_cluster().num_blocks());
+    const int p = blockIdx.x / C;
+    const int gpc = ((n + 1) / 2 + C - 1) / C;
+    float* mail = sm;                                   // [gpc][ld]
+    float* inbox = sm + static_cast<size_t>(gpc) * ld;  // [ld]
+    float* A = scratch + static_cast<size_t>(p) * ld * n;
+    const int nsw = jacobi_orthogonalize_oddeven_cluster<CHUNKS, true>(A, ld, n, kJacobiTol, kJacobiMaxSweeps, inbox, s_bars, s_flags, mail);
+    if (cooperative_groups::this_cluster().block_rank() == 0 && threadIdx.x == 0 && sweeps_out) sweeps_out[p] = nsw;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -448,7 +481,7 @@ selector_bwd_kernel(int n, int Lt, int P, const float* __restrict__ gw_raw, cons
 static size_t pooled_smem(int n, bool large) { return ((large ? 0 : static_cast<size_t>(jacobi_ld(n)) * n) + 3 * n + 64 + jacobi_ld(n) + 8) * sizeof(float); }
 static size_t angles_smem(int n, bool large) { return ((large ? 0 : static_cast<size_t>(jacobi_ld(n - 1)) * (n - 1)) + 3 * n + 128 + n + 16 + jacobi_ld(n)) * sizeof(float); }
 bool spectral_large(int n) { return n > kSpectralSmemMax; }
-size_t pooled_eig_scratch_floats(int n, int problems) { return spectral_large(n) ? static_cast<size_t>(problems) * jacobi_ld(n) * n : 0; }
+size_t pooled_eig_scratch_floats(int n, int problems) { return spectral_large(n) ? static_cast<size_t>(problems) * jacobi_ld(n) * n + problems + 64 : 0; }
 
 cudaError_t launch_pooled_eig(const float* stats, int n, int Lt, int P, float Mt, float Ms, int* ranks, float* evals,
                               float* evecs_km, float* evecs_cm, int* sweeps, float* scratch, cudaStream_t st) {
@@ -458,7 +491,44 @@ cudaError_t launch_pooled_eig(const float* stats, int n, int Lt, int P, float Mt
         if (!scratch) return cudaErrorInvalidValue;
         cudaError_t e = cudaFuncSetAttribute(pooled_eig_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;
-        pooled_eig_kernel<true><<<2 * Lt + P, kPooledLargeThreads, smem, st>>>(stats, n, Lt, P, Mt, Ms, ranks, evals, evecs_km, evecs_cm, sweeps, scratch);
+        const int problems = 2 * Lt + P;
+        const int ld = jacobi_ld(n);
+        const int chunks = (ld + JAC_CHUNK_ROWS - 1) / JAC_CHUNK_ROWS;
+        int* chol_flags = reinterpret_cast<int*>(scratch + static_cast<size_t>(problems) * ld * n);     // (pooled_eig_scratch_floats leaves room)
+        if (chunks > 12) {          // beyond the register-resident cluster solver (marchenko_pastur_rank on wide features): one CTA per problem
+            pooled_eig_kernel<true><<<problems, kPooledLargeThreads, smem, st>>>(stats, n, Lt, P, Mt, Ms, ranks, evals, evecs_km, evecs_cm, sweeps, scratch, 1, chol_flags);
+            return cudaGetLastError();
+        }
+        pooled_eig_kernel<true><<<problems, kPooledLargeThreads, smem, st>>>(stats, n, Lt, P, Mt, Ms, ranks, evals, evecs_km, evecs_cm, sweeps, scratch, 0, chol_flags);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        {
+            const int groups = (n + 1) / 2, per_cta = kPooledThreads / JAC_GROUP;
+            const int cluster = (groups + per_cta - 1) / per_cta;                                       // 6 CTAs for n = 384
+            if (cluster > 8) return cudaErrorInvalidValue;
+            const int gpc = (groups + cluster - 1) / cluster;
+            const size_t jsmem = (static_cast<size_t>(gpc) * ld + ld + 8) * sizeof(float);
+            using JK = void (*)(float*, int, int*);
+            static const JK kerns[5] = {jacobi_cluster_global_kernel<8>, jacobi_cluster_global_kernel<9>, jacobi_cluster_global_kernel<10>,
+                                        jacobi_cluster_global_kernel<11>, jacobi_cluster_global_kernel<12>};
+            const JK kern = kerns[chunks < 8 ? 0 : chunks - 8];
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(jsmem));
+            if (e != cudaSuccess) return e;
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof cfg);
+            cfg.gridDim = dim3(problems * cluster);
+            cfg.blockDim = dim3(kPooledThreads);
+            cfg.dynamicSmemBytes = jsmem;
+            cfg.stream = st;
+            cudaLaunchAttribute attr;
+            attr.id = cudaLaunchAttributeClusterDimension;
+            attr.val.clusterDim.x = cluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+            cfg.attrs = &attr;
+            cfg.numAttrs = 1;
+            e = cudaLaunchKernelEx(&cfg, kern, scratch, n, sweeps);
+            if (e != cudaSuccess) return e;
+        }
+        pooled_eig_kernel<true><<<problems, kPooledLargeThreads, smem, st>>>(stats, n, Lt, P, Mt, Ms, ranks, evals, evecs_km, evecs_cm, sweeps, scratch, 2, chol_flags);
         return cudaGetLastError();
     }
     cudaError_t e = cudaFuncSetAttribute(pooled_eig_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -480,7 +550,8 @@ cudaError_t launch_pooled_eig(const float* stats, int n, int Lt, int P, float Mt
     attr.val.clusterDim.x = cluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, pooled_eig_kernel<false>, stats, n, Lt, P, Mt, Ms, ranks, evals, evecs_km, evecs_cm, sweeps, scratch);
+    return cudaLaunchKernelEx(&cfg, pooled_eig_kernel<false>, stats, n, Lt, P, Mt, Ms, ranks, evals, evecs_km, evecs_cm, sweeps, scratch, 1,
+                              static_cast<int*>(nullptr));
 }
 
 cudaError_t launch_angles(int n, int Lt, int P, const int* ranks, const float* evals, const float* evecs_km,
