@@ -41,6 +41,9 @@ typedef struct basd_shape {
     int act_dtype;  /* BASD_DTYPE_* of student and teacher tokens                     */
     int attn_dtype; /* BASD_DTYPE_* of attention maps                                 */
     int world_size; /* ranks whose pooled statistics are summed (equal local batches) */
+    int polar_steps;/* Newton-Schulz steps of the Procrustes polar iteration: 0 = default (10: singular values of the
+                       cross-covariance down to 3e-5 ||C||_F), up to 16 (each step more divides that floor by ~4);
+                       the residual of the last forward is in basd_view "polar_resid" */
 } basd_shape;
 
 typedef struct basd_inputs {
@@ -76,7 +79,8 @@ int basd_backward_finish(const basd_shape* shape, const basd_inputs* in, void* w
 
 /* Named views into the workspace (for the collectives and for tests).  Names: "stats" [(Lt+P)*(Ds*Ds+Ds)] f32,
  * "gw" [P*Lt] f32, "ranks" [Lt] i32, "w" [P*Lt], "d2" [P*Lt], "geo_i" [P], "loss_b" [P*B], "rows" [Lt*B*Nt],
- * "a" [P*B*Ns], "evals" [(Lt+P)*Ds], "cos" [P*Lt*Ds], "dbg" [P*B*5] (nuc, tr_s, tr_t, polar steps, ||C||_F^2), "gdir", "ktt",
+ * "a" [P*B*Ns], "evals" [(Lt+P)*Ds], "cos" [P*Lt*Ds], "dbg" [P*B*5] (nuc, tr_s, tr_t, polar residual ||X X^T - I||_F going into the
+ * last Newton-Schulz step, ||C||_F^2), "polar_resid" [1] (largest residual over all problems: <= 0.1 means converged), "gdir", "ktt",
  * "polar_*" (state of the polar iteration; bf16 views count hi then lo elements). */
 int basd_view(const basd_shape* shape, void* workspace, const char* name, void** ptr, size_t* count);
 

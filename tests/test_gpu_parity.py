@@ -210,7 +210,12 @@ def test_tiny_cases_against_oracle_and_reference_golden(lib, cuda_dev, name):
     inp = synth.make_inputs(w, seed=g["seed"])
     m = build_module(w, cuda_dev)
     out = run_module(m, inp, cuda_dev)
-    assert_parity(out, oracle_case(m, inp, w), w, tgrad_tol=3e-3 if name.startswith("tiny") else TOL_TGRAD)
+    ref = oracle_case(m, inp, w)
+    # Temperature gradients of these 256-row problems: the softmax derivative is a difference of nearly equal per-layer
+    # terms, which amplifies the 2^-17 relative precision of the split-bf16 polar products; entries are held to 1e-3 of
+    # the LARGEST entry plus 1e-3 of themselves (the BASELINE shapes, cfg1 / cfg2 below, to 1e-3 of each entry).
+    tfloor = 1e-3 * ref["grad_log_temperatures"].abs().max().item() + 1e-7
+    assert_parity(out, ref, w, tgrad_floor=tfloor)
     assert out["ranks"] == g["ranks"]
     assert abs(out["loss"].item() - g["loss"].item()) <= TOL_LOSS * abs(g["loss"].item())
     for l in g["token_layers"]:
@@ -219,10 +224,8 @@ def test_tiny_cases_against_oracle_and_reference_golden(lib, cuda_dev, name):
         # softmax over a single layer: w == 1 and no temperature gradient (an fma leaves ~1e-7 of rounding, the reference 0)
         assert out["grad_log_temperatures"].abs().max() < 1e-6 and (out["w"] == 1).all()
     else:
-        # 256 pooled rows only: the bf16 rounding of the projected teacher tokens does not average out as it does at
-        # the BASELINE sizes (>= 6272 rows, where 1e-3 holds) -> 3e-3 here
         assert ((out["grad_log_temperatures"] - g["grad_log_temperatures"]).abs()
-                <= 3e-3 * g["grad_log_temperatures"].abs() + 1e-7).all()
+                <= TOL_TGRAD * g["grad_log_temperatures"].abs() + tfloor).all()
 
 
 @pytest.mark.parametrize("act_dtype,views", [(torch.bfloat16, False), (torch.float32, False), (torch.float32, True),
@@ -253,11 +256,9 @@ def test_cfg1_small_batch_against_oracle(lib, cuda_dev):
     w = dataclasses.replace(synth.CONFIGS["cfg1"], B=4)
     inp = synth.make_inputs(w)
     m = build_module(w, cuda_dev)
-    # 784 pooled rows for 192 dimensions: eigen-gaps of the pooled Gram are small and the gradient through the
-    # eigenvectors amplifies the ~1e-9 run-to-run reordering of the split-K atomics (observed 0.4-1.5e-2 between
-    # launches of the same build; the solver itself is bitwise repeatable, tools/gpu_debug_eig.py).  The BASELINE
-    # batch sizes (cfg1 B=32, cfg2 B=256 below) are held to TOL_SGRAD itself.
-    assert_parity(run_module(m, inp, cuda_dev), oracle_case(m, inp, w), w, sgrad_tol=3 * TOL_SGRAD)
+    # (every reduction is fixed-order now: the 3x tolerance this case needed while the split-K Grams used atomics is gone)
+    assert_parity(run_module(m, inp, cuda_dev), oracle_case(m, inp, w), w)
+    assert m.last_polar_residual.item() <= m.POLAR_RESIDUAL_OK
 
 
 def test_bf16_attention_maps(lib, cuda_dev):
@@ -267,11 +268,10 @@ def test_bf16_attention_maps(lib, cuda_dev):
     a = run_module(m, inp, cuda_dev, attn_dtype=torch.float32)
     b = run_module(m, inp, cuda_dev, attn_dtype=torch.bfloat16)
     assert abs(a["loss"].item() - b["loss"].item()) <= 1e-6 * abs(a["loss"].item())
-    # Not bitwise: split-K atomics reorder the pooled sums by ~1e-9, the Jacobi / polar iterations land within their
-    # tolerance of it, and the polar factor amplifies that by its condition number (~1e4 here) -> a few 1e-4, which is
-    # the sensitivity the reference's own fp32 LAPACK path has on these inputs.
+    # the values are bf16-representable, so both dtypes feed identical numbers: identical results, bit for bit
     for l in a["grad_student"]:
-        assert rel(a["grad_student"][l], b["grad_student"][l]) < TOL_SGRAD
+        assert torch.equal(a["grad_student"][l], b["grad_student"][l])
+    assert torch.equal(a["grad_log_temperatures"], b["grad_log_temperatures"])
     assert_parity(b, oracle_case(m, inp, w), w)
 
 
@@ -312,6 +312,52 @@ def test_cfg345_reduced_batch_against_reference_golden(lib, cuda_dev, name):
         pr = torch.stack([(out["grad_student"][l] * p).sum() for p in _probes(out["grad_student"][l].shape)])
         assert (pr - g["grad_student_probe"][l]).abs().max() <= TOL_SGRAD * g["grad_student_norm"][l] * math.sqrt(out["grad_student"][l].numel()) * 0.05
     assert_parity(out, oracle_case(m, inp, w), w, tgrad_floor=1e-6 if w.Lt == 1 else 1e-7)
+
+
+@pytest.mark.parametrize("shape", [dict(B=4, Ns=196, Nt=196, Ds=192, Dt=384, Lt=12, H=6, has_cls=True),        # cfg1 at B=4: feature form, fused polar kernel
+                                   dict(B=3, Ns=220, Nt=110, Ds=216, Dt=256, Lt=2, H=2, has_cls=True),         # teacher-token form with resampling
+                                   dict(B=4, Ns=300, Nt=300, Ds=256, Dt=512, Lt=3, H=2, has_cls=True)])        # global-memory eigen-solver, tiled products
+def test_two_executions_are_bitwise_equal(lib, cuda_dev, shape):
+    """Every cross-CTA reduction (split-K Grams, column sums, traces, weight-gradient dots, centring correction) is a
+    fixed-order two-stage sum: two executions of the same step give the same bits (loss, every gradient)."""
+    w = synth.Workload("repeat", shape["B"], shape["Ns"], shape["Nt"], shape["Ds"], shape["Dt"], shape["Lt"], shape["H"], shape["has_cls"])
+    inp = synth.make_inputs(w, seed=5)
+    m = build_module(w, cuda_dev)
+    a = run_module(m, inp, cuda_dev)
+    b = run_module(m, inp, cuda_dev)
+    assert torch.equal(a["loss"], b["loss"]) and torch.equal(a["grad_log_temperatures"], b["grad_log_temperatures"])
+    for l in a["grad_student"]:
+        assert torch.equal(a["grad_student"][l], b["grad_student"][l])
+
+
+def test_ill_conditioned_cross_covariance(lib, cuda_dev):
+    """A steep student spectrum (0.94^i: kappa(C) ~ 2e5, smallest singular value 2e-6 ||C||_F - below the 3e-5 floor of the
+    default 10-step schedule).  The reference's SVD gives every singular direction unit weight in the gradient
+    (relational.py:48), so: (1) the residual reported by the default run exceeds the bound, (2) the module raises its step
+    count on the next call with a warning, (3) with the longer schedule loss and student gradients match the fp64 oracle at
+    the north-star tolerances."""
+    import warnings
+    w = dataclasses.replace(synth.CONFIGS["cfg1"], B=4)
+    inp = synth.make_inputs(w)
+    gen = torch.Generator().manual_seed(77)
+    inp["student"] = {l: synth.geometric(w.B, w.Ns, w.Ds, gen, rho=0.94) for l in inp["student"]}
+    m = build_module(w, cuda_dev)
+    out10 = run_module(m, inp, cuda_dev)
+    assert m.last_polar_residual.item() > m.POLAR_RESIDUAL_OK                 # (1) not converged, and reported
+    torch.cuda.synchronize()
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        run_module(m, inp, cuda_dev)                                           # (2) the next call reads the residual back
+    assert m.polar_steps == 12 and any("polar iteration" in str(r.message) for r in rec)
+    m.polar_steps = 14
+    out = run_module(m, inp, cuda_dev)
+    assert m.last_polar_residual.item() <= m.POLAR_RESIDUAL_OK
+    ref = oracle_case(m, inp, w, dtype=torch.float64)
+    assert out["ranks"] == ref["ranks"]
+    assert abs(out["loss"].item() - ref["loss"].item()) <= TOL_LOSS * abs(ref["loss"].item())
+    worst10 = max(rel(out10["grad_student"][l], ref["grad_student"][l]) for l in ref["grad_student"])
+    for l in ref["grad_student"]:
+        assert rel(out["grad_student"][l], ref["grad_student"][l]) < TOL_SGRAD, f"student grad layer {l} (10 steps gave {worst10:.2e})"
 
 
 # ------------------------------------------------------------------------------------------------ properties
@@ -421,10 +467,8 @@ def test_host_stager_matches_device_path(lib, cuda_dev):
         assert abs(loss.item() - ref["loss"].item()) <= 1e-5 * abs(ref["loss"].item())
         assert rel(m.layer_selector.log_temperatures.grad.cpu(), ref["grad_log_temperatures"]) < TOL_TGRAD
         for l in ref["grad_student"]:
-            # two separate executions of an ill-conditioned small-batch case (784 pooled rows for 192 dimensions: the
-            # eigen-gaps the selector backward divides by are tiny): bf16 gradient rounding + the run-to-run sensitivity
-            # documented in test_bf16_attention_maps, so 3x the north-star tolerance here
-            assert rel(h["leaf_student"][l].grad.float().cpu(), ref["grad_student"][l]) < 3 * TOL_SGRAD
+            # same kernels on the same values: bitwise the same gradients
+            assert torch.equal(h["leaf_student"][l].grad.float().cpu(), ref["grad_student"][l])
         assert stager.h2d_bytes_last < 1.05 * (sum(v.numel() * 2 for v in inp["teacher"].values()) + sum(v.numel() * 2 for v in inp["student"].values())
                                                + inp["logits"].numel() * 4 + 8 * w.B + w.Lt * w.B * w.H * (w.Nt + 1) * 2)
 
@@ -482,12 +526,21 @@ def test_irregular_shapes_against_oracle(lib, cuda_dev, shape):
     assert out["ranks"] == ref["ranks"]
     assert abs(out["loss"].item() - ref["loss"].item()) <= TOL_LOSS * abs(ref["loss"].item())
     assert (out["w"] - ref["w"].float()).abs().max() < 2e-4
-    # few pooled rows: small eigen-gaps, so the referee-scaled tolerances of the tiny fixtures apply
     gt, rt = out["grad_log_temperatures"], ref["grad_log_temperatures"].float()
-    # (entries that are themselves a cancellation to ~5 % of the largest one are judged against the largest; the softmax
-    # derivative is a difference of the per-layer terms, which at these sizes - a few hundred pooled rows, one or two
-    # layers - amplifies their ~1e-3 agreement to 0.5-1 %, varying with the order of the split-K atomics from run to
-    # run.  The BASELINE shapes are held to TOL_TGRAD = 1e-3 in the cfg1 / cfg2 tests.)
-    assert ((gt - rt).abs() <= 2e-2 * rt.abs().max()).all(), f"temperature grads {gt.tolist()} vs {rt.tolist()}"
+    # Temperature gradients: entries that are themselves a cancellation to a few % of the largest one are judged against the
+    # largest.  The softmax derivative is a difference of nearly equal per-layer terms; at these sizes (a few hundred pooled
+    # rows, one to four layers) that amplifies the 2^-17 precision of the split-bf16 polar products to at most 3e-3 (measured
+    # against the fp64 oracle: the reference's own fp32 is 1e-5 there, so this is OUR error, stated - not reference noise).
+    # The BASELINE shapes are held to TOL_TGRAD = 1e-3 of each entry in the cfg1 - cfg5 tests.
+    assert ((gt - rt).abs() <= 3e-3 * rt.abs().max()).all(), f"temperature grads {gt.tolist()} vs {rt.tolist()}"
     for l in ref["grad_student"]:
-        assert rel(out["grad_student"][l], ref["grad_student"][l]) < 3 * TOL_SGRAD, f"student grad layer {l}"
+        assert rel(out["grad_student"][l], ref["grad_student"][l]) < TOL_SGRAD, f"student grad layer {l}"
+    if m.last_polar_residual.item() > m.POLAR_RESIDUAL_OK:
+        # near-square cross-covariances (D_s within a few rows of N - 1) have a few singular values below the 3e-5 floor of
+        # the default schedule: reported by the residual, and gone with the two extra steps the module would add by itself
+        assert shape["Ds"] >= min(shape["Ns"], shape["Nt"]) - 10
+        m.polar_steps = 12
+        out = run_module(m, inp, cuda_dev)
+        assert m.last_polar_residual.item() <= m.POLAR_RESIDUAL_OK
+        for l in ref["grad_student"]:
+            assert rel(out["grad_student"][l], ref["grad_student"][l]) < TOL_SGRAD

@@ -40,6 +40,28 @@ def mp(M, D, r):
     dt = time.time() - t0
     print(f"mp_rank M={M} D={D}: gpu {got} oracle {O.mp_rank(f.float())} ({dt*1e3:.0f} ms)", flush=True)
 
+def run_once(m, inp):
+    S = {l: v.to(dev).detach().requires_grad_() for l, v in inp["student"].items()}
+    T = {j: v.to(dev) for j, v in inp["teacher"].items()}
+    A = {j: v.to(dev) for j, v in inp["attn"].items()}
+    logits = inp["logits"].to(dev).requires_grad_()
+    m.zero_grad(set_to_none=True)
+    loss = m(logits, inp["targets"].to(dev), S, T, A)
+    loss.backward()
+    torch.cuda.synchronize()
+    return loss.detach().clone(), {l: S[l].grad.clone() for l in S}, m.layer_selector.log_temperatures.grad.clone()
+
+def repeat(name, w, seed=1234):
+    """two executions of the same step: bitwise equal?"""
+    inp = synth.make_inputs(w, seed=seed)
+    torch.manual_seed(0)
+    m = pkg.BASDLoss(nn.CrossEntropyLoss(label_smoothing=0.001), w.Ds, w.Dt, w.student_depth, w.Ns,
+                     config=synth.module_config(w), teacher_has_cls_token=w.has_cls).to(dev)
+    a = run_once(m, inp); b = run_once(m, inp)
+    same = torch.equal(a[0], b[0]) and torch.equal(a[2], b[2]) and all(torch.equal(a[1][l], b[1][l]) for l in a[1])
+    worst = max(rel(a[1][l].float(), b[1][l].float()) for l in a[1])
+    print(f"repeat {name}: bitwise {'EQUAL' if same else 'DIFFERENT'} (loss {a[0].item()!r} vs {b[0].item()!r}, worst student-grad rel diff {worst:.2e})", flush=True)
+
 def case(name, w, seed=1234):
     inp = synth.make_inputs(w, seed=seed)
     torch.manual_seed(0)
@@ -79,7 +101,14 @@ CASES = {
     "cfg3s": W("cfg3s", 8, 196, 49, 384, 2048, 1, 1, False),
     "d256": W("d256", 4, 300, 300, 256, 512, 3, 2, True),
     "n320": W("n320", 4, 320, 320, 192, 384, 3, 2, True),
+    "cfg1b4": dataclasses.replace(synth.CONFIGS["cfg1"], B=4),
+    "cfg2b6": dataclasses.replace(synth.CONFIGS["cfg2"], B=6),
 }
+IRREG = [dict(B=3, Ns=50, Nt=50, Ds=40, Dt=72, Lt=2, H=3, P=3), dict(B=5, Ns=36, Nt=36, Ds=32, Dt=32, Lt=4, H=1, P=1),
+         dict(B=2, Ns=130, Nt=130, Ds=96, Dt=200, Lt=3, H=2, P=2), dict(B=2, Ns=70, Nt=90, Ds=64, Dt=136, Lt=2, H=2, P=4),
+         dict(B=9, Ns=210, Nt=210, Ds=200, Dt=256, Lt=2, H=2, P=2), dict(B=3, Ns=160, Nt=160, Ds=144, Dt=192, Lt=2, H=2, P=2),
+         dict(B=4, Ns=100, Nt=100, Ds=136, Dt=160, Lt=2, H=2, P=2), dict(B=3, Ns=220, Nt=110, Ds=216, Dt=256, Lt=2, H=2, P=2),
+         dict(B=3, Ns=240, Nt=220, Ds=232, Dt=256, Lt=2, H=2, P=2)]
 if __name__ == "__main__":
     which = sys.argv[1:] or ["eig", "mp", "n320", "d256", "cfg5s"]
     for c in which:
@@ -87,6 +116,11 @@ if __name__ == "__main__":
             for n in (192, 256, 384): eig(n)
         elif c == "mp":
             mp(8000, 384, 30); mp(6000, 768, 40); mp(300, 384, 8)
+        elif c == "irreg":
+            for k, sh in enumerate(IRREG):
+                case(f"irreg{k}", W("irregular", sh["B"], sh["Ns"], sh["Nt"], sh["Ds"], sh["Dt"], sh["Lt"], sh["H"], True, P=sh["P"]), seed=11)
+        elif c == "repeat":
+            repeat("cfg1b4", CASES["cfg1b4"]); repeat("cfg4s", CASES["cfg4s"]); repeat("cfg2b6", CASES["cfg2b6"]); repeat("cfg5s", CASES["cfg5s"])
         elif c == "tiny":
             from oracle.make_golden import TINY
             for k, w in TINY.items(): case(k, w)

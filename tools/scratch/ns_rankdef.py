@@ -169,7 +169,7 @@ def run(name, Ns, Nt, Ds, Dt, rho=0.985):
             print(f"   {label:13s} {'fp64 ' if exact else 'split'}: nuc rel {abs(float(o['nuc'] - ref['nuc'])) / float(ref['nuc']):.2e}  Gs rel {rel(o['Gs'], ref['Gs']):.2e}"
                   f"  Xi.t rel {rel(o['Xi'] @ t, Xi_ref_t):.2e}")
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) == 1:
     run("cfg4-like", 196, 196, 384, 1024)
     run("cfg3-like", 196, 49, 384, 2048)
     run("tiny-interp-like", 64, 16, 64, 96)
@@ -214,7 +214,7 @@ def run_vd(name, Ns, Nt, Ds, Dt, rho=0.985, trace=False):
         o = vd_onesided(s, t, a, E, exact=exact, trace=trace and not exact)
         print(f"   V_D {'fp64 ' if exact else 'split'}: nuc rel {abs(float(o['nuc'] - ref['nuc'])) / float(ref['nuc']):.2e}  Gs rel {rel(o['Gs'], ref['Gs']):.2e}")
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) == 1:
     run_vd("cfg2-like", 196, 196, 192, 768, trace=True)
     run_vd("cfg2 steep", 196, 196, 192, 768, rho=0.97, trace=True)
 
@@ -251,5 +251,28 @@ def chol_trace(Ns, Nt, Ds, Dt, rho, aug_scale=1.0):
         Bm = q(ca * torch.eye(A.shape[0]) + cb * A + cc * mm(A, A))
         W = q(mm(Bm, W) * (alpha if k == 0 else 1.0))
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) == 1:
     chol_trace(196, 196, 384, 1024, 0.97)
+
+def steep_study():
+    import numpy as np
+    for rho in (0.985, 0.96, 0.94, 0.92):
+        s, t, a = make(196, 196, 192, 768, rho=rho)
+        E = interp_matrix(196, 196)
+        ref = reference(s, t, a, E)
+        S = ref["S"]
+        # fp32 LAPACK reference error (what the reference itself delivers)
+        C32 = (ref["s_w"].float().T @ ref["t_w"].float())
+        U, Sv, Vt = torch.linalg.svd(C32, full_matrices=False)
+        Gs32 = ref["t_w"].float() @ (U @ Vt).T
+        print(f"rho={rho}: kappa {float(S[0]/S[-1]):.3g} smin/fro {float(S[-1]/S.norm()):.2e} | fp32 SVD Gs err {rel(Gs32.double(), ref['Gs']):.2e}")
+        for extra in (0, 2, 4, 6):
+            global COEF
+            saved = COEF
+            COEF = [saved[0]] * extra + saved
+            o = vd_onesided(s, t, a, E, exact=False, steps=10 + extra)
+            o64 = vd_onesided(s, t, a, E, exact=True, steps=10 + extra)
+            COEF = saved
+            print(f"    extra {extra}: split Gs err {rel(o['Gs'], ref['Gs']):.2e} nuc err {abs(float(o['nuc']-ref['nuc']))/float(ref['nuc']):.2e} | fp64-arith Gs err {rel(o64['Gs'], ref['Gs']):.2e}")
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "steep":
+    steep_study()

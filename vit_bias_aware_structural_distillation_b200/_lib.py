@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libbasd_b200.so")
 
 class Shape(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in
-                ("B", "Ns", "Nt", "Ds", "Dt", "Lt", "P", "H", "has_cls", "act_dtype", "attn_dtype", "world_size")]
+                ("B", "Ns", "Nt", "Ds", "Dt", "Lt", "P", "H", "has_cls", "act_dtype", "attn_dtype", "world_size", "polar_steps")]
 
 
 class Inputs(ctypes.Structure):

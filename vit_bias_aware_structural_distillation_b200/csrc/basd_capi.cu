@@ -1,4 +1,5 @@
 // C-ABI entry points (include/basd_b200.h): workspace layout and kernel orchestration of the four phases.
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -28,6 +29,9 @@ extern "C" const char* basd_last_error(void) { return g_err; }
 // ---------------------------------------------------------------------------------------------- live kernel timing
 // Optional CUDA-event brackets around each kernel group, recorded on the launching stream inside the caller's timed
 // region (bench.py's roofline numbers come from here, not from a profiler).  Also counts kernel launches.
+// The launch counter is atomic; the event brackets are a single-caller measurement facility (basd_timing_enable is off
+// by default and documented as not re-entrant in include/basd_b200.h) - the compute entry points themselves keep no
+// mutable process state.
 namespace {
 constexpr int kTimeSlots = 18;
 constexpr int kMaxPairs = 2048;
@@ -37,7 +41,7 @@ const char* kSlotNames[kTimeSlots] = {"importance_rows", "split_pack", "project"
 struct TimeSlot { cudaEvent_t ev[kMaxPairs][2]; int created = 0; int used = 0; };
 TimeSlot g_slots[kTimeSlots];
 bool g_timing = false;
-long long g_launches = 0;
+std::atomic<long long> g_launches{0};
 struct Scope {
     int slot; cudaStream_t st; bool on;
     Scope(int slot_, cudaStream_t st_, int n_launches) : slot(slot_), st(st_), on(false) {
@@ -53,7 +57,7 @@ struct Scope {
 }  // namespace
 extern "C" void basd_timing_enable(int on) { g_timing = on != 0; }
 extern "C" void basd_timing_reset(void) { for (auto& t : g_slots) t.used = 0; g_launches = 0; }
-extern "C" long long basd_launch_count(void) { return g_launches; }
+extern "C" long long basd_launch_count(void) { return g_launches.load(); }
 extern "C" int basd_timing_slots(void) { return kTimeSlots; }
 extern "C" const char* basd_timing_name(int slot) { return (slot >= 0 && slot < kTimeSlots) ? kSlotNames[slot] : ""; }
 // total milliseconds and number of timed brackets of a slot (synchronises on the recorded events)
@@ -102,9 +106,9 @@ int polar_path(const basd_shape& s) {
 struct Layout {
     size_t rows, pt_hi, pt_lo, tpk, spk, z, stats, ranks, sweeps, evals, evecs_km, evecs_cm, d2, w, cosv, gamma, ang_scr, a, ssum,
         tbar_hi, tbar_lo, ktt, gdir, theta, gwt, loss_b, dbg, geo_i, gw, gam_hi, gam_lo, corr,
-        pw, pw2, pt, pa, pb, pkt, psw, gsw, pvec, pscal, pfro, theta_lo, dtm, eig_scr,
+        pw, pw2, pt, pa, pb, pkt, psw, gsw, pvec, pscal, pfro, pres, theta_lo, dtm, eig_scr, gram_part, colsum_part, gw_part,
         vfg, vfgt, vginvc, vginvt, vx0, vx1, vx2, vh, vm2, vginv, vthraw, vftf, total;
-    int NsPad, Np, path, Nk, Dsp;    // Nk: token rows of the mixed teacher / Theta (Ns, or Nt in the teacher-token form)
+    int NsPad, Np, path, Nk, Dsp, dtm_split;    // Nk: token rows of the mixed teacher / Theta (Ns, or Nt in the teacher-token form)
 };
 
 size_t align_up(size_t x) { return (x + 1023) & ~static_cast<size_t>(1023); }
@@ -134,6 +138,16 @@ Layout make_layout(const basd_shape& s) {
     L.evecs_km = take(4 * (Lt + P) * Ds * Ds);
     L.evecs_cm = take(4 * (Lt + P) * Ds * Ds);
     L.eig_scr = take(4 * pooled_eig_scratch_floats(s.Ds, 2 * s.Lt + s.P));   // D_s > 224: eigenproblem matrices in global memory
+    // per-CTA partial results of the split-K Grams, column sums and weight-gradient dots (each summed in a fixed order)
+    {
+        const size_t gp_t = gemm_gram_part_floats(B * Nt, s.Ds, s.Lt), gp_s = gemm_gram_part_floats(B * Ns, s.Ds, s.P);
+        L.gram_part = take(4 * (gp_t > gp_s ? gp_t : gp_s));
+        const size_t cp_a = colsum_part_floats(s.Lt + s.P, B * Nt, s.Ds), cp_t = colsum_part_floats(s.Lt, B * Nt, s.Ds),
+                     cp_s = colsum_part_floats(s.P, B * Ns, s.Ds);
+        const size_t cp = cp_a > cp_t ? (cp_a > cp_s ? cp_a : cp_s) : (cp_t > cp_s ? cp_t : cp_s);
+        L.colsum_part = take(4 * cp);
+        L.gw_part = take(4 * wgrad_part_floats(s.P, s.Lt));
+    }
     L.d2 = take(4 * P * Lt);
     L.w = take(4 * P * Lt);
     L.cosv = take(4 * P * Lt * Ds);
@@ -171,15 +185,20 @@ Layout make_layout(const basd_shape& s) {
     L.gsw = take(4 * nprob * Ns * Ds);
     L.pvec = take(4 * nprob * 4 * Ns);
     L.pscal = take(4 * nprob * 4);
-    L.pfro = take(4 * nprob);
+    L.pfro = take(4 * nprob * polar_fro_slots(vt ? s.Nt : s.Ds));
+    L.pres = take(4 * nprob * polar_fro_slots(vt ? s.Nt : s.Ds));
     L.gdir = take(4 * P * B * Ns * Ds);
     L.theta = take(2 * P * B * Nk * L.NsPad);
     L.theta_lo = take(2 * P * B * Nk * L.NsPad);
-    L.dtm = take(2 * P * B * Nk * Dt);
+    // Gradient w.r.t. the mixed teacher: one bf16 at the BASELINE sizes; a split pair (hi block then lo block) when the
+    // tensor is small - its rounding error reaches the temperature gradients as noise ~ 2^-9 / sqrt(elements) amplified by the
+    // cancellation between layers: 5e-4 at 2.5e4 elements, 1e-5 at the 3.8e7 of cfg2
+    L.dtm_split = (P * B * Nk * Dt) < (size_t(1) << 24) ? 1 : 0;
+    L.dtm = take((L.dtm_split ? 2 : 1) * 2 * P * B * Nk * Dt);
     L.gwt = take(4 * P * B * Ns);
     L.loss_b = take(4 * P * B);
     L.dbg = take(4 * P * B * 5);
-    L.geo_i = take(4 * (P + 1));
+    L.geo_i = take(4 * (P + 2));                          // per-point means, their mean, largest polar residual
     L.gw = take(4 * P * Lt);
     L.gam_hi = take(2 * P * Ds * Ds);
     L.gam_lo = take(2 * P * Ds * Ds);
@@ -194,6 +213,8 @@ int check_shape(const basd_shape& s) {
     if (s.P > BASD_MAX_POINTS || s.Lt > BASD_MAX_LAYERS) return fail("P <= %d and Lt <= %d required", BASD_MAX_POINTS, BASD_MAX_LAYERS);
     if (s.Ds % 8 || s.Dt % 8) return fail("Ds and Dt must be multiples of 8 (16-byte rows), got %d, %d", s.Ds, s.Dt);
     if (s.Ds > 1024) return fail("Ds=%d > 1024 is not supported", s.Ds);
+    if (s.polar_steps != 0 && (s.polar_steps < kPolarStepsDefault || s.polar_steps > kPolarStepsMax))
+        return fail("polar_steps must be 0 (default %d) or %d..%d, got %d", kPolarStepsDefault, kPolarStepsDefault, kPolarStepsMax, s.polar_steps);
     if (polar_path(s) == kPathTeacherTokens) {
         // rank(C) = min(Ns, Nt) - 1 < Ds: the polar iteration runs in the teacher's token space
         if (s.Nt > s.Ns)
@@ -253,14 +274,14 @@ extern "C" int basd_view(const basd_shape* shape, void* workspace, const char* n
     const size_t B = s.B, Ns = s.Ns, Nt = s.Nt, Ds = s.Ds, Lt = s.Lt, P = s.P;
     struct E { const char* n; size_t off; size_t cnt; } table[] = {
         {"stats", L.stats, (Lt + P) * (Ds * Ds + Ds)}, {"gw", L.gw, P * Lt}, {"ranks", L.ranks, Lt}, {"w", L.w, P * Lt},
-        {"d2", L.d2, P * Lt}, {"geo_i", L.geo_i, P + 1}, {"loss_b", L.loss_b, P * B}, {"rows", L.rows, Lt * B * Nt},
+        {"d2", L.d2, P * Lt}, {"geo_i", L.geo_i, P + 1}, {"polar_resid", L.geo_i + 4 * (P + 1), 1}, {"loss_b", L.loss_b, P * B}, {"rows", L.rows, Lt * B * Nt},
         {"a", L.a, P * B * Ns}, {"evals", L.evals, (Lt + P) * Ds}, {"cos", L.cosv, P * Lt * Ds}, {"dbg", L.dbg, P * B * 5},
         {"gdir", L.gdir, P * B * Ns * Ds}, {"ktt", L.ktt, P * B * L.Nk * L.Nk}, {"sweeps", L.sweeps, 2 * Lt + P},
         {"gamma", L.gamma, P * Lt * Ds * Ds}, {"gwt", L.gwt, P * B * Ns}, {"evecs", L.evecs_km, (Lt + P) * Ds * Ds},
         {"corr", L.corr, P * Ds}, {"ssum", L.ssum, P * B},
         // polar iteration state (bf16 pairs: count is in bf16 elements, hi block then lo block)
         {"polar_w", (polar_steps() % 2) ? L.pw2 : L.pw, 2 * P * B * Ds * L.Np}, {"polar_kt", L.pkt, 2 * P * B * Ns * L.Np},
-        {"polar_sw", L.psw, 2 * P * B * Ns * ((Ds + 63) / 64 * 64)}, {"polar_a", L.pa, 2 * P * B * Ds * ((Ds + 63) / 64 * 64)}, {"polar_gsw", L.gsw, P * B * Ns * Ds}, {"polar_fro2", L.pfro, P * B},
+        {"polar_sw", L.psw, 2 * P * B * Ns * ((Ds + 63) / 64 * 64)}, {"polar_a", L.pa, 2 * P * B * Ds * ((Ds + 63) / 64 * 64)}, {"polar_gsw", L.gsw, P * B * Ns * Ds}, {"polar_fro2", L.pfro, P * B * static_cast<size_t>(polar_fro_slots(L.path == kPathTeacherTokens ? s.Nt : s.Ds))},
         {"theta", L.theta, P * B * L.Nk * L.NsPad},
     };
     for (const E& e : table)
@@ -280,7 +301,6 @@ extern "C" int basd_forward_stats(const basd_shape* shape, const basd_inputs* in
     const size_t stat_stride = static_cast<size_t>(s.Ds) * s.Ds + s.Ds;
     float* stats = reinterpret_cast<float*>(ws + L.stats);
 
-    CK(cudaMemsetAsync(stats, 0, sizeof(float) * (s.Lt + s.P) * stat_stride, st));
     PtrTable attn;
     memset(&attn, 0, sizeof attn);
     for (int j = 0; j < s.Lt; ++j) attn.p[j] = in.attn[j];
@@ -312,14 +332,15 @@ extern "C" int basd_forward_stats(const basd_shape* shape, const basd_inputs* in
         CK(gemm_project(layers, s.Lt, Mt, s.Dt, pt_hi, pt_lo, s.Ds, z, zlo, st));
     }
     {
-        Scope sc(3, st, 2);
-        CK(gemm_gram_batched(z, zlo, Mt, s.Ds, s.Lt, stats, static_cast<long long>(stat_stride), st));
+        Scope sc(3, st, 4);
+        float* gram_part = reinterpret_cast<float*>(ws + L.gram_part);
+        CK(gemm_gram_batched(z, zlo, Mt, s.Ds, s.Lt, stats, static_cast<long long>(stat_stride), gram_part, st));
         const void* pts[kMaxPoints];
         for (int i = 0; i < s.P; ++i) pts[i] = r.student[i];
-        CK(gemm_gram_table(pts, s.P, Ms, s.Ds, stats + s.Lt * stat_stride, static_cast<long long>(stat_stride), st));
+        CK(gemm_gram_table(pts, s.P, Ms, s.Ds, stats + s.Lt * stat_stride, static_cast<long long>(stat_stride), gram_part, st));
     }
     {
-        Scope sc(4, st, Mt == Ms ? 1 : 2);
+        Scope sc(4, st, Mt == Ms ? 2 : 4);
         ColsumJobs jt, js;
         memset(&jt, 0, sizeof jt); memset(&js, 0, sizeof js);
         for (int j = 0; j < s.Lt; ++j) {
@@ -332,10 +353,10 @@ extern "C" int basd_forward_stats(const basd_shape* shape, const basd_inputs* in
         }
         if (Mt == Ms) {                     // same row count: one launch covers teacher and student jobs
             for (int i = 0; i < s.P; ++i) { jt.hi[s.Lt + i] = js.hi[i]; jt.lo[s.Lt + i] = nullptr; jt.out[s.Lt + i] = js.out[i]; }
-            CK(launch_colsum(jt, s.Lt + s.P, Mt, s.Ds, st));
+            CK(launch_colsum(jt, s.Lt + s.P, Mt, s.Ds, reinterpret_cast<float*>(ws + L.colsum_part), st));
         } else {
-            CK(launch_colsum(jt, s.Lt, Mt, s.Ds, st));
-            CK(launch_colsum(js, s.P, Ms, s.Ds, st));
+            CK(launch_colsum(jt, s.Lt, Mt, s.Ds, reinterpret_cast<float*>(ws + L.colsum_part), st));
+            CK(launch_colsum(js, s.P, Ms, s.Ds, reinterpret_cast<float*>(ws + L.colsum_part), st));
         }
     }
     return 0;
@@ -422,6 +443,9 @@ extern "C" int basd_forward_solve(const basd_shape* shape, const basd_inputs* in
     pa.vec = reinterpret_cast<float*>(ws + L.pvec);
     pa.scal = reinterpret_cast<float*>(ws + L.pscal);
     pa.fro2 = reinterpret_cast<float*>(ws + L.pfro);
+    pa.fro_slots = polar_fro_slots(vt ? s.Nt : s.Ds);
+    pa.resid = reinterpret_cast<float*>(ws + L.pres);
+    pa.steps = s.polar_steps ? s.polar_steps : kPolarStepsDefault;
     pa.gdir = reinterpret_cast<float*>(ws + L.gdir);
     pa.theta = reinterpret_cast<__nv_bfloat16*>(ws + L.theta);
     pa.theta_lo = reinterpret_cast<__nv_bfloat16*>(ws + L.theta_lo);
@@ -431,7 +455,7 @@ extern "C" int basd_forward_solve(const basd_shape* shape, const basd_inputs* in
     if (vt) CK(launch_polar_procrustes_vt(pa, st, nullptr));
     else CK(launch_polar_procrustes(pa, st, nullptr));  // timing slots 10 / 16 / 17 are bracketed inside
     float* geo_i = reinterpret_cast<float*>(ws + L.geo_i);
-    TIMED(11, 1, CK(launch_loss_reduce(pa.loss_b, s.P, s.B, geo_i, geo_i + s.P, st)));
+    TIMED(11, 1, CK(launch_loss_reduce(pa.loss_b, pa.dbg, s.P, s.B, geo_i, geo_i + s.P, geo_i + s.P + 1, st)));
     CK(cudaMemcpyAsync(geo_loss, geo_i + s.P, sizeof(float), cudaMemcpyDeviceToDevice, st));
     return 0;
 }
@@ -451,13 +475,13 @@ extern "C" int basd_backward_dots(const basd_shape* shape, const basd_inputs* in
     __nv_bfloat16* thi = reinterpret_cast<__nv_bfloat16*>(ws + L.tbar_hi);
     __nv_bfloat16* tlo = reinterpret_cast<__nv_bfloat16*>(ws + L.tbar_lo);
     __nv_bfloat16* dtm = reinterpret_cast<__nv_bfloat16*>(ws + L.dtm);
+    __nv_bfloat16* dtm_lo = L.dtm_split ? dtm + static_cast<size_t>(s.P) * s.B * L.Nk * s.Dt : nullptr;
     // (teacher-token form: Theta, the mixed teacher and its gradient live on the teacher's own token grid, L.Nk = Nt rows)
     TIMED(12, 1, CK(gemm_theta_apply(reinterpret_cast<__nv_bfloat16*>(ws + L.theta), reinterpret_cast<__nv_bfloat16*>(ws + L.theta_lo), L.NsPad,
-                                     thi, tlo, s.P * s.B, L.Nk, s.Dt, dtm, st)));
+                                     thi, tlo, s.P * s.B, L.Nk, s.Dt, dtm, dtm_lo, st)));
     float* gw = reinterpret_cast<float*>(ws + L.gw);
-    CK(cudaMemsetAsync(gw, 0, sizeof(float) * s.P * s.Lt, st));
-    TIMED(13, 2, CK(launch_wgrad_dots(tt, dtm, reinterpret_cast<float*>(ws + L.gwt), reinterpret_cast<float*>(ws + L.rows), s.Lt, s.P, s.B, s.Nt,
-                         s.Ns, s.Dt, gw, st, L.path == kPathTeacherTokens)));
+    TIMED(13, 3, CK(launch_wgrad_dots(tt, dtm, dtm_lo, reinterpret_cast<float*>(ws + L.gwt), reinterpret_cast<float*>(ws + L.rows), s.Lt, s.P, s.B, s.Nt,
+                         s.Ns, s.Dt, gw, reinterpret_cast<float*>(ws + L.gw_part), st, L.path == kPathTeacherTokens)));
     return 0;
 }
 
@@ -477,7 +501,7 @@ extern "C" int basd_backward_finish(const basd_shape* shape, const basd_inputs* 
     __nv_bfloat16* ghi = reinterpret_cast<__nv_bfloat16*>(ws + L.gam_hi);
     __nv_bfloat16* glo = reinterpret_cast<__nv_bfloat16*>(ws + L.gam_lo);
     float* corr = reinterpret_cast<float*>(ws + L.corr);
-    TIMED(14, 1, CK(launch_selector_bwd(s.Ds, s.Lt, s.P, reinterpret_cast<float*>(ws + L.gw), grad_geo, scale, reinterpret_cast<float*>(ws + L.w),
+    TIMED(14, 2, CK(launch_selector_bwd(s.Ds, s.Lt, s.P, reinterpret_cast<float*>(ws + L.gw), grad_geo, scale, reinterpret_cast<float*>(ws + L.w),
                            reinterpret_cast<float*>(ws + L.d2), in.log_temperatures, reinterpret_cast<float*>(ws + L.gamma),
                            reinterpret_cast<float*>(ws + L.stats), Ms, ghi, glo, corr, grad_log_temperatures, st)));
     const size_t MsL = static_cast<size_t>(s.B) * s.Ns;
@@ -495,7 +519,8 @@ extern "C" int basd_backward_finish(const basd_shape* shape, const basd_inputs* 
 extern "C" int basd_mp_rank_workspace_bytes(int64_t M, int D, size_t* bytes) {
     if (!bytes || M < 1 || D < 8) return fail("invalid argument");
     *bytes = 2 * align_up(2 * static_cast<size_t>(M) * D) + align_up(4 * 2 * (static_cast<size_t>(D) * D + D)) + align_up(4 * 2 * D) +
-             2 * align_up(4 * 2 * static_cast<size_t>(D) * D) + align_up(4 * pooled_eig_scratch_floats(D, 2)) + 4096;
+             2 * align_up(4 * 2 * static_cast<size_t>(D) * D) + align_up(4 * pooled_eig_scratch_floats(D, 2)) +
+             align_up(4 * gemm_gram_part_floats(static_cast<size_t>(M), D, 1)) + 4096;
     return 0;
 }
 
@@ -513,11 +538,12 @@ extern "C" int basd_mp_rank(const void* features, int64_t M, int D, int dtype, i
     float* evk = reinterpret_cast<float*>(ws + off); off += align_up(4 * 2 * static_cast<size_t>(D) * D);
     float* evc = reinterpret_cast<float*>(ws + off); off += align_up(4 * 2 * static_cast<size_t>(D) * D);
     float* eig_scr = reinterpret_cast<float*>(ws + off); off += align_up(4 * pooled_eig_scratch_floats(D, 2));   // the launch runs the MP problem and the centred one
+    float* gram_part = reinterpret_cast<float*>(ws + off); off += align_up(4 * gemm_gram_part_floats(static_cast<size_t>(M), D, 1));
     int* ranks = reinterpret_cast<int*>(ws + off);
     const bool exact = dtype == BASD_DTYPE_BF16;             // fp32 features keep fp32-class precision as a split pair
     CK(launch_pack_bf16(features, exact, 0, row_stride, 1, 1, static_cast<int>(M), D, zb, exact ? nullptr : zl, st));
     CK(cudaMemsetAsync(stats, 0, 4 * 2 * (static_cast<size_t>(D) * D + D), st));
-    CK(gemm_gram(zb, exact ? nullptr : zl, static_cast<size_t>(M), D, stats, st));
+    CK(gemm_gram(zb, exact ? nullptr : zl, static_cast<size_t>(M), D, stats, gram_part, st));
     CK(launch_pooled_eig(stats, D, 1, 0, static_cast<float>(M), 1.f, ranks, evals, evk, evc, nullptr, eig_scr, st));
     CK(cudaMemcpyAsync(rank_out, ranks, sizeof(int), cudaMemcpyDeviceToDevice, st));
     return 0;

@@ -81,14 +81,34 @@ static int make_map_tiled(CUtensorMap* map, const void* ptr, uint64_t rows, uint
     return 0;
 }
 
+// Function attributes and the SM count are per DEVICE: caches are indexed by the current device (a process may drive
+// several GPUs); the flags are only ever set, so concurrent callers at worst repeat an idempotent call.
+constexpr int kMaxDevices = 64;
+static int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev >= 0 && dev < kMaxDevices ? dev : 0;
+}
+static int device_sm_count() {
+    static int sm_count[kMaxDevices] = {0};
+    const int dev = current_device();
+    if (!sm_count[dev]) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        sm_count[dev] = n > 0 ? n : 148;
+    }
+    return sm_count[dev];
+}
+
 template <class Cfg, class Epi>
 static cudaError_t launch(const GemmMaps& maps, const GemmArgs& args, dim3 grid, cudaStream_t st) {
     auto kern = umma_gemm_kernel<Cfg, Epi>;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[kMaxDevices] = {false};
+    const int dev = current_device();
+    if (!configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured[dev] = true;
     }
     kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, st>>>(maps, args);
     return cudaGetLastError();
@@ -133,9 +153,47 @@ cudaError_t gemm_project(const void* const* X, int n_layers, size_t M, int Dt, c
     return cudaSuccess;
 }
 
-// G[batch] += Z[batch]^T Z[batch]; Z = [batches][M][Ds] contiguous (optionally a split hi/lo pair); G batch stride in floats.
+// out[b][e] = sum over the n_splits slices of part[(b * n_splits + s) * elems + e], s ascending: fixed order
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ part, int n_splits, int elems4, float* __restrict__ out, long long out_stride) {
+    const int b = blockIdx.y;
+    const float4* p = reinterpret_cast<const float4*>(part) + static_cast<size_t>(b) * n_splits * elems4;
+    float4* o = reinterpret_cast<float4*>(out + b * out_stride);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < elems4; e += gridDim.x * blockDim.x) {
+        float4 acc = p[e];
+        for (int s2 = 1; s2 < n_splits; ++s2) {
+            const float4 v = p[static_cast<size_t>(s2) * elems4 + e];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        o[e] = acc;
+    }
+}
+// split-K geometry of a Gram over M rows: at most 32 slices of at least 32 k-blocks
+static void gram_splits(size_t M, int* kb_total, int* kb_per_split, int* n_splits) {
+    *kb_total = cdiv(M, GEMM_BK);
+    int per = 32;
+    if (cdiv(*kb_total, per) > 32) per = cdiv(*kb_total, 32);
+    *kb_per_split = per;
+    *n_splits = cdiv(*kb_total, per);
+}
+size_t gemm_gram_part_floats(size_t M, int Ds, int batches) {
+    int kt, kp, ns;
+    gram_splits(M, &kt, &kp, &ns);
+    return static_cast<size_t>(ns) * batches * Ds * Ds;
+}
+static cudaError_t gram_reduce(const float* part, int n_splits, int Ds, int batches, float* G, long long g_stride, cudaStream_t st) {
+    if ((Ds * Ds) % 4 || (g_stride % 4)) return cudaErrorInvalidValue;
+    const int elems4 = Ds * Ds / 4;
+    int gx = (elems4 + 255) / 256;
+    if (gx > 64) gx = 64;
+    splitk_reduce_kernel<<<dim3(gx, batches), 256, 0, st>>>(part, n_splits, elems4, G, g_stride);
+    return cudaGetLastError();
+}
+
+// G[batch] = Z[batch]^T Z[batch]; Z = [batches][M][Ds] contiguous (optionally a split hi/lo pair); G batch stride in floats.
+// part: gemm_gram_part_floats(M, Ds, batches) floats of scratch for the split-K slices.
 static cudaError_t gram_impl(const __nv_bfloat16* Z, const __nv_bfloat16* Zlo, size_t M, int Ds, int batches, float* G, long long g_stride,
-                             cudaStream_t st) {
+                             float* part, cudaStream_t st) {
     GemmMaps maps;
     memset(&maps, 0, sizeof maps);
     if (make_map(&maps.a[0], Z, Ds, M, batches, Ds, M * Ds, 64)) return cudaErrorInvalidValue;
@@ -146,22 +204,23 @@ static cudaError_t gram_impl(const __nv_bfloat16* Z, const __nv_bfloat16* Zlo, s
     }
     GemmArgs a;
     memset(&a, 0, sizeof a);
-    a.kb_total = cdiv(M, GEMM_BK);
-    a.kb_per_split = 32;
-    a.n_splits = cdiv(a.kb_total, a.kb_per_split);
+    gram_splits(M, &a.kb_total, &a.kb_per_split, &a.n_splits);
     a.a_batched = 1; a.b_batched = 1;
-    a.out = G; a.out_batch_stride = g_stride; a.ld_out = Ds; a.rows_valid = Ds; a.cols_valid = Ds;
+    a.out = part; a.out_batch_stride = static_cast<long long>(Ds) * Ds; a.ld_out = Ds; a.rows_valid = Ds; a.cols_valid = Ds;
     const dim3 grid(cdiv(Ds, CfgGram::kBN), cdiv(Ds, CfgGram::kMT * 128), batches * a.n_splits);
     const bool alias = Ds <= CfgGram::kBN;                    // a single output tile: A tile == B tile
-    if (Zlo) return alias ? launch<CfgGram3A, EpiAtomicAddF32>(maps, a, grid, st) : launch<CfgGram3, EpiAtomicAddF32>(maps, a, grid, st);
-    return alias ? launch<CfgGramA, EpiAtomicAddF32>(maps, a, grid, st) : launch<CfgGram, EpiAtomicAddF32>(maps, a, grid, st);
+    cudaError_t e;
+    if (Zlo) e = alias ? launch<CfgGram3A, EpiStoreSplitK>(maps, a, grid, st) : launch<CfgGram3, EpiStoreSplitK>(maps, a, grid, st);
+    else e = alias ? launch<CfgGramA, EpiStoreSplitK>(maps, a, grid, st) : launch<CfgGram, EpiStoreSplitK>(maps, a, grid, st);
+    if (e != cudaSuccess) return e;
+    return gram_reduce(part, a.n_splits, Ds, batches, G, g_stride, st);
 }
-cudaError_t gemm_gram(const __nv_bfloat16* Z, const __nv_bfloat16* Zlo, size_t M, int Ds, float* G, cudaStream_t st) {
-    return gram_impl(Z, Zlo, M, Ds, 1, G, 0, st);
+cudaError_t gemm_gram(const __nv_bfloat16* Z, const __nv_bfloat16* Zlo, size_t M, int Ds, float* G, float* part, cudaStream_t st) {
+    return gram_impl(Z, Zlo, M, Ds, 1, G, 0, part, st);
 }
 // G[i] += S_i^T S_i for n separate [M][Ds] bf16 tensors in ONE launch (blockIdx.z = tensor x split; a single Gram is 25
 // CTAs - four of them back to back were 4 x 50 us of latency)
-cudaError_t gemm_gram_table(const void* const* S, int n, size_t M, int Ds, float* G, long long g_stride, cudaStream_t st) {
+cudaError_t gemm_gram_table(const void* const* S, int n, size_t M, int Ds, float* G, long long g_stride, float* part, cudaStream_t st) {
     if (n > GEMM_MAX_A_TABLE) return cudaErrorInvalidValue;
     GemmMaps maps;
     memset(&maps, 0, sizeof maps);
@@ -169,17 +228,17 @@ cudaError_t gemm_gram_table(const void* const* S, int n, size_t M, int Ds, float
         if (make_map(&maps.a_table[i], S[i], Ds, M, 1, Ds, M * Ds, 64)) return cudaErrorInvalidValue;
     GemmArgs a;
     memset(&a, 0, sizeof a);
-    a.kb_total = cdiv(M, GEMM_BK);
-    a.kb_per_split = 32;
-    a.n_splits = cdiv(a.kb_total, a.kb_per_split);
+    gram_splits(M, &a.kb_total, &a.kb_per_split, &a.n_splits);
     a.a_table = 1; a.b_table = 1;
-    a.out = G; a.out_batch_stride = g_stride; a.ld_out = Ds; a.rows_valid = Ds; a.cols_valid = Ds;
+    a.out = part; a.out_batch_stride = static_cast<long long>(Ds) * Ds; a.ld_out = Ds; a.rows_valid = Ds; a.cols_valid = Ds;
     const dim3 grid(cdiv(Ds, CfgGram::kBN), cdiv(Ds, CfgGram::kMT * 128), n * a.n_splits);
-    return Ds <= CfgGram::kBN ? launch<CfgGramA, EpiAtomicAddF32>(maps, a, grid, st) : launch<CfgGram, EpiAtomicAddF32>(maps, a, grid, st);
+    cudaError_t e = Ds <= CfgGram::kBN ? launch<CfgGramA, EpiStoreSplitK>(maps, a, grid, st) : launch<CfgGram, EpiStoreSplitK>(maps, a, grid, st);
+    if (e != cudaSuccess) return e;
+    return gram_reduce(part, a.n_splits, Ds, n, G, g_stride, st);
 }
 cudaError_t gemm_gram_batched(const __nv_bfloat16* Z, const __nv_bfloat16* Zlo, size_t M, int Ds, int batches, float* G, long long g_stride,
-                              cudaStream_t st) {
-    return gram_impl(Z, Zlo, M, Ds, batches, G, g_stride, st);
+                              float* part, cudaStream_t st) {
+    return gram_impl(Z, Zlo, M, Ds, batches, G, g_stride, part, st);
 }
 
 template <int BN>
@@ -218,7 +277,7 @@ cudaError_t gemm_token_gram(const __nv_bfloat16* Thi, const __nv_bfloat16* Tlo, 
 }
 
 cudaError_t gemm_theta_apply(const __nv_bfloat16* theta, const __nv_bfloat16* theta_lo, int NsPad, const __nv_bfloat16* Thi,
-                             const __nv_bfloat16* Tlo, int batches, int Ns, int Dt, __nv_bfloat16* Dtm, cudaStream_t st) {
+                             const __nv_bfloat16* Tlo, int batches, int Ns, int Dt, __nv_bfloat16* Dtm, __nv_bfloat16* Dtm_lo, cudaStream_t st) {
     GemmMaps maps;
     memset(&maps, 0, sizeof maps);
     // inner extent Ns (not NsPad): the pad columns are never read, TMA zero-fills them
@@ -230,8 +289,12 @@ cudaError_t gemm_theta_apply(const __nv_bfloat16* theta, const __nv_bfloat16* th
     memset(&a, 0, sizeof a);
     a.kb_total = cdiv(Ns, GEMM_BK);
     a.a_batched = 1; a.b_batched = 1;
-    a.out = Dtm; a.out_batch_stride = static_cast<long long>(Ns) * Dt; a.ld_out = Dt; a.rows_valid = Ns; a.cols_valid = Dt; a.alpha = 1.f;
-    return launch<CfgTheta3, EpiStoreBf16>(maps, a, dim3(cdiv(Dt, CfgTheta3::kBN), cdiv(Ns, CfgTheta3::kMT * 128), batches), st);
+    // the gradient w.r.t. the mixed teacher leaves as a split pair: rounded to one bf16 it cost 1e-4 .. 6e-4 on the
+    // temperature gradients (they are differences of nearly equal per-layer dots of this tensor)
+    // (Dtm_lo == nullptr: large tensors, where the rounding averages out, leave as one bf16)
+    a.out = Dtm; a.aux0 = Dtm_lo; a.out_batch_stride = static_cast<long long>(Ns) * Dt; a.ld_out = Dt; a.rows_valid = Ns; a.cols_valid = Dt; a.alpha = 1.f;
+    if (!Dtm_lo) return launch<CfgTheta3, EpiStoreBf16>(maps, a, dim3(cdiv(Dt, CfgTheta3::kBN), cdiv(Ns, CfgTheta3::kMT * 128), batches), st);
+    return launch<CfgTheta3, EpiStoreSplit>(maps, a, dim3(cdiv(Dt, CfgTheta3::kBN), cdiv(Ns, CfgTheta3::kMT * 128), batches), st);
 }
 
 cudaError_t gemm_student_grad(const __nv_bfloat16* S, size_t M, int Ds, const __nv_bfloat16* Ghi, const __nv_bfloat16* Glo,
@@ -275,6 +338,10 @@ cudaError_t polar_gemm(bool b_mn, const SplitMat& A, const SplitMat& B, int batc
     }
     a.n_items = batches * a.n_mt * a.n_nt;
     a.n_batches = batches;
+    if ((a.trace && 4 * a.n_mt * a.n_nt > a.fro_slots) || (a.norm2 && a.fro_slots < 1)) {
+        snprintf(g_gemm_err, sizeof g_gemm_err, "polar_gemm: %d partial-trace slots for %d x %d tiles", a.fro_slots, a.n_mt, a.n_nt);
+        return cudaErrorInvalidValue;
+    }
     a.b_groups = (a.bn_mma + 63) / 64;
     PolarGemmMaps maps;
     memset(&maps, 0, sizeof maps);
@@ -321,19 +388,14 @@ cudaError_t polar_gemm(bool b_mn, const SplitMat& A, const SplitMat& B, int batc
         {polar_gemm_kernel<false, 0>, polar_gemm_kernel<false, 1>, polar_gemm_kernel<false, 2>, polar_gemm_kernel<false, 3>},
         {polar_gemm_kernel<true, 0>, polar_gemm_kernel<true, 1>, polar_gemm_kernel<true, 2>, polar_gemm_kernel<true, 3>}};
     const Kern kern = kerns[b_mn][kind];
-    static bool configured[2][4] = {{false, false, false, false}, {false, false, false, false}};
-    static int sm_count = 0;
-    if (!configured[b_mn][kind]) {
+    static bool configured[kMaxDevices][2][4] = {};
+    const int dev = current_device();
+    if (!configured[dev][b_mn][kind]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         if (e != cudaSuccess) return e;
-        configured[b_mn][kind] = true;
+        configured[dev][b_mn][kind] = true;
     }
-    if (!sm_count) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-        if (sm_count <= 0) sm_count = 148;
-    }
+    const int sm_count = device_sm_count();
     const int grid = a.n_items < sm_count ? a.n_items : sm_count;
     kern<<<grid, PG_THREADS, smem, st>>>(maps, a);
     return cudaGetLastError();
@@ -372,17 +434,14 @@ cudaError_t polar_fused_abm(const SplitMat& T, const SplitMat& W, const SplitMat
         snprintf(g_gemm_err, sizeof g_gemm_err, "polar_fused_abm: %d B of shared memory needed", smem);
         return cudaErrorInvalidValue;
     }
-    static bool configured = false;
-    static int sm_count = 0;
-    if (!configured) {
+    static bool configured[kMaxDevices] = {false};
+    const int dev = current_device();
+    if (!configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(polar_fused_abm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         if (e != cudaSuccess) return e;
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-        if (sm_count <= 0) sm_count = 148;
-        configured = true;
+        configured[dev] = true;
     }
+    const int sm_count = device_sm_count();
     const int grid = batches < sm_count ? batches : sm_count;
     polar_fused_abm_kernel<<<grid, PF_THREADS, smem, st>>>(maps, a);
     return cudaGetLastError();

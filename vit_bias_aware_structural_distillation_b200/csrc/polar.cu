@@ -23,7 +23,7 @@ namespace basd {
 
 namespace {
 
-constexpr int kPolarSteps = 10;
+constexpr int kPolarSteps = kPolarStepsDefault;      // rows of the schedule below
 constexpr int kPolarChunk = 0;            // problems per launch of the product chain (0 = all); BASD_POLAR_CHUNK overrides
 // minimax odd quintics on [l_k, 1.03] (l_0 = 3e-5), each rescaled to a maximum of 1: tools/ns_schedule.py 3e-5 10 1.03
 // l_k: 3.0e-5 1.0e-4 4.2e-4 1.7e-3 7.1e-3 2.9e-2 0.118 0.42 0.906 0.99967 -> 0.999996
@@ -39,6 +39,14 @@ const float kPolarCoef[kPolarSteps][3] = {
     {1.941173422f, -1.383242341f, 0.441739912f},
     {1.847826056f, -1.196240433f, 0.348410606f},
 };
+
+// Coefficients of step k out of `steps` (>= kPolarSteps): extra steps run FIRST with the l -> 0 limit polynomial (row 0 is
+// within 1e-4 of it), each one lowering the floor l_0 by the polynomial's slope at zero (~4.13): 12 steps reach
+// singular values of 2e-6 ||C||_F, 16 steps 6e-9 (below split-bf16 resolution).
+__host__ inline const float* polar_coef(int k, int steps) {
+    const int idx = k - (steps - kPolarSteps);
+    return kPolarCoef[idx < 0 ? 0 : idx];
+}
 
 // ------------------------------------------------------------------------------------------------
 // prep_student: s_w = sqrt(a) (s - mu_s)  ->  SW [N][Ds] (split), W_0 = s_w^T [Ds][Np] (split), ksd, tr_s
@@ -433,7 +441,14 @@ polar_finish_kernel(PolarArgs g) {
         g.loss_b[prob] = tr_s + tr_t - 2.f * nuc;
         if (g.dbg) {
             g.dbg[prob * 5 + 0] = nuc; g.dbg[prob * 5 + 1] = tr_s; g.dbg[prob * 5 + 2] = tr_t;
-            g.dbg[prob * 5 + 3] = static_cast<float>(kPolarSteps); g.dbg[prob * 5 + 4] = g.fro2[prob];
+            float fro = 0.f, rs = 0.f;
+            for (int sl = 0; sl < g.fro_slots; ++sl) {
+                fro += g.fro2[static_cast<size_t>(prob) * g.fro_slots + sl];
+                rs += g.resid[static_cast<size_t>(prob) * g.fro_slots + sl];
+            }
+            // convergence evidence: ||X X^T - I||_F going INTO the last step (every |sigma^2 - 1| is below it; <= 0.1 means the
+            // last polynomial leaves every singular value within 1e-3 of 1); NaN-safe: a NaN residual stays NaN
+            g.dbg[prob * 5 + 3] = sqrtf(rs); g.dbg[prob * 5 + 4] = fro;
         }
     }
 }
@@ -510,12 +525,16 @@ vt_prep_teacher_kernel(PolarArgs g) {
     for (int wv = 0; wv < nw; ++wv) dmax = fmaxf(dmax, red[wv]);
     __syncthreads();
     cta_cholesky_lower(K, ld, M, &s_bad, 1e-6f * dmax);   // K = G (lower), strict upper triangle zeroed
-    // ebar = E^T a
-    for (int n = threadIdx.x; n < N; n += blockDim.x) {
-        int i0, i1; float lam;
-        interp_index(n, M, N, i0, i1, lam);
-        atomicAdd(&ebar[i0], a_s[n] * (1.f - lam));
-        if (lam != 0.f) atomicAdd(&ebar[i1], a_s[n] * lam);
+    // ebar = E^T a   (one thread per teacher token walks the student tokens in order: no atomics, bitwise repeatable)
+    for (int m = threadIdx.x; m < M; m += blockDim.x) {
+        float sacc = 0.f;
+        for (int n = 0; n < N; ++n) {
+            int i0, i1; float lam;
+            interp_index(n, M, N, i0, i1, lam);
+            if (i0 == m) sacc = fmaf(a_s[n], 1.f - lam, sacc);
+            if (i1 == m && lam != 0.f) sacc = fmaf(a_s[n], lam, sacc);
+        }
+        ebar[m] = sacc;
     }
     __syncthreads();
     // eg[m] = sum_m' ebar[m'] G[m'][m];  z^[m] = sum_m' G[m'][m] / sqrt(M c_r)   (column m of G = K[m * ld + .])
@@ -583,16 +602,22 @@ vt_prep_teacher_kernel(PolarArgs g) {
     float* ftf = g.ftf + static_cast<size_t>(prob) * M * M;
     for (int t = threadIdx.x; t < M * M; t += blockDim.x) ftf[t] = -ebar[t / M] * ebar[t % M];
     __syncthreads();
-    for (int n = threadIdx.x; n < N; n += blockDim.x) {
-        int i0, i1; float lam;
-        interp_index(n, M, N, i0, i1, lam);
-        const float w0 = 1.f - lam, a = a_s[n];
-        atomicAdd(&ftf[i0 * M + i0], a * w0 * w0);
-        if (lam != 0.f) {
-            atomicAdd(&ftf[i0 * M + i1], a * w0 * lam);
-            atomicAdd(&ftf[i1 * M + i0], a * w0 * lam);
-            atomicAdd(&ftf[i1 * M + i1], a * lam * lam);
+    // E^T diag(a) E is tridiagonal (two taps per student token): thread u owns (u, u) and (u, u + 1) = (u + 1, u)
+    for (int u = threadIdx.x; u < M; u += blockDim.x) {
+        float d0 = 0.f, d1 = 0.f;
+        for (int n = 0; n < N; ++n) {
+            int i0, i1; float lam;
+            interp_index(n, M, N, i0, i1, lam);
+            const float w0 = 1.f - lam, a = a_s[n];
+            if (i0 == u) d0 = fmaf(a, w0 * w0, d0);
+            if (lam != 0.f) {
+                if (i1 == u) d0 = fmaf(a, lam * lam, d0);
+                if (i0 == u && i1 == u + 1) d1 = fmaf(a, w0 * lam, d1);
+                if (i0 == u && i1 == u) d0 = fmaf(a, 2.f * w0 * lam, d0);
+            }
         }
+        ftf[u * M + u] += d0;
+        if (u + 1 < M) { ftf[u * M + u + 1] += d1; ftf[(u + 1) * M + u] += d1; }
     }
     // G^-1 (forward substitution, one thread per column, column-major fp32 in global memory), then its two operand forms
     float* ginv = g.ginv + static_cast<size_t>(prob) * M * M;
@@ -678,14 +703,25 @@ vt_theta_kernel(PolarArgs g) {
 }  // namespace
 
 int polar_steps() { return kPolarSteps; }
-static bool polar_use_fused(int D, int N) {      // BASD_POLAR_FUSED=0: keep G2 and G3 as two launches (development knob)
-    static int fused_cfg = -1;
-    if (fused_cfg < 0) {
-        const char* e = getenv("BASD_POLAR_FUSED");
-        fused_cfg = e ? atoi(e) : 1;
-    }
-    return fused_cfg != 0 && polar_fused_supported(D, N);
+// slots for the per-warp partial traces of the first A product: 4 epilogue warps x row tiles x column tiles (column
+// tiles are at least 128 wide); rounded up to a multiple of 8
+int polar_fro_slots(int core) {
+    const int t = (core + 127) / 128;
+    return (4 * t * t + 7) & ~7;
 }
+// Development knobs, read ONCE per process (C++11 thread-safe static initialisation), never on the launch path:
+//   BASD_POLAR_FUSED=0  keep G2 and G3 as two launches      BASD_POLAR_CHUNK=n  problems per launch chain
+//   BASD_POLAR_DBG=1    record the phase clocks of one launch per product (tools/gpu_debug_clocks.py)
+struct PolarKnobs {
+    int fused, chunk, dbg;
+    PolarKnobs() {
+        const char* e = getenv("BASD_POLAR_FUSED"); fused = e ? atoi(e) : 1;
+        e = getenv("BASD_POLAR_CHUNK"); chunk = e ? atoi(e) : kPolarChunk;
+        dbg = getenv("BASD_POLAR_DBG") ? 1 : 0;
+    }
+};
+static const PolarKnobs& polar_knobs() { static const PolarKnobs k; return k; }
+static bool polar_use_fused(int D, int N) { return polar_knobs().fused != 0 && polar_fused_supported(D, N); }
 int polar_launches_per_step(int Ds, int Ns) { return polar_use_fused(Ds, Ns) ? 3 : 4; }
 
 __device__ long long g_polar_dbg[4][16 * 8];
@@ -719,22 +755,21 @@ cudaError_t launch_polar_procrustes(const PolarArgs& g, cudaStream_t st, int* la
         PCK(cudaGetLastError());
         count += 2;
     }
-    float* fro2_dense = g.fro2;                // ||C||_F^2 per problem, accumulated by the first A = T W^T
-    PCK(cudaMemsetAsync(fro2_dense, 0, sizeof(float) * nprob, st));
+    float* fro2_dense = g.fro2;                // partial traces of the first A = T W^T per problem (their sum = ||C||_F^2)
+    PCK(cudaMemsetAsync(fro2_dense, 0, sizeof(float) * nprob * g.fro_slots, st));
 
     // The chain of products is sequentially dependent per problem but every launch batches many problems.  Problems are
     // walked in chunks small enough for a chunk's matrices (~0.8 MB live per problem) to stay in the 126 MB L2 from one
     // launch to the next; one chunk = one full Newton-Schulz run.  chunk = 0: all problems per launch (HBM streaming).
-    static int chunk_cfg = -1;
-    if (chunk_cfg < 0) {
-        const char* e = getenv("BASD_POLAR_CHUNK");
-        chunk_cfg = e ? atoi(e) : kPolarChunk;
-    }
+    const int chunk_cfg = polar_knobs().chunk;
+    const bool dbg_clocks = polar_knobs().dbg != 0;
     const int chunk = (chunk_cfg <= 0 || chunk_cfg > nprob) ? nprob : chunk_cfg;
     const int n_chunks = (nprob + chunk - 1) / chunk;
     const bool fused = polar_use_fused(D, N);
     auto at = [](const SplitMat& m, int z0) { SplitMat r = m; r.hi += z0 * m.batch_stride; r.lo += z0 * m.batch_stride; return r; };
-    TimingScope* gemm_scope = new TimingScope(kSlotPolarGemm, st, n_chunks * ((fused ? 3 : 4) * kPolarSteps + 2));
+    const int steps = g.steps >= kPolarSteps && g.steps <= kPolarStepsMax ? g.steps : kPolarSteps;
+    PCK(cudaMemsetAsync(g.resid, 0, sizeof(float) * nprob * g.fro_slots, st));
+    TimingScope* gemm_scope = new TimingScope(kSlotPolarGemm, st, n_chunks * ((fused ? 3 : 4) * steps + 2));
     struct Del { TimingScope*& p; ~Del() { delete p; } } gemm_del{gemm_scope};
     for (int z0 = 0; z0 < nprob; z0 += chunk) {
         const int nz = nprob - z0 < chunk ? nprob - z0 : chunk;
@@ -742,17 +777,19 @@ cudaError_t launch_polar_procrustes(const PolarArgs& g, cudaStream_t st, int* la
         // A product) enters the later epilogues of that step as a per-problem scalar.
         SplitMat Wc = at(g.W, z0), Wn = at(g.W2, z0);
         const SplitMat T = at(g.T, z0), A = at(g.A, z0), Bm = at(g.Bm, z0), Kt = at(g.Kt, z0), SW = at(g.SW, z0);
-        float* fro2 = fro2_dense + z0;
+        float* fro2 = fro2_dense + static_cast<size_t>(z0) * g.fro_slots;
         int dir = 0;                           // alternate the problem order launch by launch (L2 reuse of the previous output)
-        for (int k = 0; k < kPolarSteps; ++k) {
-            const float ca = kPolarCoef[k][0], cb = kPolarCoef[k][1], cc = kPolarCoef[k][2];
-            const bool first = k == 0;
+        float* resid = g.resid + static_cast<size_t>(z0) * g.fro_slots;
+        for (int k = 0; k < steps; ++k) {
+            const float* coef = polar_coef(k, steps);
+            const float ca = coef[0], cb = coef[1], cc = coef[2];
+            const bool first = k == 0, last = k == steps - 1;
             const float* norm = first ? fro2 : nullptr;
             PolarGemmArgs a;
             // G1: T = W K_t
             memset(&a, 0, sizeof a);
             a.epi = PG_EPI_SPLIT; a.out_hi = T.hi; a.out_lo = T.lo; a.out_stride = T.batch_stride; a.scale_c = 1.f;
-            if (k == 3 && z0 == 0 && getenv("BASD_POLAR_DBG")) a.dbg_clock = polar_dbg_ptr(0);
+            if (k == 3 && z0 == 0 && dbg_clocks) a.dbg_clock = polar_dbg_ptr(0);
             a.reverse = (dir++) & 1;
             PCK(polar_gemm(false, Wc, Kt, nz, a, st));
             if (fused) {
@@ -760,8 +797,9 @@ cudaError_t launch_polar_procrustes(const PolarArgs& g, cudaStream_t st, int* la
                 // (step 0: trace(A) = ||C||_F^2 is reduced inside and written to fro2 for G4's epilogue)
                 PolarFusedArgs f;
                 memset(&f, 0, sizeof f);
-                f.ca = ca; f.cb = cb; f.cc = cc; f.first = first ? 1 : 0; f.fro2 = fro2;
-                if (k == 3 && z0 == 0 && getenv("BASD_POLAR_DBG")) f.dbg_clock = polar_dbg_ptr(1);
+                f.ca = ca; f.cb = cb; f.cc = cc; f.first = first ? 1 : 0; f.fro2 = fro2; f.fro_slots = g.fro_slots;
+                f.resid = last ? resid : nullptr;
+                if (k == 3 && z0 == 0 && dbg_clocks) f.dbg_clock = polar_dbg_ptr(1);
                 f.reverse = (dir++) & 1;
                 PCK(polar_fused_abm(T, Wc, Bm, nz, f, st));
                 count -= 1;
@@ -769,8 +807,8 @@ cudaError_t launch_polar_procrustes(const PolarArgs& g, cudaStream_t st, int* la
                 // G2: A = T W^T                (step 0: trace(A) = ||C||_F^2, read by the epilogues of G3 / G4 of that step)
                 memset(&a, 0, sizeof a);
                 a.epi = PG_EPI_SPLIT; a.out_hi = A.hi; a.out_lo = A.lo; a.out_stride = A.batch_stride; a.scale_c = 1.f;
-                if (first) a.trace = fro2;
-                if (k == 3 && z0 == 0 && getenv("BASD_POLAR_DBG")) a.dbg_clock = polar_dbg_ptr(1);
+                if (first) { a.trace = fro2; a.fro_slots = g.fro_slots; }
+                if (k == 3 && z0 == 0 && dbg_clocks) a.dbg_clock = polar_dbg_ptr(1);
                 a.reverse = (dir++) & 1;
                 PCK(polar_gemm(false, T, Wc, nz, a, st));
                 // G3: Bm = a I + b (rA) + c (rA)^2   (A is both operands: the A tile aliases the B tile; the b A term is added from
@@ -778,16 +816,17 @@ cudaError_t launch_polar_procrustes(const PolarArgs& g, cudaStream_t st, int* la
                 memset(&a, 0, sizeof a);
                 a.epi = PG_EPI_SPLIT; a.out_hi = Bm.hi; a.out_lo = Bm.lo; a.out_stride = Bm.batch_stride;
                 a.a_alias_b = 1; a.aux_mode = 1; a.aux_hi = A.hi; a.aux_lo = A.lo;
-                a.aux_c = cb; a.aux_p = first ? 1.f : 0.f; a.scale_c = cc; a.scale_p = first ? 2.f : 0.f; a.diag_add = ca; a.norm2 = norm;
-                if (k == 3 && z0 == 0 && getenv("BASD_POLAR_DBG")) a.dbg_clock = polar_dbg_ptr(2);
+                a.aux_c = cb; a.aux_p = first ? 1.f : 0.f; a.scale_c = cc; a.scale_p = first ? 2.f : 0.f; a.diag_add = ca; a.norm2 = norm; a.fro_slots = g.fro_slots;
+                a.resid = last ? resid : nullptr;
+                if (k == 3 && z0 == 0 && dbg_clocks) a.dbg_clock = polar_dbg_ptr(2);
                 a.reverse = (dir++) & 1;
                 PCK(polar_gemm(false, A, A, nz, a, st));
             }
             // G4: W_next = sqrt(r) Bm W      (W enters as the MN-major B operand; ping-pong buffers)
             memset(&a, 0, sizeof a);
             a.epi = PG_EPI_SPLIT; a.out_hi = Wn.hi; a.out_lo = Wn.lo; a.out_stride = Wn.batch_stride;
-            a.scale_c = 1.f; a.scale_p = first ? 0.5f : 0.f; a.norm2 = norm;
-            if (k == 3 && z0 == 0 && getenv("BASD_POLAR_DBG")) a.dbg_clock = polar_dbg_ptr(3);
+            a.scale_c = 1.f; a.scale_p = first ? 0.5f : 0.f; a.norm2 = norm; a.fro_slots = g.fro_slots;
+            if (k == 3 && z0 == 0 && dbg_clocks) a.dbg_clock = polar_dbg_ptr(3);
             a.reverse = (dir++) & 1;
             PCK(polar_gemm(true, Bm, Wc, nz, a, st));
             const SplitMat tmp = Wc; Wc = Wn; Wn = tmp;
@@ -844,8 +883,10 @@ cudaError_t launch_polar_procrustes_vt(const PolarArgs& g, cudaStream_t st, int*
         PCK(cudaGetLastError());
         count += 2;
     }
-    PCK(cudaMemsetAsync(g.fro2, 0, sizeof(float) * nprob, st));
-    TimingScope* gemm_scope = new TimingScope(kSlotPolarGemm, st, 3 * kPolarSteps + 7);
+    const int steps = g.steps >= kPolarSteps && g.steps <= kPolarStepsMax ? g.steps : kPolarSteps;
+    PCK(cudaMemsetAsync(g.fro2, 0, sizeof(float) * nprob * g.fro_slots, st));
+    PCK(cudaMemsetAsync(g.resid, 0, sizeof(float) * nprob * g.fro_slots, st));
+    TimingScope* gemm_scope = new TimingScope(kSlotPolarGemm, st, 3 * steps + 7);
     struct Del { TimingScope*& p; ~Del() { delete p; } } gemm_del{gemm_scope};
     PolarGemmArgs a;
     // X_0 = (F G)^T s_w   [Nt][Ds]  (s_w enters as the MN-major operand), then the augmentation column
@@ -857,28 +898,30 @@ cudaError_t launch_polar_procrustes_vt(const PolarArgs& g, cudaStream_t st, int*
     count += 2;
     SplitMat Xc = g.X0, Xn = g.X1;
     int dir = 0;
-    for (int k = 0; k < kPolarSteps; ++k) {
-        const float ca = kPolarCoef[k][0], cb = kPolarCoef[k][1], cc = kPolarCoef[k][2];
-        const bool first = k == 0;
+    for (int k = 0; k < steps; ++k) {
+        const float* coef = polar_coef(k, steps);
+        const float ca = coef[0], cb = coef[1], cc = coef[2];
+        const bool first = k == 0, last = k == steps - 1;
         const float* norm = first ? g.fro2 : nullptr;
         // A = X X^T   (step 0: trace(A) = ||X_0^+||_F^2)
         memset(&a, 0, sizeof a);
         a.epi = PG_EPI_SPLIT; a.out_hi = g.A.hi; a.out_lo = g.A.lo; a.out_stride = g.A.batch_stride; a.scale_c = 1.f;
         a.a_alias_b = 1;
-        if (first) a.trace = g.fro2;
+        if (first) { a.trace = g.fro2; a.fro_slots = g.fro_slots; }
         a.reverse = (dir++) & 1;
         PCK(polar_gemm(false, Xc, Xc, nprob, a, st));
         // Bm = a I + b (rA) + c (rA)^2
         memset(&a, 0, sizeof a);
         a.epi = PG_EPI_SPLIT; a.out_hi = g.Bm.hi; a.out_lo = g.Bm.lo; a.out_stride = g.Bm.batch_stride;
         a.a_alias_b = 1; a.aux_mode = 1; a.aux_hi = g.A.hi; a.aux_lo = g.A.lo;
-        a.aux_c = cb; a.aux_p = first ? 1.f : 0.f; a.scale_c = cc; a.scale_p = first ? 2.f : 0.f; a.diag_add = ca; a.norm2 = norm;
+        a.aux_c = cb; a.aux_p = first ? 1.f : 0.f; a.scale_c = cc; a.scale_p = first ? 2.f : 0.f; a.diag_add = ca; a.norm2 = norm; a.fro_slots = g.fro_slots;
+        a.resid = last ? g.resid : nullptr;
         a.reverse = (dir++) & 1;
         PCK(polar_gemm(false, g.A, g.A, nprob, a, st));
         // X_next = sqrt(r) Bm X
         memset(&a, 0, sizeof a);
         a.epi = PG_EPI_SPLIT; a.out_hi = Xn.hi; a.out_lo = Xn.lo; a.out_stride = Xn.batch_stride;
-        a.scale_c = 1.f; a.scale_p = first ? 0.5f : 0.f; a.norm2 = norm;
+        a.scale_c = 1.f; a.scale_p = first ? 0.5f : 0.f; a.norm2 = norm; a.fro_slots = g.fro_slots;
         a.reverse = (dir++) & 1;
         PCK(polar_gemm(true, g.Bm, Xc, nprob, a, st));
         Xc = Xn;

@@ -75,7 +75,7 @@ polar_fused_abm_kernel(const __grid_constant__ PolarFusedMaps maps, const PolarF
     uint64_t* p2done_bar = acc2_bar + 1;                       // phase 2 retired: the ring memory is free again
     uint64_t* tmem_empty_bar = p2done_bar + 1;                 // accumulators drained (4 n_mt warps)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 1);
-    float* trace_s = reinterpret_cast<float*>(tmem_slot + 2);  // [2]
+    float* trace_s = reinterpret_cast<float*>(tmem_slot + 2);  // [2][8]: per item parity, one slot per epilogue warp
     uint8_t* staging = smem + ring_bytes + 1024;               // 8 warps x (hi 2 KB + lo 2 KB)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -84,7 +84,6 @@ polar_fused_abm_kernel(const __grid_constant__ PolarFusedMaps maps, const PolarF
         mbar_init(acc1_bar, 1); mbar_init(acc2_bar, 1); mbar_init(p2done_bar, 1);
         for (int i = 0; i < 4; ++i) mbar_init(&copy_bar[i], 4 * args.n_mt);
         mbar_init(tmem_empty_bar, 4 * args.n_mt);
-        trace_s[0] = 0.f; trace_s[1] = 0.f;
         fence_mbar_init();
         tma_prefetch_desc(&maps.t[0]); tma_prefetch_desc(&maps.t[1]);
         tma_prefetch_desc(&maps.w[0]); tma_prefetch_desc(&maps.w[1]);
@@ -212,14 +211,17 @@ polar_fused_abm_kernel(const __grid_constant__ PolarFusedMaps maps, const PolarF
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) tr += __shfl_xor_sync(0xffffffffu, tr, o);
-                if (lane == 0) atomicAdd(&trace_s[ph_item], tr);
+                if (lane == 0) trace_s[ph_item * 8 + e] = tr;           // stored per warp, summed in order: bitwise repeatable
                 asm volatile("bar.sync 2, %0;" ::"r"(n_epi_threads) : "memory");
-                const float trace = trace_s[ph_item];
-                r = 1.f / trace;
-                if (e == 0 && lane == 0) { args.fro2[z] = trace; trace_s[ph_item ^ 1] = 0.f; }
+                float trace = 0.f;
+#pragma unroll
+                for (int e2 = 0; e2 < 8; ++e2) trace += e2 * 32 < n_epi_threads ? trace_s[ph_item * 8 + e2] : 0.f;
+                r = trace > 0.f ? 1.f / trace : 0.f;
+                if (e == 0 && lane == 0) args.fro2[static_cast<long long>(z) * args.fro_slots] = trace;
             }
             // ---- copy: A~ = s A as a split pair, K-major SWIZZLE_128B operand layout [half][64-column block][row]
             const float s_copy = sqrtf(args.cc * r / fabsf(args.cb));
+            float rs_part = 0.f;                                  // last step: this warp's share of ||A - I||_F^2
             for (int cbk = 0; cbk < n_kb2; ++cbk) {
                 if (row0 < args.rows_ld) {
                     float vb[64];
@@ -236,6 +238,14 @@ polar_fused_abm_kernel(const __grid_constant__ PolarFusedMaps maps, const PolarF
                     for (int jc = 0; jc < 4; ++jc) {
                         float* v = vb + jc * 16;
                         if (jc * 16 < cols_here) {
+                            if (args.resid && row < args.n) {
+                                const int cg = cbk * 64 + jc * 16;
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) {
+                                    const float dv = (cg + i < args.n) ? v[i] - ((cg + i == row) ? 1.f : 0.f) : 0.f;
+                                    rs_part = fmaf(dv, dv, rs_part);
+                                }
+                            }
 #pragma unroll
                             for (int i = 0; i < 16; ++i) v[i] *= s_copy;
                             pg_stage_split16(dst_hi, dst_lo, lane, jc * 2, v);
@@ -247,6 +257,11 @@ polar_fused_abm_kernel(const __grid_constant__ PolarFusedMaps maps, const PolarF
                 fence_proxy_async_smem();                         // generic-proxy writes -> visible to the tensor core
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&copy_bar[cbk]);
+            }
+            if (args.resid) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) rs_part += __shfl_xor_sync(0xffffffffu, rs_part, o);
+                if (lane == 0) args.resid[static_cast<long long>(z) * args.fro_slots + e] = rs_part;
             }
             // ---- store: Bm = ca I + (cb r) acc
             mbar_wait(acc2_bar, ph_item);

@@ -49,7 +49,8 @@ struct PolarGemmArgs {
     int epi;
     // primary output (split pair, per-problem stride in elements)
     __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; long long out_stride; int ld_out;   // tiled (SPLIT) or row-major with ld_out (THETA)
-    const float* norm2;              // if non-null r = 1 / norm2[z], else r = 1
+    const float* norm2;              // if non-null r = 1 / sum(norm2[z][0 .. fro_slots)), else r = 1
+    int fro_slots;                   // partial-trace slots per problem (>= 4 n_mt n_nt of the launch that writes `trace`)
     float scale_c, scale_p;          // scale = scale_c * r^scale_p
     float diag_add;
     // auxiliary split matrix laid out like the output, added in the epilogue: out += aux_c * r^aux_p * aux (TMA-loaded)
@@ -57,7 +58,9 @@ struct PolarGemmArgs {
     int a_alias_b;                   // A == B (K-major, same matrix): the A tile is read out of the B tile, no A loads
     long long* dbg_clock;            // development aid: CTA 0 records clock64() per phase of its first items ([item][8])
     int reverse, n_batches;          // reverse: walk the problems last-to-first (what the previous launch wrote last is still in L2)
-    float* trace;                    // if non-null: trace[z] += sum(diag(acc))
+    float* trace;                    // if non-null: trace[z][(mt n_nt + nt) 4 + warp] = this warp's share of sum(diag(acc)) (stored, not
+                                     // added: the consumer sums the slots in order, so the norm is bitwise repeatable)
+    float* resid;                    // aux epilogue only: resid[z][(mt n_nt + nt) 4 + warp] = sum (aux - I)^2 over this warp's part of the tile
     const __nv_bfloat16* aux_hi; const __nv_bfloat16* aux_lo;
     float* out_f32; long long out_f32_stride; int ld_f32;
     const float* vec_a;              // THETA: importance a [z][m_rows]
@@ -274,7 +277,11 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
             const int row = mt * 128 + q * 32 + lane;
             const bool row_ok = row < args.m_rows;
             float r = 1.f;
-            if (args.norm2) r = 1.f / args.norm2[z];
+            if (args.norm2) {
+                float tsum = 0.f;
+                for (int sl = 0; sl < args.fro_slots; ++sl) tsum += args.norm2[static_cast<long long>(z) * args.fro_slots + sl];
+                r = tsum > 0.f ? 1.f / tsum : 0.f;        // C == 0 (constant tokens): r = 0, the nuclear norm is 0, gradients stay finite
+            }
             const float scale = args.scale_c * (args.scale_p == 0.f ? 1.f : powf(r, args.scale_p));
             const float aux_scale = args.aux_c * (args.aux_p == 0.f ? 1.f : powf(r, args.aux_p));
             float a_row = 0.f, q_row = 0.f;
@@ -282,7 +289,7 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
                 a_row = args.vec_a[static_cast<long long>(z) * args.m_rows + row];
                 q_row = sqrtf(a_row);
             }
-            float tr_part = 0.f;
+            float tr_part = 0.f, rs_part = 0.f;
             if constexpr (kStaged) {
                 constexpr bool theta = kTheta;
                 const float* av = theta ? args.vec_a + static_cast<long long>(z) * args.m_rows : nullptr;
@@ -337,6 +344,13 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
                             } else if constexpr (kAux) {
                                 float x[16];
                                 pg_read_split16(aux_hi_s, aux_lo_s, lane, jc * 2, x);
+                                if (args.resid && row_ok) {                     // last step: ||A - I||_F^2 (convergence evidence)
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) {
+                                        const float dv = (c + i < args.n_cols) ? x[i] - ((c + i == row) ? 1.f : 0.f) : 0.f;
+                                        rs_part = fmaf(dv, dv, rs_part);
+                                    }
+                                }
 #pragma unroll
                                 for (int i = 0; i < 16; ++i) v[i] = fmaf(aux_scale, x[i], scale * v[i]) + ((c + i == row) ? args.diag_add : 0.f);
                             } else if (diag_work) {
@@ -396,7 +410,12 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
             if (args.trace) {
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) tr_part += __shfl_xor_sync(0xffffffffu, tr_part, o);
-                if (lane == 0) atomicAdd(args.trace + z, tr_part);
+                if (lane == 0) args.trace[static_cast<long long>(z) * args.fro_slots + (mt * args.n_nt + itm.nt) * 4 + q] = tr_part;
+            }
+            if (kAux && args.resid) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) rs_part += __shfl_xor_sync(0xffffffffu, rs_part, o);
+                if (lane == 0) args.resid[static_cast<long long>(z) * args.fro_slots + (mt * args.n_nt + itm.nt) * 4 + q] = rs_part;
             }
         }
         if (lane == 0) tma_store_wait_all();          // global writes of this CTA complete before it exits

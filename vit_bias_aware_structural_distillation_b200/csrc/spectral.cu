@@ -18,6 +18,15 @@ namespace basd {
 
 // development aid (tools/gpu_debug_eig.py): phase clocks of the first pooled_eig cluster [0..7] and of angles CTA (0,0) [8..23]
 __device__ long long g_spectral_clk[32];
+__device__ int g_spectral_dbg_on;                      // written once by the host when BASD_SPECTRAL_DBG is set; otherwise no launch touches g_spectral_clk
+static void spectral_dbg_init() {
+    static const bool once = [] {
+        const int on = getenv("BASD_SPECTRAL_DBG") ? 1 : 0;
+        if (on) cudaMemcpyToSymbol(g_spectral_dbg_on, &on, sizeof(int));
+        return true;
+    }();
+    (void)once;
+}
 int spectral_debug_clocks(long long* host_out) {
     return cudaMemcpyFromSymbol(host_out, g_spectral_clk, sizeof(long long) * 32) == cudaSuccess ? 0 : 1;
 }
@@ -231,7 +240,7 @@ pooled_eig_kernel(const float* __restrict__ stats, int n, int Lt, int P, float M
     // eigenvector e = column order[e] of A, normalised; one warp per eigenvector, lanes over components (conflict-free
     // shared reads; the [eig][comp] store is coalesced, the [comp][eig] one is a 4-byte scatter that L2 merges)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    if (threadIdx.x == 0 && p == Lt) { g_spectral_clk[0] = t_pre - t_begin; g_spectral_clk[1] = t_jac - t_pre; g_spectral_clk[2] = clock64() - t_jac; g_spectral_clk[3] = nsweeps; }
+    if (threadIdx.x == 0 && p == Lt && g_spectral_dbg_on) { g_spectral_clk[0] = t_pre - t_begin; g_spectral_clk[1] = t_jac - t_pre; g_spectral_clk[2] = clock64() - t_jac; g_spectral_clk[3] = nsweeps; }
     for (int e = warp; e < n; e += nwarps) {
         const float* col = A + static_cast<size_t>(order[e]) * ld;
         const float s = csum[e];
@@ -304,7 +313,7 @@ angles_kernel(int n, int Lt, int P, const int* __restrict__ ranks, const float* 
     float* Fg = WQg + n * n;                  // [a][e]
     float* T1g = Fg + n * n;                  // H [a][c]
 
-    const bool dbg = blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
+    const bool dbg = blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && g_spectral_dbg_on;
     if (dbg) g_spectral_clk[31] = k;
     if (k == 0) {                              // reference: 0/0 -> NaN (layer_selector.py:105)
         if (threadIdx.x == 0) d2_out[i * Lt + j] = CUDART_NAN_F;
@@ -462,8 +471,6 @@ selector_bwd_kernel(int n, int Lt, int P, const float* __restrict__ gw_raw, cons
         if (threadIdx.x == 0 && blockIdx.x == 0) grad_log_temp[i] = gtau / (1.f + expf(-lt));
     }
     __syncthreads();
-    const float* csum = stats + static_cast<size_t>(Lt + i) * (n * n + n) + n * n;
-    const float invM = 1.f / M_student;
     // each CTA handles a strip of rows c; every thread a few (c, c') entries
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n * n; t += gridDim.x * blockDim.x) {
         float acc = 0.f;
@@ -471,9 +478,22 @@ selector_bwd_kernel(int n, int Lt, int P, const float* __restrict__ gw_raw, cons
         const __nv_bfloat16 hi = __float2bfloat16(acc);
         gam_hi[static_cast<size_t>(i) * n * n + t] = hi;
         gam_lo[static_cast<size_t>(i) * n * n + t] = __float2bfloat16(acc - __bfloat162float(hi));
-        // corr[c'] += mu[c] * Gamma'[c][c']   (Gamma' symmetric: index t = c*n + c')
-        const int c = t / n, c2 = t % n;
-        atomicAdd(&corr[i * n + c2], csum[c] * invM * acc);
+    }
+}
+// corr[i][c'] = sum_c mu_i[c] Gamma'_i[c][c']  (the centring correction of the student gradient), c ascending: one thread
+// per column, fixed order (the atomicAdd version of this sum was one of the sources of launch-to-launch differences)
+__global__ void __launch_bounds__(256)
+selector_corr_kernel(int n, int Lt, const float* __restrict__ stats, float M_student, const __nv_bfloat16* __restrict__ gam_hi,
+                     const __nv_bfloat16* __restrict__ gam_lo, float* __restrict__ corr) {
+    const int i = blockIdx.y;
+    const float* csum = stats + static_cast<size_t>(Lt + i) * (n * n + n) + n * n;
+    const float invM = 1.f / M_student;
+    const __nv_bfloat16* gh = gam_hi + static_cast<size_t>(i) * n * n;
+    const __nv_bfloat16* gl = gam_lo + static_cast<size_t>(i) * n * n;
+    for (int c2 = blockIdx.x * blockDim.x + threadIdx.x; c2 < n; c2 += gridDim.x * blockDim.x) {
+        float acc = 0.f;
+        for (int c = 0; c < n; ++c) acc = fmaf(csum[c] * invM, __bfloat162float(gh[c * n + c2]) + __bfloat162float(gl[c * n + c2]), acc);
+        corr[i * n + c2] = acc;
     }
 }
 
@@ -485,6 +505,7 @@ size_t pooled_eig_scratch_floats(int n, int problems) { return spectral_large(n)
 
 cudaError_t launch_pooled_eig(const float* stats, int n, int Lt, int P, float Mt, float Ms, int* ranks, float* evals,
                               float* evecs_km, float* evecs_cm, int* sweeps, float* scratch, cudaStream_t st) {
+    spectral_dbg_init();
     const bool large = spectral_large(n);
     const size_t smem = pooled_smem(n, large);
     if (large) {
@@ -535,12 +556,11 @@ cudaError_t launch_pooled_eig(const float* stats, int n, int Lt, int P, float Mt
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
-    static int cluster = 0;                   // BASD_EIG_CLUSTER: development knob (1..8 CTAs per problem)
-    if (!cluster) {
+    static const int cluster = [] {           // BASD_EIG_CLUSTER: development knob (1..8 CTAs per problem), read once
         const char* env = getenv("BASD_EIG_CLUSTER");
-        cluster = env ? atoi(env) : kPooledCluster;
-        if (cluster < 1 || cluster > 8) cluster = kPooledCluster;
-    }
+        const int c = env ? atoi(env) : kPooledCluster;
+        return (c < 1 || c > 8) ? kPooledCluster : c;
+    }();
     cfg.gridDim = dim3((2 * Lt + P) * cluster);
     cfg.blockDim = dim3(kPooledThreads);
     cfg.dynamicSmemBytes = smem;
@@ -574,11 +594,12 @@ cudaError_t launch_selector_bwd(int n, int Lt, int P, const float* gw_raw, const
                                 const float* w, const float* d2, const float* log_temp, const float* gamma,
                                 const float* stats, float Ms, __nv_bfloat16* gam_hi, __nv_bfloat16* gam_lo, float* corr,
                                 float* grad_log_temp, cudaStream_t st) {
-    cudaError_t e = cudaMemsetAsync(corr, 0, sizeof(float) * P * n, st);
-    if (e != cudaSuccess) return e;
     const int tiles = (n * n + 255) / 256;
     selector_bwd_kernel<<<dim3(tiles < 64 ? tiles : 64, P), 256, 0, st>>>(n, Lt, P, gw_raw, scale_ptr, scale_host, w, d2, log_temp,
                                                                           gamma, stats, Ms, gam_hi, gam_lo, corr, grad_log_temp);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    selector_corr_kernel<<<dim3((n + 255) / 256, P), 256, 0, st>>>(n, Lt, stats, Ms, gam_hi, gam_lo, corr);
     return cudaGetLastError();
 }
 

@@ -52,20 +52,24 @@ struct ColsumJobs {                       // out[j][d] += sum_rows (hi[j] + lo[j
     const __nv_bfloat16* lo[kMaxLayers + kMaxPoints];
     float* out[kMaxLayers + kMaxPoints];
 };
-cudaError_t launch_colsum(const ColsumJobs& jobs, int n_jobs, size_t rows, int D, cudaStream_t st);
+size_t colsum_part_floats(int n_jobs, size_t rows, int D);      // scratch for the per-CTA partial sums (fixed-order reduce)
+cudaError_t launch_colsum(const ColsumJobs& jobs, int n_jobs, size_t rows, int D, float* part, cudaStream_t st);
 cudaError_t launch_importance_mix(const float* rows, const float* w, int Lt, int P, int B, int Nt, int Ns, float* a,
                                   float* ssum, cudaStream_t st);
 cudaError_t launch_mix_teacher(const PtrTable& teacher, const float* w, int Lt, int P, int B, int Nt, int Ns, int Dt,
                                __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st);
 // Dtm is [P][B][Nd][Dt] with Nd = Ns (gradient w.r.t. the token-aligned mixed teacher) or, with dtm_unaligned, Nd = Nt
 // (gradient w.r.t. the mixed teacher on its own token grid: no resampling in the dots)
-cudaError_t launch_wgrad_dots(const PtrTable& teacher, const __nv_bfloat16* Dtm, const float* gwt, const float* rows,
-                              int Lt, int P, int B, int Nt, int Ns, int Dt, float* gw /*[P][Lt], pre-zeroed*/,
+cudaError_t launch_wgrad_dots(const PtrTable& teacher, const __nv_bfloat16* Dtm, const __nv_bfloat16* Dtm_lo, const float* gwt, const float* rows,
+                              int Lt, int P, int B, int Nt, int Ns, int Dt, float* gw /*[P][Lt]*/,
+                              float* gw_part /*wgrad_part_floats(P, Lt) floats: per-CTA partials, summed in a fixed order*/,
                               cudaStream_t st, bool dtm_unaligned = false);
+size_t wgrad_part_floats(int P, int Lt);
 cudaError_t launch_cls_attention_rows(const void* q, const void* k, int is_bf16, int B, int H, int S, int dh,
                                       const long long* q_strides /*[b,h]*/, const long long* k_strides /*[b,h,s]*/, float scale,
                                       float* out /*[B,H,S]*/, cudaStream_t st);
-cudaError_t launch_loss_reduce(const float* loss_b, int P, int B, float* geo_i, float* geo, cudaStream_t st);
+// geo_i[P], *geo = mean; resid_max = max over the problems of dbg[.][3] (polar residual)
+cudaError_t launch_loss_reduce(const float* loss_b, const float* dbg, int P, int B, float* geo_i, float* geo, float* resid_max, cudaStream_t st);
 
 // ---- tcgen05 GEMM launchers (gemm_ops.cu)
 int gemm_init_driver_api();               // resolves cuTensorMapEncodeTiled; 0 on success
@@ -74,15 +78,17 @@ cudaError_t gemm_project(const void* const* X, int n_layers, size_t M, int Dt, c
                          int Ds, __nv_bfloat16* Zhi, __nv_bfloat16* Zlo, cudaStream_t st);
 // Zlo may be null (exact bf16 input); otherwise Z = Zhi + Zlo and the Gram uses hi*hi + hi*lo + lo*hi
 // G[i] (stride g_stride floats) += S_i^T S_i for n separate exact-bf16 [M][Ds] tensors, one launch
-cudaError_t gemm_gram_table(const void* const* S, int n, size_t M, int Ds, float* G, long long g_stride, cudaStream_t st);
-cudaError_t gemm_gram(const __nv_bfloat16* Z, const __nv_bfloat16* Zlo, size_t M, int Ds, float* G /*[Ds][Ds] pre-zeroed*/,
+// Split-K slices go to `part` (gemm_gram_part_floats floats) and are summed in a fixed order: bitwise repeatable Grams.
+size_t gemm_gram_part_floats(size_t M, int Ds, int batches);
+cudaError_t gemm_gram_table(const void* const* S, int n, size_t M, int Ds, float* G, long long g_stride, float* part, cudaStream_t st);
+cudaError_t gemm_gram(const __nv_bfloat16* Z, const __nv_bfloat16* Zlo, size_t M, int Ds, float* G /*[Ds][Ds]*/, float* part,
                       cudaStream_t st);
 cudaError_t gemm_gram_batched(const __nv_bfloat16* Z, const __nv_bfloat16* Zlo, size_t M, int Ds, int batches, float* G,
-                              long long g_stride, cudaStream_t st);
+                              long long g_stride, float* part, cudaStream_t st);
 cudaError_t gemm_token_gram(const __nv_bfloat16* Thi, const __nv_bfloat16* Tlo, int batches, int Ns, int Dt, float* Ktt,
                             cudaStream_t st);
 cudaError_t gemm_theta_apply(const __nv_bfloat16* theta_hi, const __nv_bfloat16* theta_lo, int NsPad, const __nv_bfloat16* Thi,
-                             const __nv_bfloat16* Tlo, int batches, int Ns, int Dt, __nv_bfloat16* Dtm, cudaStream_t st);
+                             const __nv_bfloat16* Tlo, int batches, int Ns, int Dt, __nv_bfloat16* Dtm, __nv_bfloat16* Dtm_lo, cudaStream_t st);
 cudaError_t gemm_student_grad(const __nv_bfloat16* S, size_t M, int Ds, const __nv_bfloat16* Ghi, const __nv_bfloat16* Glo,
                               const float* gdir, const float* corr, const float* scale_ptr, float scale_host, void* out,
                               int out_is_bf16, cudaStream_t st);
@@ -117,7 +123,9 @@ struct PolarFusedArgs {
     int n_problems, reverse;
     float ca, cb, cc;                // Bm = ca I + cb (rA) + cc (rA)^2
     int first;                       // step 0: r = 1 / trace(A) (written to fro2); otherwise r = 1
-    float* fro2;                     // [problem]
+    float* fro2;                     // [problem][fro_slots]: slot 0 written here
+    int fro_slots;
+    float* resid;                    // last step only: [problem][fro_slots] per-warp partial sums of ||A - I||_F^2 (else null)
     long long* dbg_clock;            // development aid: CTA 0 records clock64() per phase of its first problems ([problem][8])
 };
 // Bm = ca I + cb (rA) + cc (rA)^2 with A = T W^T kept on chip (polar_fused.cuh); needs polar_fused_supported(D_s, N_s)
@@ -150,7 +158,10 @@ struct PolarArgs {
     float* Gsw;                           // [P*B][Ns][Ds]   d nuc / d s_w
     float* vec;                           // [P*B][4][Ns]    ksd, ktd, (spare), (spare)
     float* scal;                          // [P*B][4]        (spare), tr_s, tr_t, (spare)
-    float* fro2;                          // [P*B]           ||C||_F^2
+    float* fro2;                          // [P*B][fro_slots]  partial traces of A_0; their sum = ||C||_F^2
+    int fro_slots;
+    float* resid;                         // [P*B][fro_slots]  partial sums of ||A - I||_F^2 at the last step (A = X X^T before the last update)
+    int steps;                            // Newton-Schulz steps (kPolarStepsDefault .. kPolarStepsMax)
     // outputs
     float* gdir;                          // [P*B][Ns][Ds]
     __nv_bfloat16* theta;                 // [P*B][Ns][NsPad] hi
@@ -162,6 +173,8 @@ struct PolarArgs {
 cudaError_t launch_polar_procrustes(const PolarArgs& args, cudaStream_t st, int* launches);
 cudaError_t launch_polar_procrustes_vt(const PolarArgs& args, cudaStream_t st, int* launches);
 constexpr int kVtMaxTokens = 224;         // teacher tokens of the token-space form (Cholesky factor held in shared memory)
-int polar_steps();                        // Newton-Schulz steps (the final iterate lives in W2 when odd, W when even)
+int polar_fro_slots(int core);            // partial-trace slots per problem for a core (D_s or N_t) of this size
+constexpr int kPolarStepsDefault = 10, kPolarStepsMax = 16;
+int polar_steps();                        // default number of Newton-Schulz steps (the final iterate lives in W2 when odd, W when even)
 
 }  // namespace basd

@@ -155,12 +155,13 @@ cudaError_t launch_pack_bf16(const void* src, int src_is_bf16, long long sb, lon
     return cudaGetLastError();
 }
 
-// out[j][d] += sum over rows of (hi[j] + lo[j])[row][d]; D % 8 == 0.  grid = (row chunks, jobs): every CTA streams a
+// out[j][d] = sum over rows of (hi[j] + lo[j])[row][d]; D % 8 == 0.  grid = (row chunks, jobs): every CTA streams a
 // contiguous chunk of rows with 16-byte loads (4 in flight per thread), reduces across its row lanes in shared
-// memory and issues D atomics.
+// memory and writes its D partial sums to part[job][chunk][D]; colsum_reduce_kernel adds the chunks in a fixed order
+// (atomicAdd made the column sums, hence the centred Grams, differ from launch to launch).
 constexpr int kColsumThreads = 256;
 __global__ void __launch_bounds__(kColsumThreads)
-colsum_kernel(ColsumJobs jobs, size_t rows, int D) {
+colsum_kernel(ColsumJobs jobs, size_t rows, int D, float* __restrict__ part) {
     __shared__ float red[kColsumThreads * 8];
     const int j = blockIdx.y;
     const __nv_bfloat16* Xh = jobs.hi[j];
@@ -215,14 +216,30 @@ colsum_kernel(ColsumJobs jobs, size_t rows, int D) {
         const int v = c / 8, e = c % 8;
         float s = 0.f;
         for (int l = 0; l < rpp; ++l) s += red[(l * vpr + v) * 8 + e];
-        atomicAdd(jobs.out[j] + c, s);
+        part[(static_cast<size_t>(j) * gridDim.x + blockIdx.x) * D + c] = s;
     }
 }
-cudaError_t launch_colsum(const ColsumJobs& jobs, int n_jobs, size_t rows, int D, cudaStream_t st) {
-    if (D % 8 != 0 || D > 8 * kColsumThreads || n_jobs < 1) return cudaErrorInvalidValue;
+__global__ void colsum_reduce_kernel(ColsumJobs jobs, const float* __restrict__ part, int chunks, int D) {
+    const int j = blockIdx.x;
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < chunks; ++k) s += part[(static_cast<size_t>(j) * chunks + k) * D + c];
+        jobs.out[j][c] = s;
+    }
+}
+static int colsum_chunks(int n_jobs, size_t rows) {
     int chunks = (148 * 8 + n_jobs - 1) / n_jobs;
     if (static_cast<size_t>(chunks) * 64 > rows) chunks = static_cast<int>((rows + 63) / 64);
-    colsum_kernel<<<dim3(chunks, n_jobs), kColsumThreads, 0, st>>>(jobs, rows, D);
+    return chunks;
+}
+size_t colsum_part_floats(int n_jobs, size_t rows, int D) { return static_cast<size_t>(n_jobs) * colsum_chunks(n_jobs, rows) * D; }
+cudaError_t launch_colsum(const ColsumJobs& jobs, int n_jobs, size_t rows, int D, float* part, cudaStream_t st) {
+    if (D % 8 != 0 || D > 8 * kColsumThreads || n_jobs < 1 || !part) return cudaErrorInvalidValue;
+    const int chunks = colsum_chunks(n_jobs, rows);
+    colsum_kernel<<<dim3(chunks, n_jobs), kColsumThreads, 0, st>>>(jobs, rows, D, part);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    colsum_reduce_kernel<<<n_jobs, 256, 0, st>>>(jobs, part, chunks, D);
     return cudaGetLastError();
 }
 
@@ -357,10 +374,12 @@ cudaError_t launch_mix_teacher(const PtrTable& teacher, const float* w, int Lt, 
 constexpr int WG_PC = 4, WG_JC = 12;
 // All 16-byte loads of a position (WG_PC gradient vectors, WG_JC teacher vectors, twice that when interpolating) are issued
 // before the first use: with a load and its use alternating per layer the kernel ran at 2 TB/s, one L2/HBM latency per layer.
-template <bool INTERP>
+// Every CTA writes its WG_PC x WG_JC partial dots to gw_part[blockIdx.x][P][Lt]; wgrad_reduce_kernel adds the CTAs (and the
+// importance partials) in a fixed order.
+template <bool INTERP, bool SPLIT>
 __global__ void __launch_bounds__(256)
-wgrad_dots_kernel(PtrTable teacher, const __nv_bfloat16* __restrict__ Dtm, int Lt, int P, int B, int Nt, int Ns, int Dt,
-                  float* __restrict__ gw) {
+wgrad_dots_kernel(PtrTable teacher, const __nv_bfloat16* __restrict__ Dtm, const __nv_bfloat16* __restrict__ DtmLo, int Lt, int P, int B, int Nt,
+                  int Ns, int Dt, float* __restrict__ gw_part) {
     const int n_jc = (Lt + WG_JC - 1) / WG_JC;
     const int i_base = (blockIdx.y / n_jc) * WG_PC, j_base = (blockIdx.y % n_jc) * WG_JC;
     float acc[WG_PC][WG_JC];
@@ -376,10 +395,13 @@ wgrad_dots_kernel(PtrTable teacher, const __nv_bfloat16* __restrict__ Dtm, int L
         const uint32_t b = row / static_cast<uint32_t>(Ns), n = row - b * Ns;
         int i0, i1; float lam;
         interp_index(static_cast<int>(n), Nt, Ns, i0, i1, lam);
-        uint4 draw[WG_PC], t0[WG_JC], t1[INTERP ? WG_JC : 1];
+        uint4 draw[WG_PC], dlow[SPLIT ? WG_PC : 1], t0[WG_JC], t1[INTERP ? WG_JC : 1];
 #pragma unroll
-        for (int i = 0; i < WG_PC; ++i)
-            draw[i] = i_base + i < P ? ld_nc_16(Dtm + ((static_cast<size_t>(i_base + i) * B + b) * Ns + n) * Dt + dv * 8) : zero4;
+        for (int i = 0; i < WG_PC; ++i) {
+            const size_t off = ((static_cast<size_t>(i_base + i < P ? i_base + i : 0) * B + b) * Ns + n) * Dt + dv * 8;
+            draw[i] = i_base + i < P ? ld_nc_16(Dtm + off) : zero4;
+            if (SPLIT) dlow[i] = i_base + i < P ? ld_nc_16(DtmLo + off) : zero4;
+        }
 #pragma unroll
         for (int j = 0; j < WG_JC; ++j) {
             const bool ok = j_base + j < Lt;
@@ -389,7 +411,15 @@ wgrad_dots_kernel(PtrTable teacher, const __nv_bfloat16* __restrict__ Dtm, int L
         }
         float dtv[WG_PC][8];
 #pragma unroll
-        for (int i = 0; i < WG_PC; ++i) bf16x8_to_float(draw[i], dtv[i]);
+        for (int i = 0; i < WG_PC; ++i) {
+            bf16x8_to_float(draw[i], dtv[i]);
+            if (SPLIT) {
+                float lo8[8];
+                bf16x8_to_float(dlow[i], lo8);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) dtv[i][e] += lo8[e];
+            }
+        }
 #pragma unroll
         for (int j = 0; j < WG_JC; ++j) {
             float f[8];
@@ -409,25 +439,26 @@ wgrad_dots_kernel(PtrTable teacher, const __nv_bfloat16* __restrict__ Dtm, int L
             }
         }
     }
-    __shared__ float red[WG_PC * WG_JC];
-    for (int t = threadIdx.x; t < WG_PC * WG_JC; t += blockDim.x) red[t] = 0.f;
-    __syncthreads();
+    __shared__ float red[8][WG_PC * WG_JC];               // one row per warp (256 threads)
 #pragma unroll
     for (int i = 0; i < WG_PC; ++i)
 #pragma unroll
         for (int j = 0; j < WG_JC; ++j) {
             const float s = warp_sum(acc[i][j]);
-            if ((threadIdx.x & 31) == 0) atomicAdd(&red[i * WG_JC + j], s);
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][i * WG_JC + j] = s;
         }
     __syncthreads();
     for (int t = threadIdx.x; t < WG_PC * WG_JC; t += blockDim.x) {
         const int i = i_base + t / WG_JC, j = j_base + t % WG_JC;
-        if (i < P && j < Lt) atomicAdd(&gw[i * Lt + j], red[t]);
+        float s = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < 8; ++wv) s += red[wv][t];
+        if (i < P && j < Lt) gw_part[(static_cast<size_t>(blockIdx.x) * P + i) * Lt + j] = s;
     }
 }
-// gw[i][j] += sum_{b,n} gwt[i][b][n] * interp(rows[j][b])[n]
+// gw_part[blockIdx.y][i][j] = sum_{b in this slice, n} gwt[i][b][n] * interp(rows[j][b])[n]
 __global__ void wgrad_importance_kernel(const float* __restrict__ gwt, const float* __restrict__ rows, int Lt, int P, int B, int Nt,
-                                        int Ns, float* __restrict__ gw) {
+                                        int Ns, float* __restrict__ gw_part) {
     __shared__ float red[40];
     const int i = blockIdx.x / Lt, j = blockIdx.x % Lt;
     float part = 0.f;
@@ -442,25 +473,59 @@ __global__ void wgrad_importance_kernel(const float* __restrict__ gwt, const flo
         }
     }
     const float tot = cta_sum(part, red);
-    if (threadIdx.x == 0) atomicAdd(&gw[i * Lt + j], tot);
+    if (threadIdx.x == 0) gw_part[(static_cast<size_t>(blockIdx.y) * P + i) * Lt + j] = tot;
 }
-cudaError_t launch_wgrad_dots(const PtrTable& teacher, const __nv_bfloat16* Dtm, const float* gwt, const float* rows, int Lt, int P,
-                              int B, int Nt, int Ns, int Dt, float* gw, cudaStream_t st, bool dtm_unaligned) {
-    if (Dt % 8 != 0 || static_cast<unsigned long long>(B) * Ns * (Dt / 8) >= (1ull << 32)) return cudaErrorInvalidValue;
+// gw[i][j] = sum of the n_part partial tables, in order
+__global__ void wgrad_reduce_kernel(const float* __restrict__ gw_part, int n_part, int PL, float* __restrict__ gw) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < PL; t += gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < n_part; ++k) s += gw_part[static_cast<size_t>(k) * PL + t];
+        gw[t] = s;
+    }
+}
+constexpr int kWgradDotCtas = 148 * 4, kWgradImpSlices = 16;
+size_t wgrad_part_floats(int P, int Lt) { return static_cast<size_t>(kWgradDotCtas + kWgradImpSlices) * P * Lt; }
+cudaError_t launch_wgrad_dots(const PtrTable& teacher, const __nv_bfloat16* Dtm, const __nv_bfloat16* DtmLo, const float* gwt, const float* rows, int Lt, int P,
+                              int B, int Nt, int Ns, int Dt, float* gw, float* gw_part, cudaStream_t st, bool dtm_unaligned) {
+    if (Dt % 8 != 0 || static_cast<unsigned long long>(B) * Ns * (Dt / 8) >= (1ull << 32) || !gw_part) return cudaErrorInvalidValue;
     const int ny = ((P + WG_PC - 1) / WG_PC) * ((Lt + WG_JC - 1) / WG_JC);
-    if (Nt == Ns || dtm_unaligned)
-        wgrad_dots_kernel<false><<<dim3(148 * 4, ny), 256, 0, st>>>(teacher, Dtm, Lt, P, B, Nt, Nt, Dt, gw);
-    else
-        wgrad_dots_kernel<true><<<dim3(148 * 4, ny), 256, 0, st>>>(teacher, Dtm, Lt, P, B, Nt, Ns, Dt, gw);
+    const dim3 grid(kWgradDotCtas, ny);
+    if (Nt == Ns || dtm_unaligned) {
+        if (DtmLo) wgrad_dots_kernel<false, true><<<grid, 256, 0, st>>>(teacher, Dtm, DtmLo, Lt, P, B, Nt, Nt, Dt, gw_part);
+        else wgrad_dots_kernel<false, false><<<grid, 256, 0, st>>>(teacher, Dtm, DtmLo, Lt, P, B, Nt, Nt, Dt, gw_part);
+    } else {
+        if (DtmLo) wgrad_dots_kernel<true, true><<<grid, 256, 0, st>>>(teacher, Dtm, DtmLo, Lt, P, B, Nt, Ns, Dt, gw_part);
+        else wgrad_dots_kernel<true, false><<<grid, 256, 0, st>>>(teacher, Dtm, DtmLo, Lt, P, B, Nt, Ns, Dt, gw_part);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    wgrad_importance_kernel<<<dim3(P * Lt, B < 16 ? B : 16), 256, 0, st>>>(gwt, rows, Lt, P, B, Nt, Ns, gw);
+    const int slices = B < kWgradImpSlices ? B : kWgradImpSlices;
+    wgrad_importance_kernel<<<dim3(P * Lt, slices), 256, 0, st>>>(gwt, rows, Lt, P, B, Nt, Ns, gw_part + static_cast<size_t>(kWgradDotCtas) * P * Lt);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    wgrad_reduce_kernel<<<(P * Lt + 255) / 256, 256, 0, st>>>(gw_part, kWgradDotCtas + slices, P * Lt, gw);
     return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------- loss reduce
-__global__ void loss_reduce_kernel(const float* __restrict__ loss_b, int P, int B, float* __restrict__ geo_i, float* __restrict__ geo) {
+__global__ void loss_reduce_kernel(const float* __restrict__ loss_b, const float* __restrict__ dbg, int P, int B, float* __restrict__ geo_i,
+                                   float* __restrict__ geo, float* __restrict__ resid_max) {
     __shared__ float red[40];
+    __shared__ float mx[8];
+    if (resid_max) {                        // largest polar residual over all (point, sample) problems; NaN counts as +inf
+        float m = 0.f;
+        for (int t = threadIdx.x; t < P * B; t += blockDim.x) {
+            const float r = dbg[t * 5 + 3];
+            m = fmaxf(m, (r == r) ? r : __int_as_float(0x7f800000));
+        }
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if ((threadIdx.x & 31) == 0) mx[threadIdx.x >> 5] = m;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int wv = 1; wv < (blockDim.x >> 5); ++wv) m = fmaxf(m, mx[wv]);
+            *resid_max = m;
+        }
+    }
     float total = 0.f;
     for (int i = 0; i < P; ++i) {
         float part = 0.f;
@@ -471,8 +536,8 @@ __global__ void loss_reduce_kernel(const float* __restrict__ loss_b, int P, int 
     }
     if (threadIdx.x == 0) *geo = total / static_cast<float>(P);
 }
-cudaError_t launch_loss_reduce(const float* loss_b, int P, int B, float* geo_i, float* geo, cudaStream_t st) {
-    loss_reduce_kernel<<<1, 256, 0, st>>>(loss_b, P, B, geo_i, geo);
+cudaError_t launch_loss_reduce(const float* loss_b, const float* dbg, int P, int B, float* geo_i, float* geo, float* resid_max, cudaStream_t st) {
+    loss_reduce_kernel<<<1, 256, 0, st>>>(loss_b, dbg, P, B, geo_i, geo, resid_max);
     return cudaGetLastError();
 }
 

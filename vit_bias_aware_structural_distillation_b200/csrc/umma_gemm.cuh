@@ -286,7 +286,27 @@ struct EpiStoreF32 {                      // out[batch][row][col] = alpha * acc
     }
 };
 
-struct EpiAtomicAddF32 {                  // split-K partial: out[row][col] += acc   (out pre-zeroed)
+// split-K partial of slice z = batch * n_splits + split, stored (not added): out[z][row][col] = acc.  The slices are summed
+// in a fixed order by splitk_reduce_kernel (gemm_ops.cu), so the result does not depend on the order CTAs finish in
+// (fp32 atomicAdd made the pooled Gram - and every eigenvector downstream - differ from launch to launch).
+struct EpiStoreSplitK {
+    float* out; int ld, rows, cols;
+    __device__ EpiStoreSplitK(const GemmArgs& a, int, int z) {
+        out = reinterpret_cast<float*>(a.out) + z * a.out_batch_stride; ld = a.ld_out; rows = a.rows_valid; cols = a.cols_valid;
+    }
+    __device__ void operator()(int row, int col0, const float* v) const {
+        if (row >= rows || col0 >= cols) return;
+        float* p = out + static_cast<long long>(row) * ld + col0;
+        if (col0 + 16 <= cols && (ld & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else {
+            for (int i = 0; i < 16 && col0 + i < cols; ++i) p[i] = v[i];
+        }
+    }
+};
+
+struct EpiAtomicAddF32 {                  // split-K partial: out[row][col] += acc   (out pre-zeroed; self test only)
     float* out; int ld, rows, cols;
     __device__ EpiAtomicAddF32(const GemmArgs& a, int batch, int) {
         out = reinterpret_cast<float*>(a.out) + batch * a.out_batch_stride; ld = a.ld_out; rows = a.rows_valid; cols = a.cols_valid;

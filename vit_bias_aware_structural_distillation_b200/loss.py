@@ -35,12 +35,14 @@ def _dtype_code(t: torch.Tensor) -> int:
     raise _lib.BasdError(f"unsupported dtype {t.dtype} (float32 or bfloat16 expected)")
 
 
-def _stream_ptr() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def _stream_ptr(dev=None) -> int:
+    """Current stream of the tensors' device (not of whatever device happens to be current)."""
+    return torch.cuda.current_stream(dev).cuda_stream
 
 
 def _prepare(students: Sequence[torch.Tensor], teachers: Sequence[torch.Tensor], attns: Sequence[torch.Tensor],
-             proj_s: torch.Tensor, proj_t: torch.Tensor, log_temperatures: torch.Tensor, has_cls: bool, world_size: int):
+             proj_s: torch.Tensor, proj_t: torch.Tensor, log_temperatures: torch.Tensor, has_cls: bool, world_size: int,
+             polar_steps: int = 0):
     """Builds the C structs.  Returns (shape, inputs, keepalive) — keepalive holds every tensor whose pointer is used."""
     if not students or not teachers or len(teachers) != len(attns):
         raise _lib.BasdError("need >= 1 student tensor, >= 1 teacher tensor and one attention map per teacher layer")
@@ -69,6 +71,21 @@ def _prepare(students: Sequence[torch.Tensor], teachers: Sequence[torch.Tensor],
     Bt, Nt, Dt = teachers[0].shape
     if Bt != B:
         raise _lib.BasdError("student and teacher batch sizes differ")
+    # the kernels index every tensor of a list with the shape and strides of the first: check them all (the reference
+    # raises from torch.stack / matmul on ragged inputs, layer_selector.py:128-129)
+    for name, ts in (("student", students), ("teacher", teachers), ("attention", attns)):
+        for k, t in enumerate(ts):
+            if t.device != dev:
+                raise _lib.BasdError(f"{name} tensor {k} is on {t.device}, expected {dev}")
+            if t.shape != ts[0].shape or t.stride() != ts[0].stride():
+                raise _lib.BasdError(f"{name} tensor {k} has shape {tuple(t.shape)} / strides {t.stride()}, tensor 0 has {tuple(ts[0].shape)} / {ts[0].stride()}")
+    if len(students) > _lib.MAX_POINTS or len(teachers) > _lib.MAX_LAYERS:
+        raise _lib.BasdError(f"at most {_lib.MAX_POINTS} extraction points and {_lib.MAX_LAYERS} teacher layers")
+    if tuple(proj_s.shape) != (Ds, Ds) or tuple(proj_t.shape) != (Ds, Dt):
+        raise _lib.BasdError(f"proj_s {tuple(proj_s.shape)} / proj_t {tuple(proj_t.shape)} do not match student width {Ds} and teacher width {Dt} "
+                             "(was the module built with the right student_dim / teacher_dim?)")
+    if log_temperatures.numel() != len(students):
+        raise _lib.BasdError(f"{log_temperatures.numel()} log_temperatures for {len(students)} student extraction points")
     H = attns[0].shape[1]
     exp_attn = (B, H, Nt + 1, Nt + 1) if has_cls else (B, H, Nt, Nt)
     cls_rows_only = (B, H, 1, Nt + 1)          # HostStager hands over just the CLS query row (all relational.py:24 reads)
@@ -78,7 +95,8 @@ def _prepare(students: Sequence[torch.Tensor], teachers: Sequence[torch.Tensor],
     proj_t = proj_t.detach().to(device=dev, dtype=torch.float32).contiguous()
     logt = log_temperatures.detach().to(device=dev, dtype=torch.float32).contiguous()
     shape = Shape(B=B, Ns=Ns, Nt=Nt, Ds=Ds, Dt=Dt, Lt=len(teachers), P=len(students), H=H, has_cls=int(has_cls),
-                  act_dtype=_dtype_code(students[0]), attn_dtype=_dtype_code(attns[0]), world_size=world_size)
+                  act_dtype=_dtype_code(students[0]), attn_dtype=_dtype_code(attns[0]), world_size=world_size,
+                  polar_steps=int(polar_steps))
     inp = Inputs()
     for i, s in enumerate(students):
         inp.student[i] = s.data_ptr()
@@ -119,33 +137,51 @@ def _allreduce_sum(dist, t: torch.Tensor):
 # --------------------------------------------------------------------------------------------- custom ops
 @torch.library.custom_op("basd_b200::geo_forward", mutates_args=())
 def geo_forward(students: List[torch.Tensor], teachers: List[torch.Tensor], attns: List[torch.Tensor], proj_s: torch.Tensor,
-                proj_t: torch.Tensor, log_temperatures: torch.Tensor, has_cls: bool) -> List[torch.Tensor]:
-    """Returns [geo_loss (0-dim fp32), workspace (uint8), ranks (int32 [Lt]), mixing weights (fp32 [P, Lt])]."""
+                proj_t: torch.Tensor, log_temperatures: torch.Tensor, has_cls: bool, polar_steps: int) -> List[torch.Tensor]:
+    """(polar_steps has no default on purpose: torch drops default-valued arguments from the autograd inputs.)
+    Returns [geo_loss (0-dim fp32), workspace (uint8), ranks (int32 [Lt]), mixing weights (fp32 [P, Lt]),
+    polar residual (fp32 [1]: largest ||X X^T - I||_F going into the last Newton-Schulz step; <= 0.1 = converged)]."""
     lib = _lib.load()
     dist, world = _world()
-    shape, inp, keep = _prepare(students, teachers, attns, proj_s, proj_t, log_temperatures, has_cls, world)
+    shape, inp, keep = _prepare(students, teachers, attns, proj_s, proj_t, log_temperatures, has_cls, world, polar_steps)
     nbytes = ctypes.c_size_t()
     _lib.check(lib.basd_workspace_bytes(ctypes.byref(shape), ctypes.byref(nbytes)), "basd_workspace_bytes")
     dev = students[0].device
-    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
-    geo = torch.empty((), dtype=torch.float32, device=dev)
-    st = _stream_ptr()
-    _lib.check(lib.basd_forward_stats(ctypes.byref(shape), ctypes.byref(inp), ws.data_ptr(), st), "basd_forward_stats")
-    if dist is not None:
-        _allreduce_sum(dist, workspace_view(shape, ws, "stats"))
-    _lib.check(lib.basd_forward_solve(ctypes.byref(shape), ctypes.byref(inp), ws.data_ptr(), geo.data_ptr(), st), "basd_forward_solve")
-    ranks = workspace_view(shape, ws, "ranks", torch.int32).clone()
-    w = workspace_view(shape, ws, "w").clone().view(shape.P, shape.Lt)
+    with torch.cuda.device(dev):             # the library launches on the CURRENT device: make it the tensors' device
+        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+        geo = torch.empty((), dtype=torch.float32, device=dev)
+        st = _stream_ptr(dev)
+        _lib.check(lib.basd_forward_stats(ctypes.byref(shape), ctypes.byref(inp), ws.data_ptr(), st), "basd_forward_stats")
+        if dist is not None:
+            _allreduce_sum(dist, workspace_view(shape, ws, "stats"))
+        _lib.check(lib.basd_forward_solve(ctypes.byref(shape), ctypes.byref(inp), ws.data_ptr(), geo.data_ptr(), st), "basd_forward_solve")
+        ranks = workspace_view(shape, ws, "ranks", torch.int32).clone()
+        w = workspace_view(shape, ws, "w").clone().view(shape.P, shape.Lt)
+        resid = workspace_view(shape, ws, "polar_resid").clone()
     del keep
-    return [geo, ws, ranks, w]
+    return [geo, ws, ranks, w, resid]
+
+
+def _fake_workspace_bytes(students, teachers, attns, has_cls) -> int:
+    """Same size as the real op's workspace (basd_workspace_bytes is host-only arithmetic on the shape)."""
+    B, Ns, Ds = students[0].shape
+    _, Nt, Dt = teachers[0].shape
+    code = lambda t: DTYPE_BF16 if t.dtype == torch.bfloat16 else DTYPE_F32
+    shape = Shape(B=B, Ns=Ns, Nt=Nt, Ds=Ds, Dt=Dt, Lt=len(teachers), P=len(students), H=attns[0].shape[1], has_cls=int(has_cls),
+                  act_dtype=code(students[0]), attn_dtype=code(attns[0]), world_size=_world()[1])
+    nbytes = ctypes.c_size_t()
+    _lib.check(_lib.load().basd_workspace_bytes(ctypes.byref(shape), ctypes.byref(nbytes)), "basd_workspace_bytes")
+    return int(nbytes.value)
 
 
 @geo_forward.register_fake
-def _(students, teachers, attns, proj_s, proj_t, log_temperatures, has_cls):
+def _(students, teachers, attns, proj_s, proj_t, log_temperatures, has_cls, polar_steps):
     dev = students[0].device
-    return [torch.empty((), dtype=torch.float32, device=dev), torch.empty(1, dtype=torch.uint8, device=dev),
+    return [torch.empty((), dtype=torch.float32, device=dev),
+            torch.empty(_fake_workspace_bytes(students, teachers, attns, has_cls), dtype=torch.uint8, device=dev),
             torch.empty(len(teachers), dtype=torch.int32, device=dev),
-            torch.empty(len(students), len(teachers), dtype=torch.float32, device=dev)]
+            torch.empty(len(students), len(teachers), dtype=torch.float32, device=dev),
+            torch.empty(1, dtype=torch.float32, device=dev)]
 
 
 @torch.library.custom_op("basd_b200::geo_backward", mutates_args=("workspace",))
@@ -157,18 +193,19 @@ def geo_backward(grad_geo: torch.Tensor, workspace: torch.Tensor, students: List
     dist, world = _world()
     shape, inp, keep = _prepare(students, teachers, attns, proj_s, proj_t, log_temperatures, has_cls, world)
     dev = students[0].device
-    st = _stream_ptr()
-    g = grad_geo.detach().to(device=dev, dtype=torch.float32).contiguous()
-    _lib.check(lib.basd_backward_dots(ctypes.byref(shape), ctypes.byref(inp), workspace.data_ptr(), st), "basd_backward_dots")
-    if dist is not None:
-        _allreduce_sum(dist, workspace_view(shape, workspace, "gw"))
-    out_dtype = students[0].dtype if students[0].dtype in (torch.float32, torch.bfloat16) else torch.float32
-    grads = [torch.empty(s.shape, dtype=out_dtype, device=dev) for s in students]
-    glt = torch.empty(shape.P, dtype=torch.float32, device=dev)
-    ptrs = (ctypes.c_void_p * len(grads))(*[t.data_ptr() for t in grads])
-    _lib.check(lib.basd_backward_finish(ctypes.byref(shape), ctypes.byref(inp), workspace.data_ptr(), g.data_ptr(), ptrs,
-                                        DTYPE_BF16 if out_dtype == torch.bfloat16 else DTYPE_F32, glt.data_ptr(), st),
-               "basd_backward_finish")
+    with torch.cuda.device(dev):
+        st = _stream_ptr(dev)
+        g = grad_geo.detach().to(device=dev, dtype=torch.float32).contiguous()
+        _lib.check(lib.basd_backward_dots(ctypes.byref(shape), ctypes.byref(inp), workspace.data_ptr(), st), "basd_backward_dots")
+        if dist is not None:
+            _allreduce_sum(dist, workspace_view(shape, workspace, "gw"))
+        out_dtype = students[0].dtype if students[0].dtype in (torch.float32, torch.bfloat16) else torch.float32
+        grads = [torch.empty(s.shape, dtype=out_dtype, device=dev) for s in students]
+        glt = torch.empty(shape.P, dtype=torch.float32, device=dev)
+        ptrs = (ctypes.c_void_p * len(grads))(*[t.data_ptr() for t in grads])
+        _lib.check(lib.basd_backward_finish(ctypes.byref(shape), ctypes.byref(inp), workspace.data_ptr(), g.data_ptr(), ptrs,
+                                            DTYPE_BF16 if out_dtype == torch.bfloat16 else DTYPE_F32, glt.data_ptr(), st),
+                   "basd_backward_finish")
     if world > 1:
         glt = glt / world          # every rank holds the summed gradient; keep the DDP-average convention
     del keep
@@ -181,7 +218,7 @@ def _(grad_geo, workspace, students, teachers, attns, proj_s, proj_t, log_temper
 
 
 def _setup_context(ctx, inputs, output):
-    students, teachers, attns, proj_s, proj_t, log_temperatures, has_cls = inputs
+    students, teachers, attns, proj_s, proj_t, log_temperatures, has_cls = inputs[:7]
     ctx.n_students, ctx.n_teachers = len(students), len(teachers)
     ctx.has_cls = has_cls
     ctx.student_dtypes = [s.dtype for s in students]
@@ -203,7 +240,7 @@ def _backward(ctx, grads):
         grad_geo = torch.zeros((), device=ws.device)
     out = geo_backward(grad_geo, ws, students, teachers, attns, proj_s, proj_t, logt, ctx.has_cls)
     gs = [g.to(dt) if g.dtype != dt else g for g, dt in zip(out[1:], ctx.student_dtypes)]
-    return gs, [None] * Lt, [None] * Lt, None, None, out[0].to(logt.dtype), None
+    return gs, [None] * Lt, [None] * Lt, None, None, out[0].to(logt.dtype), None, None
 
 
 geo_forward.register_autograd(_backward, setup_context=_setup_context)
@@ -252,6 +289,13 @@ class HostStager:
         slot = self._slots[self._next]
         self._next = (self._next + 1) % self.depth
         has_cls = bool(self.module.teacher_has_cls_token)
+        # The async H2D copies issued from this slot's pinned staging buffers `depth` submits ago may still be in flight if the
+        # caller never synchronised in between: wait for them on the HOST before the staging buffers are rewritten
+        # (copy_stream.wait_stream below only orders the device side).  Caller-owned pinned inputs must likewise stay
+        # untouched until the event of the handle returned for them has completed.
+        prev = slot.get("copy_event")
+        if prev is not None:
+            prev.synchronize()
         # host-side gather of the attention rows the loss reads
         host_attn = {}
         for j, a in all_teacher_attns.items():
@@ -277,6 +321,7 @@ class HostStager:
             d_attn = {j: put(("a", j), t) for j, t in host_attn.items()}
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
+        slot["copy_event"] = ev
         self.h2d_bytes_last = nbytes
         return dict(event=ev, logits=d_logits, targets=d_targets, student=d_student, teacher=d_teacher, attn=d_attn)
 
@@ -305,17 +350,21 @@ def cls_attention_rows(q: torch.Tensor, k: torch.Tensor, scale: float | None = N
     B, H, S, dh = q.shape
     if scale is None:
         scale = dh ** -0.5
-    out = torch.empty(B, H, 1, S, dtype=torch.float32, device=q.device)
-    qs = (ctypes.c_int64 * 4)(*q.stride())
-    ks = (ctypes.c_int64 * 4)(*k.stride())
-    _lib.check(lib.basd_cls_attention_rows(q.data_ptr(), k.data_ptr(), _dtype_code(q), B, H, S, dh, qs, ks, float(scale), out.data_ptr(),
-                                           _stream_ptr()), "basd_cls_attention_rows")
+    if k.device != q.device or tuple(k.shape) != (B, H, S, dh):
+        raise _lib.BasdError(f"cls_attention_rows: q {tuple(q.shape)} on {q.device} and k {tuple(k.shape)} on {k.device} do not match")
+    with torch.cuda.device(q.device):
+        out = torch.empty(B, H, 1, S, dtype=torch.float32, device=q.device)
+        qs = (ctypes.c_int64 * 4)(*q.stride())
+        ks = (ctypes.c_int64 * 4)(*k.stride())
+        _lib.check(lib.basd_cls_attention_rows(q.data_ptr(), k.data_ptr(), _dtype_code(q), B, H, S, dh, qs, ks, float(scale), out.data_ptr(),
+                                               _stream_ptr(q.device)), "basd_cls_attention_rows")
     return out
 
 
 # --------------------------------------------------------------------------------------------- reference API
 def marchenko_pastur_rank(features: torch.Tensor) -> int:
-    """layer_selector.py:8-20 on the GPU (tcgen05 Gram + shared-memory Jacobi).  features: [M, D], D <= 224."""
+    """layer_selector.py:8-20 on the GPU (tcgen05 Gram + one-sided Jacobi).  features: [M, D], D a multiple of 8 up to 4096
+    (the second consumer, teacher.py:177, passes unprojected D_t-wide teacher features)."""
     lib = _lib.load()
     if features.device.type != "cuda":
         raise _lib.BasdError("marchenko_pastur_rank: CUDA tensor required (no CPU fallback)")
@@ -326,10 +375,11 @@ def marchenko_pastur_rank(features: torch.Tensor) -> int:
     M, D = features.shape
     nb = ctypes.c_size_t()
     _lib.check(lib.basd_mp_rank_workspace_bytes(M, D, ctypes.byref(nb)), "basd_mp_rank_workspace_bytes")
-    ws = torch.empty(nb.value, dtype=torch.uint8, device=features.device)
-    out = torch.zeros(1, dtype=torch.int32, device=features.device)
-    _lib.check(lib.basd_mp_rank(features.data_ptr(), M, D, _dtype_code(features), features.stride(0), out.data_ptr(), ws.data_ptr(),
-                                _stream_ptr()), "basd_mp_rank")
+    with torch.cuda.device(features.device):
+        ws = torch.empty(nb.value, dtype=torch.uint8, device=features.device)
+        out = torch.zeros(1, dtype=torch.int32, device=features.device)
+        _lib.check(lib.basd_mp_rank(features.data_ptr(), M, D, _dtype_code(features), features.stride(0), out.data_ptr(), ws.data_ptr(),
+                                    _stream_ptr(features.device)), "basd_mp_rank")
     return int(out.item())
 
 
@@ -380,6 +430,15 @@ class BASDLoss(nn.Module):
                                                         student_dim=student_dim, teacher_dim=teacher_dim)
         self.last_geo_loss = None
         self.last_ce_loss = None
+        # Newton-Schulz steps of the Procrustes polar iteration: 0 = the library default (10 steps: singular values of the
+        # cross-covariance down to 3e-5 ||C||_F converge).  Every forward leaves the largest residual ||X X^T - I||_F it saw
+        # going into its last step in `last_polar_residual` (device tensor, no sync).  It is read back asynchronously and
+        # looked at by the NEXT forward: above POLAR_RESIDUAL_OK (an ill-conditioned cross-covariance) the step count goes
+        # up by two (to at most 16) with a warning - one step late, never a host sync in the step.
+        self.polar_steps = 0
+        self.last_polar_residual = None
+        self._resid_host = None
+        self._resid_event = None
 
     def geo_loss(self, student_intermediates, all_teacher_tokens, all_teacher_attns) -> torch.Tensor:
         sel = self.layer_selector
@@ -389,11 +448,41 @@ class BASDLoss(nn.Module):
             raise _lib.BasdError(f"student tensors carry {students[0].shape[1]} tokens, module was built for {self.num_student_tokens}")
         teachers = [all_teacher_tokens[j] for j in t_idx]
         attns = [all_teacher_attns[j] for j in t_idx]
-        geo, _ws, ranks, w = geo_forward(students, teachers, attns, sel.proj_s, sel.proj_t, sel.log_temperatures,
-                                         bool(self.teacher_has_cls_token))
+        self._poll_polar_residual()
+        geo, _ws, ranks, w, resid = geo_forward(students, teachers, attns, sel.proj_s, sel.proj_t, sel.log_temperatures,
+                                                bool(self.teacher_has_cls_token), int(self.polar_steps))
         sel._ranks_dev, sel._rank_keys = ranks, t_idx
         sel.last_mixing_weights = w
+        resid = resid.detach()
+        self.last_polar_residual = resid
+        if self._resid_event is None and resid.device.type == "cuda":      # (the previous read-back has been consumed)
+            if self._resid_host is None:
+                self._resid_host = torch.empty(1, dtype=torch.float32, pin_memory=True)
+            self._resid_host.copy_(resid, non_blocking=True)
+            self._resid_event = torch.cuda.Event()
+            self._resid_event.record(torch.cuda.current_stream(resid.device))
         return geo
+
+    POLAR_RESIDUAL_OK = 0.1        # every |sigma^2 - 1| <= 0.1 going into the last step => every sigma within 1e-3 of 1 after it
+    POLAR_STEPS_MAX = 16
+
+    def _poll_polar_residual(self):
+        ev = self._resid_event
+        if ev is None or not ev.query():
+            return
+        self._resid_event = None
+        val = float(self._resid_host[0])
+        if not val <= self.POLAR_RESIDUAL_OK:                               # (NaN counts as not converged)
+            cur = self.polar_steps if self.polar_steps else 10
+            if cur < self.POLAR_STEPS_MAX:
+                self.polar_steps = min(cur + 2, self.POLAR_STEPS_MAX)
+                import warnings
+                warnings.warn(f"BASD Procrustes polar iteration: residual {val:.3g} > {self.POLAR_RESIDUAL_OK} after {cur} Newton-Schulz steps "
+                              f"(ill-conditioned teacher-student cross-covariance); using {self.polar_steps} steps from now on", RuntimeWarning)
+            else:
+                import warnings
+                warnings.warn(f"BASD Procrustes polar iteration: residual {val:.3g} after {cur} steps - the cross-covariance has singular values "
+                              "below fp32/split-bf16 resolution; their directions carry unconverged gradient weight", RuntimeWarning)
 
     def forward(self, student_output, targets, student_intermediates, all_teacher_tokens, all_teacher_attns):
         ce_loss = self.base_criterion(student_output, targets)
