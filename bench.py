@@ -209,6 +209,9 @@ def main():
     ap.add_argument("--cpu-sample-batch", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--views", action="store_true",
+                    help="hand the tokens over as the CLS-stripped views out[:, 1:, :] of [B, N+1, D] tensors, like trainer.py:29 / teacher.py:157 do "
+                         "(consumed in place; default: dense tensors)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -238,6 +241,13 @@ def main():
     torch.manual_seed(0)
     m = pkg.BASDLoss(nn.CrossEntropyLoss(label_smoothing=0.001), w.Ds, w.Dt, w.student_depth, w.Ns, config=synth.module_config(w),
                      teacher_has_cls_token=w.has_cls).to(dev)
+    if args.views:
+        def cls_view(t):
+            full = torch.zeros(t.shape[0], t.shape[1] + 1, t.shape[2], device=t.device, dtype=t.dtype)
+            full[:, 1:] = t
+            return full[:, 1:, :]
+        student = {k: cls_view(v) for k, v in student.items()}
+        teacher = {k: cls_view(v) for k, v in teacher.items()}
     logits.requires_grad_()
     for t in student.values():
         t.requires_grad_()
@@ -418,7 +428,8 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
             "config": {"workload": w.name, "per_gpu_batch": w.B, "global_batch": w.B * world, "Ns": w.Ns, "Nt": w.Nt, "Ds": w.Ds, "Dt": w.Dt,
-                       "Lt": w.Lt, "H": w.H, "P": w.P, "parallelism": f"dp{world} (batch-sharded, pooled statistics all-reduced)",
+                       "Lt": w.Lt, "H": w.H, "P": w.P, "token_tensors": "CLS-stripped [:,1:,:] views, consumed in place" if args.views else "dense",
+                       "parallelism": f"dp{world} (batch-sharded, pooled statistics all-reduced)",
                        "arithmetic": "bf16 tokens, fp32 accumulation, split-bf16 (hi+lo) tensor-core products, fp32 Jacobi",
                        "l2": f"inputs ({(w.Lt * w.B * w.Nt * w.Dt + w.P * w.B * w.Ns * w.Ds) * 2 / 1e9:.1f} GB of tokens per step) exceed the 126 MB L2; no explicit flush"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "loss": loss_val}

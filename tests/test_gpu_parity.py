@@ -247,6 +247,37 @@ def test_cfg1_against_reference_golden(lib, cuda_dev, act_dtype, views):
         assert rel(pr, g["grad_student_probe"][l]) < TOL_SGRAD
 
 
+def test_cls_stripped_bf16_views_are_consumed_in_place(lib, cuda_dev):
+    """trainer.py:29 / teacher.py:157 hand over out[:, 1:, :] views of [B, N+1, D] tensors.  bf16 views reach the kernels
+    without a copy (TMA descriptors / batch strides follow the view) and give the dense path's result."""
+    from vit_bias_aware_structural_distillation_b200 import loss as L
+    w = dataclasses.replace(synth.CONFIGS["cfg1"], B=4)
+    inp = synth.make_inputs(w)
+    m = build_module(w, cuda_dev)
+    dense = run_module(m, inp, cuda_dev, views=False)
+    viewed = run_module(m, inp, cuda_dev, views=True)
+    assert viewed["ranks"] == dense["ranks"]
+    assert abs(viewed["loss"].item() - dense["loss"].item()) <= 1e-6 * abs(dense["loss"].item())
+    assert rel(viewed["grad_log_temperatures"], dense["grad_log_temperatures"]) < 1e-4
+    for l in dense["grad_student"]:
+        assert rel(viewed["grad_student"][l], dense["grad_student"][l]) < 2e-3        # (bf16 gradient storage: 2^-9 per element)
+    assert_parity(viewed, oracle_case(m, inp, w), w)
+    # no copy: the pointers the C ABI receives are the views' own
+    def view(v):
+        full = torch.zeros(v.shape[0], v.shape[1] + 1, v.shape[2], device=cuda_dev, dtype=torch.bfloat16)
+        full[:, 1:] = v.to(cuda_dev)
+        return full[:, 1:, :]
+    sel = m.layer_selector
+    students = [view(inp["student"][l]) for l in m.token_layers]
+    teachers = [view(inp["teacher"][j]) for j in sorted(inp["teacher"])]
+    attns = [inp["attn"][j].to(cuda_dev) for j in sorted(inp["attn"])]
+    shape, cin, keep = L._prepare(students, teachers, attns, sel.proj_s, sel.proj_t, sel.log_temperatures, w.has_cls, 1)
+    assert [cin.student[i] for i in range(w.P)] == [t.data_ptr() for t in students]
+    assert [cin.teacher[j] for j in range(w.Lt)] == [t.data_ptr() for t in teachers]
+    assert cin.student_strides[0] == (w.Ns + 1) * w.Ds and cin.teacher_strides[0] == (w.Nt + 1) * w.Dt
+    del keep
+
+
 def _probes(shape, n=4, seed=99):
     gen = torch.Generator().manual_seed(seed)
     return [torch.randn(shape, generator=gen) for _ in range(n)]

@@ -130,7 +130,7 @@ Layout make_layout(const basd_shape& s) {
     const bool pack = s.act_dtype == BASD_DTYPE_F32;
     L.tpk = take(pack ? 2 * Lt * B * Nt * Dt : 0);
     L.spk = take(pack ? 2 * P * B * Ns * Ds : 0);
-    L.z = take(2 * 2 * Lt * B * Nt * Ds);          // projected teacher tokens, split pair: hi block then lo block
+    L.z = take(2 * 2 * Lt * B * (Nt + 1) * Ds);    // projected teacher tokens, split pair: hi block then lo block (rows of a CLS-stripped view: B (Nt + 1) - 1)
     L.stats = take(4 * (Lt + P) * (Ds * Ds + Ds));
     L.ranks = take(4 * Lt);
     L.sweeps = take(4 * (2 * Lt + P));
@@ -140,9 +140,10 @@ Layout make_layout(const basd_shape& s) {
     L.eig_scr = take(4 * pooled_eig_scratch_floats(s.Ds, 2 * s.Lt + s.P));   // D_s > 224: eigenproblem matrices in global memory
     // per-CTA partial results of the split-K Grams, column sums and weight-gradient dots (each summed in a fixed order)
     {
-        const size_t gp_t = gemm_gram_part_floats(B * Nt, s.Ds, s.Lt), gp_s = gemm_gram_part_floats(B * Ns, s.Ds, s.P);
+        // (sized for the CLS-stripped-view variants too: B (Nt + 1) projected rows; 64-row blocks per sample for the student)
+        const size_t gp_t = gemm_gram_part_floats(B * (Nt + 1), s.Ds, s.Lt), gp_s = gemm_gram_part_floats(B * ((Ns + 63) / 64 * 64), s.Ds, s.P);
         L.gram_part = take(4 * (gp_t > gp_s ? gp_t : gp_s));
-        const size_t cp_a = colsum_part_floats(s.Lt + s.P, B * Nt, s.Ds), cp_t = colsum_part_floats(s.Lt, B * Nt, s.Ds),
+        const size_t cp_a = colsum_part_floats(s.Lt + s.P, B * Nt, s.Ds), cp_t = colsum_part_floats(s.Lt, B * (Nt + 1), s.Ds),
                      cp_s = colsum_part_floats(s.P, B * Ns, s.Ds);
         const size_t cp = cp_a > cp_t ? (cp_a > cp_s ? cp_a : cp_s) : (cp_t > cp_s ? cp_t : cp_s);
         L.colsum_part = take(4 * cp);
@@ -229,18 +230,31 @@ int check_shape(const basd_shape& s) {
 }
 
 bool dense3(const int64_t* st, int N, int D) { return st[2] == 1 && st[1] == D && st[0] == static_cast<int64_t>(N) * D; }
+// the CLS-stripped view out[:, 1:, :] of a dense [B][N+1][D] tensor (trainer.py:29, teacher.py:157): consumed in place
+bool cls_view3(const int64_t* st, int N, int D) { return st[2] == 1 && st[1] == D && st[0] == static_cast<int64_t>(N + 1) * D; }
 
 struct Resolved {
     const __nv_bfloat16* teacher[BASD_MAX_LAYERS];
     const __nv_bfloat16* student[BASD_MAX_POINTS];
+    long long teacher_bs, student_bs;       // batch strides in elements
+    int teacher_gap, student_gap;           // 1: rows of the tensor read as a flat matrix carry one foreign row between samples
 };
 
 // After phase 1 the bf16, dense versions of the tokens are either the inputs themselves or the packed copies.
 int resolve(const basd_shape& s, const basd_inputs& in, uint8_t* ws, const Layout& L, Resolved* r) {
     const bool pack = s.act_dtype == BASD_DTYPE_F32;
+    r->teacher_bs = static_cast<long long>(s.Nt) * s.Dt; r->student_bs = static_cast<long long>(s.Ns) * s.Ds;
+    r->teacher_gap = 0; r->student_gap = 0;
     if (!pack) {
-        if (!dense3(in.teacher_strides, s.Nt, s.Dt) || !dense3(in.student_strides, s.Ns, s.Ds))
-            return fail("bf16 token tensors must be dense [B,N,D] (make them contiguous in the binding)");
+        // bf16 tokens are consumed in place by TMA: dense [B,N,D], or the CLS-stripped view of a dense [B,N+1,D] tensor
+        if (cls_view3(in.teacher_strides, s.Nt, s.Dt)) { r->teacher_gap = 1; r->teacher_bs = in.teacher_strides[0]; }
+        else if (!dense3(in.teacher_strides, s.Nt, s.Dt))
+            return fail("bf16 teacher tokens must be dense [B,N,D] or a [:,1:,:] view of a dense [B,N+1,D] tensor (strides %lld,%lld,%lld)",
+                        (long long)in.teacher_strides[0], (long long)in.teacher_strides[1], (long long)in.teacher_strides[2]);
+        if (cls_view3(in.student_strides, s.Ns, s.Ds)) { r->student_gap = 1; r->student_bs = in.student_strides[0]; }
+        else if (!dense3(in.student_strides, s.Ns, s.Ds))
+            return fail("bf16 student tokens must be dense [B,N,D] or a [:,1:,:] view of a dense [B,N+1,D] tensor (strides %lld,%lld,%lld)",
+                        (long long)in.student_strides[0], (long long)in.student_strides[1], (long long)in.student_strides[2]);
     }
     for (int j = 0; j < s.Lt; ++j) {
         if (!in.teacher[j] || !in.attn[j]) return fail("null teacher/attention pointer at layer %d", j);
@@ -323,41 +337,48 @@ extern "C" int basd_forward_stats(const basd_shape* shape, const basd_inputs* in
     delete pack_scope; pack_del.p = nullptr;
     Resolved r;
     if (resolve(s, in, ws, L, &r)) return 1;
+    // A CLS-stripped teacher view is projected as the dense matrix of B (Nt + 1) - 1 rows it is in memory; the rows that
+    // belong to no sample leave the projection as zeros, so the Gram and the column sums below are those of the B Nt tokens.
+    const size_t Mt_dense = Mt;
+    const size_t Mt_rows = r.teacher_gap ? static_cast<size_t>(s.B) * (s.Nt + 1) - 1 : Mt;
     __nv_bfloat16* z = reinterpret_cast<__nv_bfloat16*>(ws + L.z);
-    __nv_bfloat16* zlo = z + static_cast<size_t>(s.Lt) * Mt * s.Ds;
+    __nv_bfloat16* zlo = z + static_cast<size_t>(s.Lt) * Mt_rows * s.Ds;
     {
         Scope sc(2, st, (s.Lt + 15) / 16);
         const void* layers[kMaxLayers];
         for (int j = 0; j < s.Lt; ++j) layers[j] = r.teacher[j];
-        CK(gemm_project(layers, s.Lt, Mt, s.Dt, pt_hi, pt_lo, s.Ds, z, zlo, st));
+        CK(gemm_project(layers, s.Lt, Mt_rows, s.Dt, pt_hi, pt_lo, s.Ds, z, zlo, r.teacher_gap ? s.Nt + 1 : 0, s.Nt, st));
     }
     {
         Scope sc(3, st, 4);
         float* gram_part = reinterpret_cast<float*>(ws + L.gram_part);
-        CK(gemm_gram_batched(z, zlo, Mt, s.Ds, s.Lt, stats, static_cast<long long>(stat_stride), gram_part, st));
+        CK(gemm_gram_batched(z, zlo, Mt_rows, s.Ds, s.Lt, stats, static_cast<long long>(stat_stride), gram_part, st));
         const void* pts[kMaxPoints];
         for (int i = 0; i < s.P; ++i) pts[i] = r.student[i];
-        CK(gemm_gram_table(pts, s.P, Ms, s.Ds, stats + s.Lt * stat_stride, static_cast<long long>(stat_stride), gram_part, st));
+        CK(gemm_gram_table(pts, s.P, Ms, s.Ds, stats + s.Lt * stat_stride, static_cast<long long>(stat_stride), gram_part,
+                           r.student_gap ? s.Ns : 0, r.student_bs, st));
     }
     {
-        Scope sc(4, st, Mt == Ms ? 2 : 4);
+        const bool one_launch = Mt_rows == Ms && !r.student_gap;
+        Scope sc(4, st, one_launch ? 2 : 4);
         ColsumJobs jt, js;
         memset(&jt, 0, sizeof jt); memset(&js, 0, sizeof js);
         for (int j = 0; j < s.Lt; ++j) {
-            jt.hi[j] = z + static_cast<size_t>(j) * Mt * s.Ds; jt.lo[j] = zlo + static_cast<size_t>(j) * Mt * s.Ds;
+            jt.hi[j] = z + static_cast<size_t>(j) * Mt_rows * s.Ds; jt.lo[j] = zlo + static_cast<size_t>(j) * Mt_rows * s.Ds;
             jt.out[j] = stats + j * stat_stride + static_cast<size_t>(s.Ds) * s.Ds;
         }
         for (int i = 0; i < s.P; ++i) {
             js.hi[i] = r.student[i]; js.lo[i] = nullptr;
             js.out[i] = stats + (s.Lt + i) * stat_stride + static_cast<size_t>(s.Ds) * s.Ds;
         }
-        if (Mt == Ms) {                     // same row count: one launch covers teacher and student jobs
+        if (one_launch) {                   // same row count, same addressing: one launch covers teacher and student jobs
             for (int i = 0; i < s.P; ++i) { jt.hi[s.Lt + i] = js.hi[i]; jt.lo[s.Lt + i] = nullptr; jt.out[s.Lt + i] = js.out[i]; }
-            CK(launch_colsum(jt, s.Lt + s.P, Mt, s.Ds, reinterpret_cast<float*>(ws + L.colsum_part), st));
+            CK(launch_colsum(jt, s.Lt + s.P, Mt_rows, s.Ds, reinterpret_cast<float*>(ws + L.colsum_part), st));
         } else {
-            CK(launch_colsum(jt, s.Lt, Mt, s.Ds, reinterpret_cast<float*>(ws + L.colsum_part), st));
-            CK(launch_colsum(js, s.P, Ms, s.Ds, reinterpret_cast<float*>(ws + L.colsum_part), st));
+            CK(launch_colsum(jt, s.Lt, Mt_rows, s.Ds, reinterpret_cast<float*>(ws + L.colsum_part), st));
+            CK(launch_colsum(js, s.P, Ms, s.Ds, reinterpret_cast<float*>(ws + L.colsum_part), st, r.student_gap ? s.Ns : 0, r.student_bs));
         }
+        (void)Mt_dense;
     }
     return 0;
 }
@@ -395,7 +416,7 @@ extern "C" int basd_forward_solve(const basd_shape* shape, const basd_inputs* in
     __nv_bfloat16* tlo = reinterpret_cast<__nv_bfloat16*>(ws + L.tbar_lo);
     // teacher-token form: the mixed teacher stays on its own token grid (the resampling is folded into F, polar.cu)
     const bool vt = L.path == kPathTeacherTokens;
-    TIMED(8, 1, CK(launch_mix_teacher(tt, w, s.Lt, s.P, s.B, s.Nt, L.Nk, s.Dt, thi, tlo, st)));
+    TIMED(8, 1, CK(launch_mix_teacher(tt, w, s.Lt, s.P, s.B, s.Nt, L.Nk, s.Dt, thi, tlo, st, r.teacher_bs)));
     float* ktt = reinterpret_cast<float*>(ws + L.ktt);
     TIMED(9, 1, CK(gemm_token_gram(thi, tlo, s.P * s.B, L.Nk, s.Dt, ktt, st)));
 
@@ -403,6 +424,7 @@ extern "C" int basd_forward_solve(const basd_shape* shape, const basd_inputs* in
     memset(&pa, 0, sizeof pa);
     pa.Ns = s.Ns; pa.Ds = s.Ds; pa.B = s.B; pa.P = s.P; pa.NsPad = L.NsPad; pa.n_problems = s.P * s.B;
     for (int i = 0; i < s.P; ++i) pa.student[i] = r.student[i];
+    pa.student_bs = r.student_bs;
     pa.Ktt = ktt; pa.a = a; pa.ssum = ssum;
     {
         const long long nprob = pa.n_problems;
@@ -481,7 +503,7 @@ extern "C" int basd_backward_dots(const basd_shape* shape, const basd_inputs* in
                                      thi, tlo, s.P * s.B, L.Nk, s.Dt, dtm, dtm_lo, st)));
     float* gw = reinterpret_cast<float*>(ws + L.gw);
     TIMED(13, 3, CK(launch_wgrad_dots(tt, dtm, dtm_lo, reinterpret_cast<float*>(ws + L.gwt), reinterpret_cast<float*>(ws + L.rows), s.Lt, s.P, s.B, s.Nt,
-                         s.Ns, s.Dt, gw, reinterpret_cast<float*>(ws + L.gw_part), st, L.path == kPathTeacherTokens)));
+                         s.Ns, s.Dt, gw, reinterpret_cast<float*>(ws + L.gw_part), st, L.path == kPathTeacherTokens, r.teacher_bs)));
     return 0;
 }
 
@@ -505,12 +527,15 @@ extern "C" int basd_backward_finish(const basd_shape* shape, const basd_inputs* 
                            reinterpret_cast<float*>(ws + L.d2), in.log_temperatures, reinterpret_cast<float*>(ws + L.gamma),
                            reinterpret_cast<float*>(ws + L.stats), Ms, ghi, glo, corr, grad_log_temperatures, st)));
     const size_t MsL = static_cast<size_t>(s.B) * s.Ns;
+    // (a CLS-stripped student view enters the product as the dense matrix of B (Ns + 1) - 1 rows it is in memory; the
+    //  epilogue skips the rows between samples and writes the dense [B][Ns][Ds] gradient)
+    const size_t Ms_rows = r.student_gap ? static_cast<size_t>(s.B) * (s.Ns + 1) - 1 : MsL;
     Scope sg(15, st, s.P);
     for (int i = 0; i < s.P; ++i) {
         if (!grad_student[i]) return fail("null grad_student[%d]", i);
-        CK(gemm_student_grad(r.student[i], MsL, s.Ds, ghi + static_cast<size_t>(i) * s.Ds * s.Ds, glo + static_cast<size_t>(i) * s.Ds * s.Ds,
+        CK(gemm_student_grad(r.student[i], Ms_rows, s.Ds, ghi + static_cast<size_t>(i) * s.Ds * s.Ds, glo + static_cast<size_t>(i) * s.Ds * s.Ds,
                              reinterpret_cast<float*>(ws + L.gdir) + static_cast<size_t>(i) * MsL * s.Ds, corr + static_cast<size_t>(i) * s.Ds,
-                             grad_geo, scale, grad_student[i], grad_dtype == BASD_DTYPE_BF16, st));
+                             grad_geo, scale, grad_student[i], grad_dtype == BASD_DTYPE_BF16, r.student_gap ? s.Ns + 1 : 0, s.Ns, st));
     }
     return 0;
 }

@@ -132,9 +132,10 @@ using CfgTestTN  = GemmCfg<false, false, 192, 1, 1, 1, 1, false, 4>;
 // Z[j] = X[j] P_t^T for all L_t teacher layers in ONE launch (blockIdx.z = layer; the layers are separate tensors, so each
 // has its own tensor map in maps.a_table).  12 launches of 392 CTAs each left the last wave of every launch 65 % empty.
 cudaError_t gemm_project(const void* const* X, int n_layers, size_t M, int Dt, const __nv_bfloat16* Phi, const __nv_bfloat16* Plo, int Ds,
-                         __nv_bfloat16* Z, __nv_bfloat16* Zlo, cudaStream_t st) {
+                         __nv_bfloat16* Z, __nv_bfloat16* Zlo, int gap_period, int gap_valid, cudaStream_t st) {
     GemmArgs a;
     memset(&a, 0, sizeof a);
+    a.gap_period = gap_period; a.gap_valid = gap_valid;
     a.kb_total = cdiv(Dt, GEMM_BK);
     a.ld_out = Ds; a.rows_valid = static_cast<int>(M); a.cols_valid = Ds; a.alpha = 1.f;
     a.out_batch_stride = static_cast<long long>(M) * Ds; a.a_table = 1;
@@ -220,15 +221,26 @@ cudaError_t gemm_gram(const __nv_bfloat16* Z, const __nv_bfloat16* Zlo, size_t M
 }
 // G[i] += S_i^T S_i for n separate [M][Ds] bf16 tensors in ONE launch (blockIdx.z = tensor x split; a single Gram is 25
 // CTAs - four of them back to back were 4 x 50 us of latency)
-cudaError_t gemm_gram_table(const void* const* S, int n, size_t M, int Ds, float* G, long long g_stride, float* part, cudaStream_t st) {
+// rows_per_batch > 0: the tensors are [B][rows_per_batch][Ds] with batch stride batch_stride elements (CLS-stripped views):
+// the K dimension walks 64-row blocks per sample (GemmArgs::kb_per_batch), M = B * rows_per_batch
+cudaError_t gemm_gram_table(const void* const* S, int n, size_t M, int Ds, float* G, long long g_stride, float* part, int rows_per_batch,
+                            long long batch_stride, cudaStream_t st) {
     if (n > GEMM_MAX_A_TABLE) return cudaErrorInvalidValue;
     GemmMaps maps;
     memset(&maps, 0, sizeof maps);
-    for (int i = 0; i < n; ++i)
-        if (make_map(&maps.a_table[i], S[i], Ds, M, 1, Ds, M * Ds, 64)) return cudaErrorInvalidValue;
     GemmArgs a;
     memset(&a, 0, sizeof a);
-    gram_splits(M, &a.kb_total, &a.kb_per_split, &a.n_splits);
+    if (rows_per_batch > 0) {
+        const size_t B = M / rows_per_batch;
+        for (int i = 0; i < n; ++i)
+            if (make_map(&maps.a_table[i], S[i], Ds, rows_per_batch, B, Ds, batch_stride, 64)) return cudaErrorInvalidValue;
+        a.kb_per_batch = cdiv(rows_per_batch, GEMM_BK);
+        gram_splits(B * a.kb_per_batch * GEMM_BK, &a.kb_total, &a.kb_per_split, &a.n_splits);
+    } else {
+        for (int i = 0; i < n; ++i)
+            if (make_map(&maps.a_table[i], S[i], Ds, M, 1, Ds, M * Ds, 64)) return cudaErrorInvalidValue;
+        gram_splits(M, &a.kb_total, &a.kb_per_split, &a.n_splits);
+    }
     a.a_table = 1; a.b_table = 1;
     a.out = part; a.out_batch_stride = static_cast<long long>(Ds) * Ds; a.ld_out = Ds; a.rows_valid = Ds; a.cols_valid = Ds;
     const dim3 grid(cdiv(Ds, CfgGram::kBN), cdiv(Ds, CfgGram::kMT * 128), n * a.n_splits);
@@ -299,7 +311,7 @@ cudaError_t gemm_theta_apply(const __nv_bfloat16* theta, const __nv_bfloat16* th
 
 cudaError_t gemm_student_grad(const __nv_bfloat16* S, size_t M, int Ds, const __nv_bfloat16* Ghi, const __nv_bfloat16* Glo,
                               const float* gdir, const float* corr, const float* scale_ptr, float scale_host, void* out,
-                              int out_is_bf16, cudaStream_t st) {
+                              int out_is_bf16, int gap_period, int gap_valid, cudaStream_t st) {
     GemmMaps maps;
     memset(&maps, 0, sizeof maps);
     if (make_map(&maps.a[0], S, Ds, M, 1, Ds, M * Ds, 128)) return cudaErrorInvalidValue;
@@ -310,6 +322,7 @@ cudaError_t gemm_student_grad(const __nv_bfloat16* S, size_t M, int Ds, const __
     a.kb_total = cdiv(Ds, GEMM_BK);
     a.out = out; a.ld_out = Ds; a.rows_valid = static_cast<int>(M); a.cols_valid = Ds;
     a.aux0 = gdir; a.aux1 = corr; a.aux2 = scale_ptr; a.alpha = scale_host; a.beta = out_is_bf16 ? 1.f : 0.f;
+    a.gap_period = gap_period; a.gap_valid = gap_valid;
     return launch<CfgStudentGrad, EpiStudentGrad>(maps, a, dim3(cdiv(Ds, CfgStudentGrad::kBN), cdiv(M, 128), 1), st);
 }
 

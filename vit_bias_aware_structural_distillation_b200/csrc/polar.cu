@@ -86,7 +86,7 @@ polar_prep_student_kernel(PolarArgs g) {
     float* red = mu + D;                              // 40
     const int prob = blockIdx.x;
     const int i = prob / g.B, b = prob % g.B;
-    const __nv_bfloat16* S = g.student[i] + static_cast<size_t>(b) * N * D;
+    const __nv_bfloat16* S = g.student[i] + static_cast<size_t>(b) * g.student_bs;
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
         const float a = g.a[static_cast<size_t>(prob) * N + n];
         a_s[n] = a;
@@ -164,7 +164,7 @@ polar_prep_student_vec_kernel(PolarArgs g) {
     float* partial = red + 40;                                      // [slices][D]
     const int prob = blockIdx.x;
     const int i = prob / g.B, b = prob % g.B;
-    const __nv_bfloat16* S = g.student[i] + static_cast<size_t>(b) * N * D;
+    const __nv_bfloat16* S = g.student[i] + static_cast<size_t>(b) * g.student_bs;
     const __nv_bfloat16* raw = STAGE ? reinterpret_cast<const __nv_bfloat16*>(sm_raw) : S;      // [N][pitch]
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
         const float a = g.a[static_cast<size_t>(prob) * N + n];

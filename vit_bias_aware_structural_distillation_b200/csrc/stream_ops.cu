@@ -161,7 +161,7 @@ cudaError_t launch_pack_bf16(const void* src, int src_is_bf16, long long sb, lon
 // (atomicAdd made the column sums, hence the centred Grams, differ from launch to launch).
 constexpr int kColsumThreads = 256;
 __global__ void __launch_bounds__(kColsumThreads)
-colsum_kernel(ColsumJobs jobs, size_t rows, int D, float* __restrict__ part) {
+colsum_kernel(ColsumJobs jobs, size_t rows, int D, float* __restrict__ part, int rpb, long long bstride) {
     __shared__ float red[kColsumThreads * 8];
     const int j = blockIdx.y;
     const __nv_bfloat16* Xh = jobs.hi[j];
@@ -172,12 +172,14 @@ colsum_kernel(ColsumJobs jobs, size_t rows, int D, float* __restrict__ part) {
     const size_t chunk = (rows + gridDim.x - 1) / gridDim.x;
     const size_t r0 = blockIdx.x * chunk, r1 = r0 + chunk < rows ? r0 + chunk : rows;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    // rpb > 0: row r is token r % rpb of sample r / rpb of a [B][rpb][D] tensor with batch stride bstride elements
+    auto row_off = [&](size_t r) -> size_t { return rpb > 0 ? (r / rpb) * static_cast<size_t>(bstride) + (r % rpb) * static_cast<size_t>(D) : r * D; };
     if (lr < rpp) {
         size_t r = r0 + lr;
         for (; r + 3 * static_cast<size_t>(rpp) < r1; r += 4 * static_cast<size_t>(rpp)) {
             uint4 v[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = ld_nc_16(Xh + (r + static_cast<size_t>(u) * rpp) * D + cv * 8);
+            for (int u = 0; u < 4; ++u) v[u] = ld_nc_16(Xh + row_off(r + static_cast<size_t>(u) * rpp) + cv * 8);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 float f[8];
@@ -187,7 +189,7 @@ colsum_kernel(ColsumJobs jobs, size_t rows, int D, float* __restrict__ part) {
             }
             if (Xl) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) v[u] = ld_nc_16(Xl + (r + static_cast<size_t>(u) * rpp) * D + cv * 8);
+                for (int u = 0; u < 4; ++u) v[u] = ld_nc_16(Xl + row_off(r + static_cast<size_t>(u) * rpp) + cv * 8);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     float f[8];
@@ -199,11 +201,11 @@ colsum_kernel(ColsumJobs jobs, size_t rows, int D, float* __restrict__ part) {
         }
         for (; r < r1; r += rpp) {
             float f[8];
-            bf16x8_to_float(ld_nc_16(Xh + r * D + cv * 8), f);
+            bf16x8_to_float(ld_nc_16(Xh + row_off(r) + cv * 8), f);
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc[i] += f[i];
             if (Xl) {
-                bf16x8_to_float(ld_nc_16(Xl + r * D + cv * 8), f);
+                bf16x8_to_float(ld_nc_16(Xl + row_off(r) + cv * 8), f);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) acc[i] += f[i];
             }
@@ -233,10 +235,11 @@ static int colsum_chunks(int n_jobs, size_t rows) {
     return chunks;
 }
 size_t colsum_part_floats(int n_jobs, size_t rows, int D) { return static_cast<size_t>(n_jobs) * colsum_chunks(n_jobs, rows) * D; }
-cudaError_t launch_colsum(const ColsumJobs& jobs, int n_jobs, size_t rows, int D, float* part, cudaStream_t st) {
+cudaError_t launch_colsum(const ColsumJobs& jobs, int n_jobs, size_t rows, int D, float* part, cudaStream_t st, int rows_per_batch,
+                          long long batch_stride) {
     if (D % 8 != 0 || D > 8 * kColsumThreads || n_jobs < 1 || !part) return cudaErrorInvalidValue;
     const int chunks = colsum_chunks(n_jobs, rows);
-    colsum_kernel<<<dim3(chunks, n_jobs), kColsumThreads, 0, st>>>(jobs, rows, D, part);
+    colsum_kernel<<<dim3(chunks, n_jobs), kColsumThreads, 0, st>>>(jobs, rows, D, part, rows_per_batch, batch_stride);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     colsum_reduce_kernel<<<n_jobs, 256, 0, st>>>(jobs, part, chunks, D);
@@ -280,7 +283,7 @@ cudaError_t launch_importance_mix(const float* rows, const float* w, int Lt, int
 constexpr int MT_JC = 12;
 template <int PMAX, bool INTERP>
 __global__ void __launch_bounds__(256)
-mix_teacher_kernel(PtrTable teacher, const float* __restrict__ w, int Lt, int P, int B, int Nt, int Ns, int Dt,
+mix_teacher_kernel(PtrTable teacher, const float* __restrict__ w, int Lt, int P, int B, int Nt, int Ns, int Dt, long long tbs,
                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
     __shared__ float ws[PMAX * kMaxLayers];
     for (int t = threadIdx.x; t < P * Lt; t += blockDim.x) ws[t] = w[t];
@@ -303,7 +306,7 @@ mix_teacher_kernel(PtrTable teacher, const float* __restrict__ w, int Lt, int P,
 #pragma unroll
             for (int jj = 0; jj < MT_JC; ++jj) {
                 const bool ok = j0 + jj < Lt;
-                const __nv_bfloat16* T = reinterpret_cast<const __nv_bfloat16*>(teacher.p[ok ? j0 + jj : 0]) + (static_cast<size_t>(b) * Nt) * Dt + dv * 8;
+                const __nv_bfloat16* T = reinterpret_cast<const __nv_bfloat16*>(teacher.p[ok ? j0 + jj : 0]) + static_cast<size_t>(b) * tbs + dv * 8;
                 t0[jj] = ok ? ld_nc_16(T + static_cast<size_t>(i0) * Dt) : zero4;
                 if (INTERP) t1[jj] = ok ? ld_nc_16(T + static_cast<size_t>(i1) * Dt) : zero4;
             }
@@ -353,18 +356,19 @@ mix_teacher_kernel(PtrTable teacher, const float* __restrict__ w, int Lt, int P,
     }
 }
 cudaError_t launch_mix_teacher(const PtrTable& teacher, const float* w, int Lt, int P, int B, int Nt, int Ns, int Dt,
-                               __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st) {
+                               __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st, long long tbs) {
+    if (tbs <= 0) tbs = static_cast<long long>(Nt) * Dt;
     if (Dt % 8 != 0 || P > kMaxPoints) return cudaErrorInvalidValue;
     const size_t total = static_cast<size_t>(B) * Ns * (Dt / 8);
     const int blocks = static_cast<int>((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
     if (static_cast<unsigned long long>(B) * Ns * (Dt / 8) >= (1ull << 32)) return cudaErrorInvalidValue;
     const bool interp = Nt != Ns;
     if (P <= 4) {
-        if (interp) mix_teacher_kernel<4, true><<<blocks, 256, 0, st>>>(teacher, w, Lt, P, B, Nt, Ns, Dt, hi, lo);
-        else mix_teacher_kernel<4, false><<<blocks, 256, 0, st>>>(teacher, w, Lt, P, B, Nt, Ns, Dt, hi, lo);
+        if (interp) mix_teacher_kernel<4, true><<<blocks, 256, 0, st>>>(teacher, w, Lt, P, B, Nt, Ns, Dt, tbs, hi, lo);
+        else mix_teacher_kernel<4, false><<<blocks, 256, 0, st>>>(teacher, w, Lt, P, B, Nt, Ns, Dt, tbs, hi, lo);
     } else {
-        if (interp) mix_teacher_kernel<8, true><<<blocks, 256, 0, st>>>(teacher, w, Lt, P, B, Nt, Ns, Dt, hi, lo);
-        else mix_teacher_kernel<8, false><<<blocks, 256, 0, st>>>(teacher, w, Lt, P, B, Nt, Ns, Dt, hi, lo);
+        if (interp) mix_teacher_kernel<8, true><<<blocks, 256, 0, st>>>(teacher, w, Lt, P, B, Nt, Ns, Dt, tbs, hi, lo);
+        else mix_teacher_kernel<8, false><<<blocks, 256, 0, st>>>(teacher, w, Lt, P, B, Nt, Ns, Dt, tbs, hi, lo);
     }
     return cudaGetLastError();
 }
@@ -379,7 +383,7 @@ constexpr int WG_PC = 4, WG_JC = 12;
 template <bool INTERP, bool SPLIT>
 __global__ void __launch_bounds__(256)
 wgrad_dots_kernel(PtrTable teacher, const __nv_bfloat16* __restrict__ Dtm, const __nv_bfloat16* __restrict__ DtmLo, int Lt, int P, int B, int Nt,
-                  int Ns, int Dt, float* __restrict__ gw_part) {
+                  int Ns, int Dt, long long tbs, float* __restrict__ gw_part) {
     const int n_jc = (Lt + WG_JC - 1) / WG_JC;
     const int i_base = (blockIdx.y / n_jc) * WG_PC, j_base = (blockIdx.y % n_jc) * WG_JC;
     float acc[WG_PC][WG_JC];
@@ -405,7 +409,7 @@ wgrad_dots_kernel(PtrTable teacher, const __nv_bfloat16* __restrict__ Dtm, const
 #pragma unroll
         for (int j = 0; j < WG_JC; ++j) {
             const bool ok = j_base + j < Lt;
-            const __nv_bfloat16* T = reinterpret_cast<const __nv_bfloat16*>(teacher.p[ok ? j_base + j : 0]) + (static_cast<size_t>(b) * Nt) * Dt + dv * 8;
+            const __nv_bfloat16* T = reinterpret_cast<const __nv_bfloat16*>(teacher.p[ok ? j_base + j : 0]) + static_cast<size_t>(b) * tbs + dv * 8;
             t0[j] = ok ? ld_nc_16(T + static_cast<size_t>(i0) * Dt) : zero4;
             if (INTERP) t1[j] = ok ? ld_nc_16(T + static_cast<size_t>(i1) * Dt) : zero4;
         }
@@ -486,16 +490,17 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ gw_part, int n_par
 constexpr int kWgradDotCtas = 148 * 4, kWgradImpSlices = 16;
 size_t wgrad_part_floats(int P, int Lt) { return static_cast<size_t>(kWgradDotCtas + kWgradImpSlices) * P * Lt; }
 cudaError_t launch_wgrad_dots(const PtrTable& teacher, const __nv_bfloat16* Dtm, const __nv_bfloat16* DtmLo, const float* gwt, const float* rows, int Lt, int P,
-                              int B, int Nt, int Ns, int Dt, float* gw, float* gw_part, cudaStream_t st, bool dtm_unaligned) {
+                              int B, int Nt, int Ns, int Dt, float* gw, float* gw_part, cudaStream_t st, bool dtm_unaligned, long long tbs) {
+    if (tbs <= 0) tbs = static_cast<long long>(Nt) * Dt;
     if (Dt % 8 != 0 || static_cast<unsigned long long>(B) * Ns * (Dt / 8) >= (1ull << 32) || !gw_part) return cudaErrorInvalidValue;
     const int ny = ((P + WG_PC - 1) / WG_PC) * ((Lt + WG_JC - 1) / WG_JC);
     const dim3 grid(kWgradDotCtas, ny);
     if (Nt == Ns || dtm_unaligned) {
-        if (DtmLo) wgrad_dots_kernel<false, true><<<grid, 256, 0, st>>>(teacher, Dtm, DtmLo, Lt, P, B, Nt, Nt, Dt, gw_part);
-        else wgrad_dots_kernel<false, false><<<grid, 256, 0, st>>>(teacher, Dtm, DtmLo, Lt, P, B, Nt, Nt, Dt, gw_part);
+        if (DtmLo) wgrad_dots_kernel<false, true><<<grid, 256, 0, st>>>(teacher, Dtm, DtmLo, Lt, P, B, Nt, Nt, Dt, tbs, gw_part);
+        else wgrad_dots_kernel<false, false><<<grid, 256, 0, st>>>(teacher, Dtm, DtmLo, Lt, P, B, Nt, Nt, Dt, tbs, gw_part);
     } else {
-        if (DtmLo) wgrad_dots_kernel<true, true><<<grid, 256, 0, st>>>(teacher, Dtm, DtmLo, Lt, P, B, Nt, Ns, Dt, gw_part);
-        else wgrad_dots_kernel<true, false><<<grid, 256, 0, st>>>(teacher, Dtm, DtmLo, Lt, P, B, Nt, Ns, Dt, gw_part);
+        if (DtmLo) wgrad_dots_kernel<true, true><<<grid, 256, 0, st>>>(teacher, Dtm, DtmLo, Lt, P, B, Nt, Ns, Dt, tbs, gw_part);
+        else wgrad_dots_kernel<true, false><<<grid, 256, 0, st>>>(teacher, Dtm, DtmLo, Lt, P, B, Nt, Ns, Dt, tbs, gw_part);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;

@@ -44,6 +44,14 @@ struct GemmArgs {
     long long aux_batch_stride;
     float alpha;
     float beta;
+    // Row-gapped A operand (K-major, rows = M): a [B][N+1][D] buffer read through its CLS-stripped view [:,1:,:] is a dense
+    // 2-D matrix whose rows r with r % gap_period >= gap_valid belong to no sample (trainer.py:29, teacher.py:157 hand such
+    // views over).  gap_period == 0: no gaps.  Epilogues zero (project) or skip (student_grad) those rows.
+    int gap_period, gap_valid;
+    // MN-major operands whose K dimension runs over the rows of a [B][N][D] tensor with an arbitrary batch stride: the tensor
+    // map is 3-D (D, N, B) and k-block kb covers rows (kb % kb_per_batch) * 64.. of sample kb / kb_per_batch; rows past N are
+    // zero-filled by TMA.  kb_per_batch == 0: flat rows.
+    int kb_per_batch;
 };
 
 template <bool A_MN, bool B_MN, int BN, int MT, int NA, int NB, int NTERMS, bool B_ALIAS_A, int STAGES>
@@ -123,9 +131,11 @@ umma_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
                     uint8_t* dst = st + i * Cfg::kABytes;
                     const CUtensorMap* amap = args.a_table ? &maps.a_table[batch] : &maps.a[i];
                     if (Cfg::kAMN) {
+                        const int krow = args.kb_per_batch ? (kb % args.kb_per_batch) * GEMM_BK : kb * GEMM_BK;
+                        const int kz = args.kb_per_batch ? kb / args.kb_per_batch : za;
 #pragma unroll
                         for (int g = 0; g < Cfg::kMT * 2; ++g)
-                            tma_load_3d(dst + g * 8192, amap, &full_bar[s], a_row0 + g * 64, kb * GEMM_BK, za);
+                            tma_load_3d(dst + g * 8192, amap, &full_bar[s], a_row0 + g * 64, krow, kz);
                     } else {
 #pragma unroll
                         for (int mt = 0; mt < Cfg::kMT; ++mt)
@@ -138,9 +148,11 @@ umma_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
                         uint8_t* dst = st + Cfg::kNA * Cfg::kABytes + i * Cfg::kBBytes;
                         const CUtensorMap* bmap = args.b_table ? &maps.a_table[batch] : &maps.b[i];
                         if (Cfg::kBMN) {
+                            const int krow = args.kb_per_batch ? (kb % args.kb_per_batch) * GEMM_BK : kb * GEMM_BK;
+                            const int kz = args.kb_per_batch ? kb / args.kb_per_batch : zb;
 #pragma unroll
                             for (int g = 0; g < Cfg::kBN / 64; ++g)
-                                tma_load_3d(dst + g * 8192, bmap, &full_bar[s], b_row0 + g * 64, kb * GEMM_BK, zb);
+                                tma_load_3d(dst + g * 8192, bmap, &full_bar[s], b_row0 + g * 64, krow, kz);
                         } else {
                             tma_load_3d(dst, bmap, &full_bar[s], kb * GEMM_BK, b_row0, zb);
                         }
@@ -235,15 +247,22 @@ struct EpiStoreBf16 {                     // out[batch][row][col] = bf16(alpha *
 };
 
 struct EpiStoreSplit {                    // out = hi, aux0 = lo:  hi = bf16(acc), lo = bf16(acc - hi)   (fp32-class storage)
-    __nv_bfloat16* hi; __nv_bfloat16* lo; int ld, rows, cols;
+    __nv_bfloat16* hi; __nv_bfloat16* lo; int ld, rows, cols, gap_period, gap_valid;
     __device__ EpiStoreSplit(const GemmArgs& a, int batch, int) {
         hi = reinterpret_cast<__nv_bfloat16*>(a.out) + batch * a.out_batch_stride;
         lo = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(a.aux0)) + batch * a.out_batch_stride;
-        ld = a.ld_out; rows = a.rows_valid; cols = a.cols_valid;
+        ld = a.ld_out; rows = a.rows_valid; cols = a.cols_valid; gap_period = a.gap_period; gap_valid = a.gap_valid;
     }
-    __device__ void operator()(int row, int col0, const float* v) const {
+    __device__ void operator()(int row, int col0, const float* vin) const {
         if (row >= rows || col0 >= cols) return;
         const long long off = static_cast<long long>(row) * ld + col0;
+        float vz[16];
+        const float* v = vin;
+        if (gap_period && row % gap_period >= gap_valid) {          // a row between two samples (another sample's CLS token): zeros,
+#pragma unroll
+            for (int i = 0; i < 16; ++i) vz[i] = 0.f;               // so the Gram and the column sums over these rows are unaffected
+            v = vz;
+        }
         if (col0 + 16 <= cols) {
             uint32_t hw[8], lw[8];
 #pragma unroll
@@ -343,14 +362,21 @@ struct EpiThetaApply {
 //   aux0 = gdir fp32 [rows][cols] (direct-path gradient, unscaled), aux1 = corr fp32 [cols] (= mu^T Gamma)
 //   out dtype: beta == 0 -> fp32, beta == 1 -> bf16
 struct EpiStudentGrad {
-    void* out; const float* gdir; const float* corr; int ld, rows, cols; float alpha; bool bf16_out;
+    void* out; const float* gdir; const float* corr; int ld, rows, cols, gap_period, gap_valid; float alpha; bool bf16_out;
     __device__ EpiStudentGrad(const GemmArgs& g, int, int) {
         out = g.out; gdir = reinterpret_cast<const float*>(g.aux0); corr = reinterpret_cast<const float*>(g.aux1);
         ld = g.ld_out; rows = g.rows_valid; cols = g.cols_valid; bf16_out = g.beta != 0.f;
+        gap_period = g.gap_period; gap_valid = g.gap_valid;
         alpha = g.alpha * (g.aux2 ? *reinterpret_cast<const float*>(g.aux2) : 1.f);
     }
-    __device__ void operator()(int row, int col0, const float* v) const {
-        if (row >= rows || col0 >= cols) return;
+    __device__ void operator()(int row_in, int col0, const float* v) const {
+        if (row_in >= rows || col0 >= cols) return;
+        int row = row_in;
+        if (gap_period) {                  // input rows are the CLS-stripped view of a [B][N+1][D] buffer; the gradient is dense [B][N][D]
+            const int b = row_in / gap_period, n = row_in - b * gap_period;
+            if (n >= gap_valid) return;
+            row = b * gap_valid + n;
+        }
         const long long off = static_cast<long long>(row) * ld + col0;
         float r[16];
         const float* gp = gdir + static_cast<long long>(row) * cols + col0;

@@ -55,9 +55,17 @@ def _prepare(students: Sequence[torch.Tensor], teachers: Sequence[torch.Tensor],
         act_dt = torch.float32
     teachers = [t if t.dtype == act_dt else t.to(act_dt) for t in teachers]
     students = [s if s.dtype == act_dt else s.to(act_dt) for s in students]
-    if act_dt == torch.bfloat16:            # bf16 operands are consumed in place by TMA and must be dense
-        students = [s.contiguous() for s in students]
-        teachers = [t.contiguous() for t in teachers]
+    if act_dt == torch.bfloat16:
+        # bf16 operands are consumed IN PLACE by TMA: dense [B,N,D] tensors, or the CLS-stripped views out[:, 1:, :] of dense
+        # [B,N+1,D] tensors that the reference's extraction hooks hand over (trainer.py:29, teacher.py:157) - no copy for
+        # either.  Anything else (e.g. the CNN [B,HW,C] transposed view, teacher.py:155) is made contiguous once.
+        def in_place(t):
+            n, d = t.shape[1], t.shape[2]
+            return t.is_contiguous() or (t.stride() == ((n + 1) * d, d, 1) and t.data_ptr() % 16 == 0)
+        if not all(in_place(s) for s in students) or len({s.stride() for s in students}) > 1:
+            students = [s.contiguous() for s in students]
+        if not all(in_place(t) for t in teachers) or len({t.stride() for t in teachers}) > 1:
+            teachers = [t.contiguous() for t in teachers]
     else:                                   # fp32: the pack kernel reads through arbitrary strides; equalise them
         if len({s.stride() for s in students}) > 1:
             students = [s.contiguous() for s in students]
