@@ -84,7 +84,9 @@ int basd_backward_finish(const basd_shape* shape, const basd_inputs* in, void* w
  * "polar_*" (state of the polar iteration; bf16 views count hi then lo elements). */
 int basd_view(const basd_shape* shape, void* workspace, const char* name, void** ptr, size_t* count);
 
-/* marchenko_pastur_rank(features[M,D]) (layer_selector.py:8-20), rank written to device int; D <= 224 and a multiple of 8; either branch of :12-15 (M >= D, M < D).
+/* marchenko_pastur_rank(features[M,D]) (layer_selector.py:8-20), rank written to device int; D a multiple of 8 up to 4096
+ * (teacher.py:177 passes unprojected D_t-wide features: D <= 224 runs in shared memory, <= 384 on the cluster solver, larger on
+ * the one-CTA global-memory solver); either branch of :12-15 (M >= D, M < D).
  * workspace: at least basd_mp_rank_workspace_bytes(M, D). */
 int basd_mp_rank_workspace_bytes(int64_t M, int D, size_t* bytes);
 int basd_mp_rank(const void* features, int64_t M, int D, int dtype, int64_t row_stride, int* rank_out, void* workspace,
@@ -98,11 +100,19 @@ int basd_mp_rank(const void* features, int64_t M, int D, int dtype, int64_t row_
 int basd_cls_attention_rows(const void* q, const void* k, int dtype, int B, int H, int S, int dh, const int64_t* q_strides,
                             const int64_t* k_strides, float scale, float* out, void* stream);
 
+/* Host-resident teacher attention (an offline / CPU-resident teacher): copies the CLS query rows of a HOST map [B,H,S,S]
+ * (element strides (b,h,q,k), k stride 1, 2- or 4-byte elements) to a dense DEVICE tensor [B,H,1,S] with one pitched DMA -
+ * the only part of the map relational.py:24 reads.  Asynchronous on `stream` when the host memory is pinned. */
+int basd_copy_cls_rows_h2d(const void* host_attn, int elem_bytes, int B, int H, int S, const int64_t* strides, void* dev_rows,
+                           void* stream);
+
 /* Test hooks (used by tests/ only). */
 int basd_selftest_gemm(int variant, const void* A, const void* B, float* C, int M, int N, int K, void* stream);
 int basd_selftest_eig(const float* G, int n, float* evals, float* evecs, int* sweeps, void* workspace, void* stream);
 
-/* Live timing (CUDA events on the launching stream around each kernel group) and launch counting, for bench.py. */
+/* Live timing (CUDA events on the launching stream around each kernel group) and launch counting, for bench.py.
+ * A single-caller measurement facility: the event brackets are process-global and NOT re-entrant (off by default; the
+ * launch counter is atomic).  The compute entry points themselves keep no mutable process state. */
 void basd_timing_enable(int on);
 void basd_timing_reset(void);
 long long basd_launch_count(void);
@@ -115,6 +125,10 @@ int basd_polar_steps(void);
 /* Products launched per Newton-Schulz step for these sizes: 3 when A = T W^T and the polynomial in A are fused into one
  * kernel (D_s <= 192), 4 otherwise.  For bench.py's launch and byte counts. */
 int basd_polar_launches_per_step(int Ds, int Ns);
+
+/* Development aids (tools/gpu_debug_*.py): phase clocks recorded by one CTA when BASD_POLAR_DBG / BASD_SPECTRAL_DBG is set. */
+int basd_debug_polar_clocks(int which, long long* host_out);
+int basd_debug_spectral_clocks(long long* host_out);
 
 const char* basd_last_error(void);
 const char* basd_version(void);

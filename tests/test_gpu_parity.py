@@ -446,10 +446,7 @@ def test_full_size_properties(lib, cuda_dev):
     assert abs(geo4.item()) < 2e-3 * abs(geo.item())
 
 
-def test_two_rank_sharding_matches_single_process(lib, cuda_dev, tmp_path):
-    """SURVEY.md §8(e): two ranks each holding half the batch, pooled statistics and d loss / d w summed across
-    ranks, against ONE process on the concatenated batch.  Both ranks share cuda:0 (gloo moves the CUDA buffers),
-    so the test runs on a single-GPU box; on multi-GPU boxes bench.py exercises the same code over NCCL."""
+def _two_rank_case(cuda_dev, tmp_path, env_extra):
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -458,7 +455,7 @@ def test_two_rank_sharding_matches_single_process(lib, cuda_dev, tmp_path):
     port = 29500 + (os.getpid() % 2000)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(root, "tests", "sharded_worker.py"), str(out)]
-    env = dict(os.environ, BASD_SHARD_DEVICE="cuda:0")
+    env = dict(os.environ, **env_extra)
     r = subprocess.run(cmd, cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     w = dataclasses.replace(synth.CONFIGS["cfg1"], B=8)
@@ -476,6 +473,22 @@ def test_two_rank_sharding_matches_single_process(lib, cuda_dev, tmp_path):
         # per-rank loss is the mean over the local half batch -> local gradients are 2x the global-mean gradients
         cat = torch.cat([parts[0]["grad_student"][l], parts[1]["grad_student"][l]]) / 2
         assert rel(cat, single["grad_student"][l]) < TOL_SGRAD
+
+
+def test_two_rank_sharding_matches_single_process(lib, cuda_dev, tmp_path):
+    """SURVEY.md §8(e): two ranks each holding half the batch, pooled statistics and d loss / d w summed across
+    ranks, against ONE process on the concatenated batch.  Both ranks share cuda:0 (gloo moves the CUDA buffers),
+    so the test runs on a single-GPU box; the NCCL variant below needs two GPUs."""
+    _two_rank_case(cuda_dev, tmp_path, {"BASD_SHARD_DEVICE": "cuda:0"})
+
+
+def test_two_rank_nccl_on_two_gpus_matches_single_process(lib, cuda_dev, tmp_path):
+    """The same comparison with one rank per GPU over NCCL (the configuration bench.py and a real run use): loss, ranks,
+    mixing weights, temperature gradients and the concatenated student gradients of two ranks on two B200s against a
+    single process on the whole batch.  Skipped on single-GPU boxes."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    _two_rank_case(cuda_dev, tmp_path, {})
 
 
 def test_host_stager_matches_device_path(lib, cuda_dev):

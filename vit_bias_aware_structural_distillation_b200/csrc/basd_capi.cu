@@ -586,6 +586,30 @@ extern "C" int basd_cls_attention_rows(const void* q, const void* k, int dtype, 
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------- host attention rows
+// Of a teacher attention map [B,H,S,S] in HOST memory the loss reads the CLS query row only (relational.py:24).  One pitched
+// DMA per layer (width = one row, pitch = one map) moves exactly those rows to a dense device [B,H,1,S] tensor - no host-side
+// gather, no staging buffer; asynchronous when the host tensor is pinned.
+extern "C" int basd_copy_cls_rows_h2d(const void* host_attn, int elem_bytes, int B, int H, int S, const int64_t* strides, void* dev_rows,
+                                      void* stream) {
+    if (!host_attn || !dev_rows || !strides) return fail("null argument");
+    if (B < 1 || H < 1 || S < 1 || (elem_bytes != 2 && elem_bytes != 4)) return fail("invalid attention shape");
+    if (strides[3] != 1) return fail("basd_copy_cls_rows_h2d: the key stride must be 1");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t width = static_cast<size_t>(S) * elem_bytes;
+    const char* src = reinterpret_cast<const char*>(host_attn);
+    char* dst = reinterpret_cast<char*>(dev_rows);
+    if (strides[0] == static_cast<int64_t>(H) * strides[1]) {          // (b, h) rows equally spaced: one copy
+        CK(cudaMemcpy2DAsync(dst, width, src, static_cast<size_t>(strides[1]) * elem_bytes, width, static_cast<size_t>(B) * H,
+                             cudaMemcpyHostToDevice, st));
+    } else {
+        for (int b = 0; b < B; ++b)
+            CK(cudaMemcpy2DAsync(dst + static_cast<size_t>(b) * H * width, width, src + static_cast<size_t>(b) * strides[0] * elem_bytes,
+                                 static_cast<size_t>(strides[1]) * elem_bytes, width, H, cudaMemcpyHostToDevice, st));
+    }
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------- test hooks
 extern "C" int basd_selftest_gemm(int variant, const void* A, const void* B, float* C, int M, int N, int K, void* stream) {
     CK(gemm_selftest(variant, reinterpret_cast<const __nv_bfloat16*>(A), reinterpret_cast<const __nv_bfloat16*>(B), C, M, N, K,

@@ -304,10 +304,14 @@ class HostStager:
         prev = slot.get("copy_event")
         if prev is not None:
             prev.synchronize()
-        # host-side gather of the attention rows the loss reads
-        host_attn = {}
+        # Of a [B,H,N+1,N+1] map with a CLS token the loss reads query row 0 only.  Pinned maps: one pitched DMA per layer
+        # straight out of the caller's tensor (basd_copy_cls_rows_h2d) - no host-side work at all.  Pageable or oddly
+        # strided maps: gather the rows into a pinned staging buffer first.
+        host_attn, dma_attn = {}, {}
         for j, a in all_teacher_attns.items():
-            if has_cls:
+            if has_cls and a.dim() == 4 and a.shape[2] > 1 and a.is_pinned() and a.stride(3) == 1 and a.dtype in (torch.float32, torch.bfloat16):
+                dma_attn[j] = a
+            elif has_cls and a.dim() == 4 and a.shape[2] > 1:
                 rows = self._pinned(slot, ("pin_attn", j), a, (a.shape[0], a.shape[1], 1, a.shape[3]))
                 rows.copy_(a[:, :, 0:1, :])
                 host_attn[j] = rows
@@ -327,6 +331,15 @@ class HostStager:
             d_student = {l: put(("s", l), t) for l, t in student_intermediates.items()}
             d_teacher = {j: put(("t", j), t) for j, t in all_teacher_tokens.items()}
             d_attn = {j: put(("a", j), t) for j, t in host_attn.items()}
+            lib = _lib.load()
+            for j, a in dma_attn.items():
+                B_, H_, S_ = a.shape[0], a.shape[1], a.shape[3]
+                d = self._dev(slot, ("a", j), a, (B_, H_, 1, S_))
+                strides = (ctypes.c_int64 * 4)(*a.stride())
+                _lib.check(lib.basd_copy_cls_rows_h2d(a.data_ptr(), a.element_size(), B_, H_, S_, strides, d.data_ptr(),
+                                                      self.copy_stream.cuda_stream), "basd_copy_cls_rows_h2d")
+                nbytes += B_ * H_ * S_ * a.element_size()
+                d_attn[j] = d
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
         slot["copy_event"] = ev
