@@ -569,7 +569,7 @@ extern "C" int basd_mp_rank(const void* features, int64_t M, int D, int dtype, i
     CK(launch_pack_bf16(features, exact, 0, row_stride, 1, 1, static_cast<int>(M), D, zb, exact ? nullptr : zl, st));
     CK(cudaMemsetAsync(stats, 0, 4 * 2 * (static_cast<size_t>(D) * D + D), st));
     CK(gemm_gram(zb, exact ? nullptr : zl, static_cast<size_t>(M), D, stats, gram_part, st));
-    CK(launch_pooled_eig(stats, D, 1, 0, static_cast<float>(M), 1.f, ranks, evals, evk, evc, nullptr, eig_scr, st));
+    CK(launch_pooled_eig(stats, D, 1, 0, static_cast<float>(M), 1.f, ranks, evals, evk, evc, nullptr, eig_scr, st, kEigMpOnly));
     CK(cudaMemcpyAsync(rank_out, ranks, sizeof(int), cudaMemcpyDeviceToDevice, st));
     return 0;
 }

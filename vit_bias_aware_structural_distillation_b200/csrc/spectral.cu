@@ -10,6 +10,8 @@
 #include <math_constants.h>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <vector>
 
 #include "cta_linalg.cuh"
 #include "jacobi.cuh"
@@ -68,11 +70,17 @@ __device__ __forceinline__ bool run_jacobi_oddeven_cluster(float* A, int ld, int
 }
 
 // ------------------------------------------------------------------------------------------------
-// pooled_eig_kernel: one CLUSTER of kPooledCluster CTAs per symmetric problem of size n = Ds.  Rank 0 of the cluster
-// holds the matrix and runs every phase; the other ranks only take their share of the Jacobi pairs (jacobi.cuh).
-//   problem p in [0, Lt)        : MP rank of teacher layer p   (uncentred G / M)
-//   problem p in [Lt, 2Lt)      : centred eigen-decomposition of teacher layer p - Lt
-//   problem p in [2Lt, 2Lt + P) : centred eigen-decomposition of student extraction point p - 2Lt
+// pooled_eig_kernel: one CLUSTER of CTAs per symmetric problem of size n = Ds.  Rank 0 of the cluster holds the matrix
+// and runs every phase; the other ranks only take their share of the Jacobi pairs (jacobi.cuh).
+//   mode kEigPooled (the loss):  problem p in [0, Lt)      : centred eigen-decomposition of teacher layer p AND its MP rank
+//                                problem p in [Lt, Lt + P) : centred eigen-decomposition of student extraction point p - Lt
+//   mode kEigMpOnly (the free function marchenko_pastur_rank): problem p in [0, Lt): MP rank from the uncentred G / M itself
+// The MP rank (layer_selector.py:8-20) needs the eigenvalues of the UNCENTRED second moment G / M.  With c the column sums,
+// G / M = G_c / M + (c / M)(c / M)^T is a rank-one update of the centred Gram whose eigensystem (lambda_i, v_i) this kernel
+// computes anyway: its eigenvalues x_i are the roots of the secular equation f(x) = 1 + sum_i u_i^2 / (d_i - x) = 0 with
+// d_i = lambda_i / M, u_i = v_i . c / M, and they interlace the d_i.  Only the median and a count above a threshold are
+// needed, both of which come from the inertia count  #{x > t} = #{d_i > t} + [f(t) < 0]  (mp_count_above below), so the Lt
+// separate uncentred eigenproblems of the first version of this kernel (12 of 28 at cfg2) are gone.
 // stats layout: [(Lt + P)][n*n + n]  (Gram row-major, then column sums)
 // ------------------------------------------------------------------------------------------------
 // History of the Jacobi phase on B200 (cfg2, ms for the 28 pooled problems), one 768-thread CTA per problem, round-robin
@@ -107,8 +115,41 @@ __device__ __forceinline__ void pooled_load_gram(const float* __restrict__ G, co
     }
 }
 
-constexpr int kPooledThreads = 256;        // 32 eight-lane groups per CTA x 4 CTAs: n <= 256; 255 registers per thread, no spills
-constexpr int kPooledCluster = 4;           // 28 problems x 4 = 112 of the 148 SMs
+// Number of eigenvalues of diag(d) + u u^T above t (one warp; u2 = u^2).  Interlacing puts x_i in [d_i, d_(i+1)]
+// (ascending), so for t between two poles only one eigenvalue is undecided, and it lies above t iff f(t) < 0 (f rises from
+// -inf to +inf between two poles).  t == d_i counts as t = d_i + 0.  All 32 lanes call; the result is warp-uniform.
+__device__ __forceinline__ int mp_count_above(const float* __restrict__ d, const float* __restrict__ u2, int n, float t) {
+    const int lane = threadIdx.x & 31;
+    int cnt = 0;
+    float f = 0.f;
+    for (int i = lane; i < n; i += 32) {
+        const float di = d[i], den = di - t;
+        cnt += di > t;
+        f += u2[i] / (den == 0.f ? -1e-37f : den);
+    }
+    f = warp_sum(f);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    return cnt + ((1.f + f) < 0.f ? 1 : 0);
+}
+// MP rank of diag(d) + u u^T (warp 0 of the CTA; d_lo / d_hi bracket the median eigenvalue by interlacing)
+__device__ __forceinline__ int mp_rank_secular(const float* __restrict__ d, const float* __restrict__ u2, int n, float d_lo, float d_hi,
+                                               float q_ratio /* D / M */) {
+    // median = ascending index (n-1)/2 (torch.median: lower middle): the smallest t with #{x > t} <= n - 1 - (n-1)/2
+    const int want = n - 1 - (n - 1) / 2;
+    float lo = d_lo, hi = d_hi;
+    for (int it = 0; it < 40; ++it) {
+        const float mid = 0.5f * (lo + hi);
+        if (!(mid > lo && mid < hi)) break;             // the bracket is one ulp wide
+        if (mp_count_above(d, u2, n, mid) <= want) hi = mid; else lo = mid;
+    }
+    const float med = mp_count_above(d, u2, n, lo) <= want ? lo : hi;
+    const float sq = 1.f + sqrtf(q_ratio);
+    return mp_count_above(d, u2, n, med * sq * sq);
+}
+
+constexpr int kPooledThreads = 256;        // 32 eight-lane groups per CTA: n <= 64 x cluster size; 255 registers per thread, no spills
+constexpr int kPooledCluster = 4;           // smallest cluster (n = 192: 24 pairs per CTA); pooled_pick_cluster takes a larger one when the SMs are there
 constexpr int kPooledLargeThreads = 768;
 // global-memory Jacobi on one CTA: 4-lane groups when that puts every pair of a step in flight at once
 __device__ __forceinline__ int run_jacobi_global(float* A, int ld, int n) {
@@ -126,7 +167,7 @@ __global__ void __launch_bounds__(LARGE ? kPooledLargeThreads : kPooledThreads, 
 pooled_eig_kernel(const float* __restrict__ stats, int n, int Lt, int P, float M_teacher, float M_student,
                   int* __restrict__ ranks, float* __restrict__ evals, float* __restrict__ evecs_km,
                   float* __restrict__ evecs_cm, int* __restrict__ sweeps_out, float* __restrict__ scratch, int phase,
-                  int* __restrict__ chol_flags) {
+                  int* __restrict__ chol_flags, int mode) {
     // phase (LARGE only): 1 = everything in this launch; 0 = up to the Cholesky factor (the Jacobi sweeps then run in
     // jacobi_cluster_global_kernel over a cluster per problem); 2 = from the rotated columns on
     extern __shared__ float sm[];
@@ -144,8 +185,8 @@ pooled_eig_kernel(const float* __restrict__ stats, int n, int Lt, int P, float M
     const long long t_begin = clock64();
     const int crank = LARGE ? 0 : static_cast<int>(cooperative_groups::this_cluster().block_rank());
     const int p = LARGE ? blockIdx.x : blockIdx.x / static_cast<int>(cooperative_groups::this_cluster().num_blocks());
-    const bool mp_mode = p < Lt;
-    const int gram_idx = mp_mode ? p : (p - Lt);                  // index into stats (teacher 0..Lt-1, student Lt..)
+    const bool mp_mode = mode == kEigMpOnly;
+    const int gram_idx = p;                                       // index into stats (teacher 0..Lt-1, student Lt..)
     const float Mrows = gram_idx < Lt ? M_teacher : M_student;
     const float* G = stats + static_cast<size_t>(gram_idx) * (n * n + n);
     const float* cs = G + n * n;
@@ -153,6 +194,7 @@ pooled_eig_kernel(const float* __restrict__ stats, int n, int Lt, int P, float M
     bool use_chol = false;
     if (LARGE && phase == 2) {
         use_chol = chol_flags[blockIdx.x] != 0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) csum[i] = cs[i];
         if (threadIdx.x == 0) s_count = 0;
         __syncthreads();
     } else
@@ -226,7 +268,35 @@ pooled_eig_kernel(const float* __restrict__ stats, int n, int Lt, int P, float M
         if (threadIdx.x == 0) ranks[p] = min(s_count, n - 1);
         return;
     }
-    const int q = p - Lt;                                         // output slot: teacher 0..Lt-1, student Lt..Lt+P-1
+    if (p < Lt && ranks) {
+        // MP rank of this teacher layer from the centred eigensystem (see the header), in units of M: the eigenvalues of
+        // G_c + c c^T / M = diag(lambda) + u u^T with u_i = v_i . c / sqrt(M), v_i = column_i / |column_i|
+        float* u2 = inbox;                                        // (the Jacobi mailbox column is free now; ld + 8 >= n floats)
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+        for (int c = warp; c < n; c += nwarps) {
+            const float* col = A + static_cast<size_t>(c) * ld;
+            float dot = 0.f;
+            for (int r = lane; r < n; r += 32) dot = fmaf(col[r], csum[r], dot);
+            dot = warp_sum(dot);
+            if (lane == 0) {
+                const float nv2 = use_chol ? vals[c] : vals[c] * vals[c];       // |column|^2
+                u2[c] = nv2 > 0.f ? dot * dot / nv2 * invM : 0.f;
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // bracket of the median by interlacing: [lambda_(m), lambda_(m+1)] ascending, the top one extended by |u|^2
+            const int mi = (n - 1) / 2;
+            const float d_lo = vals[order[n - 1 - mi]];
+            float d_hi;
+            if (mi + 1 < n) d_hi = vals[order[n - 2 - mi]];
+            else { float su = 0.f; for (int i = lane; i < n; i += 32) su += u2[i]; d_hi = d_lo + warp_sum(su); }
+            const int rk = mp_rank_secular(vals, u2, n, d_lo, d_hi, static_cast<float>(n) * invM);
+            if (lane == 0) ranks[p] = min(rk, n - 1);
+        }
+        __syncthreads();
+    }
+    const int q = p;                                              // output slot: teacher 0..Lt-1, student Lt..Lt+P-1
     float* ev = evals + static_cast<size_t>(q) * n;
     float* vk = evecs_km + static_cast<size_t>(q) * n * n;        // [eig][component]
     float* vc = evecs_cm + static_cast<size_t>(q) * n * n;        // [component][eig]
@@ -240,7 +310,7 @@ pooled_eig_kernel(const float* __restrict__ stats, int n, int Lt, int P, float M
     // eigenvector e = column order[e] of A, normalised; one warp per eigenvector, lanes over components (conflict-free
     // shared reads; the [eig][comp] store is coalesced, the [comp][eig] one is a 4-byte scatter that L2 merges)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    if (threadIdx.x == 0 && p == Lt && g_spectral_dbg_on) { g_spectral_clk[0] = t_pre - t_begin; g_spectral_clk[1] = t_jac - t_pre; g_spectral_clk[2] = clock64() - t_jac; g_spectral_clk[3] = nsweeps; }
+    if (threadIdx.x == 0 && p == 0 && g_spectral_dbg_on) { g_spectral_clk[0] = t_pre - t_begin; g_spectral_clk[1] = t_jac - t_pre; g_spectral_clk[2] = clock64() - t_jac; g_spectral_clk[3] = nsweeps; }
     for (int e = warp; e < n; e += nwarps) {
         const float* col = A + static_cast<size_t>(order[e]) * ld;
         const float s = csum[e];
@@ -503,38 +573,79 @@ static size_t angles_smem(int n, bool large) { return ((large ? 0 : static_cast<
 bool spectral_large(int n) { return n > kSpectralSmemMax; }
 size_t pooled_eig_scratch_floats(int n, int problems) { return spectral_large(n) ? static_cast<size_t>(problems) * jacobi_ld(n) * n + problems + 64 : 0; }
 
+// Cluster size of the shared-memory solver: the Jacobi pair-step is a dependent chain whose latency grows with the warps an
+// SM has to issue for (jacobi.cuh), so every problem gets as many CTAs as the GPU can co-schedule for ALL problems at once
+// (a cluster lives inside one GPC: cudaOccupancyMaxActiveClusters knows how many fit).  Cached per device and shape.
+static int pooled_pick_cluster(const void* kern, int n, int problems, size_t smem_fixed, size_t smem_per_group_floats) {
+    static const int forced = [] {            // BASD_EIG_CLUSTER: development knob (1..8 CTAs per problem), read once
+        const char* env = getenv("BASD_EIG_CLUSTER");
+        const int c = env ? atoi(env) : 0;
+        return (c < 1 || c > 8) ? 0 : c;
+    }();
+    const int groups = (n + 1) / 2, per_cta = kPooledThreads / JAC_GROUP;
+    const int c_min = (groups + per_cta - 1) / per_cta;
+    if (forced) return forced < c_min ? c_min : forced;
+    struct Key { int dev, n, problems, cluster; const void* kern; };
+    static std::mutex mu;
+    static std::vector<Key> cache;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    for (const Key& k : cache)
+        if (k.dev == dev && k.n == n && k.problems == problems && k.kern == kern) return k.cluster;
+    int pick = c_min > kPooledCluster ? c_min : kPooledCluster;
+    for (int c = 8; c > pick; --c) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3(problems * c);
+        cfg.blockDim = dim3(kPooledThreads);
+        cfg.dynamicSmemBytes = smem_fixed + static_cast<size_t>((groups + c - 1) / c) * smem_per_group_floats * sizeof(float);
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = c; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        int fit = 0;
+        if (cudaOccupancyMaxActiveClusters(&fit, kern, &cfg) == cudaSuccess && fit >= problems) { pick = c; break; }
+        cudaGetLastError();
+    }
+    cache.push_back({dev, n, problems, pick, kern});
+    return pick;
+}
+
 cudaError_t launch_pooled_eig(const float* stats, int n, int Lt, int P, float Mt, float Ms, int* ranks, float* evals,
-                              float* evecs_km, float* evecs_cm, int* sweeps, float* scratch, cudaStream_t st) {
+                              float* evecs_km, float* evecs_cm, int* sweeps, float* scratch, cudaStream_t st, int mode) {
     spectral_dbg_init();
     const bool large = spectral_large(n);
     const size_t smem = pooled_smem(n, large);
+    const int problems = mode == kEigMpOnly ? Lt : Lt + P;
+    if (problems < 1) return cudaErrorInvalidValue;
     if (large) {
         if (!scratch) return cudaErrorInvalidValue;
         cudaError_t e = cudaFuncSetAttribute(pooled_eig_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;
-        const int problems = 2 * Lt + P;
         const int ld = jacobi_ld(n);
         const int chunks = (ld + JAC_CHUNK_ROWS - 1) / JAC_CHUNK_ROWS;
         int* chol_flags = reinterpret_cast<int*>(scratch + static_cast<size_t>(problems) * ld * n);     // (pooled_eig_scratch_floats leaves room)
         if (chunks > 12) {          // beyond the register-resident cluster solver (marchenko_pastur_rank on wide features): one CTA per problem
-            pooled_eig_kernel<true><<<problems, kPooledLargeThreads, smem, st>>>(stats, n, Lt, P, Mt, Ms, ranks, evals, evecs_km, evecs_cm, sweeps, scratch, 1, chol_flags);
+            pooled_eig_kernel<true><<<problems, kPooledLargeThreads, smem, st>>>(stats, n, Lt, P, Mt, Ms, ranks, evals, evecs_km, evecs_cm, sweeps, scratch, 1, chol_flags, mode);
             return cudaGetLastError();
         }
-        pooled_eig_kernel<true><<<problems, kPooledLargeThreads, smem, st>>>(stats, n, Lt, P, Mt, Ms, ranks, evals, evecs_km, evecs_cm, sweeps, scratch, 0, chol_flags);
+        pooled_eig_kernel<true><<<problems, kPooledLargeThreads, smem, st>>>(stats, n, Lt, P, Mt, Ms, ranks, evals, evecs_km, evecs_cm, sweeps, scratch, 0, chol_flags, mode);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         {
             const int groups = (n + 1) / 2, per_cta = kPooledThreads / JAC_GROUP;
-            const int cluster = (groups + per_cta - 1) / per_cta;                                       // 6 CTAs for n = 384
-            if (cluster > 8) return cudaErrorInvalidValue;
-            const int gpc = (groups + cluster - 1) / cluster;
-            const size_t jsmem = (static_cast<size_t>(gpc) * ld + ld + 8) * sizeof(float);
+            if ((groups + per_cta - 1) / per_cta > 8) return cudaErrorInvalidValue;                     // at least 6 CTAs for n = 384
             using JK = void (*)(float*, int, int*);
             static const JK kerns[5] = {jacobi_cluster_global_kernel<8>, jacobi_cluster_global_kernel<9>, jacobi_cluster_global_kernel<10>,
                                         jacobi_cluster_global_kernel<11>, jacobi_cluster_global_kernel<12>};
             const JK kern = kerns[chunks < 8 ? 0 : chunks - 8];
-            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(jsmem));
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>((static_cast<size_t>(per_cta) * ld + ld + 8) * sizeof(float)));
             if (e != cudaSuccess) return e;
+            const int cluster = pooled_pick_cluster(reinterpret_cast<const void*>(kern), n, problems, (ld + 8) * sizeof(float), ld);
+            const int gpc = (groups + cluster - 1) / cluster;
+            const size_t jsmem = (static_cast<size_t>(gpc) * ld + ld + 8) * sizeof(float);
             cudaLaunchConfig_t cfg;
             memset(&cfg, 0, sizeof cfg);
             cfg.gridDim = dim3(problems * cluster);
@@ -549,19 +660,15 @@ cudaError_t launch_pooled_eig(const float* stats, int n, int Lt, int P, float Mt
             e = cudaLaunchKernelEx(&cfg, kern, scratch, n, sweeps);
             if (e != cudaSuccess) return e;
         }
-        pooled_eig_kernel<true><<<problems, kPooledLargeThreads, smem, st>>>(stats, n, Lt, P, Mt, Ms, ranks, evals, evecs_km, evecs_cm, sweeps, scratch, 2, chol_flags);
+        pooled_eig_kernel<true><<<problems, kPooledLargeThreads, smem, st>>>(stats, n, Lt, P, Mt, Ms, ranks, evals, evecs_km, evecs_cm, sweeps, scratch, 2, chol_flags, mode);
         return cudaGetLastError();
     }
     cudaError_t e = cudaFuncSetAttribute(pooled_eig_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
-    static const int cluster = [] {           // BASD_EIG_CLUSTER: development knob (1..8 CTAs per problem), read once
-        const char* env = getenv("BASD_EIG_CLUSTER");
-        const int c = env ? atoi(env) : kPooledCluster;
-        return (c < 1 || c > 8) ? kPooledCluster : c;
-    }();
-    cfg.gridDim = dim3((2 * Lt + P) * cluster);
+    const int cluster = pooled_pick_cluster(reinterpret_cast<const void*>(pooled_eig_kernel<false>), n, problems, smem, 0);
+    cfg.gridDim = dim3(problems * cluster);
     cfg.blockDim = dim3(kPooledThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
@@ -571,7 +678,7 @@ cudaError_t launch_pooled_eig(const float* stats, int n, int Lt, int P, float Mt
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, pooled_eig_kernel<false>, stats, n, Lt, P, Mt, Ms, ranks, evals, evecs_km, evecs_cm, sweeps, scratch, 1,
-                              static_cast<int*>(nullptr));
+                              static_cast<int*>(nullptr), mode);
 }
 
 cudaError_t launch_angles(int n, int Lt, int P, const int* ranks, const float* evals, const float* evecs_km,

@@ -15,8 +15,12 @@ constexpr int kMaxLayers = 64;        // teacher layers Lt
 constexpr int kSpectralSmemMax = 224;  // largest symmetric problem whose matrix fits one SM's shared memory
 bool spectral_large(int n);            // n > kSpectralSmemMax: matrices in global scratch (pooled_eig_scratch_floats)
 size_t pooled_eig_scratch_floats(int n, int problems);
+// mode kEigPooled: Lt + P centred eigenproblems (teacher layers, then student points); the MP rank of every teacher layer comes
+// from its centred eigensystem (rank-one secular equation).  mode kEigMpOnly: Lt uncentred problems, ranks only (evals / evecs
+// unused) - the free function marchenko_pastur_rank, which also takes M < D.
+constexpr int kEigPooled = 1, kEigMpOnly = 2;
 cudaError_t launch_pooled_eig(const float* stats, int n, int Lt, int P, float Mt, float Ms, int* ranks, float* evals,
-                              float* evecs_km, float* evecs_cm, int* sweeps, float* scratch, cudaStream_t st);
+                              float* evecs_km, float* evecs_cm, int* sweeps, float* scratch, cudaStream_t st, int mode = kEigPooled);
 cudaError_t launch_angles(int n, int Lt, int P, const int* ranks, const float* evals, const float* evecs_km,
                           const float* evecs_cm, const float* proj_s, float* scratch, float* d2, float* gamma,
                           float* cos_out, const float* log_temp, float* w, cudaStream_t st);

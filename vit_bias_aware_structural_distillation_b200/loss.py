@@ -138,6 +138,11 @@ def _world():
     return None, 1
 
 
+# Test hook (tests/test_gpu_parity.py::test_workspace_contents_do_not_matter): called with the freshly allocated, uninitialised
+# workspace so that a test can poison it - no kernel may read workspace bytes it (or an earlier kernel of the step) has not written.
+_debug_workspace_fill = None
+
+
 def _allreduce_sum(dist, t: torch.Tensor):
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
 
@@ -157,6 +162,8 @@ def geo_forward(students: List[torch.Tensor], teachers: List[torch.Tensor], attn
     dev = students[0].device
     with torch.cuda.device(dev):             # the library launches on the CURRENT device: make it the tensors' device
         ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+        if _debug_workspace_fill is not None:
+            _debug_workspace_fill(ws)
         geo = torch.empty((), dtype=torch.float32, device=dev)
         st = _stream_ptr(dev)
         _lib.check(lib.basd_forward_stats(ctypes.byref(shape), ctypes.byref(inp), ws.data_ptr(), st), "basd_forward_stats")
