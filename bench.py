@@ -371,15 +371,15 @@ def main():
     ab_bytes = (2 * D * N + D * D) if per_ns_step == 3 else (2 * D * N + D * D) + 2 * D * D      # fused: T, W in, Bm out
     polar_bytes = n_prob * 4 * (ksteps * ((2 * D * N + N * N) + ab_bytes + (D * D + 2 * D * N))
                                 + (N * N + D * N + N * D) + (2 * N * D + N * N))
-    eig_bytes = 4 * ((2 * w.Lt + w.P) * (D * D + D) + (w.Lt + w.P) * (2 * D * D + D))
+    eig_bytes = 4 * ((w.Lt + w.P) * (D * D + D) + (w.Lt + w.P) * (2 * D * D + D))
     table = {   # slot -> (bound, algorithmic units per step, launches per step, description)
         "polar_gemm": ("hbm", polar_bytes, polar_launches,
                        f"Newton-Schulz polar iteration, ({per_ns_step} x steps + 2) batched launches per step: split-bf16 operands read once and the "
                        "result written once per launch (4 B per element, unpadded).  Tensor view of the same kernel: "
                        f"{polar_flops / polar_launches / 1e9:.1f} GFLOP of plain 2mnk per launch (3 split MMAs per product not counted)"),
         "pooled_eig": ("hbm", eig_bytes, 1,
-                       "28 eigenproblems (Cholesky + one-sided Jacobi, fp32 CUDA cores), one 4-CTA cluster each (112 SMs): a dependent-latency chain, "
-                       "neither roofline applies; bytes = Gram statistics in, eigenpairs out"),
+                       f"{w.Lt + w.P} eigenproblems (Cholesky + one-sided Jacobi, fp32 CUDA cores; MP ranks from the secular equation), one thread-block "
+                       "cluster each: a dependent-latency chain, neither roofline applies; bytes = Gram statistics in, eigenpairs out"),
     }
     traffic = None
     try:
@@ -387,17 +387,36 @@ def main():
         traffic = tr.get(dom, {}).get("dram_bytes_per_launch")
     except Exception:
         pass
-    feature_form = w.Ds <= min(w.Ns, w.Nt) - 1          # the byte / flop model above is the student-feature form's
-    if dom in table and table[dom][1] > 0 and feature_form:
+    feature_form = w.Ds <= min(w.Ns, w.Nt) - 1          # the byte model above is the student-feature form's
+    # the Procrustes stage's share of the algorithmic tensor flops F_tc is the cross-covariance
+    # s_w^T t_w (forward) and the two products with the polar factor (backward): 3 x 2 N_s D_s D_t per (point, sample).
+    # The Newton-Schulz products that replace the batched SVD are implementation extras and do not count.
+    procrustes_flops = 3 * 2 * n_prob * w.Ns * w.Ds * w.Dt
+    if dom == "polar_gemm":
+        n_l = polar_launches if feature_form else None
+        ms_dom = per_step[dom]
+        ach_tf = procrustes_flops / (ms_dom * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "achieved": ach_tf, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach_tf / tc_peak, "traffic": traffic,
+                    "kernel": dom,
+                    "what": "Procrustes stage (relational.py:47-48 and its backward) = the launches of the Newton-Schulz polar iteration; achieved = "
+                            "its SURVEY 8(d) share of F_tc (3 x 2 N_s D_s D_t flops per point and sample) / the stage's time per step, "
+                            "against the measured sustained bf16 peak",
+                    "algorithmic_flops_per_step": procrustes_flops, "ms_per_step": ms_dom}
+        if feature_form:
+            ms_launch = ms_dom / n_l
+            fb = polar_bytes / n_l / (ms_launch * 1e-3) / 1e9
+            roofline.update({"launches_per_step": n_l, "avg_launch_ms": ms_launch, "algorithmic_flops_per_launch": procrustes_flops / n_l})
+            roofline["formulation_view"] = {
+                "what": table[dom][3], "bound": "hbm", "bytes_per_launch": polar_bytes / n_l, "achieved_gbs": fb, "peak_gbs": hbm_peak,
+                "frac": fb / hbm_peak, "plain_2mnk_tflops": polar_flops / n_l / (ms_launch * 1e-3) / 1e12,
+                "note": "how well the launches stream the operands of THIS formulation (14.8 GB per step at cfg2); not the section 8(d) quantity"}
+    elif dom in table and table[dom][1] > 0 and feature_form:
         bound, units, n_l, what = table[dom]
         ms_launch = per_step[dom] / n_l
         ach = units / n_l / (ms_launch * 1e-3) / 1e9
         roofline = {"bound": bound, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
                     "kernel": dom, "what": what, "launches_per_step": n_l, "avg_launch_ms": ms_launch,
                     "algorithmic_bytes_per_launch": units / n_l}
-        if dom == "polar_gemm":
-            tf = polar_flops / polar_launches / (ms_launch * 1e-3) / 1e12
-            roofline["tensor_view"] = {"achieved_tflops": tf, "peak_tflops": tc_peak, "frac": tf / tc_peak}
     else:
         achieved = w_alg / (ms_step * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
