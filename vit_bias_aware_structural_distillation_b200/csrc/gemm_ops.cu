@@ -385,7 +385,8 @@ cudaError_t polar_gemm(bool b_mn, const SplitMat& A, const SplitMat& B, int batc
     if (a.a_alias_b && a.n_nt > 1) a.a_alias_b = 0;      // the A tile is only inside the B tile when one tile spans all columns
     const int b_bytes = b_mn ? a.b_groups * 8192 : a.bn_mma * 128;
     const int stage_bytes = (a.a_alias_b ? 0 : 2 * 16384) + 2 * b_bytes;
-    const int kTail = 1024 /*alignment*/ + 1024 /*barriers*/ + 4 * 8192 /*epilogue staging*/ + (a.aux_mode ? 4 * 8192 * ((a.bn_mma + 63) / 64) : 0) /*aux tiles: every column block of an item*/;   // (the aliased A tile of the last rows reads up to 8 KB past its B tile: into the barrier / staging area, rows never used)
+    const int kTail = 1024 /*alignment*/ + 1024 /*barriers*/ + 4 * 8192 /*epilogue staging*/ + (a.aux_mode ? 4 * 8192 * ((a.bn_mma + 63) / 64) : 0) /*aux tiles: every column block of an item*/ +
+                      (a.epi == PG_EPI_THETA ? 4 * 2048 : 0) /*THETA: a and sqrt(a) of the tile's columns per epilogue warp*/;   // (the aliased A tile of the last rows reads up to 8 KB past its B tile: into the barrier / staging area, rows never used)
     int stages = (232448 - kTail) / stage_bytes;
     if (stages > 4) stages = 4;
     if (stages < 1) {

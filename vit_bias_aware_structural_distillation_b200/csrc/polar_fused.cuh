@@ -69,21 +69,21 @@ polar_fused_abm_kernel(const __grid_constant__ PolarFusedMaps maps, const PolarF
     const int half_bytes = n_kb2 * blk_bytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + ring_bytes);
     uint64_t* empty_bar = full_bar + PF_STAGES;
-    uint64_t* acc1_bar = empty_bar + PF_STAGES;                // A complete in TMEM
-    uint64_t* copy_bar = acc1_bar + 1;                         // [4] 64-column block kb of the operand copy written (4 n_mt warps)
-    uint64_t* acc2_bar = copy_bar + 4;                         // A + (c r / b) A^2 complete in TMEM
-    uint64_t* p2done_bar = acc2_bar + 1;                       // phase 2 retired: the ring memory is free again
-    uint64_t* tmem_empty_bar = p2done_bar + 1;                 // accumulators drained (4 n_mt warps)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 1);
+    uint64_t* acc1_bar = empty_bar + PF_STAGES;                // [2] row tile mt of A complete in TMEM
+    uint64_t* copy_bar = acc1_bar + 2;                         // [4] 64-column block kb of the operand copy written (4 n_mt warps)
+    uint64_t* acc2_bar = copy_bar + 4;                         // [2] row tile mt of A + (c r / b) A^2 complete in TMEM
+    uint64_t* p2done_bar = acc2_bar + 2;                       // phase 2 retired: the ring memory is free again
+    uint64_t* tmem_empty_bar = p2done_bar + 1;                 // [2] accumulator of row tile mt drained (its 4 warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
     float* trace_s = reinterpret_cast<float*>(tmem_slot + 2);  // [2][8]: per item parity, one slot per epilogue warp
     uint8_t* staging = smem + ring_bytes + 1024;               // 8 warps x (hi 2 KB + lo 2 KB)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < PF_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(acc1_bar, 1); mbar_init(acc2_bar, 1); mbar_init(p2done_bar, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc1_bar[i], 1); mbar_init(&acc2_bar[i], 1); mbar_init(&tmem_empty_bar[i], 4); }
+        mbar_init(p2done_bar, 1);
         for (int i = 0; i < 4; ++i) mbar_init(&copy_bar[i], 4 * args.n_mt);
-        mbar_init(tmem_empty_bar, 4 * args.n_mt);
         fence_mbar_init();
         tma_prefetch_desc(&maps.t[0]); tma_prefetch_desc(&maps.t[1]);
         tma_prefetch_desc(&maps.w[0]); tma_prefetch_desc(&maps.w[1]);
@@ -128,8 +128,6 @@ polar_fused_abm_kernel(const __grid_constant__ PolarFusedMaps maps, const PolarF
         int it = 0, item = 0;
         for (int w = blockIdx.x; w < args.n_problems; w += gridDim.x, ++item) {
             const uint32_t ph_item = item & 1;
-            mbar_wait(tmem_empty_bar, ph_item ^ 1);               // the store phase of the previous problem has drained TMEM
-            tc_fence_after();
             const bool dbg_m = args.dbg_clock && blockIdx.x == 0 && item < 16 && lane == 0;
             if (dbg_m) args.dbg_clock[item * 8 + 2] = clock64();
             for (int kb = 0; kb < n_kb; ++kb, ++it) {             // phase 1: A = T W^T
@@ -137,11 +135,15 @@ polar_fused_abm_kernel(const __grid_constant__ PolarFusedMaps maps, const PolarF
                 const uint32_t ph = (it / PF_STAGES) & 1;
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t st = smem_u32(smem + s * stage_bytes);
-                    int ksteps = (args.k_total - kb * 64 + 15) / 16;
-                    if (ksteps > 4) ksteps = 4;
-                    for (int mt = 0; mt < args.n_mt; ++mt) {
+                const uint32_t st = smem_u32(smem + s * stage_bytes);
+                int ksteps = (args.k_total - kb * 64 + 15) / 16;
+                if (ksteps > 4) ksteps = 4;
+                for (int mt = 0; mt < args.n_mt; ++mt) {
+                    if (kb == 0) {                                // the store phase of the previous problem has drained THIS tile's accumulator
+                        mbar_wait(&tmem_empty_bar[mt], ph_item ^ 1);   // (tile 1 is still being stored while tile 0's first MMAs run)
+                        tc_fence_after();
+                    }
+                    if (lane == 0) {
 #pragma unroll
                         for (int t = 0; t < 3; ++t) {            // hi*hi, hi*lo, lo*hi
                             const uint32_t a_base = st + (t == 2 ? a_bytes : 0) + mt * 16384;
@@ -150,9 +152,13 @@ polar_fused_abm_kernel(const __grid_constant__ PolarFusedMaps maps, const PolarF
                                 umma_bf16(tmem_base + mt * args.bn, umma_smem_desc(a_base + ks * 32, 16, 1024),
                                           umma_smem_desc(b_base + ks * 32, 16, 1024), idesc1, (kb > 0 || t > 0 || ks > 0) ? 1u : 0u);
                         }
+                        if (kb == n_kb - 1) umma_commit(&acc1_bar[mt]);       // tile 0's copy starts under tile 1's last MMAs
                     }
+                    __syncwarp();
+                }
+                if (lane == 0) {
                     umma_commit(&empty_bar[s]);
-                    if (kb == n_kb - 1) { umma_commit(acc1_bar); if (dbg_m) args.dbg_clock[item * 8 + 3] = clock64(); }
+                    if (kb == n_kb - 1 && dbg_m) args.dbg_clock[item * 8 + 3] = clock64();
                 }
                 __syncwarp();
             }
@@ -163,10 +169,11 @@ polar_fused_abm_kernel(const __grid_constant__ PolarFusedMaps maps, const PolarF
                 for (int kb = 0; kb < n_kb2; ++kb) mbar_wait(&copy_bar[kb], ph_item);
                 tc_fence_after();
                 if (dbg_m) args.dbg_clock[item * 8 + 4] = clock64();
-                for (int kb = 0; kb < n_kb2; ++kb) {
-                    int ksteps = (args.n - kb * 64 + 15) / 16;
-                    if (ksteps > 4) ksteps = 4;
-                    for (int mt = 0; mt < args.n_mt; ++mt) {
+                // row tile by row tile (every operand is resident): tile 0 is stored while tile 1 is still being multiplied
+                for (int mt = 0; mt < args.n_mt; ++mt) {
+                    for (int kb = 0; kb < n_kb2; ++kb) {
+                        int ksteps = (args.n - kb * 64 + 15) / 16;
+                        if (ksteps > 4) ksteps = 4;
 #pragma unroll
                         for (int t = 0; t < 3; ++t) {
                             const uint32_t b_base = cp + (t == 1 ? half_bytes : 0) + kb * blk_bytes;
@@ -176,8 +183,8 @@ polar_fused_abm_kernel(const __grid_constant__ PolarFusedMaps maps, const PolarF
                                           umma_smem_desc(b_base + ks * 32, 16, 1024), idesc2, 1u);
                         }
                     }
+                    umma_commit(&acc2_bar[mt]);
                 }
-                umma_commit(acc2_bar);
                 umma_commit(p2done_bar);
                 if (dbg_m) args.dbg_clock[item * 8 + 5] = clock64();
             }
@@ -198,7 +205,7 @@ polar_fused_abm_kernel(const __grid_constant__ PolarFusedMaps maps, const PolarF
         for (int w = blockIdx.x; w < args.n_problems; w += gridDim.x, ++item) {
             const int z = args.reverse ? args.n_problems - 1 - w : w;
             const uint32_t ph_item = item & 1;
-            mbar_wait(acc1_bar, ph_item);
+            mbar_wait(&acc1_bar[mt], ph_item);
             tc_fence_after();
             float r = 1.f;
             if (args.first) {                                     // trace(A) = ||C||_F^2 of this problem
@@ -264,7 +271,7 @@ polar_fused_abm_kernel(const __grid_constant__ PolarFusedMaps maps, const PolarF
                 if (lane == 0) args.resid[static_cast<long long>(z) * args.fro_slots + e] = rs_part;
             }
             // ---- store: Bm = ca I + (cb r) acc
-            mbar_wait(acc2_bar, ph_item);
+            mbar_wait(&acc2_bar[mt], ph_item);
             tc_fence_after();
             const bool dbg_e = args.dbg_clock && blockIdx.x == 0 && item < 16 && e == 0 && lane == 0;
             if (dbg_e) args.dbg_clock[item * 8 + 6] = clock64();
@@ -313,7 +320,7 @@ polar_fused_abm_kernel(const __grid_constant__ PolarFusedMaps maps, const PolarF
             tc_fence_before();
             __syncwarp();
             if (dbg_e) args.dbg_clock[item * 8 + 7] = clock64();
-            if (lane == 0) mbar_arrive(tmem_empty_bar);
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[mt]);
         }
         if (lane == 0) tma_store_wait_all();
     }

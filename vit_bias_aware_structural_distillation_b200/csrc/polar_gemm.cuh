@@ -285,14 +285,26 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
             const float scale = args.scale_c * (args.scale_p == 0.f ? 1.f : powf(r, args.scale_p));
             const float aux_scale = args.aux_c * (args.aux_p == 0.f ? 1.f : powf(r, args.aux_p));
             float a_row = 0.f, q_row = 0.f;
-            if (kTheta && row_ok) {
-                a_row = args.vec_a[static_cast<long long>(z) * args.m_rows + row];
-                q_row = sqrtf(a_row);
+            // THETA: a and sqrt(a) of this tile's columns, once per item into the warp's strip of shared memory (the per-element
+            // global load + IEEE sqrtf this replaces made the launch three times as long as a plain product: 0.31 ms at cfg2)
+            float* th_a = reinterpret_cast<float*>(aux_staging) + (warp - 2) * 512;
+            float* th_q = th_a + 256;
+            if (kTheta) {
+                if (row_ok) {
+                    a_row = args.vec_a[static_cast<long long>(z) * args.m_rows + row];
+                    q_row = sqrtf(a_row);
+                }
+                const float* avz = args.vec_a + static_cast<long long>(z) * args.m_rows;
+                for (int cl = lane; cl < args.bn_mma; cl += 32) {
+                    const float ac = c0 + cl < args.n_cols ? avz[c0 + cl] : 0.f;
+                    th_a[cl] = ac;
+                    th_q[cl] = sqrtf(ac);
+                }
+                __syncwarp();
             }
             float tr_part = 0.f, rs_part = 0.f;
             if constexpr (kStaged) {
                 constexpr bool theta = kTheta;
-                const float* av = theta ? args.vec_a + static_cast<long long>(z) * args.m_rows : nullptr;
                 // convert into the warp's swizzled staging tile; every 64-column block leaves as one TMA store per half
                 uint8_t* stg_hi = staging + (warp - 2) * 8192;
                 uint8_t* stg_lo = stg_hi + 4096;
@@ -333,13 +345,10 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
                             if constexpr (theta) {
 #pragma unroll
                                 for (int i = 0; i < 16; ++i) {
-                                    float t = 0.f;
-                                    if (c + i < args.n_cols) {
-                                        const float ac = av[c + i];
-                                        t = -q_row * v[i] * sqrtf(ac) - a_row * ac;
-                                        if (c + i == row) t += a_row;
-                                    }
-                                    v[i] = 2.f * t;
+                                    const int cl = cbk * 64 + jc * 16 + i;          // column inside the tile (zero a / q past n_cols)
+                                    float t = -q_row * v[i] * th_q[cl] - a_row * th_a[cl];
+                                    if (c + i == row) t += a_row;
+                                    v[i] = c + i < args.n_cols ? 2.f * t : 0.f;
                                 }
                             } else if constexpr (kAux) {
                                 float x[16];
