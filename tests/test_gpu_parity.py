@@ -587,6 +587,9 @@ def test_workspace_contents_do_not_matter(lib, cuda_dev, shape):
     dict(B=4, Ns=100, Nt=100, Ds=136, Dt=160, Lt=2, H=2, P=2),      # D_s > N - 1 (teacher-token form), nothing a multiple of 64
     dict(B=3, Ns=220, Nt=110, Ds=216, Dt=256, Lt=2, H=2, P=2),      # teacher-token form with resampling 110 -> 220, D_s % 16 == 8
     dict(B=3, Ns=240, Nt=220, Ds=232, Dt=256, Lt=2, H=2, P=2),      # teacher-token form, N_t > 208: two column tiles in the polynomial product
+    dict(B=3, Ns=100, Nt=140, Ds=136, Dt=160, Lt=2, H=2, P=2),      # D_s > N_s - 1 with a FINER teacher grid: token-space form on the student's grid
+    dict(B=1, Ns=50, Nt=50, Ds=64, Dt=96, Lt=2, H=2, P=2),          # pooled rows M = 50 < D_s (layer_selector.py:14-15: the M eigenvalues of F F^T / M)
+    dict(B=2, Ns=40, Nt=40, Ds=96, Dt=128, Lt=3, H=2, P=2),         # M = 80 < D_s = 96, three teacher layers
 ])
 def test_irregular_shapes_against_oracle(lib, cuda_dev, shape):
     """Shapes off the BASELINE grid: padding, tails and tile boundaries of every kernel against the fp32 oracle."""

@@ -27,7 +27,7 @@ for which in range(4):
     for i in range(14):
         print(f"{i:2d} " + " ".join(f"{(v - t0):12d}" for v in t[i].tolist()))
     if which == 1 and lib.basd_polar_launches_per_step(w.Ds, w.Ns) == 3:
-        print("   (fused A/Bm kernel: columns = loads_start, loads_issued, phase1_start, phase1_issued, copy_seen, phase2_issued, store_start, store_done)")
+        print("   (fused A/Bm kernel: columns = loads_start, tile1_stored, phase1_start, phase1_issued, copy_seen, phase2_issued, store_start, store_done)")
         continue
     if which == 2 and lib.basd_polar_launches_per_step(w.Ds, w.Ns) == 3:
         print("   (not launched: fused into the previous kernel)")

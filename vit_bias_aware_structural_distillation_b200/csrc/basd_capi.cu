@@ -120,7 +120,9 @@ Layout make_layout(const basd_shape& s) {
     const size_t B = s.B, Ns = s.Ns, Nt = s.Nt, Ds = s.Ds, Dt = s.Dt, Lt = s.Lt, P = s.P;
     L.path = polar_path(s);
     const bool vt = L.path == kPathTeacherTokens;
-    const size_t Nk = vt ? Nt : Ns;
+    // token-space form: the mixed teacher stays on its own grid when that is the coarser one (the resampling is folded into F);
+    // a FINER teacher grid (N_t > N_s) is resampled to the student's first - rank(C) = N_s - 1 either way
+    const size_t Nk = vt ? (Nt < Ns ? Nt : Ns) : Ns;
     L.Nk = static_cast<int>(Nk);
     L.NsPad = static_cast<int>((Nk + 7) / 8 * 8);
     L.Dsp = static_cast<int>((Ds + 15) / 16 * 16 + 8);
@@ -163,31 +165,31 @@ Layout make_layout(const basd_shape& s) {
     L.Np = static_cast<int>((Ns + 63) / 64 * 64);      // column-block tiled storage: columns padded to 64
     const size_t nprob = P * B, Np = L.Np;
     const size_t Dp = (Ds + 63) / 64 * 64;
-    const size_t Mp = (Nt + 63) / 64 * 64, Xp = (static_cast<size_t>(L.Dsp) + 63) / 64 * 64;
+    const size_t Mp = (Nk + 63) / 64 * 64, Xp = (static_cast<size_t>(L.Dsp) + 63) / 64 * 64;
     L.pw = take(vt ? 0 : 2 * 2 * nprob * Ds * Np);
     L.pw2 = take(vt ? 0 : 2 * 2 * nprob * Ds * Np);
     L.pt = take(vt ? 0 : 2 * 2 * nprob * Ds * Np);
-    L.pa = take(vt ? 2 * 2 * nprob * Nt * Mp : 2 * 2 * nprob * Ds * Dp);       // A  (core x core)
-    L.pb = take(vt ? 2 * 2 * nprob * Nt * Mp : 2 * 2 * nprob * Ds * Dp);       // Bm
+    L.pa = take(vt ? 2 * 2 * nprob * Nk * Mp : 2 * 2 * nprob * Ds * Dp);       // A  (core x core)
+    L.pb = take(vt ? 2 * 2 * nprob * Nk * Mp : 2 * 2 * nprob * Ds * Dp);       // Bm
     L.pkt = take(vt ? 0 : 2 * 2 * nprob * Ns * Np);
     L.psw = take(2 * 2 * nprob * Ns * Dp);
     L.vfg = take(vt ? 2 * 2 * nprob * Ns * Mp : 0);
-    L.vfgt = take(vt ? 2 * 2 * nprob * Nt * Np : 0);
-    L.vginvc = take(vt ? 2 * 2 * nprob * Nt * Mp : 0);
-    L.vginvt = take(vt ? 2 * 2 * nprob * Nt * Mp : 0);
-    L.vx0 = take(vt ? 2 * 2 * nprob * Nt * Xp : 0);
-    L.vx1 = take(vt ? 2 * 2 * nprob * Nt * Xp : 0);
-    L.vx2 = take(vt ? 2 * 2 * nprob * Nt * Xp : 0);
-    L.vh = take(vt ? 2 * 2 * nprob * Nt * Mp : 0);
-    L.vm2 = take(vt ? 2 * 2 * nprob * Nt * Mp : 0);
-    L.vginv = take(vt ? 4 * nprob * Nt * Nt : 0);
-    L.vthraw = take(vt ? 4 * nprob * Nt * Nt : 0);
-    L.vftf = take(vt ? 4 * nprob * Nt * Nt : 0);
+    L.vfgt = take(vt ? 2 * 2 * nprob * Nk * Np : 0);
+    L.vginvc = take(vt ? 2 * 2 * nprob * Nk * Mp : 0);
+    L.vginvt = take(vt ? 2 * 2 * nprob * Nk * Mp : 0);
+    L.vx0 = take(vt ? 2 * 2 * nprob * Nk * Xp : 0);
+    L.vx1 = take(vt ? 2 * 2 * nprob * Nk * Xp : 0);
+    L.vx2 = take(vt ? 2 * 2 * nprob * Nk * Xp : 0);
+    L.vh = take(vt ? 2 * 2 * nprob * Nk * Mp : 0);
+    L.vm2 = take(vt ? 2 * 2 * nprob * Nk * Mp : 0);
+    L.vginv = take(vt ? 4 * nprob * Nk * Nt : 0);
+    L.vthraw = take(vt ? 4 * nprob * Nk * Nt : 0);
+    L.vftf = take(vt ? 4 * nprob * Nk * Nt : 0);
     L.gsw = take(4 * nprob * Ns * Ds);
     L.pvec = take(4 * nprob * 4 * Ns);
     L.pscal = take(4 * nprob * 4);
-    L.pfro = take(4 * nprob * polar_fro_slots(vt ? s.Nt : s.Ds));
-    L.pres = take(4 * nprob * polar_fro_slots(vt ? s.Nt : s.Ds));
+    L.pfro = take(4 * nprob * polar_fro_slots(vt ? L.Nk : s.Ds));
+    L.pres = take(4 * nprob * polar_fro_slots(vt ? L.Nk : s.Ds));
     L.gdir = take(4 * P * B * Ns * Ds);
     L.theta = take(2 * P * B * Nk * L.NsPad);
     L.theta_lo = take(2 * P * B * Nk * L.NsPad);
@@ -217,15 +219,12 @@ int check_shape(const basd_shape& s) {
     if (s.polar_steps != 0 && (s.polar_steps < kPolarStepsDefault || s.polar_steps > kPolarStepsMax))
         return fail("polar_steps must be 0 (default %d) or %d..%d, got %d", kPolarStepsDefault, kPolarStepsDefault, kPolarStepsMax, s.polar_steps);
     if (polar_path(s) == kPathTeacherTokens) {
-        // rank(C) = min(Ns, Nt) - 1 < Ds: the polar iteration runs in the teacher's token space
-        if (s.Nt > s.Ns)
-            return fail("Ds=%d > Ns-1=%d with Nt=%d > Ns: the student-token-space form of the polar iteration is not built yet", s.Ds, s.Ns - 1, s.Nt);
-        if (s.Nt > kVtMaxTokens)
-            return fail("Ds=%d > Nt-1 with Nt=%d > %d: the token-space Cholesky factor no longer fits shared memory", s.Ds, s.Nt, kVtMaxTokens);
+        // rank(C) = min(Ns, Nt) - 1 < Ds: the polar iteration runs in token space, on the coarser of the two token grids
+        const int nk = s.Nt < s.Ns ? s.Nt : s.Ns;
+        if (nk > kVtMaxTokens)
+            return fail("Ds=%d > min(Ns, Nt) - 1 with min(Ns, Nt) = %d > %d: the token-space Cholesky factor no longer fits shared memory", s.Ds, nk, kVtMaxTokens);
         if (s.Nt < 2) return fail("Nt >= 2 required");
     }
-    if (static_cast<long long>(s.B) * s.Nt * s.world_size < s.Ds)
-        return fail("pooled rows M < Ds (layer_selector.py:14-15 branch) is not supported");
     return 0;
 }
 
@@ -295,7 +294,7 @@ extern "C" int basd_view(const basd_shape* shape, void* workspace, const char* n
         {"corr", L.corr, P * Ds}, {"ssum", L.ssum, P * B},
         // polar iteration state (bf16 pairs: count is in bf16 elements, hi block then lo block)
         {"polar_w", (polar_steps() % 2) ? L.pw2 : L.pw, 2 * P * B * Ds * L.Np}, {"polar_kt", L.pkt, 2 * P * B * Ns * L.Np},
-        {"polar_sw", L.psw, 2 * P * B * Ns * ((Ds + 63) / 64 * 64)}, {"polar_a", L.pa, 2 * P * B * Ds * ((Ds + 63) / 64 * 64)}, {"polar_gsw", L.gsw, P * B * Ns * Ds}, {"polar_fro2", L.pfro, P * B * static_cast<size_t>(polar_fro_slots(L.path == kPathTeacherTokens ? s.Nt : s.Ds))},
+        {"polar_sw", L.psw, 2 * P * B * Ns * ((Ds + 63) / 64 * 64)}, {"polar_a", L.pa, 2 * P * B * Ds * ((Ds + 63) / 64 * 64)}, {"polar_gsw", L.gsw, P * B * Ns * Ds}, {"polar_fro2", L.pfro, P * B * static_cast<size_t>(polar_fro_slots(L.path == kPathTeacherTokens ? L.Nk : s.Ds))},
         {"theta", L.theta, P * B * L.Nk * L.NsPad},
     };
     for (const E& e : table)
@@ -444,18 +443,18 @@ extern "C" int basd_forward_solve(const basd_shape* shape, const basd_inputs* in
             pa.Bm = split(L.pb, s.Ds, s.Ds);
             pa.Kt = split(L.pkt, s.Ns, s.Ns);
         } else {
-            pa.vt = 1; pa.Nt = s.Nt; pa.NtPad = L.NsPad; pa.Dsp = L.Dsp;
-            pa.A = split(L.pa, s.Nt, s.Nt);
-            pa.Bm = split(L.pb, s.Nt, s.Nt);
-            pa.FG = split(L.vfg, s.Ns, s.Nt);
-            pa.FGt = split(L.vfgt, s.Nt, s.Ns);
-            pa.GinvC = split(L.vginvc, s.Nt, s.Nt);
-            pa.GinvT = split(L.vginvt, s.Nt, s.Nt);
-            pa.X0 = split(L.vx0, s.Nt, L.Dsp);
-            pa.X1 = split(L.vx1, s.Nt, L.Dsp);
-            pa.X2 = split(L.vx2, s.Nt, L.Dsp);
-            pa.Hm = split(L.vh, s.Nt, s.Nt);
-            pa.M2 = split(L.vm2, s.Nt, s.Nt);
+            pa.vt = 1; pa.Nt = L.Nk; pa.NtPad = L.NsPad; pa.Dsp = L.Dsp;
+            pa.A = split(L.pa, L.Nk, L.Nk);
+            pa.Bm = split(L.pb, L.Nk, L.Nk);
+            pa.FG = split(L.vfg, s.Ns, L.Nk);
+            pa.FGt = split(L.vfgt, L.Nk, s.Ns);
+            pa.GinvC = split(L.vginvc, L.Nk, L.Nk);
+            pa.GinvT = split(L.vginvt, L.Nk, L.Nk);
+            pa.X0 = split(L.vx0, L.Nk, L.Dsp);
+            pa.X1 = split(L.vx1, L.Nk, L.Dsp);
+            pa.X2 = split(L.vx2, L.Nk, L.Dsp);
+            pa.Hm = split(L.vh, L.Nk, L.Nk);
+            pa.M2 = split(L.vm2, L.Nk, L.Nk);
             pa.ginv = reinterpret_cast<float*>(ws + L.vginv);
             pa.thraw = reinterpret_cast<float*>(ws + L.vthraw);
             pa.ftf = reinterpret_cast<float*>(ws + L.vftf);
@@ -465,7 +464,7 @@ extern "C" int basd_forward_solve(const basd_shape* shape, const basd_inputs* in
     pa.vec = reinterpret_cast<float*>(ws + L.pvec);
     pa.scal = reinterpret_cast<float*>(ws + L.pscal);
     pa.fro2 = reinterpret_cast<float*>(ws + L.pfro);
-    pa.fro_slots = polar_fro_slots(vt ? s.Nt : s.Ds);
+    pa.fro_slots = polar_fro_slots(vt ? L.Nk : s.Ds);
     pa.resid = reinterpret_cast<float*>(ws + L.pres);
     pa.steps = s.polar_steps ? s.polar_steps : kPolarStepsDefault;
     pa.gdir = reinterpret_cast<float*>(ws + L.gdir);
@@ -503,7 +502,7 @@ extern "C" int basd_backward_dots(const basd_shape* shape, const basd_inputs* in
                                      thi, tlo, s.P * s.B, L.Nk, s.Dt, dtm, dtm_lo, st)));
     float* gw = reinterpret_cast<float*>(ws + L.gw);
     TIMED(13, 3, CK(launch_wgrad_dots(tt, dtm, dtm_lo, reinterpret_cast<float*>(ws + L.gwt), reinterpret_cast<float*>(ws + L.rows), s.Lt, s.P, s.B, s.Nt,
-                         s.Ns, s.Dt, gw, reinterpret_cast<float*>(ws + L.gw_part), st, L.path == kPathTeacherTokens, r.teacher_bs)));
+                         s.Ns, s.Dt, gw, reinterpret_cast<float*>(ws + L.gw_part), st, L.path == kPathTeacherTokens && L.Nk == s.Nt && s.Nt != s.Ns, r.teacher_bs)));
     return 0;
 }
 

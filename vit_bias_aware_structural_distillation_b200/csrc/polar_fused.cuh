@@ -118,7 +118,6 @@ polar_fused_abm_kernel(const __grid_constant__ PolarFusedMaps maps, const PolarF
                         tma_load_4d(st + 2 * a_bytes + i * b_bytes, &maps.w[i], &full_bar[s], 0, 0, kb, z);
                     }
                 }
-                if (args.dbg_clock && blockIdx.x == 0 && item < 16) args.dbg_clock[item * 8 + 1] = clock64();
             }
         }
     } else if (warp == 1) {
@@ -320,6 +319,7 @@ polar_fused_abm_kernel(const __grid_constant__ PolarFusedMaps maps, const PolarF
             tc_fence_before();
             __syncwarp();
             if (dbg_e) args.dbg_clock[item * 8 + 7] = clock64();
+            if (args.dbg_clock && blockIdx.x == 0 && item < 16 && e == 4 && lane == 0) args.dbg_clock[item * 8 + 1] = clock64();   // tile 1 stored
             if (lane == 0) mbar_arrive(&tmem_empty_bar[mt]);
         }
         if (lane == 0) tma_store_wait_all();

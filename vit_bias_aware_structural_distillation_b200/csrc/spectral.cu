@@ -134,9 +134,8 @@ __device__ __forceinline__ int mp_count_above(const float* __restrict__ d, const
 }
 // MP rank of diag(d) + u u^T (warp 0 of the CTA; d_lo / d_hi bracket the median eigenvalue by interlacing)
 __device__ __forceinline__ int mp_rank_secular(const float* __restrict__ d, const float* __restrict__ u2, int n, float d_lo, float d_hi,
-                                               float q_ratio /* D / M */) {
-    // median = ascending index (n-1)/2 (torch.median: lower middle): the smallest t with #{x > t} <= n - 1 - (n-1)/2
-    const int want = n - 1 - (n - 1) / 2;
+                                               float q_ratio /* D / M */, int want) {
+    // median of the top m eigenvalues = the smallest t with #{x > t} <= want = m - 1 - (m-1)/2 (torch.median: lower middle)
     float lo = d_lo, hi = d_hi;
     for (int it = 0; it < 40; ++it) {
         const float mid = 0.5f * (lo + hi);
@@ -285,13 +284,16 @@ pooled_eig_kernel(const float* __restrict__ stats, int n, int Lt, int P, float M
         }
         __syncthreads();
         if (warp == 0) {
-            // bracket of the median by interlacing: [lambda_(m), lambda_(m+1)] ascending, the top one extended by |u|^2
-            const int mi = (n - 1) / 2;
-            const float d_lo = vals[order[n - 1 - mi]];
+            // M < D (layer_selector.py:14-15): the reference takes the M eigenvalues of F F^T / M = the top M of the D x D problem
+            // (the other D - M are zero): median and count run over those.
+            const int m_eff = Mrows < static_cast<float>(n) ? max(1, static_cast<int>(Mrows + 0.5f)) : n;
+            const int want = m_eff - 1 - (m_eff - 1) / 2;         // eigenvalues above the median (descending index of the median)
+            // bracket of the median by interlacing (descending order: lambda_i <= x_i <= lambda_(i-1)), the top one extended by |u|^2
+            const float d_lo = vals[order[want]];
             float d_hi;
-            if (mi + 1 < n) d_hi = vals[order[n - 2 - mi]];
+            if (want >= 1) d_hi = vals[order[want - 1]];
             else { float su = 0.f; for (int i = lane; i < n; i += 32) su += u2[i]; d_hi = d_lo + warp_sum(su); }
-            const int rk = mp_rank_secular(vals, u2, n, d_lo, d_hi, static_cast<float>(n) * invM);
+            const int rk = mp_rank_secular(vals, u2, n, d_lo, d_hi, static_cast<float>(n) * invM, want);
             if (lane == 0) ranks[p] = min(rk, n - 1);
         }
         __syncthreads();
