@@ -44,7 +44,21 @@ typedef struct basd_shape {
     int polar_steps;/* Newton-Schulz steps of the Procrustes polar iteration: 0 = default (10: singular values of the
                        cross-covariance down to 3e-5 ||C||_F), up to 16 (each step more divides that floor by ~4);
                        the residual of the last forward is in basd_view "polar_resid" */
+    int mode;       /* BASD_MODE_*: which part of the path the four phases run (0 = the whole loss)                     */
 } basd_shape;
+
+/* basd_shape.mode
+ *   BASD_MODE_LOSS      BASDLoss.forward's geometric term (combined.py:58-76): selector + alignment + Procrustes.
+ *   BASD_MODE_PAIR      geometric_relational_loss (relational.py:5-50) of ONE student / teacher pair on its own: Lt = P = 1, the
+ *                       layer selector is bypassed (mixing weight 1), proj_s / proj_t / log_temperatures are not read (may be
+ *                       null); grad_log_temperatures comes back as zeros.
+ *   BASD_MODE_SELECTOR  GrassmannianLayerSelector.forward's mixing weights (layer_selector.py:116-152 up to :108) on their own:
+ *                       phases 1-2 stop at view "w" [P*Lt] (attention pointers are not read, geo_loss = 0); phase 3 is a no-op;
+ *                       phase 4 takes d(total)/d(w) from view "gw" (written by the caller, *grad_geo multiplies it) and returns
+ *                       the gradients w.r.t. the student tensors and log_temperatures through the closed-form selector backward. */
+#define BASD_MODE_LOSS 0
+#define BASD_MODE_PAIR 1
+#define BASD_MODE_SELECTOR 2
 
 typedef struct basd_inputs {
     const void* student[BASD_MAX_POINTS];   /* P  tensors [B,Ns,Ds]; element strides below            */
@@ -105,6 +119,12 @@ int basd_cls_attention_rows(const void* q, const void* k, int dtype, int B, int 
  * the only part of the map relational.py:24 reads.  Asynchronous on `stream` when the host memory is pinned. */
 int basd_copy_cls_rows_h2d(const void* host_attn, int elem_bytes, int B, int H, int S, const int64_t* strides, void* dev_rows,
                            void* stream);
+
+/* _align_token_count (combined.py:9-14) on its own: 1-D linear resampling along the token axis (align_corners = False) of
+ * tokens [B,Nin,D] (element strides (b,n,d)) to a dense [B,Nout,D] tensor of the same dtype, and its adjoint
+ * (grad_out dense [B,Nout,D] -> grad_in dense [B,Nin,D]).  Inside the loss the resampling is fused into the teacher mix. */
+int basd_align_tokens(const void* tokens, int dtype, const int64_t* strides, int B, int Nin, int Nout, int D, void* out, void* stream);
+int basd_align_tokens_bwd(const void* grad_out, int dtype, int B, int Nin, int Nout, int D, void* grad_in, void* stream);
 
 /* Test hooks (used by tests/ only). */
 int basd_selftest_gemm(int variant, const void* A, const void* B, float* C, int M, int N, int K, void* stream);

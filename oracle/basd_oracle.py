@@ -64,6 +64,52 @@ def importance_rows(attn: torch.Tensor, has_cls: bool) -> torch.Tensor:
     return attn.mean(dim=(1, 2))
 
 
+def geometric_relational_loss(student_tokens, teacher_tokens, teacher_attn, *, has_cls, dtype=torch.float32):
+    """relational.py:5-50 on its own (one student / teacher pair, teacher tokens already on the student's token grid)."""
+    s, t = student_tokens.to(dtype), teacher_tokens.to(dtype)
+    imp = importance_rows(teacher_attn.to(dtype), has_cls)               # relational.py:22-27
+    imp = interp_linear_1d(imp, s.shape[1])                              # relational.py:29-32
+    a = imp / imp.sum(dim=-1, keepdim=True)                              # relational.py:34
+    mu_s = (a.unsqueeze(-1) * s).sum(dim=1, keepdim=True)                # relational.py:36-39
+    mu_t = (a.unsqueeze(-1) * t).sum(dim=1, keepdim=True)
+    rt = a.unsqueeze(-1).sqrt()                                          # relational.py:41-43
+    s_w, t_w = rt * (s - mu_s), rt * (t - mu_t)
+    tr_s, tr_t = (s_w * s_w).sum(dim=(1, 2)), (t_w * t_w).sum(dim=(1, 2))     # relational.py:45-46
+    nuc = torch.linalg.matrix_norm(torch.bmm(s_w.transpose(1, 2), t_w), ord="nuc")   # relational.py:47-48
+    return (tr_s + tr_t - 2.0 * nuc).mean()                              # relational.py:50
+
+
+def selector_forward(student, teacher, attn, proj_s, proj_t, log_temperatures, extraction_indices, dtype=torch.float32):
+    """GrassmannianLayerSelector.forward (layer_selector.py:116-152) on its own: (mixed_teachers, mixed_attentions, ranks)."""
+    t_idx = sorted(teacher.keys())
+    Ds = proj_s.shape[0]
+    Pt, Ps = proj_t.to(dtype), proj_s.to(dtype)
+    ranks, bases, svals = {}, {}, {}
+    with torch.no_grad():
+        for j in t_idx:                                                  # ls:69-74, 131-138
+            z = teacher[j].to(dtype).reshape(-1, teacher[j].shape[2]) @ Pt.T
+            ranks[j] = min(mp_rank(z), Ds - 1)
+            zc = z - z.mean(dim=0, keepdim=True)
+            _, S, Vt = torch.linalg.svd(zc, full_matrices=False)
+            bases[j], svals[j] = Vt[: ranks[j]].T, S[: ranks[j]]
+    T = torch.stack([teacher[j].to(dtype) for j in t_idx])              # ls:128-129
+    A = torch.stack([attn[j].to(dtype) for j in t_idx])
+    mixed_t, mixed_a = {}, {}
+    for i, layer in enumerate(extraction_indices):                       # ls:76-114
+        zs = student[layer].to(dtype).reshape(-1, Ds) @ Ps.T
+        zs = zs - zs.mean(dim=0, keepdim=True)
+        _, _, Vts = torch.linalg.svd(zs, full_matrices=False)
+        d2 = []
+        for j in t_idx:
+            sig = torch.linalg.svdvals(Vts[: ranks[j]] @ bases[j])
+            theta = torch.acos(sig.clamp(max=1.0 - torch.finfo(sig.dtype).eps))
+            d2.append((svals[j] * theta.pow(2)).sum() / svals[j].sum())
+        w = F.softmax(-torch.stack(d2) / F.softplus(log_temperatures.to(dtype)[i]), dim=0).to(T.dtype)
+        mixed_t[layer] = (w.view(-1, 1, 1, 1) * T).sum(dim=0)
+        mixed_a[layer] = (w.view(-1, 1, 1, 1, 1) * A).sum(dim=0)
+    return mixed_t, mixed_a, ranks
+
+
 def forward(student, teacher, attn, proj_s, proj_t, log_temperatures, token_layers, *, has_cls,
             n_student_tokens, dtype=torch.float32, ce_loss=None, detach_weights=False):
     """Whole hot path.  `student`/`teacher`/`attn` are dicts like the reference takes.

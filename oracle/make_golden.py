@@ -76,10 +76,52 @@ def run(name: str, w: synth.Workload, label_smoothing=0.001, full=False):
     print(f"{name}: loss {loss.item():.6f} ranks {out['ranks']} tgrad {out['grad_log_temperatures'].tolist()} ({dt:.1f}s)", flush=True)
 
 
+def run_standalone():
+    """The reference's standalone entry points on their own: geometric_relational_loss (relational.py:5-50), _align_token_count
+    (combined.py:9-14) and GrassmannianLayerSelector.forward (layer_selector.py:116-152), values and gradients."""
+    from src.losses.combined import _align_token_count
+    from src.losses.layer_selector import GrassmannianLayerSelector
+    from src.losses.relational import geometric_relational_loss
+    w, inp, t_al, attn_same, attn_nocls = synth.standalone_inputs()
+    out = dict(torch_version=torch.__version__)
+    layer0 = w.token_layers()[0]
+    # a11: aligned attention (CLS), attention on another token grid (CLS, 36 -> 48), CNN-style attention without CLS (36 -> 48)
+    for key, attn, has_cls in (("pair_cls", attn_same, True), ("pair_cls_resampled", inp["attn"][0].float(), True), ("pair_nocls", attn_nocls, False)):
+        s = inp["student"][layer0].float().clone().requires_grad_()
+        loss = geometric_relational_loss(s, t_al.float(), attn, has_cls_token=has_cls)
+        loss.backward()
+        out[key] = dict(loss=loss.detach(), grad_student=s.grad.clone())
+    # a8: up- and down-sampling, with the gradient of a seeded linear functional
+    for key, n_out in (("align_up", 48), ("align_down", 20), ("align_same", 36)):
+        x = inp["teacher"][0].float().clone().requires_grad_()
+        y = _align_token_count(x, n_out)
+        probe = probes(y.shape, n=1, seed=5)[0]
+        (y * probe).sum().backward()
+        out[key] = dict(out=y.detach().clone(), grad_in=x.grad.clone(), same_object=y is x)
+    # a7: the selector's forward on its own
+    torch.manual_seed(0)
+    sel = GrassmannianLayerSelector(num_extraction_points=w.P, student_dim=w.Ds, teacher_dim=w.Dt)
+    S = {l: v.float().clone().requires_grad_() for l, v in inp["student"].items()}
+    T = {j: v.float() for j, v in inp["teacher"].items()}
+    A = {j: v.float() for j, v in inp["attn"].items()}
+    mixed_t, mixed_a = sel(S, T, A, w.token_layers())
+    total = sum((mixed_t[l] * probes(mixed_t[l].shape, n=1, seed=6 + i)[0]).sum() for i, l in enumerate(w.token_layers()))
+    total = total + sum((mixed_a[l] * probes(mixed_a[l].shape, n=1, seed=16 + i)[0]).sum() for i, l in enumerate(w.token_layers()))
+    total.backward()
+    out["selector"] = dict(mixed_tokens={l: mixed_t[l].detach().clone() for l in mixed_t}, mixed_attn_cls_row={l: mixed_a[l][:, :, 0, :].detach().clone() for l in mixed_a},
+                           ranks=dict(sel.subspace_ranks), grad_student={l: S[l].grad.clone() for l in S},
+                           grad_log_temperatures=sel.log_temperatures.grad.clone())
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    torch.save(out, os.path.join(GOLDEN_DIR, "standalone.pt"))
+    print("standalone:", {k: (v["loss"].item() if "loss" in v else "ok") for k, v in out.items() if isinstance(v, dict)}, flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["tiny", "cfg1"]
     for k in which:
-        if k == "tiny":
+        if k == "standalone":
+            run_standalone()
+        elif k == "tiny":
             for n, w in TINY.items():
                 run(n, w, full=True)
         elif k == "small":

@@ -80,3 +80,14 @@ def make_inputs(w: Workload, seed: int = 1234, batch: int | None = None, attn_dt
 
 def module_config(w: Workload):
     return types.SimpleNamespace(num_extraction_points=w.P)
+
+
+def standalone_inputs():
+    """Seeded inputs of tests/golden/standalone.pt (the reference's standalone entry points; the fixture stores outputs only)."""
+    w = Workload("standalone", 3, 48, 36, 40, 72, 3, 2, True, P=2)
+    inp = make_inputs(w, seed=77)
+    g = torch.Generator().manual_seed(78)
+    teacher_aligned = spiked(w.B, w.Ns, w.Dt, 12, g)                       # teacher tokens already on the student's grid
+    attn_same = torch.softmax(2 * torch.randn(w.B, w.H, w.Ns + 1, w.Ns + 1, generator=g), -1).bfloat16().float()
+    attn_nocls = torch.softmax(2 * torch.randn(w.B, w.H, w.Nt, w.Nt, generator=g), -1).bfloat16().float()
+    return w, inp, teacher_aligned, attn_same, attn_nocls

@@ -38,16 +38,19 @@ def test_workspace_bytes_is_host_only(lib):
         s = Shape(P=4, act_dtype=1, attn_dtype=1, world_size=1, **kw)
         assert lib.basd_workspace_bytes(ctypes.byref(s), ctypes.byref(n)) == 0, lib.basd_last_error().decode()
         assert n.value < 40e9
+    # D_s > N_s - 1 with a finer teacher grid (ViT-S at 196 tokens <- a 384 px teacher): token-space form on the student's grid
+    s = Shape(P=4, act_dtype=1, attn_dtype=1, world_size=1, B=64, Ns=196, Nt=576, Ds=384, Dt=768, Lt=12, H=12, has_cls=1)
+    assert lib.basd_workspace_bytes(ctypes.byref(s), ctypes.byref(n)) == 0, lib.basd_last_error().decode()
 
 
 @pytest.mark.parametrize("field,value,needle", [("Ds", 190, "multiples of 8"), ("Ds", 2048, "not supported"), ("Lt", 100, "Lt <="),
-                                                ("world_size", 0, "world_size"), ("Nt", 256, "student-token-space form")])
+                                                ("world_size", 0, "world_size"), ("Nt", 256, "token-space Cholesky factor"), ("mode", 7, "mode")])
 def test_unsupported_shapes_fail_loudly(lib, field, value, needle):
     from vit_bias_aware_structural_distillation_b200._lib import Shape
     kw = dict(B=8, Ns=196, Nt=196, Ds=192, Dt=768, Lt=12, P=4, H=12, has_cls=1, act_dtype=1, attn_dtype=1, world_size=1)
     kw[field] = value
     if field == "Nt":
-        kw["Ds"] = 384          # D_s > N_s - 1 with more teacher than student tokens: the one remaining unbuilt form
+        kw["Ds"], kw["Ns"] = 384, 300   # D_s > min(N_s, N_t) - 1 with more than 224 tokens on the coarser grid: the one remaining unbuilt size
     s = Shape(**kw)
     n = ctypes.c_size_t()
     assert lib.basd_workspace_bytes(ctypes.byref(s), ctypes.byref(n)) != 0

@@ -624,3 +624,53 @@ def test_irregular_shapes_against_oracle(lib, cuda_dev, shape):
         assert m.last_polar_residual.item() <= m.POLAR_RESIDUAL_OK
         for l in ref["grad_student"]:
             assert rel(out["grad_student"][l], ref["grad_student"][l]) < TOL_SGRAD
+
+
+def _probe(shape, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(shape, generator=g)
+
+
+def test_standalone_entry_points_against_reference_golden(lib, cuda_dev):
+    """The reference's three standalone entry points of the path, each through its own drop-in:
+    geometric_relational_loss (relational.py:5-50; BASD_MODE_PAIR), _align_token_count (combined.py:9-14; its own two kernels) and
+    GrassmannianLayerSelector.forward (layer_selector.py:116-152; BASD_MODE_SELECTOR) against tests/golden/standalone.pt."""
+    import vit_bias_aware_structural_distillation_b200 as pkg
+    g = torch.load(os.path.join(GOLD, "standalone.pt"), weights_only=False)
+    w, inp, t_al, attn_same, attn_nocls = synth.standalone_inputs()
+    layer0 = w.token_layers()[0]
+    for key, attn, has_cls in (("pair_cls", attn_same, True), ("pair_cls_resampled", inp["attn"][0].float(), True), ("pair_nocls", attn_nocls, False)):
+        for act in (torch.bfloat16, torch.float32):
+            s = inp["student"][layer0].to(cuda_dev).to(act).requires_grad_()
+            loss = pkg.geometric_relational_loss(s, t_al.to(cuda_dev).to(act), attn.to(cuda_dev), has_cls_token=has_cls)
+            loss.backward()
+            assert abs(loss.item() - g[key]["loss"].item()) <= TOL_LOSS * abs(g[key]["loss"].item()), key
+            assert rel(s.grad.float().cpu(), g[key]["grad_student"]) < TOL_SGRAD, key
+    for key, n_out in (("align_up", 48), ("align_down", 20), ("align_same", 36)):
+        x = inp["teacher"][0].float().to(cuda_dev).requires_grad_()
+        y = pkg.align_token_count(x, n_out)
+        assert (y is x) == g[key]["same_object"]
+        (y * _probe(y.shape, 5).to(cuda_dev)).sum().backward()
+        assert torch.allclose(y.detach().cpu(), g[key]["out"], atol=1e-5), key
+        assert torch.allclose(x.grad.cpu(), g[key]["grad_in"], atol=1e-5), key
+        xv = torch.zeros(x.shape[0], x.shape[1] + 1, x.shape[2], device=cuda_dev, dtype=torch.bfloat16)     # a CLS-stripped bf16 view
+        xv[:, 1:] = inp["teacher"][0].to(cuda_dev)
+        yv = pkg.align_token_count(xv[:, 1:, :], n_out)
+        assert rel(yv.float().cpu(), g[key]["out"]) < 4e-3, key                                               # bf16 output rounding
+    torch.manual_seed(0)
+    sel = pkg.GrassmannianLayerSelector(num_extraction_points=w.P, student_dim=w.Ds, teacher_dim=w.Dt).to(cuda_dev)
+    S = {l: v.float().to(cuda_dev).requires_grad_() for l, v in inp["student"].items()}
+    T = {j: v.float().to(cuda_dev) for j, v in inp["teacher"].items()}
+    A = {j: v.float().to(cuda_dev) for j, v in inp["attn"].items()}
+    mt, ma = sel(S, T, A, w.token_layers())
+    total = sum((mt[l] * _probe(mt[l].shape, 6 + i).to(cuda_dev)).sum() for i, l in enumerate(w.token_layers()))
+    total = total + sum((ma[l] * _probe(ma[l].shape, 16 + i).to(cuda_dev)).sum() for i, l in enumerate(w.token_layers()))
+    total.backward()
+    gs = g["selector"]
+    assert sel.subspace_ranks == gs["ranks"]
+    for l in w.token_layers():
+        assert rel(mt[l].detach().cpu(), gs["mixed_tokens"][l]) < 1e-4
+        assert rel(ma[l][:, :, 0, :].detach().cpu(), gs["mixed_attn_cls_row"][l]) < 1e-4
+        assert rel(S[l].grad.cpu(), gs["grad_student"][l]) < TOL_SGRAD
+    gt, rt = sel.log_temperatures.grad.cpu(), gs["grad_log_temperatures"]
+    assert ((gt - rt).abs() <= TOL_TGRAD * rt.abs() + 1e-7).all(), f"temperature grads {gt.tolist()} vs {rt.tolist()}"

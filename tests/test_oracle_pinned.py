@@ -121,3 +121,44 @@ def test_procrustes_core_zero_residual_for_rotated_teacher():
     core = K.procrustes_core(s, t, a)
     full = K.procrustes_core(s, torch.randn(N, 54, dtype=torch.float64), a)
     assert core["loss"].abs() < 1e-2 * full["loss"].abs()
+
+
+def _probe(shape, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(shape, generator=g)
+
+
+def test_oracle_standalone_entry_points_reproduce_reference_golden():
+    """geometric_relational_loss (relational.py:5-50), _align_token_count (combined.py:9-14) and GrassmannianLayerSelector.forward
+    (layer_selector.py:116-152) on their own: the restatements against tests/golden/standalone.pt (the unmodified reference)."""
+    g = torch.load(os.path.join(GOLD, "standalone.pt"), weights_only=False)
+    w, inp, t_al, attn_same, attn_nocls = synth.standalone_inputs()
+    layer0 = w.token_layers()[0]
+    for key, attn, has_cls in (("pair_cls", attn_same, True), ("pair_cls_resampled", inp["attn"][0].float(), True), ("pair_nocls", attn_nocls, False)):
+        s = inp["student"][layer0].float().clone().requires_grad_()
+        loss = O.geometric_relational_loss(s, t_al.float(), attn, has_cls=has_cls)
+        loss.backward()
+        assert abs(loss.item() - g[key]["loss"].item()) <= 2e-6 * abs(g[key]["loss"].item())
+        assert rel(s.grad, g[key]["grad_student"]) < 1e-3
+    for key, n_out in (("align_up", 48), ("align_down", 20), ("align_same", 36)):
+        x = inp["teacher"][0].float().clone().requires_grad_()
+        y = O.interp_linear_1d(x, n_out)
+        assert (y is x) == g[key]["same_object"]
+        (y * _probe(y.shape, 5)).sum().backward()
+        assert torch.allclose(y, g[key]["out"], atol=1e-5) and torch.allclose(x.grad, g[key]["grad_in"], atol=1e-5)
+    torch.manual_seed(0)
+    ps = torch.empty(w.Ds, w.Ds); pt = torch.empty(w.Ds, w.Dt)
+    nn.init.orthogonal_(ps); nn.init.orthogonal_(pt)
+    logt = torch.full((w.P,), math.log(math.exp(1.0) - 1)).requires_grad_()
+    S = {l: v.float().clone().requires_grad_() for l, v in inp["student"].items()}
+    mt, ma, ranks = O.selector_forward(S, {j: v.float() for j, v in inp["teacher"].items()}, {j: v.float() for j, v in inp["attn"].items()},
+                                       ps, pt, logt, w.token_layers())
+    total = sum((mt[l] * _probe(mt[l].shape, 6 + i)).sum() for i, l in enumerate(w.token_layers()))
+    total = total + sum((ma[l] * _probe(ma[l].shape, 16 + i)).sum() for i, l in enumerate(w.token_layers()))
+    total.backward()
+    gs = g["selector"]
+    assert ranks == gs["ranks"]
+    for l in w.token_layers():
+        assert rel(mt[l], gs["mixed_tokens"][l]) < 1e-5 and rel(ma[l][:, :, 0, :], gs["mixed_attn_cls_row"][l]) < 1e-5
+        assert rel(S[l].grad, gs["grad_student"][l]) < 2e-3
+    assert torch.allclose(logt.grad, gs["grad_log_temperatures"], rtol=2e-3, atol=1e-7)

@@ -8,6 +8,7 @@ import os
 MAX_POINTS = 8
 MAX_LAYERS = 64
 DTYPE_F32, DTYPE_BF16 = 0, 1
+MODE_LOSS, MODE_PAIR, MODE_SELECTOR = 0, 1, 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbasd_b200.so")
@@ -15,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libbasd_b200.so")
 
 class Shape(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in
-                ("B", "Ns", "Nt", "Ds", "Dt", "Lt", "P", "H", "has_cls", "act_dtype", "attn_dtype", "world_size", "polar_steps")]
+                ("B", "Ns", "Nt", "Ds", "Dt", "Lt", "P", "H", "has_cls", "act_dtype", "attn_dtype", "world_size", "polar_steps", "mode")]
 
 
 class Inputs(ctypes.Structure):
@@ -37,7 +38,7 @@ EXPORTS = [
     "basd_view", "basd_mp_rank_workspace_bytes", "basd_mp_rank", "basd_selftest_gemm", "basd_selftest_eig",
     "basd_last_error", "basd_version", "basd_timing_enable", "basd_timing_reset", "basd_launch_count", "basd_timing_slots",
     "basd_timing_name", "basd_timing_read", "basd_polar_steps", "basd_polar_launches_per_step", "basd_cls_attention_rows",
-    "basd_copy_cls_rows_h2d", "basd_debug_polar_clocks", "basd_debug_spectral_clocks",
+    "basd_copy_cls_rows_h2d", "basd_debug_polar_clocks", "basd_debug_spectral_clocks", "basd_align_tokens", "basd_align_tokens_bwd",
 ]
 
 _lib = None
@@ -72,6 +73,8 @@ def load():
     lib.basd_cls_attention_rows.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                             ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64), ctypes.c_float, vp, vp]
     lib.basd_copy_cls_rows_h2d.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int64), vp, vp]
+    lib.basd_align_tokens.argtypes = [vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int64), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp]
+    lib.basd_align_tokens_bwd.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp]
     lib.basd_launch_count.restype = ctypes.c_longlong
     lib.basd_timing_name.restype = ctypes.c_char_p
     lib.basd_timing_name.argtypes = [ctypes.c_int]

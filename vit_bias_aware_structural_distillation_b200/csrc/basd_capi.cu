@@ -213,6 +213,8 @@ Layout make_layout(const basd_shape& s) {
 int check_shape(const basd_shape& s) {
     if (s.B < 1 || s.Ns < 2 || s.Nt < 1 || s.Lt < 1 || s.P < 1) return fail("invalid shape");
     if (s.world_size < 1) return fail("world_size must be >= 1");
+    if (s.mode < BASD_MODE_LOSS || s.mode > BASD_MODE_SELECTOR) return fail("unknown basd_shape.mode %d", s.mode);
+    if (s.mode == BASD_MODE_PAIR && (s.Lt != 1 || s.P != 1)) return fail("BASD_MODE_PAIR takes one student and one teacher tensor (Lt = P = 1)");
     if (s.P > BASD_MAX_POINTS || s.Lt > BASD_MAX_LAYERS) return fail("P <= %d and Lt <= %d required", BASD_MAX_POINTS, BASD_MAX_LAYERS);
     if (s.Ds % 8 || s.Dt % 8) return fail("Ds and Dt must be multiples of 8 (16-byte rows), got %d, %d", s.Ds, s.Dt);
     if (s.Ds > 1024) return fail("Ds=%d > 1024 is not supported", s.Ds);
@@ -256,7 +258,7 @@ int resolve(const basd_shape& s, const basd_inputs& in, uint8_t* ws, const Layou
                         (long long)in.student_strides[0], (long long)in.student_strides[1], (long long)in.student_strides[2]);
     }
     for (int j = 0; j < s.Lt; ++j) {
-        if (!in.teacher[j] || !in.attn[j]) return fail("null teacher/attention pointer at layer %d", j);
+        if (!in.teacher[j] || (!in.attn[j] && s.mode != BASD_MODE_SELECTOR)) return fail("null teacher/attention pointer at layer %d", j);
         r->teacher[j] = pack ? reinterpret_cast<const __nv_bfloat16*>(ws + L.tpk) + static_cast<size_t>(j) * s.B * s.Nt * s.Dt
                              : reinterpret_cast<const __nv_bfloat16*>(in.teacher[j]);
         if (reinterpret_cast<uintptr_t>(r->teacher[j]) & 15) return fail("teacher tensor %d not 16-byte aligned", j);
@@ -314,17 +316,21 @@ extern "C" int basd_forward_stats(const basd_shape* shape, const basd_inputs* in
     const size_t stat_stride = static_cast<size_t>(s.Ds) * s.Ds + s.Ds;
     float* stats = reinterpret_cast<float*>(ws + L.stats);
 
-    PtrTable attn;
-    memset(&attn, 0, sizeof attn);
-    for (int j = 0; j < s.Lt; ++j) attn.p[j] = in.attn[j];
-    long long as[4] = {in.attn_strides[0], in.attn_strides[1], in.attn_strides[2], in.attn_strides[3]};
-    TIMED(0, 1, CK(launch_importance_rows(attn, s.attn_dtype == BASD_DTYPE_BF16, s.Lt, s.B, s.H, s.Nt, s.has_cls, as,
-                              reinterpret_cast<float*>(ws + L.rows), st)));
+    const bool selector = s.mode != BASD_MODE_PAIR;            // the pooled statistics feed the layer selector only
+    if (selector && (!in.proj_s || !in.proj_t || !in.log_temperatures)) return fail("null proj_s / proj_t / log_temperatures");
+    if (s.mode != BASD_MODE_SELECTOR) {
+        PtrTable attn;
+        memset(&attn, 0, sizeof attn);
+        for (int j = 0; j < s.Lt; ++j) attn.p[j] = in.attn[j];
+        long long as[4] = {in.attn_strides[0], in.attn_strides[1], in.attn_strides[2], in.attn_strides[3]};
+        TIMED(0, 1, CK(launch_importance_rows(attn, s.attn_dtype == BASD_DTYPE_BF16, s.Lt, s.B, s.H, s.Nt, s.has_cls, as,
+                                  reinterpret_cast<float*>(ws + L.rows), st)));
+    }
     __nv_bfloat16* pt_hi = reinterpret_cast<__nv_bfloat16*>(ws + L.pt_hi);
     __nv_bfloat16* pt_lo = reinterpret_cast<__nv_bfloat16*>(ws + L.pt_lo);
     Scope* pack_scope = new Scope(1, st, 1 + (s.act_dtype == BASD_DTYPE_F32 ? s.Lt + s.P : 0));
     struct ScopeDel { Scope* p; ~ScopeDel() { delete p; } } pack_del{pack_scope};
-    CK(launch_split_bf16(in.proj_t, pt_hi, pt_lo, static_cast<size_t>(s.Ds) * s.Dt, st));
+    if (selector) CK(launch_split_bf16(in.proj_t, pt_hi, pt_lo, static_cast<size_t>(s.Ds) * s.Dt, st));
     if (s.act_dtype == BASD_DTYPE_F32) {
         for (int j = 0; j < s.Lt; ++j)
             CK(launch_pack_bf16(in.teacher[j], 0, in.teacher_strides[0], in.teacher_strides[1], in.teacher_strides[2], s.B, s.Nt, s.Dt,
@@ -336,6 +342,7 @@ extern "C" int basd_forward_stats(const basd_shape* shape, const basd_inputs* in
     delete pack_scope; pack_del.p = nullptr;
     Resolved r;
     if (resolve(s, in, ws, L, &r)) return 1;
+    if (!selector) return 0;
     // A CLS-stripped teacher view is projected as the dense matrix of B (Nt + 1) - 1 rows it is in memory; the rows that
     // belong to no sample leave the projection as zeros, so the Gram and the column sums below are those of the B Nt tokens.
     const size_t Mt_dense = Mt;
@@ -401,10 +408,22 @@ extern "C" int basd_forward_solve(const basd_shape* shape, const basd_inputs* in
     float* d2 = reinterpret_cast<float*>(ws + L.d2);
     float* w = reinterpret_cast<float*>(ws + L.w);
 
-    TIMED(5, 1, CK(launch_pooled_eig(stats, s.Ds, s.Lt, s.P, Mt, Ms, ranks, evals, evk, evc, reinterpret_cast<int*>(ws + L.sweeps),
-                                  reinterpret_cast<float*>(ws + L.eig_scr), st)));
-    TIMED(6, 2, CK(launch_angles(s.Ds, s.Lt, s.P, ranks, evals, evk, evc, in.proj_s, reinterpret_cast<float*>(ws + L.ang_scr), d2,
-                     reinterpret_cast<float*>(ws + L.gamma), reinterpret_cast<float*>(ws + L.cosv), in.log_temperatures, w, st)));
+    if (s.mode == BASD_MODE_PAIR) {
+        // one teacher layer, one student point, no selector: mixing weight 1, rank and distance reported as 0
+        CK(launch_fill_f32(w, 1.f, 1, st));
+        CK(cudaMemsetAsync(ranks, 0, sizeof(int) * s.Lt, st));
+        CK(cudaMemsetAsync(d2, 0, sizeof(float) * s.P * s.Lt, st));
+    } else {
+        TIMED(5, 1, CK(launch_pooled_eig(stats, s.Ds, s.Lt, s.P, Mt, Ms, ranks, evals, evk, evc, reinterpret_cast<int*>(ws + L.sweeps),
+                                      reinterpret_cast<float*>(ws + L.eig_scr), st)));
+        TIMED(6, 2, CK(launch_angles(s.Ds, s.Lt, s.P, ranks, evals, evk, evc, in.proj_s, reinterpret_cast<float*>(ws + L.ang_scr), d2,
+                         reinterpret_cast<float*>(ws + L.gamma), reinterpret_cast<float*>(ws + L.cosv), in.log_temperatures, w, st)));
+    }
+    if (s.mode == BASD_MODE_SELECTOR) {
+        CK(cudaMemsetAsync(geo_loss, 0, sizeof(float), st));
+        CK(cudaMemsetAsync(ws + L.geo_i, 0, sizeof(float) * (s.P + 2), st));
+        return 0;
+    }
     float* a = reinterpret_cast<float*>(ws + L.a);
     float* ssum = reinterpret_cast<float*>(ws + L.ssum);
     TIMED(7, 1, CK(launch_importance_mix(reinterpret_cast<float*>(ws + L.rows), w, s.Lt, s.P, s.B, s.Nt, s.Ns, a, ssum, st)));
@@ -488,6 +507,7 @@ extern "C" int basd_backward_dots(const basd_shape* shape, const basd_inputs* in
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
     const Layout L = make_layout(s);
+    if (s.mode != BASD_MODE_LOSS) return 0;      // PAIR: no mixing weights to differentiate; SELECTOR: d total / d w comes from the caller
     Resolved r;
     if (resolve(s, *in_, ws, L, &r)) return 1;
     PtrTable tt;
@@ -518,14 +538,24 @@ extern "C" int basd_backward_finish(const basd_shape* shape, const basd_inputs* 
     Resolved r;
     if (resolve(s, in, ws, L, &r)) return 1;
     const float Ms = static_cast<float>(s.B) * s.Ns * s.world_size;
-    const float scale = 1.f / (static_cast<float>(s.P) * s.B);
+    // LOSS / PAIR: geo = mean over P points and B samples of the per-sample loss; SELECTOR: "gw" already is d total / d w
+    const float scale = s.mode == BASD_MODE_SELECTOR ? 1.f : 1.f / (static_cast<float>(s.P) * s.B);
     __nv_bfloat16* ghi = reinterpret_cast<__nv_bfloat16*>(ws + L.gam_hi);
     __nv_bfloat16* glo = reinterpret_cast<__nv_bfloat16*>(ws + L.gam_lo);
     float* corr = reinterpret_cast<float*>(ws + L.corr);
-    TIMED(14, 2, CK(launch_selector_bwd(s.Ds, s.Lt, s.P, reinterpret_cast<float*>(ws + L.gw), grad_geo, scale, reinterpret_cast<float*>(ws + L.w),
-                           reinterpret_cast<float*>(ws + L.d2), in.log_temperatures, reinterpret_cast<float*>(ws + L.gamma),
-                           reinterpret_cast<float*>(ws + L.stats), Ms, ghi, glo, corr, grad_log_temperatures, st)));
     const size_t MsL = static_cast<size_t>(s.B) * s.Ns;
+    if (s.mode == BASD_MODE_PAIR) {               // no selector path: Gamma' = 0, the gradient is the direct Procrustes term
+        CK(cudaMemsetAsync(ghi, 0, 2 * static_cast<size_t>(s.P) * s.Ds * s.Ds, st));
+        CK(cudaMemsetAsync(glo, 0, 2 * static_cast<size_t>(s.P) * s.Ds * s.Ds, st));
+        CK(cudaMemsetAsync(corr, 0, 4 * static_cast<size_t>(s.P) * s.Ds, st));
+        CK(cudaMemsetAsync(grad_log_temperatures, 0, 4 * static_cast<size_t>(s.P), st));
+    } else {
+        if (s.mode == BASD_MODE_SELECTOR)         // no Procrustes term: the direct-path gradient is zero
+            CK(cudaMemsetAsync(ws + L.gdir, 0, 4 * static_cast<size_t>(s.P) * MsL * s.Ds, st));
+        TIMED(14, 2, CK(launch_selector_bwd(s.Ds, s.Lt, s.P, reinterpret_cast<float*>(ws + L.gw), grad_geo, scale, reinterpret_cast<float*>(ws + L.w),
+                               reinterpret_cast<float*>(ws + L.d2), in.log_temperatures, reinterpret_cast<float*>(ws + L.gamma),
+                               reinterpret_cast<float*>(ws + L.stats), Ms, ghi, glo, corr, grad_log_temperatures, st)));
+    }
     // (a CLS-stripped student view enters the product as the dense matrix of B (Ns + 1) - 1 rows it is in memory; the
     //  epilogue skips the rows between samples and writes the dense [B][Ns][Ds] gradient)
     const size_t Ms_rows = r.student_gap ? static_cast<size_t>(s.B) * (s.Ns + 1) - 1 : MsL;
@@ -582,6 +612,21 @@ extern "C" int basd_cls_attention_rows(const void* q, const void* k, int dtype, 
     const long long qs[2] = {q_strides[0], q_strides[1]};
     const long long ks[3] = {k_strides[0], k_strides[1], k_strides[2]};
     CK(launch_cls_attention_rows(q, k, dtype == BASD_DTYPE_BF16, B, H, S, dh, qs, ks, scale, out, reinterpret_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------- _align_token_count
+extern "C" int basd_align_tokens(const void* tokens, int dtype, const int64_t* strides, int B, int Nin, int Nout, int D, void* out, void* stream) {
+    if (!tokens || !strides || !out) return fail("null argument");
+    if (B < 1 || Nin < 1 || Nout < 1 || D < 1) return fail("invalid token shape");
+    CK(launch_align_tokens(tokens, dtype == BASD_DTYPE_BF16, strides[0], strides[1], strides[2], B, Nin, Nout, D, out,
+                           reinterpret_cast<cudaStream_t>(stream)));
+    return 0;
+}
+extern "C" int basd_align_tokens_bwd(const void* grad_out, int dtype, int B, int Nin, int Nout, int D, void* grad_in, void* stream) {
+    if (!grad_out || !grad_in) return fail("null argument");
+    if (B < 1 || Nin < 1 || Nout < 1 || D < 1) return fail("invalid token shape");
+    CK(launch_align_tokens_bwd(grad_out, dtype == BASD_DTYPE_BF16, B, Nin, Nout, D, grad_in, reinterpret_cast<cudaStream_t>(stream)));
     return 0;
 }
 

@@ -74,6 +74,11 @@ size_t wgrad_part_floats(int P, int Lt);
 cudaError_t launch_cls_attention_rows(const void* q, const void* k, int is_bf16, int B, int H, int S, int dh,
                                       const long long* q_strides /*[b,h]*/, const long long* k_strides /*[b,h,s]*/, float scale,
                                       float* out /*[B,H,S]*/, cudaStream_t st);
+// standalone combined.py:9-14 (tokens [B,Nin,D] with element strides -> dense [B,Nout,D]) and its adjoint (dense in, dense out)
+cudaError_t launch_align_tokens(const void* src, int is_bf16, long long sb, long long sn, long long sd, int B, int Nin, int Nout, int D,
+                                void* dst, cudaStream_t st);
+cudaError_t launch_align_tokens_bwd(const void* gout, int is_bf16, int B, int Nin, int Nout, int D, void* gin, cudaStream_t st);
+cudaError_t launch_fill_f32(float* p, float v, int n, cudaStream_t st);
 // geo_i[P], *geo = mean; resid_max = max over the problems of dbg[.][3] (polar residual)
 cudaError_t launch_loss_reduce(const float* loss_b, const float* dbg, int P, int B, float* geo_i, float* geo, float* resid_max, cudaStream_t st);
 

@@ -546,4 +546,74 @@ cudaError_t launch_loss_reduce(const float* loss_b, const float* dbg, int P, int
     return cudaGetLastError();
 }
 
+
+// ---------------------------------------------------------------------------------------------- align_token_count (standalone)
+// combined.py:9-14 on its own: out[b][n][:] = (1 - lam) in[b][i0][:] + lam in[b][i1][:] along the flattened token axis
+// (interp_index: 1-D linear, align_corners = False, no anti-aliasing).  Inside the loss this resampling is fused into
+// mix_teacher; these two kernels exist so that the reference's free function has a drop-in with the same gradient.
+// One thread per (b, n, 8-feature octet) when D % 8 == 0 and the rows are 16-byte aligned, else per element.
+template <typename T>
+__global__ void __launch_bounds__(256)
+align_tokens_kernel(const T* __restrict__ src, long long sb, long long sn, long long sd, int B, int Nin, int Nout, int D,
+                    T* __restrict__ dst) {
+    const long long total = static_cast<long long>(B) * Nout * D;
+    for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total; t += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int d = static_cast<int>(t % D);
+        const int n = static_cast<int>((t / D) % Nout);
+        const long long b = t / (static_cast<long long>(D) * Nout);
+        int i0, i1; float lam;
+        interp_index(n, Nin, Nout, i0, i1, lam);
+        const float x0 = static_cast<float>(src[b * sb + i0 * sn + d * sd]), x1 = static_cast<float>(src[b * sb + i1 * sn + d * sd]);
+        dst[t] = static_cast<T>((1.f - lam) * x0 + lam * x1);
+    }
+}
+// adjoint: gin[b][m][:] = sum over the output tokens n that read input token m of their tap weight times gout[b][n][:]
+// (gather form: every input token walks the output tokens in order - no atomics, bitwise repeatable)
+template <typename T>
+__global__ void __launch_bounds__(256)
+align_tokens_bwd_kernel(const T* __restrict__ gout, int B, int Nin, int Nout, int D, T* __restrict__ gin) {
+    const long long total = static_cast<long long>(B) * Nin * D;
+    // output tokens whose taps can touch input token m lie in a window around m * Nout / Nin
+    const float ratio = static_cast<float>(Nout) / static_cast<float>(Nin);
+    for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total; t += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int d = static_cast<int>(t % D);
+        const int m = static_cast<int>((t / D) % Nin);
+        const long long b = t / (static_cast<long long>(D) * Nin);
+        int n_lo = static_cast<int>((m - 1) * ratio) - 2, n_hi = static_cast<int>((m + 2) * ratio) + 2;
+        if (n_lo < 0) n_lo = 0;
+        if (n_hi > Nout - 1) n_hi = Nout - 1;
+        float acc = 0.f;
+        for (int n = n_lo; n <= n_hi; ++n) {
+            int i0, i1; float lam;
+            interp_index(n, Nin, Nout, i0, i1, lam);
+            const float g = static_cast<float>(gout[(b * Nout + n) * D + d]);
+            if (i0 == m) acc = fmaf(1.f - lam, g, acc);
+            if (i1 == m) acc = fmaf(lam, g, acc);           // (i0 == i1 at the clamped end: both taps land on m, weights sum to 1)
+        }
+        gin[t] = static_cast<T>(acc);
+    }
+}
+cudaError_t launch_align_tokens(const void* src, int is_bf16, long long sb, long long sn, long long sd, int B, int Nin, int Nout, int D,
+                                void* dst, cudaStream_t st) {
+    const long long total = static_cast<long long>(B) * Nout * D;
+    const int grid = static_cast<int>(total / 256 + 1 < 148 * 16 ? total / 256 + 1 : 148 * 16);
+    if (is_bf16) align_tokens_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), sb, sn, sd, B, Nin, Nout, D, reinterpret_cast<__nv_bfloat16*>(dst));
+    else align_tokens_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(src), sb, sn, sd, B, Nin, Nout, D, reinterpret_cast<float*>(dst));
+    return cudaGetLastError();
+}
+cudaError_t launch_align_tokens_bwd(const void* gout, int is_bf16, int B, int Nin, int Nout, int D, void* gin, cudaStream_t st) {
+    const long long total = static_cast<long long>(B) * Nin * D;
+    const int grid = static_cast<int>(total / 256 + 1 < 148 * 16 ? total / 256 + 1 : 148 * 16);
+    if (is_bf16) align_tokens_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(gout), B, Nin, Nout, D, reinterpret_cast<__nv_bfloat16*>(gin));
+    else align_tokens_bwd_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(gout), B, Nin, Nout, D, reinterpret_cast<float*>(gin));
+    return cudaGetLastError();
+}
+__global__ void fill_f32_kernel(float* __restrict__ p, float v, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = v;
+}
+cudaError_t launch_fill_f32(float* p, float v, int n, cudaStream_t st) {
+    fill_f32_kernel<<<(n + 255) / 256 < 64 ? (n + 255) / 256 : 64, 256, 0, st>>>(p, v, n);
+    return cudaGetLastError();
+}
+
 }  // namespace basd

@@ -6,7 +6,10 @@ Mirrors, with the same names / argument meaning / state_dict keys:
   * BASDLoss                      /root/reference/src/losses/combined.py:17-85
   * GrassmannianLayerSelector     /root/reference/src/losses/layer_selector.py:40-152
   * marchenko_pastur_rank         /root/reference/src/losses/layer_selector.py:8-20
-  * geometric_relational_loss is not exposed on its own: it is fused with the selector (shared statistics).
+  * geometric_relational_loss     /root/reference/src/losses/relational.py:5-50   (standalone: one pair, selector bypassed)
+  * _align_token_count            /root/reference/src/losses/combined.py:9-14
+Inside BASDLoss.forward the three are ONE fused op (shared statistics, resampling folded into the teacher mix); the
+standalone entry points run the same kernels through basd_shape.mode (include/basd_b200.h).
 
 CE (`base_criterion`) and the two-scalar UW-SO weighting (combined.py:56,78-85) stay stock PyTorch so that any
 criterion and soft or hard targets keep working; everything between them is one custom op, `basd_b200::geo_forward`,
@@ -23,7 +26,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib
-from ._lib import DTYPE_BF16, DTYPE_F32, Inputs, Shape
+from ._lib import DTYPE_BF16, DTYPE_F32, MODE_LOSS, MODE_PAIR, MODE_SELECTOR, Inputs, Shape
 
 
 # --------------------------------------------------------------------------------------------- low-level plumbing
@@ -42,10 +45,13 @@ def _stream_ptr(dev=None) -> int:
 
 def _prepare(students: Sequence[torch.Tensor], teachers: Sequence[torch.Tensor], attns: Sequence[torch.Tensor],
              proj_s: torch.Tensor, proj_t: torch.Tensor, log_temperatures: torch.Tensor, has_cls: bool, world_size: int,
-             polar_steps: int = 0):
-    """Builds the C structs.  Returns (shape, inputs, keepalive) — keepalive holds every tensor whose pointer is used."""
-    if not students or not teachers or len(teachers) != len(attns):
+             polar_steps: int = 0, mode: int = MODE_LOSS):
+    """Builds the C structs.  Returns (shape, inputs, keepalive) — keepalive holds every tensor whose pointer is used.
+    mode (include/basd_b200.h): MODE_PAIR reads no projections / temperatures, MODE_SELECTOR no attention maps."""
+    if not students or not teachers or (mode != MODE_SELECTOR and len(teachers) != len(attns)):
         raise _lib.BasdError("need >= 1 student tensor, >= 1 teacher tensor and one attention map per teacher layer")
+    if mode == MODE_SELECTOR:
+        attns = []
     dev = students[0].device
     if dev.type != "cuda":
         raise _lib.BasdError("the BASD loss path runs on a CUDA device only (no CPU fallback); got tensors on " + str(dev))
@@ -71,7 +77,7 @@ def _prepare(students: Sequence[torch.Tensor], teachers: Sequence[torch.Tensor],
             students = [s.contiguous() for s in students]
         if len({t.stride() for t in teachers}) > 1:
             teachers = [t.contiguous() for t in teachers]
-    att_dt = attns[0].dtype if attns[0].dtype in (torch.float32, torch.bfloat16) else torch.float32
+    att_dt = attns[0].dtype if attns and attns[0].dtype in (torch.float32, torch.bfloat16) else torch.float32
     attns = [a if a.dtype == att_dt else a.to(att_dt) for a in attns]
     if len({a.stride() for a in attns}) > 1:
         attns = [a.contiguous() for a in attns]
@@ -89,34 +95,39 @@ def _prepare(students: Sequence[torch.Tensor], teachers: Sequence[torch.Tensor],
                 raise _lib.BasdError(f"{name} tensor {k} has shape {tuple(t.shape)} / strides {t.stride()}, tensor 0 has {tuple(ts[0].shape)} / {ts[0].stride()}")
     if len(students) > _lib.MAX_POINTS or len(teachers) > _lib.MAX_LAYERS:
         raise _lib.BasdError(f"at most {_lib.MAX_POINTS} extraction points and {_lib.MAX_LAYERS} teacher layers")
-    if tuple(proj_s.shape) != (Ds, Ds) or tuple(proj_t.shape) != (Ds, Dt):
-        raise _lib.BasdError(f"proj_s {tuple(proj_s.shape)} / proj_t {tuple(proj_t.shape)} do not match student width {Ds} and teacher width {Dt} "
-                             "(was the module built with the right student_dim / teacher_dim?)")
-    if log_temperatures.numel() != len(students):
-        raise _lib.BasdError(f"{log_temperatures.numel()} log_temperatures for {len(students)} student extraction points")
-    H = attns[0].shape[1]
-    exp_attn = (B, H, Nt + 1, Nt + 1) if has_cls else (B, H, Nt, Nt)
-    cls_rows_only = (B, H, 1, Nt + 1)          # HostStager hands over just the CLS query row (all relational.py:24 reads)
-    if tuple(attns[0].shape) != exp_attn and not (has_cls and tuple(attns[0].shape) == cls_rows_only):
-        raise _lib.BasdError(f"attention shape {tuple(attns[0].shape)} != expected {exp_attn}")
+    if mode != MODE_PAIR:
+        if tuple(proj_s.shape) != (Ds, Ds) or tuple(proj_t.shape) != (Ds, Dt):
+            raise _lib.BasdError(f"proj_s {tuple(proj_s.shape)} / proj_t {tuple(proj_t.shape)} do not match student width {Ds} and teacher width {Dt} "
+                                 "(was the module built with the right student_dim / teacher_dim?)")
+        if log_temperatures.numel() != len(students):
+            raise _lib.BasdError(f"{log_temperatures.numel()} log_temperatures for {len(students)} student extraction points")
+    H = attns[0].shape[1] if attns else 1
+    if attns:
+        exp_attn = (B, H, Nt + 1, Nt + 1) if has_cls else (B, H, Nt, Nt)
+        cls_rows_only = (B, H, 1, Nt + 1)          # HostStager hands over just the CLS query row (all relational.py:24 reads)
+        if tuple(attns[0].shape) != exp_attn and not (has_cls and tuple(attns[0].shape) == cls_rows_only):
+            raise _lib.BasdError(f"attention shape {tuple(attns[0].shape)} != expected {exp_attn}")
     proj_s = proj_s.detach().to(device=dev, dtype=torch.float32).contiguous()
     proj_t = proj_t.detach().to(device=dev, dtype=torch.float32).contiguous()
     logt = log_temperatures.detach().to(device=dev, dtype=torch.float32).contiguous()
     shape = Shape(B=B, Ns=Ns, Nt=Nt, Ds=Ds, Dt=Dt, Lt=len(teachers), P=len(students), H=H, has_cls=int(has_cls),
-                  act_dtype=_dtype_code(students[0]), attn_dtype=_dtype_code(attns[0]), world_size=world_size,
-                  polar_steps=int(polar_steps))
+                  act_dtype=_dtype_code(students[0]), attn_dtype=_dtype_code(attns[0]) if attns else DTYPE_F32, world_size=world_size,
+                  polar_steps=int(polar_steps), mode=int(mode))
     inp = Inputs()
     for i, s in enumerate(students):
         inp.student[i] = s.data_ptr()
-    for j, (t, a) in enumerate(zip(teachers, attns)):
+    for j, t in enumerate(teachers):
         inp.teacher[j] = t.data_ptr()
+    for j, a in enumerate(attns):
         inp.attn[j] = a.data_ptr()
     for k in range(3):
         inp.student_strides[k] = students[0].stride(k)
         inp.teacher_strides[k] = teachers[0].stride(k)
     for k in range(4):
-        inp.attn_strides[k] = attns[0].stride(k)
-    inp.proj_s, inp.proj_t, inp.log_temperatures = proj_s.data_ptr(), proj_t.data_ptr(), logt.data_ptr()
+        inp.attn_strides[k] = attns[0].stride(k) if attns else 0
+    if mode != MODE_PAIR:
+        inp.proj_s, inp.proj_t = proj_s.data_ptr(), proj_t.data_ptr()
+    inp.log_temperatures = logt.data_ptr()
     keep = (students, teachers, attns, proj_s, proj_t, logt)
     return shape, inp, keep
 
@@ -150,13 +161,15 @@ def _allreduce_sum(dist, t: torch.Tensor):
 # --------------------------------------------------------------------------------------------- custom ops
 @torch.library.custom_op("basd_b200::geo_forward", mutates_args=())
 def geo_forward(students: List[torch.Tensor], teachers: List[torch.Tensor], attns: List[torch.Tensor], proj_s: torch.Tensor,
-                proj_t: torch.Tensor, log_temperatures: torch.Tensor, has_cls: bool, polar_steps: int) -> List[torch.Tensor]:
-    """(polar_steps has no default on purpose: torch drops default-valued arguments from the autograd inputs.)
+                proj_t: torch.Tensor, log_temperatures: torch.Tensor, has_cls: bool, polar_steps: int, mode: int) -> List[torch.Tensor]:
+    """(polar_steps / mode have no defaults on purpose: torch drops default-valued arguments from the autograd inputs.)
+    mode: MODE_LOSS (the geometric term of BASDLoss), MODE_PAIR (geometric_relational_loss of one pair), MODE_SELECTOR
+    (mixing weights only; differentiable through output 3).
     Returns [geo_loss (0-dim fp32), workspace (uint8), ranks (int32 [Lt]), mixing weights (fp32 [P, Lt]),
     polar residual (fp32 [1]: largest ||X X^T - I||_F going into the last Newton-Schulz step; <= 0.1 = converged)]."""
     lib = _lib.load()
     dist, world = _world()
-    shape, inp, keep = _prepare(students, teachers, attns, proj_s, proj_t, log_temperatures, has_cls, world, polar_steps)
+    shape, inp, keep = _prepare(students, teachers, attns, proj_s, proj_t, log_temperatures, has_cls, world, polar_steps, mode)
     nbytes = ctypes.c_size_t()
     _lib.check(lib.basd_workspace_bytes(ctypes.byref(shape), ctypes.byref(nbytes)), "basd_workspace_bytes")
     dev = students[0].device
@@ -167,7 +180,7 @@ def geo_forward(students: List[torch.Tensor], teachers: List[torch.Tensor], attn
         geo = torch.empty((), dtype=torch.float32, device=dev)
         st = _stream_ptr(dev)
         _lib.check(lib.basd_forward_stats(ctypes.byref(shape), ctypes.byref(inp), ws.data_ptr(), st), "basd_forward_stats")
-        if dist is not None:
+        if dist is not None and mode != MODE_PAIR:
             _allreduce_sum(dist, workspace_view(shape, ws, "stats"))
         _lib.check(lib.basd_forward_solve(ctypes.byref(shape), ctypes.byref(inp), ws.data_ptr(), geo.data_ptr(), st), "basd_forward_solve")
         ranks = workspace_view(shape, ws, "ranks", torch.int32).clone()
@@ -177,23 +190,23 @@ def geo_forward(students: List[torch.Tensor], teachers: List[torch.Tensor], attn
     return [geo, ws, ranks, w, resid]
 
 
-def _fake_workspace_bytes(students, teachers, attns, has_cls) -> int:
+def _fake_workspace_bytes(students, teachers, attns, has_cls, mode=MODE_LOSS) -> int:
     """Same size as the real op's workspace (basd_workspace_bytes is host-only arithmetic on the shape)."""
     B, Ns, Ds = students[0].shape
     _, Nt, Dt = teachers[0].shape
     code = lambda t: DTYPE_BF16 if t.dtype == torch.bfloat16 else DTYPE_F32
-    shape = Shape(B=B, Ns=Ns, Nt=Nt, Ds=Ds, Dt=Dt, Lt=len(teachers), P=len(students), H=attns[0].shape[1], has_cls=int(has_cls),
-                  act_dtype=code(students[0]), attn_dtype=code(attns[0]), world_size=_world()[1])
+    shape = Shape(B=B, Ns=Ns, Nt=Nt, Ds=Ds, Dt=Dt, Lt=len(teachers), P=len(students), H=attns[0].shape[1] if attns else 1, has_cls=int(has_cls),
+                  act_dtype=code(students[0]), attn_dtype=code(attns[0]) if attns else DTYPE_F32, world_size=_world()[1], mode=int(mode))
     nbytes = ctypes.c_size_t()
     _lib.check(_lib.load().basd_workspace_bytes(ctypes.byref(shape), ctypes.byref(nbytes)), "basd_workspace_bytes")
     return int(nbytes.value)
 
 
 @geo_forward.register_fake
-def _(students, teachers, attns, proj_s, proj_t, log_temperatures, has_cls, polar_steps):
+def _(students, teachers, attns, proj_s, proj_t, log_temperatures, has_cls, polar_steps, mode):
     dev = students[0].device
     return [torch.empty((), dtype=torch.float32, device=dev),
-            torch.empty(_fake_workspace_bytes(students, teachers, attns, has_cls), dtype=torch.uint8, device=dev),
+            torch.empty(_fake_workspace_bytes(students, teachers, attns, has_cls, mode), dtype=torch.uint8, device=dev),
             torch.empty(len(teachers), dtype=torch.int32, device=dev),
             torch.empty(len(students), len(teachers), dtype=torch.float32, device=dev),
             torch.empty(1, dtype=torch.float32, device=dev)]
@@ -202,17 +215,20 @@ def _(students, teachers, attns, proj_s, proj_t, log_temperatures, has_cls, pola
 @torch.library.custom_op("basd_b200::geo_backward", mutates_args=("workspace",))
 def geo_backward(grad_geo: torch.Tensor, workspace: torch.Tensor, students: List[torch.Tensor], teachers: List[torch.Tensor],
                  attns: List[torch.Tensor], proj_s: torch.Tensor, proj_t: torch.Tensor, log_temperatures: torch.Tensor,
-                 has_cls: bool) -> List[torch.Tensor]:
-    """Returns [grad_log_temperatures, grad_student_0, ..., grad_student_{P-1}]."""
+                 has_cls: bool, mode: int, grad_w: torch.Tensor) -> List[torch.Tensor]:
+    """Returns [grad_log_temperatures, grad_student_0, ..., grad_student_{P-1}].  grad_w: d(total)/d(mixing weights) [P, Lt]
+    in MODE_SELECTOR (then grad_geo is the scalar that multiplies it), an empty tensor otherwise."""
     lib = _lib.load()
     dist, world = _world()
-    shape, inp, keep = _prepare(students, teachers, attns, proj_s, proj_t, log_temperatures, has_cls, world)
+    shape, inp, keep = _prepare(students, teachers, attns, proj_s, proj_t, log_temperatures, has_cls, world, 0, mode)
     dev = students[0].device
     with torch.cuda.device(dev):
         st = _stream_ptr(dev)
         g = grad_geo.detach().to(device=dev, dtype=torch.float32).contiguous()
         _lib.check(lib.basd_backward_dots(ctypes.byref(shape), ctypes.byref(inp), workspace.data_ptr(), st), "basd_backward_dots")
-        if dist is not None:
+        if mode == MODE_SELECTOR:
+            workspace_view(shape, workspace, "gw").copy_(grad_w.detach().to(device=dev, dtype=torch.float32).reshape(-1))
+        if dist is not None and mode != MODE_PAIR:
             _allreduce_sum(dist, workspace_view(shape, workspace, "gw"))
         out_dtype = students[0].dtype if students[0].dtype in (torch.float32, torch.bfloat16) else torch.float32
         grads = [torch.empty(s.shape, dtype=out_dtype, device=dev) for s in students]
@@ -228,14 +244,15 @@ def geo_backward(grad_geo: torch.Tensor, workspace: torch.Tensor, students: List
 
 
 @geo_backward.register_fake
-def _(grad_geo, workspace, students, teachers, attns, proj_s, proj_t, log_temperatures, has_cls):
+def _(grad_geo, workspace, students, teachers, attns, proj_s, proj_t, log_temperatures, has_cls, mode, grad_w):
     return [torch.empty_like(log_temperatures, dtype=torch.float32)] + [torch.empty_like(s) for s in students]
 
 
 def _setup_context(ctx, inputs, output):
     students, teachers, attns, proj_s, proj_t, log_temperatures, has_cls = inputs[:7]
-    ctx.n_students, ctx.n_teachers = len(students), len(teachers)
+    ctx.n_students, ctx.n_teachers, ctx.n_attns = len(students), len(teachers), len(attns)
     ctx.has_cls = has_cls
+    ctx.mode = int(inputs[8])
     ctx.student_dtypes = [s.dtype for s in students]
     # only geo_loss carries a gradient; without this autograd materialises zeros_like() for every other output in
     # backward, the multi-GB uint8 workspace included (0.85 ms of fill kernels per step at B=256)
@@ -247,15 +264,19 @@ def _backward(ctx, grads):
     grad_geo = grads[0]
     saved = ctx.saved_tensors
     ws, proj_s, proj_t, logt = saved[:4]
-    P, Lt = ctx.n_students, ctx.n_teachers
+    P, Lt, La = ctx.n_students, ctx.n_teachers, ctx.n_attns
     students = list(saved[4:4 + P])
     teachers = list(saved[4 + P:4 + P + Lt])
-    attns = list(saved[4 + P + Lt:4 + P + 2 * Lt])
-    if grad_geo is None:
+    attns = list(saved[4 + P + Lt:4 + P + Lt + La])
+    grad_w = torch.empty(0, device=ws.device)
+    if ctx.mode == MODE_SELECTOR:              # the gradient arrives through the mixing weights (output 3)
+        grad_w = grads[3] if grads[3] is not None else torch.zeros(P, Lt, device=ws.device)
+        grad_geo = torch.ones((), device=ws.device)
+    elif grad_geo is None:
         grad_geo = torch.zeros((), device=ws.device)
-    out = geo_backward(grad_geo, ws, students, teachers, attns, proj_s, proj_t, logt, ctx.has_cls)
+    out = geo_backward(grad_geo, ws, students, teachers, attns, proj_s, proj_t, logt, ctx.has_cls, ctx.mode, grad_w)
     gs = [g.to(dt) if g.dtype != dt else g for g, dt in zip(out[1:], ctx.student_dtypes)]
-    return gs, [None] * Lt, [None] * Lt, None, None, out[0].to(logt.dtype), None, None
+    return gs, [None] * Lt, [None] * La, None, None, out[0].to(logt.dtype), None, None, None
 
 
 geo_forward.register_autograd(_backward, setup_context=_setup_context)
@@ -411,8 +432,102 @@ def marchenko_pastur_rank(features: torch.Tensor) -> int:
     return int(out.item())
 
 
+# --------------------------------------------------------------------------------------------- standalone pieces of the path
+@torch.library.custom_op("basd_b200::align_tokens", mutates_args=())
+def _align_tokens_op(tokens: torch.Tensor, target_n: int) -> torch.Tensor:
+    lib = _lib.load()
+    if tokens.device.type != "cuda":
+        raise _lib.BasdError("align_token_count: CUDA tensor required (no CPU fallback)")
+    if tokens.dtype not in (torch.float32, torch.bfloat16):
+        tokens = tokens.float()
+    B, n_in, D = tokens.shape
+    with torch.cuda.device(tokens.device):
+        out = torch.empty(B, target_n, D, dtype=tokens.dtype, device=tokens.device)
+        strides = (ctypes.c_int64 * 3)(*tokens.stride())
+        _lib.check(lib.basd_align_tokens(tokens.data_ptr(), _dtype_code(tokens), strides, B, n_in, target_n, D, out.data_ptr(),
+                                         _stream_ptr(tokens.device)), "basd_align_tokens")
+    return out
+
+
+@_align_tokens_op.register_fake
+def _(tokens, target_n):
+    return tokens.new_empty(tokens.shape[0], target_n, tokens.shape[2])
+
+
+@torch.library.custom_op("basd_b200::align_tokens_bwd", mutates_args=())
+def _align_tokens_bwd_op(grad_out: torch.Tensor, n_in: int) -> torch.Tensor:
+    lib = _lib.load()
+    g = grad_out.contiguous()
+    if g.dtype not in (torch.float32, torch.bfloat16):
+        g = g.float()
+    B, n_out, D = g.shape
+    with torch.cuda.device(g.device):
+        gin = torch.empty(B, n_in, D, dtype=g.dtype, device=g.device)
+        _lib.check(lib.basd_align_tokens_bwd(g.data_ptr(), _dtype_code(g), B, n_in, n_out, D, gin.data_ptr(), _stream_ptr(g.device)),
+                   "basd_align_tokens_bwd")
+    return gin
+
+
+@_align_tokens_bwd_op.register_fake
+def _(grad_out, n_in):
+    return grad_out.new_empty(grad_out.shape[0], n_in, grad_out.shape[2])
+
+
+def _align_setup(ctx, inputs, output):
+    ctx.n_in = inputs[0].shape[1]
+    ctx.in_dtype = inputs[0].dtype
+
+
+def _align_backward(ctx, grad_out):
+    return _align_tokens_bwd_op(grad_out, ctx.n_in).to(ctx.in_dtype), None
+
+
+_align_tokens_op.register_autograd(_align_backward, setup_context=_align_setup)
+
+
+def align_token_count(tokens: torch.Tensor, target_n: int) -> torch.Tensor:
+    """combined.py:9-14: the same object when the token counts agree, else 1-D linear resampling along the flattened token
+    axis (align_corners=False), differentiable.  [B, N, D] -> [B, target_n, D]."""
+    if tokens.shape[1] == target_n:
+        return tokens
+    return _align_tokens_op(tokens, int(target_n))
+
+
+_align_token_count = align_token_count      # the reference's (private) name
+
+
+def geometric_relational_loss(student_tokens: torch.Tensor, teacher_tokens: torch.Tensor, teacher_attn: torch.Tensor, *,
+                              has_cls_token: bool, polar_steps: int = 0) -> torch.Tensor:
+    """relational.py:5-50 on its own: attention-weighted Procrustes loss of ONE student / teacher pair (teacher tokens already
+    on the student's token grid, like combined.py:63-67 hands them over), mean over the batch.  Runs the same kernels as the
+    fused loss with the layer selector bypassed (basd_shape.mode = BASD_MODE_PAIR).  The gradient flows to the student tokens;
+    teacher tokens and attention are constants here, as everywhere on this path (teacher.py:123-124,180)."""
+    if student_tokens.device.type != "cuda":
+        raise _lib.BasdError("geometric_relational_loss: CUDA tensors required (no CPU fallback)")
+    B, n_s, _ = student_tokens.shape
+    if teacher_tokens.shape[0] != B or teacher_tokens.shape[1] != n_s:
+        raise _lib.BasdError(f"teacher tokens {tuple(teacher_tokens.shape)} must be aligned to the student's {n_s} tokens "
+                             "(combined.py:63-67: _align_token_count first)")
+    n_a = teacher_attn.shape[-1] - (1 if has_cls_token else 0)
+    if n_a != n_s:
+        # importance on the attention's own token grid, resampled to the student's (relational.py:22-32) and handed on as the
+        # CLS row of a one-head map - the path normalises it (relational.py:34)
+        imp = teacher_attn[:, :, 0, 1:].float().mean(dim=1) if has_cls_token else teacher_attn.float().mean(dim=(1, 2))
+        imp = align_token_count(imp.unsqueeze(-1).contiguous(), n_s).squeeze(-1)
+        if has_cls_token:
+            teacher_attn = torch.cat([imp.new_zeros(B, 1), imp], dim=1).view(B, 1, 1, n_s + 1)
+        else:
+            teacher_attn = imp.view(B, 1, 1, n_s).expand(B, 1, n_s, n_s)
+    dev = student_tokens.device
+    none = torch.empty(0, device=dev)
+    out = geo_forward([student_tokens], [teacher_tokens.detach()], [teacher_attn.detach()], none, none, torch.zeros(1, device=dev),
+                      bool(has_cls_token), int(polar_steps), MODE_PAIR)
+    return out[0]
+
+
 class GrassmannianLayerSelector(nn.Module):
-    """Same constructor, buffers (`proj_s`, `proj_t`) and parameter (`log_temperatures`) as layer_selector.py:40-63."""
+    """Same constructor, buffers (`proj_s`, `proj_t`) and parameter (`log_temperatures`) as layer_selector.py:40-63.
+    Inside BASDLoss the selector runs fused with the Procrustes term; `forward` is the reference's standalone entry point."""
 
     def __init__(self, num_extraction_points: int, student_dim: int, teacher_dim: int):
         super().__init__()
@@ -438,6 +553,33 @@ class GrassmannianLayerSelector(nn.Module):
         if self._ranks_dev is None:
             return {}
         return dict(zip(self._rank_keys, self._ranks_dev.tolist()))
+
+
+    def mixing_weights(self, students: Sequence[torch.Tensor], teachers: Sequence[torch.Tensor], teacher_keys=None) -> torch.Tensor:
+        """softmax(-d_Grassmann^2 / tau) of layer_selector.py:86-108 for every (student extraction point, teacher layer):
+        [P, Lt] fp32, differentiable w.r.t. the student tokens and log_temperatures (closed-form backward, SURVEY.md B.3-B.5;
+        basd_shape.mode = BASD_MODE_SELECTOR).  Updates `subspace_ranks` like layer_selector.py:74."""
+        out = geo_forward(list(students), list(teachers), [], self.proj_s, self.proj_t, self.log_temperatures, True, 0, MODE_SELECTOR)
+        self._ranks_dev = out[2]
+        self._rank_keys = list(teacher_keys) if teacher_keys is not None else list(range(len(teachers)))
+        self.last_mixing_weights = out[3].detach()
+        return out[3]
+
+    def forward(self, student_tokens_per_layer: dict, all_teacher_tokens: dict, all_teacher_attns: dict, extraction_indices: list):
+        """layer_selector.py:116-152: (mixed_teachers, mixed_attentions), both keyed by student layer.  The spectral work (ranks,
+        subspaces, principal angles, weights) runs in the CUDA kernels; the two weighted sums are the reference's own tensor
+        expressions (:110-112) - BASDLoss never materialises the mixed attention maps, this standalone entry point has to."""
+        t_idx = sorted(all_teacher_tokens.keys())
+        teachers = [all_teacher_tokens[j] for j in t_idx]
+        w = self.mixing_weights([student_tokens_per_layer[l] for l in extraction_indices], teachers, t_idx)
+        stacked_tokens = torch.stack(teachers)
+        stacked_attns = torch.stack([all_teacher_attns[j] for j in t_idx])
+        mixed_teachers, mixed_attentions = {}, {}
+        for i, s_layer in enumerate(extraction_indices):
+            wi = w[i].to(stacked_tokens.dtype)
+            mixed_teachers[s_layer] = (wi.view(-1, 1, 1, 1) * stacked_tokens).sum(dim=0)
+            mixed_attentions[s_layer] = (wi.view(-1, 1, 1, 1, 1).to(stacked_attns.dtype) * stacked_attns).sum(dim=0)
+        return mixed_teachers, mixed_attentions
 
 
 class BASDLoss(nn.Module):
@@ -478,7 +620,7 @@ class BASDLoss(nn.Module):
         attns = [all_teacher_attns[j] for j in t_idx]
         self._poll_polar_residual()
         geo, _ws, ranks, w, resid = geo_forward(students, teachers, attns, sel.proj_s, sel.proj_t, sel.log_temperatures,
-                                                bool(self.teacher_has_cls_token), int(self.polar_steps))
+                                                bool(self.teacher_has_cls_token), int(self.polar_steps), MODE_LOSS)
         sel._ranks_dev, sel._rank_keys = ranks, t_idx
         sel.last_mixing_weights = w
         resid = resid.detach()
