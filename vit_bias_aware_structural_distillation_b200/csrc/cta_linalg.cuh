@@ -175,6 +175,42 @@ __device__ inline void cta_cholesky_lower(float* __restrict__ A, int ld, int n, 
     __syncthreads();
 }
 
+// In-place inverse of a lower-triangular matrix held column-major in shared memory: A[c * ld + r] = L(r, c) on entry,
+// = L^-1(r, c) on exit (the strict upper triangle must be zero and stays zero).  Row by row: row i of X = L^-1 is
+//   X(i, j) = -( sum_{k = j}^{i-1} L(i, k) X(k, j) ) / L(i, i)   for j < i,      X(i, i) = 1 / L(i, i),
+// it needs row i of L (not overwritten yet) and rows < i of X (already in place), so X can take L's storage.  Two adjacent
+// lanes per column j split the sum over k (even / odd distance from i - 1); the k loop is uniform over the CTA, so L(i, k) is
+// a broadcast read.  One barrier per row (all reads of row i of L before any write to it).  Needs 2 n <= blockDim.x.
+// The one-thread-per-column forward substitution into GLOBAL memory this replaces (cta_lower_inverse below) took 0.3 ms per
+// 196 x 196 problem - 3.5 of the 4 ms vt_prep_teacher spent on the 1024 problems of BASELINE.json configs[3].
+__device__ inline void cta_lower_inverse_inplace(float* __restrict__ A, int ld, int n) {
+    const int j = static_cast<int>(threadIdx.x) >> 1, half = static_cast<int>(threadIdx.x) & 1;
+    const float* xcol = A + static_cast<size_t>(j < n ? j : 0) * ld;      // X(., j): this thread pair's column
+    for (int i = 0; i < n; ++i) {
+        const float inv_lii = 1.f / A[i * ld + i];
+        float s0 = 0.f, s1 = 0.f;
+        if (j < i) {
+            int k = i - 1 - half;
+            for (; k - 2 >= j; k -= 4) {                                  // two independent chains per thread
+                s0 = fmaf(A[k * ld + i], xcol[k], s0);
+                s1 = fmaf(A[(k - 2) * ld + i], xcol[k - 2], s1);
+            }
+            if (k >= j) s0 = fmaf(A[k * ld + i], xcol[k], s0);
+        }
+        float s = s0 + s1;
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        __syncthreads();                                                  // every thread has read row i of L
+        if (half == 0) {
+            if (j < i) A[j * ld + i] = -s * inv_lii;
+            else if (j == i) A[j * ld + i] = inv_lii;
+        }
+        // (no second barrier: the next row reads row i + 1 of L, untouched so far, and this pair's own column of X - but the
+        //  partner lane's write must be visible: same warp, ordered by the shuffle + barrier of the next iteration)
+        __syncwarp();
+    }
+    __syncthreads();
+}
+
 // Inverse of a lower-triangular matrix L (column-major shared, ld) into Linv (column-major, ld_inv; may be
 // global memory).  One thread per column of the inverse (forward substitution), n <= blockDim.x assumed strided.
 __device__ inline void cta_lower_inverse(const float* __restrict__ L, int ld, int n, float* __restrict__ Linv, int ld_inv) {

@@ -619,14 +619,13 @@ vt_prep_teacher_kernel(PolarArgs g) {
         ftf[u * M + u] += d0;
         if (u + 1 < M) { ftf[u * M + u + 1] += d1; ftf[(u + 1) * M + u] += d1; }
     }
-    // G^-1 (forward substitution, one thread per column, column-major fp32 in global memory), then its two operand forms
-    float* ginv = g.ginv + static_cast<size_t>(prob) * M * M;
-    cta_lower_inverse(K, ld, M, ginv, M);
-    __threadfence_block();
+    // G^-1 in place of G (G is dead from here on; row-by-row substitution in shared memory), then its two operand forms
     __syncthreads();
+    cta_lower_inverse_inplace(K, ld, M);
+    const float* ginv = K;                                // column-major: G^-1(r, c) = ginv[c * ld + r], zero above the diagonal
     for (int r = threadIdx.x; r < M; r += blockDim.x) {
         float sacc = 0.f;
-        for (int c = 0; c <= r; ++c) sacc += ginv[static_cast<size_t>(c) * M + r];
+        for (int c = 0; c <= r; ++c) sacc += ginv[c * ld + r];
         rowm[r] = sacc / static_cast<float>(M);
     }
     __syncthreads();
@@ -643,8 +642,8 @@ vt_prep_teacher_kernel(PolarArgs g) {
             for (int e = 0; e < 8; ++e) {
                 const int c = cb * 64 + j0 + e;
                 // GinvC[r][c] = Ginv(r, c) - rowmean(r);   GinvT[r][c] = Ginv(c, r)
-                vc[e] = c < M ? (c <= r ? ginv[static_cast<size_t>(c) * M + r] : 0.f) - rowm[r] : 0.f;
-                vt[e] = c < M ? (r <= c ? ginv[static_cast<size_t>(r) * M + c] : 0.f) : 0.f;
+                vc[e] = c < M ? (c <= r ? ginv[c * ld + r] : 0.f) - rowm[r] : 0.f;
+                vt[e] = c < M ? (r <= c ? ginv[r * ld + c] : 0.f) : 0.f;
             }
             store_split8(ch, cl, (static_cast<size_t>(cb) * M + r) * 64 + j0, vc);
             store_split8(th, tl, (static_cast<size_t>(cb) * M + r) * 64 + j0, vt);

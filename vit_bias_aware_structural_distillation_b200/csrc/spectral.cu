@@ -350,7 +350,8 @@ jacobi_cluster_global_kernel(float* __restrict__ scratch, int n, int* __restrict
 //   A = V_s[:, :k]^T (P_s^T U_t)   (k x k);  cos = svdvals(A) via Jacobi on A^T A;
 //   d2 = sum sw theta^2 / sum sw;  Gamma_sym = d(d2)/dG_s + transpose   (n x n, saved for backward)
 // ------------------------------------------------------------------------------------------------
-// LARGE = true (n > 224): the k x k Jacobi matrix lives in the spare n x n slot of the scratch area (global memory).
+// LARGE = true (n > 224): the n-sized operands stay in global memory (L2); see j_in_smem for the k x k Jacobi matrix.
+constexpr int kAnglesLargeSmemK = 128;
 template <bool LARGE>
 __global__ void __launch_bounds__(kSpectralThreads, 1)
 angles_kernel(int n, int Lt, int P, const int* __restrict__ ranks, const float* __restrict__ evals,
@@ -361,13 +362,18 @@ angles_kernel(int n, int Lt, int P, const int* __restrict__ ranks, const float* 
     const int j = blockIdx.x, i = blockIdx.y;
     const int k = ranks[j];
     const int ld = jacobi_ld(max(k, 1));
-    float* J = LARGE ? scratch_all + (static_cast<size_t>(blockIdx.y) * Lt + blockIdx.x) * (8 * static_cast<size_t>(n) * n) + 7 * static_cast<size_t>(n) * n
-                     : sm;                                       // k x k Jacobi matrix (ld x k)
-    float* vals = LARGE ? sm : J + static_cast<size_t>(jacobi_ld(n - 1)) * (n - 1);
+    float* vals = LARGE ? sm : sm + static_cast<size_t>(jacobi_ld(n - 1)) * (n - 1);
     float* coef = vals + n;
     float* red = coef + n;                                       // 33 floats
     int* order = reinterpret_cast<int*>(red + 40);
     float* inbox = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(order + n + 8) + 15) & ~uintptr_t(15));   // odd-even Jacobi: one column
+    // k x k Jacobi matrix (ld x k).  n <= 224: any k fits shared memory.  LARGE: the MP rank k is far below n in practice
+    // (16 .. 60 of 384 on the BASELINE shapes): up to kAnglesLargeSmemK it runs in shared memory like the small problems, only
+    // a larger one falls back to the spare n x n slot of the scratch area (global memory, L2 latency on every rotation).
+    const bool j_in_smem = !LARGE || k <= kAnglesLargeSmemK;
+    float* J = !LARGE ? sm
+               : j_in_smem ? inbox + jacobi_ld(n) + 8
+                           : scratch_all + (static_cast<size_t>(blockIdx.y) * Lt + blockIdx.x) * (8 * static_cast<size_t>(n) * n) + 7 * static_cast<size_t>(n) * n;
     __shared__ int s_flags[16];
     __shared__ __align__(8) uint64_t s_bars[2];
 
@@ -416,7 +422,7 @@ angles_kernel(int n, int Lt, int P, const int* __restrict__ ranks, const float* 
     // odd-even ordering with register-resident columns (a "cluster" of this one CTA): half the shared-memory round trips
     // and barriers of the round-robin version per rotation; k x k with k ~ 15-40 is a pure latency chain
     int nsw = 0;
-    if constexpr (LARGE) {
+    if (!j_in_smem) {
         __threadfence_block();
         nsw = run_jacobi_global(J, ld, k);
     } else {
@@ -571,7 +577,10 @@ selector_corr_kernel(int n, int Lt, const float* __restrict__ stats, float M_stu
 
 // ------------------------------------------------------------------------------------------------ launchers
 static size_t pooled_smem(int n, bool large) { return ((large ? 0 : static_cast<size_t>(jacobi_ld(n)) * n) + 3 * n + 64 + jacobi_ld(n) + 8) * sizeof(float); }
-static size_t angles_smem(int n, bool large) { return ((large ? 0 : static_cast<size_t>(jacobi_ld(n - 1)) * (n - 1)) + 3 * n + 128 + n + 16 + jacobi_ld(n)) * sizeof(float); }
+static size_t angles_smem(int n, bool large) {
+    const size_t jmat = large ? static_cast<size_t>(jacobi_ld(kAnglesLargeSmemK)) * kAnglesLargeSmemK + 16 : static_cast<size_t>(jacobi_ld(n - 1)) * (n - 1);
+    return (jmat + 3 * n + 128 + n + 16 + jacobi_ld(n)) * sizeof(float);
+}
 bool spectral_large(int n) { return n > kSpectralSmemMax; }
 size_t pooled_eig_scratch_floats(int n, int problems) { return spectral_large(n) ? static_cast<size_t>(problems) * jacobi_ld(n) * n + problems + 64 : 0; }
 
