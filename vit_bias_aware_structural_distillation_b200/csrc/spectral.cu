@@ -558,20 +558,31 @@ selector_bwd_kernel(int n, int Lt, int P, const float* __restrict__ gw_raw, cons
         gam_lo[static_cast<size_t>(i) * n * n + t] = __float2bfloat16(acc - __bfloat162float(hi));
     }
 }
-// corr[i][c'] = sum_c mu_i[c] Gamma'_i[c][c']  (the centring correction of the student gradient), c ascending: one thread
-// per column, fixed order (the atomicAdd version of this sum was one of the sources of launch-to-launch differences)
+// corr[i][c'] = sum_c mu_i[c] Gamma'_i[c][c']  (the centring correction of the student gradient) in a fixed order: a warp
+// per 32 columns c', lanes along c' (coalesced rows of Gamma'), eight warps of the CTA each taking every eighth row c
+// ascending, combined in warp order (the atomicAdd version of this sum was one of the sources of launch-to-launch
+// differences; one thread per column walking all rows was 58 us of dependent L2 latency at cfg2).
 __global__ void __launch_bounds__(256)
 selector_corr_kernel(int n, int Lt, const float* __restrict__ stats, float M_student, const __nv_bfloat16* __restrict__ gam_hi,
                      const __nv_bfloat16* __restrict__ gam_lo, float* __restrict__ corr) {
+    __shared__ float part[8][32];
     const int i = blockIdx.y;
     const float* csum = stats + static_cast<size_t>(Lt + i) * (n * n + n) + n * n;
     const float invM = 1.f / M_student;
     const __nv_bfloat16* gh = gam_hi + static_cast<size_t>(i) * n * n;
     const __nv_bfloat16* gl = gam_lo + static_cast<size_t>(i) * n * n;
-    for (int c2 = blockIdx.x * blockDim.x + threadIdx.x; c2 < n; c2 += gridDim.x * blockDim.x) {
-        float acc = 0.f;
-        for (int c = 0; c < n; ++c) acc = fmaf(csum[c] * invM, __bfloat162float(gh[c * n + c2]) + __bfloat162float(gl[c * n + c2]), acc);
-        corr[i * n + c2] = acc;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c2 = blockIdx.x * 32 + lane;
+    float acc = 0.f;
+    if (c2 < n)
+        for (int c = warp; c < n; c += 8) acc = fmaf(csum[c] * invM, __bfloat162float(gh[c * n + c2]) + __bfloat162float(gl[c * n + c2]), acc);
+    part[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && c2 < n) {
+        float tot = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < 8; ++wv) tot += part[wv][lane];
+        corr[i * n + c2] = tot;
     }
 }
 
@@ -717,7 +728,7 @@ cudaError_t launch_selector_bwd(int n, int Lt, int P, const float* gw_raw, const
                                                                           gamma, stats, Ms, gam_hi, gam_lo, corr, grad_log_temp);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    selector_corr_kernel<<<dim3((n + 255) / 256, P), 256, 0, st>>>(n, Lt, stats, Ms, gam_hi, gam_lo, corr);
+    selector_corr_kernel<<<dim3((n + 31) / 32, P), 256, 0, st>>>(n, Lt, stats, Ms, gam_hi, gam_lo, corr);
     return cudaGetLastError();
 }
 

@@ -479,13 +479,17 @@ __global__ void wgrad_importance_kernel(const float* __restrict__ gwt, const flo
     const float tot = cta_sum(part, red);
     if (threadIdx.x == 0) gw_part[(static_cast<size_t>(blockIdx.y) * P + i) * Lt + j] = tot;
 }
-// gw[i][j] = sum of the n_part partial tables, in order
-__global__ void wgrad_reduce_kernel(const float* __restrict__ gw_part, int n_part, int PL, float* __restrict__ gw) {
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < PL; t += gridDim.x * blockDim.x) {
-        float s = 0.f;
-        for (int k = 0; k < n_part; ++k) s += gw_part[static_cast<size_t>(k) * PL + t];
-        gw[t] = s;
-    }
+// gw[i][j] = sum of the n_part partial tables in a FIXED order: one warp per entry, lane l sums partials l, l + 32, ...
+// ascending, then the 32 lane sums are combined by the xor-shuffle tree (the same association on every launch).
+// (One thread per entry walking all ~600 partials was 54 us of dependent L2 latency at cfg2.)
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ gw_part, int n_part, int PL, float* __restrict__ gw) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= PL) return;
+    float s = 0.f;
+    for (int k = lane; k < n_part; k += 32) s += gw_part[static_cast<size_t>(k) * PL + warp];
+    s = warp_sum(s);
+    if (lane == 0) gw[warp] = s;
 }
 constexpr int kWgradDotCtas = 148 * 4, kWgradImpSlices = 16;
 size_t wgrad_part_floats(int P, int Lt) { return static_cast<size_t>(kWgradDotCtas + kWgradImpSlices) * P * Lt; }
@@ -508,7 +512,7 @@ cudaError_t launch_wgrad_dots(const PtrTable& teacher, const __nv_bfloat16* Dtm,
     wgrad_importance_kernel<<<dim3(P * Lt, slices), 256, 0, st>>>(gwt, rows, Lt, P, B, Nt, Ns, gw_part + static_cast<size_t>(kWgradDotCtas) * P * Lt);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    wgrad_reduce_kernel<<<(P * Lt + 255) / 256, 256, 0, st>>>(gw_part, kWgradDotCtas + slices, P * Lt, gw);
+    wgrad_reduce_kernel<<<(P * Lt * 32 + 255) / 256, 256, 0, st>>>(gw_part, kWgradDotCtas + slices, P * Lt, gw);
     return cudaGetLastError();
 }
 
