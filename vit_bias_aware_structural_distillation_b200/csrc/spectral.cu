@@ -352,6 +352,7 @@ jacobi_cluster_global_kernel(float* __restrict__ scratch, int n, int* __restrict
 // ------------------------------------------------------------------------------------------------
 // LARGE = true (n > 224): the n-sized operands stay in global memory (L2); see j_in_smem for the k x k Jacobi matrix.
 constexpr int kAnglesLargeSmemK = 128;
+constexpr int kAnglesLargeStageFloats = 30 * 1024;     // extra staging room behind the k x k matrix (LARGE): 64 KB + 120 KB = k <= 61 at n = 384
 template <bool LARGE>
 __global__ void __launch_bounds__(kSpectralThreads, 1)
 angles_kernel(int n, int Lt, int P, const int* __restrict__ ranks, const float* __restrict__ evals,
@@ -489,7 +490,25 @@ angles_kernel(int n, int Lt, int P, const int* __restrict__ ranks, const float* 
     //     Gamma_sym[c][c'] = sum_a H[c][a] Vs[a][c'] + Vs[a][c] H[c'][a]   (one product of inner size 2k; symmetric, so the
     //     store may run along c)
     if ((n & 3) == 0) {
-        cta_gemm_sym2(n, k, T1g, Vs_km, n, [&](int c, int c2, float v) { gam[c2 * n + c] = v; });
+        // H and the first k eigenvectors (k x n each) are staged in the shared memory the Jacobi matrix no longer needs: read
+        // straight from the L2-resident scratch, this product's four 128-bit loads per 32 FMAs were pure latency (134 k of the
+        // 430 k cycles of a k = 15 CTA at n = 192)
+        const size_t stage_floats = LARGE ? static_cast<size_t>(jacobi_ld(kAnglesLargeSmemK)) * kAnglesLargeSmemK + kAnglesLargeStageFloats
+                                          : static_cast<size_t>(jacobi_ld(n - 1)) * (n - 1);
+        float* stage = LARGE ? inbox + jacobi_ld(n) + 8 : sm;
+        if (2 * static_cast<size_t>(k) * n <= stage_floats) {
+            float* sH = stage;
+            float* sV = stage + static_cast<size_t>(k) * n;
+            __syncthreads();                                  // (the Jacobi matrix and Q products are done with this memory)
+            for (int t = threadIdx.x * 4; t < k * n; t += blockDim.x * 4) {
+                *reinterpret_cast<float4*>(sH + t) = *reinterpret_cast<const float4*>(T1g + t);
+                *reinterpret_cast<float4*>(sV + t) = *reinterpret_cast<const float4*>(Vs_km + t);
+            }
+            __syncthreads();
+            cta_gemm_sym2(n, k, sH, sV, n, [&](int c, int c2, float v) { gam[c2 * n + c] = v; });
+        } else {
+            cta_gemm_sym2(n, k, T1g, Vs_km, n, [&](int c, int c2, float v) { gam[c2 * n + c] = v; });
+        }
     } else {
         cta_gemm(n, n, 2 * k,
                  [&](int c, int a) { return a < k ? T1g[a * n + c] : Vs_km[(a - k) * n + c]; },
@@ -589,7 +608,8 @@ selector_corr_kernel(int n, int Lt, const float* __restrict__ stats, float M_stu
 // ------------------------------------------------------------------------------------------------ launchers
 static size_t pooled_smem(int n, bool large) { return ((large ? 0 : static_cast<size_t>(jacobi_ld(n)) * n) + 3 * n + 64 + jacobi_ld(n) + 8) * sizeof(float); }
 static size_t angles_smem(int n, bool large) {
-    const size_t jmat = large ? static_cast<size_t>(jacobi_ld(kAnglesLargeSmemK)) * kAnglesLargeSmemK + 16 : static_cast<size_t>(jacobi_ld(n - 1)) * (n - 1);
+    const size_t jmat = large ? static_cast<size_t>(jacobi_ld(kAnglesLargeSmemK)) * kAnglesLargeSmemK + kAnglesLargeStageFloats + 16
+                              : static_cast<size_t>(jacobi_ld(n - 1)) * (n - 1);
     return (jmat + 3 * n + 128 + n + 16 + jacobi_ld(n)) * sizeof(float);
 }
 bool spectral_large(int n) { return n > kSpectralSmemMax; }
