@@ -11,7 +11,7 @@ DTYPE_F32, DTYPE_BF16 = 0, 1
 MODE_LOSS, MODE_PAIR, MODE_SELECTOR = 0, 1, 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbasd_b200.so")
+LIB_PATH = os.environ.get("BASD_B200_LIB") or os.path.join(_HERE, "libbasd_b200.so")      # (override: A/B runs of two builds)
 
 
 class Shape(ctypes.Structure):

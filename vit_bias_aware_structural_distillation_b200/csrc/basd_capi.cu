@@ -218,8 +218,8 @@ int check_shape(const basd_shape& s) {
     if (s.P > BASD_MAX_POINTS || s.Lt > BASD_MAX_LAYERS) return fail("P <= %d and Lt <= %d required", BASD_MAX_POINTS, BASD_MAX_LAYERS);
     if (s.Ds % 8 || s.Dt % 8) return fail("Ds and Dt must be multiples of 8 (16-byte rows), got %d, %d", s.Ds, s.Dt);
     if (s.Ds > 1024) return fail("Ds=%d > 1024 is not supported", s.Ds);
-    if (s.polar_steps != 0 && (s.polar_steps < kPolarStepsDefault || s.polar_steps > kPolarStepsMax))
-        return fail("polar_steps must be 0 (default %d) or %d..%d, got %d", kPolarStepsDefault, kPolarStepsDefault, kPolarStepsMax, s.polar_steps);
+    if (s.polar_steps != 0 && (s.polar_steps < kPolarStepsMin || s.polar_steps > kPolarStepsMax))
+        return fail("polar_steps must be 0 (default %d) or %d..%d, got %d", kPolarStepsDefault, kPolarStepsMin, kPolarStepsMax, s.polar_steps);
     if (polar_path(s) == kPathTeacherTokens) {
         // rank(C) = min(Ns, Nt) - 1 < Ds: the polar iteration runs in token space, on the coarser of the two token grids
         const int nk = s.Nt < s.Ns ? s.Nt : s.Ns;

@@ -766,7 +766,7 @@ cudaError_t launch_polar_procrustes(const PolarArgs& g, cudaStream_t st, int* la
     const int n_chunks = (nprob + chunk - 1) / chunk;
     const bool fused = polar_use_fused(D, N);
     auto at = [](const SplitMat& m, int z0) { SplitMat r = m; r.hi += z0 * m.batch_stride; r.lo += z0 * m.batch_stride; return r; };
-    const int steps = g.steps >= kPolarSteps && g.steps <= kPolarStepsMax ? g.steps : kPolarSteps;
+    const int steps = g.steps >= kPolarStepsMin && g.steps <= kPolarStepsMax ? g.steps : kPolarSteps;
     PCK(cudaMemsetAsync(g.resid, 0, sizeof(float) * nprob * g.fro_slots, st));
     TimingScope* gemm_scope = new TimingScope(kSlotPolarGemm, st, n_chunks * ((fused ? 3 : 4) * steps + 2));
     struct Del { TimingScope*& p; ~Del() { delete p; } } gemm_del{gemm_scope};
@@ -882,7 +882,7 @@ cudaError_t launch_polar_procrustes_vt(const PolarArgs& g, cudaStream_t st, int*
         PCK(cudaGetLastError());
         count += 2;
     }
-    const int steps = g.steps >= kPolarSteps && g.steps <= kPolarStepsMax ? g.steps : kPolarSteps;
+    const int steps = g.steps >= kPolarStepsMin && g.steps <= kPolarStepsMax ? g.steps : kPolarSteps;
     PCK(cudaMemsetAsync(g.fro2, 0, sizeof(float) * nprob * g.fro_slots, st));
     PCK(cudaMemsetAsync(g.resid, 0, sizeof(float) * nprob * g.fro_slots, st));
     TimingScope* gemm_scope = new TimingScope(kSlotPolarGemm, st, 3 * steps + 7);

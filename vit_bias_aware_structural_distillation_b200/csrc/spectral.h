@@ -189,7 +189,7 @@ cudaError_t launch_polar_procrustes(const PolarArgs& args, cudaStream_t st, int*
 cudaError_t launch_polar_procrustes_vt(const PolarArgs& args, cudaStream_t st, int* launches);
 constexpr int kVtMaxTokens = 224;         // teacher tokens of the token-space form (Cholesky factor held in shared memory)
 int polar_fro_slots(int core);            // partial-trace slots per problem for a core (D_s or N_t) of this size
-constexpr int kPolarStepsDefault = 10, kPolarStepsMax = 16;
+constexpr int kPolarStepsDefault = 10, kPolarStepsMin = 7, kPolarStepsMax = 16;   // (fewer than the default: caller override only, rows of the schedule skipped from the front)
 int polar_steps();                        // default number of Newton-Schulz steps (the final iterate lives in W2 when odd, W when even)
 
 }  // namespace basd
