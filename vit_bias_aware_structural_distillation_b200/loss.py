@@ -618,6 +618,13 @@ class BASDLoss(nn.Module):
             raise _lib.BasdError(f"student tensors carry {students[0].shape[1]} tokens, module was built for {self.num_student_tokens}")
         teachers = [all_teacher_tokens[j] for j in t_idx]
         attns = [all_teacher_attns[j] for j in t_idx]
+        # Student-feature form of the polar iteration (D_s <= min(N_s, N_t) - 1) with a teacher token Gram that is rank deficient
+        # BY CONSTRUCTION - a coarser teacher grid up-sampled to the student's (N_t < N_s), or a teacher narrower than the token
+        # count (D_t < N_s - 1): the components of the iterate in the null space of that Gram are invisible to the iteration, grow
+        # with every step and come back through rounding, so MORE steps make the result worse and the
+        # residual stays large whatever the step count.  Such shapes run with the default schedule, never escalate, and say so.
+        ns, nt, ds, dt = students[0].shape[1], teachers[0].shape[1], students[0].shape[2], teachers[0].shape[2]
+        self._kt_deficient = ds <= min(ns, nt) - 1 and (nt < ns or dt < ns - 1)
         self._poll_polar_residual()
         geo, _ws, ranks, w, resid = geo_forward(students, teachers, attns, sel.proj_s, sel.proj_t, sel.log_temperatures,
                                                 bool(self.teacher_has_cls_token), int(self.polar_steps), MODE_LOSS)
@@ -642,6 +649,15 @@ class BASDLoss(nn.Module):
             return
         self._resid_event = None
         val = float(self._resid_host[0])
+        if not val <= self.POLAR_RESIDUAL_OK and getattr(self, "_kt_deficient", False):
+            if not getattr(self, "_kt_warned", False):
+                self._kt_warned = True
+                import warnings
+                warnings.warn(f"BASD Procrustes polar iteration: residual {val:.3g} with a teacher token Gram that is rank deficient by construction "
+                              "(teacher grid coarser than the student's, or teacher width below the token count): the step count is NOT raised "
+                              "(more steps amplify the null-space components); student-gradient accuracy on such shapes is 2e-3 .. 1e-1 "
+                              "(DESIGN.md section 8)", RuntimeWarning)
+            return
         if not val <= self.POLAR_RESIDUAL_OK:                               # (NaN counts as not converged)
             cur = self.polar_steps if self.polar_steps else 10
             if cur < self.POLAR_STEPS_MAX:
