@@ -604,7 +604,7 @@ class BASDLoss(nn.Module):
         # cross-covariance down to 3e-5 ||C||_F converge).  Every forward leaves the largest residual ||X X^T - I||_F it saw
         # going into its last step in `last_polar_residual` (device tensor, no sync).  It is read back asynchronously and
         # looked at by the NEXT forward: above POLAR_RESIDUAL_OK (an ill-conditioned cross-covariance) the step count goes
-        # up by two (to at most 16) with a warning - one step late, never a host sync in the step.
+        # up by one (to at most 16) with a warning - one step late, never a host sync in the step.
         self.polar_steps = 0
         self.last_polar_residual = None
         self._resid_host = None
@@ -661,7 +661,10 @@ class BASDLoss(nn.Module):
         if not val <= self.POLAR_RESIDUAL_OK:                               # (NaN counts as not converged)
             cur = self.polar_steps if self.polar_steps else 10
             if cur < self.POLAR_STEPS_MAX:
-                self.polar_steps = min(cur + 2, self.POLAR_STEPS_MAX)
+                # one step at a time: every step beyond convergence multiplies the rounding noise of the early steps in the weak
+                # singular directions (measured on near-square cross-covariances: student-gradient error 6e-3 at 10 steps, 1.2e-2 at
+                # 11 - where the residual converges - and 1.2e-1 at 14; tools/scratch/near_square.py)
+                self.polar_steps = min(cur + 1, self.POLAR_STEPS_MAX)
                 import warnings
                 warnings.warn(f"BASD Procrustes polar iteration: residual {val:.3g} > {self.POLAR_RESIDUAL_OK} after {cur} Newton-Schulz steps "
                               f"(ill-conditioned teacher-student cross-covariance); using {self.polar_steps} steps from now on", RuntimeWarning)
