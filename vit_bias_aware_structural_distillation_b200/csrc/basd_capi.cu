@@ -356,33 +356,37 @@ extern "C" int basd_forward_stats(const basd_shape* shape, const basd_inputs* in
         CK(gemm_project(layers, s.Lt, Mt_rows, s.Dt, pt_hi, pt_lo, s.Ds, z, zlo, r.teacher_gap ? s.Nt + 1 : 0, s.Nt, st));
     }
     {
-        Scope sc(3, st, 4);
+        // Grams AND column sums in one pass over the operands (the ones-operand MMA of umma_gemm.cuh): Ds % 4 == 0 is implied by Ds % 8
+        Scope* sc = new Scope(3, st, 6);
+        struct ScDel { Scope*& p; ~ScDel() { delete p; } } sc_del{sc};
         float* gram_part = reinterpret_cast<float*>(ws + L.gram_part);
-        CK(gemm_gram_batched(z, zlo, Mt_rows, s.Ds, s.Lt, stats, static_cast<long long>(stat_stride), gram_part, st));
+        const bool fused = gemm_gram_colsum_fused(s.Ds, true);
+        CK(gemm_gram_batched(z, zlo, Mt_rows, s.Ds, s.Lt, stats, static_cast<long long>(stat_stride), gram_part, st, fused));
         const void* pts[kMaxPoints];
         for (int i = 0; i < s.P; ++i) pts[i] = r.student[i];
         CK(gemm_gram_table(pts, s.P, Ms, s.Ds, stats + s.Lt * stat_stride, static_cast<long long>(stat_stride), gram_part,
-                           r.student_gap ? s.Ns : 0, r.student_bs, st));
-    }
-    {
-        const bool one_launch = Mt_rows == Ms && !r.student_gap;
-        Scope sc(4, st, one_launch ? 2 : 4);
-        ColsumJobs jt, js;
-        memset(&jt, 0, sizeof jt); memset(&js, 0, sizeof js);
-        for (int j = 0; j < s.Lt; ++j) {
-            jt.hi[j] = z + static_cast<size_t>(j) * Mt_rows * s.Ds; jt.lo[j] = zlo + static_cast<size_t>(j) * Mt_rows * s.Ds;
-            jt.out[j] = stats + j * stat_stride + static_cast<size_t>(s.Ds) * s.Ds;
-        }
-        for (int i = 0; i < s.P; ++i) {
-            js.hi[i] = r.student[i]; js.lo[i] = nullptr;
-            js.out[i] = stats + (s.Lt + i) * stat_stride + static_cast<size_t>(s.Ds) * s.Ds;
-        }
-        if (one_launch) {                   // same row count, same addressing: one launch covers teacher and student jobs
-            for (int i = 0; i < s.P; ++i) { jt.hi[s.Lt + i] = js.hi[i]; jt.lo[s.Lt + i] = nullptr; jt.out[s.Lt + i] = js.out[i]; }
-            CK(launch_colsum(jt, s.Lt + s.P, Mt_rows, s.Ds, reinterpret_cast<float*>(ws + L.colsum_part), st));
-        } else {
-            CK(launch_colsum(jt, s.Lt, Mt_rows, s.Ds, reinterpret_cast<float*>(ws + L.colsum_part), st));
-            CK(launch_colsum(js, s.P, Ms, s.Ds, reinterpret_cast<float*>(ws + L.colsum_part), st, r.student_gap ? s.Ns : 0, r.student_bs));
+                           r.student_gap ? s.Ns : 0, r.student_bs, st, fused));
+        delete sc; sc = nullptr;
+        if (!fused) {                           // D_s > 192 (two-tile Grams): separate column-sum kernels
+            const bool one_launch = Mt_rows == Ms && !r.student_gap;
+            Scope sc2(4, st, one_launch ? 2 : 4);
+            ColsumJobs jt, js;
+            memset(&jt, 0, sizeof jt); memset(&js, 0, sizeof js);
+            for (int j = 0; j < s.Lt; ++j) {
+                jt.hi[j] = z + static_cast<size_t>(j) * Mt_rows * s.Ds; jt.lo[j] = zlo + static_cast<size_t>(j) * Mt_rows * s.Ds;
+                jt.out[j] = stats + j * stat_stride + static_cast<size_t>(s.Ds) * s.Ds;
+            }
+            for (int i = 0; i < s.P; ++i) {
+                js.hi[i] = r.student[i]; js.lo[i] = nullptr;
+                js.out[i] = stats + (s.Lt + i) * stat_stride + static_cast<size_t>(s.Ds) * s.Ds;
+            }
+            if (one_launch) {                   // same row count, same addressing: one launch covers teacher and student jobs
+                for (int i = 0; i < s.P; ++i) { jt.hi[s.Lt + i] = js.hi[i]; jt.lo[s.Lt + i] = nullptr; jt.out[s.Lt + i] = js.out[i]; }
+                CK(launch_colsum(jt, s.Lt + s.P, Mt_rows, s.Ds, reinterpret_cast<float*>(ws + L.colsum_part), st));
+            } else {
+                CK(launch_colsum(jt, s.Lt, Mt_rows, s.Ds, reinterpret_cast<float*>(ws + L.colsum_part), st));
+                CK(launch_colsum(js, s.P, Ms, s.Ds, reinterpret_cast<float*>(ws + L.colsum_part), st, r.student_gap ? s.Ns : 0, r.student_bs));
+            }
         }
         (void)Mt_dense;
     }

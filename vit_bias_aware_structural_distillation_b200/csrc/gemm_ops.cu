@@ -123,6 +123,10 @@ using CfgGram    = GemmCfg<true,  true,  192, 2, 1, 1, 1, false, 3>;
 using CfgGramA   = GemmCfg<true,  true,  192, 2, 1, 1, 1, true,  3>;      // D_s <= 192 (one output tile): the B tile is the A tile, one load per k-block
 using CfgGram3   = GemmCfg<true,  true,  192, 2, 2, 2, 3, false, 2>;      // split operands: hi*hi + hi*lo + lo*hi
 using CfgGram3A  = GemmCfg<true,  true,  192, 2, 2, 2, 3, true,  3>;      // the same with B aliased onto A (D_s <= 192)
+// ... with the column sums of the operand from the same pass (umma_gemm.cuh: COLSUM)
+using CfgGramAC  = GemmCfg<true,  true,  192, 2, 1, 1, 1, true,  3, true>;
+// (two-tile Grams, D_s > 192, keep the separate column-sum kernel: gemm_gram_colsum_fused())
+using CfgGram3AC = GemmCfg<true,  true,  192, 2, 2, 2, 3, true,  3, true>;
 using CfgTheta   = GemmCfg<false, true,  128, 2, 1, 1, 1, false, 4>;      // self test (single operands)
 using CfgTheta3  = GemmCfg<false, true,  128, 2, 2, 2, 3, false, 1>;      // split Theta x split mixed teacher; one stage (96 KB), 256 TMEM columns: two CTAs per SM
 template <int BN> using CfgTokenGram = GemmCfg<false, false, BN, 2, 2, 2, 3, true, 3>;
@@ -180,8 +184,11 @@ static void gram_splits(size_t M, int* kb_total, int* kb_per_split, int* n_split
 size_t gemm_gram_part_floats(size_t M, int Ds, int batches) {
     int kt, kp, ns;
     gram_splits(M, &kt, &kp, &ns);
-    return static_cast<size_t>(ns) * batches * Ds * Ds;
+    return static_cast<size_t>(ns) * batches * (static_cast<size_t>(Ds) * Ds + Ds);       // Gram slices, then column-sum slices
 }
+// Fused where it was measured to pay: the single-tile (aliased) Grams, D_s <= 192 (cfg2: gram + colsum 0.33 -> 0.27 ms).  Two-tile
+// Grams (D_s = 384) got SLOWER with the extra MMAs in every column tile (cfg4: gram 1.27 -> 1.59 ms against 0.04 saved).
+bool gemm_gram_colsum_fused(int Ds, bool split) { (void)split; return Ds <= CfgGram::kBN; }
 static cudaError_t gram_reduce(const float* part, int n_splits, int Ds, int batches, float* G, long long g_stride, cudaStream_t st) {
     if ((Ds * Ds) % 4 || (g_stride % 4)) return cudaErrorInvalidValue;
     const int elems4 = Ds * Ds / 4;
@@ -190,11 +197,18 @@ static cudaError_t gram_reduce(const float* part, int n_splits, int Ds, int batc
     splitk_reduce_kernel<<<dim3(gx, batches), 256, 0, st>>>(part, n_splits, elems4, G, g_stride);
     return cudaGetLastError();
 }
+// column sums: csum[b][d] = sum over the slices of cpart[(b * n_splits + s) * Ds + d], s ascending, written behind the Gram of batch b
+static cudaError_t csum_reduce(const float* cpart, int n_splits, int Ds, int batches, float* G, long long g_stride, cudaStream_t st) {
+    if (Ds % 4 || (g_stride % 4)) return cudaErrorInvalidValue;
+    splitk_reduce_kernel<<<dim3(1, batches), 256, 0, st>>>(cpart, n_splits, Ds / 4, G + static_cast<size_t>(Ds) * Ds, g_stride);
+    return cudaGetLastError();
+}
 
 // G[batch] = Z[batch]^T Z[batch]; Z = [batches][M][Ds] contiguous (optionally a split hi/lo pair); G batch stride in floats.
 // part: gemm_gram_part_floats(M, Ds, batches) floats of scratch for the split-K slices.
+// with_colsum: the column sums of Z (hi + lo) are written behind each Gram (G[b] + Ds * Ds: the layout of the pooled statistics)
 static cudaError_t gram_impl(const __nv_bfloat16* Z, const __nv_bfloat16* Zlo, size_t M, int Ds, int batches, float* G, long long g_stride,
-                             float* part, cudaStream_t st) {
+                             float* part, cudaStream_t st, bool with_colsum = false) {
     GemmMaps maps;
     memset(&maps, 0, sizeof maps);
     if (make_map(&maps.a[0], Z, Ds, M, batches, Ds, M * Ds, 64)) return cudaErrorInvalidValue;
@@ -208,13 +222,23 @@ static cudaError_t gram_impl(const __nv_bfloat16* Z, const __nv_bfloat16* Zlo, s
     gram_splits(M, &a.kb_total, &a.kb_per_split, &a.n_splits);
     a.a_batched = 1; a.b_batched = 1;
     a.out = part; a.out_batch_stride = static_cast<long long>(Ds) * Ds; a.ld_out = Ds; a.rows_valid = Ds; a.cols_valid = Ds;
+    float* cpart = part + static_cast<size_t>(a.n_splits) * batches * Ds * Ds;
+    a.aux0 = with_colsum ? cpart : nullptr;
     const dim3 grid(cdiv(Ds, CfgGram::kBN), cdiv(Ds, CfgGram::kMT * 128), batches * a.n_splits);
     const bool alias = Ds <= CfgGram::kBN;                    // a single output tile: A tile == B tile
     cudaError_t e;
-    if (Zlo) e = alias ? launch<CfgGram3A, EpiStoreSplitK>(maps, a, grid, st) : launch<CfgGram3, EpiStoreSplitK>(maps, a, grid, st);
-    else e = alias ? launch<CfgGramA, EpiStoreSplitK>(maps, a, grid, st) : launch<CfgGram, EpiStoreSplitK>(maps, a, grid, st);
+    if (with_colsum && !gemm_gram_colsum_fused(Ds, Zlo != nullptr)) return cudaErrorInvalidValue;
+    if (with_colsum) {
+        if (Zlo) e = launch<CfgGram3AC, EpiStoreSplitK>(maps, a, grid, st);
+        else e = launch<CfgGramAC, EpiStoreSplitK>(maps, a, grid, st);
+    } else {
+        if (Zlo) e = alias ? launch<CfgGram3A, EpiStoreSplitK>(maps, a, grid, st) : launch<CfgGram3, EpiStoreSplitK>(maps, a, grid, st);
+        else e = alias ? launch<CfgGramA, EpiStoreSplitK>(maps, a, grid, st) : launch<CfgGram, EpiStoreSplitK>(maps, a, grid, st);
+    }
     if (e != cudaSuccess) return e;
-    return gram_reduce(part, a.n_splits, Ds, batches, G, g_stride, st);
+    e = gram_reduce(part, a.n_splits, Ds, batches, G, g_stride, st);
+    if (e != cudaSuccess || !with_colsum) return e;
+    return csum_reduce(cpart, a.n_splits, Ds, batches, G, g_stride, st);
 }
 cudaError_t gemm_gram(const __nv_bfloat16* Z, const __nv_bfloat16* Zlo, size_t M, int Ds, float* G, float* part, cudaStream_t st) {
     return gram_impl(Z, Zlo, M, Ds, 1, G, 0, part, st);
@@ -224,7 +248,7 @@ cudaError_t gemm_gram(const __nv_bfloat16* Z, const __nv_bfloat16* Zlo, size_t M
 // rows_per_batch > 0: the tensors are [B][rows_per_batch][Ds] with batch stride batch_stride elements (CLS-stripped views):
 // the K dimension walks 64-row blocks per sample (GemmArgs::kb_per_batch), M = B * rows_per_batch
 cudaError_t gemm_gram_table(const void* const* S, int n, size_t M, int Ds, float* G, long long g_stride, float* part, int rows_per_batch,
-                            long long batch_stride, cudaStream_t st) {
+                            long long batch_stride, cudaStream_t st, bool with_colsum) {
     if (n > GEMM_MAX_A_TABLE) return cudaErrorInvalidValue;
     GemmMaps maps;
     memset(&maps, 0, sizeof maps);
@@ -243,14 +267,21 @@ cudaError_t gemm_gram_table(const void* const* S, int n, size_t M, int Ds, float
     }
     a.a_table = 1; a.b_table = 1;
     a.out = part; a.out_batch_stride = static_cast<long long>(Ds) * Ds; a.ld_out = Ds; a.rows_valid = Ds; a.cols_valid = Ds;
+    float* cpart = part + static_cast<size_t>(a.n_splits) * n * Ds * Ds;
+    a.aux0 = with_colsum ? cpart : nullptr;
     const dim3 grid(cdiv(Ds, CfgGram::kBN), cdiv(Ds, CfgGram::kMT * 128), n * a.n_splits);
-    cudaError_t e = Ds <= CfgGram::kBN ? launch<CfgGramA, EpiStoreSplitK>(maps, a, grid, st) : launch<CfgGram, EpiStoreSplitK>(maps, a, grid, st);
+    cudaError_t e;
+    if (with_colsum && !gemm_gram_colsum_fused(Ds, false)) return cudaErrorInvalidValue;
+    if (with_colsum) e = launch<CfgGramAC, EpiStoreSplitK>(maps, a, grid, st);
+    else e = Ds <= CfgGram::kBN ? launch<CfgGramA, EpiStoreSplitK>(maps, a, grid, st) : launch<CfgGram, EpiStoreSplitK>(maps, a, grid, st);
     if (e != cudaSuccess) return e;
-    return gram_reduce(part, a.n_splits, Ds, n, G, g_stride, st);
+    e = gram_reduce(part, a.n_splits, Ds, n, G, g_stride, st);
+    if (e != cudaSuccess || !with_colsum) return e;
+    return csum_reduce(cpart, a.n_splits, Ds, n, G, g_stride, st);
 }
 cudaError_t gemm_gram_batched(const __nv_bfloat16* Z, const __nv_bfloat16* Zlo, size_t M, int Ds, int batches, float* G, long long g_stride,
-                              float* part, cudaStream_t st) {
-    return gram_impl(Z, Zlo, M, Ds, batches, G, g_stride, part, st);
+                              float* part, cudaStream_t st, bool with_colsum) {
+    return gram_impl(Z, Zlo, M, Ds, batches, G, g_stride, part, st, with_colsum);
 }
 
 template <int BN>

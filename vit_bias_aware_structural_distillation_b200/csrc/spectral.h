@@ -93,12 +93,15 @@ cudaError_t gemm_project(const void* const* X, int n_layers, size_t M, int Dt, c
 // G[i] (stride g_stride floats) += S_i^T S_i for n separate exact-bf16 [M][Ds] tensors, one launch
 // Split-K slices go to `part` (gemm_gram_part_floats floats) and are summed in a fixed order: bitwise repeatable Grams.
 size_t gemm_gram_part_floats(size_t M, int Ds, int batches);
+// with_colsum: the column sums of every operand come out of the same pass (an N = 16 ones-operand MMA per k-step) and are written
+// behind its Gram, G[i] + Ds * Ds - the layout of the pooled statistics; g_stride >= Ds * Ds + Ds then.
+bool gemm_gram_colsum_fused(int Ds, bool split);         // false: that shape keeps the separate column-sum kernel
 cudaError_t gemm_gram_table(const void* const* S, int n, size_t M, int Ds, float* G, long long g_stride, float* part, int rows_per_batch,
-                            long long batch_stride, cudaStream_t st);
+                            long long batch_stride, cudaStream_t st, bool with_colsum = false);
 cudaError_t gemm_gram(const __nv_bfloat16* Z, const __nv_bfloat16* Zlo, size_t M, int Ds, float* G /*[Ds][Ds]*/, float* part,
                       cudaStream_t st);
 cudaError_t gemm_gram_batched(const __nv_bfloat16* Z, const __nv_bfloat16* Zlo, size_t M, int Ds, int batches, float* G,
-                              long long g_stride, float* part, cudaStream_t st);
+                              long long g_stride, float* part, cudaStream_t st, bool with_colsum = false);
 cudaError_t gemm_token_gram(const __nv_bfloat16* Thi, const __nv_bfloat16* Tlo, int batches, int Ns, int Dt, float* Ktt,
                             cudaStream_t st);
 cudaError_t gemm_theta_apply(const __nv_bfloat16* theta_hi, const __nv_bfloat16* theta_lo, int NsPad, const __nv_bfloat16* Thi,

@@ -54,16 +54,23 @@ struct GemmArgs {
     int kb_per_batch;
 };
 
-template <bool A_MN, bool B_MN, int BN, int MT, int NA, int NB, int NTERMS, bool B_ALIAS_A, int STAGES>
+// COLSUM (Gram configurations, A MN-major): the column sums of the A operand over the K rows of this CTA's split-K slice come out
+// of the same pass as the Gram - one extra N = 16 MMA per k-step against a constant "ones" tile (row 0 = 1, K-major), i.e.
+// sum_k A[k][m] * 1, into 16 more TMEM columns per row tile.  The separate colsum kernel re-read every Gram operand (540 MB,
+// 0.1 ms at cfg2).
+template <bool A_MN, bool B_MN, int BN, int MT, int NA, int NB, int NTERMS, bool B_ALIAS_A, int STAGES, bool COLSUM = false>
 struct GemmCfg {
-    static constexpr bool kAMN = A_MN, kBMN = B_MN, kAlias = B_ALIAS_A;
+    static constexpr bool kAMN = A_MN, kBMN = B_MN, kAlias = B_ALIAS_A, kColsum = COLSUM;
     static constexpr int kBN = BN, kMT = MT, kNA = NA, kNB = NB, kTerms = NTERMS, kStages = STAGES;
     static constexpr int kABytes = MT * 128 * 128;                    // per A buffer per stage
     static constexpr int kBBytes = B_ALIAS_A ? 0 : BN * 128;          // per B buffer per stage
     static constexpr int kStageBytes = NA * kABytes + NB * kBBytes;
-    static constexpr int kTmemCols = (MT * BN <= 32) ? 32 : (MT * BN <= 64) ? 64 : (MT * BN <= 128) ? 128 : (MT * BN <= 256) ? 256 : 512;
-    static constexpr int kSmemBytes = STAGES * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
-    static_assert(MT * BN <= 512, "accumulators exceed TMEM");
+    static constexpr int kAccCols = MT * BN + (COLSUM ? MT * 16 : 0);
+    static constexpr int kTmemCols = (kAccCols <= 32) ? 32 : (kAccCols <= 64) ? 64 : (kAccCols <= 128) ? 128 : (kAccCols <= 256) ? 256 : 512;
+    static constexpr int kOnesBytes = COLSUM ? 2048 : 0;              // [16 rows][64 k] bf16, 128-byte rows (row 0 is not moved by the swizzle)
+    static constexpr int kSmemBytes = STAGES * kStageBytes + kOnesBytes + 1024 /*align*/ + 256 /*barriers*/;
+    static_assert(kAccCols <= 512, "accumulators exceed TMEM");
+    static_assert(!COLSUM || A_MN, "COLSUM sums an MN-major A operand over its K rows");
     static_assert(BN % 16 == 0 && BN <= 256, "invalid UMMA N");
     static_assert(!B_MN || BN % 64 == 0, "MN-major B needs 64-wide groups");
     static_assert(!B_ALIAS_A || (A_MN == B_MN && BN <= MT * 128), "alias: B = the first BN rows / columns of the A tile, same major");
@@ -79,7 +86,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+    uint8_t* ones_tile = smem + Cfg::kStages * Cfg::kStageBytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kOnesBytes);
     uint64_t* empty_bar = full_bar + Cfg::kStages;
     uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
@@ -109,6 +117,11 @@ umma_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
             for (int i = 0; i < Cfg::kNB; ++i) tma_prefetch_desc(&maps.b[i]);
     }
     if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    if constexpr (Cfg::kColsum) {                            // ones tile: row 0 = 1.0 (64 bf16), rows 1..15 = 0
+        for (int t = threadIdx.x; t < Cfg::kOnesBytes / 4; t += blockDim.x)
+            reinterpret_cast<uint32_t*>(ones_tile)[t] = t < 32 ? 0x3F803F80u : 0u;
+        fence_proxy_async_smem();                            // generic-proxy writes -> visible to the tensor core
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -187,6 +200,17 @@ umma_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
                             umma_bf16(tmem_base + mt * Cfg::kBN, adesc, bdesc, idesc, (it > 0 || t > 0 || ks > 0) ? 1u : 0u);
                         }
                     }
+                    if constexpr (Cfg::kColsum) {            // column sums of every A buffer (hi, lo) of this row tile
+                        constexpr uint32_t idesc_cs = umma_idesc_bf16(128, 16, true, false);
+#pragma unroll
+                        for (int i = 0; i < Cfg::kNA; ++i) {
+                            const uint32_t a_base = st + i * Cfg::kABytes + mt * 16384;
+#pragma unroll
+                            for (int ks = 0; ks < GEMM_BK / 16; ++ks)
+                                umma_bf16(tmem_base + Cfg::kMT * Cfg::kBN + mt * 16, umma_smem_desc(a_base + ks * 2048, 8192, 1024),
+                                          umma_smem_desc(smem_u32(ones_tile) + ks * 32, 16, 1024), idesc_cs, (it > 0 || i > 0 || ks > 0) ? 1u : 0u);
+                        }
+                    }
                 }
                 umma_commit(&empty_bar[s]);                 // frees the smem slot when these MMAs retire
                 if (kb == kb1 - 1) umma_commit(tmem_full_bar);
@@ -208,6 +232,11 @@ umma_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
                     float v[16];
                     tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + mt * Cfg::kBN + c, v);
                     epi(row, b_row0 + c, v);
+                }
+                if constexpr (Cfg::kColsum) {
+                    float v[16];
+                    tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + Cfg::kMT * Cfg::kBN + mt * 16, v);
+                    if (blockIdx.x == 0) epi.colsum(row, v[0]);      // (every column tile computes it; one stores it)
                 }
             }
             tc_fence_before();
@@ -309,10 +338,13 @@ struct EpiStoreF32 {                      // out[batch][row][col] = alpha * acc
 // in a fixed order by splitk_reduce_kernel (gemm_ops.cu), so the result does not depend on the order CTAs finish in
 // (fp32 atomicAdd made the pooled Gram - and every eigenvector downstream - differ from launch to launch).
 struct EpiStoreSplitK {
-    float* out; int ld, rows, cols;
+    float* out; float* csum; int ld, rows, cols;
     __device__ EpiStoreSplitK(const GemmArgs& a, int, int z) {
         out = reinterpret_cast<float*>(a.out) + z * a.out_batch_stride; ld = a.ld_out; rows = a.rows_valid; cols = a.cols_valid;
+        csum = a.aux0 ? reinterpret_cast<float*>(const_cast<void*>(a.aux0)) + static_cast<long long>(z) * a.rows_valid : nullptr;
     }
+    // COLSUM configurations: this slice's column sum of A's column `row` (aux0 = [slices][rows] partials, summed in slice order)
+    __device__ void colsum(int row, float v) const { if (csum && row < rows) csum[row] = v; }
     __device__ void operator()(int row, int col0, const float* v) const {
         if (row >= rows || col0 >= cols) return;
         float* p = out + static_cast<long long>(row) * ld + col0;
