@@ -8,6 +8,8 @@
 
 #include "spectral.h"
 #include "polar_gemm.cuh"
+#include <cstdlib>
+
 #include "polar_fused.cuh"
 #include "umma_gemm.cuh"
 
@@ -128,7 +130,6 @@ using CfgGramAC  = GemmCfg<true,  true,  192, 2, 1, 1, 1, true,  3, true>;
 // (two-tile Grams, D_s > 192, keep the separate column-sum kernel: gemm_gram_colsum_fused())
 using CfgGram3AC = GemmCfg<true,  true,  192, 2, 2, 2, 3, true,  3, true>;
 using CfgTheta   = GemmCfg<false, true,  128, 2, 1, 1, 1, false, 4>;      // self test (single operands)
-using CfgTheta3  = GemmCfg<false, true,  128, 2, 2, 2, 3, false, 1>;      // split Theta x split mixed teacher; one stage (96 KB), 256 TMEM columns: two CTAs per SM
 template <int BN> using CfgTokenGram = GemmCfg<false, false, BN, 2, 2, 2, 3, true, 3>;
 using CfgTokenGramTiled = GemmCfg<false, false, 192, 2, 2, 2, 3, false, 2>;   // N_s > 256: 256 x 192 output tiles, B loaded separately
 using CfgTestTN  = GemmCfg<false, false, 192, 1, 1, 1, 1, false, 4>;
@@ -319,25 +320,67 @@ cudaError_t gemm_token_gram(const __nv_bfloat16* Thi, const __nv_bfloat16* Tlo, 
     return launch<CfgTokenGramTiled, EpiStoreF32>(maps, a, dim3(cdiv(Ns, CfgTokenGramTiled::kBN), cdiv(Ns, CfgTokenGramTiled::kMT * 128), batches), st);
 }
 
-cudaError_t gemm_theta_apply(const __nv_bfloat16* theta, const __nv_bfloat16* theta_lo, int NsPad, const __nv_bfloat16* Thi,
-                             const __nv_bfloat16* Tlo, int batches, int Ns, int Dt, __nv_bfloat16* Dtm, __nv_bfloat16* Dtm_lo, cudaStream_t st) {
-    GemmMaps maps;
+// D[z] = Theta[z] (Ns x Ns, row-major split pair, pitch NsPad) * T[z] (Ns x Dt, row-major split pair): the persistent polar_gemm
+// kernel (operand ring and two TMEM accumulators carried across work items, TMA-store epilogue) on row-major operands.
+// Work item = (sample, 128-row tile, column tile of <= 256).  The one-tile-per-CTA kernel this replaces (CfgTheta3: one 96 KB
+// stage, per-lane 32-byte stores) serialised load, MMA and epilogue: 0.47 ms at cfg2.
+static cudaError_t theta_apply_persistent(const __nv_bfloat16* theta, const __nv_bfloat16* theta_lo, int NsPad, const __nv_bfloat16* Thi,
+                                          const __nv_bfloat16* Tlo, int batches, int Ns, int Dt, __nv_bfloat16* Dtm, __nv_bfloat16* Dtm_lo,
+                                          cudaStream_t st) {
+    PolarGemmArgs a;
+    memset(&a, 0, sizeof a);
+    a.epi = PG_EPI_ROWMAJOR; a.scale_c = 1.f; a.a_rm = 1; a.b_rm = 1;
+    a.out_hi = Dtm; a.out_lo = Dtm_lo; a.ld_out = Dt; a.out_stride = static_cast<long long>(Ns) * Dt;
+    a.m_rows = Ns; a.n_cols = Dt; a.k_total = Ns;
+    a.n_mt = (Ns + 127) / 128;
+    if (Dt <= 256) {
+        a.n_nt = 1; a.bn_mma = (Dt + 15) / 16 * 16;
+    } else {
+        a.n_nt = (Dt + 255) / 256;
+        a.bn_mma = ((Dt + a.n_nt - 1) / a.n_nt + 63) / 64 * 64;
+        a.n_nt = (Dt + a.bn_mma - 1) / a.bn_mma;
+    }
+    a.n_items = batches * a.n_mt * a.n_nt; a.n_batches = batches;
+    a.b_groups = (a.bn_mma + 63) / 64;
+    PolarGemmMaps maps;
     memset(&maps, 0, sizeof maps);
     // inner extent Ns (not NsPad): the pad columns are never read, TMA zero-fills them
-    if (make_map(&maps.a[0], theta, Ns, Ns, batches, NsPad, static_cast<uint64_t>(Ns) * NsPad, 128)) return cudaErrorInvalidValue;
-    if (make_map(&maps.a[1], theta_lo, Ns, Ns, batches, NsPad, static_cast<uint64_t>(Ns) * NsPad, 128)) return cudaErrorInvalidValue;
+    if (make_map(&maps.a[0], theta, Ns, Ns, batches, NsPad, static_cast<uint64_t>(Ns) * NsPad, 64)) return cudaErrorInvalidValue;
+    if (make_map(&maps.a[1], theta_lo, Ns, Ns, batches, NsPad, static_cast<uint64_t>(Ns) * NsPad, 64)) return cudaErrorInvalidValue;
     if (make_map(&maps.b[0], Thi, Dt, Ns, batches, Dt, static_cast<uint64_t>(Ns) * Dt, 64)) return cudaErrorInvalidValue;
     if (make_map(&maps.b[1], Tlo, Dt, Ns, batches, Dt, static_cast<uint64_t>(Ns) * Dt, 64)) return cudaErrorInvalidValue;
-    GemmArgs a;
-    memset(&a, 0, sizeof a);
-    a.kb_total = cdiv(Ns, GEMM_BK);
-    a.a_batched = 1; a.b_batched = 1;
+    if (make_map(&maps.o[0], Dtm, Dt, Ns, batches, Dt, static_cast<uint64_t>(Ns) * Dt, 32)) return cudaErrorInvalidValue;
+    if (Dtm_lo && make_map(&maps.o[1], Dtm_lo, Dt, Ns, batches, Dt, static_cast<uint64_t>(Ns) * Dt, 32)) return cudaErrorInvalidValue;
+    const int stage_bytes = 2 * 16384 + 2 * a.b_groups * 8192;
+    const int kTail = 1024 /*alignment*/ + 1024 /*barriers*/ + 4 * 8192 /*epilogue staging*/;
+    int stages = (232448 - kTail) / stage_bytes;
+    if (stages > 4) stages = 4;
+    if (stages < 1) return cudaErrorInvalidValue;
+    a.stages = stages;
+    const int smem = stages * stage_bytes + kTail;
+    auto kern = polar_gemm_kernel<true, 4>;
+    static bool configured[kMaxDevices] = {};
+    const int dev = current_device();
+    if (!configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    const int sm_count = device_sm_count();
+    kern<<<a.n_items < sm_count ? a.n_items : sm_count, PG_THREADS, smem, st>>>(maps, a);
+    return cudaGetLastError();
+}
+
+cudaError_t gemm_theta_apply(const __nv_bfloat16* theta, const __nv_bfloat16* theta_lo, int NsPad, const __nv_bfloat16* Thi,
+                             const __nv_bfloat16* Tlo, int batches, int Ns, int Dt, __nv_bfloat16* Dtm, __nv_bfloat16* Dtm_lo, cudaStream_t st) {
     // the gradient w.r.t. the mixed teacher leaves as a split pair: rounded to one bf16 it cost 1e-4 .. 6e-4 on the
     // temperature gradients (they are differences of nearly equal per-layer dots of this tensor)
     // (Dtm_lo == nullptr: large tensors, where the rounding averages out, leave as one bf16)
-    a.out = Dtm; a.aux0 = Dtm_lo; a.out_batch_stride = static_cast<long long>(Ns) * Dt; a.ld_out = Dt; a.rows_valid = Ns; a.cols_valid = Dt; a.alpha = 1.f;
-    if (!Dtm_lo) return launch<CfgTheta3, EpiStoreBf16>(maps, a, dim3(cdiv(Dt, CfgTheta3::kBN), cdiv(Ns, CfgTheta3::kMT * 128), batches), st);
-    return launch<CfgTheta3, EpiStoreSplit>(maps, a, dim3(cdiv(Dt, CfgTheta3::kBN), cdiv(Ns, CfgTheta3::kMT * 128), batches), st);
+    if (Dt % 8 || NsPad % 8) {
+        snprintf(g_gemm_err, sizeof g_gemm_err, "theta_apply: Dt = %d and the Theta pitch %d must be multiples of 8", Dt, NsPad);
+        return cudaErrorInvalidValue;
+    }
+    return theta_apply_persistent(theta, theta_lo, NsPad, Thi, Tlo, batches, Ns, Dt, Dtm, Dtm_lo, st);
 }
 
 cudaError_t gemm_student_grad(const __nv_bfloat16* S, size_t M, int Ds, const __nv_bfloat16* Ghi, const __nv_bfloat16* Glo,

@@ -28,6 +28,7 @@ enum PolarEpi : int {
     PG_EPI_SPLIT = 0,       // out = split(scale * acc + aux_scale * aux + diag_add * I); optional trace
     PG_EPI_F32 = 2,         // out_f32 = acc
     PG_EPI_THETA = 3,       // out = split(2 (diag(a) - q acc q^T - a a^T)), ROW-MAJOR [m_rows][ld_out]   (teacher side)
+    PG_EPI_ROWMAJOR = 4,    // out = bf16(scale * acc) or its split pair (out_lo != null), ROW-MAJOR [m_rows][ld_out]
 };
 
 struct PolarGemmMaps {
@@ -64,6 +65,9 @@ struct PolarGemmArgs {
     const __nv_bfloat16* aux_hi; const __nv_bfloat16* aux_lo;
     float* out_f32; long long out_f32_stride; int ld_f32;
     const float* vec_a;              // THETA: importance a [z][m_rows]
+    // operands that are NOT column-block tiled (3-D tensor maps over row-major storage, 64 x 64 boxes):
+    int a_rm;                        // A: row-major [z][m_rows][K]                 (K-major operand)
+    int b_rm;                        // B, MN-major only: row-major [z][K][n_cols]
 };
 
 // 16 fp32 values -> bf16 hi / lo halves of staging row `row` (32 rows x 128 B, SWIZZLE_128B: 16-byte chunk j of row r
@@ -132,10 +136,11 @@ __device__ __forceinline__ int pg_a_rows(const PolarGemmArgs& a, int mt) {
 // KIND specialises the epilogue at compile time (one compact code path per instantiation: with every variant in one
 // body the epilogue was ~3900 SASS instructions of mostly-skipped branches executed by a single warp per scheduler):
 //   0 = SPLIT (scale, diagonal, optional trace of the diagonal)   1 = SPLIT + auxiliary tile   2 = THETA   3 = F32
+//   4 = ROWMAJOR (scale; one bf16 or a split pair, row-major)
 template <bool B_MN, int KIND>
 __global__ void __launch_bounds__(PG_THREADS, 1)
 polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArgs args) {
-    constexpr bool kStaged = KIND != 3, kTheta = KIND == 2, kAux = KIND == 1;
+    constexpr bool kStaged = KIND != 3, kTheta = KIND == 2, kAux = KIND == 1, kRowMajor = KIND == 4;
     extern __shared__ uint8_t pg_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(pg_smem_raw) + 1023) & ~uintptr_t(1023));
     const int kABytes = args.a_alias_b ? 0 : 128 * 128;    // one 128-row A tile per operand buffer (none when aliased)
@@ -189,14 +194,18 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
                     uint8_t* st = smem + s * stage_bytes;
                     for (int i = 0; i < 2 && !args.a_alias_b; ++i) {
                         uint8_t* dst = st + i * kABytes;
-                        for (int g = 0; g < a_rows / 64; ++g)
-                            tma_load_4d(dst + g * 8192, &maps.a[i], &full_bar[s], 0, mt * 128 + g * 64, kb, z);
+                        for (int g = 0; g < a_rows / 64; ++g) {
+                            if (args.a_rm) tma_load_3d(dst + g * 8192, &maps.a[i], &full_bar[s], kb * PG_BK, mt * 128 + g * 64, z);
+                            else tma_load_4d(dst + g * 8192, &maps.a[i], &full_bar[s], 0, mt * 128 + g * 64, kb, z);
+                        }
                     }
                     for (int i = 0; i < 2; ++i) {
                         uint8_t* dst = st + 2 * kABytes + i * b_bytes;
                         if (B_MN) {
-                            for (int g = 0; g < args.b_groups; ++g)
-                                tma_load_4d(dst + g * 8192, &maps.b[i], &full_bar[s], 0, kb * PG_BK, itm.nt * args.b_groups + g, z);
+                            for (int g = 0; g < args.b_groups; ++g) {
+                                if (args.b_rm) tma_load_3d(dst + g * 8192, &maps.b[i], &full_bar[s], (itm.nt * args.b_groups + g) * 64, kb * PG_BK, z);
+                                else tma_load_4d(dst + g * 8192, &maps.b[i], &full_bar[s], 0, kb * PG_BK, itm.nt * args.b_groups + g, z);
+                            }
                         } else {
                             tma_load_4d(dst, &maps.b[i], &full_bar[s], 0, itm.nt * args.bn_mma, kb, z);
                         }
@@ -317,6 +326,7 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
                 }
                 for (int cbk = 0; cbk < n_cb; ++cbk) {
                     if (c0 + cbk * 64 >= ((args.n_cols + 63) & ~63)) break;    // column blocks past the matrix (last tile)
+                    if (kRowMajor && c0 + cbk * 64 >= args.n_cols) break;
                     const uint8_t* aux_hi_s = aux_base + cbk * 8192;
                     const uint8_t* aux_lo_s = aux_hi_s + 4096;
                     // whole 64-column block in one tcgen05.ld (the last block of a 208-wide tile has 16 columns)
@@ -382,6 +392,9 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
                         if constexpr (theta) {                                  // row-major output, columns past n_cols are clipped
                             tma_store_3d(&maps.o[0], stg_hi, c0 + cbk * 64, mt * 128 + q * 32, z);
                             tma_store_3d(&maps.o[1], stg_lo, c0 + cbk * 64, mt * 128 + q * 32, z);
+                        } else if constexpr (kRowMajor) {
+                            tma_store_3d(&maps.o[0], stg_hi, c0 + cbk * 64, mt * 128 + q * 32, z);
+                            if (args.out_lo) tma_store_3d(&maps.o[1], stg_lo, c0 + cbk * 64, mt * 128 + q * 32, z);
                         } else {
                             tma_store_4d(&maps.o[0], stg_hi, 0, mt * 128 + q * 32, cb0 + cbk, z);
                             tma_store_4d(&maps.o[1], stg_lo, 0, mt * 128 + q * 32, cb0 + cbk, z);

@@ -5,7 +5,7 @@
 //   project      Z = X P_t^T                 (replaces layer_selector.py:72,135)      A,B K-major
 //   gram         G += Z_chunk^T Z_chunk      (replaces layer_selector.py:13,36,92)    A,B MN-major, split-K
 //   token_gram   K = T T^T per sample        (relational.py:47 moved to token space)  A,B K-major, B aliases A
-//   theta_apply  D = Theta T per sample      (closed-form backward)    A K-major, B MN-major
+//   (theta_apply D = Theta T per sample runs on the persistent polar_gemm kernel: gemm_ops.cu)
 //   student_grad dS = S Gamma + ...                                    A,B K-major
 // "Split-bf16" terms (hi/lo operand pairs) accumulate into the same TMEM tile to recover fp32-class
 // accuracy from bf16 tensor-core passes.
@@ -252,29 +252,6 @@ umma_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
 // ---------------------------------------------------------------------------------------------------
 // Epilogues.  operator()(row, col0, v[16]) handles 16 consecutive columns of one output row.
 // ---------------------------------------------------------------------------------------------------
-struct EpiStoreBf16 {                     // out[batch][row][col] = bf16(alpha * acc)
-    __nv_bfloat16* out; int ld, rows, cols; float alpha;
-    __device__ EpiStoreBf16(const GemmArgs& a, int batch, int) {
-        out = reinterpret_cast<__nv_bfloat16*>(a.out) + batch * a.out_batch_stride;
-        ld = a.ld_out; rows = a.rows_valid; cols = a.cols_valid; alpha = a.alpha;
-    }
-    __device__ void operator()(int row, int col0, const float* v) const {
-        if (row >= rows || col0 >= cols) return;
-        __nv_bfloat16* p = out + static_cast<long long>(row) * ld + col0;
-        if (col0 + 16 <= cols) {
-            uint4 w0, w1;
-            w0.x = pack_bf16x2(alpha * v[0], alpha * v[1]);   w0.y = pack_bf16x2(alpha * v[2], alpha * v[3]);
-            w0.z = pack_bf16x2(alpha * v[4], alpha * v[5]);   w0.w = pack_bf16x2(alpha * v[6], alpha * v[7]);
-            w1.x = pack_bf16x2(alpha * v[8], alpha * v[9]);   w1.y = pack_bf16x2(alpha * v[10], alpha * v[11]);
-            w1.z = pack_bf16x2(alpha * v[12], alpha * v[13]); w1.w = pack_bf16x2(alpha * v[14], alpha * v[15]);
-            reinterpret_cast<uint4*>(p)[0] = w0;
-            reinterpret_cast<uint4*>(p)[1] = w1;
-        } else {
-            for (int i = 0; i < 16 && col0 + i < cols; ++i) p[i] = __float2bfloat16(alpha * v[i]);
-        }
-    }
-};
-
 struct EpiStoreSplit {                    // out = hi, aux0 = lo:  hi = bf16(acc), lo = bf16(acc - hi)   (fp32-class storage)
     __nv_bfloat16* hi; __nv_bfloat16* lo; int ld, rows, cols, gap_period, gap_valid;
     __device__ EpiStoreSplit(const GemmArgs& a, int batch, int) {
@@ -366,27 +343,6 @@ struct EpiAtomicAddF32 {                  // split-K partial: out[row][col] += a
         if (row >= rows) return;
         float* p = out + static_cast<long long>(row) * ld + col0;
         for (int i = 0; i < 16 && col0 + i < cols; ++i) atomicAdd(p + i, v[i]);
-    }
-};
-
-// theta_apply: out = bf16( 2 * (acc - a[row] * mu_t[col]) )    aux0 = a [batch][rows], aux1 = mu_t [batch][cols]
-struct EpiThetaApply {
-    __nv_bfloat16* out; const float* a; const float* mu; int ld, rows, cols;
-    __device__ EpiThetaApply(const GemmArgs& g, int batch, int) {
-        out = reinterpret_cast<__nv_bfloat16*>(g.out) + batch * g.out_batch_stride;
-        a = reinterpret_cast<const float*>(g.aux0) + static_cast<long long>(batch) * g.rows_valid;
-        mu = reinterpret_cast<const float*>(g.aux1) + static_cast<long long>(batch) * g.cols_valid;
-        ld = g.ld_out; rows = g.rows_valid; cols = g.cols_valid;
-    }
-    __device__ void operator()(int row, int col0, const float* v) const {
-        if (row >= rows || col0 >= cols) return;
-        const float ar = a[row];
-        __nv_bfloat16* p = out + static_cast<long long>(row) * ld + col0;
-        for (int i = 0; i < 16 && col0 + i < cols; i += 2) {
-            const float x0 = 2.f * (v[i] - ar * mu[col0 + i]);
-            const float x1 = 2.f * (v[i + 1] - ar * mu[col0 + i + 1]);
-            *reinterpret_cast<uint32_t*>(p + i) = pack_bf16x2(x0, x1);
-        }
     }
 };
 
