@@ -126,6 +126,12 @@ int basd_copy_cls_rows_h2d(const void* host_attn, int elem_bytes, int B, int H, 
 int basd_align_tokens(const void* tokens, int dtype, const int64_t* strides, int B, int Nin, int Nout, int D, void* out, void* stream);
 int basd_align_tokens_bwd(const void* grad_out, int dtype, int B, int Nin, int Nout, int D, void* grad_in, void* stream);
 
+/* UW-SO weighting of the two loss terms (combined.py:78-85) in one launch: with the DETACHED values d_i (det_ce, det_geo: the
+ * terms themselves, or their means over the ranks of a batch-sharded job) and eps = the dtype's machine epsilon,
+ *     w_i = (1 / max(d_i, eps)) / sum_j (1 / max(d_j, eps)),      out = [w_ce * ce + w_geo * geo, w_ce, w_geo].
+ * All pointers are fp32 device scalars; the weights are what the backward multiplies the incoming gradient by. */
+int basd_uwso_combine(const float* ce, const float* geo, const float* det_ce, const float* det_geo, float eps, float* out3, void* stream);
+
 /* Test hooks (used by tests/ only). */
 int basd_selftest_gemm(int variant, const void* A, const void* B, float* C, int M, int N, int K, void* stream);
 int basd_selftest_eig(const float* G, int n, float* evals, float* evecs, int* sweeps, void* workspace, void* stream);

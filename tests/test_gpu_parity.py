@@ -674,3 +674,27 @@ def test_standalone_entry_points_against_reference_golden(lib, cuda_dev):
         assert rel(S[l].grad.cpu(), gs["grad_student"][l]) < TOL_SGRAD
     gt, rt = sel.log_temperatures.grad.cpu(), gs["grad_log_temperatures"]
     assert ((gt - rt).abs() <= TOL_TGRAD * rt.abs() + 1e-7).all(), f"temperature grads {gt.tolist()} vs {rt.tolist()}"
+
+
+def test_uwso_combine_matches_the_reference_expression(lib, cuda_dev):
+    """combined.py:78-85 as one kernel (basd_uwso_combine): bit-identical total, the reference's gradients, NaN propagation."""
+    from vit_bias_aware_structural_distillation_b200.loss import _UwsoCombine
+    torch.manual_seed(3)
+    cases = [(2.3, 14.08), (6.9, 0.37), (1e-9, 5.0), (0.0, 1.0), (float("nan"), 1.0), (3.0, float("inf"))]
+    for ce_v, geo_v in cases:
+        ce = torch.tensor(ce_v, device=cuda_dev, requires_grad=True)
+        geo = torch.tensor(geo_v, device=cuda_dev, requires_grad=True)
+        out = _UwsoCombine.apply(ce, geo, ce.detach(), geo.detach())
+        out.backward()
+        ce_r = torch.tensor(ce_v, device=cuda_dev, requires_grad=True)
+        geo_r = torch.tensor(geo_v, device=cuda_dev, requires_grad=True)
+        vals = [ce_r, geo_r]
+        eps = torch.finfo(torch.float32).eps
+        inv = torch.stack([1.0 / v.detach().clamp(min=eps) for v in vals])
+        wts = inv / inv.sum()
+        ref = sum(wts[i] * vals[i] for i in range(2))
+        ref.backward()
+        assert torch.equal(out.isnan(), ref.isnan()), (ce_v, geo_v)
+        if not ref.isnan():
+            assert out.item() == ref.item(), (ce_v, geo_v, out.item(), ref.item())
+            assert torch.equal(ce.grad, ce_r.grad) and torch.equal(geo.grad, geo_r.grad), (ce_v, geo_v)

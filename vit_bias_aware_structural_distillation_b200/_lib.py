@@ -39,6 +39,7 @@ EXPORTS = [
     "basd_last_error", "basd_version", "basd_timing_enable", "basd_timing_reset", "basd_launch_count", "basd_timing_slots",
     "basd_timing_name", "basd_timing_read", "basd_polar_steps", "basd_polar_launches_per_step", "basd_cls_attention_rows",
     "basd_copy_cls_rows_h2d", "basd_debug_polar_clocks", "basd_debug_spectral_clocks", "basd_align_tokens", "basd_align_tokens_bwd",
+    "basd_uwso_combine",
 ]
 
 _lib = None
@@ -75,6 +76,7 @@ def load():
     lib.basd_copy_cls_rows_h2d.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int64), vp, vp]
     lib.basd_align_tokens.argtypes = [vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int64), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp]
     lib.basd_align_tokens_bwd.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp]
+    lib.basd_uwso_combine.argtypes = [vp, vp, vp, vp, ctypes.c_float, vp, vp]
     lib.basd_launch_count.restype = ctypes.c_longlong
     lib.basd_timing_name.restype = ctypes.c_char_p
     lib.basd_timing_name.argtypes = [ctypes.c_int]

@@ -634,6 +634,30 @@ extern "C" int basd_align_tokens_bwd(const void* grad_out, int dtype, int B, int
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------- UW-SO weighting (combined.py:78-85)
+__global__ void uwso_combine_kernel(const float* __restrict__ ce, const float* __restrict__ geo, const float* __restrict__ det_ce,
+                                    const float* __restrict__ det_geo, float eps, float* __restrict__ out3) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    // the reference's own operation order: inv_i = 1 / clamp(d_i, min = eps); w = inv / sum(inv); total = w_0 L_0 + w_1 L_1
+    // (clamp keeps a NaN term NaN like torch.clamp does - SURVEY.md C.1: an MP rank of 0 makes the reference's loss NaN; no FMA
+    //  contraction: the total is bit-identical to the reference's separate multiplies and add)
+    const float d0 = *det_ce, d1 = *det_geo;
+    const float i0 = 1.0f / (d0 < eps ? eps : d0), i1 = 1.0f / (d1 < eps ? eps : d1);
+    const float sum = __fadd_rn(i0, i1);
+    const float w0 = i0 / sum, w1 = i1 / sum;
+    out3[0] = __fadd_rn(__fmul_rn(w0, *ce), __fmul_rn(w1, *geo));
+    out3[1] = w0;
+    out3[2] = w1;
+}
+extern "C" int basd_uwso_combine(const float* ce, const float* geo, const float* det_ce, const float* det_geo, float eps, float* out3,
+                                 void* stream) {
+    if (!ce || !geo || !det_ce || !det_geo || !out3) return fail("null argument");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    TIMED(11, 1, (uwso_combine_kernel<<<1, 32, 0, st>>>(ce, geo, det_ce, det_geo, eps, out3)));
+    CK(cudaGetLastError());
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------- host attention rows
 // Of a teacher attention map [B,H,S,S] in HOST memory the loss reads the CLS query row only (relational.py:24).  One pitched
 // DMA per layer (width = one row, pitch = one map) moves exactly those rows to a dense device [B,H,1,S] tensor - no host-side

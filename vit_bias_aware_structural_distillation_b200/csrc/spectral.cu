@@ -23,7 +23,8 @@ __device__ long long g_spectral_clk[32];
 __device__ int g_spectral_dbg_on;                      // written once by the host when BASD_SPECTRAL_DBG is set; otherwise no launch touches g_spectral_clk
 static void spectral_dbg_init() {
     static const bool once = [] {
-        const int on = getenv("BASD_SPECTRAL_DBG") ? 1 : 0;
+        const char* e = getenv("BASD_SPECTRAL_DBG");      // value = 1 + the teacher layer whose angles CTA is recorded
+        const int on = e ? (atoi(e) > 0 ? atoi(e) : 1) : 0;
         if (on) cudaMemcpyToSymbol(g_spectral_dbg_on, &on, sizeof(int));
         return true;
     }();
@@ -392,7 +393,7 @@ angles_kernel(int n, int Lt, int P, const int* __restrict__ ranks, const float* 
     float* Fg = WQg + n * n;                  // [a][e]
     float* T1g = Fg + n * n;                  // H [a][c]
 
-    const bool dbg = blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && g_spectral_dbg_on;
+    const bool dbg = static_cast<int>(blockIdx.x) == g_spectral_dbg_on - 1 && blockIdx.y == 0 && threadIdx.x == 0 && g_spectral_dbg_on;
     if (dbg) g_spectral_clk[31] = k;
     if (k == 0) {                              // reference: 0/0 -> NaN (layer_selector.py:105)
         if (threadIdx.x == 0) d2_out[i * Lt + j] = CUDART_NAN_F;

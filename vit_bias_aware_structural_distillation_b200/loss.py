@@ -582,6 +582,29 @@ class GrassmannianLayerSelector(nn.Module):
         return mixed_teachers, mixed_attentions
 
 
+class _UwsoCombine(torch.autograd.Function):
+    """UW-SO weighting (combined.py:78-85; Kirchdorfer et al. 2024): total = sum_i w_i L_i with w_i = (1/L_i) / sum_j (1/L_j) taken
+    on the detached values - one kernel (basd_uwso_combine) instead of a dozen scalar torch ops; the backward scales the incoming
+    gradient by the saved weights."""
+
+    @staticmethod
+    def forward(ctx, ce, geo, det_ce, det_geo):
+        lib = _lib.load()
+        with torch.cuda.device(ce.device):
+            out = torch.empty(3, dtype=torch.float32, device=ce.device)
+            ce_c, geo_c, dce, dgeo = ce.contiguous(), geo.contiguous(), det_ce.contiguous(), det_geo.contiguous()
+            _lib.check(lib.basd_uwso_combine(ce_c.data_ptr(), geo_c.data_ptr(), dce.data_ptr(), dgeo.data_ptr(),
+                                             float(torch.finfo(torch.float32).eps), out.data_ptr(), _stream_ptr(ce.device)), "basd_uwso_combine")
+        ctx.save_for_backward(out)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (out,) = ctx.saved_tensors
+        gw = g * out[1:]                   # one launch: [g w_ce, g w_geo]
+        return gw[0], gw[1], None, None
+
+
 class BASDLoss(nn.Module):
     """Drop-in for combined.py:17-85 (same constructor and forward signature, `token_layers`, state_dict keys)."""
 
@@ -684,7 +707,9 @@ class BASDLoss(nn.Module):
             pair = torch.stack([d.float() for d in det])
             dist.all_reduce(pair, op=dist.ReduceOp.SUM)
             det = [(pair[i] / world).to(vals[i].dtype) for i in range(2)]
-        eps = torch.finfo(vals[0].dtype).eps
-        inv = torch.stack([1.0 / d.clamp(min=eps) for d in det])            # combined.py:78-85
+        if all(v.dtype == torch.float32 and v.device.type == "cuda" and v.dim() == 0 for v in vals):
+            return _UwsoCombine.apply(vals[0], vals[1], det[0], det[1])      # combined.py:78-85 in one launch (+ one in the backward)
+        eps = torch.finfo(vals[0].dtype).eps                                 # other dtypes / criteria with reduction='none': the reference's expression
+        inv = torch.stack([1.0 / d.clamp(min=eps) for d in det])
         wts = inv / inv.sum()
         return sum(wts[i] * vals[i] for i in range(len(vals)))
