@@ -19,4 +19,4 @@ names = ["Ur", "W", "-", "jacobi", "distances", "Q", "WQ", "F", "H", "Gamma_sym"
 print("ranks", dict(m.layer_selector.subspace_ranks))
 print("pooled_eig: pre", c[0], "jacobi", c[1], "post", c[2], "sweeps", c[3])
 print(f"angles CTA (layer {int(os.environ['BASD_SPECTRAL_DBG']) - 1}, point 0): k =", c[31], " ".join(f"{n}={c[8+i+1]-c[8+i]}" for i, n in enumerate(names)),
-      "total", c[8 + 10] - c[8])
+      "total", c[8 + 10] - c[8], "jacobi sweeps", c[30])

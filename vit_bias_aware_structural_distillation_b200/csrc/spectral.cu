@@ -402,20 +402,29 @@ angles_kernel(int n, int Lt, int P, const int* __restrict__ ranks, const float* 
     }
     if (dbg) g_spectral_clk[8 + 0] = clock64();
     // (a) Ur[b][c] = sum_r Ut[b][r] P_s[r][c]
-    cta_gemm(n, k, n,
-             [&](int c, int r) { return proj_s[r * n + c]; },
-             [&](int r, int b) { return Ut[b * n + r]; },
-             [&](int c, int b, float v) { Ur[b * n + c] = v; });
+    const bool vec_ok = (n & 3) == 0;                  // 128-bit operand loads (cta_gemm_mk); every D_s the library accepts is a multiple of 8
+    if (vec_ok) {
+        cta_gemm_mk(n, k, n, proj_s, n, Ut, n, [&](int c, int b, float v) { Ur[b * n + c] = v; });
+    } else {
+        cta_gemm(n, k, n,
+                 [&](int c, int r) { return proj_s[r * n + c]; },
+                 [&](int r, int b) { return Ut[b * n + r]; },
+                 [&](int c, int b, float v) { Ur[b * n + c] = v; });
+    }
     __syncthreads();
     for (int t = threadIdx.x; t < ld * k; t += blockDim.x) J[t] = 0.f;
     __syncthreads();
     if (dbg) g_spectral_clk[8 + 1] = clock64();
     // (b) W[e][b] = sum_c Vs[e][c] Ur[b][c];   its top k x k block is A = V_s[:, :k]^T (P_s^T U_t)
     //     J = A^T goes straight to shared memory: column a of J = row a of A
-    cta_gemm(n, k, n,
-             [&](int e, int c) { return Vs_cm[c * n + e]; },
-             [&](int c, int b) { return Ur[b * n + c]; },
-             [&](int e, int b, float v) { Wg[b * n + e] = v; if (e < k) J[e * ld + b] = v; });
+    if (vec_ok) {
+        cta_gemm_mk(n, k, n, Vs_cm, n, Ur, n, [&](int e, int b, float v) { Wg[b * n + e] = v; if (e < k) J[e * ld + b] = v; });
+    } else {
+        cta_gemm(n, k, n,
+                 [&](int e, int c) { return Vs_cm[c * n + e]; },
+                 [&](int c, int b) { return Ur[b * n + c]; },
+                 [&](int e, int b, float v) { Wg[b * n + e] = v; if (e < k) J[e * ld + b] = v; });
+    }
     __syncthreads();
     if (dbg) g_spectral_clk[8 + 2] = clock64();
     if (dbg) g_spectral_clk[8 + 3] = clock64();
@@ -430,6 +439,7 @@ angles_kernel(int n, int Lt, int P, const int* __restrict__ ranks, const float* 
     } else {
         if (!run_jacobi_oddeven_cluster(J, ld, k, inbox, s_bars, s_flags, &nsw)) run_jacobi(J, ld, k);
     }
+    if (dbg) g_spectral_clk[30] = nsw;
     column_norms(J, ld, k, k, vals);          // vals = sigma
     __syncthreads();
     rank_descending(vals, k, order);
@@ -457,18 +467,23 @@ angles_kernel(int n, int Lt, int P, const int* __restrict__ ranks, const float* 
     if (threadIdx.x == 0) d2_out[i * Lt + j] = acc / swsum;
     __syncthreads();
     if (dbg) g_spectral_clk[8 + 5] = clock64();
-    // Q[b][b'] = sum_m J[b][m] coef_m J[b'][m]
+    // Q[b][b'] = sum_m J[b][m] coef_m J[b'][m]     (rows kq = k rounded up to 4 apart: 16-byte aligned for the 128-bit loads below)
+    const int kq = (k + 3) & ~3;
     cta_gemm(k, k, k,
              [&](int b, int m) { return J[m * ld + b] * coef[m]; },
              [&](int m, int b2) { return J[m * ld + b2]; },
-             [&](int b, int b2, float v) { Qg[b2 * k + b] = v; });
+             [&](int b, int b2, float v) { Qg[b2 * kq + b] = v; });
     __syncthreads();
     if (dbg) g_spectral_clk[8 + 6] = clock64();
     // (e) WQ[e][b'] = sum_b W[e][b] Q[b][b']
-    cta_gemm(n, k, k,
-             [&](int e, int b) { return Wg[b * n + e]; },
-             [&](int b, int b2) { return Qg[b2 * k + b]; },
-             [&](int e, int b2, float v) { WQg[b2 * n + e] = v; });
+    if (vec_ok) {
+        cta_gemm_mk(n, k, k, Wg, n, Qg, kq, [&](int e, int b2, float v) { WQg[b2 * n + e] = v; });
+    } else {
+        cta_gemm(n, k, k,
+                 [&](int e, int b) { return Wg[b * n + e]; },
+                 [&](int b, int b2) { return Qg[b2 * kq + b]; },
+                 [&](int e, int b2, float v) { WQg[b2 * n + e] = v; });
+    }
     __syncthreads();
     if (dbg) g_spectral_clk[8 + 7] = clock64();
     //     F[e][a] = (sum_b' WQ[e][b'] A[a][b']) / (lam_a - lam_e)   for e >= k, a < k
@@ -476,16 +491,20 @@ angles_kernel(int n, int Lt, int P, const int* __restrict__ ranks, const float* 
     cta_gemm(nc, k, k,
              [&](int e, int b2) { return WQg[b2 * n + k + e]; },
              [&](int b2, int a) { return Wg[b2 * n + a]; },
-             [&](int e, int a, float v) { Fg[a * n + k + e] = v / (lam_s[a] - lam_s[k + e]); });
+             [&](int e, int a, float v) { Fg[a * n + e] = v / (lam_s[a] - lam_s[k + e]); });      // (row a of F from column 0: aligned)
     __syncthreads();
     if (dbg) g_spectral_clk[8 + 8] = clock64();
     // (f) Gamma = V_hi^T F V_lo  (V_hi = eigenvectors e >= k, V_lo = a < k), associated as (V_hi^T F) V_lo: n k (n + nc)
     //     multiply-adds instead of the n n nc of V_hi^T (F V_lo), k << nc.
     //     H[c][a] = sum_{e>=k} Vs[e][c] F[e][a]
-    cta_gemm(n, k, nc,
-             [&](int c, int e) { return Vs_km[(k + e) * n + c]; },
-             [&](int e, int a) { return Fg[a * n + k + e]; },
-             [&](int c, int a, float v) { T1g[a * n + c] = v; });
+    if (vec_ok) {
+        cta_gemm_mk(n, k, nc, Vs_km + static_cast<size_t>(k) * n, n, Fg, n, [&](int c, int a, float v) { T1g[a * n + c] = v; });
+    } else {
+        cta_gemm(n, k, nc,
+                 [&](int c, int e) { return Vs_km[(k + e) * n + c]; },
+                 [&](int e, int a) { return Fg[a * n + e]; },
+                 [&](int c, int a, float v) { T1g[a * n + c] = v; });
+    }
     __syncthreads();
     if (dbg) g_spectral_clk[8 + 9] = clock64();
     //     Gamma_sym[c][c'] = sum_a H[c][a] Vs[a][c'] + Vs[a][c] H[c'][a]   (one product of inner size 2k; symmetric, so the
