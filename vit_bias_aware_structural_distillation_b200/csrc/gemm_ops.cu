@@ -60,6 +60,29 @@ static int make_map(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t 
     return 0;
 }
 
+// fp32 tensor viewed as [batch][rows][inner]; box = [1][32][32] (128-byte rows); SWIZZLE_128B; OOB -> zeros.
+static int make_map_f32(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t rows, uint64_t batch, uint64_t row_pitch_elems,
+                        uint64_t batch_pitch_elems) {
+    if (gemm_init_driver_api()) return 1;
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (row_pitch_elems * 4) % 16 || (batch_pitch_elems * 4) % 16) {
+        snprintf(g_gemm_err, sizeof g_gemm_err, "TMA fp32 operand misaligned: ptr=%p row_pitch=%llu", ptr, (unsigned long long)row_pitch_elems);
+        return 1;
+    }
+    cuuint64_t dims[3] = {inner, rows, batch};
+    cuuint64_t strides[2] = {row_pitch_elems * 4, batch_pitch_elems * 4};
+    cuuint32_t box[3] = {32, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        snprintf(g_gemm_err, sizeof g_gemm_err, "cuTensorMapEncodeTiled (fp32) failed (%d) inner=%llu rows=%llu", (int)r,
+                 (unsigned long long)inner, (unsigned long long)rows);
+        return 1;
+    }
+    return 0;
+}
+
 // bf16 split matrix stored column-block tiled: [batch][col / 64][row][col % 64]; box = [1][1][box_rows][64].
 static int make_map_tiled(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t col_blocks, uint64_t batch, uint64_t batch_pitch_elems,
                           uint32_t box_rows, uint32_t box_inner = 64) {
@@ -383,9 +406,64 @@ cudaError_t gemm_theta_apply(const __nv_bfloat16* theta, const __nv_bfloat16* th
     return theta_apply_persistent(theta, theta_lo, NsPad, Thi, Tlo, batches, Ns, Dt, Dtm, Dtm_lo, st);
 }
 
+// Student gradient on the persistent polar_gemm kernel (dense bf16 students, bf16 gradient): work item = (128-row tile of the
+// [M][Ds] gradient, column tile), A = the raw student tokens (one exact bf16 buffer: two split terms against Gamma' hi / lo), the
+// direct-path gradient and the centring correction enter in the epilogue (SGRAD), the tile leaves through swizzled staging as TMA
+// stores.  The one-tile-per-CTA kernel it replaces ran at 1.2 TB/s (ncu, r2k): single 65 KB stage, per-lane row-strided loads
+// of gdir and stores of the gradient, load -> MMA -> epilogue in sequence.
+static cudaError_t student_grad_persistent(const __nv_bfloat16* S, size_t M, int Ds, const __nv_bfloat16* Ghi, const __nv_bfloat16* Glo,
+                                           const float* gdir, const float* corr, const float* scale_ptr, float scale_host,
+                                           __nv_bfloat16* out, cudaStream_t st) {
+    PolarGemmArgs a;
+    memset(&a, 0, sizeof a);
+    a.epi = PG_EPI_SGRAD; a.scale_c = 1.f; a.a_rm = 1; a.b_rm = 1; a.a_single = 1;
+    a.sg_gdir = gdir; a.sg_corr = corr; a.sg_scale = scale_ptr; a.sg_alpha = scale_host;
+    a.out_hi = out; a.out_lo = nullptr; a.ld_out = Ds; a.out_stride = static_cast<long long>(M) * Ds;
+    a.m_rows = static_cast<int>(M); a.n_cols = Ds; a.k_total = Ds;
+    a.n_mt = static_cast<int>((M + 127) / 128);
+    if (Ds <= 256) {
+        a.n_nt = 1; a.bn_mma = (Ds + 15) / 16 * 16;
+    } else {
+        a.n_nt = (Ds + 255) / 256;
+        a.bn_mma = ((Ds + a.n_nt - 1) / a.n_nt + 63) / 64 * 64;
+        a.n_nt = (Ds + a.bn_mma - 1) / a.bn_mma;
+    }
+    a.n_items = a.n_mt * a.n_nt; a.n_batches = 1;
+    a.b_groups = (a.bn_mma + 63) / 64;
+    PolarGemmMaps maps;
+    memset(&maps, 0, sizeof maps);
+    if (make_map(&maps.a[0], S, Ds, M, 1, Ds, M * Ds, 64)) return cudaErrorInvalidValue;
+    if (make_map(&maps.b[0], Ghi, Ds, Ds, 1, Ds, static_cast<uint64_t>(Ds) * Ds, a.bn_mma)) return cudaErrorInvalidValue;
+    if (make_map(&maps.b[1], Glo, Ds, Ds, 1, Ds, static_cast<uint64_t>(Ds) * Ds, a.bn_mma)) return cudaErrorInvalidValue;
+    if (make_map(&maps.o[0], out, Ds, M, 1, Ds, M * Ds, 32)) return cudaErrorInvalidValue;
+    if (make_map_f32(&maps.o[2], gdir, Ds, M, 1, Ds, M * Ds)) return cudaErrorInvalidValue;
+    const int stage_bytes = 16384 + 2 * a.bn_mma * 128;
+    const int kTail = 1024 /*alignment*/ + 1024 /*barriers*/ + 4 * 8192 /*epilogue staging*/ + 4 * 8192 /*gdir tiles*/;
+    int stages = (232448 - kTail) / stage_bytes;
+    if (stages > 4) stages = 4;
+    if (stages < 1) return cudaErrorInvalidValue;
+    a.stages = stages;
+    const int smem = stages * stage_bytes + kTail;
+    auto kern = polar_gemm_kernel<false, 5>;
+    static bool configured[kMaxDevices] = {};
+    const int dev = current_device();
+    if (!configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    const int sm_count = device_sm_count();
+    kern<<<a.n_items < sm_count ? a.n_items : sm_count, PG_THREADS, smem, st>>>(maps, a);
+    return cudaGetLastError();
+}
+
 cudaError_t gemm_student_grad(const __nv_bfloat16* S, size_t M, int Ds, const __nv_bfloat16* Ghi, const __nv_bfloat16* Glo,
                               const float* gdir, const float* corr, const float* scale_ptr, float scale_host, void* out,
                               int out_is_bf16, int gap_period, int gap_valid, cudaStream_t st) {
+    // dense bf16 students with a bf16 gradient (the training configuration): persistent kernel; CLS-stripped views (gapped rows)
+    // and fp32 gradients keep the one-tile-per-CTA kernel below
+    if (!gap_period && out_is_bf16 && Ds % 8 == 0 && M < (size_t(1) << 31) - 128)
+        return student_grad_persistent(S, M, Ds, Ghi, Glo, gdir, corr, scale_ptr, scale_host, static_cast<__nv_bfloat16*>(out), st);
     GemmMaps maps;
     memset(&maps, 0, sizeof maps);
     if (make_map(&maps.a[0], S, Ds, M, 1, Ds, M * Ds, 128)) return cudaErrorInvalidValue;

@@ -29,6 +29,7 @@ enum PolarEpi : int {
     PG_EPI_F32 = 2,         // out_f32 = acc
     PG_EPI_THETA = 3,       // out = split(2 (diag(a) - q acc q^T - a a^T)), ROW-MAJOR [m_rows][ld_out]   (teacher side)
     PG_EPI_ROWMAJOR = 4,    // out = bf16(scale * acc) or its split pair (out_lo != null), ROW-MAJOR [m_rows][ld_out]
+    PG_EPI_SGRAD = 5,       // out = bf16(alpha * gdir + acc - corr[col]), ROW-MAJOR [m_rows][n_cols]   (student gradient)
 };
 
 struct PolarGemmMaps {
@@ -67,7 +68,10 @@ struct PolarGemmArgs {
     const float* vec_a;              // THETA: importance a [z][m_rows]
     // operands that are NOT column-block tiled (3-D tensor maps over row-major storage, 64 x 64 boxes):
     int a_rm;                        // A: row-major [z][m_rows][K]                 (K-major operand)
-    int b_rm;                        // B, MN-major only: row-major [z][K][n_cols]
+    int b_rm;                        // B: row-major [z][K][n_cols] (MN-major operand) or [z][n_cols][K] (K-major operand)
+    int a_single;                    // A is one exact bf16 buffer (no lo half): terms A * B_hi + A * B_lo
+    // SGRAD: direct-path gradient gdir fp32 [m_rows][n_cols], centring correction corr fp32 [n_cols], alpha = sg_alpha * *sg_scale (if non-null)
+    const float* sg_gdir; const float* sg_corr; const float* sg_scale; float sg_alpha;
 };
 
 // 16 fp32 values -> bf16 hi / lo halves of staging row `row` (32 rows x 128 B, SWIZZLE_128B: 16-byte chunk j of row r
@@ -136,16 +140,17 @@ __device__ __forceinline__ int pg_a_rows(const PolarGemmArgs& a, int mt) {
 // KIND specialises the epilogue at compile time (one compact code path per instantiation: with every variant in one
 // body the epilogue was ~3900 SASS instructions of mostly-skipped branches executed by a single warp per scheduler):
 //   0 = SPLIT (scale, diagonal, optional trace of the diagonal)   1 = SPLIT + auxiliary tile   2 = THETA   3 = F32
-//   4 = ROWMAJOR (scale; one bf16 or a split pair, row-major)
+//   4 = ROWMAJOR (scale; one bf16 or a split pair, row-major)   5 = SGRAD (direct gradient + product - correction, bf16 row-major)
 template <bool B_MN, int KIND>
 __global__ void __launch_bounds__(PG_THREADS, 1)
 polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArgs args) {
-    constexpr bool kStaged = KIND != 3, kTheta = KIND == 2, kAux = KIND == 1, kRowMajor = KIND == 4;
+    constexpr bool kStaged = KIND != 3, kTheta = KIND == 2, kAux = KIND == 1, kSgrad = KIND == 5, kRowMajor = KIND == 4 || kSgrad;
     extern __shared__ uint8_t pg_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(pg_smem_raw) + 1023) & ~uintptr_t(1023));
     const int kABytes = args.a_alias_b ? 0 : 128 * 128;    // one 128-row A tile per operand buffer (none when aliased)
     const int b_bytes = B_MN ? args.b_groups * 8192 : args.bn_mma * 128;
-    const int stage_bytes = 2 * kABytes + 2 * b_bytes;
+    const int a_bufs = args.a_single ? 1 : 2;
+    const int stage_bytes = a_bufs * kABytes + 2 * b_bytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + args.stages * stage_bytes);
     uint64_t* empty_bar = full_bar + args.stages;
     uint64_t* tmem_full_bar = empty_bar + args.stages;         // [2]
@@ -183,7 +188,7 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
                 const PgItem itm = pg_item(args, w);
                 const int mt = itm.mt, z = itm.z;
                 const int a_rows = pg_a_rows(args, mt);
-                const uint32_t tx = (args.a_alias_b ? 0 : 2 * a_rows * 128) + 2 * b_bytes;
+                const uint32_t tx = (args.a_alias_b ? 0 : a_bufs * a_rows * 128) + 2 * b_bytes;
                 const int item_p = (w - blockIdx.x) / gridDim.x;
                 if (args.dbg_clock && blockIdx.x == 0 && item_p < 16) args.dbg_clock[item_p * 8 + 0] = clock64();
                 for (int kb = 0; kb < n_kb; ++kb, ++it) {
@@ -192,7 +197,7 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     mbar_arrive_expect_tx(&full_bar[s], tx);
                     uint8_t* st = smem + s * stage_bytes;
-                    for (int i = 0; i < 2 && !args.a_alias_b; ++i) {
+                    for (int i = 0; i < a_bufs && !args.a_alias_b; ++i) {
                         uint8_t* dst = st + i * kABytes;
                         for (int g = 0; g < a_rows / 64; ++g) {
                             if (args.a_rm) tma_load_3d(dst + g * 8192, &maps.a[i], &full_bar[s], kb * PG_BK, mt * 128 + g * 64, z);
@@ -200,12 +205,14 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
                         }
                     }
                     for (int i = 0; i < 2; ++i) {
-                        uint8_t* dst = st + 2 * kABytes + i * b_bytes;
+                        uint8_t* dst = st + a_bufs * kABytes + i * b_bytes;
                         if (B_MN) {
                             for (int g = 0; g < args.b_groups; ++g) {
                                 if (args.b_rm) tma_load_3d(dst + g * 8192, &maps.b[i], &full_bar[s], (itm.nt * args.b_groups + g) * 64, kb * PG_BK, z);
                                 else tma_load_4d(dst + g * 8192, &maps.b[i], &full_bar[s], 0, kb * PG_BK, itm.nt * args.b_groups + g, z);
                             }
+                        } else if (args.b_rm) {
+                            tma_load_3d(dst, &maps.b[i], &full_bar[s], kb * PG_BK, itm.nt * args.bn_mma, z);
                         } else {
                             tma_load_4d(dst, &maps.b[i], &full_bar[s], 0, itm.nt * args.bn_mma, kb, z);
                         }
@@ -238,7 +245,8 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
                     if (ksteps > 4) ksteps = 4;
 #pragma unroll
                     for (int t = 0; t < 3; ++t) {                // hi*hi, hi*lo, lo*hi
-                        const uint32_t b_base = st + 2 * kABytes + (t == 1 ? b_bytes : 0);
+                        if (t == 2 && args.a_single) break;      // exact bf16 A: no lo*hi term
+                        const uint32_t b_base = st + a_bufs * kABytes + (t == 1 ? b_bytes : 0);
                         // aliased: rows mt*128.. of the (hi or lo) B tile are the A tile
                         const uint32_t a_base = args.a_alias_b ? st + (t == 2 ? b_bytes : 0) + mt_mma * 16384 : st + (t == 2 ? kABytes : 0);
                         for (int ks = 0; ks < ksteps; ++ks) {
@@ -278,6 +286,16 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
                     tma_load_4d(aux_base + cb * 8192 + 4096, &maps.o[3], &aux_bar[warp - 2], 0, mt * 128 + q * 32, cb0 + cb, z);
                 }
             }
+            // SGRAD: the direct-path gradient tile of this warp (32 rows x 64 fp32 columns per block: two 32 x 32 SWIZZLE_128B boxes)
+            // arrives by TMA - block 0 behind the main loop, block b + 1 while block b is converted.  (Read straight from global
+            // memory one row per lane, every 128-bit load touched 32 different lines: the load pipe, not DRAM, set the pace - 29 k
+            // cycles per item against 8 k of main loop.)
+            uint8_t* sg_tile = aux_staging + (warp - 2) * 8192;
+            if (kSgrad && warp_rows_ok && lane == 0) {
+                mbar_arrive_expect_tx(&aux_bar[warp - 2], 8192);
+                tma_load_3d(sg_tile, &maps.o[2], &aux_bar[warp - 2], c0, mt * 128 + q * 32, z);
+                tma_load_3d(sg_tile + 4096, &maps.o[2], &aux_bar[warp - 2], c0 + 32, mt * 128 + q * 32, z);
+            }
             if (args.dbg_clock && blockIdx.x == 0 && item < 16 && warp == 2 && lane == 0) args.dbg_clock[item * 8 + 5] = clock64();
             mbar_wait(&tmem_full_bar[acc], acc_ph);
             tc_fence_after();
@@ -292,6 +310,7 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
                 r = tsum > 0.f ? 1.f / tsum : 0.f;        // C == 0 (constant tokens): r = 0, the nuclear norm is 0, gradients stay finite
             }
             const float scale = args.scale_c * (args.scale_p == 0.f ? 1.f : powf(r, args.scale_p));
+            const float sg_alpha = kSgrad ? args.sg_alpha * (args.sg_scale ? *args.sg_scale : 1.f) : 0.f;
             const float aux_scale = args.aux_c * (args.aux_p == 0.f ? 1.f : powf(r, args.aux_p));
             float a_row = 0.f, q_row = 0.f;
             // THETA: a and sqrt(a) of this tile's columns, once per item into the warp's strip of shared memory (the per-element
@@ -334,6 +353,23 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
                     if (dbg_here) args.dbg_clock[120] = clock64();
                     float vb[64];
                     const int cols_here = min(64, args.bn_mma - cbk * 64);
+                    float4 sg_g[kSgrad ? 16 : 1];
+                    if constexpr (kSgrad) {
+                        if (warp_rows_ok) {
+                            mbar_wait(&aux_bar[warp - 2], aux_phase);
+                            aux_phase ^= 1;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)      // chunk j of this lane's row: box j / 8, 16-byte chunk (j % 8) ^ (row % 8) of its 128-byte row
+                                sg_g[j] = *reinterpret_cast<const float4*>(sg_tile + (j >> 3) * 4096 + lane * 128 + (((j & 7) ^ (lane & 7)) << 4));
+                            __syncwarp();                     // tile consumed by every lane: the next block may land on it
+                            const int cn = c0 + (cbk + 1) * 64;
+                            if (lane == 0 && cbk + 1 < n_cb && cn < args.n_cols) {
+                                mbar_arrive_expect_tx(&aux_bar[warp - 2], 8192);
+                                tma_load_3d(sg_tile, &maps.o[2], &aux_bar[warp - 2], cn, mt * 128 + q * 32, z);
+                                tma_load_3d(sg_tile + 4096, &maps.o[2], &aux_bar[warp - 2], cn + 32, mt * 128 + q * 32, z);
+                            }
+                        }
+                    }
                     if (cols_here == 64) {
                         tmem_ld64(t_addr + cbk * 64, vb);
                     } else {
@@ -372,6 +408,20 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
                                 }
 #pragma unroll
                                 for (int i = 0; i < 16; ++i) v[i] = fmaf(aux_scale, x[i], scale * v[i]) + ((c + i == row) ? args.diag_add : 0.f);
+                            } else if constexpr (kSgrad) {
+                                if (row_ok && c < args.n_cols) {             // (n_cols is a multiple of 8; chunks are 16 wide)
+                                    const float* cp = args.sg_corr + static_cast<long long>(z) * args.n_cols + c;
+                                    const int nq = min(4, (args.n_cols - c) >> 2);
+#pragma unroll
+                                    for (int i4 = 0; i4 < 4; ++i4) {
+                                        if (i4 < nq) {
+                                            const float4 g4 = sg_g[jc * 4 + i4];
+                                            const float4 c4 = __ldg(reinterpret_cast<const float4*>(cp) + i4);
+                                            v[4 * i4] = sg_alpha * g4.x + v[4 * i4] - c4.x;         v[4 * i4 + 1] = sg_alpha * g4.y + v[4 * i4 + 1] - c4.y;
+                                            v[4 * i4 + 2] = sg_alpha * g4.z + v[4 * i4 + 2] - c4.z; v[4 * i4 + 3] = sg_alpha * g4.w + v[4 * i4 + 3] - c4.w;
+                                        }
+                                    }
+                                }
                             } else if (diag_work) {
 #pragma unroll
                                 for (int i = 0; i < 16; ++i) v[i] = scale * v[i] + ((c + i == row) ? args.diag_add : 0.f);
