@@ -159,8 +159,71 @@ using CfgTestTN  = GemmCfg<false, false, 192, 1, 1, 1, 1, false, 4>;
 
 // Z[j] = X[j] P_t^T for all L_t teacher layers in ONE launch (blockIdx.z = layer; the layers are separate tensors, so each
 // has its own tensor map in maps.a_table).  12 launches of 392 CTAs each left the last wave of every launch 65 % empty.
+// The projection on the persistent polar_gemm kernel: work item = (layer, 128-row tile, column tile of <= 256 columns), A = the
+// teacher tokens of that layer through the layer's own tensor map (one exact bf16 buffer: two split terms against P_t hi / lo),
+// operand ring and two TMEM accumulators carried across items, Z leaves as a row-major split pair through swizzled staging and
+// TMA stores (ROWMAJOR epilogue; the rows between the samples of a CLS-stripped view are written as zeros).  The one-tile-per-CTA
+// kernel below ran a two-stage ring and per-lane 32-byte row stores with nothing overlapped: 59 k cycles per 256-row tile against
+// 18 k of MMAs (0.48 ms at cfg2).
+static cudaError_t project_persistent(const void* const* X, int n_layers, size_t M, int Dt, const __nv_bfloat16* Phi, const __nv_bfloat16* Plo,
+                                      int Ds, __nv_bfloat16* Z, __nv_bfloat16* Zlo, int gap_period, int gap_valid, cudaStream_t st) {
+    PolarGemmArgs a;
+    memset(&a, 0, sizeof a);
+    a.epi = PG_EPI_ROWMAJOR; a.scale_c = 1.f; a.a_rm = 1; a.b_rm = 1; a.a_single = 1; a.b_shared = 1;
+    a.gap_period = gap_period; a.gap_valid = gap_valid;
+    a.ld_out = Ds; a.out_stride = static_cast<long long>(M) * Ds;
+    a.m_rows = static_cast<int>(M); a.n_cols = Ds; a.k_total = Dt;
+    a.n_mt = static_cast<int>((M + 127) / 128);
+    if (Ds <= 256) {
+        a.n_nt = 1; a.bn_mma = (Ds + 15) / 16 * 16;
+    } else {
+        a.n_nt = (Ds + 255) / 256;
+        a.bn_mma = ((Ds + a.n_nt - 1) / a.n_nt + 63) / 64 * 64;
+        a.n_nt = (Ds + a.bn_mma - 1) / a.bn_mma;
+    }
+    a.b_groups = (a.bn_mma + 63) / 64;
+    const int stage_bytes = 16384 + 2 * a.bn_mma * 128;
+    const int kTail = 1024 /*alignment*/ + 1024 /*barriers*/ + 4 * 8192 /*epilogue staging*/;
+    int stages = (232448 - kTail) / stage_bytes;
+    if (stages > 4) stages = 4;
+    if (stages < 1) return cudaErrorInvalidValue;
+    a.stages = stages;
+    const int smem = stages * stage_bytes + kTail;
+    auto kern = polar_gemm_kernel<false, 4, true>;
+    static bool configured[kMaxDevices] = {};
+    const int dev = current_device();
+    if (!configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    const int sm_count = device_sm_count();
+    for (int j0 = 0; j0 < n_layers; j0 += PG_MAX_A_TABLE) {
+        const int nl = n_layers - j0 < PG_MAX_A_TABLE ? n_layers - j0 : PG_MAX_A_TABLE;
+        PolarGemmMapsT maps;
+        memset(&maps, 0, sizeof maps);
+        for (int j = 0; j < nl; ++j)
+            if (make_map(&maps.a_tab[j], X[j0 + j], Dt, M, 1, Dt, M * Dt, 64)) return cudaErrorInvalidValue;
+        if (make_map(&maps.b[0], Phi, Dt, Ds, 1, Dt, static_cast<uint64_t>(Ds) * Dt, a.bn_mma)) return cudaErrorInvalidValue;
+        if (make_map(&maps.b[1], Plo, Dt, Ds, 1, Dt, static_cast<uint64_t>(Ds) * Dt, a.bn_mma)) return cudaErrorInvalidValue;
+        a.out_hi = Z + static_cast<size_t>(j0) * M * Ds; a.out_lo = Zlo + static_cast<size_t>(j0) * M * Ds;
+        if (make_map(&maps.o[0], a.out_hi, Ds, M, nl, Ds, M * Ds, 32)) return cudaErrorInvalidValue;
+        if (make_map(&maps.o[1], a.out_lo, Ds, M, nl, Ds, M * Ds, 32)) return cudaErrorInvalidValue;
+        a.n_items = nl * a.n_mt * a.n_nt; a.n_batches = nl;
+        kern<<<a.n_items < sm_count ? a.n_items : sm_count, PG_THREADS, smem, st>>>(maps, a);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+// BASD_PROJECT_TILE=1 (read once per process): keep the one-tile-per-CTA kernel (A/B measurements)
+static bool project_use_tile_kernel() { static const bool v = [] { const char* e = getenv("BASD_PROJECT_TILE"); return e && atoi(e) != 0; }(); return v; }
+
 cudaError_t gemm_project(const void* const* X, int n_layers, size_t M, int Dt, const __nv_bfloat16* Phi, const __nv_bfloat16* Plo, int Ds,
                          __nv_bfloat16* Z, __nv_bfloat16* Zlo, int gap_period, int gap_valid, cudaStream_t st) {
+    if (Ds % 8 == 0 && Dt % 8 == 0 && M < (size_t(1) << 31) - 128 && !project_use_tile_kernel())
+        return project_persistent(X, n_layers, M, Dt, Phi, Plo, Ds, Z, Zlo, gap_period, gap_valid, st);
     GemmArgs a;
     memset(&a, 0, sizeof a);
     a.gap_period = gap_period; a.gap_valid = gap_valid;
@@ -322,7 +385,61 @@ static cudaError_t token_gram_impl(const __nv_bfloat16* Thi, const __nv_bfloat16
     a.out = Ktt; a.out_batch_stride = static_cast<long long>(Ns) * Ns; a.ld_out = Ns; a.rows_valid = Ns; a.cols_valid = Ns; a.alpha = 1.f;
     return launch<CfgTokenGram<BN>, EpiStoreF32>(maps, a, dim3(1, 1, batches), st);
 }
+// K[z] = T[z] T[z]^T on the persistent polar_gemm kernel: T (row-major split pair [Ns][Dt]) is both operands, work item =
+// (sample, 128-row tile, column tile); with one column tile (Ns <= 256) the A tile is read out of the B tile (no A loads; the
+// second row tile of a sample re-reads the B tile from L2), the fp32 result leaves from the epilogue warps while the next item's
+// MMAs fill the other TMEM accumulator.  The one-tile-per-CTA kernel below (both row tiles against one load of T, nothing
+// overlapped) took 69 k cycles per sample against 30 k of MMAs (0.24 ms at cfg2).
+static cudaError_t token_gram_persistent(const __nv_bfloat16* Thi, const __nv_bfloat16* Tlo, int batches, int Ns, int Dt, float* Ktt,
+                                         cudaStream_t st) {
+    PolarGemmArgs a;
+    memset(&a, 0, sizeof a);
+    a.epi = PG_EPI_F32; a.scale_c = 1.f; a.a_rm = 1; a.b_rm = 1;
+    a.out_f32 = Ktt; a.out_f32_stride = static_cast<long long>(Ns) * Ns; a.ld_f32 = Ns;
+    a.m_rows = Ns; a.n_cols = Ns; a.k_total = Dt;
+    a.n_mt = (Ns + 127) / 128;
+    if (Ns <= 256) {
+        a.n_nt = 1; a.bn_mma = (Ns + 15) / 16 * 16; a.a_alias_b = 1;
+    } else {
+        a.n_nt = (Ns + 255) / 256;
+        a.bn_mma = ((Ns + a.n_nt - 1) / a.n_nt + 63) / 64 * 64;
+        a.n_nt = (Ns + a.bn_mma - 1) / a.bn_mma;
+    }
+    a.n_items = batches * a.n_mt * a.n_nt; a.n_batches = batches;
+    a.b_groups = (a.bn_mma + 63) / 64;
+    PolarGemmMaps maps;
+    memset(&maps, 0, sizeof maps);
+    const __nv_bfloat16* tp[2] = {Thi, Tlo};
+    for (int i = 0; i < 2; ++i) {
+        if (make_map(&maps.a[i], tp[i], Dt, Ns, batches, Dt, static_cast<uint64_t>(Ns) * Dt, 64)) return cudaErrorInvalidValue;
+        if (make_map(&maps.b[i], tp[i], Dt, Ns, batches, Dt, static_cast<uint64_t>(Ns) * Dt, a.bn_mma)) return cudaErrorInvalidValue;
+    }
+    const int stage_bytes = (a.a_alias_b ? 0 : 2 * 16384) + 2 * a.bn_mma * 128;
+    // (the aliased A tile of the last rows reads up to 16 KB past its B tile: into the next tile or the barrier / staging area -
+    //  rows past Ns, never stored)
+    const int kTail = 1024 /*alignment*/ + 1024 /*barriers*/ + 4 * 8192 /*epilogue staging (unused by the fp32 epilogue; over-read area)*/;
+    int stages = (232448 - kTail) / stage_bytes;
+    if (stages > 4) stages = 4;
+    if (stages < 1) return cudaErrorInvalidValue;
+    a.stages = stages;
+    const int smem = stages * stage_bytes + kTail;
+    auto kern = polar_gemm_kernel<false, 3>;
+    static bool configured[kMaxDevices] = {};
+    const int dev = current_device();
+    if (!configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    const int sm_count = device_sm_count();
+    kern<<<a.n_items < sm_count ? a.n_items : sm_count, PG_THREADS, smem, st>>>(maps, a);
+    return cudaGetLastError();
+}
+// BASD_TOKEN_GRAM_TILE=1 (read once per process): keep the one-tile-per-CTA kernels (A/B measurements)
+static bool token_gram_use_tile_kernel() { static const bool v = [] { const char* e = getenv("BASD_TOKEN_GRAM_TILE"); return e && atoi(e) != 0; }(); return v; }
+
 cudaError_t gemm_token_gram(const __nv_bfloat16* Thi, const __nv_bfloat16* Tlo, int batches, int Ns, int Dt, float* Ktt, cudaStream_t st) {
+    if (Dt % 8 == 0 && Ns >= 16 && !token_gram_use_tile_kernel()) return token_gram_persistent(Thi, Tlo, batches, Ns, Dt, Ktt, st);
     if (Ns <= 64) return token_gram_impl<64>(Thi, Tlo, batches, Ns, Dt, Ktt, st);
     if (Ns <= 128) return token_gram_impl<128>(Thi, Tlo, batches, Ns, Dt, Ktt, st);
     if (Ns <= 208) return token_gram_impl<208>(Thi, Tlo, batches, Ns, Dt, Ktt, st);

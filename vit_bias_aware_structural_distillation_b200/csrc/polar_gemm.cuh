@@ -37,6 +37,12 @@ struct PolarGemmMaps {
     CUtensorMap b[2];
     CUtensorMap o[4];                // SPLIT: out hi, out lo (TMA stores), aux hi, aux lo (TMA loads); box = 32 rows x 64 columns
 };
+// A_TABLE instantiations: the A operand of problem z is its own allocation with its own tensor map (the teacher layers of the
+// projection are separate tensors); only those instantiations carry the table in their kernel parameters.
+constexpr int PG_MAX_A_TABLE = 16;
+struct PolarGemmMapsT : PolarGemmMaps {
+    CUtensorMap a_tab[PG_MAX_A_TABLE];
+};
 
 struct PolarGemmArgs {
     int m_rows, n_cols, k_total;     // valid sizes
@@ -72,6 +78,10 @@ struct PolarGemmArgs {
     int a_single;                    // A is one exact bf16 buffer (no lo half): terms A * B_hi + A * B_lo
     // SGRAD: direct-path gradient gdir fp32 [m_rows][n_cols], centring correction corr fp32 [n_cols], alpha = sg_alpha * *sg_scale (if non-null)
     const float* sg_gdir; const float* sg_corr; const float* sg_scale; float sg_alpha;
+    int b_shared;                    // row-major K-major B: one matrix for every problem (batch coordinate 0)
+    // ROWMAJOR: rows r with r % gap_period >= gap_valid are written as zeros (the CLS rows between the samples of a [:,1:,:] view
+    // read as one dense matrix, umma_gemm.cuh GemmArgs::gap_period); 0 = no gaps
+    int gap_period, gap_valid;
 };
 
 // 16 fp32 values -> bf16 hi / lo halves of staging row `row` (32 rows x 128 B, SWIZZLE_128B: 16-byte chunk j of row r
@@ -141,9 +151,11 @@ __device__ __forceinline__ int pg_a_rows(const PolarGemmArgs& a, int mt) {
 // body the epilogue was ~3900 SASS instructions of mostly-skipped branches executed by a single warp per scheduler):
 //   0 = SPLIT (scale, diagonal, optional trace of the diagonal)   1 = SPLIT + auxiliary tile   2 = THETA   3 = F32
 //   4 = ROWMAJOR (scale; one bf16 or a split pair, row-major)   5 = SGRAD (direct gradient + product - correction, bf16 row-major)
-template <bool B_MN, int KIND>
+template <bool A_TABLE> struct PgMapsOf { using type = PolarGemmMaps; };
+template <> struct PgMapsOf<true> { using type = PolarGemmMapsT; };
+template <bool B_MN, int KIND, bool A_TABLE = false>
 __global__ void __launch_bounds__(PG_THREADS, 1)
-polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArgs args) {
+polar_gemm_kernel(const __grid_constant__ typename PgMapsOf<A_TABLE>::type maps, const PolarGemmArgs args) {
     constexpr bool kStaged = KIND != 3, kTheta = KIND == 2, kAux = KIND == 1, kSgrad = KIND == 5, kRowMajor = KIND == 4 || kSgrad;
     extern __shared__ uint8_t pg_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(pg_smem_raw) + 1023) & ~uintptr_t(1023));
@@ -168,7 +180,7 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 4); }
         for (int i = 0; i < 4; ++i) mbar_init(&aux_bar[i], 1);
         fence_mbar_init();
-        tma_prefetch_desc(&maps.a[0]); tma_prefetch_desc(&maps.a[1]);
+        if constexpr (!A_TABLE) { tma_prefetch_desc(&maps.a[0]); tma_prefetch_desc(&maps.a[1]); }
         tma_prefetch_desc(&maps.b[0]); tma_prefetch_desc(&maps.b[1]);
         if (kStaged) { tma_prefetch_desc(&maps.o[0]); tma_prefetch_desc(&maps.o[1]); }
     }
@@ -200,7 +212,8 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
                     for (int i = 0; i < a_bufs && !args.a_alias_b; ++i) {
                         uint8_t* dst = st + i * kABytes;
                         for (int g = 0; g < a_rows / 64; ++g) {
-                            if (args.a_rm) tma_load_3d(dst + g * 8192, &maps.a[i], &full_bar[s], kb * PG_BK, mt * 128 + g * 64, z);
+                            if constexpr (A_TABLE) tma_load_3d(dst + g * 8192, &maps.a_tab[z], &full_bar[s], kb * PG_BK, mt * 128 + g * 64, 0);
+                            else if (args.a_rm) tma_load_3d(dst + g * 8192, &maps.a[i], &full_bar[s], kb * PG_BK, mt * 128 + g * 64, z);
                             else tma_load_4d(dst + g * 8192, &maps.a[i], &full_bar[s], 0, mt * 128 + g * 64, kb, z);
                         }
                     }
@@ -212,7 +225,7 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
                                 else tma_load_4d(dst + g * 8192, &maps.b[i], &full_bar[s], 0, kb * PG_BK, itm.nt * args.b_groups + g, z);
                             }
                         } else if (args.b_rm) {
-                            tma_load_3d(dst, &maps.b[i], &full_bar[s], kb * PG_BK, itm.nt * args.bn_mma, z);
+                            tma_load_3d(dst, &maps.b[i], &full_bar[s], kb * PG_BK, itm.nt * args.bn_mma, args.b_shared ? 0 : z);
                         } else {
                             tma_load_4d(dst, &maps.b[i], &full_bar[s], 0, itm.nt * args.bn_mma, kb, z);
                         }
@@ -303,6 +316,7 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * args.bn_mma;
             const int row = mt * 128 + q * 32 + lane;
             const bool row_ok = row < args.m_rows;
+            const bool gap_row = KIND == 4 && args.gap_period > 0 && row % args.gap_period >= args.gap_valid;
             float r = 1.f;
             if (args.norm2) {
                 float tsum = 0.f;
@@ -425,6 +439,9 @@ polar_gemm_kernel(const __grid_constant__ PolarGemmMaps maps, const PolarGemmArg
                             } else if (diag_work) {
 #pragma unroll
                                 for (int i = 0; i < 16; ++i) v[i] = scale * v[i] + ((c + i == row) ? args.diag_add : 0.f);
+                            } else if (KIND == 4 && gap_row) {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) v[i] = 0.f;
                             } else {
 #pragma unroll
                                 for (int i = 0; i < 16; ++i) v[i] *= scale;
