@@ -159,6 +159,13 @@ using CfgTestTN  = GemmCfg<false, false, 192, 1, 1, 1, 1, false, 4>;
 
 // Z[j] = X[j] P_t^T for all L_t teacher layers in ONE launch (blockIdx.z = layer; the layers are separate tensors, so each
 // has its own tensor map in maps.a_table).  12 launches of 392 CTAs each left the last wave of every launch 65 % empty.
+// fp32 row-major outputs can leave the persistent kernel as TMA stores (epilogue kind 6) when base, row pitch and batch pitch are
+// 16-byte aligned; BASD_F32_EPI_LANES=1 (read once per process) keeps the per-lane stores (A/B measurements)
+static bool f32_tma_ok(const float* out, int ld, long long batch_stride) {
+    static const bool off = [] { const char* e = getenv("BASD_F32_EPI_LANES"); return e && atoi(e) != 0; }();
+    return !off && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && ld % 4 == 0 && batch_stride % 4 == 0;
+}
+
 // The projection on the persistent polar_gemm kernel: work item = (layer, 128-row tile, column tile of <= 256 columns), A = the
 // teacher tokens of that layer through the layer's own tensor map (one exact bf16 buffer: two split terms against P_t hi / lo),
 // operand ring and two TMEM accumulators carried across items, Z leaves as a row-major split pair through swizzled staging and
@@ -423,13 +430,15 @@ static cudaError_t token_gram_persistent(const __nv_bfloat16* Thi, const __nv_bf
     if (stages < 1) return cudaErrorInvalidValue;
     a.stages = stages;
     const int smem = stages * stage_bytes + kTail;
-    auto kern = polar_gemm_kernel<false, 3>;
-    static bool configured[kMaxDevices] = {};
+    const bool tma_out = f32_tma_ok(Ktt, Ns, a.out_f32_stride);
+    if (tma_out && make_map_f32(&maps.o[0], Ktt, Ns, Ns, batches, Ns, a.out_f32_stride)) return cudaErrorInvalidValue;
+    auto kern = tma_out ? polar_gemm_kernel<false, 6> : polar_gemm_kernel<false, 3>;
+    static bool configured[kMaxDevices][2] = {};
     const int dev = current_device();
-    if (!configured[dev]) {
+    if (!configured[dev][tma_out]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         if (e != cudaSuccess) return e;
-        configured[dev] = true;
+        configured[dev][tma_out] = true;
     }
     const int sm_count = device_sm_count();
     kern<<<a.n_items < sm_count ? a.n_items : sm_count, PG_THREADS, smem, st>>>(maps, a);
@@ -664,14 +673,19 @@ cudaError_t polar_gemm(bool b_mn, const SplitMat& A, const SplitMat& B, int batc
     }
     a.stages = stages;
     const int smem = stages * stage_bytes + kTail;
-    // epilogue kind -> kernel instantiation (polar_gemm.cuh)
-    const int kind = a.epi == PG_EPI_F32 ? 3 : a.epi == PG_EPI_THETA ? 2 : a.aux_mode ? 1 : 0;
+    // epilogue kind -> kernel instantiation (polar_gemm.cuh); fp32 outputs leave as TMA stores (table index 4 = kind 6) when the
+    // row pitch allows it
+    int kind = a.epi == PG_EPI_F32 ? 3 : a.epi == PG_EPI_THETA ? 2 : a.aux_mode ? 1 : 0;
+    if (kind == 3 && f32_tma_ok(a.out_f32, a.ld_f32, a.out_f32_stride)) {
+        if (make_map_f32(&maps.o[0], a.out_f32, n_cols, m_rows, batches, a.ld_f32, a.out_f32_stride)) return cudaErrorInvalidValue;
+        kind = 4;
+    }
     using Kern = void (*)(const PolarGemmMaps, const PolarGemmArgs);
-    static const Kern kerns[2][4] = {
-        {polar_gemm_kernel<false, 0>, polar_gemm_kernel<false, 1>, polar_gemm_kernel<false, 2>, polar_gemm_kernel<false, 3>},
-        {polar_gemm_kernel<true, 0>, polar_gemm_kernel<true, 1>, polar_gemm_kernel<true, 2>, polar_gemm_kernel<true, 3>}};
+    static const Kern kerns[2][5] = {
+        {polar_gemm_kernel<false, 0>, polar_gemm_kernel<false, 1>, polar_gemm_kernel<false, 2>, polar_gemm_kernel<false, 3>, polar_gemm_kernel<false, 6>},
+        {polar_gemm_kernel<true, 0>, polar_gemm_kernel<true, 1>, polar_gemm_kernel<true, 2>, polar_gemm_kernel<true, 3>, polar_gemm_kernel<true, 6>}};
     const Kern kern = kerns[b_mn][kind];
-    static bool configured[kMaxDevices][2][4] = {};
+    static bool configured[kMaxDevices][2][5] = {};
     const int dev = current_device();
     if (!configured[dev][b_mn][kind]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);

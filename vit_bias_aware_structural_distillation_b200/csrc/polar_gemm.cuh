@@ -107,6 +107,15 @@ __device__ __forceinline__ void pg_stage_split16(uint32_t stg_hi, uint32_t stg_l
     st_shared_v4(stg_lo + p0, lw[0], lw[1], lw[2], lw[3]);
     st_shared_v4(stg_lo + p1, lw[4], lw[5], lw[6], lw[7]);
 }
+// 16 fp32 values -> staging row `row` of a 32 rows x 32 fp32 tile (128-byte rows, SWIZZLE_128B); chunk0 = first of the four
+// 16-byte chunks they occupy
+__device__ __forceinline__ void pg_stage_f32x16(uint32_t stg, int row, int chunk0, const float* v) {
+    const uint32_t base = stg + row * 128;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        st_shared_v4(base + (((chunk0 + i) ^ (row & 7)) << 4), __float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]),
+                     __float_as_uint(v[4 * i + 2]), __float_as_uint(v[4 * i + 3]));
+}
 __device__ __forceinline__ void pg_stage_zero16(uint32_t stg_hi, uint32_t stg_lo, int row, int chunk0) {
     const uint32_t base = row * 128, p0 = base + ((chunk0 ^ (row & 7)) << 4), p1 = base + (((chunk0 + 1) ^ (row & 7)) << 4);
     st_shared_v4(stg_hi + p0, 0u, 0u, 0u, 0u);
@@ -151,12 +160,16 @@ __device__ __forceinline__ int pg_a_rows(const PolarGemmArgs& a, int mt) {
 // body the epilogue was ~3900 SASS instructions of mostly-skipped branches executed by a single warp per scheduler):
 //   0 = SPLIT (scale, diagonal, optional trace of the diagonal)   1 = SPLIT + auxiliary tile   2 = THETA   3 = F32
 //   4 = ROWMAJOR (scale; one bf16 or a split pair, row-major)   5 = SGRAD (direct gradient + product - correction, bf16 row-major)
+//   6 = F32 through the staging tiles: the warp's two 4 KB tiles hold 32 rows x 32 fp32 columns each and leave as TMA stores
+//       (maps.o[0] = fp32 map of the row-major output; needs a 16-byte row pitch).  The per-lane row stores of kind 3 (32 rows x
+//       16 bytes per instruction) cost ~20 k cycles per 128 x 192 item - more than the item's MMAs.
 template <bool A_TABLE> struct PgMapsOf { using type = PolarGemmMaps; };
 template <> struct PgMapsOf<true> { using type = PolarGemmMapsT; };
 template <bool B_MN, int KIND, bool A_TABLE = false>
 __global__ void __launch_bounds__(PG_THREADS, 1)
 polar_gemm_kernel(const __grid_constant__ typename PgMapsOf<A_TABLE>::type maps, const PolarGemmArgs args) {
-    constexpr bool kStaged = KIND != 3, kTheta = KIND == 2, kAux = KIND == 1, kSgrad = KIND == 5, kRowMajor = KIND == 4 || kSgrad;
+    constexpr bool kStaged = KIND != 3, kTheta = KIND == 2, kAux = KIND == 1, kSgrad = KIND == 5, kF32Staged = KIND == 6;
+    constexpr bool kRowMajor = KIND == 4 || kSgrad || kF32Staged;
     extern __shared__ uint8_t pg_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(pg_smem_raw) + 1023) & ~uintptr_t(1023));
     const int kABytes = args.a_alias_b ? 0 : 128 * 128;    // one 128-row A tile per operand buffer (none when aliased)
@@ -182,7 +195,7 @@ polar_gemm_kernel(const __grid_constant__ typename PgMapsOf<A_TABLE>::type maps,
         fence_mbar_init();
         if constexpr (!A_TABLE) { tma_prefetch_desc(&maps.a[0]); tma_prefetch_desc(&maps.a[1]); }
         tma_prefetch_desc(&maps.b[0]); tma_prefetch_desc(&maps.b[1]);
-        if (kStaged) { tma_prefetch_desc(&maps.o[0]); tma_prefetch_desc(&maps.o[1]); }
+        if (kStaged) { tma_prefetch_desc(&maps.o[0]); if (!kF32Staged) tma_prefetch_desc(&maps.o[1]); }
     }
     uint32_t tmem_cols = 32;
     while (tmem_cols < static_cast<uint32_t>(2 * args.bn_mma)) tmem_cols <<= 1;
@@ -397,6 +410,10 @@ polar_gemm_kernel(const __grid_constant__ typename PgMapsOf<A_TABLE>::type maps,
                     for (int jc = 0; jc < 4; ++jc) {
                         const int c = c0 + cbk * 64 + jc * 16;                  // global column of v[0]
                         float* v = vb + jc * 16;
+                        if constexpr (kF32Staged) {                             // plain fp32 result (scale_c == 1): columns 0-31 -> tile "hi", 32-63 -> tile "lo"
+                            if (cbk * 64 + jc * 16 < args.bn_mma) pg_stage_f32x16(jc < 2 ? stg_hi_s : stg_lo_s, lane, (jc & 1) * 4, v);
+                            continue;
+                        }
                         if (cbk * 64 + jc * 16 < args.bn_mma) {
                             if (KIND == 0 && args.trace && row_ok) {
 #pragma unroll
@@ -456,7 +473,11 @@ polar_gemm_kernel(const __grid_constant__ typename PgMapsOf<A_TABLE>::type maps,
                     __syncwarp();                                               // staging complete; aux tile fully consumed
                     if (dbg_here) args.dbg_clock[123] = clock64();
                     if (lane == 0 && warp_rows_ok) {
-                        if constexpr (theta) {                                  // row-major output, columns past n_cols are clipped
+                        if constexpr (kF32Staged) {                             // two 32 x 32 fp32 boxes; columns past n_cols / rows past m_rows are clipped
+                            tma_store_3d(&maps.o[0], stg_hi, c0 + cbk * 64, mt * 128 + q * 32, z);
+                            if (c0 + cbk * 64 + 32 < args.n_cols && cbk * 64 + 32 < args.bn_mma)
+                                tma_store_3d(&maps.o[0], stg_lo, c0 + cbk * 64 + 32, mt * 128 + q * 32, z);
+                        } else if constexpr (theta) {                           // row-major output, columns past n_cols are clipped
                             tma_store_3d(&maps.o[0], stg_hi, c0 + cbk * 64, mt * 128 + q * 32, z);
                             tma_store_3d(&maps.o[1], stg_lo, c0 + cbk * 64, mt * 128 + q * 32, z);
                         } else if constexpr (kRowMajor) {
