@@ -267,18 +267,30 @@ splitk_reduce_kernel(const float* __restrict__ part, int n_splits, int elems4, f
         o[e] = acc;
     }
 }
-// split-K geometry of a Gram over M rows: at most 32 slices of at least 32 k-blocks
-static void gram_splits(size_t M, int* kb_total, int* kb_per_split, int* n_splits) {
+// split-K geometry of a Gram over M rows: at most kGramMaxSplits slices.  The Gram kernels run one CTA per SM, so the launch lasts
+// (waves of CTAs) x (k-blocks per slice + the fixed cost of a CTA: set-up and the unoverlapped epilogue, ~10 k-blocks' worth) plus
+// the fixed-order reduction over the slices; ctas_per_slice = output tiles x batches.  (32 k-blocks per slice whatever the grid
+// gave 12 layers x 25 slices = 300 CTAs at cfg2: two full waves and a third of four CTAs - a third of the launch.)
+constexpr int kGramMaxSplits = 32;
+static void gram_splits(size_t M, int ctas_per_slice, int* kb_total, int* kb_per_split, int* n_splits) {
     *kb_total = cdiv(M, GEMM_BK);
-    int per = 32;
-    if (cdiv(*kb_total, per) > 32) per = cdiv(*kb_total, 32);
-    *kb_per_split = per;
-    *n_splits = cdiv(*kb_total, per);
+    const int sms = device_sm_count();
+    int best_per = *kb_total;
+    double best_cost = 1e300;
+    for (int ns = 1; ns <= kGramMaxSplits && ns <= *kb_total; ++ns) {
+        const int per = cdiv(*kb_total, ns);
+        if (cdiv(*kb_total, per) != ns) continue;                       // the same geometry as a smaller ns
+        const double waves = static_cast<double>(cdiv(static_cast<long long>(ctas_per_slice) * ns, sms));
+        const double cost = waves * (per + 10.0) + 0.08 * ns * ctas_per_slice;
+        if (cost < best_cost) { best_cost = cost; best_per = per; }
+    }
+    *kb_per_split = best_per;
+    *n_splits = cdiv(*kb_total, best_per);
 }
-size_t gemm_gram_part_floats(size_t M, int Ds, int batches) {
-    int kt, kp, ns;
-    gram_splits(M, &kt, &kp, &ns);
-    return static_cast<size_t>(ns) * batches * (static_cast<size_t>(Ds) * Ds + Ds);       // Gram slices, then column-sum slices
+static int gram_tiles(int Ds) { return cdiv(Ds, CfgGram::kBN) * cdiv(Ds, CfgGram::kMT * 128); }
+size_t gemm_gram_part_floats(size_t M, int Ds, int batches) {      // sized for the largest slice count (device independent)
+    const int ns = cdiv(M, GEMM_BK) < kGramMaxSplits ? cdiv(M, GEMM_BK) : kGramMaxSplits;
+    return static_cast<size_t>(ns > 0 ? ns : 1) * batches * (static_cast<size_t>(Ds) * Ds + Ds);       // Gram slices, then column-sum slices
 }
 // Fused where it was measured to pay: the single-tile (aliased) Grams, D_s <= 192 (cfg2: gram + colsum 0.33 -> 0.27 ms).  Two-tile
 // Grams (D_s = 384) got SLOWER with the extra MMAs in every column tile (cfg4: gram 1.27 -> 1.59 ms against 0.04 saved).
@@ -313,7 +325,7 @@ static cudaError_t gram_impl(const __nv_bfloat16* Z, const __nv_bfloat16* Zlo, s
     }
     GemmArgs a;
     memset(&a, 0, sizeof a);
-    gram_splits(M, &a.kb_total, &a.kb_per_split, &a.n_splits);
+    gram_splits(M, gram_tiles(Ds) * batches, &a.kb_total, &a.kb_per_split, &a.n_splits);
     a.a_batched = 1; a.b_batched = 1;
     a.out = part; a.out_batch_stride = static_cast<long long>(Ds) * Ds; a.ld_out = Ds; a.rows_valid = Ds; a.cols_valid = Ds;
     float* cpart = part + static_cast<size_t>(a.n_splits) * batches * Ds * Ds;
@@ -353,11 +365,11 @@ cudaError_t gemm_gram_table(const void* const* S, int n, size_t M, int Ds, float
         for (int i = 0; i < n; ++i)
             if (make_map(&maps.a_table[i], S[i], Ds, rows_per_batch, B, Ds, batch_stride, 64)) return cudaErrorInvalidValue;
         a.kb_per_batch = cdiv(rows_per_batch, GEMM_BK);
-        gram_splits(B * a.kb_per_batch * GEMM_BK, &a.kb_total, &a.kb_per_split, &a.n_splits);
+        gram_splits(B * a.kb_per_batch * GEMM_BK, gram_tiles(Ds) * n, &a.kb_total, &a.kb_per_split, &a.n_splits);
     } else {
         for (int i = 0; i < n; ++i)
             if (make_map(&maps.a_table[i], S[i], Ds, M, 1, Ds, M * Ds, 64)) return cudaErrorInvalidValue;
-        gram_splits(M, &a.kb_total, &a.kb_per_split, &a.n_splits);
+        gram_splits(M, gram_tiles(Ds) * n, &a.kb_total, &a.kb_per_split, &a.n_splits);
     }
     a.a_table = 1; a.b_table = 1;
     a.out = part; a.out_batch_stride = static_cast<long long>(Ds) * Ds; a.ld_out = Ds; a.rows_valid = Ds; a.cols_valid = Ds;
