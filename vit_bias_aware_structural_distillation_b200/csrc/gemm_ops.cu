@@ -750,7 +750,12 @@ cudaError_t polar_fused_abm(const SplitMat& T, const SplitMat& W, const SplitMat
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
-    const int sm_count = device_sm_count();
+    // development knobs, read once per process: BASD_POLAR_FUSED_GRID (CTAs), BASD_POLAR_FUSED_STAGGER (cycles, odd CTAs)
+    static const int knob_grid = [] { const char* e = getenv("BASD_POLAR_FUSED_GRID"); return e ? atoi(e) : 0; }();
+    static const int knob_stagger = [] { const char* e = getenv("BASD_POLAR_FUSED_STAGGER"); return e ? atoi(e) : 0; }();
+    a.stagger = knob_stagger;
+    int sm_count = device_sm_count();
+    if (knob_grid > 0 && knob_grid < sm_count) sm_count = knob_grid;
     const int grid = batches < sm_count ? batches : sm_count;
     polar_fused_abm_kernel<<<grid, PF_THREADS, smem, st>>>(maps, a);
     return cudaGetLastError();

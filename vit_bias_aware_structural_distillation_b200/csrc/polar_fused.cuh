@@ -102,6 +102,10 @@ polar_fused_abm_kernel(const __grid_constant__ PolarFusedMaps maps, const PolarF
         if (lane == 0) {
             const uint32_t tx = stage_bytes;
             int it = 0, item = 0;
+            if (args.stagger > 0 && (blockIdx.x & 1)) {
+                const long long t0 = clock64();
+                while (clock64() - t0 < args.stagger) __nanosleep(200);
+            }
             for (int w = blockIdx.x; w < args.n_problems; w += gridDim.x, ++item) {
                 const int z = args.reverse ? args.n_problems - 1 - w : w;
                 if (item > 0) mbar_wait(p2done_bar, (item - 1) & 1);       // the operand copy of the previous problem is dead

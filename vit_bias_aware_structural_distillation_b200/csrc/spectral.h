@@ -144,6 +144,7 @@ struct PolarFusedArgs {
     int fro_slots;
     float* resid;                    // last step only: [problem][fro_slots] per-warp partial sums of ||A - I||_F^2 (else null)
     long long* dbg_clock;            // development aid: CTA 0 records clock64() per phase of its first problems ([problem][8])
+    int stagger;                     // development aid (BASD_POLAR_FUSED_STAGGER): odd CTAs start their first loads this many cycles late
 };
 // Bm = ca I + cb (rA) + cc (rA)^2 with A = T W^T kept on chip (polar_fused.cuh); needs polar_fused_supported(D_s, N_s)
 bool polar_fused_supported(int n, int k);
