@@ -638,6 +638,9 @@ size_t pooled_eig_scratch_floats(int n, int problems) { return spectral_large(n)
 // Cluster size of the shared-memory solver: the Jacobi pair-step is a dependent chain whose latency grows with the warps an
 // SM has to issue for (jacobi.cuh), so every problem gets as many CTAs as the GPU can co-schedule for ALL problems at once
 // (a cluster lives inside one GPC: cudaOccupancyMaxActiveClusters knows how many fit).  Cached per device and shape.
+// When the problems do not fit at once whatever the size (cfg4: 28 problems of size 384, 24 six-CTA clusters fit) the smallest
+// cluster stays: picking the size from a waves x pair-step-time model chose a larger one there and measured 10.0 ms against
+// 9.4 ms (r2w).
 static int pooled_pick_cluster(const void* kern, int n, int problems, size_t smem_fixed, size_t smem_per_group_floats) {
     static const int forced = [] {            // BASD_EIG_CLUSTER: development knob (1..8 CTAs per problem), read once
         const char* env = getenv("BASD_EIG_CLUSTER");
