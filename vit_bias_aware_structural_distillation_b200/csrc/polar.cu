@@ -232,13 +232,9 @@ polar_prep_student_vec_kernel(PolarArgs g) {
     // SW = s_w [N][Ds], tiled [d block][n][64]: a thread takes 8 consecutive d of one row
     __nv_bfloat16* swh = g.SW.hi + prob * g.SW.batch_stride;
     __nv_bfloat16* swl = g.SW.lo + prob * g.SW.batch_stride;
-    // (row, column block) walked incrementally: the runtime divisions of the flat index were a third of this kernel's 85 M
-    // warp instructions (ncu, r2t: issue-bound at 48 % with 1.3 barrier / 3.8 scoreboard stalls per issue)
     const int n_cb = (D + 63) / 64;
-    const int j0 = (threadIdx.x & 7) * 8, oct_step = blockDim.x >> 3;
-    for (int n = threadIdx.x >> 3, cb = 0;;) {
-        while (n >= N) { n -= N; ++cb; }
-        if (cb >= n_cb) break;
+    for (int t = threadIdx.x; t < n_cb * N * 8; t += blockDim.x) {
+        const int j0 = (t & 7) * 8, n = (t >> 3) % N, cb = (t >> 3) / N;
         const int d0 = cb * 64 + j0;
         float v[8];
         if (d0 < D) {
@@ -256,27 +252,26 @@ polar_prep_student_vec_kernel(PolarArgs g) {
             for (int e = 0; e < 8; ++e) v[e] = 0.f;
         }
         store_split8(swh, swl, (static_cast<size_t>(cb) * N + n) * 64 + j0, v);
-        n += oct_step;
     }
     if (g.vt) return;
     // W_0 = s_w^T [Ds][N], tiled [n block][d][64], padding columns zero: a thread takes 8 consecutive n of one d; lanes run
-    // along d (conflict-free 2-byte shared reads; the 16-byte stores of a warp land 128 B apart and are merged in L2);
-    // a warp owns an octet of n (its sqrt(a) values stay in registers) and walks d
+    // along d (conflict-free 2-byte shared reads; the 16-byte stores of a warp land 128 B apart and are merged in L2).
+    // (Walking (row, block) incrementally instead of dividing the flat index - a warp per octet of n here, running indices in the
+    // loop above and in prep_teacher - was measured: 0.31 -> 0.30 ms at cfg2, 1.25 -> 1.67 ms at cfg5, where the tile is read
+    // from global memory and the flat order keeps neighbouring warps on the same lines; taken out.)
     __nv_bfloat16* wh = g.W.hi + prob * g.W.batch_stride;
     __nv_bfloat16* wl = g.W.lo + prob * g.W.batch_stride;
     const int n_nb = (N + 63) / 64;
-    for (int c = warp; c < n_nb * 8; c += nw) {
-        const int nb = c >> 3, n0 = nb * 64 + (c & 7) * 8;
-        float qn[8];
+    for (int t = threadIdx.x; t < n_nb * 8 * D; t += blockDim.x) {
+        const int d = t % D, j0 = ((t / D) & 7) * 8, nb = t / (8 * D);
+        const float md = mu[d];
+        float v[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) qn[e] = n0 + e < N ? q_s[n0 + e] : 0.f;
-        for (int d = lane; d < D; d += 32) {
-            const float md = mu[d];
-            float v[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = n0 + e < N ? qn[e] * (__bfloat162float(raw[(n0 + e) * pitch + d]) - md) : 0.f;
-            store_split8(wh, wl, (static_cast<size_t>(nb) * D + d) * 64 + (c & 7) * 8, v);
+        for (int e = 0; e < 8; ++e) {
+            const int n = nb * 64 + j0 + e;
+            v[e] = n < N ? q_s[n] * (__bfloat162float(raw[n * pitch + d]) - md) : 0.f;
         }
+        store_split8(wh, wl, (static_cast<size_t>(nb) * D + d) * 64 + j0, v);
     }
 }
 
@@ -325,12 +320,8 @@ polar_prep_teacher_kernel(PolarArgs g) {
     // N is a multiple of 4, one 16-byte store per half); the second read of Ktt comes from L2
     const int n_cb = (N + 63) / 64;
     const bool vec_ok = (N & 3) == 0;
-    // (row, column block) walked incrementally (no runtime divisions).  More loads in flight per thread (four rows per warp in the
-    // pass above, two octets here) cost registers: 48 instead of 32, five CTAs per SM instead of eight and a second wave of CTAs.
-    const int j0 = (threadIdx.x & 7) * 8, oct_step = blockDim.x >> 3;
-    for (int n = threadIdx.x >> 3, cb = 0;; n += oct_step) {
-        while (n >= N) { n -= N; ++cb; }
-        if (cb >= n_cb) break;
+    for (int t = threadIdx.x; t < n_cb * N * 8; t += blockDim.x) {
+        const int j0 = (t & 7) * 8, n = (t >> 3) % N, cb = (t >> 3) / N;
         const int m0 = cb * 64 + j0;
         float v[8];
         const float* row = Ktt + static_cast<size_t>(n) * N;
