@@ -227,6 +227,31 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+_ORIGINAL_AFFINITY = None
+
+
+def bind_to_gpu_numa_node(index):
+    """One process per GPU: run on the CPUs next to that GPU (NVML's ideal affinity), so the pinned host buffers of the end-to-end
+    leg are first touched on the GPU's own NUMA node and eight ranks do not share one socket's memory controllers.  Returns the
+    number of CPUs the process is bound to (None when NVML or the call is unavailable - the bench runs unbound then)."""
+    global _ORIGINAL_AFFINITY
+    try:
+        import pynvml
+        _ORIGINAL_AFFINITY = os.sched_getaffinity(0)
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(index).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        n = len(os.sched_getaffinity(0))
+        torch.set_num_threads(max(1, min(torch.get_num_threads(), n)))
+        return n
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -255,6 +280,7 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback for the product path)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    cpu_affinity = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -467,6 +493,8 @@ def main():
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
+        if _ORIGINAL_AFFINITY is not None:           # the CPU baseline uses every host core, not just the GPU's NUMA node
+            os.sched_setaffinity(0, _ORIGINAL_AFFINITY)
         torch.set_num_threads(os.cpu_count() or 1)
         cpu_b = min(args.cpu_sample_batch, w.B)
         stepfn, kind, desc = cpu_reference_step_fn(w, cpu_b)
@@ -481,7 +509,7 @@ def main():
                        "parallelism": f"dp{world} (batch-sharded, pooled statistics all-reduced)",
                        "arithmetic": "bf16 tokens, fp32 accumulation, split-bf16 (hi+lo) tensor-core products, fp32 Jacobi",
                        "l2": f"inputs ({(w.Lt * w.B * w.Nt * w.Dt + w.P * w.B * w.Ns * w.Ds) * 2 / 1e9:.1f} GB of tokens per step) exceed the 126 MB L2; no explicit flush"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "loss": loss_val}
+            "clocks": clocks, "e2e": e2e, "cpu_affinity": cpu_affinity, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "loss": loss_val}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
