@@ -642,7 +642,9 @@ size_t pooled_eig_scratch_floats(int n, int problems) { return spectral_large(n)
 // cluster stays: picking the size from a waves x pair-step-time model chose a larger one there and measured 10.0 ms against
 // 9.4 ms (r2w); 320- / 384-thread CTAs (clusters of 5 / 4, all 28 problems in ONE wave; the 12-chunk columns then live in 168
 // registers with 44 bytes of spills) measured 9.26 against 9.39 ms (r3b) - at n = 384 the pair-step is bound by the instructions
-// an SM issues, not by the chain, so fewer SMs per problem give back what the second wave cost; not kept.
+// an SM issues, not by the chain, so fewer SMs per problem give back what the second wave cost; not kept.  Splitting the launch
+// (24 problems on 6-CTA clusters, then the last 4 on 8-CTA clusters) measured 10.2 ms (r3c): in ONE launch the remaining clusters
+// start as soon as any problem converges, the split makes them wait for the slowest of the first 24.
 static int pooled_pick_cluster(const void* kern, int n, int problems, size_t smem_fixed, size_t smem_per_group_floats) {
     static const int forced = [] {            // BASD_EIG_CLUSTER: development knob (1..8 CTAs per problem), read once
         const char* env = getenv("BASD_EIG_CLUSTER");
